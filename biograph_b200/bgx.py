@@ -1,0 +1,269 @@
+"""ctypes binding of include/bgx.h (the C ABI of libbgx.so).
+
+Mirrors the reference's stage interfaces for this path: add reads ->
+count k-mers -> correct -> build seqset -> export tables.  Everything computes on the GPU; the
+library refuses to create a context without a CUDA device."""
+import ctypes as C
+import json
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB = None
+
+
+class BgxError(RuntimeError):
+    pass
+
+
+class Options(C.Structure):
+    _fields_ = [("kmer_size", C.c_int32), ("min_kmer_count", C.c_int32), ("max_corrections", C.c_int32),
+                ("min_good_run", C.c_int32), ("trim_after_portion", C.c_float), ("device", C.c_int32),
+                ("sort_key_bits", C.c_int32), ("reserved", C.c_int32)]
+
+
+def lib_path():
+    return os.path.join(_HERE, "libbgx.so")
+
+
+def build_library(force=False):
+    """Compile libbgx.so in-tree with nvcc for sm_100a (cross-compiles without a GPU)."""
+    args = ["make", "-C", os.path.join(_HERE, "csrc"), "-s", "-j8"]
+    if force:
+        subprocess.check_call(args + ["clean"])
+    subprocess.check_call(args)
+    return lib_path()
+
+
+EXPORTS = ["bgx_default_options", "bgx_last_error", "bgx_version", "bgx_device_count", "bgx_create", "bgx_destroy",
+           "bgx_free", "bgx_add_reads_ascii", "bgx_add_reads_packed", "bgx_count_kmers", "bgx_export_kmers",
+           "bgx_correct", "bgx_export_corrected", "bgx_build_seqset", "bgx_export_seqset",
+           "bgx_export_entries_ascii", "bgx_run", "bgx_reset_results", "bgx_clear_reads", "bgx_stats_json"]
+
+
+def load_library():
+    global _LIB
+    if _LIB is not None:
+        return _LIB
+    path = lib_path()
+    if not os.path.exists(path):
+        raise BgxError(f"{path} is missing: run `python -c 'import __graft_entry__ as g; g.build()'` "
+                       "(there is no CPU fallback)")
+    L = C.CDLL(path)
+    vp, u64p = C.c_void_p, C.POINTER(C.c_uint64)
+    L.bgx_last_error.restype = C.c_char_p
+    L.bgx_version.restype = C.c_char_p
+    L.bgx_default_options.argtypes = [C.POINTER(Options)]
+    L.bgx_create.argtypes = [C.POINTER(Options), C.POINTER(vp)]
+    L.bgx_destroy.argtypes = [vp]
+    L.bgx_free.argtypes = [vp]
+    L.bgx_add_reads_ascii.argtypes = [vp, vp, vp, C.c_uint64]
+    L.bgx_add_reads_packed.argtypes = [vp, vp, vp, vp, vp, C.c_uint64]
+    L.bgx_count_kmers.argtypes = [vp]
+    L.bgx_export_kmers.argtypes = [vp, C.c_uint32, u64p, C.POINTER(vp), C.POINTER(vp), C.POINTER(vp), C.POINTER(vp)]
+    L.bgx_correct.argtypes = [vp]
+    L.bgx_export_corrected.argtypes = [vp, u64p, C.POINTER(vp), C.POINTER(vp), u64p, C.POINTER(vp), C.POINTER(vp),
+                                       C.POINTER(vp)]
+    L.bgx_build_seqset.argtypes = [vp]
+    L.bgx_export_seqset.argtypes = [vp, u64p, C.POINTER(C.c_uint32), C.POINTER(vp), C.POINTER(vp), vp * 4, vp * 4,
+                                    vp * 4, C.c_uint64 * 5]
+    L.bgx_export_entries_ascii.argtypes = [vp, C.c_uint64, C.c_uint64, C.POINTER(vp), C.POINTER(vp)]
+    L.bgx_run.argtypes = [vp]
+    L.bgx_reset_results.argtypes = [vp]
+    L.bgx_clear_reads.argtypes = [vp]
+    L.bgx_stats_json.argtypes = [vp, C.c_char_p, C.c_size_t]
+    _LIB = L
+    return L
+
+
+def pack_reads_2bit(reads):
+    """Host-side packing into the bgx_add_reads_packed layout (dna_sequence byte order, every read
+    on an 8-byte boundary) + N mask.  reads: list of str/bytes or (buffer, offsets) pair.
+    Returns (packed uint8[8*W], nmask uint32[W] or None, word_offs uint64[n+1], lens uint16[n])."""
+    if isinstance(reads, tuple):
+        buf, offs = reads
+        offs = np.asarray(offs, dtype=np.int64)
+        arr = np.frombuffer(buf, dtype=np.uint8)
+    else:
+        bs = [r.encode() if isinstance(r, str) else bytes(r) for r in reads]
+        offs = np.zeros(len(bs) + 1, dtype=np.int64)
+        if bs:
+            np.cumsum([len(b) for b in bs], out=offs[1:])
+        arr = np.frombuffer(b"".join(bs), dtype=np.uint8)
+    n = len(offs) - 1
+    lens = np.diff(offs).astype(np.int64)
+    nwords = (lens + 31) // 32
+    word_offs = np.zeros(n + 1, dtype=np.uint64)
+    np.cumsum(nwords, out=word_offs[1:])
+    W = int(word_offs[n])
+    code = np.zeros(256, dtype=np.uint8)
+    isn = np.ones(256, dtype=bool)
+    for i, ch in enumerate(b"ACGT"):
+        code[ch] = i
+        code[ch + 32] = i
+        isn[ch] = isn[ch + 32] = False
+    # position of every base in the padded (32 bases per word) layout
+    read_of = np.repeat(np.arange(n), lens)
+    within = np.arange(len(arr)) - np.repeat(offs[:-1], lens) if len(arr) else np.zeros(0, dtype=np.int64)
+    dst = (word_offs[:-1].astype(np.int64)[read_of] * 32 + within) if len(arr) else np.zeros(0, dtype=np.int64)
+    codes = np.zeros(W * 32, dtype=np.uint8)
+    codes[dst] = code[arr]
+    nflag = np.zeros(W * 32, dtype=bool)
+    nflag[dst] = isn[arr]
+    c4 = codes.reshape(-1, 4)
+    packed = ((c4[:, 0] << 6) | (c4[:, 1] << 4) | (c4[:, 2] << 2) | c4[:, 3]).astype(np.uint8)
+    nmask = None
+    if nflag.any():
+        bits = np.packbits(nflag.reshape(-1, 32), axis=1, bitorder="big")  # bit 31 = first base
+        nmask = (bits[:, 0].astype(np.uint32) << 24) | (bits[:, 1].astype(np.uint32) << 16) | \
+                (bits[:, 2].astype(np.uint32) << 8) | bits[:, 3].astype(np.uint32)
+        nmask = np.ascontiguousarray(nmask, dtype=np.uint32)
+    return np.ascontiguousarray(packed), nmask, word_offs, lens.astype(np.uint16)
+
+
+class Bgx:
+    """One seqset build on one GPU.  Method names follow the reference stages they replace."""
+
+    def __init__(self, kmer_size=30, min_kmer_count=5, max_corrections=8, min_good_run=2, trim_after_portion=0.7,
+                 device=0, sort_key_bits=48):
+        self.L = load_library()
+        o = Options()
+        self.L.bgx_default_options(C.byref(o))
+        o.kmer_size, o.min_kmer_count, o.max_corrections = kmer_size, min_kmer_count, max_corrections
+        o.min_good_run, o.trim_after_portion, o.device, o.sort_key_bits = min_good_run, trim_after_portion, device, \
+            sort_key_bits
+        self.h = C.c_void_p()
+        if self.L.bgx_create(C.byref(o), C.byref(self.h)):
+            raise BgxError(self.L.bgx_last_error().decode())
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.L.bgx_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+    def _ck(self, rc):
+        if rc:
+            raise BgxError(self.L.bgx_last_error().decode())
+
+    def _take(self, ptr, n, dtype):
+        n = int(n)
+        if n:
+            a = np.frombuffer((C.c_char * (n * np.dtype(dtype).itemsize)).from_address(ptr.value), dtype=dtype).copy()
+        else:
+            a = np.zeros(0, dtype=dtype)
+        self.L.bgx_free(ptr)
+        return a
+
+    # -- prob_pass_processor::add ------------------------------------------------------------
+    def add_reads(self, reads):
+        """reads: list of str/bytes, or (bytes buffer, offsets int64[n+1])"""
+        if isinstance(reads, tuple):
+            buf, offs = reads
+        else:
+            bs = [r.encode() if isinstance(r, str) else bytes(r) for r in reads]
+            offs = np.zeros(len(bs) + 1, dtype=np.uint64)
+            if bs:
+                np.cumsum([len(b) for b in bs], out=offs[1:])
+            buf = b"".join(bs)
+        offs = np.ascontiguousarray(offs, dtype=np.uint64)
+        if isinstance(buf, np.ndarray):
+            p = buf.ctypes.data
+        else:
+            self._keep = C.create_string_buffer(buf, len(buf)) if len(buf) else C.create_string_buffer(1)
+            p = C.addressof(self._keep)
+        self._ck(self.L.bgx_add_reads_ascii(self.h, p, offs.ctypes.data, len(offs) - 1))
+
+    def add_reads_packed(self, packed, nmask, word_offs, lens):
+        self._ck(self.L.bgx_add_reads_packed(self.h, packed.ctypes.data, None if nmask is None else nmask.ctypes.data,
+                                             word_offs.ctypes.data, lens.ctypes.data, len(lens)))
+
+    def add_reads_packed_ptr(self, packed_ptr, nmask_ptr, word_offs_ptr, lens_ptr, n):
+        self._ck(self.L.bgx_add_reads_packed(self.h, packed_ptr, nmask_ptr, word_offs_ptr, lens_ptr, n))
+
+    # -- kmer_counter / run_kmerize_subtask ----------------------------------------------------
+    def count_kmers(self):
+        self._ck(self.L.bgx_count_kmers(self.h))
+
+    def export_kmers(self, min_count=1):
+        n = C.c_uint64()
+        pk, pf, pr, pfl = C.c_void_p(), C.c_void_p(), C.c_void_p(), C.c_void_p()
+        self._ck(self.L.bgx_export_kmers(self.h, min_count, C.byref(n), C.byref(pk), C.byref(pf), C.byref(pr),
+                                         C.byref(pfl)))
+        return {"kmers": self._take(pk, n.value, np.uint64), "fwd": self._take(pf, n.value, np.uint32),
+                "rev": self._take(pr, n.value, np.uint32), "flags": self._take(pfl, n.value, np.uint8)}
+
+    # -- correct_reads::correct ------------------------------------------------------------------
+    def correct(self):
+        self._ck(self.L.bgx_correct(self.h))
+
+    def export_corrected(self):
+        n, nb = C.c_uint64(), C.c_uint64()
+        pl, pb, pc, pf, pr = (C.c_void_p() for _ in range(5))
+        self._ck(self.L.bgx_export_corrected(self.h, C.byref(n), C.byref(pl), C.byref(pb), C.byref(nb), C.byref(pc),
+                                             C.byref(pf), C.byref(pr)))
+        lens = self._take(pl, n.value, np.uint16)
+        seq = self._take(pb, nb.value, np.uint8).tobytes()
+        offs = np.zeros(n.value + 1, dtype=np.int64)
+        np.cumsum(lens, out=offs[1:])
+        return {"seq": seq, "offs": offs, "kept": (lens > 0).astype(np.uint8), "lens": lens,
+                "corrections": self._take(pc, n.value, np.uint8).astype(np.int32),
+                "next_fwd": self._take(pf, n.value, np.uint16).astype(np.int32),
+                "next_rev": self._take(pr, n.value, np.uint16).astype(np.int32), "n_kept": int((lens > 0).sum())}
+
+    # -- expander + builder -----------------------------------------------------------------------
+    def build_seqset(self):
+        self._ck(self.L.bgx_build_seqset(self.h))
+
+    def run(self):
+        self._ck(self.L.bgx_run(self.h))
+
+    def export_seqset(self):
+        n, ml = C.c_uint64(), C.c_uint32()
+        ps, psh = C.c_void_p(), C.c_void_p()
+        pb, psub, pacc = (C.c_void_p * 4)(), (C.c_void_p * 4)(), (C.c_void_p * 4)()
+        fixed = (C.c_uint64 * 5)()
+        self._ck(self.L.bgx_export_seqset(self.h, C.byref(n), C.byref(ml), C.byref(ps), C.byref(psh), pb, psub, pacc,
+                                          fixed))
+        N = n.value
+        words, subw, accw = (N + 63) // 64, (N + 511) // 512, (N + 1 + 511) // 512
+        out = {"n": N, "max_entry_len": ml.value, "sizes": self._take(ps, N, np.uint16),
+               "shared": self._take(psh, N, np.uint16), "fixed": np.array(list(fixed), dtype=np.uint64)}
+        out["prev"] = np.stack([self._take(C.c_void_p(pb[b]), words, np.uint64) for b in range(4)]) if True else None
+        out["subaccum"] = [self._take(C.c_void_p(psub[b]), subw, np.uint64) for b in range(4)]
+        out["accum"] = [self._take(C.c_void_p(pacc[b]), accw, np.uint64) for b in range(4)]
+        return out
+
+    def export_entries(self, first=0, count=None):
+        if count is None:
+            count = self.stats().get("entries", 0) - first
+        count = int(count)
+        pb, po = C.c_void_p(), C.c_void_p()
+        self._ck(self.L.bgx_export_entries_ascii(self.h, first, count, C.byref(pb), C.byref(po)))
+        offs = self._take(po, count + 1, np.uint64)
+        seq = self._take(pb, int(offs[-1]) if count else 0, np.uint8).tobytes().decode()
+        return [seq[int(offs[i]):int(offs[i + 1])] for i in range(count)]
+
+    def reset_results(self):
+        self._ck(self.L.bgx_reset_results(self.h))
+
+    def clear_reads(self):
+        self._ck(self.L.bgx_clear_reads(self.h))
+
+    def stats(self):
+        buf = C.create_string_buffer(1 << 16)
+        self._ck(self.L.bgx_stats_json(self.h, buf, len(buf)))
+        return json.loads(buf.value.decode())

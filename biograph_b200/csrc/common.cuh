@@ -1,0 +1,108 @@
+// common.cuh -- shared device helpers for the bgx kernels (sm_100a).
+//
+// Data layout in HBM:
+//   base words : uint64, 32 bases per word, first base in the HIGH bits (so integer order ==
+//                lexicographic order A<C<G<T).  Every read starts on a word boundary; unused
+//                trailing bits are zero.  This is the reference's dna_sequence byte order
+//                (modules/bio_base/dna_sequence.h:95-99) read as big-endian 64-bit words.
+//   k-mer      : uint64, first base in the high bits of the low 2k bits (modules/bio_base/kmer.h:30-38).
+#pragma once
+
+#include <cuda_runtime.h>
+
+#include <cstdint>
+#include <stdexcept>
+#include <string>
+
+namespace bgx {
+
+struct Error : std::runtime_error {
+  using std::runtime_error::runtime_error;
+};
+
+#define BGX_CUDA(expr)                                                                       \
+  do {                                                                                       \
+    cudaError_t e__ = (expr);                                                                \
+    if (e__ != cudaSuccess)                                                                  \
+      throw ::bgx::Error(std::string(#expr) + " failed: " + cudaGetErrorString(e__));        \
+  } while (0)
+
+#define BGX_CHECK(cond, msg)                                 \
+  do {                                                       \
+    if (!(cond)) throw ::bgx::Error(std::string(msg));       \
+  } while (0)
+
+constexpr int kNumSMs = 148;  // B200
+
+constexpr uint64_t kEmptyKey = ~0ULL;                 // kmer_count_table::k_unused_entry
+constexpr uint64_t kKmerMask = (1ULL << 62) - 1;      // kmer_count_table::k_kmer_mask
+constexpr uint64_t kFwdFlag = 1ULL << 63;             // k_fwd_flag  (fwd_starts_read)
+constexpr uint64_t kRevFlag = 1ULL << 62;             // k_rev_flag  (rev_starts_read)
+
+// suffix locator: base address in the corrected-base store << 16 | length
+constexpr int kLocLenBits = 16;
+__host__ __device__ __forceinline__ uint64_t make_loc(uint64_t addr, uint32_t len) { return (addr << kLocLenBits) | len; }
+__host__ __device__ __forceinline__ uint64_t loc_addr(uint64_t loc) { return loc >> kLocLenBits; }
+__host__ __device__ __forceinline__ uint32_t loc_len(uint64_t loc) { return (uint32_t)(loc & ((1u << kLocLenBits) - 1)); }
+
+// mask keeping the top nb bases of a word (nb in [0,32])
+__host__ __device__ __forceinline__ uint64_t top_bases_mask(int nb) {
+  return nb >= 32 ? ~0ULL : ~(~0ULL >> (2 * nb));
+}
+
+__host__ __device__ __forceinline__ uint64_t kmer_low_mask(int k) { return k >= 32 ? ~0ULL : ((1ULL << (2 * k)) - 1); }
+
+#ifdef __CUDACC__
+
+// 32 bases starting at base address a (the array must have one readable pad word at the end).
+__device__ __forceinline__ uint64_t load_window(const uint64_t* __restrict__ w, uint64_t a) {
+  uint64_t q = a >> 5;
+  unsigned s = (unsigned)(a & 31) * 2;
+  uint64_t hi = w[q];
+  if (s == 0) return hi;
+  uint64_t lo = w[q + 1];
+  return (hi << s) | (lo >> (64 - s));
+}
+
+// first min(len,32) bases of the suffix at addr, zero padded: the radix key of a suffix
+__device__ __forceinline__ uint64_t suffix_key(const uint64_t* __restrict__ w, uint64_t addr, int len) {
+  return load_window(w, addr) & top_bases_mask(len);
+}
+
+// modules/bio_base/dna_sequence.cpp:330-351: reverse complement of a k-mer held in the low 2k bits
+__device__ __forceinline__ uint64_t revcomp_kmer(uint64_t x, int k) {
+  x = __brevll(~x);
+  x = ((x >> 1) & 0x5555555555555555ULL) | ((x & 0x5555555555555555ULL) << 1);
+  return x >> (64 - 2 * k);
+}
+
+// modules/bio_base/dna_sequence.cpp:378-385
+__device__ __forceinline__ uint64_t canonicalize(uint64_t kmer, int k, bool& flipped) {
+  uint64_t rc = revcomp_kmer(kmer, k);
+  flipped = rc < kmer;
+  return flipped ? rc : kmer;
+}
+
+__device__ __forceinline__ uint64_t mix64(uint64_t x) {
+  x ^= x >> 33;
+  x *= 0xff51afd7ed558ccdULL;
+  x ^= x >> 33;
+  x *= 0xc4ceb9fe1a85ec53ULL;
+  x ^= x >> 33;
+  return x;
+}
+
+__device__ __forceinline__ unsigned lane_id() { return threadIdx.x & 31; }
+
+// streaming 128-bit loads/stores that do not pollute L1
+__device__ __forceinline__ uint4 ld_stream_u4(const uint4* p) {
+  uint4 r;
+  asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];"
+               : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w)
+               : "l"(p));
+  return r;
+}
+
+#endif  // __CUDACC__
+
+}  // namespace bgx

@@ -1,0 +1,115 @@
+// ctx.h -- the bgx context: device-resident state of one seqset build on one GPU.
+#pragma once
+
+#include <map>
+#include <string>
+#include <vector>
+
+#include "../../include/bgx.h"
+#include "prims.cuh"
+
+namespace bgx {
+
+struct CountEntry {            // 16 B, one per slot: key+flags and both counters share a DRAM sector
+  unsigned long long key;      // canonical k-mer | kFwdFlag | kRevFlag ; kEmptyKey when unused
+  unsigned long long cnt;      // rev_count << 32 | fwd_count
+};
+
+struct StageTimer {
+  cudaEvent_t a = nullptr, b = nullptr;
+};
+
+struct Context {
+  bgx_options opt{};
+  int device = 0;
+  cudaStream_t stream = nullptr;
+  cudaMemPool_t pool = nullptr;
+
+  // ---- reads (device resident) ---------------------------------------------------------
+  uint64_t n_reads = 0;
+  uint64_t n_words = 0;          // total 64-bit base words (32 bases each)
+  uint64_t n_bases = 0;          // sum of read lengths
+  uint64_t n_kmer_instances = 0; // sum max(0, len-k+1)
+  bool has_n = false;
+  uint32_t max_len = 0;
+  DevBuf<uint64_t> words;        // n_words + 1 (pad)
+  DevBuf<uint32_t> nmask;        // n_words + 1, only if has_n
+  DevBuf<uint32_t> word_off;     // n_reads + 1
+  DevBuf<uint16_t> lens;         // n_reads
+  size_t cap_words = 0, cap_reads = 0;
+
+  // ---- k-mer stage -----------------------------------------------------------------------
+  bool counted = false;
+  DevBuf<CountEntry> table;      // open addressing, power-of-two slots
+  uint64_t table_slots = 0;
+  uint64_t n_distinct = 0, n_solid = 0;
+  DevBuf<unsigned long long> solid;  // hash set of solid k-mers (key|flags), power-of-two slots
+  uint64_t solid_slots = 0;
+
+  // ---- correction stage --------------------------------------------------------------------
+  bool corrected = false;
+  DevBuf<uint64_t> store;        // corrected base store: [fwd reads | rc reads] 2*n_words + 1 words
+  DevBuf<uint16_t> clen;         // corrected length per read (0 = dropped)
+  DevBuf<uint8_t> ncorr;         // substitutions per read
+  DevBuf<uint16_t> next_fwd, next_rev;
+  uint64_t n_kept = 0, kept_bases = 0, n_seeds = 0;
+
+  // ---- seqset stage ------------------------------------------------------------------------
+  bool built = false;
+  uint64_t n_entries = 0;
+  uint32_t max_entry_len = 0;
+  DevBuf<uint64_t> ent_key, ent_loc;   // final sorted entries
+  DevBuf<uint16_t> sizes, shared;
+  DevBuf<uint64_t> prev_bits;          // 4 * prev_words
+  DevBuf<uint64_t> prev_sub, prev_acc; // 4 * sub_words, 4 * acc_words
+  uint64_t prev_words = 0, sub_words = 0, acc_words = 0;
+  uint64_t fixed[5] = {0, 0, 0, 0, 0};
+
+  // ---- stats ---------------------------------------------------------------------------------
+  std::map<std::string, double> stats;       // numeric stats (ms, counts, bytes)
+  std::vector<std::string> stat_order;
+  void set_stat(const std::string& k, double v) {
+    if (!stats.count(k)) stat_order.push_back(k);
+    stats[k] = v;
+  }
+  void add_stat(const std::string& k, double v) {
+    if (!stats.count(k)) { stat_order.push_back(k); stats[k] = 0; }
+    stats[k] += v;
+  }
+};
+
+// RAII CUDA-event stage timer: records on construction, on stop() synchronises and stores ms.
+struct ScopedStage {
+  Context* c;
+  std::string name;
+  cudaEvent_t a, b;
+  bool done = false;
+  ScopedStage(Context* c_, const std::string& n) : c(c_), name(n) {
+    cudaEventCreate(&a); cudaEventCreate(&b);
+    cudaEventRecord(a, c->stream);
+  }
+  double stop() {
+    if (done) return 0;
+    done = true;
+    cudaEventRecord(b, c->stream);
+    cudaEventSynchronize(b);
+    float ms = 0;
+    cudaEventElapsedTime(&ms, a, b);
+    c->add_stat("ms_" + name, ms);
+    cudaEventDestroy(a); cudaEventDestroy(b);
+    return ms;
+  }
+  ~ScopedStage() { if (!done) { cudaEventDestroy(a); cudaEventDestroy(b); } }
+};
+
+// stage entry points (each in its own .cu)
+void reads_append_ascii(Context* c, const char* bases, const uint64_t* offs, uint64_t n);
+void reads_append_packed(Context* c, const uint8_t* packed, const uint32_t* n_mask, const uint64_t* word_offs,
+                         const uint16_t* lens, uint64_t n);
+void stage_count_kmers(Context* c);
+void export_kmers(Context* c, uint32_t min_count, uint64_t* n, uint64_t** kmers, uint32_t** fwd, uint32_t** rev,
+                  uint8_t** flags);
+void stage_correct(Context* c);
+void stage_build_seqset(Context* c);
+
+}  // namespace bgx

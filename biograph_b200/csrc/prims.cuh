@@ -1,0 +1,58 @@
+// prims.cuh -- device-wide primitives written for this path (no CUB/Thrust): exclusive scan
+// and the LSD radix sort of (uint64 key, uint64 value) pairs used for suffix records and k-mers.
+#pragma once
+
+#include <cstddef>
+#include <cstdint>
+
+#include "common.cuh"
+
+namespace bgx {
+
+// Stream-ordered device allocation (cudaMallocAsync on the context's pool).
+void* dev_alloc(size_t bytes, cudaStream_t s);
+void dev_free(void* p, cudaStream_t s);
+
+template <typename T>
+struct DevBuf {
+  T* p = nullptr;
+  size_t n = 0;
+  cudaStream_t s = nullptr;
+  DevBuf() = default;
+  DevBuf(size_t n_, cudaStream_t s_) { alloc(n_, s_); }
+  DevBuf(const DevBuf&) = delete;
+  DevBuf& operator=(const DevBuf&) = delete;
+  DevBuf(DevBuf&& o) noexcept : p(o.p), n(o.n), s(o.s) { o.p = nullptr; o.n = 0; }
+  DevBuf& operator=(DevBuf&& o) noexcept {
+    if (this != &o) { release(); p = o.p; n = o.n; s = o.s; o.p = nullptr; o.n = 0; }
+    return *this;
+  }
+  ~DevBuf() { release(); }
+  void alloc(size_t n_, cudaStream_t s_) {
+    release();
+    s = s_; n = n_;
+    p = static_cast<T*>(dev_alloc((n_ ? n_ : 1) * sizeof(T), s_));
+  }
+  void release() {
+    if (p) dev_free(p, s);
+    p = nullptr; n = 0;
+  }
+  size_t bytes() const { return n * sizeof(T); }
+};
+
+// out[i] = sum(in[0..i)), in place allowed.  If total_out != nullptr the grand total is written
+// there (device pointer).
+void exclusive_scan_u32(const uint32_t* in, uint32_t* out, size_t n, uint32_t* total_out, cudaStream_t s);
+
+// Stable LSD radix sort of n (key, value) pairs on key bits [begin_bit, end_bit), 8 bits per
+// pass.  Ping-pongs between (keys, vals) and (keys_alt, vals_alt); returns true if the sorted
+// data ended up in the *_alt buffers.  n < 2^32.
+// passes_out (optional) receives the number of passes run.
+bool radix_sort_pairs(uint64_t* keys, uint64_t* vals, uint64_t* keys_alt, uint64_t* vals_alt, size_t n,
+                      int begin_bit, int end_bit, cudaStream_t s, int* passes_out = nullptr);
+
+// algorithmic HBM bytes of one radix pass over n pairs (read+write every 16-byte record;
+// SURVEY 8d "2*N*S") and the extra bytes this implementation moves (separate digit-count read).
+inline double radix_pass_alg_bytes(size_t n) { return 2.0 * 16.0 * (double)n; }
+
+}  // namespace bgx

@@ -1,0 +1,659 @@
+// seqset.cu -- suffix seeds -> sort -> prefix-dedup -> closure -> seqset tables, on the GPU.
+//
+// Replaces (reference, CPU + temp files): part_repo::write seeds (bs/part_repo.cpp:53-126),
+// expander::sort_and_dedup / expand (bs/expand.cpp:418-661, driver biograph_create.cpp:921-931),
+// builder::build_chunks / make_seqset (bs/builder.cpp:8-263), bitcount::finalize
+// (modules/io/bitcount.cpp:84-123) and seqset::finalize (modules/bio_base/seqset.cpp:113-129).
+//
+// A suffix record is 16 bytes held as two arrays: key = first 32 bases (MSB-first, zero padded,
+// so integer order == sequence order with a proper prefix first when lengths break ties) and
+// loc = (base address in the corrected store << 16) | length.  The store keeps every kept read
+// AND its reverse complement, so every suffix is a plain forward slice (no rc logic in any
+// comparison).
+//
+// Rounds (result-identical to the reference's seed / stride-7 / stride-1 scheme because the
+// final set is the closure):
+//   1. seeds: first next_fwd suffixes of each read, first next_rev of its reverse complement
+//   2. sort (LSD radix on the top key bits, then tie groups resolved by full comparison) + dedup
+//   3. closure walk: for every entry whose pop_front is not covered, emit pop_front and the
+//      following suffixes up to the first covered one (one round reaches the closure)
+//   4. sort + dedup of (round-2 survivors + walk output)
+//   5. tables: sizes, shared (LCP with predecessor), prev bits (lower_bound of pop_front),
+//      bitcount accum/subaccum, fixed.
+#include <algorithm>
+#include <vector>
+
+#include "ctx.h"
+
+namespace bgx {
+namespace {
+
+constexpr int kSmallGroup = 32;   // tie groups up to this size are sorted by one thread
+constexpr int kChunkBases = 12;   // bases resolved per refinement round for big tie groups
+
+// ---- comparisons ----------------------------------------------------------------------------
+// compare suffixes la, lb from base depth d on (all bases before d known equal).
+// <0, 0, >0 ; a proper prefix sorts first (bs/repo_seq.cpp:660-684, dna_sequence.cpp:528-566).
+__device__ __forceinline__ int compare_from(const uint64_t* __restrict__ store, uint64_t la, uint64_t lb, int d,
+                                            int* lcp) {
+  const uint64_t aa = loc_addr(la), ab = loc_addr(lb);
+  const int na = (int)loc_len(la), nb = (int)loc_len(lb);
+  const int m = min(na, nb);
+  while (d < m) {
+    int c = min(32, m - d);
+    uint64_t msk = top_bases_mask(c);
+    uint64_t wa = load_window(store, aa + d) & msk;
+    uint64_t wb = load_window(store, ab + d) & msk;
+    if (wa != wb) {
+      if (lcp) *lcp = d + (__clzll(wa ^ wb) >> 1);
+      return wa < wb ? -1 : 1;
+    }
+    d += c;
+  }
+  if (lcp) *lcp = m;
+  return na - nb;
+}
+
+__device__ __forceinline__ bool rec_less(const uint64_t* __restrict__ store, uint64_t ka, uint64_t la, uint64_t kb,
+                                         uint64_t lb) {
+  if (ka != kb) return ka < kb;
+  int na = (int)loc_len(la), nb = (int)loc_len(lb);
+  if (na <= 32 || nb <= 32) return na < nb;  // equal padded keys: the shorter one is a prefix
+  return compare_from(store, la, lb, 32, nullptr) < 0;
+}
+
+// a prefix of / equal to b ?
+__device__ __forceinline__ bool prefix_or_equal(const uint64_t* __restrict__ store, uint64_t ka, uint64_t la,
+                                                uint64_t kb, uint64_t lb) {
+  int na = (int)loc_len(la), nb = (int)loc_len(lb);
+  if (na > nb) return false;
+  if ((ka ^ kb) & top_bases_mask(min(na, 32))) return false;
+  if (na <= 32) return true;
+  int lcp;
+  compare_from(store, la, lb, 32, &lcp);
+  return lcp >= na;
+}
+
+// first index in [0,n) whose record is not less than x
+__device__ __forceinline__ uint32_t lower_bound_rec(const uint64_t* __restrict__ store,
+                                                    const uint64_t* __restrict__ keys,
+                                                    const uint64_t* __restrict__ locs, uint32_t n, uint64_t xk,
+                                                    uint64_t xl) {
+  uint32_t lo = 0, hi = n;
+  while (lo < hi) {
+    uint32_t mid = lo + ((hi - lo) >> 1);
+    if (rec_less(store, keys[mid], locs[mid], xk, xl)) lo = mid + 1; else hi = mid;
+  }
+  return lo;
+}
+
+// ---- seeds ------------------------------------------------------------------------------------
+__global__ void seed_count_kernel(const uint16_t* __restrict__ clen, const uint16_t* __restrict__ nf,
+                                  const uint16_t* __restrict__ nr, uint32_t n_reads, uint32_t* __restrict__ cnt) {
+  uint32_t r = blockIdx.x * blockDim.x + threadIdx.x;
+  if (r < n_reads) cnt[r] = clen[r] ? (uint32_t)nf[r] + nr[r] : 0u;
+}
+
+__global__ void seed_emit_kernel(const uint64_t* __restrict__ store, uint64_t rc_word_base,
+                                 const uint32_t* __restrict__ word_off, const uint16_t* __restrict__ clen,
+                                 const uint16_t* __restrict__ nf, const uint16_t* __restrict__ nr,
+                                 const uint32_t* __restrict__ seed_off, uint32_t n_reads, uint64_t* __restrict__ keys,
+                                 uint64_t* __restrict__ locs) {
+  uint32_t r = blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= n_reads) return;
+  int L = clen[r];
+  if (!L) return;
+  uint32_t o = seed_off[r];
+  uint64_t fa = (uint64_t)word_off[r] * 32, ra = (rc_word_base + word_off[r]) * 32;
+  int f = nf[r], v = nr[r];
+  for (int i = 0; i < f; ++i, ++o) {
+    keys[o] = suffix_key(store, fa + i, L - i);
+    locs[o] = make_loc(fa + i, L - i);
+  }
+  for (int i = 0; i < v; ++i, ++o) {
+    keys[o] = suffix_key(store, ra + i, L - i);
+    locs[o] = make_loc(ra + i, L - i);
+  }
+}
+
+// ---- tie groups after the radix sort on the top `sbits` bits -------------------------------------
+// One thread per record.  Every record measures its run of equal top bits (at most small_limit+1
+// to either side), so no thread ever walks a long run: members of runs longer than small_limit
+// flag themselves for the refinement path; the leader of a shorter run insertion-sorts it in
+// place with the full comparator.
+__global__ void __launch_bounds__(128) tie_small_kernel(const uint64_t* __restrict__ store,
+                                                        uint64_t* __restrict__ keys, uint64_t* __restrict__ locs,
+                                                        uint32_t n, int sbits, int small_limit,
+                                                        uint32_t* __restrict__ big_flag,
+                                                        unsigned long long* __restrict__ n_big) {
+  uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  const int sh = 64 - sbits;  // sbits in [8,64]
+  bool big = false;
+  uint32_t left = 0, right = 0;
+  if (i < n) {
+    uint64_t top = keys[i] >> sh;
+    while (left <= (uint32_t)small_limit && i > left && (keys[i - left - 1] >> sh) == top) ++left;
+    while (right <= (uint32_t)small_limit && i + right + 1 < n && (keys[i + right + 1] >> sh) == top) ++right;
+    big = left + right + 1 > (uint32_t)small_limit;
+    if (big) big_flag[i] = 1;
+  }
+  unsigned bm = __ballot_sync(0xffffffffu, big);
+  if (lane_id() == 0 && bm) atomicAdd(n_big, (unsigned long long)__popc(bm));
+  if (i >= n || big || left != 0 || right == 0) return;
+  const uint32_t g = right + 1;
+  for (uint32_t a = 1; a < g; ++a) {
+    uint64_t k = keys[i + a], l = locs[i + a];
+    int j = (int)a - 1;
+    while (j >= 0 && rec_less(store, k, l, keys[i + j], locs[i + j])) {
+      keys[i + j + 1] = keys[i + j];
+      locs[i + j + 1] = locs[i + j];
+      --j;
+    }
+    keys[i + j + 1] = k;
+    locs[i + j + 1] = l;
+  }
+}
+
+// ---- refinement of big tie groups -------------------------------------------------------------------
+// members are listed by ascending position (midx) with a non-decreasing dense group id (mgid).
+// compound key = gid << 33 | chunk(12 bases at depth D) << 9 | min(len, D + 12)
+__global__ void refine_init_kernel(const uint32_t* __restrict__ big_flag, const uint32_t* __restrict__ big_pos,
+                                   const uint64_t* __restrict__ keys, uint32_t n, int sbits,
+                                   uint32_t* __restrict__ midx, uint32_t* __restrict__ head) {
+  uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n || !big_flag[i]) return;
+  uint32_t j = big_pos[i];
+  midx[j] = i;
+  const int sh = 64 - sbits;
+  bool is_head = (i == 0) || !big_flag[i - 1] || (keys[i - 1] >> sh) != (keys[i] >> sh);
+  head[j] = is_head ? 1u : 0u;
+}
+
+__global__ void refine_key_kernel(const uint64_t* __restrict__ store, const uint64_t* __restrict__ locs,
+                                  const uint32_t* __restrict__ midx, const uint32_t* __restrict__ gid_incl /*head scan*/,
+                                  const uint32_t* __restrict__ head, uint32_t m, int D, uint64_t* __restrict__ ckey,
+                                  uint64_t* __restrict__ cloc) {
+  uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= m) return;
+  uint64_t l = locs[midx[j]];
+  int len = (int)loc_len(l);
+  uint64_t gid = gid_incl[j] + head[j] - 1;  // exclusive scan + own head - 1 => dense id of this record's group
+  int rem = len - D;
+  uint64_t chunk = 0;
+  if (rem > 0) chunk = (load_window(store, loc_addr(l) + D) & top_bases_mask(min(rem, kChunkBases))) >> (64 - 2 * kChunkBases);
+  uint64_t lf = (uint64_t)min(len, D + kChunkBases);
+  ckey[j] = (gid << 33) | (chunk << 9) | lf;
+  cloc[j] = l;
+}
+
+// after sorting (ckey, cloc): write records back to their positions and find the members that are
+// still tied (equal compound key and both continue past D + chunk)
+__global__ void refine_writeback_kernel(const uint64_t* __restrict__ store, const uint64_t* __restrict__ ckey,
+                                        const uint64_t* __restrict__ cloc, const uint32_t* __restrict__ midx,
+                                        uint32_t m, int D, uint64_t* __restrict__ keys, uint64_t* __restrict__ locs,
+                                        uint32_t* __restrict__ tied, uint32_t* __restrict__ new_head) {
+  uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= m) return;
+  uint64_t l = cloc[j];
+  uint32_t pos = midx[j];
+  locs[pos] = l;
+  keys[pos] = suffix_key(store, loc_addr(l), (int)loc_len(l));
+  uint64_t ck = ckey[j];
+  bool cont = (int)(ck & 0x1ff) == D + kChunkBases && (int)loc_len(l) > D + kChunkBases;
+  bool same_prev = j > 0 && ckey[j - 1] == ck;
+  bool same_next = j + 1 < m && ckey[j + 1] == ck;
+  // records with equal compound keys that all end exactly at D+chunk are identical sequences;
+  // a record ending exactly at D+chunk sorts before longer ones with the same chunk only if the
+  // length field differs, which it does not -- so order them by full length in the next round too
+  bool t = (same_prev || same_next) && (cont || (int)(ck & 0x1ff) == D + kChunkBases);
+  tied[j] = t ? 1u : 0u;
+  new_head[j] = (t && !same_prev) ? 1u : 0u;
+}
+
+__global__ void refine_compact_kernel(const uint32_t* __restrict__ tied, const uint32_t* __restrict__ tied_pos,
+                                      const uint32_t* __restrict__ midx, const uint32_t* __restrict__ new_head,
+                                      uint32_t m, uint32_t* __restrict__ midx2, uint32_t* __restrict__ head2) {
+  uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= m || !tied[j]) return;
+  uint32_t o = tied_pos[j];
+  midx2[o] = midx[j];
+  head2[o] = new_head[j];
+}
+
+// ---- dedup ----------------------------------------------------------------------------------------
+__global__ void dedup_flag_kernel(const uint64_t* __restrict__ store, const uint64_t* __restrict__ keys,
+                                  const uint64_t* __restrict__ locs, uint32_t n, uint32_t* __restrict__ keep) {
+  uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  bool drop = (i + 1 < n) && prefix_or_equal(store, keys[i], locs[i], keys[i + 1], locs[i + 1]);
+  keep[i] = drop ? 0u : 1u;
+}
+
+__global__ void compact_pairs_kernel(const uint64_t* __restrict__ keys, const uint64_t* __restrict__ locs,
+                                     const uint32_t* __restrict__ keep, const uint32_t* __restrict__ pos, uint32_t n,
+                                     uint64_t* __restrict__ okeys, uint64_t* __restrict__ olocs) {
+  uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n || !keep[i]) return;
+  okeys[pos[i]] = keys[i];
+  olocs[pos[i]] = locs[i];
+}
+
+// ---- closure walk ------------------------------------------------------------------------------------
+__device__ __forceinline__ bool covered(const uint64_t* __restrict__ store, const uint64_t* __restrict__ keys,
+                                        const uint64_t* __restrict__ locs, uint32_t n, uint64_t addr, int len,
+                                        uint32_t* where) {
+  if (len == 0) { if (where) *where = 0; return true; }  // the empty sequence is a prefix of everything
+  uint64_t xk = suffix_key(store, addr, len), xl = make_loc(addr, len);
+  uint32_t lb = lower_bound_rec(store, keys, locs, n, xk, xl);
+  if (where) *where = lb;
+  return lb < n && prefix_or_equal(store, xk, xl, keys[lb], locs[lb]);
+}
+
+// phase 1: one thread per entry; entries whose pop_front is not covered start a chain
+__global__ void __launch_bounds__(128) walk_phase1_kernel(const uint64_t* __restrict__ store,
+                                                          const uint64_t* __restrict__ keys,
+                                                          const uint64_t* __restrict__ locs, uint32_t n,
+                                                          uint32_t* __restrict__ chains,
+                                                          unsigned long long* __restrict__ n_chains) {
+  uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  bool start = false;
+  if (i < n) {
+    uint64_t l = locs[i];
+    start = !covered(store, keys, locs, n, loc_addr(l) + 1, (int)loc_len(l) - 1, nullptr);
+  }
+  unsigned mask = __ballot_sync(0xffffffffu, start);
+  if (!mask) return;
+  unsigned lane = lane_id();
+  unsigned long long base = 0;
+  if (lane == 0) base = atomicAdd(n_chains, (unsigned long long)__popc(mask));
+  base = __shfl_sync(0xffffffffu, base, 0);
+  if (start) chains[base + __popc(mask & ((1u << lane) - 1))] = i;
+}
+
+// phase 2: one warp per chain; lanes test pops j = 1 + lane + 32*iter in parallel; chain_stop =
+// first covered j (or len).  Emits e[j:] for 1 <= j < chain_stop.
+__global__ void __launch_bounds__(128) walk_phase2_kernel(const uint64_t* __restrict__ store,
+                                                          const uint64_t* __restrict__ keys,
+                                                          const uint64_t* __restrict__ locs, uint32_t n,
+                                                          const uint32_t* __restrict__ chains, uint32_t n_chains,
+                                                          uint32_t* __restrict__ chain_stop) {
+  uint32_t c = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  if (c >= n_chains) return;
+  unsigned lane = lane_id();
+  uint64_t l = locs[chains[c]];
+  uint64_t addr = loc_addr(l);
+  int len = (int)loc_len(l);
+  int stop = len;
+  for (int j0 = 2; j0 < len; j0 += 32) {  // j = 1 is known uncovered
+    int j = j0 + (int)lane;
+    bool cov = j < len && covered(store, keys, locs, n, addr + j, len - j, nullptr);
+    unsigned mask = __ballot_sync(0xffffffffu, cov);
+    if (mask) { stop = j0 + __ffs(mask) - 1; break; }
+  }
+  if (lane == 0) chain_stop[c] = (uint32_t)(stop - 1);  // number of emitted suffixes
+}
+
+__global__ void walk_emit_kernel(const uint64_t* __restrict__ store, const uint64_t* __restrict__ locs,
+                                 const uint32_t* __restrict__ chains, const uint32_t* __restrict__ chain_cnt,
+                                 const uint32_t* __restrict__ chain_off, uint32_t n_chains, uint64_t* __restrict__ okeys,
+                                 uint64_t* __restrict__ olocs) {
+  uint32_t c = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  if (c >= n_chains) return;
+  unsigned lane = lane_id();
+  uint64_t l = locs[chains[c]];
+  uint64_t addr = loc_addr(l);
+  int len = (int)loc_len(l);
+  uint32_t cnt = chain_cnt[c], off = chain_off[c];
+  for (uint32_t t = lane; t < cnt; t += 32) {
+    int j = 1 + (int)t;
+    okeys[off + t] = suffix_key(store, addr + j, len - j);
+    olocs[off + t] = make_loc(addr + j, len - j);
+  }
+}
+
+// ---- tables ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128) tables_kernel(const uint64_t* __restrict__ store,
+                                                     const uint64_t* __restrict__ keys,
+                                                     const uint64_t* __restrict__ locs, uint32_t n,
+                                                     uint16_t* __restrict__ sizes, uint16_t* __restrict__ shared,
+                                                     unsigned long long* __restrict__ prev_bits, uint64_t prev_words,
+                                                     unsigned int* __restrict__ max_len, int* __restrict__ missing) {
+  uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  unsigned len = 0;
+  if (i < n) {
+    uint64_t k = keys[i], l = locs[i];
+    len = loc_len(l);
+    sizes[i] = (uint16_t)len;
+    // shared = LCP with the previous entry (bs/builder.cpp:72-80)
+    int lcp = 0;
+    if (i > 0) {
+      uint64_t pk = keys[i - 1], pl = locs[i - 1];
+      int m = min((int)len, (int)loc_len(pl));
+      uint64_t x = (k ^ pk) & top_bases_mask(min(m, 32));
+      if (x) lcp = __clzll(x) >> 1;
+      else if (m <= 32) lcp = m;
+      else compare_from(store, pl, l, 32, &lcp);
+    }
+    shared[i] = (uint16_t)lcp;
+    // prev bit: first entry having pop_front(e) as a prefix (bs/builder.cpp:85-107)
+    uint32_t where;
+    bool cov = covered(store, keys, locs, n, loc_addr(l) + 1, (int)len - 1, &where);
+    if (!cov) {
+      *missing = 1;  // LOG(FATAL) << "Missing expansion?" (bs/builder.cpp:96)
+    } else {
+      unsigned b = (unsigned)(k >> 62);
+      atomicOr(&prev_bits[(uint64_t)b * prev_words + (where >> 6)], 1ULL << (where & 63));
+    }
+  }
+  unsigned mx = __reduce_max_sync(0xffffffffu, len);
+  if (lane_id() == 0 && mx) atomicMax(max_len, mx);
+}
+
+// bitcount::finalize (modules/io/bitcount.cpp:84-123): per 512-bit group popcounts
+__global__ void bitcount_groups_kernel(const unsigned long long* __restrict__ bits, uint64_t words, uint64_t groups,
+                                       uint32_t* __restrict__ group_pop, unsigned long long* __restrict__ subaccum) {
+  uint64_t g = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (g >= groups) return;
+  unsigned long long sub = 0;
+  uint32_t tot = 0;
+  for (int j = 0; j < 8; ++j) {
+    uint64_t wi = g * 8 + j;
+    sub <<= 8;  // missing words of the last group keep shifting: left-justified (bitcount.cpp:108-113)
+    if (wi < words) {
+      unsigned c = __popcll(bits[wi]);
+      sub |= c;
+      tot += c;
+    }
+  }
+  group_pop[g] = tot;
+  subaccum[g] = sub;
+}
+
+__global__ void bitcount_accum_kernel(const uint32_t* __restrict__ group_excl, const uint32_t* __restrict__ total,
+                                      uint64_t groups, uint64_t acc_words, unsigned long long* __restrict__ accum) {
+  uint64_t g = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (g >= acc_words) return;
+  accum[g] = g < groups ? group_excl[g] : *total;  // extra slot only when nbits % 512 == 0
+}
+
+__global__ void entries_ascii_kernel(const uint64_t* __restrict__ store, const uint64_t* __restrict__ locs,
+                                     const uint64_t* __restrict__ offs, uint64_t first, uint64_t count,
+                                     char* __restrict__ out) {
+  uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= count) return;
+  uint64_t l = locs[first + i];
+  uint64_t a = loc_addr(l);
+  int len = (int)loc_len(l);
+  char* o = out + offs[i];
+  for (int j = 0; j < len; ++j) {
+    uint64_t p = a + j;
+    o[j] = "ACGT"[(store[p >> 5] >> (62 - 2 * (p & 31))) & 3];
+  }
+}
+
+__global__ void entry_offs_kernel(const uint64_t* __restrict__ locs, uint64_t first, uint64_t count,
+                                  uint32_t* __restrict__ lens) {
+  uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < count) lens[i] = loc_len(locs[first + i]);
+}
+
+inline unsigned grid_for(uint64_t n, unsigned block) { return (unsigned)std::max<uint64_t>(1, (n + block - 1) / block); }
+
+uint32_t read_u32(const uint32_t* d, cudaStream_t s) {
+  uint32_t h;
+  BGX_CUDA(cudaMemcpyAsync(&h, d, sizeof(h), cudaMemcpyDeviceToHost, s));
+  BGX_CUDA(cudaStreamSynchronize(s));
+  return h;
+}
+unsigned long long read_u64(const unsigned long long* d, cudaStream_t s) {
+  unsigned long long h;
+  BGX_CUDA(cudaMemcpyAsync(&h, d, sizeof(h), cudaMemcpyDeviceToHost, s));
+  BGX_CUDA(cudaStreamSynchronize(s));
+  return h;
+}
+
+// Sort n records completely.  keys/locs and the alt buffers all hold >= n elements; the sorted
+// data ends in (keys, locs).
+void sort_records(Context* c, DevBuf<uint64_t>& keys, DevBuf<uint64_t>& locs, DevBuf<uint64_t>& keys_alt,
+                  DevBuf<uint64_t>& locs_alt, uint32_t n, const std::string& tag) {
+  cudaStream_t s = c->stream;
+  if (n == 0) return;
+  int sbits = c->opt.sort_key_bits;
+  int passes = 0;
+  {
+    ScopedStage st(c, "sort_radix");
+    bool alt = radix_sort_pairs(keys.p, locs.p, keys_alt.p, locs_alt.p, n, 64 - sbits, 64, s, &passes);
+    if (alt) { std::swap(keys, keys_alt); std::swap(locs, locs_alt); }
+    st.stop();
+  }
+  c->add_stat("sort_radix_passes", passes);
+  c->add_stat("sort_radix_records", (double)n * passes);
+  c->add_stat("alg_bytes_sort_radix", radix_pass_alg_bytes(n) * passes);
+  c->add_stat("useful_bytes_sort", 14.0 * n);
+
+  ScopedStage st(c, "sort_ties");
+  DevBuf<uint32_t> big_flag(n, s);
+  DevBuf<unsigned long long> n_big(1, s);
+  BGX_CUDA(cudaMemsetAsync(big_flag.p, 0, (size_t)n * 4, s));
+  BGX_CUDA(cudaMemsetAsync(n_big.p, 0, 8, s));
+  int small_limit = kSmallGroup;
+  if (const char* e = getenv("BGX_SMALL_GROUP")) small_limit = std::max(1, atoi(e));  // test hook: force the refinement path
+  tie_small_kernel<<<grid_for(n, 128), 128, 0, s>>>(c->store.p, keys.p, locs.p, n, sbits, small_limit, big_flag.p,
+                                                   n_big.p);
+  BGX_CUDA(cudaGetLastError());
+  uint32_t m = (uint32_t)read_u64(n_big.p, s);
+  c->add_stat("tie_big_records_" + tag, m);
+  if (m) {
+    // refinement rounds over the members of big groups
+    DevBuf<uint32_t> big_pos(n, s);
+    exclusive_scan_u32(big_flag.p, big_pos.p, n, nullptr, s);
+    DevBuf<uint32_t> midx(m, s), head(m, s);
+    refine_init_kernel<<<grid_for(n, 256), 256, 0, s>>>(big_flag.p, big_pos.p, keys.p, n, sbits, midx.p, head.p);
+    int D = sbits / 2;
+    int rounds = 0;
+    while (m) {
+      DevBuf<uint32_t> gid(m, s);
+      exclusive_scan_u32(head.p, gid.p, m, nullptr, s);
+      DevBuf<uint64_t> ck(m, s), cl(m, s), ck2(m, s), cl2(m, s);
+      refine_key_kernel<<<grid_for(m, 256), 256, 0, s>>>(c->store.p, locs.p, midx.p, gid.p, head.p, m, D, ck.p, cl.p);
+      bool alt = radix_sort_pairs(ck.p, cl.p, ck2.p, cl2.p, m, 0, 64, s);
+      DevBuf<uint32_t> tied(m, s), nhead(m, s), tpos(m, s), tot(1, s);
+      refine_writeback_kernel<<<grid_for(m, 256), 256, 0, s>>>(c->store.p, alt ? ck2.p : ck.p, alt ? cl2.p : cl.p, midx.p,
+                                                              m, D, keys.p, locs.p, tied.p, nhead.p);
+      exclusive_scan_u32(tied.p, tpos.p, m, tot.p, s);
+      BGX_CUDA(cudaGetLastError());
+      uint32_t m2 = read_u32(tot.p, s);
+      DevBuf<uint32_t> midx2(std::max<uint32_t>(m2, 1), s), head2(std::max<uint32_t>(m2, 1), s);
+      if (m2)
+        refine_compact_kernel<<<grid_for(m, 256), 256, 0, s>>>(tied.p, tpos.p, midx.p, nhead.p, m, midx2.p, head2.p);
+      midx = std::move(midx2);
+      head = std::move(head2);
+      m = m2;
+      D += kChunkBases;
+      ++rounds;
+      BGX_CHECK(rounds < 64, "tie refinement did not converge");
+    }
+    c->add_stat("tie_refine_rounds_" + tag, rounds);
+  }
+  st.stop();
+}
+
+// drop every record that is a prefix of / equal to its successor; returns the survivor count and
+// leaves them in (keys, locs) (buffers are swapped with the alt ones).
+uint32_t dedup_records(Context* c, DevBuf<uint64_t>& keys, DevBuf<uint64_t>& locs, DevBuf<uint64_t>& keys_alt,
+                       DevBuf<uint64_t>& locs_alt, uint32_t n) {
+  cudaStream_t s = c->stream;
+  if (n == 0) return 0;
+  ScopedStage st(c, "dedup");
+  DevBuf<uint32_t> keep(n, s), pos(n, s), tot(1, s);
+  dedup_flag_kernel<<<grid_for(n, 256), 256, 0, s>>>(c->store.p, keys.p, locs.p, n, keep.p);
+  exclusive_scan_u32(keep.p, pos.p, n, tot.p, s);
+  compact_pairs_kernel<<<grid_for(n, 256), 256, 0, s>>>(keys.p, locs.p, keep.p, pos.p, n, keys_alt.p, locs_alt.p);
+  BGX_CUDA(cudaGetLastError());
+  uint32_t m = read_u32(tot.p, s);
+  std::swap(keys, keys_alt);
+  std::swap(locs, locs_alt);
+  c->add_stat("alg_bytes_dedup", 16.0 * n + 16.0 * m);
+  st.stop();
+  return m;
+}
+
+}  // namespace
+
+void stage_build_seqset(Context* c) {
+  BGX_CHECK(c->corrected, "bgx_build_seqset: call bgx_correct first");
+  cudaStream_t s = c->stream;
+  ScopedStage st_all(c, "seqset_total");
+  const uint32_t n_reads = (uint32_t)c->n_reads;
+  BGX_CHECK(c->n_seeds < (1ull << 31), "too many seed records for one GPU shard");
+
+  // 1. seeds
+  uint32_t n = (uint32_t)c->n_seeds;
+  size_t cap = (size_t)n + n / 2 + 1024;
+  DevBuf<uint64_t> keys(cap, s), locs(cap, s), keys_alt(cap, s), locs_alt(cap, s);
+  {
+    ScopedStage st(c, "seed_emit");
+    DevBuf<uint32_t> cnt(n_reads, s), off(n_reads, s);
+    seed_count_kernel<<<grid_for(n_reads, 256), 256, 0, s>>>(c->clen.p, c->next_fwd.p, c->next_rev.p, n_reads, cnt.p);
+    exclusive_scan_u32(cnt.p, off.p, n_reads, nullptr, s);
+    seed_emit_kernel<<<grid_for(n_reads, 128), 128, 0, s>>>(c->store.p, c->n_words, c->word_off.p, c->clen.p,
+                                                            c->next_fwd.p, c->next_rev.p, off.p, n_reads, keys.p, locs.p);
+    BGX_CUDA(cudaGetLastError());
+    st.stop();
+  }
+
+  // 2. sort + dedup
+  sort_records(c, keys, locs, keys_alt, locs_alt, n, "r1");
+  uint32_t n1 = dedup_records(c, keys, locs, keys_alt, locs_alt, n);
+  c->set_stat("entries_round1", n1);
+
+  // 3. closure walk
+  uint32_t n_new = 0;
+  {
+    ScopedStage st(c, "walk");
+    DevBuf<uint32_t> chains(std::max<uint32_t>(n1, 1), s);
+    DevBuf<unsigned long long> n_chains_d(1, s);
+    BGX_CUDA(cudaMemsetAsync(n_chains_d.p, 0, 8, s));
+    walk_phase1_kernel<<<grid_for(n1, 128), 128, 0, s>>>(c->store.p, keys.p, locs.p, n1, chains.p, n_chains_d.p);
+    BGX_CUDA(cudaGetLastError());
+    uint32_t n_chains = (uint32_t)read_u64(n_chains_d.p, s);
+    c->set_stat("walk_chains", n_chains);
+    if (n_chains) {
+      DevBuf<uint32_t> ccnt(n_chains, s), coff(n_chains, s), tot(1, s);
+      walk_phase2_kernel<<<grid_for((uint64_t)n_chains * 32, 128), 128, 0, s>>>(c->store.p, keys.p, locs.p, n1, chains.p,
+                                                                                n_chains, ccnt.p);
+      exclusive_scan_u32(ccnt.p, coff.p, n_chains, tot.p, s);
+      BGX_CUDA(cudaGetLastError());
+      n_new = read_u32(tot.p, s);
+      uint64_t need = (uint64_t)n1 + n_new;
+      BGX_CHECK(need < (1ull << 31), "too many records for one GPU shard");
+      if (need > keys.n) {
+        DevBuf<uint64_t> k2(need + 1024, s), l2(need + 1024, s);
+        BGX_CUDA(cudaMemcpyAsync(k2.p, keys.p, (size_t)n1 * 8, cudaMemcpyDeviceToDevice, s));
+        BGX_CUDA(cudaMemcpyAsync(l2.p, locs.p, (size_t)n1 * 8, cudaMemcpyDeviceToDevice, s));
+        keys = std::move(k2);
+        locs = std::move(l2);
+        keys_alt.alloc(need + 1024, s);
+        locs_alt.alloc(need + 1024, s);
+      }
+      walk_emit_kernel<<<grid_for((uint64_t)n_chains * 32, 128), 128, 0, s>>>(c->store.p, locs.p, chains.p, ccnt.p, coff.p,
+                                                                              n_chains, keys.p + n1, locs.p + n1);
+      BGX_CUDA(cudaGetLastError());
+    }
+    st.stop();
+  }
+  c->set_stat("walk_new_records", n_new);
+
+  // 4. sort + dedup of survivors + walk output
+  uint32_t n2 = n1;
+  if (n_new) {
+    sort_records(c, keys, locs, keys_alt, locs_alt, n1 + n_new, "r2");
+    n2 = dedup_records(c, keys, locs, keys_alt, locs_alt, n1 + n_new);
+  }
+  c->n_entries = n2;
+  c->set_stat("entries", n2);
+
+  // 5. tables
+  {
+    ScopedStage st(c, "tables");
+    const uint64_t nb = n2;
+    c->prev_words = (nb + 63) / 64;
+    c->sub_words = (nb + 511) / 512;
+    c->acc_words = (nb + 1 + 511) / 512;
+    c->sizes.alloc(std::max<uint64_t>(nb, 1), s);
+    c->shared.alloc(std::max<uint64_t>(nb, 1), s);
+    c->prev_bits.alloc(std::max<uint64_t>(4 * c->prev_words, 1), s);
+    c->prev_sub.alloc(std::max<uint64_t>(4 * c->sub_words, 1), s);
+    c->prev_acc.alloc(std::max<uint64_t>(4 * c->acc_words, 1), s);
+    BGX_CUDA(cudaMemsetAsync(c->prev_bits.p, 0, std::max<uint64_t>(4 * c->prev_words, 1) * 8, s));
+    BGX_CUDA(cudaMemsetAsync(c->prev_acc.p, 0, std::max<uint64_t>(4 * c->acc_words, 1) * 8, s));
+    DevBuf<unsigned int> max_len(1, s);
+    DevBuf<int> missing(1, s);
+    BGX_CUDA(cudaMemsetAsync(max_len.p, 0, 4, s));
+    BGX_CUDA(cudaMemsetAsync(missing.p, 0, 4, s));
+    if (nb) {
+      tables_kernel<<<grid_for(nb, 128), 128, 0, s>>>(c->store.p, keys.p, locs.p, n2, c->sizes.p, c->shared.p,
+                                                      reinterpret_cast<unsigned long long*>(c->prev_bits.p),
+                                                      c->prev_words, max_len.p, missing.p);
+      DevBuf<uint32_t> gpop(c->sub_words, s), gex(c->sub_words, s), tot(1, s);
+      uint64_t off = 0;
+      for (int b = 0; b < 4; ++b) {
+        bitcount_groups_kernel<<<grid_for(c->sub_words, 256), 256, 0, s>>>(
+            reinterpret_cast<unsigned long long*>(c->prev_bits.p) + b * c->prev_words, c->prev_words, c->sub_words, gpop.p,
+            reinterpret_cast<unsigned long long*>(c->prev_sub.p) + b * c->sub_words);
+        exclusive_scan_u32(gpop.p, gex.p, c->sub_words, tot.p, s);
+        bitcount_accum_kernel<<<grid_for(c->acc_words, 256), 256, 0, s>>>(
+            gex.p, tot.p, c->sub_words, c->acc_words, reinterpret_cast<unsigned long long*>(c->prev_acc.p) + b * c->acc_words);
+        BGX_CUDA(cudaGetLastError());
+        c->fixed[b] = off;
+        off += read_u32(tot.p, s);
+      }
+      c->fixed[4] = off;
+    } else {
+      for (int b = 0; b < 5; ++b) c->fixed[b] = 0;
+    }
+    unsigned int h_max;
+    int h_missing;
+    BGX_CUDA(cudaMemcpyAsync(&h_max, max_len.p, 4, cudaMemcpyDeviceToHost, s));
+    BGX_CUDA(cudaMemcpyAsync(&h_missing, missing.p, 4, cudaMemcpyDeviceToHost, s));
+    BGX_CUDA(cudaStreamSynchronize(s));
+    c->max_entry_len = h_max;
+    BGX_CHECK(!h_missing, "Missing expansion?");  // bs/builder.cpp:96
+    // seqset::finalize (seqset.cpp:123-126)
+    BGX_CHECK(c->fixed[4] == nb, "Invalid seqset in finalize: prev bit totals != entries");
+    st.stop();
+  }
+  c->ent_key = std::move(keys);
+  c->ent_loc = std::move(locs);
+  c->built = true;
+  st_all.stop();
+}
+
+void export_entries_ascii(Context* c, uint64_t first, uint64_t count, char** bases, uint64_t** offs_out) {
+  BGX_CHECK(c->built, "bgx_export_entries_ascii: call bgx_build_seqset first");
+  BGX_CHECK(first + count <= c->n_entries, "bgx_export_entries_ascii: range out of bounds");
+  cudaStream_t s = c->stream;
+  std::vector<uint32_t> lens(count);
+  DevBuf<uint32_t> d_lens(std::max<uint64_t>(count, 1), s);
+  if (count) {
+    entry_offs_kernel<<<grid_for(count, 256), 256, 0, s>>>(c->ent_loc.p, first, count, d_lens.p);
+    BGX_CUDA(cudaMemcpyAsync(lens.data(), d_lens.p, count * 4, cudaMemcpyDeviceToHost, s));
+    BGX_CUDA(cudaStreamSynchronize(s));
+  }
+  uint64_t* offs = (uint64_t*)malloc((count + 1) * 8);
+  offs[0] = 0;
+  for (uint64_t i = 0; i < count; ++i) offs[i + 1] = offs[i] + lens[i];
+  char* out = (char*)malloc(std::max<uint64_t>(offs[count], 1));
+  if (count) {
+    DevBuf<uint64_t> d_offs(count + 1, s);
+    DevBuf<char> d_out(std::max<uint64_t>(offs[count], 1), s);
+    BGX_CUDA(cudaMemcpyAsync(d_offs.p, offs, (count + 1) * 8, cudaMemcpyHostToDevice, s));
+    entries_ascii_kernel<<<grid_for(count, 128), 128, 0, s>>>(c->store.p, c->ent_loc.p, d_offs.p, first, count, d_out.p);
+    BGX_CUDA(cudaMemcpyAsync(out, d_out.p, offs[count], cudaMemcpyDeviceToHost, s));
+    BGX_CUDA(cudaStreamSynchronize(s));
+  }
+  *bases = out;
+  *offs_out = offs;
+}
+
+}  // namespace bgx

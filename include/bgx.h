@@ -1,0 +1,134 @@
+/* bgx.h -- C ABI of the B200-native seqset construction path ("bgx").
+ *
+ * This is the drop-in boundary for BioGraph's `biograph create` hot path
+ * (modules/build_seqset + the k-mer glue in modules/bio_mapred): k-mer counting, k-mer based
+ * read correction, and suffix seed/expand + sort/dedup/shared-prefix/prev-bit computation that
+ * emits the seqset tables.  Every entry point names the reference interface it replaces
+ * (paths relative to the reference checkout; "bs/" = modules/build_seqset/).
+ *
+ * Conventions
+ *   - plain C linkage, plain pointers and sizes; no CUDA or torch types.
+ *   - every call returns 0 on success, non-zero on error; bgx_last_error() gives the
+ *     thread-local message (the reference throws io_exception / CHECK-aborts instead).
+ *   - the caller owns every input buffer; the library owns every output buffer until
+ *     bgx_free() (host memory) or bgx_destroy().
+ *   - one context drives one GPU (one process per GPU; multi-GPU runs shard above this ABI,
+ *     see DESIGN.md).  There is NO CPU fallback: without a CUDA device bgx_create fails.
+ *   - base codes A=0 C=1 G=2 T=3 (modules/bio_base/dna_base.h:38-57); k-mers are uint64 with the
+ *     first base in the high bits of the low 2k bits (modules/bio_base/kmer.h:30-38).
+ */
+#ifndef BGX_H_
+#define BGX_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct bgx_ctx bgx_ctx;
+
+/* `biograph create` flags that reach the path (modules/biograph/biograph_create.cpp:258-335,
+ * validated :483-498) plus the device to run on. */
+typedef struct bgx_options {
+  int32_t kmer_size;          /* --kmer-size, default 30; 16..31 (bs/kmer_counter.cpp:52-54) */
+  int32_t min_kmer_count;     /* --min-kmer-count, default 5 */
+  int32_t max_corrections;    /* --max-corrections, default 8 (<= 16 here) */
+  int32_t min_good_run;       /* --min-good-run, default 2 */
+  float trim_after_portion;   /* --trim-after-portion, default 0.7f (parsed as float: :489-490) */
+  int32_t device;             /* CUDA device ordinal */
+  int32_t sort_key_bits;      /* radix-sorted key bits per round (multiple of 8, 16..64); 0 = default */
+  int32_t reserved;
+} bgx_options;
+
+#define BGX_FLAG_FWD_STARTS_READ 1u /* kmer_set::k_fwd_starts_read */
+#define BGX_FLAG_REV_STARTS_READ 2u /* kmer_set::k_rev_starts_read */
+#define BGX_MAX_READ_LEN 255        /* biograph_create.cpp:134-139 (reads > 255 need --allow-long-reads) */
+
+void bgx_default_options(bgx_options* opts);
+const char* bgx_last_error(void);
+const char* bgx_version(void);
+int bgx_device_count(void);
+
+/* replaces: kmer_counter(count_kmer_options) + part_repo + correct_reads + expander + builder
+ * construction in SEQSETMain::run (modules/biograph/biograph_create.cpp:540-779). */
+int bgx_create(const bgx_options* opts, bgx_ctx** out);
+void bgx_destroy(bgx_ctx* ctx);
+void bgx_free(void* host_ptr);
+
+/* replaces: prob_pass_processor::add(string_view) (bs/kmer_counter.h:297-326) called from
+ * read_importer_state::process (biograph_create.cpp:119-151).  ASCII over {A,C,G,T,N}; read r is
+ * bases[offs[r] .. offs[r+1]).  May be called repeatedly; reads are appended (H2D copy included).
+ * Thread-compatible, not thread-safe: serialise calls on one context. */
+int bgx_add_reads_ascii(bgx_ctx* ctx, const char* bases, const uint64_t* offs, uint64_t n_reads);
+
+/* Same, for reads already 2-bit packed (T0 of the benchmark clock).
+ *   packed   : dna_sequence byte order (4 bases/byte, first base in the high bits,
+ *              modules/bio_base/dna_sequence.h:95-99); read r starts at byte 8*word_offs[r] and
+ *              occupies ceil(lens[r]/32) 8-byte words; unused trailing bits must be zero.
+ *   n_mask   : optional (NULL = no N anywhere); one uint32 per 8-byte word of `packed`; bit
+ *              (31 - j%32) set means base j of the read is 'N' (its 2-bit code must be 0).
+ *   word_offs: n_reads+1 entries; word_offs[n_reads] = total words.
+ * Pinned host memory makes the copy asynchronous; pageable memory works too. */
+int bgx_add_reads_packed(bgx_ctx* ctx, const uint8_t* packed, const uint32_t* n_mask,
+                         const uint64_t* word_offs, const uint16_t* lens, uint64_t n_reads);
+
+/* replaces: kmer_counter::close_prob_pass + run_kmerize_subtask (bs/kmer_counter.cpp:234-404,
+ * modules/bio_mapred/kmerize_bf.h:81-84): exact canonical k-mer counts with fwd/rev counts and
+ * starts-read flags, min-count filter, and the device k-mer set used by correction. */
+int bgx_count_kmers(bgx_ctx* ctx);
+
+/* Parity hook + histogram feed (kmer_counter::extract_exact_counts, kmerize_bf.cpp:353-429).
+ * All k-mers with fwd+rev >= min_count, ascending; flags use BGX_FLAG_*.  Arrays are
+ * bgx_free()'d by the caller. */
+int bgx_export_kmers(bgx_ctx* ctx, uint32_t min_count, uint64_t* n, uint64_t** kmers,
+                     uint32_t** fwd_counts, uint32_t** rev_counts, uint8_t** flags);
+
+/* replaces: correct_reads::correct over all reads (bs/correct_reads.cpp:154-231) including
+ * fast_read_correct (modules/bio_base/fast_read_correct.cpp) and the seed counts. */
+int bgx_correct(bgx_ctx* ctx);
+
+/* Parity hook + make_readmap input (corrected_reads kv sink, biograph_create.cpp:868-893).
+ * lens[r] = corrected length, 0 if the read was dropped; bases = ASCII of kept reads
+ * concatenated in input order; corrections[r], next_fwd[r], next_rev[r] as in
+ * bs/correct_reads.cpp:195-210.  Any output pointer may be NULL. */
+int bgx_export_corrected(bgx_ctx* ctx, uint64_t* n_reads, uint16_t** lens, char** bases,
+                         uint64_t* n_bases, uint8_t** corrections, uint16_t** next_fwd,
+                         uint16_t** next_rev);
+
+/* replaces: expander::sort_and_dedup / expander::expand rounds + builder::build_chunks
+ * (biograph_create.cpp:914-931, bs/expand.cpp, bs/builder.cpp:8-164). */
+int bgx_build_seqset(bgx_ctx* ctx);
+
+/* replaces: builder::make_seqset + seqset::finalize (bs/builder.cpp:207-263,
+ * modules/bio_base/seqset.cpp:113-129).  sizes/shared are uint16 per entry; prev_bits[b] is the
+ * bitcount `bits` member of prev_<b> (ceil(n/64) uint64 words, bit i at word[i/64]>>(i&63));
+ * prev_subaccum / prev_accum are the bitcount index members (modules/io/bitcount.cpp:84-123);
+ * fixed[5] as in seqset::finalize.  Any output pointer may be NULL. */
+int bgx_export_seqset(bgx_ctx* ctx, uint64_t* n_entries, uint32_t* max_entry_len, uint16_t** sizes,
+                      uint16_t** shared, uint64_t* prev_bits[4], uint64_t* prev_subaccum[4],
+                      uint64_t* prev_accum[4], uint64_t fixed[5]);
+
+/* Debug/parity hook: entry i as ASCII (entries are <= BGX_MAX_READ_LEN bases). */
+int bgx_export_entries_ascii(bgx_ctx* ctx, uint64_t first, uint64_t count, char** bases,
+                             uint64_t** offs);
+
+/* Whole path on resident reads: count -> correct -> seqset.  Equivalent to the three calls. */
+int bgx_run(bgx_ctx* ctx);
+
+/* Drops everything derived from the reads (tables, corrected reads, seqset) but keeps the
+ * uploaded reads resident, so the path can be re-run (benchmark loop). */
+int bgx_reset_results(bgx_ctx* ctx);
+/* Drops the reads too. */
+int bgx_clear_reads(bgx_ctx* ctx);
+
+/* replaces: runtime_stats / SPLOG stage counters (modules/io/runtime_stats.h, qc/create_stats.json).
+ * Writes a JSON object (stage times in ms measured with CUDA events, counts, algorithmic bytes
+ * per kernel family) into buf; returns non-zero if cap is too small. */
+int bgx_stats_json(bgx_ctx* ctx, char* buf, size_t cap);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* BGX_H_ */

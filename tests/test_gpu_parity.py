@@ -1,0 +1,320 @@
+"""GPU parity tests: the CUDA path (through the C ABI) against the CPU oracle on the same inputs,
+against the reference's golden fixture, and against the reference tests' known answers.
+Bit-exact everywhere (integer / byte / index work)."""
+import os
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+from oracle import oracle as O  # noqa: E402
+from tests import frc_cases as F  # noqa: E402
+
+
+@pytest.fixture(scope="module")
+def B():
+    import biograph_b200 as B
+    if B.load_library().bgx_device_count() == 0:
+        pytest.fail("no CUDA device visible: the gpu tests need a B200 (there is no CPU fallback)")
+    return B
+
+
+def run_gpu(B, reads, **opts):
+    g = B.Bgx(**opts)
+    g.add_reads(reads)
+    g.count_kmers()
+    km = g.export_kmers(1)
+    g.correct()
+    cr = g.export_corrected()
+    g.build_seqset()
+    ss = g.export_seqset()
+    st = g.stats()
+    return g, km, cr, ss, st
+
+
+def check_seqset_equal(a, b):
+    assert a["n"] == b["n"]
+    for k in ("sizes", "shared", "prev", "fixed"):
+        assert np.array_equal(a[k], b[k]), k
+
+
+def check_bitcount(ss):
+    for b in range(4):
+        sub, acc, tot = O.bitcount_finalize(ss["prev"][b], ss["n"])
+        assert np.array_equal(sub, ss["subaccum"][b])
+        assert np.array_equal(acc, ss["accum"][b])
+        assert tot == int(ss["fixed"][b + 1] - ss["fixed"][b])
+
+
+def full_compare(B, reads, k=30, min_count=5, max_corrections=8, min_good_run=2, trim=0.7, closed_form=False, **kw):
+    g, km, cr, ss, st = run_gpu(B, reads, kmer_size=k, min_kmer_count=min_count, max_corrections=max_corrections,
+                                min_good_run=min_good_run, trim_after_portion=trim, **kw)
+    oc = O.count_kmers(reads, k)
+    for f in ("kmers", "fwd", "rev", "flags"):
+        assert np.array_equal(oc[f], km[f]), f
+    solid = O.solid_set(oc, min_count)
+    gs = g.export_kmers(min_count)
+    for f in ("kmers", "fwd", "rev", "flags"):
+        assert np.array_equal(solid[f], gs[f]), f
+    ocr = O.correct_reads(reads, solid, k, max_corrections, min_good_run, trim)
+    assert np.array_equal(ocr["kept"], cr["kept"])
+    assert np.array_equal(ocr["offs"], cr["offs"])
+    assert ocr["seq"] == cr["seq"]
+    assert np.array_equal(ocr["corrections"], cr["corrections"])
+    assert np.array_equal(ocr["next_fwd"], cr["next_fwd"])
+    assert np.array_equal(ocr["next_rev"], cr["next_rev"])
+    oss = O.seqset_staged((ocr["seq"], ocr["offs"]), ocr["next_fwd"], ocr["next_rev"])
+    check_seqset_equal(oss, ss)
+    if closed_form:
+        check_seqset_equal(O.seqset_closed_form((ocr["seq"], ocr["offs"])), ss)
+    check_bitcount(ss)
+    g.close()
+    return ss, st
+
+
+def test_golden_e_coli_10000snp(B, golden, golden_reads):
+    """BASELINE config 1: golden/e_coli_10000snp.fq -> every payload member of the reference's own
+    golden/e_coli_10000snp.bg/seqset, byte for byte."""
+    g, km, cr, ss, st = run_gpu(B, golden_reads)
+    assert len(g.export_kmers(5)["kmers"]) == 7108
+    assert cr["n_kept"] == 8444 and int(cr["lens"].sum()) == 288464
+    assert ss["n"] == 19935
+    assert np.array_equal(ss["fixed"], golden["fixed"])
+    assert np.array_equal(ss["sizes"].astype(np.uint8), golden["entry_sizes"])
+    assert np.array_equal(ss["shared"].astype(np.uint8), golden["shared"])
+    for b, ch in enumerate("ACGT"):
+        assert np.array_equal(ss["prev"][b], golden[f"prev_{ch}_bits"])
+        assert np.array_equal(ss["subaccum"][b], golden[f"prev_{ch}_subaccum"])
+        assert np.array_equal(ss["accum"][b], golden[f"prev_{ch}_accum"])
+    # entries are strictly sorted, prefix-free, and are exactly dedup(all suffixes) of the corrected reads
+    ents = g.export_entries()
+    assert ents == sorted(ents) and len(set(ents)) == len(ents)
+    g.close()
+
+
+def test_golden_against_oracle_stages(B, golden_reads):
+    full_compare(B, golden_reads, closed_form=True)
+
+
+# ---- bs/builder_test.cpp known answers (seqset_for_reads: no correction) -----------------------------
+def seqset_for_reads(B, reads, **kw):
+    """modules/bio_base/seqset_testutil.cpp:19-59 analogue: reads in, seqset out, correction made a
+    no-op by using each read min_count times... instead we bypass correction: every k-mer solid."""
+    k = 16
+    g = B.Bgx(kmer_size=k, min_kmer_count=1, max_corrections=0, trim_after_portion=1.0, **kw)
+    g.add_reads(reads)
+    g.run()
+    ss = g.export_seqset()
+    ents = g.export_entries()
+    g.close()
+    return ss, ents
+
+
+SEQ1 = ["AAAATTAC", "AAATTAC", "AATTAC", "AATTTTAG", "AC", "AG", "ATTAC", "ATTTTAG", "CTAAAATTAC", "GTAATTTTAG",
+        "TAAAATTAC", "TAATTTTAG", "TAC", "TAG", "TTAC", "TTAG", "TTTAG", "TTTTAG"]
+
+
+@pytest.mark.parametrize("reads,size", [
+    ([O.tseq("ab")], None),
+    ([O.tseq("abcdefg")], 129),
+    ([O.tseq("abcd"), O.tseq("cdef"), O.tseq_rc("efgh")], 152),
+    ([O.tseq("ab"), O.tseq("bc"), O.tseq("cd"), O.tseq("be")], 91),
+    ([O.tseq("AB"), O.tseq("BC"), O.tseq("CD"), O.tseq("BE")], 91),
+    ([O.tseq("abc"), O.tseq("cde")], 89),
+    ([O.tseq("abc"), O.tseq("efg")], 99),
+])
+def test_builder_known_answers(B, reads, size):
+    ss, ents = seqset_for_reads(B, reads)
+    exp = O.entries_closed_form_py(reads)
+    assert ents == exp
+    if size is not None:
+        assert ss["n"] == size
+    check_seqset_equal(O.seqset_closed_form(reads), ss)
+    check_bitcount(ss)
+
+
+# ---- synthetic genomes ---------------------------------------------------------------------------------
+def _sim(glen, n, L, err, seed, n_rate=0.0, paired=True):
+    from biograph_b200 import synth
+    genome = synth.random_genome(glen, seed=seed, repeat_frac=0.05)
+    reads = synth.simulate_reads(genome, n, read_len=L, error_rate=err, seed=seed + 1, paired=paired,
+                                 frag_mean=max(L + 50, 2 * L), frag_sd=20, n_rate=n_rate)
+    buf, offs = synth.as_buffer(reads)
+    return (buf.tobytes(), offs)
+
+
+@pytest.mark.parametrize("glen,n,L,err,nrate,seed", [
+    (5000, 3000, 100, 0.005, 0.0, 1),
+    (20000, 8000, 150, 0.005, 0.0, 2),
+    (20000, 8000, 150, 0.02, 0.002, 3),   # heavy errors + N calls: exercises the DFS and N handling
+    (3000, 4000, 60, 0.01, 0.001, 4),
+    (50000, 10000, 250, 0.005, 0.0, 5),   # long reads (8 words)
+])
+def test_synthetic_full_path(B, glen, n, L, err, nrate, seed):
+    full_compare(B, _sim(glen, n, L, err, seed, n_rate=nrate), closed_form=(n * L <= 1_500_000))
+
+
+@pytest.mark.parametrize("k,min_count,maxc,run,trim", [(16, 2, 2, 2, 0.5), (21, 3, 4, 1, 0.7), (31, 5, 8, 3, 0.9),
+                                                        (30, 5, 0, 2, 1.0), (25, 4, 16, 2, 0.0)])
+def test_parameter_sweep(B, k, min_count, maxc, run, trim):
+    full_compare(B, _sim(8000, 4000, 120, 0.01, 40 + k, n_rate=0.001), k=k, min_count=min_count, max_corrections=maxc,
+                 min_good_run=run, trim=trim)
+
+
+def test_ragged_and_short_reads(B):
+    rng = np.random.default_rng(9)
+    from biograph_b200 import synth
+    genome = synth.random_genome(6000, seed=99).tobytes().decode()
+    reads = []
+    for _ in range(5000):
+        L = int(rng.integers(1, 256))
+        s = int(rng.integers(0, len(genome) - L))
+        r = genome[s:s + L]
+        if rng.random() < 0.5:
+            r = O.revcomp(r)
+        reads.append(r)
+    reads += ["A", "ACGT", "N" * 40, "ACGTN" * 30, genome[:29], genome[:30], genome[:31]]
+    full_compare(B, reads)
+
+
+def test_repeats_force_big_tie_groups(B):
+    # low-complexity sequence: thousands of suffixes share their first 24+ bases -> refinement path
+    rng = np.random.default_rng(3)
+    unit = "ACGTTGCA"
+    base = "".join("ACGT"[i] for i in rng.integers(0, 4, 300))
+    reads = []
+    for i in range(600):
+        reads.append(base[i % 100:i % 100 + 60] + "A" * int(rng.integers(40, 120)) + base[200:230 + i % 40])
+        reads.append(base[i % 50:i % 50 + 50] + unit * int(rng.integers(5, 20)) + base[100:150])
+    ss, st = full_compare(B, reads, min_count=2, closed_form=True)
+    assert st.get("tie_big_records_r1", 0) + st.get("tie_big_records_r2", 0) > 0
+
+
+def test_refinement_path_equals_small_group_path(B):
+    reads = _sim(10000, 5000, 150, 0.005, 77)
+    ss_a, _ = full_compare(B, reads)
+    os.environ["BGX_SMALL_GROUP"] = "1"
+    try:
+        ss_b, st = full_compare(B, reads)
+        assert st.get("tie_big_records_r1", 0) > 0
+    finally:
+        del os.environ["BGX_SMALL_GROUP"]
+    check_seqset_equal(ss_a, ss_b)
+
+
+@pytest.mark.parametrize("bits", [16, 32, 48, 64])
+def test_sort_key_bits_do_not_change_result(B, bits):
+    reads = _sim(10000, 5000, 150, 0.005, 78)
+    full_compare(B, reads, sort_key_bits=bits)
+
+
+def test_packed_input_equals_ascii_input(B):
+    from biograph_b200 import bgx
+    reads = _sim(8000, 4000, 150, 0.01, 31, n_rate=0.002)
+    g1, km1, cr1, ss1, _ = run_gpu(B, reads)
+    packed, nmask, woffs, lens = bgx.pack_reads_2bit(reads)
+    assert nmask is not None
+    g2 = B.Bgx()
+    g2.add_reads_packed(packed, nmask, woffs, lens)
+    g2.run()
+    ss2 = g2.export_seqset()
+    check_seqset_equal(ss1, ss2)
+    assert g2.export_corrected()["seq"] == cr1["seq"]
+    g1.close()
+    g2.close()
+
+
+def test_incremental_add_reads(B):
+    reads = _sim(8000, 4000, 150, 0.01, 32)
+    buf, offs = reads
+    g1, _, _, ss1, _ = run_gpu(B, reads)
+    g2 = B.Bgx()
+    cut = 1500
+    g2.add_reads((buf[:offs[cut]], offs[:cut + 1]))
+    g2.add_reads((buf[offs[cut]:], offs[cut:] - offs[cut]))
+    g2.run()
+    check_seqset_equal(ss1, g2.export_seqset())
+    g1.close()
+    g2.close()
+
+
+def test_nothing_survives(B):
+    # all k-mers below min count: every read is dropped, the seqset is empty
+    reads = _sim(200000, 300, 100, 0.0, 33)
+    g = B.Bgx()
+    g.add_reads(reads)
+    g.run()
+    ss = g.export_seqset()
+    assert ss["n"] == 0 and int(ss["fixed"][4]) == 0
+    g.close()
+
+
+def test_errors_are_reported(B):
+    g = B.Bgx()
+    with pytest.raises(B.BgxError):
+        g.count_kmers()  # no reads
+    with pytest.raises(B.BgxError):
+        g.add_reads(["A" * 300])  # longer than 255
+    g.add_reads(["ACGT" * 20])
+    with pytest.raises(B.BgxError):
+        g.correct()  # before count
+    with pytest.raises(B.BgxError):
+        g.build_seqset()
+    g.close()
+    with pytest.raises(B.BgxError):
+        B.Bgx(kmer_size=32)
+
+
+# ---- fast_read_correct analytic cases through the CUDA corrector ----------------------------------------------
+@pytest.mark.parametrize("mode", ["N", "X"])
+@pytest.mark.parametrize("size", [30, 33, 61, 92, 122, 255])
+def test_frc_analytic_gpu(B, size, mode):
+    """modules/bio_base/fast_read_correct_test.cpp:108-258.  The k-mer set is injected by adding the
+    error-free sequence min_count times; every erroneous k-mer occurs far fewer times."""
+    seq = F.LONG[:size]
+    cs = list(F.cases(size, mode, with_three=(size <= 33)))
+    copies = 2000
+    reads = [seq] * copies + [c[1] for c in cs]
+    g = B.Bgx(kmer_size=F.K, min_kmer_count=copies, max_corrections=F.MAXC, min_good_run=F.RUN, trim_after_portion=0.0)
+    g.add_reads(reads)
+    g.count_kmers()
+    solid = g.export_kmers(copies)
+    assert np.array_equal(solid["kmers"], F.kmer_set_of(seq))
+    g.correct()
+    cr = g.export_corrected()
+    s, o = cr["seq"].decode(), cr["offs"]
+    for i, (name, read, exp, ec) in enumerate(cs):
+        r = copies + i
+        got = s[o[r]:o[r + 1]]
+        assert got == exp, (size, mode, name)
+        if exp:
+            assert cr["corrections"][r] == ec, (size, mode, name)
+    g.close()
+
+
+# ---- size-independent properties at a larger size ---------------------------------------------------------------
+def test_properties_large(B):
+    reads = _sim(400000, 300000, 150, 0.005, 55)
+    g = B.Bgx()
+    g.add_reads(reads)
+    g.run()
+    ss = g.export_seqset()
+    n = ss["n"]
+    assert n > 0 and int(ss["fixed"][4]) == n and int(ss["fixed"][0]) == 0
+    assert np.all(ss["shared"][1:] < ss["sizes"][1:]) and ss["shared"][0] == 0   # prefix-free
+    assert np.all(ss["shared"][1:] <= ss["sizes"][:-1])
+    pc = [int(np.unpackbits(ss["prev"][b].view(np.uint8)).sum()) for b in range(4)]
+    assert sum(pc) == n and [int(ss["fixed"][b + 1] - ss["fixed"][b]) for b in range(4)] == pc
+    check_bitcount(ss)
+    ents = g.export_entries(0, 20000) + g.export_entries(n - 20000, 20000)
+    assert all(a < b and not b.startswith(a) for a, b in zip(ents[:19999], ents[1:20000]))
+    # idempotence: re-running on the resident reads gives the same tables
+    g.reset_results()
+    g.run()
+    check_seqset_equal(ss, g.export_seqset())
+    # and the staged oracle agrees at this size
+    cr = g.export_corrected()
+    oss = O.seqset_staged((cr["seq"], cr["offs"]), cr["next_fwd"], cr["next_rev"])
+    check_seqset_equal(oss, ss)
+    g.close()
