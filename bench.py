@@ -1,0 +1,353 @@
+#!/usr/bin/env python
+"""bench.py -- seqset construction throughput (input bases/sec to finished seqset) on B200.
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--workload ecoli100x|chr20_30x|small]
+  python bench.py --impl reference ...      # the restated CPU path (oracle) on the host cores
+
+A "step" is one pass of the hot path (k-mer count -> correct -> seqset tables) over the whole
+synthetic read set of the workload.
+  value : bases/s with the 2-bit packed reads already resident in HBM when the timed region
+          starts (tables left in HBM).
+  e2e   : bases/s through the C ABI with HOST buffers: H2D of the packed reads from pinned
+          memory, the three stages, and D2H of every seqset table, all inside the timed region.
+Timing: CUDA events recorded on the library's own stream (bgx_timer_start/stop), max over ranks;
+L2 is flushed between steps and the working set (GBs of table + records) is far larger than L2.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+WORKLOADS = {
+    # BASELINE.json configs[1]: synthetic E. coli 100x 150bp paired reads, 0.5% error
+    "ecoli100x": dict(genome="ecoli", coverage=100, read_len=150, error=0.005, seed=20260101, paired=True),
+    # configs[2]: synthetic human chr20 30x
+    "chr20_30x": dict(genome=("random", 64444167, 20, 21), coverage=30, read_len=150, error=0.005, seed=22,
+                      paired=False),
+    "small": dict(genome=("random", 200000, 5, 6), coverage=100, read_len=150, error=0.005, seed=7, paired=True),
+}
+
+
+def make_workload(name, rank=0, reads_override=None, genome_prefix_reads=None):
+    """genome_prefix_reads: build the reads, at the workload's coverage and read model, over only a
+    prefix of the genome sized to give that many reads (the bounded CPU-baseline sample)."""
+    from biograph_b200 import synth
+    w = WORKLOADS[name]
+    if w["genome"] == "ecoli":
+        z = np.load(os.path.join(ROOT, "tests", "golden", "e_coli_genome.npz"))
+        genome = synth.unpack_genome(z["packed"], int(z["length"]))
+    else:
+        _, glen, s1, s2 = w["genome"]
+        genome = synth.random_genome(glen, seed=s1, repeat_frac=0.05, repeat_seed=s2)
+    if genome_prefix_reads:
+        glen = max(2000, genome_prefix_reads * w["read_len"] // w["coverage"])
+        genome = genome[:min(len(genome), glen)]
+    n_reads = -(-w["coverage"] * len(genome) // w["read_len"])
+    if reads_override:
+        n_reads = reads_override
+    # weak scaling: every rank builds its own read set of the same shape (different seed)
+    reads = synth.simulate_reads(genome, n_reads, read_len=w["read_len"], error_rate=w["error"],
+                                 seed=w["seed"] + 1000 * rank, paired=w["paired"])
+    return reads
+
+
+class ClockSampler:
+    """nvidia-smi clocks + throttle reasons during the timed region (B200_PROFILING.md)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, device):
+        self.device = device
+        self.rows = []
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "100", "-i", str(self.device)], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
+            self.th = threading.Thread(target=self._read, daemon=True)
+            self.th.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([x.strip() for x in line.split(",")])
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        for r in self.rows:
+            try:
+                sm.append(float(r[1])); mx.append(float(r[2]))
+                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[5:9]):
+                    if v.lower().startswith("active"):
+                        reasons.add(name)
+            except Exception:
+                pass
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def measured_peak_gbs():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+def cpu_port_run(reads2d, threads, k=30):
+    """The restated CPU path (oracle port) on a read sample: count -> filter -> correct -> staged
+    seqset (seed + stride-7/255 + stride-1/6 rounds, as the reference).  Returns seconds."""
+    from oracle import oracle as O
+    from biograph_b200 import synth
+    buf, offs = synth.as_buffer(reads2d)
+    rb = (buf.tobytes(), offs)
+    t0 = time.perf_counter()
+    counts = O.count_kmers(rb, k, threads=threads)
+    solid = O.solid_set(counts, 5)
+    cr = O.correct_reads(rb, solid, k, 8, 2, 0.7, threads=threads)
+    ss = O.seqset_staged((cr["seq"], cr["offs"]), cr["next_fwd"], cr["next_rev"], threads=threads)
+    dt = time.perf_counter() - t0
+    return dt, ss["n"]
+
+
+def run_reference(args):
+    """--impl reference: the reference's CPU path cannot be built offline (Bazel + Boost),
+    so this arm times the oracle port -- the restated CPU path -- with all host threads."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from oracle import oracle as O
+    O.build()
+    threads = O.max_threads()
+    w = WORKLOADS[args.workload]
+    total = args.reads or -(-w["coverage"] * (4938920 if w["genome"] == "ecoli" else w["genome"][1]) // w["read_len"])
+    # bounded sample: the workload's read model at the workload's coverage over a genome prefix
+    sub = make_workload(args.workload, 0, None, genome_prefix_reads=min(total, args.cpu_sample_reads))
+    sample = sub.shape[0]
+    reads = sub
+    times = []
+    for i in range(args.warmup + args.steps):
+        dt, n_ent = cpu_port_run(sub, threads)
+        if i >= args.warmup:
+            times.append(dt)
+    bases = sub.size
+    ms = 1e3 * float(np.mean(times))
+    val = bases / (ms / 1e3)
+    line = {"impl": "reference", "metric": "input bases/sec to finished seqset", "value": val, "unit": "bases/s",
+            "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u64", "data": "synthetic",
+            "config": {"workload": args.workload, "reads": int(total), "read_len": int(reads.shape[1])},
+            "cpu_baseline": {"value": val, "unit": "bases/s", "cores": threads, "kind": "port",
+                             "sample": f"{sample} reads at the workload's coverage over a genome prefix "
+                                       f"(workload has {total}), whole path (count+correct+staged seqset), "
+                                       "oracle port (reference binary not buildable offline)"},
+            "e2e": {"value": val, "unit": "bases/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="bgx", choices=["bgx", "reference"])
+    ap.add_argument("--workload", default="ecoli100x", choices=sorted(WORKLOADS))
+    ap.add_argument("--reads", type=int, default=None, help="override the read count (debug)")
+    ap.add_argument("--cpu-sample-reads", type=int, default=600000)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference(args)
+
+    import torch
+    import biograph_b200 as B
+    from biograph_b200 import bgx as bgxmod
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    assert world == args.gpus or world == 1, "launch with torchrun --nproc-per-node N for --gpus N"
+    torch.cuda.set_device(local)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(x):
+        if dist is None:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def sum_over_ranks(x):
+        if dist is None:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        return float(t.item())
+
+    # ---- workload: synthetic reads, 2-bit packed into pinned host memory (T0 of the clock) ----
+    reads = make_workload(args.workload, rank, args.reads)
+    n_reads, read_len = reads.shape
+    bases = int(reads.size)
+    packed, nmask, woffs, lens = bgxmod.pack_reads_2bit(reads)
+    pinned = torch.empty(packed.nbytes, dtype=torch.uint8).pin_memory()
+    pinned.numpy()[:] = packed
+    pinned_mask = None
+    if nmask is not None:
+        pinned_mask = torch.empty(nmask.nbytes, dtype=torch.uint8).pin_memory()
+        pinned_mask.numpy()[:] = nmask.view(np.uint8)
+    h2d = packed.nbytes + (nmask.nbytes if nmask is not None else 0) + woffs.nbytes // 2 + lens.nbytes
+    del packed
+
+    g = B.Bgx(device=local)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")  # > 126 MB L2
+
+    def flush_l2():
+        flush.zero_()
+        torch.cuda.synchronize()
+
+    def upload():
+        g.add_reads_packed_ptr(pinned.data_ptr(), None if pinned_mask is None else pinned_mask.data_ptr(),
+                               woffs.ctypes.data, lens.ctypes.data, n_reads)
+
+    # ---- device-resident arm ----------------------------------------------------------------------
+    upload()
+    stats_acc = {}
+    for i in range(args.warmup):
+        g.reset_results(); flush_l2(); g.run()
+    sampler = ClockSampler(local)
+    barrier()
+    sampler.start()
+    launches0 = g.launch_count()
+    t_wall0 = time.perf_counter()
+    dev_ms = 0.0
+    for i in range(args.steps):
+        g.reset_results()
+        flush_l2()
+        g.timer_start()
+        g.run()
+        dev_ms += g.timer_stop()
+        st = g.stats()
+        for k_, v in st.items():
+            if isinstance(v, (int, float)) and not isinstance(v, bool):
+                stats_acc[k_] = stats_acc.get(k_, 0.0) + v
+    barrier()
+    wall_s = time.perf_counter() - t_wall0
+    launches = g.launch_count() - launches0
+    clocks = sampler.stop()
+    ms_per_step = max_over_ranks(dev_ms / args.steps)
+    total_bases = sum_over_ranks(bases)
+    value = total_bases / (ms_per_step / 1e3)
+    st_mean = {k_: v / args.steps for k_, v in stats_acc.items()}
+    ss_n = int(st_mean.get("entries", 0))
+
+    # ---- end-to-end arm: host buffers in, host tables out ------------------------------------------------
+    e2e_ms = 0.0
+    d2h = 0
+    for i in range(max(1, min(args.warmup, 2)) + args.steps):
+        g.clear_reads(); g.reset_results(); flush_l2()
+        g.timer_start()
+        upload()
+        g.run()
+        out = g.export_seqset()
+        ms = g.timer_stop()
+        if i >= max(1, min(args.warmup, 2)):
+            e2e_ms += ms
+        d2h = sum(int(np.asarray(v).nbytes) for v in (out["sizes"], out["shared"], out["prev"], out["fixed"])) + \
+            sum(int(a.nbytes) for a in out["subaccum"]) + sum(int(a.nbytes) for a in out["accum"])
+    barrier()
+    e2e_ms_step = max_over_ranks(e2e_ms / args.steps)
+    e2e_val = total_bases / (e2e_ms_step / 1e3)
+
+    # ---- roofline of the dominant kernel (live CUDA-event time inside the timed steps) -------------------------
+    peak, peak_src = measured_peak_gbs()
+    kern_ms = {k_[3:]: v for k_, v in st_mean.items() if k_.startswith("ms_")}
+    K = st_mean.get("kmer_instances", 0.0)
+    alg = {
+        "count_kernel": bases / 4 + 32.0 * K,                       # SURVEY 8d count, without table init/sweep
+        "correct_kernel": st_mean.get("alg_bytes_correct", 0.0),
+        "sort_radix": st_mean.get("alg_bytes_sort_radix", 0.0),
+    }
+    stages = {}
+    for name, b_ in alg.items():
+        ms = kern_ms.get(name, 0.0)
+        if ms > 0:
+            stages[name] = {"ms": ms, "alg_bytes": b_, "achieved_gbs": b_ / ms / 1e6, "frac": b_ / ms / 1e6 / peak}
+    dom = max(("count_kernel", "correct_kernel", "sort_radix"), key=lambda n_: kern_ms.get(n_, 0.0))
+    roof = {"bound": "hbm", "kernel": dom, "achieved": stages.get(dom, {}).get("achieved_gbs"), "peak": peak,
+            "unit": "GB/s", "frac": stages.get(dom, {}).get("frac"), "traffic": None, "peak_source": peak_src,
+            "stages": stages, "share_of_step": kern_ms.get(dom, 0.0) / (dev_ms / args.steps)}
+    tr = os.path.join(ROOT, "profiles", "traffic.json")
+    if os.path.exists(tr):
+        try:
+            roof["traffic"] = json.load(open(tr)).get(dom)
+        except Exception:
+            pass
+
+    # ---- CPU baseline on a bounded sample (rank 0, N=1 only) -------------------------------------------------------
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        from oracle import oracle as O
+        threads = O.max_threads()
+        sub = make_workload(args.workload, 0, None, genome_prefix_reads=min(n_reads, args.cpu_sample_reads))
+        sample = sub.shape[0]
+        dt, _ = cpu_port_run(sub, threads)
+        cpu = {"value": sample * read_len / dt, "unit": "bases/s", "cores": threads, "kind": "port",
+               "sample": f"{sample} reads at the workload's coverage over a genome prefix (workload has {n_reads}), "
+                         f"whole path (count+correct+staged seqset) once, {dt:.1f} s; oracle port "
+                         "(reference binary not buildable offline)"}
+
+    if rank == 0:
+        line = {
+            "metric": "input bases/sec to finished seqset", "value": value, "unit": "bases/s", "n_gpus": world,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "u64", "data": "synthetic",
+            "config": {"workload": args.workload, "reads_per_gpu": int(n_reads), "read_len": int(read_len),
+                       "bases_per_gpu": bases, "kmer_size": 30, "entries": ss_n,
+                       "parallelism": f"replicas x{world} (independent read sets; sharded build is DESIGN.md 'next')" if world > 1 else "1 gpu",
+                       "l2": "flushed between steps (256 MiB memset); working set >> L2"},
+            "e2e": {"value": e2e_val, "unit": "bases/s", "ms_per_step": e2e_ms_step, "h2d_bytes_per_step": int(h2d),
+                    "d2h_bytes_per_step": int(d2h)},
+            "gpu_launches": int(launches),
+            "roofline": roof,
+            "cpu_baseline": cpu,
+            "clocks": clocks,
+            "wall_s_timed_region": wall_s,
+            "stage_ms": {k_: round(v, 3) for k_, v in sorted(kern_ms.items())},
+        }
+        print(json.dumps(line))
+    g.close()
+    if dist is not None:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -40,7 +40,8 @@ def build_library(force=False):
 EXPORTS = ["bgx_default_options", "bgx_last_error", "bgx_version", "bgx_device_count", "bgx_create", "bgx_destroy",
            "bgx_free", "bgx_add_reads_ascii", "bgx_add_reads_packed", "bgx_count_kmers", "bgx_export_kmers",
            "bgx_correct", "bgx_export_corrected", "bgx_build_seqset", "bgx_export_seqset",
-           "bgx_export_entries_ascii", "bgx_run", "bgx_reset_results", "bgx_clear_reads", "bgx_stats_json"]
+           "bgx_export_entries_ascii", "bgx_run", "bgx_reset_results", "bgx_clear_reads", "bgx_stats_json", "bgx_timer_start", "bgx_timer_stop",
+           "bgx_launch_count"]
 
 
 def load_library():
@@ -74,6 +75,9 @@ def load_library():
     L.bgx_reset_results.argtypes = [vp]
     L.bgx_clear_reads.argtypes = [vp]
     L.bgx_stats_json.argtypes = [vp, C.c_char_p, C.c_size_t]
+    L.bgx_timer_start.argtypes = [vp]
+    L.bgx_timer_stop.argtypes = [vp, C.POINTER(C.c_double)]
+    L.bgx_launch_count.restype = C.c_uint64
     _LIB = L
     return L
 
@@ -82,6 +86,8 @@ def pack_reads_2bit(reads):
     """Host-side packing into the bgx_add_reads_packed layout (dna_sequence byte order, every read
     on an 8-byte boundary) + N mask.  reads: list of str/bytes or (buffer, offsets) pair.
     Returns (packed uint8[8*W], nmask uint32[W] or None, word_offs uint64[n+1], lens uint16[n])."""
+    if isinstance(reads, np.ndarray) and reads.ndim == 2:
+        return _pack_fixed_len(reads)
     if isinstance(reads, tuple):
         buf, offs = reads
         offs = np.asarray(offs, dtype=np.int64)
@@ -121,6 +127,37 @@ def pack_reads_2bit(reads):
                 (bits[:, 2].astype(np.uint32) << 8) | bits[:, 3].astype(np.uint32)
         nmask = np.ascontiguousarray(nmask, dtype=np.uint32)
     return np.ascontiguousarray(packed), nmask, word_offs, lens.astype(np.uint16)
+
+
+def _pack_fixed_len(reads2d, chunk=1 << 18):
+    """fast path of pack_reads_2bit for an [n, L] uint8 ASCII array"""
+    n, L = reads2d.shape
+    wpr = (L + 31) // 32
+    code = np.zeros(256, dtype=np.uint8)
+    isn = np.ones(256, dtype=bool)
+    for i, ch in enumerate(b"ACGT"):
+        code[ch] = i
+        code[ch + 32] = i
+        isn[ch] = isn[ch + 32] = False
+    packed = np.zeros((n, wpr * 8), dtype=np.uint8)
+    nmask = np.zeros((n, wpr), dtype=np.uint32)
+    any_n = False
+    for s0 in range(0, n, chunk):
+        blk = reads2d[s0:s0 + chunk]
+        c = np.zeros((blk.shape[0], wpr * 32), dtype=np.uint8)
+        c[:, :L] = code[blk]
+        c4 = c.reshape(blk.shape[0], wpr * 8, 4)
+        packed[s0:s0 + chunk] = (c4[:, :, 0] << 6) | (c4[:, :, 1] << 4) | (c4[:, :, 2] << 2) | c4[:, :, 3]
+        nf = isn[blk]
+        if nf.any():
+            any_n = True
+            f = np.zeros((blk.shape[0], wpr * 32), dtype=bool)
+            f[:, :L] = nf
+            bits = np.packbits(f.reshape(blk.shape[0], wpr, 32), axis=2, bitorder="big").astype(np.uint32)
+            nmask[s0:s0 + chunk] = (bits[:, :, 0] << 24) | (bits[:, :, 1] << 16) | (bits[:, :, 2] << 8) | bits[:, :, 3]
+    word_offs = (np.arange(n + 1, dtype=np.uint64) * np.uint64(wpr))
+    lens = np.full(n, L, dtype=np.uint16)
+    return packed.reshape(-1), (nmask.reshape(-1) if any_n else None), word_offs, lens
 
 
 class Bgx:
@@ -262,6 +299,17 @@ class Bgx:
 
     def clear_reads(self):
         self._ck(self.L.bgx_clear_reads(self.h))
+
+    def timer_start(self):
+        self._ck(self.L.bgx_timer_start(self.h))
+
+    def timer_stop(self):
+        ms = C.c_double()
+        self._ck(self.L.bgx_timer_stop(self.h, C.byref(ms)))
+        return ms.value
+
+    def launch_count(self):
+        return int(self.L.bgx_launch_count())
 
     def stats(self):
         buf = C.create_string_buffer(1 << 16)

@@ -174,7 +174,7 @@ int bgx_export_corrected(bgx_ctx* x, uint64_t* n_reads, uint16_t** lens, char** 
       DevBuf<uint64_t> d_off(n + 1, s);
       DevBuf<char> d_out(std::max<uint64_t>(off[n], 1), s);
       BGX_CUDA(cudaMemcpyAsync(d_off.p, off.data(), (n + 1) * 8, cudaMemcpyHostToDevice, s));
-      if (n) corrected_ascii_kernel<<<(unsigned)((n * 32 + 255) / 256), 256, 0, s>>>(c->store.p, c->word_off.p, c->clen.p,
+      if (n) KLAUNCH(corrected_ascii_kernel)<<<(unsigned)((n * 32 + 255) / 256), 256, 0, s>>>(c->store.p, c->word_off.p, c->clen.p,
                                                                                   d_off.p, n, d_out.p);
       BGX_CUDA(cudaGetLastError());
       BGX_CUDA(cudaMemcpyAsync(out, d_out.p, off[n], cudaMemcpyDeviceToHost, s));
@@ -253,5 +253,25 @@ int bgx_stats_json(bgx_ctx* x, char* buf, size_t cap) {
     memcpy(buf, sjson.c_str(), sjson.size() + 1);
   })
 }
+
+int bgx_timer_start(bgx_ctx* x) {
+  CTX_GUARD({
+    if (!c->t0) { BGX_CUDA(cudaEventCreate(&c->t0)); BGX_CUDA(cudaEventCreate(&c->t1)); }
+    BGX_CUDA(cudaEventRecord(c->t0, c->stream));
+  })
+}
+
+int bgx_timer_stop(bgx_ctx* x, double* elapsed_ms) {
+  CTX_GUARD({
+    BGX_CHECK(c->t0 != nullptr, "bgx_timer_stop without bgx_timer_start");
+    BGX_CUDA(cudaEventRecord(c->t1, c->stream));
+    BGX_CUDA(cudaEventSynchronize(c->t1));
+    float ms = 0;
+    BGX_CUDA(cudaEventElapsedTime(&ms, c->t0, c->t1));
+    *elapsed_ms = ms;
+  })
+}
+
+uint64_t bgx_launch_count(void) { return __atomic_load_n(&bgx::g_launches, __ATOMIC_RELAXED); }
 
 }  // extern "C"

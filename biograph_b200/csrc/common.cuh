@@ -34,6 +34,12 @@ struct Error : std::runtime_error {
 
 constexpr int kNumSMs = 148;  // B200
 
+// every kernel launch of this library goes through KLAUNCH so that bgx_launch_count() can report
+// how many of OUR kernels ran (bench.py "gpu_launches")
+extern unsigned long long g_launches;
+inline void note_launch() { __atomic_fetch_add(&g_launches, 1ULL, __ATOMIC_RELAXED); }
+#define KLAUNCH(k) (::bgx::note_launch(), (k))
+
 constexpr uint64_t kEmptyKey = ~0ULL;                 // kmer_count_table::k_unused_entry
 constexpr uint64_t kKmerMask = (1ULL << 62) - 1;      // kmer_count_table::k_kmer_mask
 constexpr uint64_t kFwdFlag = 1ULL << 63;             // k_fwd_flag  (fwd_starts_read)

@@ -377,7 +377,7 @@ void stage_correct(Context* c) {
   P.set_mask = c->solid_slots - 1;
   {
     ScopedStage st(c, "correct_kernel");
-    correct_kernel<<<(unsigned)((n + 127) / 128), 128, 0, s>>>(c->words.p, c->has_n ? c->nmask.p : nullptr,
+    KLAUNCH(correct_kernel)<<<(unsigned)((n + 127) / 128), 128, 0, s>>>(c->words.p, c->has_n ? c->nmask.p : nullptr,
                                                               c->word_off.p, c->lens.p, (uint32_t)n, P, c->store.p,
                                                               c->n_words, c->clen.p, c->ncorr.p, c->next_fwd.p,
                                                               c->next_rev.p, seed_cnt.p, totals.p);

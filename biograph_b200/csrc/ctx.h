@@ -24,6 +24,7 @@ struct Context {
   int device = 0;
   cudaStream_t stream = nullptr;
   cudaMemPool_t pool = nullptr;
+  cudaEvent_t t0 = nullptr, t1 = nullptr;  // bgx_timer_start/stop
 
   // ---- reads (device resident) ---------------------------------------------------------
   uint64_t n_reads = 0;

@@ -186,7 +186,7 @@ void stage_count_kmers(Context* c) {
   c->table.alloc(slots, s);
   {
     ScopedStage st(c, "count_init");
-    fill_empty_kernel<<<(unsigned)((slots + 255) / 256), 256, 0, s>>>(reinterpret_cast<uint4*>(c->table.p), slots);
+    KLAUNCH(fill_empty_kernel)<<<(unsigned)((slots + 255) / 256), 256, 0, s>>>(reinterpret_cast<uint4*>(c->table.p), slots);
     st.stop();
   }
   DevBuf<int> overflow(1, s);
@@ -195,7 +195,7 @@ void stage_count_kmers(Context* c) {
     ScopedStage st(c, "count_kernel");
     // persistent-style grid: 148 SMs x 8 resident 256-thread CTAs
     unsigned blocks = (unsigned)std::min<uint64_t>((c->n_reads * 32 + 255) / 256, (uint64_t)kNumSMs * 8);
-    kmer_count_kernel<<<blocks, 256, 0, s>>>(c->words.p, c->has_n ? c->nmask.p : nullptr, c->word_off.p, c->lens.p,
+    KLAUNCH(kmer_count_kernel)<<<blocks, 256, 0, s>>>(c->words.p, c->has_n ? c->nmask.p : nullptr, c->word_off.p, c->lens.p,
                                              (uint32_t)c->n_reads, k, c->table.p, slots - 1, overflow.p);
     BGX_CUDA(cudaGetLastError());
     st.stop();
@@ -212,7 +212,7 @@ void stage_count_kmers(Context* c) {
   {
     ScopedStage st(c, "count_filter");
     BGX_CUDA(cudaMemsetAsync(counters.p, 0, 2 * sizeof(unsigned long long), s));
-    table_sweep_kernel<<<(unsigned)((slots + 255) / 256), 256, 0, s>>>(c->table.p, slots, (uint32_t)c->opt.min_kmer_count,
+    KLAUNCH(table_sweep_kernel)<<<(unsigned)((slots + 255) / 256), 256, 0, s>>>(c->table.p, slots, (uint32_t)c->opt.min_kmer_count,
                                                                      counters.p, nullptr, nullptr);
     BGX_CUDA(cudaMemcpyAsync(h_cnt, counters.p, sizeof(h_cnt), cudaMemcpyDeviceToHost, s));
     BGX_CUDA(cudaStreamSynchronize(s));
@@ -221,13 +221,13 @@ void stage_count_kmers(Context* c) {
     // "Too many kmers for kmer table!" (kmer_set.cpp:554-556) has no analogue: the set is sized to fit.
     DevBuf<unsigned long long> sk(c->n_solid, s), sc(c->n_solid, s);
     BGX_CUDA(cudaMemsetAsync(counters.p, 0, 2 * sizeof(unsigned long long), s));
-    table_sweep_kernel<<<(unsigned)((slots + 255) / 256), 256, 0, s>>>(c->table.p, slots, (uint32_t)c->opt.min_kmer_count,
+    KLAUNCH(table_sweep_kernel)<<<(unsigned)((slots + 255) / 256), 256, 0, s>>>(c->table.p, slots, (uint32_t)c->opt.min_kmer_count,
                                                                      counters.p, sk.p, sc.p);
     c->solid_slots = pow2_ceil(std::max<uint64_t>(1024, c->n_solid * 2));
     c->solid.alloc(c->solid_slots, s);
-    fill_u64_kernel<<<(unsigned)((c->solid_slots + 255) / 256), 256, 0, s>>>(c->solid.p, c->solid_slots, kEmptyKey);
+    KLAUNCH(fill_u64_kernel)<<<(unsigned)((c->solid_slots + 255) / 256), 256, 0, s>>>(c->solid.p, c->solid_slots, kEmptyKey);
     if (c->n_solid)
-      solid_insert_kernel<<<(unsigned)((c->n_solid + 255) / 256), 256, 0, s>>>(sk.p, c->n_solid, c->solid.p,
+      KLAUNCH(solid_insert_kernel)<<<(unsigned)((c->n_solid + 255) / 256), 256, 0, s>>>(sk.p, c->n_solid, c->solid.p,
                                                                              c->solid_slots - 1);
     BGX_CUDA(cudaGetLastError());
     st.stop();
@@ -251,7 +251,7 @@ void export_kmers(Context* c, uint32_t min_count, uint64_t* n_out, uint64_t** km
   DevBuf<unsigned long long> counters(2, s);
   unsigned long long h_cnt[2];
   BGX_CUDA(cudaMemsetAsync(counters.p, 0, 2 * sizeof(unsigned long long), s));
-  table_sweep_kernel<<<(unsigned)((slots + 255) / 256), 256, 0, s>>>(c->table.p, slots, min_count, counters.p, nullptr,
+  KLAUNCH(table_sweep_kernel)<<<(unsigned)((slots + 255) / 256), 256, 0, s>>>(c->table.p, slots, min_count, counters.p, nullptr,
                                                                    nullptr);
   BGX_CUDA(cudaMemcpyAsync(h_cnt, counters.p, sizeof(h_cnt), cudaMemcpyDeviceToHost, s));
   BGX_CUDA(cudaStreamSynchronize(s));
@@ -265,16 +265,16 @@ void export_kmers(Context* c, uint32_t min_count, uint64_t* n_out, uint64_t** km
   if (n == 0) return;
   DevBuf<unsigned long long> ek(n, s), ec(n, s);
   BGX_CUDA(cudaMemsetAsync(counters.p, 0, 2 * sizeof(unsigned long long), s));
-  table_sweep_kernel<<<(unsigned)((slots + 255) / 256), 256, 0, s>>>(c->table.p, slots, min_count, counters.p, ek.p, ec.p);
+  KLAUNCH(table_sweep_kernel)<<<(unsigned)((slots + 255) / 256), 256, 0, s>>>(c->table.p, slots, min_count, counters.p, ek.p, ec.p);
   DevBuf<uint64_t> k0(n, s), v0(n, s), k1(n, s), v1(n, s);
   unsigned g = (unsigned)((n + 255) / 256);
-  export_prepare_kernel<<<g, 256, 0, s>>>(ek.p, n, k0.p, v0.p);
+  KLAUNCH(export_prepare_kernel)<<<g, 256, 0, s>>>(ek.p, n, k0.p, v0.p);
   int bits = ((2 * c->opt.kmer_size + 7) / 8) * 8;
   bool alt = radix_sort_pairs(k0.p, v0.p, k1.p, v1.p, n, 0, bits, s);
   DevBuf<uint64_t> dk(n, s);
   DevBuf<uint32_t> df(n, s), dr(n, s);
   DevBuf<uint8_t> dfl(n, s);
-  export_gather_kernel<<<g, 256, 0, s>>>(alt ? k1.p : k0.p, alt ? v1.p : v0.p, ek.p, ec.p, n, dk.p, df.p, dr.p, dfl.p);
+  KLAUNCH(export_gather_kernel)<<<g, 256, 0, s>>>(alt ? k1.p : k0.p, alt ? v1.p : v0.p, ek.p, ec.p, n, dk.p, df.p, dr.p, dfl.p);
   BGX_CUDA(cudaGetLastError());
   BGX_CUDA(cudaMemcpyAsync(*kmers, dk.p, n * 8, cudaMemcpyDeviceToHost, s));
   BGX_CUDA(cudaMemcpyAsync(*fwd, df.p, n * 4, cudaMemcpyDeviceToHost, s));

@@ -3,6 +3,8 @@
 
 namespace bgx {
 
+unsigned long long g_launches = 0;
+
 void* dev_alloc(size_t bytes, cudaStream_t s) {
   void* p = nullptr;
   BGX_CUDA(cudaMallocAsync(&p, bytes, s));
@@ -229,9 +231,9 @@ void exclusive_scan_u32(const uint32_t* in, uint32_t* out, size_t n, uint32_t* t
   }
   size_t nb = (n + SC_TILE - 1) / SC_TILE;
   DevBuf<uint32_t> block_sums(nb, s);
-  scan_reduce_kernel<<<(unsigned)nb, SC_THREADS, 0, s>>>(in, block_sums.p, n);
-  scan_blocksums_kernel<<<1, 1024, 0, s>>>(block_sums.p, nb, total_out);
-  scan_final_kernel<<<(unsigned)nb, SC_THREADS, 0, s>>>(in, out, block_sums.p, n);
+  KLAUNCH(scan_reduce_kernel)<<<(unsigned)nb, SC_THREADS, 0, s>>>(in, block_sums.p, n);
+  KLAUNCH(scan_blocksums_kernel)<<<1, 1024, 0, s>>>(block_sums.p, nb, total_out);
+  KLAUNCH(scan_final_kernel)<<<(unsigned)nb, SC_THREADS, 0, s>>>(in, out, block_sums.p, n);
   BGX_CUDA(cudaGetLastError());
 }
 
@@ -255,9 +257,9 @@ bool radix_sort_pairs(uint64_t* keys, uint64_t* vals, uint64_t* keys_alt, uint64
     const uint64_t* vi = in_alt ? vals_alt : vals;
     uint64_t* ko = in_alt ? keys : keys_alt;
     uint64_t* vo = in_alt ? vals : vals_alt;
-    radix_count_kernel<<<ntiles, RS_THREADS, 0, s>>>(ki, counts.p, (uint32_t)n, shift, ntiles);
+    KLAUNCH(radix_count_kernel)<<<ntiles, RS_THREADS, 0, s>>>(ki, counts.p, (uint32_t)n, shift, ntiles);
     exclusive_scan_u32(counts.p, counts.p, (size_t)RADIX * ntiles, nullptr, s);
-    radix_scatter_kernel<<<ntiles, RS_THREADS, RS_TILE * sizeof(uint64_t), s>>>(ki, vi, ko, vo, counts.p,
+    KLAUNCH(radix_scatter_kernel)<<<ntiles, RS_THREADS, RS_TILE * sizeof(uint64_t), s>>>(ki, vi, ko, vo, counts.p,
                                                                                (uint32_t)n, shift, ntiles);
     BGX_CUDA(cudaGetLastError());
     in_alt = !in_alt;

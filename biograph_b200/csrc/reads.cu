@@ -138,7 +138,7 @@ void reads_append_ascii(Context* c, const char* bases, const uint64_t* offs, uin
   BGX_CUDA(cudaMemcpyAsync(c->word_off.p + c->n_reads, woff.data(), (n + 1) * sizeof(uint32_t),
                            cudaMemcpyHostToDevice, s));
   uint64_t threads = n * 32;
-  pack_ascii_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, s>>>(d_bases.p, d_offs.p, n,
+  KLAUNCH(pack_ascii_kernel)<<<(unsigned)((threads + 255) / 256), 256, 0, s>>>(d_bases.p, d_offs.p, n,
                                                                       c->word_off.p + c->n_reads, c->words.p,
                                                                       c->nmask.p, d_flag.p);
   BGX_CUDA(cudaGetLastError());
@@ -165,11 +165,11 @@ void reads_append_packed(Context* c, const uint8_t* packed, const uint32_t* n_ma
   BGX_CUDA(cudaMemsetAsync(d_flag.p, 0, sizeof(int), s));
   BGX_CUDA(cudaMemcpyAsync(c->words.p + words_before, packed + 8 * word_offs[0], new_words * 8,
                            cudaMemcpyHostToDevice, s));
-  if (new_words) bswap_words_kernel<<<(unsigned)((new_words + 255) / 256), 256, 0, s>>>(c->words.p + words_before, new_words);
+  if (new_words) KLAUNCH(bswap_words_kernel)<<<(unsigned)((new_words + 255) / 256), 256, 0, s>>>(c->words.p + words_before, new_words);
   if (n_mask) {
     BGX_CUDA(cudaMemcpyAsync(c->nmask.p + words_before, n_mask + word_offs[0], new_words * 4,
                              cudaMemcpyHostToDevice, s));
-    if (new_words) any_nonzero_kernel<<<(unsigned)((new_words + 255) / 256), 256, 0, s>>>(c->nmask.p + words_before, new_words, d_flag.p);
+    if (new_words) KLAUNCH(any_nonzero_kernel)<<<(unsigned)((new_words + 255) / 256), 256, 0, s>>>(c->nmask.p + words_before, new_words, d_flag.p);
   } else {
     BGX_CUDA(cudaMemsetAsync(c->nmask.p + words_before, 0, new_words * 4, s));
   }

@@ -438,7 +438,7 @@ void sort_records(Context* c, DevBuf<uint64_t>& keys, DevBuf<uint64_t>& locs, De
   BGX_CUDA(cudaMemsetAsync(n_big.p, 0, 8, s));
   int small_limit = kSmallGroup;
   if (const char* e = getenv("BGX_SMALL_GROUP")) small_limit = std::max(1, atoi(e));  // test hook: force the refinement path
-  tie_small_kernel<<<grid_for(n, 128), 128, 0, s>>>(c->store.p, keys.p, locs.p, n, sbits, small_limit, big_flag.p,
+  KLAUNCH(tie_small_kernel)<<<grid_for(n, 128), 128, 0, s>>>(c->store.p, keys.p, locs.p, n, sbits, small_limit, big_flag.p,
                                                    n_big.p);
   BGX_CUDA(cudaGetLastError());
   uint32_t m = (uint32_t)read_u64(n_big.p, s);
@@ -448,24 +448,24 @@ void sort_records(Context* c, DevBuf<uint64_t>& keys, DevBuf<uint64_t>& locs, De
     DevBuf<uint32_t> big_pos(n, s);
     exclusive_scan_u32(big_flag.p, big_pos.p, n, nullptr, s);
     DevBuf<uint32_t> midx(m, s), head(m, s);
-    refine_init_kernel<<<grid_for(n, 256), 256, 0, s>>>(big_flag.p, big_pos.p, keys.p, n, sbits, midx.p, head.p);
+    KLAUNCH(refine_init_kernel)<<<grid_for(n, 256), 256, 0, s>>>(big_flag.p, big_pos.p, keys.p, n, sbits, midx.p, head.p);
     int D = sbits / 2;
     int rounds = 0;
     while (m) {
       DevBuf<uint32_t> gid(m, s);
       exclusive_scan_u32(head.p, gid.p, m, nullptr, s);
       DevBuf<uint64_t> ck(m, s), cl(m, s), ck2(m, s), cl2(m, s);
-      refine_key_kernel<<<grid_for(m, 256), 256, 0, s>>>(c->store.p, locs.p, midx.p, gid.p, head.p, m, D, ck.p, cl.p);
+      KLAUNCH(refine_key_kernel)<<<grid_for(m, 256), 256, 0, s>>>(c->store.p, locs.p, midx.p, gid.p, head.p, m, D, ck.p, cl.p);
       bool alt = radix_sort_pairs(ck.p, cl.p, ck2.p, cl2.p, m, 0, 64, s);
       DevBuf<uint32_t> tied(m, s), nhead(m, s), tpos(m, s), tot(1, s);
-      refine_writeback_kernel<<<grid_for(m, 256), 256, 0, s>>>(c->store.p, alt ? ck2.p : ck.p, alt ? cl2.p : cl.p, midx.p,
+      KLAUNCH(refine_writeback_kernel)<<<grid_for(m, 256), 256, 0, s>>>(c->store.p, alt ? ck2.p : ck.p, alt ? cl2.p : cl.p, midx.p,
                                                               m, D, keys.p, locs.p, tied.p, nhead.p);
       exclusive_scan_u32(tied.p, tpos.p, m, tot.p, s);
       BGX_CUDA(cudaGetLastError());
       uint32_t m2 = read_u32(tot.p, s);
       DevBuf<uint32_t> midx2(std::max<uint32_t>(m2, 1), s), head2(std::max<uint32_t>(m2, 1), s);
       if (m2)
-        refine_compact_kernel<<<grid_for(m, 256), 256, 0, s>>>(tied.p, tpos.p, midx.p, nhead.p, m, midx2.p, head2.p);
+        KLAUNCH(refine_compact_kernel)<<<grid_for(m, 256), 256, 0, s>>>(tied.p, tpos.p, midx.p, nhead.p, m, midx2.p, head2.p);
       midx = std::move(midx2);
       head = std::move(head2);
       m = m2;
@@ -486,9 +486,9 @@ uint32_t dedup_records(Context* c, DevBuf<uint64_t>& keys, DevBuf<uint64_t>& loc
   if (n == 0) return 0;
   ScopedStage st(c, "dedup");
   DevBuf<uint32_t> keep(n, s), pos(n, s), tot(1, s);
-  dedup_flag_kernel<<<grid_for(n, 256), 256, 0, s>>>(c->store.p, keys.p, locs.p, n, keep.p);
+  KLAUNCH(dedup_flag_kernel)<<<grid_for(n, 256), 256, 0, s>>>(c->store.p, keys.p, locs.p, n, keep.p);
   exclusive_scan_u32(keep.p, pos.p, n, tot.p, s);
-  compact_pairs_kernel<<<grid_for(n, 256), 256, 0, s>>>(keys.p, locs.p, keep.p, pos.p, n, keys_alt.p, locs_alt.p);
+  KLAUNCH(compact_pairs_kernel)<<<grid_for(n, 256), 256, 0, s>>>(keys.p, locs.p, keep.p, pos.p, n, keys_alt.p, locs_alt.p);
   BGX_CUDA(cudaGetLastError());
   uint32_t m = read_u32(tot.p, s);
   std::swap(keys, keys_alt);
@@ -514,9 +514,9 @@ void stage_build_seqset(Context* c) {
   {
     ScopedStage st(c, "seed_emit");
     DevBuf<uint32_t> cnt(n_reads, s), off(n_reads, s);
-    seed_count_kernel<<<grid_for(n_reads, 256), 256, 0, s>>>(c->clen.p, c->next_fwd.p, c->next_rev.p, n_reads, cnt.p);
+    KLAUNCH(seed_count_kernel)<<<grid_for(n_reads, 256), 256, 0, s>>>(c->clen.p, c->next_fwd.p, c->next_rev.p, n_reads, cnt.p);
     exclusive_scan_u32(cnt.p, off.p, n_reads, nullptr, s);
-    seed_emit_kernel<<<grid_for(n_reads, 128), 128, 0, s>>>(c->store.p, c->n_words, c->word_off.p, c->clen.p,
+    KLAUNCH(seed_emit_kernel)<<<grid_for(n_reads, 128), 128, 0, s>>>(c->store.p, c->n_words, c->word_off.p, c->clen.p,
                                                             c->next_fwd.p, c->next_rev.p, off.p, n_reads, keys.p, locs.p);
     BGX_CUDA(cudaGetLastError());
     st.stop();
@@ -534,13 +534,13 @@ void stage_build_seqset(Context* c) {
     DevBuf<uint32_t> chains(std::max<uint32_t>(n1, 1), s);
     DevBuf<unsigned long long> n_chains_d(1, s);
     BGX_CUDA(cudaMemsetAsync(n_chains_d.p, 0, 8, s));
-    walk_phase1_kernel<<<grid_for(n1, 128), 128, 0, s>>>(c->store.p, keys.p, locs.p, n1, chains.p, n_chains_d.p);
+    KLAUNCH(walk_phase1_kernel)<<<grid_for(n1, 128), 128, 0, s>>>(c->store.p, keys.p, locs.p, n1, chains.p, n_chains_d.p);
     BGX_CUDA(cudaGetLastError());
     uint32_t n_chains = (uint32_t)read_u64(n_chains_d.p, s);
     c->set_stat("walk_chains", n_chains);
     if (n_chains) {
       DevBuf<uint32_t> ccnt(n_chains, s), coff(n_chains, s), tot(1, s);
-      walk_phase2_kernel<<<grid_for((uint64_t)n_chains * 32, 128), 128, 0, s>>>(c->store.p, keys.p, locs.p, n1, chains.p,
+      KLAUNCH(walk_phase2_kernel)<<<grid_for((uint64_t)n_chains * 32, 128), 128, 0, s>>>(c->store.p, keys.p, locs.p, n1, chains.p,
                                                                                 n_chains, ccnt.p);
       exclusive_scan_u32(ccnt.p, coff.p, n_chains, tot.p, s);
       BGX_CUDA(cudaGetLastError());
@@ -556,7 +556,7 @@ void stage_build_seqset(Context* c) {
         keys_alt.alloc(need + 1024, s);
         locs_alt.alloc(need + 1024, s);
       }
-      walk_emit_kernel<<<grid_for((uint64_t)n_chains * 32, 128), 128, 0, s>>>(c->store.p, locs.p, chains.p, ccnt.p, coff.p,
+      KLAUNCH(walk_emit_kernel)<<<grid_for((uint64_t)n_chains * 32, 128), 128, 0, s>>>(c->store.p, locs.p, chains.p, ccnt.p, coff.p,
                                                                               n_chains, keys.p + n1, locs.p + n1);
       BGX_CUDA(cudaGetLastError());
     }
@@ -592,17 +592,17 @@ void stage_build_seqset(Context* c) {
     BGX_CUDA(cudaMemsetAsync(max_len.p, 0, 4, s));
     BGX_CUDA(cudaMemsetAsync(missing.p, 0, 4, s));
     if (nb) {
-      tables_kernel<<<grid_for(nb, 128), 128, 0, s>>>(c->store.p, keys.p, locs.p, n2, c->sizes.p, c->shared.p,
+      KLAUNCH(tables_kernel)<<<grid_for(nb, 128), 128, 0, s>>>(c->store.p, keys.p, locs.p, n2, c->sizes.p, c->shared.p,
                                                       reinterpret_cast<unsigned long long*>(c->prev_bits.p),
                                                       c->prev_words, max_len.p, missing.p);
       DevBuf<uint32_t> gpop(c->sub_words, s), gex(c->sub_words, s), tot(1, s);
       uint64_t off = 0;
       for (int b = 0; b < 4; ++b) {
-        bitcount_groups_kernel<<<grid_for(c->sub_words, 256), 256, 0, s>>>(
+        KLAUNCH(bitcount_groups_kernel)<<<grid_for(c->sub_words, 256), 256, 0, s>>>(
             reinterpret_cast<unsigned long long*>(c->prev_bits.p) + b * c->prev_words, c->prev_words, c->sub_words, gpop.p,
             reinterpret_cast<unsigned long long*>(c->prev_sub.p) + b * c->sub_words);
         exclusive_scan_u32(gpop.p, gex.p, c->sub_words, tot.p, s);
-        bitcount_accum_kernel<<<grid_for(c->acc_words, 256), 256, 0, s>>>(
+        KLAUNCH(bitcount_accum_kernel)<<<grid_for(c->acc_words, 256), 256, 0, s>>>(
             gex.p, tot.p, c->sub_words, c->acc_words, reinterpret_cast<unsigned long long*>(c->prev_acc.p) + b * c->acc_words);
         BGX_CUDA(cudaGetLastError());
         c->fixed[b] = off;
@@ -636,7 +636,7 @@ void export_entries_ascii(Context* c, uint64_t first, uint64_t count, char** bas
   std::vector<uint32_t> lens(count);
   DevBuf<uint32_t> d_lens(std::max<uint64_t>(count, 1), s);
   if (count) {
-    entry_offs_kernel<<<grid_for(count, 256), 256, 0, s>>>(c->ent_loc.p, first, count, d_lens.p);
+    KLAUNCH(entry_offs_kernel)<<<grid_for(count, 256), 256, 0, s>>>(c->ent_loc.p, first, count, d_lens.p);
     BGX_CUDA(cudaMemcpyAsync(lens.data(), d_lens.p, count * 4, cudaMemcpyDeviceToHost, s));
     BGX_CUDA(cudaStreamSynchronize(s));
   }
@@ -648,7 +648,7 @@ void export_entries_ascii(Context* c, uint64_t first, uint64_t count, char** bas
     DevBuf<uint64_t> d_offs(count + 1, s);
     DevBuf<char> d_out(std::max<uint64_t>(offs[count], 1), s);
     BGX_CUDA(cudaMemcpyAsync(d_offs.p, offs, (count + 1) * 8, cudaMemcpyHostToDevice, s));
-    entries_ascii_kernel<<<grid_for(count, 128), 128, 0, s>>>(c->store.p, c->ent_loc.p, d_offs.p, first, count, d_out.p);
+    KLAUNCH(entries_ascii_kernel)<<<grid_for(count, 128), 128, 0, s>>>(c->store.p, c->ent_loc.p, d_offs.p, first, count, d_out.p);
     BGX_CUDA(cudaMemcpyAsync(out, d_out.p, offs[count], cudaMemcpyDeviceToHost, s));
     BGX_CUDA(cudaStreamSynchronize(s));
   }

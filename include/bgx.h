@@ -128,6 +128,14 @@ int bgx_clear_reads(bgx_ctx* ctx);
  * per kernel family) into buf; returns non-zero if cap is too small. */
 int bgx_stats_json(bgx_ctx* ctx, char* buf, size_t cap);
 
+/* Measurement hooks (no reference analogue).  bgx_timer_start/stop bracket a region with CUDA
+ * events on the context's own stream (the stream every kernel and copy of this library is issued
+ * on), so host-side gaps between enqueues are inside the measured span.  bgx_launch_count is the
+ * process-wide number of kernels this library has launched. */
+int bgx_timer_start(bgx_ctx* ctx);
+int bgx_timer_stop(bgx_ctx* ctx, double* elapsed_ms);
+uint64_t bgx_launch_count(void);
+
 #ifdef __cplusplus
 }
 #endif
