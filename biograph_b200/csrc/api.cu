@@ -1,6 +1,7 @@
 // api.cu -- the C ABI (include/bgx.h) over the CUDA stages.  No CPU fallback: every entry
 // point needs a CUDA device and fails loudly without one.
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <sstream>
 #include <vector>
@@ -95,6 +96,13 @@ int bgx_create(const bgx_options* opts, bgx_ctx** out) {
     BGX_CHECK(e == cudaSuccess && ndev > 0, "no CUDA device: bgx has no CPU fallback");
     BGX_CHECK(o.device >= 0 && o.device < ndev, "bad device ordinal");
     BGX_CUDA(cudaSetDevice(o.device));
+    {
+      // The hot tables are probed at random: ask L2 to fetch 32-byte sectors instead of
+      // promoting misses to 64/128 bytes (hint; BGX_L2_FETCH overrides for experiments).
+      size_t gran = 32;
+      if (const char* e = getenv("BGX_L2_FETCH")) gran = (size_t)atoi(e);
+      if (gran) cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, gran);
+    }
     bgx_ctx* x = new bgx_ctx();
     x->c.opt = o;
     x->c.device = o.device;
