@@ -107,9 +107,6 @@ int bgx_create(const bgx_options* opts, bgx_ctx** out) {
     x->c.opt = o;
     x->c.device = o.device;
     BGX_CUDA(cudaStreamCreateWithFlags(&x->c.stream, cudaStreamNonBlocking));
-    BGX_CUDA(cudaDeviceGetDefaultMemPool(&x->c.pool, o.device));
-    uint64_t thresh = ~0ULL;  // keep freed blocks in the pool: stage buffers are reused across runs
-    BGX_CUDA(cudaMemPoolSetAttribute(x->c.pool, cudaMemPoolAttrReleaseThreshold, &thresh));
     *out = x;
   });
 }
@@ -127,7 +124,7 @@ void bgx_destroy(bgx_ctx* x) {
     c.next_fwd.release(); c.next_rev.release(); c.ent_key.release(); c.ent_loc.release();
     c.sizes.release(); c.shared.release(); c.prev_bits.release(); c.prev_sub.release(); c.prev_acc.release();
   }
-  cudaStreamSynchronize(s);
+  dev_trim(s);
   cudaStreamDestroy(s);
   delete x;
 }

@@ -100,6 +100,38 @@ __device__ __forceinline__ uint64_t mix64(uint64_t x) {
 
 __device__ __forceinline__ unsigned lane_id() { return threadIdx.x & 31; }
 
+__device__ __forceinline__ uint32_t warp_incl_scan_u32(uint32_t v) {
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    uint32_t t = __shfl_up_sync(0xffffffffu, v, o);
+    if (lane_id() >= o) v += t;
+  }
+  return v;
+}
+
+// block-wide exclusive scan of one value per thread (blockDim.x <= 1024, a multiple of 32);
+// returns the exclusive prefix, *total = block sum.  Ends with a barrier, so it can be called
+// back to back.
+__device__ __forceinline__ uint32_t block_excl_scan_u32(uint32_t v, uint32_t* total) {
+  __shared__ uint32_t wsum[32];
+  __shared__ uint32_t tot;
+  unsigned lane = lane_id(), warp = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
+  uint32_t inc = warp_incl_scan_u32(v);
+  if (lane == 31) wsum[warp] = inc;
+  __syncthreads();
+  if (warp == 0) {
+    uint32_t w = lane < nw ? wsum[lane] : 0;
+    uint32_t wi = warp_incl_scan_u32(w);
+    wsum[lane] = wi - w;
+    if (lane == 31) tot = wi;
+  }
+  __syncthreads();
+  uint32_t r = wsum[warp] + inc - v;
+  *total = tot;
+  __syncthreads();
+  return r;
+}
+
 // streaming 128-bit loads/stores that do not pollute L1
 __device__ __forceinline__ uint4 ld_stream_u4(const uint4* p) {
   uint4 r;

@@ -23,7 +23,6 @@ struct Context {
   bgx_options opt{};
   int device = 0;
   cudaStream_t stream = nullptr;
-  cudaMemPool_t pool = nullptr;
   cudaEvent_t t0 = nullptr, t1 = nullptr;  // bgx_timer_start/stop
 
   // ---- reads (device resident) ---------------------------------------------------------

@@ -21,101 +21,252 @@
 namespace bgx {
 namespace {
 
-__device__ __forceinline__ void table_upsert(CountEntry* __restrict__ table, uint64_t slot_mask, uint64_t canon,
-                                             bool flipped, uint64_t flags, int* __restrict__ overflow) {
-  uint64_t slot = mix64(canon) & slot_mask;
-  for (uint64_t probes = 0;; ++probes) {
-    unsigned long long cur = *reinterpret_cast<volatile unsigned long long*>(&table[slot].key);
-    if (cur == kEmptyKey) {
-      unsigned long long old = atomicCAS(&table[slot].key, (unsigned long long)kEmptyKey,
-                                         (unsigned long long)(canon | flags));
-      if (old == kEmptyKey) { flags = 0; break; }
-      cur = old;
+// ---- partitioned counting -------------------------------------------------------------------
+// A k-mer instance travels between the two kernels as one 8-byte word:
+//   bits 0..2k-1 the k-mer as seen in the read (NOT canonical), bit 63 = first k-mer of its read,
+//   bit 62 = last k-mer of its read (bs/kmer_counter.h:318-321).  k <= 31, so the fields never meet.
+constexpr uint64_t kPkFirst = 1ULL << 63;
+constexpr uint64_t kPkLast = 1ULL << 62;
+constexpr int kMaxPartBits = 10;            // <= 1024 hash partitions
+constexpr int kPartThreads = 256;
+constexpr int kPartWarps = kPartThreads / 32;
+
+// The table slot of a k-mer is the TOP bits of its hash, so the top part_bits bits (its partition)
+// select a contiguous 1/P slice of the table.
+__device__ __forceinline__ uint64_t table_slot(uint64_t h, int log2_slots) { return h >> (64 - log2_slots); }
+
+// Pass 1: extract every k-mer instance, bucket it by hash partition.
+//   * the block's reads (kPartWarps*RPW consecutive reads) are pulled into shared memory with
+//     128-bit coalesced loads; a warp takes one read at a time, lane l forms the k-mers at
+//     positions l, l+32, ... by funnel shifts (semantics of pass_processor::add,
+//     bs/kmer_counter.h:297-326: a window containing 'N' is skipped)
+//   * rank within (tile, partition) from a shared-memory histogram, tile staged in partition
+//     order, one global cursor bump per (block, partition), coalesced per-partition runs out
+//   * fused distinct-k-mer estimate: linear counting over the 1/16 of hash space whose low 4
+//     hash bits are zero (sizes the table; sampling by hash value is unbiased for distinct counts)
+// Partition p owns out[part_base[p] .. part_base[p] + cap).  cursors[] keep counting past cap, so
+// after an overflowing run they are the exact histogram for the exact re-run.
+template <int MAXIT, int RPW>
+__global__ void __launch_bounds__(kPartThreads, (MAXIT <= 4 ? 4 : 2))
+kmer_partition_kernel(const uint64_t* __restrict__ words, const uint32_t* __restrict__ nmask,
+                      const uint32_t* __restrict__ word_off, const uint16_t* __restrict__ lens, uint32_t n_reads,
+                      int k, int part_bits, unsigned long long* __restrict__ cursors,
+                      const unsigned long long* __restrict__ part_base, unsigned long long cap,
+                      unsigned long long* __restrict__ out, unsigned int* __restrict__ bitmap, uint64_t bit_mask,
+                      int* __restrict__ overflow) {
+  constexpr int kTileReads = kPartWarps * RPW;
+  constexpr int kTileKmers = kTileReads * MAXIT * 32;
+  constexpr int kWordsPerRead = MAXIT + 1;          // MAXIT*32 k-mers of k<=31 bases span <= MAXIT+1 words
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  unsigned long long* stage = reinterpret_cast<unsigned long long*>(smem_raw);            // kTileKmers
+  uint64_t* rwords = reinterpret_cast<uint64_t*>(stage + kTileKmers);                     // kTileReads*kWordsPerRead + 2
+  uint32_t* rmask = reinterpret_cast<uint32_t*>(rwords + kTileReads * kWordsPerRead + 2); // same count
+  uint16_t* stage_bin = reinterpret_cast<uint16_t*>(rmask + kTileReads * kWordsPerRead + 2);  // kTileKmers
+  const int P = 1 << part_bits;
+  unsigned long long* gdst = reinterpret_cast<unsigned long long*>(stage_bin + kTileKmers);   // P
+  uint32_t* hist = reinterpret_cast<uint32_t*>(gdst + P);                                     // P
+  uint32_t* bin_start = hist + P;                                                             // P
+  __shared__ uint32_t tile_word0, tile_nwords;
+
+  const unsigned tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const uint32_t n_tiles = (n_reads + kTileReads - 1) / kTileReads;
+
+  for (uint32_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+    const uint32_t r0 = tile * kTileReads;
+    const uint32_t r1 = min(n_reads, r0 + kTileReads);
+    for (int d = tid; d < P; d += kPartThreads) hist[d] = 0;
+    if (tid == 0) {
+      tile_word0 = word_off[r0] & ~1u;  // 16-byte aligned start
+      tile_nwords = word_off[r1] - (word_off[r0] & ~1u);
     }
-    if ((cur & kKmerMask) == canon) {
-      flags &= ~cur;
-      break;
+    __syncthreads();
+    {
+      // 128-bit coalesced loads of the tile's packed reads (+ N mask) into shared memory
+      const uint32_t w0 = tile_word0, nw2 = (tile_nwords + 1) >> 1;
+      const uint4* src = reinterpret_cast<const uint4*>(words + w0);
+      uint4* dst = reinterpret_cast<uint4*>(rwords);
+      for (uint32_t i = tid; i < nw2; i += kPartThreads) dst[i] = ld_stream_u4(src + i);
+      if (nmask != nullptr) {
+        const uint2* msrc = reinterpret_cast<const uint2*>(nmask + w0);
+        uint2* mdst = reinterpret_cast<uint2*>(rmask);
+        for (uint32_t i = tid; i < nw2; i += kPartThreads) mdst[i] = msrc[i];
+      }
     }
-    slot = (slot + 1) & slot_mask;
-    if (probes > slot_mask) { *overflow = 1; return; }
+    __syncthreads();
+
+    unsigned long long kw[RPW * MAXIT];
+    uint32_t br[RPW * MAXIT];  // bin << 16 | rank ; 0xffffffff = no k-mer
+#pragma unroll
+    for (int q = 0; q < RPW; ++q) {
+      const uint32_t r = r0 + warp * RPW + q;
+      int nk = 0;
+      uint32_t wb = 0;
+      if (r < r1) {
+        nk = (int)lens[r] - k + 1;
+        wb = word_off[r] - tile_word0;
+      }
+#pragma unroll
+      for (int it = 0; it < MAXIT; ++it) {
+        const int p = it * 32 + (int)lane;
+        uint32_t code = 0xffffffffu;
+        unsigned long long word = 0;
+        if (p < nk) {
+          const uint64_t hi = rwords[wb + it], lo = rwords[wb + it + 1];
+          const unsigned s = lane * 2;
+          const uint64_t win = s ? ((hi << s) | (lo >> (64 - s))) : hi;
+          bool has_n = false;
+          if (nmask != nullptr) {
+            const uint32_t mh = rmask[wb + it], ml = rmask[wb + it + 1];
+            const uint32_t mwin = lane ? ((mh << lane) | (ml >> (32 - lane))) : mh;
+            has_n = (mwin >> (32 - k)) != 0;  // an 'N' inside the window (bs/kmer_counter.h:306-311)
+          }
+          if (!has_n) {
+            const uint64_t kmer = win >> (64 - 2 * k);
+            bool flipped;
+            const uint64_t canon = canonicalize(kmer, k, flipped);
+            const uint64_t h = mix64(canon);
+            const uint32_t bin = (uint32_t)(h >> (64 - part_bits));
+            const uint32_t rank = atomicAdd(&hist[bin], 1u);
+            code = (bin << 16) | rank;
+            word = kmer | (p == 0 ? kPkFirst : 0ULL) | (p == nk - 1 ? kPkLast : 0ULL);
+            if ((h & 15) == 0) {
+              const uint64_t bit = (h >> 4) & bit_mask;
+              atomicOr(&bitmap[bit >> 5], 1u << (bit & 31));  // RED: fire and forget, no read-back stall
+            }
+          }
+        }
+        kw[q * MAXIT + it] = word;
+        br[q * MAXIT + it] = code;
+      }
+    }
+    __syncthreads();
+    // exclusive scan of the tile histogram; one cursor bump per non-empty partition
+    {
+      const int per = (P + kPartThreads - 1) / kPartThreads;  // 1..4
+      uint32_t loc[4];
+      uint32_t sum = 0;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int d = (int)tid * per + j;
+        loc[j] = (j < per && d < P) ? hist[d] : 0u;
+        sum += loc[j];
+      }
+      uint32_t tot;
+      uint32_t ex = block_excl_scan_u32(sum, &tot);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int d = (int)tid * per + j;
+        if (j < per && d < P) {
+          bin_start[d] = ex;
+          if (loc[j]) {
+            const unsigned long long g = atomicAdd(&cursors[d], (unsigned long long)loc[j]);
+            if (g + loc[j] > cap) *overflow = 1;
+            gdst[d] = g;
+          }
+          ex += loc[j];
+        }
+      }
+      if (tid == 0) tile_nwords = tot;  // reuse: number of k-mers staged
+    }
+    __syncthreads();
+#pragma unroll
+    for (int i = 0; i < RPW * MAXIT; ++i) {
+      if (br[i] != 0xffffffffu) {
+        const uint32_t bin = br[i] >> 16, pos = bin_start[bin] + (br[i] & 0xffffu);
+        stage[pos] = kw[i];
+        stage_bin[pos] = (uint16_t)bin;
+      }
+    }
+    __syncthreads();
+    const uint32_t n_staged = tile_nwords;
+    for (uint32_t j = tid; j < n_staged; j += kPartThreads) {
+      const uint32_t bin = stage_bin[j];
+      const unsigned long long o = gdst[bin] + (j - bin_start[bin]);
+      if (o < cap) out[part_base[bin] + o] = stage[j];
+    }
+    __syncthreads();
   }
-  if (flags) atomicOr(&table[slot].key, (unsigned long long)flags);
-  atomicAdd(&table[slot].cnt, flipped ? (1ULL << 32) : 1ULL);
 }
 
-// Enumerate the k-mers of read r cooperatively in one warp: lanes < nw pull the read's words once
-// (coalesced), every lane forms the k-mers at positions lane, lane+32, ... by funnel shifts out
-// of warp-shuffled words.  f(canon, flipped, flags) is called for every valid k-mer instance
-// (semantics of pass_processor::add, bs/kmer_counter.h:297-326).
-template <typename F>
-__device__ __forceinline__ void warp_read_kmers(const uint64_t* __restrict__ words, const uint32_t* __restrict__ nmask,
-                                                uint32_t base, int L, int k, F&& f) {
-  const unsigned lane = lane_id();
-  const int nk = L - k + 1;
-  const unsigned nw = (unsigned)(L + 31) >> 5;
-  uint64_t myw = lane < nw ? words[base + lane] : 0;
-  uint32_t mym = (nmask != nullptr && lane < nw) ? nmask[base + lane] : 0;
-  const int iters = (nk + 31) >> 5;
-  for (int it = 0; it < iters; ++it) {
-    uint64_t hi = __shfl_sync(0xffffffffu, myw, it);
-    uint64_t lo = __shfl_sync(0xffffffffu, myw, it + 1);
-    uint32_t mh = __shfl_sync(0xffffffffu, mym, it);
-    uint32_t ml = __shfl_sync(0xffffffffu, mym, it + 1);
-    int p = it * 32 + (int)lane;
-    if (p >= nk) continue;
-    unsigned s = lane * 2;
-    uint64_t win = s ? ((hi << s) | (lo >> (64 - s))) : hi;
-    uint32_t mwin = lane ? ((mh << lane) | (ml >> (32 - lane))) : mh;
-    if (mwin >> (32 - k)) continue;  // an 'N' inside the window (bs/kmer_counter.h:306-311)
-    uint64_t kmer = win >> (64 - 2 * k);
-    bool flipped;
-    uint64_t canon = canonicalize(kmer, k, flipped);
+// Pass 2: upsert the partitioned instances into the table.  Block (p, t) handles tile t of
+// partition p; blocks are dispatched in index order, so at any moment the resident blocks work
+// on one or two partitions = a few MB of table that stay in L2: the CAS / atomicAdd / atomicOr
+// traffic (kmer_count_table::increment, bs/kmer_count_table.h:54-103) never leaves L2, and DRAM
+// sees the table exactly twice (first touch, final write-back).
+constexpr int kUpsItems = 4;
+constexpr int kUpsTile = 256 * kUpsItems;
+__global__ void __launch_bounds__(256, 4) kmer_upsert_kernel(const unsigned long long* __restrict__ pk,
+                                                             const unsigned long long* __restrict__ part_base,
+                                                             const unsigned long long* __restrict__ part_count,
+                                                             uint32_t tiles_per_part, int k,
+                                                             CountEntry* __restrict__ table, int log2_slots,
+                                                             int* __restrict__ overflow) {
+  const uint32_t p = blockIdx.x / tiles_per_part, t = blockIdx.x % tiles_per_part;
+  const unsigned long long cnt = part_count[p];
+  const unsigned long long first = (unsigned long long)t * kUpsTile;
+  if (first >= cnt) return;
+  const unsigned long long* src = pk + part_base[p];
+  const uint64_t slot_mask = (1ULL << log2_slots) - 1;
+  // lock-step phases over the thread's items keep kUpsItems L2 round trips in flight per thread:
+  // A) instance words  B) first-probe keys  C) CAS claims of empty slots  D) counters (RED)
+  unsigned long long w[kUpsItems], key[kUpsItems], cur[kUpsItems];
+  uint32_t slot[kUpsItems];   // offset from the partition-aligned base (fits 32 bits: slots < 2^32 per call)
+  bool flip[kUpsItems];
+#pragma unroll
+  for (int i = 0; i < kUpsItems; ++i) {
+    const unsigned long long idx = first + (unsigned long long)i * 256 + threadIdx.x;
+    w[i] = idx < cnt ? src[idx] : ~0ULL;   // ~0 = no item (a real word never has all k-mer bits and both flags set for k<=31)
+  }
+#pragma unroll
+  for (int i = 0; i < kUpsItems; ++i) {
+    const bool valid = w[i] != ~0ULL;
+    bool fl;
+    const uint64_t canon = canonicalize(w[i] & kKmerMask, k, fl);
+    flip[i] = fl;
     // fwd_flag = first k-mer of the read, rev_flag = last; swapped when flipped
     // (bs/kmer_counter.h:318-321, bs/kmer_count_table.h:82-86)
-    bool first = (p == 0), last = (p == nk - 1);
-    uint64_t flags = 0;
-    if (flipped ? last : first) flags |= kFwdFlag;
-    if (flipped ? first : last) flags |= kRevFlag;
-    f(canon, flipped, flags);
+    const bool is_first = (w[i] & kPkFirst) != 0, is_last = (w[i] & kPkLast) != 0;
+    uint64_t f = 0;
+    if (fl ? is_last : is_first) f |= kFwdFlag;
+    if (fl ? is_first : is_last) f |= kRevFlag;
+    key[i] = valid ? (canon | f) : ~0ULL;
+    slot[i] = (uint32_t)table_slot(mix64(canon), log2_slots);
   }
-}
-
-// warp per read (grid-stride)
-__global__ void __launch_bounds__(256) kmer_count_kernel(const uint64_t* __restrict__ words,
-                                                         const uint32_t* __restrict__ nmask,
-                                                         const uint32_t* __restrict__ word_off,
-                                                         const uint16_t* __restrict__ lens, uint32_t n_reads, int k,
-                                                         CountEntry* __restrict__ table, uint64_t slot_mask,
-                                                         int* __restrict__ overflow) {
-  const uint32_t warps_total = (gridDim.x * blockDim.x) >> 5;
-  for (uint32_t r = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; r < n_reads; r += warps_total) {
-    const int L = lens[r];
-    if (L < k) continue;
-    warp_read_kmers(words, nmask, word_off[r], L, k, [&](uint64_t canon, bool flipped, uint64_t flags) {
-      table_upsert(table, slot_mask, canon, flipped, flags, overflow);
-    });
-  }
-}
-
-// Distinct-k-mer estimate for sizing the table: linear counting over the 1/16 of the hash space
-// whose low 4 hash bits are zero (sampling by hash value is unbiased for distinct counts).
-__global__ void __launch_bounds__(256) kmer_estimate_kernel(const uint64_t* __restrict__ words,
-                                                            const uint32_t* __restrict__ nmask,
-                                                            const uint32_t* __restrict__ word_off,
-                                                            const uint16_t* __restrict__ lens, uint32_t n_reads, int k,
-                                                            unsigned int* __restrict__ bitmap, uint64_t bit_mask) {
-  const uint32_t warps_total = (gridDim.x * blockDim.x) >> 5;
-  for (uint32_t r = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; r < n_reads; r += warps_total) {
-    const int L = lens[r];
-    if (L < k) continue;
-    warp_read_kmers(words, nmask, word_off[r], L, k, [&](uint64_t canon, bool, uint64_t) {
-      uint64_t h = mix64(canon ^ 0x9e3779b97f4a7c15ULL);
-      if ((h & 15) == 0) {
-        uint64_t bit = (h >> 4) & bit_mask;
-        unsigned int m = 1u << (bit & 31);
-        if (!(bitmap[bit >> 5] & m)) atomicOr(&bitmap[bit >> 5], m);
+#pragma unroll
+  for (int i = 0; i < kUpsItems; ++i)
+    cur[i] = key[i] != ~0ULL ? *reinterpret_cast<volatile unsigned long long*>(&table[slot[i]].key) : 0ULL;
+#pragma unroll
+  for (int i = 0; i < kUpsItems; ++i)
+    if (key[i] != ~0ULL && cur[i] == kEmptyKey)
+      cur[i] = atomicCAS(&table[slot[i]].key, (unsigned long long)kEmptyKey, key[i]);  // returns kEmptyKey when claimed
+#pragma unroll
+  for (int i = 0; i < kUpsItems; ++i) {
+    if (key[i] == ~0ULL) continue;
+    const uint64_t canon = key[i] & kKmerMask;
+    uint64_t f = key[i] & ~kKmerMask;
+    uint64_t s = slot[i];
+    unsigned long long c = cur[i];
+    if (c == kEmptyKey) {
+      f = 0;  // claimed by the CAS above: key and flags are in place
+    } else if ((c & kKmerMask) == canon) {
+      f &= ~c;
+    } else {
+      // collision: linear probing (rare at load factor <= 2/3)
+      bool done = false;
+      for (uint64_t probes = 0; probes <= slot_mask; ++probes) {
+        s = (s + 1) & slot_mask;
+        c = *reinterpret_cast<volatile unsigned long long*>(&table[s].key);
+        if (c == kEmptyKey) {
+          c = atomicCAS(&table[s].key, (unsigned long long)kEmptyKey, key[i]);
+          if (c == kEmptyKey) { f = 0; done = true; break; }
+        }
+        if ((c & kKmerMask) == canon) { f &= ~c; done = true; break; }
       }
-    });
+      if (!done) { *overflow = 1; continue; }
+    }
+    if (f) atomicOr(&table[s].key, (unsigned long long)f);
+    // one 32-bit RED on the fwd (low) or rev (high) half of the counter word
+    atomicAdd(reinterpret_cast<unsigned int*>(&table[s].cnt) + (flip[i] ? 1 : 0), 1u);
   }
 }
 
@@ -249,63 +400,163 @@ uint64_t pow2_ceil(uint64_t x) {
 
 }  // namespace
 
+namespace {
+
+struct PartitionLaunch {
+  int maxit, rpw;
+  size_t smem;
+};
+
+template <int MAXIT, int RPW>
+void launch_partition(Context* c, unsigned n_tiles_hint, int part_bits, unsigned long long* cursors,
+                      const unsigned long long* part_base, unsigned long long cap, unsigned long long* out,
+                      unsigned int* bitmap, uint64_t bit_mask, int* overflow) {
+  constexpr int tile_reads = kPartWarps * RPW;
+  constexpr int tile_kmers = tile_reads * MAXIT * 32;
+  constexpr int wpr = MAXIT + 1;
+  const size_t smem = (size_t)tile_kmers * 8 + (size_t)(tile_reads * wpr + 2) * 12 + (size_t)tile_kmers * 2 +
+                      ((size_t)16 << part_bits);
+  static bool attr_set = false;
+  if (!attr_set) {
+    const size_t smem_max = (size_t)tile_kmers * 10 + (size_t)(tile_reads * wpr + 2) * 12 + ((size_t)16 << kMaxPartBits);
+    BGX_CUDA(cudaFuncSetAttribute(kmer_partition_kernel<MAXIT, RPW>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  (int)smem_max));
+    attr_set = true;
+  }
+  int blocks_per_sm = 1;
+  BGX_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, kmer_partition_kernel<MAXIT, RPW>,
+                                                         kPartThreads, smem));
+  blocks_per_sm = std::max(blocks_per_sm, 1);
+  // persistent grid: every SM fully occupied, tiles handed out grid-stride
+  const unsigned n_tiles = (unsigned)((c->n_reads + tile_reads - 1) / tile_reads);
+  const unsigned grid = std::min<unsigned>(n_tiles, (unsigned)(kNumSMs * blocks_per_sm));
+  (void)n_tiles_hint;
+  note_launch();
+  kmer_partition_kernel<MAXIT, RPW><<<grid, kPartThreads, smem, c->stream>>>(
+      c->words.p, c->has_n ? c->nmask.p : nullptr, c->word_off.p, c->lens.p, (uint32_t)c->n_reads, c->opt.kmer_size,
+      part_bits, cursors, part_base, cap, out, bitmap, bit_mask, overflow);
+  BGX_CUDA(cudaGetLastError());
+}
+
+void run_partition(Context* c, int maxit, unsigned grid, int part_bits, unsigned long long* cursors,
+                   const unsigned long long* part_base, unsigned long long cap, unsigned long long* out,
+                   unsigned int* bitmap, uint64_t bit_mask, int* overflow) {
+  if (maxit <= 4)
+    launch_partition<4, 4>(c, grid, part_bits, cursors, part_base, cap, out, bitmap, bit_mask, overflow);
+  else
+    launch_partition<8, 2>(c, grid, part_bits, cursors, part_base, cap, out, bitmap, bit_mask, overflow);
+}
+
+int log2_exact(uint64_t x) {
+  int l = 0;
+  while ((1ULL << l) < x) ++l;
+  return l;
+}
+
+}  // namespace
+
 void stage_count_kmers(Context* c) {
   cudaStream_t s = c->stream;
   const int k = c->opt.kmer_size;
   BGX_CHECK(c->n_reads > 0, "bgx_count_kmers: no reads");
   ScopedStage st_all(c, "count_total");
+  const uint64_t K = c->n_kmer_instances;
 
-  // Size the table from a distinct-k-mer estimate (one cheap extra pass over the packed reads):
-  // load factor in (1/3, 2/3].  An overflow (estimate off) is retried below with a doubled table.
-  const unsigned grid_reads = (unsigned)std::min<uint64_t>((c->n_reads * 32 + 255) / 256, (uint64_t)kNumSMs * 8);
-  uint64_t est_distinct = 0;
+  // ---- pass 1: extract + hash-partition every k-mer instance; fused distinct estimate -------------
+  // P partitions so that one partition's slice of the table (~4 B per instance at typical
+  // coverage) is at most ~64 MB = half of L2; measured on B200: fewer, larger partitions make
+  // pass 1 faster (longer coalesced runs) and pass 2 is insensitive down to 64 MB slices.
+  int part_bits = 7;
+  while (part_bits < kMaxPartBits && (K * 4 >> part_bits) > (64ull << 20)) ++part_bits;
+  if (const char* e = getenv("BGX_PART_BITS")) part_bits = std::max(1, std::min(kMaxPartBits, atoi(e)));
+  const int P = 1 << part_bits;
+  const int maxit = (int)((std::max<int64_t>((int64_t)c->max_len - k + 1, 1) + 31) / 32);
+  BGX_CHECK(maxit <= 8, "read longer than 255 bases");
+  unsigned long long cap = K / P + K / (8ull * P) + 4096;  // hash partitions are near uniform
+  DevBuf<unsigned long long> pk((size_t)cap * P, s), cursors(P, s), part_base(P, s);
+  std::vector<unsigned long long> h_base(P), h_count(P);
+  for (int p = 0; p < P; ++p) h_base[p] = (unsigned long long)p * cap;
+  BGX_CUDA(cudaMemcpyAsync(part_base.p, h_base.data(), P * 8, cudaMemcpyHostToDevice, s));
+  BGX_CUDA(cudaMemsetAsync(cursors.p, 0, P * 8, s));
+  DevBuf<int> overflow(1, s);
+  BGX_CUDA(cudaMemsetAsync(overflow.p, 0, sizeof(int), s));
+  const uint64_t bits = pow2_ceil(std::max<uint64_t>(1 << 20, K / 8));
+  DevBuf<unsigned int> bitmap(bits / 32, s);
+  DevBuf<unsigned long long> ones(1, s);
+  BGX_CUDA(cudaMemsetAsync(bitmap.p, 0, bits / 8, s));
+  BGX_CUDA(cudaMemsetAsync(ones.p, 0, 8, s));
+  const unsigned grid_part = (unsigned)std::min<uint64_t>((c->n_reads + 15) / 16, (uint64_t)kNumSMs * 4);
+  unsigned long long h_ones = 0;
+  int h_over = 0;
   {
-    ScopedStage st(c, "count_estimate");
-    uint64_t bits = pow2_ceil(std::max<uint64_t>(1 << 20, c->n_kmer_instances / 8));
-    DevBuf<unsigned int> bitmap(bits / 32, s);
-    DevBuf<unsigned long long> ones(1, s);
-    BGX_CUDA(cudaMemsetAsync(bitmap.p, 0, bits / 8, s));
-    BGX_CUDA(cudaMemsetAsync(ones.p, 0, 8, s));
-    KLAUNCH(kmer_estimate_kernel)<<<grid_reads, 256, 0, s>>>(c->words.p, c->has_n ? c->nmask.p : nullptr, c->word_off.p,
-                                                           c->lens.p, (uint32_t)c->n_reads, k, bitmap.p, bits - 1);
+    ScopedStage st(c, "count_partition");
+    run_partition(c, maxit, grid_part, part_bits, cursors.p, part_base.p, cap, pk.p, bitmap.p, bits - 1, overflow.p);
     KLAUNCH(popcount_kernel)<<<(unsigned)((bits / 32 + 255) / 256), 256, 0, s>>>(bitmap.p, bits / 32, ones.p);
     BGX_CUDA(cudaGetLastError());
-    unsigned long long h_ones = 0;
     BGX_CUDA(cudaMemcpyAsync(&h_ones, ones.p, 8, cudaMemcpyDeviceToHost, s));
+    BGX_CUDA(cudaMemcpyAsync(&h_over, overflow.p, sizeof(int), cudaMemcpyDeviceToHost, s));
+    BGX_CUDA(cudaMemcpyAsync(h_count.data(), cursors.p, P * 8, cudaMemcpyDeviceToHost, s));
     BGX_CUDA(cudaStreamSynchronize(s));
-    double zero_frac = std::max(1.0 / (double)bits, 1.0 - (double)h_ones / (double)bits);
-    est_distinct = (uint64_t)(16.0 * -(double)bits * std::log(zero_frac));
-    est_distinct = std::min<uint64_t>(est_distinct + est_distinct / 16 + 4096, c->n_kmer_instances + 1);
+    if (h_over) {
+      // a heavy-hitter k-mer overfilled its partition: the cursors are now the exact histogram,
+      // so re-run with exact offsets (the reference has no analogue; its tables are sized up front)
+      uint64_t total = 0;
+      cap = 0;
+      for (int p = 0; p < P; ++p) { h_base[p] = total; total += h_count[p]; cap = std::max<unsigned long long>(cap, h_count[p]); }
+      pk.alloc(std::max<uint64_t>(total, 1), s);
+      BGX_CUDA(cudaMemcpyAsync(part_base.p, h_base.data(), P * 8, cudaMemcpyHostToDevice, s));
+      BGX_CUDA(cudaMemsetAsync(cursors.p, 0, P * 8, s));
+      BGX_CUDA(cudaMemsetAsync(overflow.p, 0, sizeof(int), s));
+      run_partition(c, maxit, grid_part, part_bits, cursors.p, part_base.p, cap, pk.p, bitmap.p, bits - 1, overflow.p);
+      BGX_CUDA(cudaMemcpyAsync(&h_over, overflow.p, sizeof(int), cudaMemcpyDeviceToHost, s));
+      BGX_CUDA(cudaStreamSynchronize(s));
+      BGX_CHECK(!h_over, "internal: exact partition pass overflowed");
+      c->add_stat("count_partition_reruns", 1);
+    }
     st.stop();
   }
+  uint64_t n_inst = 0, max_count = 0;
+  for (int p = 0; p < P; ++p) { n_inst += h_count[p]; max_count = std::max<uint64_t>(max_count, h_count[p]); }
+
+  // ---- size the table: load factor in (1/3, 2/3] of the estimated distinct count -----------------
+  const double zero_frac = std::max(1.0 / (double)bits, 1.0 - (double)h_ones / (double)bits);
+  uint64_t est_distinct = (uint64_t)(16.0 * -(double)bits * std::log(zero_frac));
+  est_distinct = std::min<uint64_t>(est_distinct + est_distinct / 16 + 4096, n_inst + 1);
   c->set_stat("kmer_distinct_estimate", (double)est_distinct);
   uint64_t slots = pow2_ceil(std::max<uint64_t>(1024, est_distinct + est_distinct / 2));
   if (const char* e = getenv("BGX_TABLE_SLOTS_LOG2")) slots = 1ull << atoi(e);  // experiment hook
-  size_t free_b = 0, total_b = 0;
-  BGX_CUDA(cudaMemGetInfo(&free_b, &total_b));
-  BGX_CHECK(slots * sizeof(CountEntry) < free_b, "not enough device memory for the k-mer table");
-  c->table_slots = slots;
-  c->table.alloc(slots, s);
-  {
-    ScopedStage st(c, "count_init");
-    KLAUNCH(fill_empty_kernel)<<<(unsigned)((slots + 255) / 256), 256, 0, s>>>(reinterpret_cast<uint4*>(c->table.p), slots);
-    st.stop();
+  int tries = 0;
+  for (;;) {
+    size_t free_b = 0, total_b = 0;
+    BGX_CUDA(cudaMemGetInfo(&free_b, &total_b));
+    BGX_CHECK(slots * sizeof(CountEntry) < free_b, "not enough device memory for the k-mer table");
+    BGX_CHECK(slots <= (1ull << 32), "k-mer table too large for one GPU shard (slot index is 32-bit)");
+    c->table_slots = slots;
+    c->table.alloc(slots, s);
+    {
+      ScopedStage st(c, "count_init");
+      KLAUNCH(fill_empty_kernel)<<<(unsigned)((slots + 255) / 256), 256, 0, s>>>(reinterpret_cast<uint4*>(c->table.p), slots);
+      st.stop();
+    }
+    BGX_CUDA(cudaMemsetAsync(overflow.p, 0, sizeof(int), s));
+    {
+      ScopedStage st(c, "count_kernel");
+      const uint32_t tiles_per_part = (uint32_t)std::max<uint64_t>(1, (max_count + kUpsTile - 1) / kUpsTile);
+      BGX_CHECK((uint64_t)tiles_per_part * P < (1ull << 31), "too many k-mer tiles for one launch");
+      KLAUNCH(kmer_upsert_kernel)<<<tiles_per_part * (uint32_t)P, 256, 0, s>>>(pk.p, part_base.p, cursors.p, tiles_per_part, k,
+                                                                      c->table.p, log2_exact(slots), overflow.p);
+      BGX_CUDA(cudaGetLastError());
+      st.stop();
+    }
+    BGX_CUDA(cudaMemcpyAsync(&h_over, overflow.p, sizeof(int), cudaMemcpyDeviceToHost, s));
+    BGX_CUDA(cudaStreamSynchronize(s));
+    if (!h_over) break;
+    // estimate was off (cannot happen for slots > distinct; belt and braces): double and redo.
+    // The reference throws io_exception("Kmer table (...) too small") (bs/kmer_count_table.h:75).
+    BGX_CHECK(++tries < 4, "Kmer table too small");
+    slots *= 2;
   }
-  DevBuf<int> overflow(1, s);
-  BGX_CUDA(cudaMemsetAsync(overflow.p, 0, sizeof(int), s));
-  {
-    ScopedStage st(c, "count_kernel");
-    // persistent-style grid: 148 SMs x 8 resident 256-thread CTAs
-    KLAUNCH(kmer_count_kernel)<<<grid_reads, 256, 0, s>>>(c->words.p, c->has_n ? c->nmask.p : nullptr, c->word_off.p, c->lens.p,
-                                             (uint32_t)c->n_reads, k, c->table.p, slots - 1, overflow.p);
-    BGX_CUDA(cudaGetLastError());
-    st.stop();
-  }
-  int h_over = 0;
-  BGX_CUDA(cudaMemcpyAsync(&h_over, overflow.p, sizeof(int), cudaMemcpyDeviceToHost, s));
-  BGX_CUDA(cudaStreamSynchronize(s));
-  // the reference throws io_exception("Kmer table (...) too small") (bs/kmer_count_table.h:75)
-  BGX_CHECK(!h_over, "Kmer table too small");
+  pk.release();
 
   // filter (kmer_passes: fwd+rev >= min_count) and build the solid set: ONE sweep into buffers
   // sized by the bound #solid <= K / min_count.
@@ -313,16 +564,16 @@ void stage_count_kmers(Context* c) {
   unsigned long long h_cnt[2];
   {
     ScopedStage st(c, "count_filter");
-    uint64_t cap = std::min<uint64_t>(slots, c->n_kmer_instances / (uint64_t)c->opt.min_kmer_count + 1);
-    DevBuf<unsigned long long> sk(cap, s), sc(cap, s);
+    uint64_t capf = std::min<uint64_t>(slots, K / (uint64_t)c->opt.min_kmer_count + 1);
+    DevBuf<unsigned long long> sk(capf, s), sc(capf, s);
     BGX_CUDA(cudaMemsetAsync(counters.p, 0, 2 * sizeof(unsigned long long), s));
     KLAUNCH(table_sweep_kernel)<<<(unsigned)((slots + kSweepPerBlock - 1) / kSweepPerBlock), 256, 0, s>>>(
-        c->table.p, slots, (uint32_t)c->opt.min_kmer_count, counters.p, sk.p, sc.p, cap);
+        c->table.p, slots, (uint32_t)c->opt.min_kmer_count, counters.p, sk.p, sc.p, capf);
     BGX_CUDA(cudaMemcpyAsync(h_cnt, counters.p, sizeof(h_cnt), cudaMemcpyDeviceToHost, s));
     BGX_CUDA(cudaStreamSynchronize(s));
     c->n_distinct = h_cnt[0];
     c->n_solid = h_cnt[1];
-    BGX_CHECK(c->n_solid <= cap, "internal: solid k-mer bound violated");
+    BGX_CHECK(c->n_solid <= capf, "internal: solid k-mer bound violated");
     // "Too many kmers for kmer table!" (kmer_set.cpp:554-556) has no analogue: the set is sized to fit.
     c->solid_slots = pow2_ceil(std::max<uint64_t>(1024, c->n_solid * 2));
     c->solid.alloc(c->solid_slots, s);
@@ -336,12 +587,16 @@ void stage_count_kmers(Context* c) {
   c->counted = true;
   c->corrected = c->built = false;
   st_all.stop();
-  c->set_stat("kmer_instances", (double)c->n_kmer_instances);
+  c->set_stat("kmer_instances", (double)n_inst);
   c->set_stat("kmer_distinct", (double)c->n_distinct);
   c->set_stat("kmer_solid", (double)c->n_solid);
   c->set_stat("count_table_slots", (double)slots);
-  // B/4 + K*32 + T*16*2
-  c->set_stat("alg_bytes_count", (double)c->n_bases / 4 + 32.0 * (double)c->n_kmer_instances + 32.0 * (double)slots);
+  c->set_stat("count_partitions", (double)P);
+  // partition pass: reads in, one 8-byte word per instance out; upsert pass: the words back in,
+  // the table touched twice (first touch + write-back), 16 B per slot
+  c->set_stat("alg_bytes_count_partition", (double)c->n_bases / 4 + 8.0 * (double)n_inst);
+  c->set_stat("alg_bytes_count_kernel", 8.0 * (double)n_inst + 32.0 * (double)slots);
+  c->set_stat("alg_bytes_count", (double)c->n_bases / 4 + 16.0 * (double)n_inst + 48.0 * (double)slots);
 }
 
 void export_kmers(Context* c, uint32_t min_count, uint64_t* n_out, uint64_t** kmers, uint32_t** fwd, uint32_t** rev,

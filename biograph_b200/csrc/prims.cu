@@ -1,17 +1,108 @@
 // prims.cu -- exclusive scan and LSD radix sort kernels (sm_100a, hand-written; no CUB).
 #include "prims.cuh"
 
+#include <algorithm>
+#include <map>
+#include <mutex>
+#include <unordered_map>
+
 namespace bgx {
 
 unsigned long long g_launches = 0;
 
+// ---- device memory arena ---------------------------------------------------------------------
+// A size-keyed cache of cudaMalloc blocks.  Every buffer of the path is allocated and released
+// in the same order with the same sizes on every run over the same reads, so after the first
+// run every request is served from the cache with no driver call (cudaMallocAsync's pool was
+// measured to stall for tens of ms when multi-GB blocks were recycled in a different order).
+// Reuse is safe because all work of a context is ordered on one stream.
+namespace {
+struct Block {
+  void* p;
+  cudaStream_t s;
+};
+struct Arena {
+  std::mutex mu;
+  std::multimap<size_t, Block> free_blocks;                       // size -> block
+  std::unordered_map<void*, std::pair<size_t, cudaStream_t>> live;  // block -> (size, stream)
+  size_t live_bytes = 0, peak_bytes = 0;
+  // frees every cached block (of one stream, or of all when s == nullptr)
+  void trim_locked(cudaStream_t s, bool all) {
+    for (auto it = free_blocks.begin(); it != free_blocks.end();) {
+      if (all || it->second.s == s) {
+        cudaFree(it->second.p);
+        it = free_blocks.erase(it);
+      } else {
+        ++it;
+      }
+    }
+  }
+};
+Arena& arena() {
+  static Arena a;
+  return a;
+}
+}  // namespace
+
 void* dev_alloc(size_t bytes, cudaStream_t s) {
+  Arena& a = arena();
+  bytes = (bytes + 511) & ~(size_t)511;
+  std::lock_guard<std::mutex> lk(a.mu);
   void* p = nullptr;
-  BGX_CUDA(cudaMallocAsync(&p, bytes, s));
+  size_t sz = bytes;
+  // exact-size match among this stream's cached blocks: sizes repeat run after run, and a
+  // near-fit policy lets a smaller request steal the block a later exact request needs
+  for (auto it = a.free_blocks.lower_bound(bytes); it != a.free_blocks.end() && it->first == bytes; ++it) {
+    if (it->second.s != s) continue;
+    p = it->second.p;
+    sz = it->first;
+    a.free_blocks.erase(it);
+    break;
+  }
+  if (!p) {
+    cudaError_t e = cudaMalloc(&p, bytes);
+    if (e != cudaSuccess) {
+      cudaGetLastError();
+      cudaDeviceSynchronize();
+      a.trim_locked(nullptr, true);  // give cached blocks back and retry once
+      e = cudaMalloc(&p, bytes);
+    }
+    if (e != cudaSuccess) {
+      cudaGetLastError();
+      throw Error("out of device memory allocating " + std::to_string(bytes) + " bytes (" +
+                  std::to_string(a.live_bytes) + " live)");
+    }
+  }
+  a.live[p] = {sz, s};
+  a.live_bytes += sz;
+  a.peak_bytes = std::max(a.peak_bytes, a.live_bytes);
   return p;
 }
-void dev_free(void* p, cudaStream_t s) {
-  if (p) cudaFreeAsync(p, s);
+
+void dev_free(void* p, cudaStream_t) {
+  if (!p) return;
+  Arena& a = arena();
+  std::lock_guard<std::mutex> lk(a.mu);
+  auto it = a.live.find(p);
+  if (it == a.live.end()) return;
+  a.free_blocks.emplace(it->second.first, Block{p, it->second.second});
+  a.live_bytes -= it->second.first;
+  a.live.erase(it);
+}
+
+void dev_trim(cudaStream_t s) {
+  Arena& a = arena();
+  cudaStreamSynchronize(s);
+  std::lock_guard<std::mutex> lk(a.mu);
+  a.trim_locked(s, false);
+}
+
+size_t dev_peak_bytes(bool reset) {
+  Arena& a = arena();
+  std::lock_guard<std::mutex> lk(a.mu);
+  size_t v = a.peak_bytes;
+  if (reset) a.peak_bytes = a.live_bytes;
+  return v;
 }
 
 namespace {
@@ -21,37 +112,6 @@ namespace {
 constexpr int SC_THREADS = 256;
 constexpr int SC_ITEMS = 8;
 constexpr int SC_TILE = SC_THREADS * SC_ITEMS;
-
-__device__ __forceinline__ uint32_t warp_incl_scan(uint32_t v) {
-#pragma unroll
-  for (int o = 1; o < 32; o <<= 1) {
-    uint32_t t = __shfl_up_sync(0xffffffffu, v, o);
-    if (lane_id() >= o) v += t;
-  }
-  return v;
-}
-
-// block-wide exclusive scan of one value per thread (blockDim.x <= 1024); returns exclusive
-// prefix, *total = block sum
-__device__ __forceinline__ uint32_t block_excl_scan(uint32_t v, uint32_t* total) {
-  __shared__ uint32_t wsum[32];
-  __shared__ uint32_t tot;
-  unsigned lane = lane_id(), warp = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
-  uint32_t inc = warp_incl_scan(v);
-  if (lane == 31) wsum[warp] = inc;
-  __syncthreads();
-  if (warp == 0) {
-    uint32_t w = lane < nw ? wsum[lane] : 0;
-    uint32_t wi = warp_incl_scan(w);
-    wsum[lane] = wi - w;
-    if (lane == 31) tot = wi;
-  }
-  __syncthreads();
-  uint32_t r = wsum[warp] + inc - v;
-  *total = tot;
-  __syncthreads();
-  return r;
-}
 
 __global__ void __launch_bounds__(SC_THREADS) scan_reduce_kernel(const uint32_t* __restrict__ in,
                                                                  uint32_t* __restrict__ block_sums, size_t n) {
@@ -63,7 +123,7 @@ __global__ void __launch_bounds__(SC_THREADS) scan_reduce_kernel(const uint32_t*
     if (idx < n) s += in[idx];
   }
   uint32_t tot;
-  block_excl_scan(s, &tot);
+  block_excl_scan_u32(s, &tot);
   if (threadIdx.x == 0) block_sums[blockIdx.x] = tot;
 }
 
@@ -74,7 +134,7 @@ __global__ void __launch_bounds__(1024) scan_blocksums_kernel(uint32_t* __restri
     size_t idx = base + threadIdx.x;
     uint32_t v = idx < nb ? block_sums[idx] : 0;
     uint32_t tot;
-    uint32_t ex = block_excl_scan(v, &tot);
+    uint32_t ex = block_excl_scan_u32(v, &tot);
     if (idx < nb) block_sums[idx] = carry + ex;
     carry += tot;
   }
@@ -94,7 +154,7 @@ __global__ void __launch_bounds__(SC_THREADS) scan_final_kernel(const uint32_t* 
     s += v[i];
   }
   uint32_t tot;
-  uint32_t ex = block_excl_scan(s, &tot) + block_sums[blockIdx.x];
+  uint32_t ex = block_excl_scan_u32(s, &tot) + block_sums[blockIdx.x];
 #pragma unroll
   for (int i = 0; i < SC_ITEMS; ++i) {
     size_t idx = base + i;
@@ -192,7 +252,7 @@ radix_scatter_kernel(const uint64_t* __restrict__ keys_in, const uint64_t* __res
       sum += c;
     }
     uint32_t tot;
-    uint32_t ex = block_excl_scan(sum, &tot);
+    uint32_t ex = block_excl_scan_u32(sum, &tot);
     digit_start[d] = ex;
     glob_base[d] = offsets[(size_t)d * ntiles + blockIdx.x] - ex;
   }

@@ -9,9 +9,12 @@
 
 namespace bgx {
 
-// Stream-ordered device allocation (cudaMallocAsync on the context's pool).
+// Device allocation from the library's caching arena (prims.cu).  Blocks are recycled by size
+// among allocations of the same stream (one stream per context), so reuse is stream-ordered.
 void* dev_alloc(size_t bytes, cudaStream_t s);
 void dev_free(void* p, cudaStream_t s);
+void dev_trim(cudaStream_t s);         // return the cached blocks of stream s to the driver
+size_t dev_peak_bytes(bool reset);     // high-water mark of live bytes
 
 template <typename T>
 struct DevBuf {
