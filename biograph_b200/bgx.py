@@ -41,7 +41,7 @@ EXPORTS = ["bgx_default_options", "bgx_last_error", "bgx_version", "bgx_device_c
            "bgx_free", "bgx_add_reads_ascii", "bgx_add_reads_packed", "bgx_count_kmers", "bgx_export_kmers",
            "bgx_correct", "bgx_export_corrected", "bgx_build_seqset", "bgx_export_seqset",
            "bgx_export_entries_ascii", "bgx_run", "bgx_reset_results", "bgx_clear_reads", "bgx_stats_json", "bgx_timer_start", "bgx_timer_stop",
-           "bgx_launch_count"]
+           "bgx_launch_count", "bgx_debug_sort_pairs"]
 
 
 def load_library():
@@ -78,6 +78,7 @@ def load_library():
     L.bgx_timer_start.argtypes = [vp]
     L.bgx_timer_stop.argtypes = [vp, C.POINTER(C.c_double)]
     L.bgx_launch_count.restype = C.c_uint64
+    L.bgx_debug_sort_pairs.argtypes = [vp, vp, vp, C.c_uint64, C.c_int, C.c_int]
     _LIB = L
     return L
 
@@ -307,6 +308,11 @@ class Bgx:
         ms = C.c_double()
         self._ck(self.L.bgx_timer_stop(self.h, C.byref(ms)))
         return ms.value
+
+    def debug_sort_pairs(self, keys, vals, begin_bit=0, end_bit=64):
+        """in-place stable radix sort of host uint64 arrays on the GPU (test hook)"""
+        assert keys.dtype == np.uint64 and vals.dtype == np.uint64 and len(keys) == len(vals)
+        self._ck(self.L.bgx_debug_sort_pairs(self.h, keys.ctypes.data, vals.ctypes.data, len(keys), begin_bit, end_bit))
 
     def launch_count(self):
         return int(self.L.bgx_launch_count())

@@ -277,6 +277,19 @@ int bgx_timer_stop(bgx_ctx* x, double* elapsed_ms) {
   })
 }
 
+int bgx_debug_sort_pairs(bgx_ctx* x, uint64_t* keys, uint64_t* vals, uint64_t n, int begin_bit, int end_bit) {
+  CTX_GUARD({
+    cudaStream_t s = c->stream;
+    DevBuf<uint64_t> k0(n + 1, s), v0(n + 1, s), k1(n + 1, s), v1(n + 1, s);
+    BGX_CUDA(cudaMemcpyAsync(k0.p, keys, n * 8, cudaMemcpyHostToDevice, s));
+    BGX_CUDA(cudaMemcpyAsync(v0.p, vals, n * 8, cudaMemcpyHostToDevice, s));
+    bool alt = radix_sort_pairs(k0.p, v0.p, k1.p, v1.p, n, begin_bit, end_bit, s);
+    BGX_CUDA(cudaMemcpyAsync(keys, alt ? k1.p : k0.p, n * 8, cudaMemcpyDeviceToHost, s));
+    BGX_CUDA(cudaMemcpyAsync(vals, alt ? v1.p : v0.p, n * 8, cudaMemcpyDeviceToHost, s));
+    BGX_CUDA(cudaStreamSynchronize(s));
+  })
+}
+
 uint64_t bgx_launch_count(void) { return __atomic_load_n(&bgx::g_launches, __ATOMIC_RELAXED); }
 
 }  // extern "C"

@@ -164,122 +164,218 @@ __global__ void __launch_bounds__(SC_THREADS) scan_final_kernel(const uint32_t* 
 }
 
 // ------------------------------------------------------------------------------------------
-// LSD radix sort, 8-bit digits.  Per pass:
-//   radix_count_kernel  : per-tile digit histogram (keys only, 8 B/elem)
-//   exclusive scan of the digit-major (digit, tile) count matrix
-//   radix_scatter_kernel: stable in-tile ranking (warp match_any), tile staged in shared
-//                         memory in digit order, written out as coalesced per-digit runs.
+// LSD radix sort of (uint64 key, uint64 value) pairs, 8-bit digits, "one sweep" per digit:
+//   radix_hist_kernel   : ONE read of the keys builds the global digit histograms of every pass
+//   radix_bases_kernel  : exclusive scan of each pass's 256 bins -> first output index per digit
+//   onesweep_kernel     : per pass, per tile of 4096 records:
+//       - the tile's keys and values are pulled into shared memory by TMA bulk copies
+//         (cp.async.bulk.shared::cluster.global + mbarrier complete_tx), no registers held
+//       - stable in-tile ranking: warp-striped items, match_any per digit, per-warp counters
+//       - the tile's digit counts are published and the exclusive prefix over earlier tiles is
+//         fetched by decoupled look-back (one thread per digit), so a pass reads and writes every
+//         record exactly once (2*N*16 bytes per pass)
+//       - records are reordered in shared memory and leave as coalesced per-digit runs
+// Tiles are handed out by an atomic ticket, so every tile a block can wait on has started.
 constexpr int RS_THREADS = 256;
 constexpr int RS_WARPS = RS_THREADS / 32;
 constexpr int RS_ITEMS = 16;
-constexpr int RS_TILE = RS_THREADS * RS_ITEMS;  // 4096 elements
+constexpr int RS_TILE = RS_THREADS * RS_ITEMS;  // 4096 records
 constexpr int RADIX = 256;
+constexpr uint32_t ST_AGG = 1u << 30;    // tile aggregate available
+constexpr uint32_t ST_INCL = 1u << 31;   // inclusive prefix available
+constexpr uint32_t ST_VAL = (1u << 30) - 1;
 
-__global__ void __launch_bounds__(RS_THREADS) radix_count_kernel(const uint64_t* __restrict__ keys,
-                                                                 uint32_t* __restrict__ counts, uint32_t n,
-                                                                 int shift, uint32_t ntiles) {
-  __shared__ uint32_t hist[RS_WARPS][RADIX];
-  for (int i = threadIdx.x; i < RS_WARPS * RADIX; i += RS_THREADS) (&hist[0][0])[i] = 0;
-  __syncthreads();
-  unsigned warp = threadIdx.x >> 5;
-  uint32_t base = blockIdx.x * RS_TILE;
-#pragma unroll 4
-  for (int i = 0; i < RS_ITEMS; ++i) {
-    uint32_t idx = base + i * RS_THREADS + threadIdx.x;
-    if (idx < n) {
-      unsigned d = (unsigned)(keys[idx] >> shift) & (RADIX - 1);
-      atomicAdd(&hist[warp][d], 1u);
-    }
-  }
-  __syncthreads();
-  unsigned d = threadIdx.x;
-  uint32_t c = 0;
-#pragma unroll
-  for (int w = 0; w < RS_WARPS; ++w) c += hist[w][d];
-  counts[(size_t)d * ntiles + blockIdx.x] = c;
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, unsigned count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, unsigned parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "WAIT_%=:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra DONE_%=;\n"
+      "bra WAIT_%=;\n"
+      "DONE_%=:\n"
+      "}\n" ::"r"(smem_u32(bar)),
+      "r"(parity)
+      : "memory");
+}
+// TMA 1-D bulk copy global -> shared; completion is signalled on the mbarrier as transferred bytes.
+// dst, src 16-byte aligned; bytes a multiple of 16.
+__device__ __forceinline__ void tma_load_1d(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                   smem_u32(dst)),
+               "l"(src), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
 }
 
-__global__ void __launch_bounds__(RS_THREADS)
-radix_scatter_kernel(const uint64_t* __restrict__ keys_in, const uint64_t* __restrict__ vals_in,
-                     uint64_t* __restrict__ keys_out, uint64_t* __restrict__ vals_out,
-                     const uint32_t* __restrict__ offsets, uint32_t n, int shift, uint32_t ntiles) {
-  __shared__ uint32_t warp_cnt[RS_WARPS][RADIX];
-  __shared__ uint32_t digit_start[RADIX];
-  __shared__ uint32_t glob_base[RADIX];
-  __shared__ uint8_t stage_digit[RS_TILE];
-  extern __shared__ uint64_t stage[];  // RS_TILE words
-
-  const unsigned tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const uint32_t tile_base = blockIdx.x * RS_TILE;
-  const uint32_t nvalid = min((uint32_t)RS_TILE, n - tile_base);
-  const uint32_t warp_base = warp * (RS_ITEMS * 32);
-
-  for (int i = tid; i < RS_WARPS * RADIX; i += RS_THREADS) (&warp_cnt[0][0])[i] = 0;
-
-  uint64_t k[RS_ITEMS];
-#pragma unroll
-  for (int i = 0; i < RS_ITEMS; ++i) {
-    uint32_t e = warp_base + i * 32 + lane;
-    k[i] = e < nvalid ? keys_in[tile_base + e] : ~0ULL;  // pads sort to the very end of the tile
+constexpr int RH_THREADS = 256;
+constexpr int RH_ITEMS = 16;
+constexpr int RH_MAXPASS = 8;
+__global__ void __launch_bounds__(RH_THREADS) radix_hist_kernel(const uint64_t* __restrict__ keys, uint32_t n,
+                                                                int begin_bit, int passes,
+                                                                uint32_t* __restrict__ ghist /*[passes][256]*/) {
+  __shared__ uint32_t h[RH_MAXPASS][RADIX];
+  for (int i = threadIdx.x; i < passes * RADIX; i += RH_THREADS) (&h[0][0])[i] = 0;
+  __syncthreads();
+  for (uint32_t base = blockIdx.x * (RH_THREADS * RH_ITEMS); base < n; base += gridDim.x * (RH_THREADS * RH_ITEMS)) {
+#pragma unroll 4
+    for (int i = 0; i < RH_ITEMS; ++i) {
+      uint32_t idx = base + i * RH_THREADS + threadIdx.x;
+      if (idx < n) {
+        uint64_t k = keys[idx] >> begin_bit;
+        for (int p = 0; p < passes; ++p) atomicAdd(&h[p][(unsigned)(k >> (8 * p)) & (RADIX - 1)], 1u);
+      }
+    }
   }
   __syncthreads();
+  for (int i = threadIdx.x; i < passes * RADIX; i += RH_THREADS) {
+    uint32_t v = (&h[0][0])[i];
+    if (v) atomicAdd(&ghist[i], v);
+  }
+}
 
-  uint16_t rank[RS_ITEMS];
+// one block of 256 threads per pass: ghist[p][d] -> exclusive prefix over d
+__global__ void __launch_bounds__(RADIX) radix_bases_kernel(uint32_t* __restrict__ ghist) {
+  uint32_t* g = ghist + blockIdx.x * RADIX;
+  uint32_t v = g[threadIdx.x], tot;
+  uint32_t ex = block_excl_scan_u32(v, &tot);
+  g[threadIdx.x] = ex;
+}
+
+struct OnesweepSmem {
+  uint64_t keys[RS_TILE];    // TMA destination, then the reorder stage
+  uint64_t vals[RS_TILE];    // TMA destination
+  uint32_t warp_cnt[RS_WARPS][RADIX];
+  uint32_t digit_start[RADIX];
+  uint32_t glob_base[RADIX];
+  uint8_t stage_digit[RS_TILE];
+  uint64_t bar_keys, bar_vals;
+  uint32_t tile;
+};
+
+__global__ void __launch_bounds__(RS_THREADS, 2)
+onesweep_kernel(const uint64_t* __restrict__ keys_in, const uint64_t* __restrict__ vals_in,
+                uint64_t* __restrict__ keys_out, uint64_t* __restrict__ vals_out,
+                const uint32_t* __restrict__ digit_base /*[256] exclusive*/, uint32_t* __restrict__ status /*[ntiles][256]*/,
+                uint32_t* __restrict__ ticket, uint32_t n, int shift) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  OnesweepSmem& sm = *reinterpret_cast<OnesweepSmem*>(smem_raw);
+  const unsigned tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+
+  if (tid == 0) {
+    sm.tile = atomicAdd(ticket, 1u);
+    mbar_init(&sm.bar_keys, 1);
+    mbar_init(&sm.bar_vals, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  for (int i = tid; i < RS_WARPS * RADIX; i += RS_THREADS) (&sm.warp_cnt[0][0])[i] = 0;
+  __syncthreads();
+  const uint32_t tile = sm.tile;
+  const uint32_t tile_base = tile * RS_TILE;
+  const uint32_t nvalid = min((uint32_t)RS_TILE, n - tile_base);
+  if (tid == 0) {
+    const uint32_t bytes = ((nvalid * 8u) + 15u) & ~15u;  // buffers are padded to 512 B by the arena
+    mbar_expect_tx(&sm.bar_keys, bytes);
+    tma_load_1d(sm.keys, keys_in + tile_base, bytes, &sm.bar_keys);
+    mbar_expect_tx(&sm.bar_vals, bytes);
+    tma_load_1d(sm.vals, vals_in + tile_base, bytes, &sm.bar_vals);
+  }
+  mbar_wait(&sm.bar_keys, 0);
+
+  // ---- stable ranking: item (i, lane) of warp w is tile element w*512 + i*32 + lane ------------
+  const uint32_t warp_base = warp * (RS_ITEMS * 32);
   const unsigned lt_mask = (1u << lane) - 1;
+  uint32_t packed_rank[RS_ITEMS / 2];  // two 16-bit ranks per register
+  uint32_t digs[RS_ITEMS / 4];         // four 8-bit digits per register
 #pragma unroll
   for (int i = 0; i < RS_ITEMS; ++i) {
-    unsigned d = (unsigned)(k[i] >> shift) & (RADIX - 1);
-    unsigned peers = __match_any_sync(0xffffffffu, d);
-    int leader = __ffs(peers) - 1;
+    const uint32_t e = warp_base + i * 32 + lane;
+    // pads (beyond nvalid) rank as digit 255 after every real record of their warp
+    const unsigned d = e < nvalid ? (unsigned)(sm.keys[e] >> shift) & (RADIX - 1) : (RADIX - 1);
+    const unsigned peers = __match_any_sync(0xffffffffu, d);
+    const int leader = __ffs(peers) - 1;
     uint32_t old = 0;
     if ((int)lane == leader) {
-      old = warp_cnt[warp][d];
-      warp_cnt[warp][d] = old + __popc(peers);
+      old = sm.warp_cnt[warp][d];
+      sm.warp_cnt[warp][d] = old + __popc(peers);
     }
     old = __shfl_sync(0xffffffffu, old, leader);
-    rank[i] = (uint16_t)(old + __popc(peers & lt_mask));
+    const uint32_t r = old + __popc(peers & lt_mask);
+    if (i & 1) packed_rank[i >> 1] |= r << 16; else packed_rank[i >> 1] = r;
+    if (i & 3) digs[i >> 2] |= d << (8 * (i & 3)); else digs[i >> 2] = d;
     __syncwarp();
   }
   __syncthreads();
 
+  // ---- per-digit: warp offsets, tile count, decoupled look-back ---------------------------------
   {
-    unsigned d = tid;  // RS_THREADS == RADIX
+    const unsigned d = tid;  // RS_THREADS == RADIX
     uint32_t sum = 0;
 #pragma unroll
     for (int w = 0; w < RS_WARPS; ++w) {
-      uint32_t c = warp_cnt[w][d];
-      warp_cnt[w][d] = sum;
+      const uint32_t c = sm.warp_cnt[w][d];
+      sm.warp_cnt[w][d] = sum;
       sum += c;
     }
+    // pads were counted as digit 255: remove them from the published count
+    const uint32_t real = (d == RADIX - 1) ? sum - (RS_TILE - nvalid) : sum;
+    volatile uint32_t* st = status + (size_t)tile * RADIX + d;
+    uint32_t excl = 0;
+    if (tile == 0) {
+      *st = ST_INCL | real;
+    } else {
+      *st = ST_AGG | real;
+      for (int64_t j = (int64_t)tile - 1;; --j) {
+        volatile uint32_t* sp = status + (size_t)j * RADIX + d;
+        uint32_t v;
+        do { v = *sp; } while (v == 0);
+        excl += v & ST_VAL;
+        if (v & ST_INCL) break;
+      }
+      *st = ST_INCL | (excl + real);
+    }
     uint32_t tot;
-    uint32_t ex = block_excl_scan_u32(sum, &tot);
-    digit_start[d] = ex;
-    glob_base[d] = offsets[(size_t)d * ntiles + blockIdx.x] - ex;
+    const uint32_t ex = block_excl_scan_u32(sum, &tot);
+    sm.digit_start[d] = ex;
+    sm.glob_base[d] = digit_base[d] + excl - ex;
   }
   __syncthreads();
 
-  uint16_t pos[RS_ITEMS];
+  // ---- keys: shared (tile order) -> registers -> shared (digit order) -> global ------------------
+  uint64_t k[RS_ITEMS];
 #pragma unroll
-  for (int i = 0; i < RS_ITEMS; ++i) {
-    unsigned d = (unsigned)(k[i] >> shift) & (RADIX - 1);
-    pos[i] = (uint16_t)(digit_start[d] + warp_cnt[warp][d] + rank[i]);
-    stage[pos[i]] = k[i];
-    stage_digit[pos[i]] = (uint8_t)d;
-  }
-  __syncthreads();
-  for (uint32_t j = tid; j < nvalid; j += RS_THREADS) {
-    keys_out[glob_base[stage_digit[j]] + j] = stage[j];
-  }
+  for (int i = 0; i < RS_ITEMS; ++i) k[i] = sm.keys[warp_base + i * 32 + lane];
   __syncthreads();
 #pragma unroll
   for (int i = 0; i < RS_ITEMS; ++i) {
-    uint32_t e = warp_base + i * 32 + lane;
-    if (e < nvalid) stage[pos[i]] = vals_in[tile_base + e];
+    const unsigned d = (digs[i >> 2] >> (8 * (i & 3))) & 0xffu;
+    const uint32_t r = (packed_rank[i >> 1] >> (16 * (i & 1))) & 0xffffu;
+    const uint32_t pos = sm.digit_start[d] + sm.warp_cnt[warp][d] + r;
+    sm.keys[pos] = k[i];
+    sm.stage_digit[pos] = (uint8_t)d;
   }
   __syncthreads();
-  for (uint32_t j = tid; j < nvalid; j += RS_THREADS) {
-    vals_out[glob_base[stage_digit[j]] + j] = stage[j];
+  for (uint32_t j = tid; j < nvalid; j += RS_THREADS) keys_out[sm.glob_base[sm.stage_digit[j]] + j] = sm.keys[j];
+  // ---- values: same permutation -----------------------------------------------------------------------
+  mbar_wait(&sm.bar_vals, 0);
+#pragma unroll
+  for (int i = 0; i < RS_ITEMS; ++i) k[i] = sm.vals[warp_base + i * 32 + lane];
+  __syncthreads();
+#pragma unroll
+  for (int i = 0; i < RS_ITEMS; ++i) {
+    const unsigned d = (digs[i >> 2] >> (8 * (i & 3))) & 0xffu;
+    const uint32_t r = (packed_rank[i >> 1] >> (16 * (i & 1))) & 0xffffu;
+    sm.vals[sm.digit_start[d] + sm.warp_cnt[warp][d] + r] = k[i];
   }
+  __syncthreads();
+  for (uint32_t j = tid; j < nvalid; j += RS_THREADS) vals_out[sm.glob_base[sm.stage_digit[j]] + j] = sm.vals[j];
 }
 
 }  // namespace
@@ -299,33 +395,37 @@ void exclusive_scan_u32(const uint32_t* in, uint32_t* out, size_t n, uint32_t* t
 
 bool radix_sort_pairs(uint64_t* keys, uint64_t* vals, uint64_t* keys_alt, uint64_t* vals_alt, size_t n,
                       int begin_bit, int end_bit, cudaStream_t s, int* passes_out) {
-  BGX_CHECK(n < (1ull << 32), "radix_sort_pairs: n must be < 2^32");
+  BGX_CHECK(n < (1ull << 30), "radix_sort_pairs: n must be < 2^30");
   BGX_CHECK(begin_bit >= 0 && end_bit <= 64 && begin_bit <= end_bit, "radix_sort_pairs: bad bit range");
-  int passes = 0;
-  if (n == 0) { if (passes_out) *passes_out = 0; return false; }
-  uint32_t ntiles = (uint32_t)((n + RS_TILE - 1) / RS_TILE);
-  DevBuf<uint32_t> counts((size_t)RADIX * ntiles, s);
+  const int passes = (end_bit - begin_bit + 7) / 8;
+  if (passes_out) *passes_out = n ? passes : 0;
+  if (n == 0 || passes == 0) return false;
+  const uint32_t ntiles = (uint32_t)((n + RS_TILE - 1) / RS_TILE);
+  // one zeroed scratch block: [passes][256] histograms | [passes] tickets | [passes][ntiles][256] status
+  const size_t hist_words = (size_t)passes * RADIX, status_words = (size_t)ntiles * RADIX;
+  const size_t ticket_off = hist_words, status_off = (hist_words + passes + 63) & ~(size_t)63;
+  DevBuf<uint32_t> scratch(status_off + status_words * passes, s);
+  BGX_CUDA(cudaMemsetAsync(scratch.p, 0, scratch.n * sizeof(uint32_t), s));
   static bool attr_set = false;
   if (!attr_set) {
-    BGX_CUDA(cudaFuncSetAttribute(radix_scatter_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                  RS_TILE * (int)sizeof(uint64_t)));
+    BGX_CUDA(cudaFuncSetAttribute(onesweep_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(OnesweepSmem)));
     attr_set = true;
   }
+  const unsigned hist_grid = (unsigned)std::min<size_t>((n + RH_THREADS * RH_ITEMS - 1) / (RH_THREADS * RH_ITEMS), (size_t)kNumSMs * 8);
+  KLAUNCH(radix_hist_kernel)<<<hist_grid, RH_THREADS, 0, s>>>(keys, (uint32_t)n, begin_bit, passes, scratch.p);
+  KLAUNCH(radix_bases_kernel)<<<passes, RADIX, 0, s>>>(scratch.p);
   bool in_alt = false;
-  for (int shift = begin_bit; shift < end_bit; shift += 8) {
+  for (int p = 0; p < passes; ++p) {
     const uint64_t* ki = in_alt ? keys_alt : keys;
     const uint64_t* vi = in_alt ? vals_alt : vals;
     uint64_t* ko = in_alt ? keys : keys_alt;
     uint64_t* vo = in_alt ? vals : vals_alt;
-    KLAUNCH(radix_count_kernel)<<<ntiles, RS_THREADS, 0, s>>>(ki, counts.p, (uint32_t)n, shift, ntiles);
-    exclusive_scan_u32(counts.p, counts.p, (size_t)RADIX * ntiles, nullptr, s);
-    KLAUNCH(radix_scatter_kernel)<<<ntiles, RS_THREADS, RS_TILE * sizeof(uint64_t), s>>>(ki, vi, ko, vo, counts.p,
-                                                                               (uint32_t)n, shift, ntiles);
-    BGX_CUDA(cudaGetLastError());
+    KLAUNCH(onesweep_kernel)<<<ntiles, RS_THREADS, sizeof(OnesweepSmem), s>>>(
+        ki, vi, ko, vo, scratch.p + (size_t)p * RADIX, scratch.p + status_off + status_words * p,
+        scratch.p + ticket_off + p, (uint32_t)n, begin_bit + 8 * p);
     in_alt = !in_alt;
-    ++passes;
   }
-  if (passes_out) *passes_out = passes;
+  BGX_CUDA(cudaGetLastError());
   return in_alt;
 }
 

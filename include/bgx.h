@@ -136,6 +136,11 @@ int bgx_timer_start(bgx_ctx* ctx);
 int bgx_timer_stop(bgx_ctx* ctx, double* elapsed_ms);
 uint64_t bgx_launch_count(void);
 
+/* Test hook for the device-wide primitives (no reference analogue): stable LSD radix sort of
+ * n (key, value) pairs held in HOST arrays on key bits [begin_bit, end_bit), in place, run by the
+ * same kernels the seqset stage uses. */
+int bgx_debug_sort_pairs(bgx_ctx* ctx, uint64_t* keys, uint64_t* vals, uint64_t n, int begin_bit, int end_bit);
+
 #ifdef __cplusplus
 }
 #endif

@@ -318,3 +318,30 @@ def test_properties_large(B):
     oss = O.seqset_staged((cr["seq"], cr["offs"]), cr["next_fwd"], cr["next_rev"])
     check_seqset_equal(oss, ss)
     g.close()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("n,begin,end,kind", [
+    (1, 0, 64, "rand"), (2, 0, 64, "rand"), (4095, 0, 64, "rand"), (4096, 0, 64, "rand"), (4097, 16, 64, "rand"),
+    (100001, 0, 64, "rand"), (1 << 20, 16, 64, "few"), (3000003, 0, 32, "sorted"), (777777, 8, 40, "const"),
+])
+def test_radix_sort_pairs_is_a_stable_sort(B, n, begin, end, kind):
+    """the onesweep LSD radix sort (prims.cu) against numpy's stable argsort, incl. ragged last tiles,
+    skewed digits (look-back with empty digit bins) and sub-ranges of key bits"""
+    rng = np.random.default_rng(n + begin)
+    if kind == "rand":
+        keys = rng.integers(0, 1 << 63, size=n, dtype=np.uint64) * np.uint64(2) + rng.integers(0, 2, size=n, dtype=np.uint64)
+    elif kind == "few":
+        keys = rng.choice(rng.integers(0, 1 << 62, size=37, dtype=np.uint64), size=n)
+    elif kind == "sorted":
+        keys = np.sort(rng.integers(0, 1 << 40, size=n, dtype=np.uint64))
+    else:
+        keys = np.full(n, 0x0123456789ABCDEF, dtype=np.uint64)
+    vals = np.arange(n, dtype=np.uint64)
+    mask = np.uint64(((1 << (end - begin)) - 1) << begin) if end - begin < 64 else np.uint64(0xFFFFFFFFFFFFFFFF)
+    order = np.argsort(keys & mask, kind="stable")
+    k2, v2 = keys.copy(), vals.copy()
+    with B.Bgx() as g:
+        g.debug_sort_pairs(k2, v2, begin, end)
+    assert np.array_equal(v2, vals[order])
+    assert np.array_equal(k2, keys[order])
