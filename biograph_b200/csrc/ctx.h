@@ -1,6 +1,7 @@
 // ctx.h -- the bgx context: device-resident state of one seqset build on one GPU.
 #pragma once
 
+#include <chrono>
 #include <map>
 #include <string>
 #include <vector>
@@ -84,9 +85,11 @@ struct ScopedStage {
   std::string name;
   cudaEvent_t a, b;
   bool done = false;
+  std::chrono::steady_clock::time_point h0;
   ScopedStage(Context* c_, const std::string& n) : c(c_), name(n) {
     cudaEventCreate(&a); cudaEventCreate(&b);
     cudaEventRecord(a, c->stream);
+    h0 = std::chrono::steady_clock::now();
   }
   double stop() {
     if (done) return 0;
@@ -96,6 +99,9 @@ struct ScopedStage {
     float ms = 0;
     cudaEventElapsedTime(&ms, a, b);
     c->add_stat("ms_" + name, ms);
+    // host wall clock over the same span: a gap to the device time is host-side stall
+    c->add_stat("hostms_" + name,
+                std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - h0).count());
     cudaEventDestroy(a); cudaEventDestroy(b);
     return ms;
   }

@@ -473,6 +473,7 @@ void stage_count_kmers(Context* c) {
   const int maxit = (int)((std::max<int64_t>((int64_t)c->max_len - k + 1, 1) + 31) / 32);
   BGX_CHECK(maxit <= 8, "read longer than 255 bases");
   unsigned long long cap = K / P + K / (8ull * P) + 4096;  // hash partitions are near uniform
+  ScopedStage st_alloc(c, "count_setup");
   DevBuf<unsigned long long> pk((size_t)cap * P, s), cursors(P, s), part_base(P, s);
   std::vector<unsigned long long> h_base(P), h_count(P);
   for (int p = 0; p < P; ++p) h_base[p] = (unsigned long long)p * cap;
@@ -488,6 +489,7 @@ void stage_count_kmers(Context* c) {
   const unsigned grid_part = (unsigned)std::min<uint64_t>((c->n_reads + 15) / 16, (uint64_t)kNumSMs * 4);
   unsigned long long h_ones = 0;
   int h_over = 0;
+  st_alloc.stop();
   {
     ScopedStage st(c, "count_partition");
     run_partition(c, maxit, grid_part, part_bits, cursors.p, part_base.p, cap, pk.p, bitmap.p, bits - 1, overflow.p);
@@ -527,12 +529,11 @@ void stage_count_kmers(Context* c) {
   if (const char* e = getenv("BGX_TABLE_SLOTS_LOG2")) slots = 1ull << atoi(e);  // experiment hook
   int tries = 0;
   for (;;) {
-    size_t free_b = 0, total_b = 0;
-    BGX_CUDA(cudaMemGetInfo(&free_b, &total_b));
-    BGX_CHECK(slots * sizeof(CountEntry) < free_b, "not enough device memory for the k-mer table");
+    ScopedStage st_sz(c, "count_table_alloc");
     BGX_CHECK(slots <= (1ull << 32), "k-mer table too large for one GPU shard (slot index is 32-bit)");
     c->table_slots = slots;
-    c->table.alloc(slots, s);
+    c->table.alloc(slots, s);  // throws "out of device memory" if the table cannot fit
+    st_sz.stop();
     {
       ScopedStage st(c, "count_init");
       KLAUNCH(fill_empty_kernel)<<<(unsigned)((slots + 255) / 256), 256, 0, s>>>(reinterpret_cast<uint4*>(c->table.p), slots);
@@ -556,7 +557,11 @@ void stage_count_kmers(Context* c) {
     BGX_CHECK(++tries < 4, "Kmer table too small");
     slots *= 2;
   }
-  pk.release();
+  {
+    ScopedStage st(c, "count_release");
+    pk.release();
+    st.stop();
+  }
 
   // filter (kmer_passes: fwd+rev >= min_count) and build the solid set: ONE sweep into buffers
   // sized by the bound #solid <= K / min_count.
@@ -575,7 +580,7 @@ void stage_count_kmers(Context* c) {
     c->n_solid = h_cnt[1];
     BGX_CHECK(c->n_solid <= capf, "internal: solid k-mer bound violated");
     // "Too many kmers for kmer table!" (kmer_set.cpp:554-556) has no analogue: the set is sized to fit.
-    c->solid_slots = pow2_ceil(std::max<uint64_t>(1024, c->n_solid * 2));
+    c->solid_slots = pow2_ceil(std::max<uint64_t>(1024, c->n_solid * 2));  // load factor in (1/4, 1/2]: short probe runs matter more than L2 residency (measured)
     c->solid.alloc(c->solid_slots, s);
     KLAUNCH(fill_u64_kernel)<<<(unsigned)((c->solid_slots + 255) / 256), 256, 0, s>>>(c->solid.p, c->solid_slots, kEmptyKey);
     if (c->n_solid)

@@ -176,9 +176,9 @@ __global__ void __launch_bounds__(SC_THREADS) scan_final_kernel(const uint32_t* 
 //         record exactly once (2*N*16 bytes per pass)
 //       - records are reordered in shared memory and leave as coalesced per-digit runs
 // Tiles are handed out by an atomic ticket, so every tile a block can wait on has started.
-constexpr int RS_THREADS = 256;
+constexpr int RS_THREADS = 512;
 constexpr int RS_WARPS = RS_THREADS / 32;
-constexpr int RS_ITEMS = 16;
+constexpr int RS_ITEMS = 8;
 constexpr int RS_TILE = RS_THREADS * RS_ITEMS;  // 4096 records
 constexpr int RADIX = 256;
 constexpr uint32_t ST_AGG = 1u << 30;    // tile aggregate available
@@ -316,35 +316,38 @@ onesweep_kernel(const uint64_t* __restrict__ keys_in, const uint64_t* __restrict
 
   // ---- per-digit: warp offsets, tile count, decoupled look-back ---------------------------------
   {
-    const unsigned d = tid;  // RS_THREADS == RADIX
-    uint32_t sum = 0;
+    const unsigned d = tid;  // threads [0, 256) own one digit each
+    uint32_t sum = 0, excl = 0;
+    if (d < RADIX) {
 #pragma unroll
-    for (int w = 0; w < RS_WARPS; ++w) {
-      const uint32_t c = sm.warp_cnt[w][d];
-      sm.warp_cnt[w][d] = sum;
-      sum += c;
-    }
-    // pads were counted as digit 255: remove them from the published count
-    const uint32_t real = (d == RADIX - 1) ? sum - (RS_TILE - nvalid) : sum;
-    volatile uint32_t* st = status + (size_t)tile * RADIX + d;
-    uint32_t excl = 0;
-    if (tile == 0) {
-      *st = ST_INCL | real;
-    } else {
-      *st = ST_AGG | real;
-      for (int64_t j = (int64_t)tile - 1;; --j) {
-        volatile uint32_t* sp = status + (size_t)j * RADIX + d;
-        uint32_t v;
-        do { v = *sp; } while (v == 0);
-        excl += v & ST_VAL;
-        if (v & ST_INCL) break;
+      for (int w = 0; w < RS_WARPS; ++w) {
+        const uint32_t c = sm.warp_cnt[w][d];
+        sm.warp_cnt[w][d] = sum;
+        sum += c;
       }
-      *st = ST_INCL | (excl + real);
+      // pads were counted as digit 255: remove them from the published count
+      const uint32_t real = (d == RADIX - 1) ? sum - (RS_TILE - nvalid) : sum;
+      volatile uint32_t* st = status + (size_t)tile * RADIX + d;
+      if (tile == 0) {
+        *st = ST_INCL | real;
+      } else {
+        *st = ST_AGG | real;
+        for (int64_t j = (int64_t)tile - 1;; --j) {
+          volatile uint32_t* sp = status + (size_t)j * RADIX + d;
+          uint32_t v;
+          do { v = *sp; } while (v == 0);
+          excl += v & ST_VAL;
+          if (v & ST_INCL) break;
+        }
+        *st = ST_INCL | (excl + real);
+      }
     }
     uint32_t tot;
     const uint32_t ex = block_excl_scan_u32(sum, &tot);
-    sm.digit_start[d] = ex;
-    sm.glob_base[d] = digit_base[d] + excl - ex;
+    if (d < RADIX) {
+      sm.digit_start[d] = ex;
+      sm.glob_base[d] = digit_base[d] + excl - ex;
+    }
   }
   __syncthreads();
 

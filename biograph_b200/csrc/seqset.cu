@@ -74,12 +74,11 @@ __device__ __forceinline__ bool prefix_or_equal(const uint64_t* __restrict__ sto
   return lcp >= na;
 }
 
-// first index in [0,n) whose record is not less than x
+// first index in [lo,hi) whose record is not less than x (hi if none)
 __device__ __forceinline__ uint32_t lower_bound_rec(const uint64_t* __restrict__ store,
                                                     const uint64_t* __restrict__ keys,
-                                                    const uint64_t* __restrict__ locs, uint32_t n, uint64_t xk,
-                                                    uint64_t xl) {
-  uint32_t lo = 0, hi = n;
+                                                    const uint64_t* __restrict__ locs, uint32_t lo, uint32_t hi,
+                                                    uint64_t xk, uint64_t xl) {
   while (lo < hi) {
     uint32_t mid = lo + ((hi - lo) >> 1);
     if (rec_less(store, keys[mid], locs[mid], xk, xl)) lo = mid + 1; else hi = mid;
@@ -244,7 +243,7 @@ __device__ __forceinline__ bool covered(const uint64_t* __restrict__ store, cons
                                         uint32_t* where) {
   if (len == 0) { if (where) *where = 0; return true; }  // the empty sequence is a prefix of everything
   uint64_t xk = suffix_key(store, addr, len), xl = make_loc(addr, len);
-  uint32_t lb = lower_bound_rec(store, keys, locs, n, xk, xl);
+  uint32_t lb = lower_bound_rec(store, keys, locs, 0, n, xk, xl);
   if (where) *where = lb;
   return lb < n && prefix_or_equal(store, xk, xl, keys[lb], locs[lb]);
 }
@@ -309,6 +308,41 @@ __global__ void walk_emit_kernel(const uint64_t* __restrict__ store, const uint6
     okeys[off + t] = suffix_key(store, addr + j, len - j);
     olocs[off + t] = make_loc(addr + j, len - j);
   }
+}
+
+// ---- merge of the (few) new records into the sorted survivors ----------------------------------------
+// rank[j] = number of old records that sort before new record j; marks[r] counts the new records
+// inserted in front of old record r.
+__global__ void merge_rank_kernel(const uint64_t* __restrict__ store, const uint64_t* __restrict__ okeys,
+                                  const uint64_t* __restrict__ olocs, uint32_t n_old,
+                                  const uint64_t* __restrict__ nkeys, const uint64_t* __restrict__ nlocs,
+                                  uint32_t n_new, uint32_t* __restrict__ rank, uint32_t* __restrict__ marks) {
+  uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= n_new) return;
+  uint32_t r = lower_bound_rec(store, okeys, olocs, 0, n_old, nkeys[j], nlocs[j]);
+  rank[j] = r;
+  atomicAdd(&marks[r], 1u);
+}
+
+// old record i moves behind the new records ranked <= i: shift = exclusive_scan(marks)[i + 1]
+__global__ void merge_scatter_old_kernel(const uint64_t* __restrict__ okeys, const uint64_t* __restrict__ olocs,
+                                         uint32_t n_old, const uint32_t* __restrict__ marks_excl,
+                                         uint64_t* __restrict__ out_keys, uint64_t* __restrict__ out_locs) {
+  uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n_old) return;
+  uint32_t d = i + marks_excl[i + 1];
+  out_keys[d] = okeys[i];
+  out_locs[d] = olocs[i];
+}
+
+__global__ void merge_scatter_new_kernel(const uint64_t* __restrict__ nkeys, const uint64_t* __restrict__ nlocs,
+                                         uint32_t n_new, const uint32_t* __restrict__ rank,
+                                         uint64_t* __restrict__ out_keys, uint64_t* __restrict__ out_locs) {
+  uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= n_new) return;
+  uint32_t d = rank[j] + j;
+  out_keys[d] = nkeys[j];
+  out_locs[d] = nlocs[j];
 }
 
 // ---- tables ---------------------------------------------------------------------------------------------
@@ -505,7 +539,7 @@ void stage_build_seqset(Context* c) {
   cudaStream_t s = c->stream;
   ScopedStage st_all(c, "seqset_total");
   const uint32_t n_reads = (uint32_t)c->n_reads;
-  BGX_CHECK(c->n_seeds < (1ull << 31), "too many seed records for one GPU shard");
+  BGX_CHECK(c->n_seeds < (1ull << 30), "too many seed records for one GPU shard");
 
   // 1. seeds
   uint32_t n = (uint32_t)c->n_seeds;
@@ -527,8 +561,9 @@ void stage_build_seqset(Context* c) {
   uint32_t n1 = dedup_records(c, keys, locs, keys_alt, locs_alt, n);
   c->set_stat("entries_round1", n1);
 
-  // 3. closure walk
+  // 3. closure walk: the new records are emitted into their own buffers
   uint32_t n_new = 0;
+  DevBuf<uint64_t> nkeys, nlocs;
   {
     ScopedStage st(c, "walk");
     DevBuf<uint32_t> chains(std::max<uint32_t>(n1, 1), s);
@@ -545,30 +580,49 @@ void stage_build_seqset(Context* c) {
       exclusive_scan_u32(ccnt.p, coff.p, n_chains, tot.p, s);
       BGX_CUDA(cudaGetLastError());
       n_new = read_u32(tot.p, s);
-      uint64_t need = (uint64_t)n1 + n_new;
-      BGX_CHECK(need < (1ull << 31), "too many records for one GPU shard");
-      if (need > keys.n) {
-        DevBuf<uint64_t> k2(need + 1024, s), l2(need + 1024, s);
-        BGX_CUDA(cudaMemcpyAsync(k2.p, keys.p, (size_t)n1 * 8, cudaMemcpyDeviceToDevice, s));
-        BGX_CUDA(cudaMemcpyAsync(l2.p, locs.p, (size_t)n1 * 8, cudaMemcpyDeviceToDevice, s));
-        keys = std::move(k2);
-        locs = std::move(l2);
-        keys_alt.alloc(need + 1024, s);
-        locs_alt.alloc(need + 1024, s);
-      }
+      BGX_CHECK((uint64_t)n1 + n_new < (1ull << 30), "too many records for one GPU shard");
+      nkeys.alloc(std::max<uint32_t>(n_new, 1), s);
+      nlocs.alloc(std::max<uint32_t>(n_new, 1), s);
       KLAUNCH(walk_emit_kernel)<<<grid_for((uint64_t)n_chains * 32, 128), 128, 0, s>>>(c->store.p, locs.p, chains.p, ccnt.p, coff.p,
-                                                                              n_chains, keys.p + n1, locs.p + n1);
+                                                                              n_chains, nkeys.p, nlocs.p);
       BGX_CUDA(cudaGetLastError());
     }
     st.stop();
   }
   c->set_stat("walk_new_records", n_new);
 
-  // 4. sort + dedup of survivors + walk output
+  // 4. sort the new records alone, merge them into the sorted survivors by rank, dedup
   uint32_t n2 = n1;
   if (n_new) {
-    sort_records(c, keys, locs, keys_alt, locs_alt, n1 + n_new, "r2");
-    n2 = dedup_records(c, keys, locs, keys_alt, locs_alt, n1 + n_new);
+    {
+      DevBuf<uint64_t> nkeys_alt(n_new, s), nlocs_alt(n_new, s);
+      sort_records(c, nkeys, nlocs, nkeys_alt, nlocs_alt, n_new, "r2");
+    }
+    const uint32_t nm = n1 + n_new;
+    {
+      ScopedStage st(c, "merge");
+      if ((size_t)nm > keys_alt.n) {
+        keys_alt.alloc((size_t)nm + 1024, s);
+        locs_alt.alloc((size_t)nm + 1024, s);
+      }
+      DevBuf<uint32_t> rank(n_new, s), marks((size_t)n1 + 2, s);
+      BGX_CUDA(cudaMemsetAsync(marks.p, 0, ((size_t)n1 + 2) * 4, s));
+      KLAUNCH(merge_rank_kernel)<<<grid_for(n_new, 128), 128, 0, s>>>(c->store.p, keys.p, locs.p, n1, nkeys.p, nlocs.p, n_new,
+                                                             rank.p, marks.p);
+      exclusive_scan_u32(marks.p, marks.p, (size_t)n1 + 2, nullptr, s);
+      if (n1) KLAUNCH(merge_scatter_old_kernel)<<<grid_for(n1, 256), 256, 0, s>>>(keys.p, locs.p, n1, marks.p, keys_alt.p, locs_alt.p);
+      KLAUNCH(merge_scatter_new_kernel)<<<grid_for(n_new, 256), 256, 0, s>>>(nkeys.p, nlocs.p, n_new, rank.p, keys_alt.p, locs_alt.p);
+      BGX_CUDA(cudaGetLastError());
+      std::swap(keys, keys_alt);
+      std::swap(locs, locs_alt);
+      if ((size_t)nm > keys_alt.n) {  // dedup writes into the alt buffers
+        keys_alt.alloc((size_t)nm + 1024, s);
+        locs_alt.alloc((size_t)nm + 1024, s);
+      }
+      c->add_stat("alg_bytes_merge", 32.0 * nm + 8.0 * n1);
+      st.stop();
+    }
+    n2 = dedup_records(c, keys, locs, keys_alt, locs_alt, nm);
   }
   c->n_entries = n2;
   c->set_stat("entries", n2);

@@ -20,5 +20,6 @@ for i in range(runs):
     ms = g.timer_stop()
     st = g.stats()
     print(f"run {i}: {ms:.2f} ms  " + " ".join(f"{k[3:]}={v:.2f}" for k, v in st.items() if k.startswith("ms_")), flush=True)
-print({k: v for k, v in st.items() if not k.startswith("ms_")})
+print({k: v for k, v in st.items() if not k.startswith("ms_") and not k.startswith("hostms_")})
+print("host:", {k[7:]: round(v, 2) for k, v in st.items() if k.startswith("hostms_")})
 g.close()
