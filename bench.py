@@ -290,9 +290,12 @@ def main():
     # ---- roofline of the dominant kernel (live CUDA-event time inside the timed steps) -------------------------
     peak, peak_src = measured_peak_gbs()
     kern_ms = {k_[3:]: v for k_, v in st_mean.items() if k_.startswith("ms_")}
-    K = st_mean.get("kmer_instances", 0.0)
+    kernel_of = {"count_partition": "kmer_partition_kernel", "count_kernel": "kmer_upsert_kernel",
+                 "correct_kernel": "correct_kernel", "sort_radix": "radix_hist_kernel + onesweep_kernel x passes"}
+    # algorithmic bytes per launch, as defined in DESIGN.md section 3 (reported by the library per run)
     alg = {
-        "count_kernel": bases / 4 + 32.0 * K,                       # SURVEY 8d count, without table init/sweep
+        "count_partition": st_mean.get("alg_bytes_count_partition", 0.0),
+        "count_kernel": st_mean.get("alg_bytes_count_kernel", 0.0),
         "correct_kernel": st_mean.get("alg_bytes_correct", 0.0),
         "sort_radix": st_mean.get("alg_bytes_sort_radix", 0.0),
     }
@@ -301,8 +304,8 @@ def main():
         ms = kern_ms.get(name, 0.0)
         if ms > 0:
             stages[name] = {"ms": ms, "alg_bytes": b_, "achieved_gbs": b_ / ms / 1e6, "frac": b_ / ms / 1e6 / peak}
-    dom = max(("count_kernel", "correct_kernel", "sort_radix"), key=lambda n_: kern_ms.get(n_, 0.0))
-    roof = {"bound": "hbm", "kernel": dom, "achieved": stages.get(dom, {}).get("achieved_gbs"), "peak": peak,
+    dom = max(alg, key=lambda n_: kern_ms.get(n_, 0.0))
+    roof = {"bound": "hbm", "kernel": kernel_of[dom], "stage": dom, "achieved": stages.get(dom, {}).get("achieved_gbs"), "peak": peak,
             "unit": "GB/s", "frac": stages.get(dom, {}).get("frac"), "traffic": None, "peak_source": peak_src,
             "stages": stages, "share_of_step": kern_ms.get(dom, 0.0) / (dev_ms / args.steps)}
     tr = os.path.join(ROOT, "profiles", "traffic.json")

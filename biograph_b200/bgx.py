@@ -41,7 +41,7 @@ EXPORTS = ["bgx_default_options", "bgx_last_error", "bgx_version", "bgx_device_c
            "bgx_free", "bgx_add_reads_ascii", "bgx_add_reads_packed", "bgx_count_kmers", "bgx_export_kmers",
            "bgx_correct", "bgx_export_corrected", "bgx_build_seqset", "bgx_export_seqset",
            "bgx_export_entries_ascii", "bgx_run", "bgx_reset_results", "bgx_clear_reads", "bgx_stats_json", "bgx_timer_start", "bgx_timer_stop",
-           "bgx_launch_count", "bgx_debug_sort_pairs"]
+           "bgx_launch_count", "bgx_debug_sort_pairs", "bgx_dist_unique_id", "bgx_dist_init", "bgx_seqset_layout"]
 
 
 def load_library():
@@ -79,6 +79,9 @@ def load_library():
     L.bgx_timer_stop.argtypes = [vp, C.POINTER(C.c_double)]
     L.bgx_launch_count.restype = C.c_uint64
     L.bgx_debug_sort_pairs.argtypes = [vp, vp, vp, C.c_uint64, C.c_int, C.c_int]
+    L.bgx_dist_unique_id.argtypes = [vp]
+    L.bgx_dist_init.argtypes = [vp, C.c_int32, C.c_int32, vp]
+    L.bgx_seqset_layout.argtypes = [vp, C.c_uint64 * 6]
     _LIB = L
     return L
 
@@ -269,6 +272,25 @@ class Bgx:
     def run(self):
         self._ck(self.L.bgx_run(self.h))
 
+    # -- multi-GPU ------------------------------------------------------------------------------------
+    @staticmethod
+    def unique_id():
+        """rank 0: 128-byte NCCL id to broadcast to every rank"""
+        L = load_library()
+        buf = (C.c_uint8 * 128)()
+        if L.bgx_dist_unique_id(buf):
+            raise BgxError(L.bgx_last_error().decode())
+        return bytes(buf)
+
+    def dist_init(self, world_size, rank, unique_id):
+        buf = (C.c_uint8 * 128).from_buffer_copy(unique_id)
+        self._ck(self.L.bgx_dist_init(self.h, world_size, rank, buf))
+
+    def seqset_layout(self):
+        lay = (C.c_uint64 * 6)()
+        self._ck(self.L.bgx_seqset_layout(self.h, lay))
+        return dict(zip(("n", "n_global", "first", "prev_words", "sub_words", "acc_words"), (int(v) for v in lay)))
+
     def export_seqset(self):
         n, ml = C.c_uint64(), C.c_uint32()
         ps, psh = C.c_void_p(), C.c_void_p()
@@ -277,8 +299,9 @@ class Bgx:
         self._ck(self.L.bgx_export_seqset(self.h, C.byref(n), C.byref(ml), C.byref(ps), C.byref(psh), pb, psub, pacc,
                                           fixed))
         N = n.value
-        words, subw, accw = (N + 63) // 64, (N + 511) // 512, (N + 1 + 511) // 512
-        out = {"n": N, "max_entry_len": ml.value, "sizes": self._take(ps, N, np.uint16),
+        lay = self.seqset_layout()
+        words, subw, accw = lay["prev_words"], lay["sub_words"], lay["acc_words"]
+        out = {"n": N, "n_global": lay["n_global"], "first": lay["first"], "max_entry_len": ml.value, "sizes": self._take(ps, N, np.uint16),
                "shared": self._take(psh, N, np.uint16), "fixed": np.array(list(fixed), dtype=np.uint64)}
         out["prev"] = np.stack([self._take(C.c_void_p(pb[b]), words, np.uint64) for b in range(4)]) if True else None
         out["subaccum"] = [self._take(C.c_void_p(psub[b]), subw, np.uint64) for b in range(4)]
@@ -321,3 +344,18 @@ class Bgx:
         buf = C.create_string_buffer(1 << 16)
         self._ck(self.L.bgx_stats_json(self.h, buf, len(buf)))
         return json.loads(buf.value.decode())
+
+
+def assemble_seqset(parts):
+    """Concatenate the per-rank tables of a multi-GPU build (in rank order) into the whole seqset.
+    Every rank but the last holds a multiple of 512 entries, so the bit vectors and their bitcount
+    index simply concatenate; `fixed` and `max_entry_len` are global on every rank."""
+    parts = sorted(parts, key=lambda p: p["first"])
+    n = sum(p["n"] for p in parts)
+    assert all(p["n_global"] == n for p in parts)
+    out = {"n": n, "max_entry_len": parts[0]["max_entry_len"], "fixed": parts[0]["fixed"],
+           "sizes": np.concatenate([p["sizes"] for p in parts]), "shared": np.concatenate([p["shared"] for p in parts]),
+           "prev": np.stack([np.concatenate([p["prev"][b] for p in parts]) for b in range(4)]),
+           "subaccum": [np.concatenate([p["subaccum"][b] for p in parts]) for b in range(4)],
+           "accum": [np.concatenate([p["accum"][b] for p in parts]) for b in range(4)]}
+    return out

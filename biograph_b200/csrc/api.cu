@@ -120,10 +120,11 @@ void bgx_destroy(bgx_ctx* x) {
     Context& c = x->c;
     // release buffers while the stream is alive
     c.words.release(); c.nmask.release(); c.word_off.release(); c.lens.release();
-    c.table.release(); c.solid.release(); c.store.release(); c.clen.release(); c.ncorr.release();
+    c.table.release(); c.solid.release(); c.store.release(); c.gstore.release(); c.clen.release(); c.ncorr.release();
     c.next_fwd.release(); c.next_rev.release(); c.ent_key.release(); c.ent_loc.release();
     c.sizes.release(); c.shared.release(); c.prev_bits.release(); c.prev_sub.release(); c.prev_acc.release();
   }
+  dist_destroy(&x->c);
   dev_trim(s);
   cudaStreamDestroy(s);
   delete x;
@@ -227,7 +228,7 @@ int bgx_run(bgx_ctx* x) {
 
 int bgx_reset_results(bgx_ctx* x) {
   CTX_GUARD({
-    c->table.release(); c->solid.release(); c->store.release(); c->clen.release(); c->ncorr.release();
+    c->table.release(); c->solid.release(); c->store.release(); c->gstore.release(); c->clen.release(); c->ncorr.release();
     c->next_fwd.release(); c->next_rev.release(); c->ent_key.release(); c->ent_loc.release();
     c->sizes.release(); c->shared.release(); c->prev_bits.release(); c->prev_sub.release(); c->prev_acc.release();
     c->counted = c->corrected = c->built = false;
@@ -274,6 +275,26 @@ int bgx_timer_stop(bgx_ctx* x, double* elapsed_ms) {
     float ms = 0;
     BGX_CUDA(cudaEventElapsedTime(&ms, c->t0, c->t1));
     *elapsed_ms = ms;
+  })
+}
+
+int bgx_dist_unique_id(uint8_t id[128]) {
+  return guard([&] { dist_get_unique_id(id); });
+}
+
+int bgx_dist_init(bgx_ctx* x, int32_t world_size, int32_t rank, const uint8_t id[128]) {
+  CTX_GUARD({ dist_init(c, world_size, rank, id); })
+}
+
+int bgx_seqset_layout(bgx_ctx* x, uint64_t layout[6]) {
+  CTX_GUARD({
+    BGX_CHECK(c->built, "bgx_seqset_layout: call bgx_build_seqset first");
+    layout[0] = c->n_entries;
+    layout[1] = c->n_entries_global;
+    layout[2] = c->first_entry_global;
+    layout[3] = c->prev_words;
+    layout[4] = c->sub_words;
+    layout[5] = c->acc_words;
   })
 }
 

@@ -7,6 +7,7 @@
 #include <vector>
 
 #include "../../include/bgx.h"
+#include "dist.h"
 #include "prims.cuh"
 
 namespace bgx {
@@ -25,6 +26,7 @@ struct Context {
   int device = 0;
   cudaStream_t stream = nullptr;
   cudaEvent_t t0 = nullptr, t1 = nullptr;  // bgx_timer_start/stop
+  Dist dist;                               // multi-GPU: world size, rank, NCCL communicator
 
   // ---- reads (device resident) ---------------------------------------------------------
   uint64_t n_reads = 0;
@@ -50,6 +52,9 @@ struct Context {
   // ---- correction stage --------------------------------------------------------------------
   bool corrected = false;
   DevBuf<uint64_t> store;        // corrected base store: [fwd reads | rc reads] 2*n_words + 1 words
+  DevBuf<uint64_t> gstore;       // multi-GPU: every rank's store, concatenated in rank order (replicated)
+  uint64_t gstore_word_base = 0; // word offset of this rank's store inside gstore
+  const uint64_t* seq_store() const { return gstore.p ? gstore.p : store.p; }
   DevBuf<uint16_t> clen;         // corrected length per read (0 = dropped)
   DevBuf<uint8_t> ncorr;         // substitutions per read
   DevBuf<uint16_t> next_fwd, next_rev;
@@ -65,6 +70,8 @@ struct Context {
   DevBuf<uint64_t> prev_sub, prev_acc; // 4 * sub_words, 4 * acc_words
   uint64_t prev_words = 0, sub_words = 0, acc_words = 0;
   uint64_t fixed[5] = {0, 0, 0, 0, 0};
+  uint64_t n_entries_global = 0;       // multi-GPU: entries over all ranks; this rank holds
+  uint64_t first_entry_global = 0;     //   [first_entry_global, first_entry_global + n_entries)
 
   // ---- stats ---------------------------------------------------------------------------------
   std::map<std::string, double> stats;       // numeric stats (ms, counts, bytes)

@@ -1,0 +1,173 @@
+// dist.cu -- NCCL binding (run-time) and the collectives the sharded build uses.
+#include "dist.h"
+
+#include <dlfcn.h>
+#include <nccl.h>
+
+#include <cstring>
+#include <mutex>
+
+#include "ctx.h"
+
+namespace bgx {
+namespace {
+
+struct NcclApi {
+  void* handle = nullptr;
+  ncclResult_t (*GetUniqueId)(ncclUniqueId*) = nullptr;
+  ncclResult_t (*CommInitRank)(ncclComm_t*, int, ncclUniqueId, int) = nullptr;
+  ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
+  ncclResult_t (*AllReduce)(const void*, void*, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t) = nullptr;
+  ncclResult_t (*AllGather)(const void*, void*, size_t, ncclDataType_t, ncclComm_t, cudaStream_t) = nullptr;
+  ncclResult_t (*Send)(const void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
+  ncclResult_t (*Recv)(void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
+  ncclResult_t (*GroupStart)() = nullptr;
+  ncclResult_t (*GroupEnd)() = nullptr;
+  const char* (*GetErrorString)(ncclResult_t) = nullptr;
+};
+
+NcclApi& nccl() {
+  static NcclApi api;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    // by SONAME: if the process already holds an NCCL (e.g. the one torch bundles) that one is reused
+    void* h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
+    if (!h) h = dlopen("libnccl.so", RTLD_NOW | RTLD_GLOBAL);
+    if (!h) return;
+    api.handle = h;
+#define BGX_SYM(field, name) api.field = reinterpret_cast<decltype(api.field)>(dlsym(h, name))
+    BGX_SYM(GetUniqueId, "ncclGetUniqueId");
+    BGX_SYM(CommInitRank, "ncclCommInitRank");
+    BGX_SYM(CommDestroy, "ncclCommDestroy");
+    BGX_SYM(AllReduce, "ncclAllReduce");
+    BGX_SYM(AllGather, "ncclAllGather");
+    BGX_SYM(Send, "ncclSend");
+    BGX_SYM(Recv, "ncclRecv");
+    BGX_SYM(GroupStart, "ncclGroupStart");
+    BGX_SYM(GroupEnd, "ncclGroupEnd");
+    BGX_SYM(GetErrorString, "ncclGetErrorString");
+#undef BGX_SYM
+  });
+  BGX_CHECK(api.handle && api.GetUniqueId && api.CommInitRank && api.Send && api.Recv && api.GroupStart && api.GroupEnd &&
+                api.AllReduce && api.AllGather,
+            "NCCL (libnccl.so.2) is not available: multi-GPU builds need it");
+  return api;
+}
+
+#define BGX_NCCL(expr)                                                                                 \
+  do {                                                                                                 \
+    ncclResult_t r__ = (expr);                                                                         \
+    if (r__ != ncclSuccess)                                                                            \
+      throw ::bgx::Error(std::string(#expr) + " failed: " + (nccl().GetErrorString ? nccl().GetErrorString(r__) : "?")); \
+  } while (0)
+
+inline ncclComm_t comm_of(Context* c) { return reinterpret_cast<ncclComm_t>(c->dist.comm); }
+
+}  // namespace
+
+void dist_get_unique_id(uint8_t id[128]) {
+  static_assert(sizeof(ncclUniqueId) == 128, "ncclUniqueId is 128 bytes");
+  ncclUniqueId u;
+  BGX_NCCL(nccl().GetUniqueId(&u));
+  memcpy(id, &u, 128);
+}
+
+void dist_init(Context* c, int nranks, int rank, const uint8_t id[128]) {
+  BGX_CHECK(nranks >= 1 && rank >= 0 && rank < nranks, "bgx_dist_init: bad rank / world size");
+  BGX_CHECK((nranks & (nranks - 1)) == 0 && nranks <= 64, "bgx_dist_init: world size must be a power of two <= 64");
+  BGX_CHECK(c->dist.comm == nullptr, "bgx_dist_init: already initialised");
+  BGX_CHECK(c->n_reads == 0, "bgx_dist_init: call before adding reads");
+  c->dist.nranks = nranks;
+  c->dist.rank = rank;
+  if (nranks == 1) return;
+  ncclUniqueId u;
+  memcpy(&u, id, 128);
+  ncclComm_t comm = nullptr;
+  BGX_NCCL(nccl().CommInitRank(&comm, nranks, u, rank));
+  c->dist.comm = comm;
+}
+
+void dist_destroy(Context* c) {
+  if (c->dist.comm) {
+    nccl().CommDestroy(comm_of(c));
+    c->dist.comm = nullptr;
+  }
+  c->dist.nranks = 1;
+  c->dist.rank = 0;
+}
+
+void dist_allreduce_sum_u64(Context* c, unsigned long long* buf, size_t n) {
+  if (c->dist.nranks == 1 || n == 0) return;
+  BGX_NCCL(nccl().AllReduce(buf, buf, n, ncclUint64, ncclSum, comm_of(c), c->stream));
+}
+
+void dist_allgather_bytes(Context* c, const void* send, void* recv, size_t bytes) {
+  if (c->dist.nranks == 1) {
+    if (send != recv && bytes) BGX_CUDA(cudaMemcpyAsync(recv, send, bytes, cudaMemcpyDeviceToDevice, c->stream));
+    return;
+  }
+  if (bytes == 0) return;
+  BGX_NCCL(nccl().AllGather(send, recv, bytes, ncclUint8, comm_of(c), c->stream));
+}
+
+void dist_p2p_batch(Context* c, const std::vector<P2P>& sends, const std::vector<P2P>& recvs) {
+  if (c->dist.nranks == 1) {
+    // degenerate world: a send to self pairs with the recv of the same ordinal
+    BGX_CHECK(sends.size() == recvs.size(), "dist_p2p_batch: unmatched self exchange");
+    for (size_t i = 0; i < sends.size(); ++i) {
+      BGX_CHECK(sends[i].bytes == recvs[i].bytes, "dist_p2p_batch: self exchange size mismatch");
+      if (sends[i].bytes)
+        BGX_CUDA(cudaMemcpyAsync(recvs[i].recv, sends[i].send, sends[i].bytes, cudaMemcpyDeviceToDevice, c->stream));
+    }
+    return;
+  }
+  BGX_NCCL(nccl().GroupStart());
+  for (const P2P& s : sends)
+    if (s.bytes) BGX_NCCL(nccl().Send(s.send, s.bytes, ncclUint8, s.peer, comm_of(c), c->stream));
+  for (const P2P& r : recvs)
+    if (r.bytes) BGX_NCCL(nccl().Recv(r.recv, r.bytes, ncclUint8, r.peer, comm_of(c), c->stream));
+  BGX_NCCL(nccl().GroupEnd());
+}
+
+void dist_alltoallv(Context* c, const void* send, const uint64_t* send_off, const uint64_t* send_cnt, void* recv,
+                    const uint64_t* recv_off, const uint64_t* recv_cnt, size_t elem_bytes) {
+  std::vector<P2P> sends, recvs;
+  for (int r = 0; r < c->dist.nranks; ++r) {
+    P2P s, q;
+    s.send = static_cast<const char*>(send) + send_off[r] * elem_bytes;
+    s.bytes = send_cnt[r] * elem_bytes;
+    s.peer = r;
+    q.recv = static_cast<char*>(recv) + recv_off[r] * elem_bytes;
+    q.bytes = recv_cnt[r] * elem_bytes;
+    q.peer = r;
+    sends.push_back(s);
+    recvs.push_back(q);
+  }
+  dist_p2p_batch(c, sends, recvs);
+}
+
+void dist_allgather_host_u64(Context* c, const uint64_t* in, size_t n, uint64_t* out) {
+  const int N = c->dist.nranks;
+  if (N == 1) {
+    memcpy(out, in, n * 8);
+    return;
+  }
+  cudaStream_t s = c->stream;
+  DevBuf<uint64_t> d_in(n, s), d_out(n * N, s);
+  BGX_CUDA(cudaMemcpyAsync(d_in.p, in, n * 8, cudaMemcpyHostToDevice, s));
+  dist_allgather_bytes(c, d_in.p, d_out.p, n * 8);
+  BGX_CUDA(cudaMemcpyAsync(out, d_out.p, n * N * 8, cudaMemcpyDeviceToHost, s));
+  BGX_CUDA(cudaStreamSynchronize(s));
+}
+
+void dist_allreduce_sum_host_u64(Context* c, uint64_t* v, size_t n) {
+  if (c->dist.nranks == 1 || n == 0) return;
+  cudaStream_t s = c->stream;
+  DevBuf<unsigned long long> d(n, s);
+  BGX_CUDA(cudaMemcpyAsync(d.p, v, n * 8, cudaMemcpyHostToDevice, s));
+  dist_allreduce_sum_u64(c, d.p, n);
+  BGX_CUDA(cudaMemcpyAsync(v, d.p, n * 8, cudaMemcpyDeviceToHost, s));
+  BGX_CUDA(cudaStreamSynchronize(s));
+}
+
+}  // namespace bgx

@@ -1,0 +1,55 @@
+// dist.h -- multi-GPU plumbing: one context per rank (one process per GPU), NCCL over NVLink.
+//
+// The reference is single-process (threads + temp files) and has no collective anywhere
+// (SURVEY 5 / 8e); its two shard keys -- the hash partition of a k-mer (bs/kmer_counter.h:167-178)
+// and the prefix partition of a suffix (bs/part_repo.cpp:32-45) -- are the keys the exchanges
+// below route by.  NCCL is bound at run time (dlopen of libnccl.so.2), so libbgx.so loads on a
+// box without NCCL and single-GPU builds never touch it.
+#pragma once
+
+#include <cstddef>
+#include <cstdint>
+#include <vector>
+
+#include <cuda_runtime.h>
+
+namespace bgx {
+
+struct Context;
+
+struct Dist {
+  int nranks = 1;
+  int rank = 0;
+  void* comm = nullptr;  // ncclComm_t
+};
+
+// rank 0: a fresh NCCL unique id (128 bytes) to hand to every rank out of band
+void dist_get_unique_id(uint8_t id[128]);
+void dist_init(Context* c, int nranks, int rank, const uint8_t id[128]);
+void dist_destroy(Context* c);
+
+// ---- collectives on device buffers, enqueued on the context's stream ---------------------------------
+void dist_allreduce_sum_u64(Context* c, unsigned long long* buf, size_t n);
+// every rank contributes `bytes` bytes; recv holds nranks * bytes
+void dist_allgather_bytes(Context* c, const void* send, void* recv, size_t bytes);
+// personalised exchange: rank r gets send[send_off[r] .. +send_cnt[r]) and writes what rank s
+// sent it to recv[recv_off[s] .. +recv_cnt[s]) (units: elements of elem_bytes).  One grouped
+// ncclSend/ncclRecv batch = an all-to-all over NVSwitch.
+void dist_alltoallv(Context* c, const void* send, const uint64_t* send_off, const uint64_t* send_cnt, void* recv,
+                    const uint64_t* recv_off, const uint64_t* recv_cnt, size_t elem_bytes);
+// grouped point-to-point batch for irregular layouts
+struct P2P {
+  const void* send = nullptr;
+  void* recv = nullptr;
+  size_t bytes = 0;
+  int peer = 0;
+};
+void dist_p2p_batch(Context* c, const std::vector<P2P>& sends, const std::vector<P2P>& recvs);
+
+// ---- small host-side metadata (counts, boundaries): staged through the device, synchronous -------------
+// out[r * n .. (r+1) * n) = rank r's in[0..n)
+void dist_allgather_host_u64(Context* c, const uint64_t* in, size_t n, uint64_t* out);
+// in place: v[i] = sum over ranks of v[i]
+void dist_allreduce_sum_host_u64(Context* c, uint64_t* v, size_t n);
+
+}  // namespace bgx

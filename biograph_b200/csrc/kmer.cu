@@ -13,6 +13,7 @@
 // table once and builds the 8-byte-slot solid hash set that correction probes.
 #include <algorithm>
 #include <cmath>
+#include <numeric>
 #include <cstdlib>
 #include <vector>
 
@@ -33,7 +34,11 @@ constexpr int kPartWarps = kPartThreads / 32;
 
 // The table slot of a k-mer is the TOP bits of its hash, so the top part_bits bits (its partition)
 // select a contiguous 1/P slice of the table.
-__device__ __forceinline__ uint64_t table_slot(uint64_t h, int log2_slots) { return h >> (64 - log2_slots); }
+// With 2^rank_bits GPUs the top rank_bits bits of the hash name the owning rank (a contiguous block
+// of partitions) and are dropped before indexing that rank's table.
+__device__ __forceinline__ uint64_t table_slot(uint64_t h, int log2_slots, int rank_bits) {
+  return (h << rank_bits) >> (64 - log2_slots);
+}
 
 // Pass 1: extract every k-mer instance, bucket it by hash partition.
 //   * the block's reads (kPartWarps*RPW consecutive reads) are pulled into shared memory with
@@ -200,7 +205,7 @@ __global__ void __launch_bounds__(256, 4) kmer_upsert_kernel(const unsigned long
                                                              const unsigned long long* __restrict__ part_count,
                                                              uint32_t tiles_per_part, int k,
                                                              CountEntry* __restrict__ table, int log2_slots,
-                                                             int* __restrict__ overflow) {
+                                                             int rank_bits, int* __restrict__ overflow) {
   const uint32_t p = blockIdx.x / tiles_per_part, t = blockIdx.x % tiles_per_part;
   const unsigned long long cnt = part_count[p];
   const unsigned long long first = (unsigned long long)t * kUpsTile;
@@ -230,7 +235,7 @@ __global__ void __launch_bounds__(256, 4) kmer_upsert_kernel(const unsigned long
     if (fl ? is_last : is_first) f |= kFwdFlag;
     if (fl ? is_first : is_last) f |= kRevFlag;
     key[i] = valid ? (canon | f) : ~0ULL;
-    slot[i] = (uint32_t)table_slot(mix64(canon), log2_slots);
+    slot[i] = (uint32_t)table_slot(mix64(canon), log2_slots, rank_bits);
   }
 #pragma unroll
   for (int i = 0; i < kUpsItems; ++i)
@@ -267,6 +272,29 @@ __global__ void __launch_bounds__(256, 4) kmer_upsert_kernel(const unsigned long
     if (f) atomicOr(&table[s].key, (unsigned long long)f);
     // one 32-bit RED on the fwd (low) or rev (high) half of the counter word
     atomicAdd(reinterpret_cast<unsigned int*>(&table[s].cnt) + (flip[i] ? 1 : 0), 1u);
+  }
+}
+
+// Distinct estimate over partitioned instance words (multi-GPU: run by the owner after the
+// exchange, because the fused estimate of pass 1 only saw this rank's own reads).
+__global__ void __launch_bounds__(256) kmer_estimate_words_kernel(const unsigned long long* __restrict__ pk,
+                                                                  const unsigned long long* __restrict__ part_base,
+                                                                  const unsigned long long* __restrict__ part_count,
+                                                                  uint32_t tiles_per_part, int k,
+                                                                  unsigned int* __restrict__ bitmap, uint64_t bit_mask) {
+  const uint32_t p = blockIdx.x / tiles_per_part, t = blockIdx.x % tiles_per_part;
+  const unsigned long long cnt = part_count[p];
+  const unsigned long long* src = pk + part_base[p];
+#pragma unroll
+  for (int i = 0; i < kUpsItems; ++i) {
+    const unsigned long long idx = (unsigned long long)t * kUpsTile + (unsigned long long)i * 256 + threadIdx.x;
+    if (idx >= cnt) continue;
+    bool fl;
+    const uint64_t h = mix64(canonicalize(src[idx] & kKmerMask, k, fl));
+    if ((h & 15) == 0) {
+      const uint64_t bit = (h >> 4) & bit_mask;
+      atomicOr(&bitmap[bit >> 5], 1u << (bit & 31));
+    }
   }
 }
 
@@ -458,17 +486,24 @@ int log2_exact(uint64_t x) {
 void stage_count_kmers(Context* c) {
   cudaStream_t s = c->stream;
   const int k = c->opt.kmer_size;
-  BGX_CHECK(c->n_reads > 0, "bgx_count_kmers: no reads");
+  const int N = c->dist.nranks, R = c->dist.rank;
+  const int rank_bits = log2_exact((uint64_t)N);
+  BGX_CHECK(c->n_reads > 0 || N > 1, "bgx_count_kmers: no reads");
   ScopedStage st_all(c, "count_total");
-  const uint64_t K = c->n_kmer_instances;
+  const uint64_t K = c->n_kmer_instances;  // this rank's reads
+  uint64_t K_all = K;                      // all ranks' reads
+  dist_allreduce_sum_host_u64(c, &K_all, 1);
+  const uint64_t K_share = K_all / N;      // instances this rank will own (hash-uniform)
 
   // ---- pass 1: extract + hash-partition every k-mer instance; fused distinct estimate -------------
-  // P partitions so that one partition's slice of the table (~4 B per instance at typical
+  // P partitions so that one partition's slice of the owner's table (~4 B per instance at typical
   // coverage) is at most ~64 MB = half of L2; measured on B200: fewer, larger partitions make
   // pass 1 faster (longer coalesced runs) and pass 2 is insensitive down to 64 MB slices.
+  // Rank r owns the contiguous block of partitions [r*P/N, (r+1)*P/N) (same P on every rank).
   int part_bits = 7;
-  while (part_bits < kMaxPartBits && (K * 4 >> part_bits) > (64ull << 20)) ++part_bits;
+  while (part_bits < kMaxPartBits && (K_all * 4 >> part_bits) > (64ull << 20)) ++part_bits;
   if (const char* e = getenv("BGX_PART_BITS")) part_bits = std::max(1, std::min(kMaxPartBits, atoi(e)));
+  part_bits = std::max(part_bits, rank_bits);
   const int P = 1 << part_bits;
   const int maxit = (int)((std::max<int64_t>((int64_t)c->max_len - k + 1, 1) + 31) / 32);
   BGX_CHECK(maxit <= 8, "read longer than 255 bases");
@@ -481,19 +516,18 @@ void stage_count_kmers(Context* c) {
   BGX_CUDA(cudaMemsetAsync(cursors.p, 0, P * 8, s));
   DevBuf<int> overflow(1, s);
   BGX_CUDA(cudaMemsetAsync(overflow.p, 0, sizeof(int), s));
-  const uint64_t bits = pow2_ceil(std::max<uint64_t>(1 << 20, K / 8));
+  const uint64_t bits = pow2_ceil(std::max<uint64_t>(1 << 20, std::max(K, K_share) / 8));
   DevBuf<unsigned int> bitmap(bits / 32, s);
   DevBuf<unsigned long long> ones(1, s);
   BGX_CUDA(cudaMemsetAsync(bitmap.p, 0, bits / 8, s));
   BGX_CUDA(cudaMemsetAsync(ones.p, 0, 8, s));
-  const unsigned grid_part = (unsigned)std::min<uint64_t>((c->n_reads + 15) / 16, (uint64_t)kNumSMs * 4);
   unsigned long long h_ones = 0;
   int h_over = 0;
   st_alloc.stop();
   {
     ScopedStage st(c, "count_partition");
-    run_partition(c, maxit, grid_part, part_bits, cursors.p, part_base.p, cap, pk.p, bitmap.p, bits - 1, overflow.p);
-    KLAUNCH(popcount_kernel)<<<(unsigned)((bits / 32 + 255) / 256), 256, 0, s>>>(bitmap.p, bits / 32, ones.p);
+    if (c->n_reads) run_partition(c, maxit, 0, part_bits, cursors.p, part_base.p, cap, pk.p, bitmap.p, bits - 1, overflow.p);
+    if (N == 1) KLAUNCH(popcount_kernel)<<<(unsigned)((bits / 32 + 255) / 256), 256, 0, s>>>(bitmap.p, bits / 32, ones.p);
     BGX_CUDA(cudaGetLastError());
     BGX_CUDA(cudaMemcpyAsync(&h_ones, ones.p, 8, cudaMemcpyDeviceToHost, s));
     BGX_CUDA(cudaMemcpyAsync(&h_over, overflow.p, sizeof(int), cudaMemcpyDeviceToHost, s));
@@ -509,7 +543,11 @@ void stage_count_kmers(Context* c) {
       BGX_CUDA(cudaMemcpyAsync(part_base.p, h_base.data(), P * 8, cudaMemcpyHostToDevice, s));
       BGX_CUDA(cudaMemsetAsync(cursors.p, 0, P * 8, s));
       BGX_CUDA(cudaMemsetAsync(overflow.p, 0, sizeof(int), s));
-      run_partition(c, maxit, grid_part, part_bits, cursors.p, part_base.p, cap, pk.p, bitmap.p, bits - 1, overflow.p);
+      BGX_CUDA(cudaMemsetAsync(bitmap.p, 0, bits / 8, s));
+      BGX_CUDA(cudaMemsetAsync(ones.p, 0, 8, s));
+      run_partition(c, maxit, 0, part_bits, cursors.p, part_base.p, cap, pk.p, bitmap.p, bits - 1, overflow.p);
+      if (N == 1) KLAUNCH(popcount_kernel)<<<(unsigned)((bits / 32 + 255) / 256), 256, 0, s>>>(bitmap.p, bits / 32, ones.p);
+      BGX_CUDA(cudaMemcpyAsync(&h_ones, ones.p, 8, cudaMemcpyDeviceToHost, s));
       BGX_CUDA(cudaMemcpyAsync(&h_over, overflow.p, sizeof(int), cudaMemcpyDeviceToHost, s));
       BGX_CUDA(cudaStreamSynchronize(s));
       BGX_CHECK(!h_over, "internal: exact partition pass overflowed");
@@ -517,8 +555,69 @@ void stage_count_kmers(Context* c) {
     }
     st.stop();
   }
+
+  // ---- multi-GPU: every partition goes to its owner (NCCL all-to-all over NVLink) ------------------
+  // After this block (pk, part_base, cursors) describe the Pl partitions this rank owns, each one
+  // contiguous and holding the instances of ALL ranks' reads.
+  int Pl = P;
+  if (N > 1) {
+    ScopedStage st(c, "count_exchange");
+    Pl = P / N;
+    const int p0 = R * Pl;
+    std::vector<uint64_t> mine(h_count.begin(), h_count.end()), all((size_t)N * P);
+    dist_allgather_host_u64(c, mine.data(), P, all.data());
+    std::vector<unsigned long long> l_base(Pl), l_count(Pl);
+    uint64_t total = 0;
+    std::vector<P2P> sends, recvs;
+    for (int p = 0; p < P; ++p) {
+      P2P x;
+      x.send = pk.p + h_base[p];
+      x.bytes = (size_t)h_count[p] * 8;
+      x.peer = p / Pl;
+      sends.push_back(x);
+    }
+    for (int pl = 0; pl < Pl; ++pl) {
+      l_base[pl] = total;
+      for (int src = 0; src < N; ++src) total += all[(size_t)src * P + p0 + pl];
+      l_count[pl] = total - l_base[pl];
+    }
+    DevBuf<unsigned long long> rbuf(std::max<uint64_t>(total, 1), s);
+    // recvs from one peer must be posted in the order that peer sends: ascending partition
+    for (int src = 0; src < N; ++src) {
+      for (int pl = 0; pl < Pl; ++pl) {
+        uint64_t off = l_base[pl];
+        for (int q = 0; q < src; ++q) off += all[(size_t)q * P + p0 + pl];
+        P2P x;
+        x.recv = rbuf.p + off;
+        x.bytes = (size_t)all[(size_t)src * P + p0 + pl] * 8;
+        x.peer = src;
+        recvs.push_back(x);
+      }
+    }
+    dist_p2p_batch(c, sends, recvs);
+    pk = std::move(rbuf);
+    part_base.alloc(Pl, s);
+    cursors.alloc(Pl, s);
+    h_base.assign(l_base.begin(), l_base.end());
+    h_count.assign(l_count.begin(), l_count.end());
+    BGX_CUDA(cudaMemcpyAsync(part_base.p, h_base.data(), Pl * 8, cudaMemcpyHostToDevice, s));
+    BGX_CUDA(cudaMemcpyAsync(cursors.p, h_count.data(), Pl * 8, cudaMemcpyHostToDevice, s));
+    c->add_stat("count_exchange_bytes_out", 8.0 * (double)std::accumulate(mine.begin(), mine.end(), (uint64_t)0));
+    st.stop();
+  }
   uint64_t n_inst = 0, max_count = 0;
-  for (int p = 0; p < P; ++p) { n_inst += h_count[p]; max_count = std::max<uint64_t>(max_count, h_count[p]); }
+  for (int p = 0; p < Pl; ++p) { n_inst += h_count[p]; max_count = std::max<uint64_t>(max_count, h_count[p]); }
+  const uint32_t tiles_per_part = (uint32_t)std::max<uint64_t>(1, (max_count + kUpsTile - 1) / kUpsTile);
+  BGX_CHECK((uint64_t)tiles_per_part * Pl < (1ull << 31), "too many k-mer tiles for one launch");
+  if (N > 1) {
+    // the owner estimates the distinct count of what it received
+    KLAUNCH(kmer_estimate_words_kernel)<<<tiles_per_part * (uint32_t)Pl, 256, 0, s>>>(pk.p, part_base.p, cursors.p,
+                                                                             tiles_per_part, k, bitmap.p, bits - 1);
+    KLAUNCH(popcount_kernel)<<<(unsigned)((bits / 32 + 255) / 256), 256, 0, s>>>(bitmap.p, bits / 32, ones.p);
+    BGX_CUDA(cudaGetLastError());
+    BGX_CUDA(cudaMemcpyAsync(&h_ones, ones.p, 8, cudaMemcpyDeviceToHost, s));
+    BGX_CUDA(cudaStreamSynchronize(s));
+  }
 
   // ---- size the table: load factor in (1/3, 2/3] of the estimated distinct count -----------------
   const double zero_frac = std::max(1.0 / (double)bits, 1.0 - (double)h_ones / (double)bits);
@@ -542,10 +641,8 @@ void stage_count_kmers(Context* c) {
     BGX_CUDA(cudaMemsetAsync(overflow.p, 0, sizeof(int), s));
     {
       ScopedStage st(c, "count_kernel");
-      const uint32_t tiles_per_part = (uint32_t)std::max<uint64_t>(1, (max_count + kUpsTile - 1) / kUpsTile);
-      BGX_CHECK((uint64_t)tiles_per_part * P < (1ull << 31), "too many k-mer tiles for one launch");
-      KLAUNCH(kmer_upsert_kernel)<<<tiles_per_part * (uint32_t)P, 256, 0, s>>>(pk.p, part_base.p, cursors.p, tiles_per_part, k,
-                                                                      c->table.p, log2_exact(slots), overflow.p);
+      KLAUNCH(kmer_upsert_kernel)<<<tiles_per_part * (uint32_t)Pl, 256, 0, s>>>(pk.p, part_base.p, cursors.p, tiles_per_part, k,
+                                                                       c->table.p, log2_exact(slots), rank_bits, overflow.p);
       BGX_CUDA(cudaGetLastError());
       st.stop();
     }
@@ -557,19 +654,15 @@ void stage_count_kmers(Context* c) {
     BGX_CHECK(++tries < 4, "Kmer table too small");
     slots *= 2;
   }
-  {
-    ScopedStage st(c, "count_release");
-    pk.release();
-    st.stop();
-  }
+  pk.release();
 
   // filter (kmer_passes: fwd+rev >= min_count) and build the solid set: ONE sweep into buffers
-  // sized by the bound #solid <= K / min_count.
+  // sized by the bound #solid <= instances / min_count.
   DevBuf<unsigned long long> counters(2, s);
   unsigned long long h_cnt[2];
   {
     ScopedStage st(c, "count_filter");
-    uint64_t capf = std::min<uint64_t>(slots, K / (uint64_t)c->opt.min_kmer_count + 1);
+    uint64_t capf = std::min<uint64_t>(slots, n_inst / (uint64_t)c->opt.min_kmer_count + 1);
     DevBuf<unsigned long long> sk(capf, s), sc(capf, s);
     BGX_CUDA(cudaMemsetAsync(counters.p, 0, 2 * sizeof(unsigned long long), s));
     KLAUNCH(table_sweep_kernel)<<<(unsigned)((slots + kSweepPerBlock - 1) / kSweepPerBlock), 256, 0, s>>>(
@@ -577,14 +670,29 @@ void stage_count_kmers(Context* c) {
     BGX_CUDA(cudaMemcpyAsync(h_cnt, counters.p, sizeof(h_cnt), cudaMemcpyDeviceToHost, s));
     BGX_CUDA(cudaStreamSynchronize(s));
     c->n_distinct = h_cnt[0];
-    c->n_solid = h_cnt[1];
-    BGX_CHECK(c->n_solid <= capf, "internal: solid k-mer bound violated");
+    uint64_t n_solid_local = h_cnt[1];
+    BGX_CHECK(n_solid_local <= capf, "internal: solid k-mer bound violated");
+    // multi-GPU: every rank needs the whole solid set for correction -> all-gather the owners' lists
+    const unsigned long long* all_keys = sk.p;
+    DevBuf<unsigned long long> gathered;
+    c->n_solid = n_solid_local;
+    if (N > 1) {
+      std::vector<uint64_t> cnts(N), offs(N), zero(N, 0), mine_cnt(N, n_solid_local);
+      dist_allgather_host_u64(c, &n_solid_local, 1, cnts.data());
+      uint64_t tot = 0;
+      for (int r = 0; r < N; ++r) { offs[r] = tot; tot += cnts[r]; }
+      gathered.alloc(std::max<uint64_t>(tot, 1), s);
+      dist_alltoallv(c, sk.p, zero.data(), mine_cnt.data(), gathered.p, offs.data(), cnts.data(), 8);
+      all_keys = gathered.p;
+      c->n_solid = tot;
+      c->set_stat("kmer_solid_owned", (double)n_solid_local);
+    }
     // "Too many kmers for kmer table!" (kmer_set.cpp:554-556) has no analogue: the set is sized to fit.
     c->solid_slots = pow2_ceil(std::max<uint64_t>(1024, c->n_solid * 2));  // load factor in (1/4, 1/2]: short probe runs matter more than L2 residency (measured)
     c->solid.alloc(c->solid_slots, s);
     KLAUNCH(fill_u64_kernel)<<<(unsigned)((c->solid_slots + 255) / 256), 256, 0, s>>>(c->solid.p, c->solid_slots, kEmptyKey);
     if (c->n_solid)
-      KLAUNCH(solid_insert_kernel)<<<(unsigned)((c->n_solid + 255) / 256), 256, 0, s>>>(sk.p, c->n_solid, c->solid.p,
+      KLAUNCH(solid_insert_kernel)<<<(unsigned)((c->n_solid + 255) / 256), 256, 0, s>>>(all_keys, c->n_solid, c->solid.p,
                                                                              c->solid_slots - 1);
     BGX_CUDA(cudaGetLastError());
     st.stop();
@@ -599,9 +707,9 @@ void stage_count_kmers(Context* c) {
   c->set_stat("count_partitions", (double)P);
   // partition pass: reads in, one 8-byte word per instance out; upsert pass: the words back in,
   // the table touched twice (first touch + write-back), 16 B per slot
-  c->set_stat("alg_bytes_count_partition", (double)c->n_bases / 4 + 8.0 * (double)n_inst);
+  c->set_stat("alg_bytes_count_partition", (double)c->n_bases / 4 + 8.0 * (double)K);
   c->set_stat("alg_bytes_count_kernel", 8.0 * (double)n_inst + 32.0 * (double)slots);
-  c->set_stat("alg_bytes_count", (double)c->n_bases / 4 + 16.0 * (double)n_inst + 48.0 * (double)slots);
+  c->set_stat("alg_bytes_count", (double)c->n_bases / 4 + 8.0 * (double)K + 8.0 * (double)n_inst + 48.0 * (double)slots);
 }
 
 void export_kmers(Context* c, uint32_t min_count, uint64_t* n_out, uint64_t** kmers, uint32_t** fwd, uint32_t** rev,

@@ -93,7 +93,7 @@ __global__ void seed_count_kernel(const uint16_t* __restrict__ clen, const uint1
   if (r < n_reads) cnt[r] = clen[r] ? (uint32_t)nf[r] + nr[r] : 0u;
 }
 
-__global__ void seed_emit_kernel(const uint64_t* __restrict__ store, uint64_t rc_word_base,
+__global__ void seed_emit_kernel(const uint64_t* __restrict__ store, uint64_t fwd_word_base, uint64_t rc_word_base,
                                  const uint32_t* __restrict__ word_off, const uint16_t* __restrict__ clen,
                                  const uint16_t* __restrict__ nf, const uint16_t* __restrict__ nr,
                                  const uint32_t* __restrict__ seed_off, uint32_t n_reads, uint64_t* __restrict__ keys,
@@ -103,7 +103,7 @@ __global__ void seed_emit_kernel(const uint64_t* __restrict__ store, uint64_t rc
   int L = clen[r];
   if (!L) return;
   uint32_t o = seed_off[r];
-  uint64_t fa = (uint64_t)word_off[r] * 32, ra = (rc_word_base + word_off[r]) * 32;
+  uint64_t fa = (fwd_word_base + word_off[r]) * 32, ra = (rc_word_base + word_off[r]) * 32;
   int f = nf[r], v = nr[r];
   for (int i = 0; i < f; ++i, ++o) {
     keys[o] = suffix_key(store, fa + i, L - i);
@@ -220,11 +220,20 @@ __global__ void refine_compact_kernel(const uint32_t* __restrict__ tied, const u
 }
 
 // ---- dedup ----------------------------------------------------------------------------------------
+// `next` (optional) is the record that follows this rank's last one in the global order: the
+// first record of the next non-empty rank (skip_dups' next_entry, bs/expand.cpp:37-47).
+struct NextRec {
+  int has;
+  uint64_t key, loc;
+};
 __global__ void dedup_flag_kernel(const uint64_t* __restrict__ store, const uint64_t* __restrict__ keys,
-                                  const uint64_t* __restrict__ locs, uint32_t n, uint32_t* __restrict__ keep) {
+                                  const uint64_t* __restrict__ locs, uint32_t n, NextRec next,
+                                  uint32_t* __restrict__ keep) {
   uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
-  bool drop = (i + 1 < n) && prefix_or_equal(store, keys[i], locs[i], keys[i + 1], locs[i + 1]);
+  bool drop;
+  if (i + 1 < n) drop = prefix_or_equal(store, keys[i], locs[i], keys[i + 1], locs[i + 1]);
+  else drop = next.has && prefix_or_equal(store, keys[i], locs[i], next.key, next.loc);
   keep[i] = drop ? 0u : 1u;
 }
 
@@ -431,6 +440,222 @@ __global__ void entry_offs_kernel(const uint64_t* __restrict__ locs, uint64_t fi
   if (i < count) lens[i] = loc_len(locs[first + i]);
 }
 
+// ==== multi-GPU: routing by splitters, sentinel-aware lookups ========================================
+// Rank d owns the records x with splitter[d-1] <= x < splitter[d] in the sequence order.  Before
+// anything is sorted the splitters are synthetic bucket boundaries (key = first 8 bases, length
+// 0: such a record never reads the store); once every rank holds a sorted range they are the
+// ranks' first entries.
+constexpr int kMaxRanks = 64;
+struct Splitters {
+  int n;  // nranks - 1
+  uint64_t key[kMaxRanks - 1], loc[kMaxRanks - 1];
+};
+
+__device__ __forceinline__ int route_dest(const uint64_t* __restrict__ store, const Splitters& sp, uint64_t k, uint64_t l) {
+  int d = 0;
+  while (d < sp.n && sp.loc[d] != ~0ULL /* +inf: an empty rank */ && !rec_less(store, k, l, sp.key[d], sp.loc[d])) ++d;
+  return d;
+}
+
+// histogram of the first 8 bases (65536 buckets): the input of the balanced split
+// (the reference pre-sizes its sort sections the same way, bs/part_counts.h:17-32)
+__global__ void bucket_hist_kernel(const uint64_t* __restrict__ keys, uint32_t n, unsigned long long* __restrict__ hist) {
+  uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) atomicAdd(&hist[keys[i] >> 48], 1ULL);
+}
+
+__global__ void __launch_bounds__(256) route_count_kernel(const uint64_t* __restrict__ store,
+                                                          const uint64_t* __restrict__ keys,
+                                                          const uint64_t* __restrict__ locs, uint32_t n, Splitters sp,
+                                                          uint8_t* __restrict__ dest,
+                                                          unsigned long long* __restrict__ counts) {
+  __shared__ unsigned int sc[kMaxRanks];
+  if (threadIdx.x < kMaxRanks) sc[threadIdx.x] = 0;
+  __syncthreads();
+  uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) {
+    // bits 14..15 of a routed loc may carry a tag (prev-bit queries): not part of the length
+    int d = route_dest(store, sp, keys[i], locs[i] & ~0xC000ULL);
+    dest[i] = (uint8_t)d;
+    atomicAdd(&sc[d], 1u);
+  }
+  __syncthreads();
+  if (threadIdx.x <= (unsigned)sp.n && sc[threadIdx.x]) atomicAdd(&counts[threadIdx.x], (unsigned long long)sc[threadIdx.x]);
+}
+
+__global__ void __launch_bounds__(256) route_scatter_kernel(const uint64_t* __restrict__ keys,
+                                                            const uint64_t* __restrict__ locs,
+                                                            const uint8_t* __restrict__ dest, uint32_t n, int nranks,
+                                                            unsigned long long* __restrict__ cursors /*start offsets*/,
+                                                            uint64_t* __restrict__ okeys, uint64_t* __restrict__ olocs) {
+  __shared__ unsigned int sc[kMaxRanks];
+  __shared__ unsigned long long sbase[kMaxRanks];
+  if (threadIdx.x < kMaxRanks) sc[threadIdx.x] = 0;
+  __syncthreads();
+  uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  unsigned r = 0;
+  int d = 0;
+  if (i < n) {
+    d = dest[i];
+    r = atomicAdd(&sc[d], 1u);
+  }
+  __syncthreads();
+  if (threadIdx.x < (unsigned)nranks && sc[threadIdx.x])
+    sbase[threadIdx.x] = atomicAdd(&cursors[threadIdx.x], (unsigned long long)sc[threadIdx.x]);
+  __syncthreads();
+  if (i < n) {
+    unsigned long long o = sbase[d] + r;
+    okeys[o] = keys[i];
+    olocs[o] = locs[i];
+  }
+}
+
+// covered() against this rank's sorted range plus the record that follows it globally
+__device__ __forceinline__ bool covered_next(const uint64_t* __restrict__ store, const uint64_t* __restrict__ keys,
+                                             const uint64_t* __restrict__ locs, uint32_t n, const NextRec& next,
+                                             uint64_t xk, uint64_t xl, uint32_t* where) {
+  uint32_t lb = lower_bound_rec(store, keys, locs, 0, n, xk, xl);
+  *where = lb;
+  if (lb < n) return prefix_or_equal(store, xk, xl, keys[lb], locs[lb]);
+  return next.has && prefix_or_equal(store, xk, xl, next.key, next.loc);
+}
+
+// queries = pop_front of every local entry (entries of length 1 pop to the empty sequence, which
+// every entry covers: skipped).  tag_base: write the entry's first base into loc bits 14..15.
+__global__ void pop_queries_kernel(const uint64_t* __restrict__ store, const uint64_t* __restrict__ keys,
+                                   const uint64_t* __restrict__ locs, uint32_t n, int tag_base,
+                                   uint64_t* __restrict__ qkeys, uint64_t* __restrict__ qlocs,
+                                   unsigned long long* __restrict__ n_out) {
+  uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  bool has = false;
+  uint64_t qk = 0, ql = 0;
+  if (i < n) {
+    uint64_t l = locs[i];
+    int len = (int)loc_len(l);
+    if (len > 1) {
+      has = true;
+      qk = suffix_key(store, loc_addr(l) + 1, len - 1);
+      ql = make_loc(loc_addr(l) + 1, len - 1);
+      if (tag_base) ql |= (keys[i] >> 62) << 14;
+    }
+  }
+  unsigned mask = __ballot_sync(0xffffffffu, has);
+  if (!mask) return;
+  unsigned lane = lane_id();
+  unsigned long long base = 0;
+  if (lane == 0) base = atomicAdd(n_out, (unsigned long long)__popc(mask));
+  base = __shfl_sync(0xffffffffu, base, 0);
+  if (has) {
+    unsigned long long o = base + __popc(mask & ((1u << lane) - 1));
+    qkeys[o] = qk;
+    qlocs[o] = ql;
+  }
+}
+
+// flag[i] = 1 if record i is NOT covered by the local range (+ next); cnt[i] = how many records
+// it will emit (all its suffixes when emit_suffixes, else itself)
+__global__ void __launch_bounds__(128) uncovered_kernel(const uint64_t* __restrict__ store,
+                                                        const uint64_t* __restrict__ keys,
+                                                        const uint64_t* __restrict__ locs, uint32_t n, NextRec next,
+                                                        const uint64_t* __restrict__ xkeys,
+                                                        const uint64_t* __restrict__ xlocs, uint32_t m,
+                                                        int emit_suffixes, uint32_t* __restrict__ cnt) {
+  uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= m) return;
+  uint32_t where;
+  bool cov = covered_next(store, keys, locs, n, next, xkeys[j], xlocs[j], &where);
+  cnt[j] = cov ? 0u : (emit_suffixes ? loc_len(xlocs[j]) : 1u);
+}
+
+// emit record j itself (and, when emit_suffixes, every further suffix of it) at off[j]
+__global__ void emit_uncovered_kernel(const uint64_t* __restrict__ store, const uint64_t* __restrict__ xkeys,
+                                      const uint64_t* __restrict__ xlocs, const uint32_t* __restrict__ cnt,
+                                      const uint32_t* __restrict__ off, uint32_t m, uint64_t* __restrict__ okeys,
+                                      uint64_t* __restrict__ olocs) {
+  uint32_t j = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  if (j >= m) return;
+  uint32_t c = cnt[j];
+  if (!c) return;
+  uint64_t addr = loc_addr(xlocs[j]);
+  int len = (int)loc_len(xlocs[j]);
+  uint32_t o = off[j];
+  for (uint32_t t = lane_id(); t < c; t += 32) {
+    okeys[o + t] = suffix_key(store, addr + t, len - (int)t);
+    olocs[o + t] = make_loc(addr + t, len - (int)t);
+  }
+}
+
+// sizes / shared / max length of this rank's range; `prev` = the entry before the range globally
+__global__ void __launch_bounds__(128) tables_local_kernel(const uint64_t* __restrict__ store,
+                                                           const uint64_t* __restrict__ keys,
+                                                           const uint64_t* __restrict__ locs, uint32_t n, NextRec prev,
+                                                           uint16_t* __restrict__ sizes, uint16_t* __restrict__ shared,
+                                                           unsigned int* __restrict__ max_len) {
+  uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  unsigned len = 0;
+  if (i < n) {
+    uint64_t k = keys[i], l = locs[i];
+    len = loc_len(l);
+    sizes[i] = (uint16_t)len;
+    int lcp = 0;
+    if (i > 0 || prev.has) {
+      uint64_t pk = i > 0 ? keys[i - 1] : prev.key, pl = i > 0 ? locs[i - 1] : prev.loc;
+      int m = min((int)len, (int)loc_len(pl));
+      uint64_t x = (k ^ pk) & top_bases_mask(min(m, 32));
+      if (x) lcp = __clzll(x) >> 1;
+      else if (m <= 32) lcp = m;
+      else compare_from(store, pl, l, 32, &lcp);
+    }
+    shared[i] = (uint16_t)lcp;
+  }
+  unsigned mx = __reduce_max_sync(0xffffffffu, len);
+  if (lane_id() == 0 && mx) atomicMax(max_len, mx);
+}
+
+// routed prev-bit queries: x = pop_front(e) tagged with e's first base.  Sets prev[b][where] for
+// the first local entry having x as a prefix; where == n means the next rank's entry 0 (carry).
+__global__ void __launch_bounds__(128) prev_apply_kernel(const uint64_t* __restrict__ store,
+                                                         const uint64_t* __restrict__ keys,
+                                                         const uint64_t* __restrict__ locs, uint32_t n, NextRec next,
+                                                         const uint64_t* __restrict__ xkeys,
+                                                         const uint64_t* __restrict__ xlocs, uint32_t m,
+                                                         unsigned long long* __restrict__ prev_bits, uint64_t prev_words,
+                                                         int* __restrict__ carry /*[4]*/, int* __restrict__ missing) {
+  uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= m) return;
+  uint64_t xl = xlocs[j];
+  unsigned b = (unsigned)((xl >> 14) & 3);
+  xl &= ~0xC000ULL;
+  uint32_t where;
+  if (!covered_next(store, keys, locs, n, next, xkeys[j], xl, &where)) {
+    *missing = 1;  // LOG(FATAL) << "Missing expansion?" (bs/builder.cpp:96)
+  } else if (where < n) {
+    atomicOr(&prev_bits[(uint64_t)b * prev_words + (where >> 6)], 1ULL << (where & 63));
+  } else {
+    carry[b] = 1;
+  }
+}
+
+// entries of length 1 pop to the empty sequence: it is a prefix of the globally first entry
+__global__ void single_base_kernel(const uint64_t* __restrict__ keys, const uint64_t* __restrict__ locs, uint32_t n,
+                                   int* __restrict__ flags /*[4]*/) {
+  uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n && loc_len(locs[i]) == 1) flags[keys[i] >> 62] = 1;
+}
+
+__global__ void set_bit0_kernel(unsigned long long* __restrict__ prev_bits, uint64_t prev_words, int b) {
+  atomicOr(&prev_bits[(uint64_t)b * prev_words], 1ULL);
+}
+
+// accum with the ones of earlier ranks added (bitcount::finalize over the global bit vector)
+__global__ void bitcount_accum_offset_kernel(const uint32_t* __restrict__ group_excl, const uint32_t* __restrict__ total,
+                                             uint64_t groups, uint64_t acc_words, unsigned long long before,
+                                             unsigned long long* __restrict__ accum) {
+  uint64_t g = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (g >= acc_words) return;
+  accum[g] = before + (g < groups ? group_excl[g] : *total);
+}
+
 inline unsigned grid_for(uint64_t n, unsigned block) { return (unsigned)std::max<uint64_t>(1, (n + block - 1) / block); }
 
 uint32_t read_u32(const uint32_t* d, cudaStream_t s) {
@@ -472,7 +697,7 @@ void sort_records(Context* c, DevBuf<uint64_t>& keys, DevBuf<uint64_t>& locs, De
   BGX_CUDA(cudaMemsetAsync(n_big.p, 0, 8, s));
   int small_limit = kSmallGroup;
   if (const char* e = getenv("BGX_SMALL_GROUP")) small_limit = std::max(1, atoi(e));  // test hook: force the refinement path
-  KLAUNCH(tie_small_kernel)<<<grid_for(n, 128), 128, 0, s>>>(c->store.p, keys.p, locs.p, n, sbits, small_limit, big_flag.p,
+  KLAUNCH(tie_small_kernel)<<<grid_for(n, 128), 128, 0, s>>>(c->seq_store(), keys.p, locs.p, n, sbits, small_limit, big_flag.p,
                                                    n_big.p);
   BGX_CUDA(cudaGetLastError());
   uint32_t m = (uint32_t)read_u64(n_big.p, s);
@@ -489,10 +714,10 @@ void sort_records(Context* c, DevBuf<uint64_t>& keys, DevBuf<uint64_t>& locs, De
       DevBuf<uint32_t> gid(m, s);
       exclusive_scan_u32(head.p, gid.p, m, nullptr, s);
       DevBuf<uint64_t> ck(m, s), cl(m, s), ck2(m, s), cl2(m, s);
-      KLAUNCH(refine_key_kernel)<<<grid_for(m, 256), 256, 0, s>>>(c->store.p, locs.p, midx.p, gid.p, head.p, m, D, ck.p, cl.p);
+      KLAUNCH(refine_key_kernel)<<<grid_for(m, 256), 256, 0, s>>>(c->seq_store(), locs.p, midx.p, gid.p, head.p, m, D, ck.p, cl.p);
       bool alt = radix_sort_pairs(ck.p, cl.p, ck2.p, cl2.p, m, 0, 64, s);
       DevBuf<uint32_t> tied(m, s), nhead(m, s), tpos(m, s), tot(1, s);
-      KLAUNCH(refine_writeback_kernel)<<<grid_for(m, 256), 256, 0, s>>>(c->store.p, alt ? ck2.p : ck.p, alt ? cl2.p : cl.p, midx.p,
+      KLAUNCH(refine_writeback_kernel)<<<grid_for(m, 256), 256, 0, s>>>(c->seq_store(), alt ? ck2.p : ck.p, alt ? cl2.p : cl.p, midx.p,
                                                               m, D, keys.p, locs.p, tied.p, nhead.p);
       exclusive_scan_u32(tied.p, tpos.p, m, tot.p, s);
       BGX_CUDA(cudaGetLastError());
@@ -515,12 +740,12 @@ void sort_records(Context* c, DevBuf<uint64_t>& keys, DevBuf<uint64_t>& locs, De
 // drop every record that is a prefix of / equal to its successor; returns the survivor count and
 // leaves them in (keys, locs) (buffers are swapped with the alt ones).
 uint32_t dedup_records(Context* c, DevBuf<uint64_t>& keys, DevBuf<uint64_t>& locs, DevBuf<uint64_t>& keys_alt,
-                       DevBuf<uint64_t>& locs_alt, uint32_t n) {
+                       DevBuf<uint64_t>& locs_alt, uint32_t n, NextRec next = NextRec{0, 0, 0}) {
   cudaStream_t s = c->stream;
   if (n == 0) return 0;
   ScopedStage st(c, "dedup");
   DevBuf<uint32_t> keep(n, s), pos(n, s), tot(1, s);
-  KLAUNCH(dedup_flag_kernel)<<<grid_for(n, 256), 256, 0, s>>>(c->store.p, keys.p, locs.p, n, keep.p);
+  KLAUNCH(dedup_flag_kernel)<<<grid_for(n, 256), 256, 0, s>>>(c->seq_store(), keys.p, locs.p, n, next, keep.p);
   exclusive_scan_u32(keep.p, pos.p, n, tot.p, s);
   KLAUNCH(compact_pairs_kernel)<<<grid_for(n, 256), 256, 0, s>>>(keys.p, locs.p, keep.p, pos.p, n, keys_alt.p, locs_alt.p);
   BGX_CUDA(cudaGetLastError());
@@ -532,10 +757,43 @@ uint32_t dedup_records(Context* c, DevBuf<uint64_t>& keys, DevBuf<uint64_t>& loc
   return m;
 }
 
+// merge n_new sorted records into the n1 sorted records of (keys, locs) by rank; the result
+// (n1 + n_new records) ends in (keys, locs); the alt buffers are grown to hold as many.
+void merge_new_records(Context* c, DevBuf<uint64_t>& keys, DevBuf<uint64_t>& locs, DevBuf<uint64_t>& keys_alt,
+                       DevBuf<uint64_t>& locs_alt, uint32_t n1, const DevBuf<uint64_t>& nkeys,
+                       const DevBuf<uint64_t>& nlocs, uint32_t n_new) {
+  cudaStream_t s = c->stream;
+  const uint32_t nm = n1 + n_new;
+  ScopedStage st(c, "merge");
+  if ((size_t)nm > keys_alt.n) {
+    keys_alt.alloc((size_t)nm + 1024, s);
+    locs_alt.alloc((size_t)nm + 1024, s);
+  }
+  DevBuf<uint32_t> rank(n_new, s), marks((size_t)n1 + 2, s);
+  BGX_CUDA(cudaMemsetAsync(marks.p, 0, ((size_t)n1 + 2) * 4, s));
+  KLAUNCH(merge_rank_kernel)<<<grid_for(n_new, 128), 128, 0, s>>>(c->seq_store(), keys.p, locs.p, n1, nkeys.p, nlocs.p, n_new,
+                                                         rank.p, marks.p);
+  exclusive_scan_u32(marks.p, marks.p, (size_t)n1 + 2, nullptr, s);
+  if (n1) KLAUNCH(merge_scatter_old_kernel)<<<grid_for(n1, 256), 256, 0, s>>>(keys.p, locs.p, n1, marks.p, keys_alt.p, locs_alt.p);
+  KLAUNCH(merge_scatter_new_kernel)<<<grid_for(n_new, 256), 256, 0, s>>>(nkeys.p, nlocs.p, n_new, rank.p, keys_alt.p, locs_alt.p);
+  BGX_CUDA(cudaGetLastError());
+  std::swap(keys, keys_alt);
+  std::swap(locs, locs_alt);
+  if ((size_t)nm > keys_alt.n) {  // dedup writes into the alt buffers
+    keys_alt.alloc((size_t)nm + 1024, s);
+    locs_alt.alloc((size_t)nm + 1024, s);
+  }
+  c->add_stat("alg_bytes_merge", 32.0 * nm + 8.0 * n1);
+  st.stop();
+}
+
 }  // namespace
+
+void stage_build_seqset_dist(Context* c);
 
 void stage_build_seqset(Context* c) {
   BGX_CHECK(c->corrected, "bgx_build_seqset: call bgx_correct first");
+  if (c->dist.nranks > 1) return stage_build_seqset_dist(c);
   cudaStream_t s = c->stream;
   ScopedStage st_all(c, "seqset_total");
   const uint32_t n_reads = (uint32_t)c->n_reads;
@@ -550,7 +808,7 @@ void stage_build_seqset(Context* c) {
     DevBuf<uint32_t> cnt(n_reads, s), off(n_reads, s);
     KLAUNCH(seed_count_kernel)<<<grid_for(n_reads, 256), 256, 0, s>>>(c->clen.p, c->next_fwd.p, c->next_rev.p, n_reads, cnt.p);
     exclusive_scan_u32(cnt.p, off.p, n_reads, nullptr, s);
-    KLAUNCH(seed_emit_kernel)<<<grid_for(n_reads, 128), 128, 0, s>>>(c->store.p, c->n_words, c->word_off.p, c->clen.p,
+    KLAUNCH(seed_emit_kernel)<<<grid_for(n_reads, 128), 128, 0, s>>>(c->store.p, 0, c->n_words, c->word_off.p, c->clen.p,
                                                             c->next_fwd.p, c->next_rev.p, off.p, n_reads, keys.p, locs.p);
     BGX_CUDA(cudaGetLastError());
     st.stop();
@@ -599,32 +857,12 @@ void stage_build_seqset(Context* c) {
       sort_records(c, nkeys, nlocs, nkeys_alt, nlocs_alt, n_new, "r2");
     }
     const uint32_t nm = n1 + n_new;
-    {
-      ScopedStage st(c, "merge");
-      if ((size_t)nm > keys_alt.n) {
-        keys_alt.alloc((size_t)nm + 1024, s);
-        locs_alt.alloc((size_t)nm + 1024, s);
-      }
-      DevBuf<uint32_t> rank(n_new, s), marks((size_t)n1 + 2, s);
-      BGX_CUDA(cudaMemsetAsync(marks.p, 0, ((size_t)n1 + 2) * 4, s));
-      KLAUNCH(merge_rank_kernel)<<<grid_for(n_new, 128), 128, 0, s>>>(c->store.p, keys.p, locs.p, n1, nkeys.p, nlocs.p, n_new,
-                                                             rank.p, marks.p);
-      exclusive_scan_u32(marks.p, marks.p, (size_t)n1 + 2, nullptr, s);
-      if (n1) KLAUNCH(merge_scatter_old_kernel)<<<grid_for(n1, 256), 256, 0, s>>>(keys.p, locs.p, n1, marks.p, keys_alt.p, locs_alt.p);
-      KLAUNCH(merge_scatter_new_kernel)<<<grid_for(n_new, 256), 256, 0, s>>>(nkeys.p, nlocs.p, n_new, rank.p, keys_alt.p, locs_alt.p);
-      BGX_CUDA(cudaGetLastError());
-      std::swap(keys, keys_alt);
-      std::swap(locs, locs_alt);
-      if ((size_t)nm > keys_alt.n) {  // dedup writes into the alt buffers
-        keys_alt.alloc((size_t)nm + 1024, s);
-        locs_alt.alloc((size_t)nm + 1024, s);
-      }
-      c->add_stat("alg_bytes_merge", 32.0 * nm + 8.0 * n1);
-      st.stop();
-    }
+    merge_new_records(c, keys, locs, keys_alt, locs_alt, n1, nkeys, nlocs, n_new);
     n2 = dedup_records(c, keys, locs, keys_alt, locs_alt, nm);
   }
   c->n_entries = n2;
+  c->n_entries_global = n2;
+  c->first_entry_global = 0;
   c->set_stat("entries", n2);
 
   // 5. tables
@@ -683,6 +921,416 @@ void stage_build_seqset(Context* c) {
   st_all.stop();
 }
 
+// ==== multi-GPU seqset build =============================================================================
+namespace {
+
+struct Routed {
+  DevBuf<uint64_t> keys, locs;
+  uint32_t n = 0;
+};
+
+// Send every record to the rank that owns it (all-to-all over NVLink); returns what this rank got.
+Routed route_records(Context* c, const uint64_t* keys, const uint64_t* locs, uint32_t n, const Splitters& sp) {
+  cudaStream_t s = c->stream;
+  const int N = c->dist.nranks, R = c->dist.rank;
+  ScopedStage st(c, "route");
+  DevBuf<uint8_t> dest(std::max<uint32_t>(n, 1), s);
+  DevBuf<unsigned long long> counts(kMaxRanks, s);
+  BGX_CUDA(cudaMemsetAsync(counts.p, 0, kMaxRanks * 8, s));
+  if (n) KLAUNCH(route_count_kernel)<<<grid_for(n, 256), 256, 0, s>>>(c->seq_store(), keys, locs, n, sp, dest.p, counts.p);
+  std::vector<uint64_t> send_cnt(N), send_off(N), all((size_t)N * N), recv_cnt(N), recv_off(N);
+  {
+    unsigned long long h[kMaxRanks];
+    BGX_CUDA(cudaMemcpyAsync(h, counts.p, N * 8, cudaMemcpyDeviceToHost, s));
+    BGX_CUDA(cudaStreamSynchronize(s));
+    uint64_t o = 0;
+    for (int r = 0; r < N; ++r) { send_cnt[r] = h[r]; send_off[r] = o; o += h[r]; }
+  }
+  DevBuf<uint64_t> skeys(std::max<uint32_t>(n, 1), s), slocs(std::max<uint32_t>(n, 1), s);
+  {
+    std::vector<unsigned long long> cur(send_off.begin(), send_off.end());
+    BGX_CUDA(cudaMemcpyAsync(counts.p, cur.data(), N * 8, cudaMemcpyHostToDevice, s));
+    if (n) KLAUNCH(route_scatter_kernel)<<<grid_for(n, 256), 256, 0, s>>>(keys, locs, dest.p, n, N, counts.p, skeys.p, slocs.p);
+    BGX_CUDA(cudaGetLastError());
+  }
+  dist_allgather_host_u64(c, send_cnt.data(), N, all.data());
+  uint64_t m = 0;
+  for (int src = 0; src < N; ++src) { recv_cnt[src] = all[(size_t)src * N + R]; recv_off[src] = m; m += recv_cnt[src]; }
+  BGX_CHECK(m < (1ull << 30), "too many records for one GPU shard");
+  Routed out;
+  out.n = (uint32_t)m;
+  out.keys.alloc(m + 1024, s);  // slack: the sort / dedup ping-pong buffers are sized alike
+  out.locs.alloc(m + 1024, s);
+  dist_alltoallv(c, skeys.p, send_off.data(), send_cnt.data(), out.keys.p, recv_off.data(), recv_cnt.data(), 8);
+  dist_alltoallv(c, slocs.p, send_off.data(), send_cnt.data(), out.locs.p, recv_off.data(), recv_cnt.data(), 8);
+  BGX_CUDA(cudaStreamSynchronize(s));  // the send buffers die with this scope
+  c->add_stat("route_records_out", (double)n - (double)send_cnt[R]);
+  c->add_stat("route_bytes_out", 16.0 * ((double)n - (double)send_cnt[R]));
+  st.stop();
+  return out;
+}
+
+struct RankEnds {  // first and last record of every rank's sorted range
+  std::vector<uint64_t> v;  // [rank][5] = has, first key, first loc, last key, last loc
+  bool has(int r) const { return v[(size_t)r * 5] != 0; }
+  NextRec first(int r) const { return NextRec{1, v[(size_t)r * 5 + 1], v[(size_t)r * 5 + 2]}; }
+  NextRec last(int r) const { return NextRec{1, v[(size_t)r * 5 + 3], v[(size_t)r * 5 + 4]}; }
+};
+
+RankEnds exchange_ends(Context* c, const DevBuf<uint64_t>& keys, const DevBuf<uint64_t>& locs, uint32_t n) {
+  cudaStream_t s = c->stream;
+  uint64_t mine[5] = {n ? 1ull : 0ull, 0, 0, 0, 0};
+  if (n) {
+    BGX_CUDA(cudaMemcpyAsync(&mine[1], keys.p, 8, cudaMemcpyDeviceToHost, s));
+    BGX_CUDA(cudaMemcpyAsync(&mine[2], locs.p, 8, cudaMemcpyDeviceToHost, s));
+    BGX_CUDA(cudaMemcpyAsync(&mine[3], keys.p + (n - 1), 8, cudaMemcpyDeviceToHost, s));
+    BGX_CUDA(cudaMemcpyAsync(&mine[4], locs.p + (n - 1), 8, cudaMemcpyDeviceToHost, s));
+    BGX_CUDA(cudaStreamSynchronize(s));
+  }
+  RankEnds e;
+  e.v.resize((size_t)c->dist.nranks * 5);
+  dist_allgather_host_u64(c, mine, 5, e.v.data());
+  return e;
+}
+
+// the record that follows this rank's range in the global order / the one that precedes it
+NextRec next_of(const RankEnds& e, int R, int N) {
+  for (int r = R + 1; r < N; ++r)
+    if (e.has(r)) return e.first(r);
+  return NextRec{0, 0, 0};
+}
+NextRec prev_of(const RankEnds& e, int R) {
+  for (int r = R - 1; r >= 0; --r)
+    if (e.has(r)) return e.last(r);
+  return NextRec{0, 0, 0};
+}
+
+}  // namespace
+
+void stage_build_seqset_dist(Context* c) {
+  BGX_CHECK(c->corrected, "bgx_build_seqset: call bgx_correct first");
+  cudaStream_t s = c->stream;
+  const int N = c->dist.nranks, R = c->dist.rank;
+  ScopedStage st_all(c, "seqset_total");
+  const uint32_t n_reads = (uint32_t)c->n_reads;
+  BGX_CHECK(c->n_seeds < (1ull << 30), "too many seed records for one GPU shard");
+
+  // 0. replicate the corrected stores: comparisons past the 32-base key read the sequence, and a
+  //    record may be compared on any rank (peer-memory reads are the planned alternative)
+  {
+    ScopedStage st(c, "store_allgather");
+    uint64_t mine = 2 * c->n_words + 1;
+    std::vector<uint64_t> words(N), base(N);
+    dist_allgather_host_u64(c, &mine, 1, words.data());
+    uint64_t tot = 0;
+    for (int r = 0; r < N; ++r) { base[r] = tot; tot += words[r]; }
+    BGX_CHECK(tot * 32 < (1ull << 47), "corrected store too large for 48-bit suffix locators");
+    c->gstore.alloc(tot + 1, s);
+    BGX_CUDA(cudaMemsetAsync(c->gstore.p + tot, 0, 8, s));
+    std::vector<uint64_t> zero(N, 0), send_cnt(N, mine);
+    dist_alltoallv(c, c->store.p, zero.data(), send_cnt.data(), c->gstore.p, base.data(), words.data(), 8);
+    c->gstore_word_base = base[R];
+    c->add_stat("store_allgather_bytes", 8.0 * (double)tot);
+    st.stop();
+  }
+  const uint64_t* store = c->seq_store();
+
+  // 1. seeds of this rank's reads, addressed in the replicated store
+  uint32_t n = (uint32_t)c->n_seeds;
+  DevBuf<uint64_t> keys(std::max<uint32_t>(n, 1), s), locs(std::max<uint32_t>(n, 1), s), keys_alt, locs_alt;
+  {
+    ScopedStage st(c, "seed_emit");
+    DevBuf<uint32_t> cnt(std::max<uint32_t>(n_reads, 1), s), off(std::max<uint32_t>(n_reads, 1), s);
+    if (n_reads) {
+      KLAUNCH(seed_count_kernel)<<<grid_for(n_reads, 256), 256, 0, s>>>(c->clen.p, c->next_fwd.p, c->next_rev.p, n_reads, cnt.p);
+      exclusive_scan_u32(cnt.p, off.p, n_reads, nullptr, s);
+      KLAUNCH(seed_emit_kernel)<<<grid_for(n_reads, 128), 128, 0, s>>>(store, c->gstore_word_base, c->gstore_word_base + c->n_words,
+                                                              c->word_off.p, c->clen.p, c->next_fwd.p, c->next_rev.p, off.p,
+                                                              n_reads, keys.p, locs.p);
+    }
+    BGX_CUDA(cudaGetLastError());
+    st.stop();
+  }
+
+  // 2. balanced split of the prefix space (histogram of the first 8 bases over all ranks) and
+  //    routing of every seed to the owner of its prefix bucket
+  Splitters sp;
+  sp.n = N - 1;
+  {
+    ScopedStage st(c, "split");
+    const size_t NB = 65536;
+    DevBuf<unsigned long long> hist(NB, s);
+    BGX_CUDA(cudaMemsetAsync(hist.p, 0, NB * 8, s));
+    if (n) KLAUNCH(bucket_hist_kernel)<<<grid_for(n, 256), 256, 0, s>>>(keys.p, n, hist.p);
+    dist_allreduce_sum_u64(c, hist.p, NB);
+    std::vector<unsigned long long> h(NB);
+    BGX_CUDA(cudaMemcpyAsync(h.data(), hist.p, NB * 8, cudaMemcpyDeviceToHost, s));
+    BGX_CUDA(cudaStreamSynchronize(s));
+    uint64_t total = 0;
+    for (size_t b = 0; b < NB; ++b) total += h[b];
+    uint64_t cum = 0;
+    size_t b = 0;
+    for (int r = 1; r < N; ++r) {
+      const uint64_t target = total / N * r;
+      while (b < NB && cum + h[b] <= target) cum += h[b++];  // bucket b is the first one of rank r
+      sp.key[r - 1] = b >= NB ? ~0ULL : ((uint64_t)b << 48);
+      sp.loc[r - 1] = b >= NB ? ~0ULL : make_loc(0, 0);
+    }
+    st.stop();
+  }
+  {
+    Routed r1 = route_records(c, keys.p, locs.p, n, sp);
+    keys = std::move(r1.keys);
+    locs = std::move(r1.locs);
+    n = r1.n;
+  }
+  c->set_stat("seeds_owned", n);
+  keys_alt.alloc((size_t)n + 1024, s);
+  locs_alt.alloc((size_t)n + 1024, s);
+  if (keys.n < (size_t)n + 1024) {  // sort/dedup ping-pong between equally sized buffers
+    DevBuf<uint64_t> k2((size_t)n + 1024, s), l2((size_t)n + 1024, s);
+    if (n) {
+      BGX_CUDA(cudaMemcpyAsync(k2.p, keys.p, (size_t)n * 8, cudaMemcpyDeviceToDevice, s));
+      BGX_CUDA(cudaMemcpyAsync(l2.p, locs.p, (size_t)n * 8, cudaMemcpyDeviceToDevice, s));
+    }
+    keys = std::move(k2);
+    locs = std::move(l2);
+  }
+
+  // 3. sort + dedup of the owned range; the last record is checked against the next rank's first
+  sort_records(c, keys, locs, keys_alt, locs_alt, n, "r1");
+  RankEnds ends = exchange_ends(c, keys, locs, n);
+  uint32_t n1 = dedup_records(c, keys, locs, keys_alt, locs_alt, n, next_of(ends, R, N));
+  c->set_stat("entries_round1", n1);
+
+  // 4. closure: route pop_front(e) of every entry to the owner of its prefix; an uncovered one and
+  //    all of its suffixes become candidates, routed to THEIR owners, who keep the uncovered ones.
+  //    One round reaches the fixed point: every suffix of anything new was itself a candidate.
+  uint32_t n_new = 0;
+  DevBuf<uint64_t> nkeys, nlocs;
+  {
+    ScopedStage st(c, "walk");
+    ends = exchange_ends(c, keys, locs, n1);
+    NextRec next = next_of(ends, R, N);
+    DevBuf<uint64_t> qk(std::max<uint32_t>(n1, 1), s), ql(std::max<uint32_t>(n1, 1), s);
+    DevBuf<unsigned long long> nq_d(1, s);
+    BGX_CUDA(cudaMemsetAsync(nq_d.p, 0, 8, s));
+    if (n1) KLAUNCH(pop_queries_kernel)<<<grid_for(n1, 256), 256, 0, s>>>(store, keys.p, locs.p, n1, 0, qk.p, ql.p, nq_d.p);
+    uint32_t nq = (uint32_t)read_u64(nq_d.p, s);
+    Routed q = route_records(c, qk.p, ql.p, nq, sp);
+    qk.release();
+    ql.release();
+    // uncovered queries -> themselves + all their suffixes
+    DevBuf<uint32_t> cnt(std::max<uint32_t>(q.n, 1), s), off(std::max<uint32_t>(q.n, 1), s), tot(1, s);
+    if (q.n) KLAUNCH(uncovered_kernel)<<<grid_for(q.n, 128), 128, 0, s>>>(store, keys.p, locs.p, n1, next, q.keys.p, q.locs.p, q.n,
+                                                                  1, cnt.p);
+    exclusive_scan_u32(cnt.p, off.p, q.n, tot.p, s);
+    uint32_t n_cand = read_u32(tot.p, s);
+    c->set_stat("walk_candidates", n_cand);
+    DevBuf<uint64_t> ck(std::max<uint32_t>(n_cand, 1), s), cl(std::max<uint32_t>(n_cand, 1), s);
+    if (q.n) KLAUNCH(emit_uncovered_kernel)<<<grid_for((uint64_t)q.n * 32, 128), 128, 0, s>>>(store, q.keys.p, q.locs.p, cnt.p,
+                                                                                       off.p, q.n, ck.p, cl.p);
+    BGX_CUDA(cudaGetLastError());
+    Routed cd = route_records(c, ck.p, cl.p, n_cand, sp);
+    // owners keep the candidates nothing covers yet
+    DevBuf<uint32_t> cnt2(std::max<uint32_t>(cd.n, 1), s), off2(std::max<uint32_t>(cd.n, 1), s);
+    if (cd.n) KLAUNCH(uncovered_kernel)<<<grid_for(cd.n, 128), 128, 0, s>>>(store, keys.p, locs.p, n1, next, cd.keys.p, cd.locs.p,
+                                                                    cd.n, 0, cnt2.p);
+    exclusive_scan_u32(cnt2.p, off2.p, cd.n, tot.p, s);
+    n_new = read_u32(tot.p, s);
+    nkeys.alloc(std::max<uint32_t>(n_new, 1), s);
+    nlocs.alloc(std::max<uint32_t>(n_new, 1), s);
+    if (cd.n) KLAUNCH(emit_uncovered_kernel)<<<grid_for((uint64_t)cd.n * 32, 128), 128, 0, s>>>(store, cd.keys.p, cd.locs.p, cnt2.p,
+                                                                                        off2.p, cd.n, nkeys.p, nlocs.p);
+    BGX_CUDA(cudaGetLastError());
+    st.stop();
+  }
+  c->set_stat("walk_new_records", n_new);
+  BGX_CHECK((uint64_t)n1 + n_new < (1ull << 30), "too many records for one GPU shard");
+  uint32_t n2 = n1;
+  {
+    // every rank takes part in the exchanges below even with nothing new of its own
+    if (n_new) {
+      DevBuf<uint64_t> nkeys_alt(n_new, s), nlocs_alt(n_new, s);
+      sort_records(c, nkeys, nlocs, nkeys_alt, nlocs_alt, n_new, "r2");
+      merge_new_records(c, keys, locs, keys_alt, locs_alt, n1, nkeys, nlocs, n_new);
+    }
+    ends = exchange_ends(c, keys, locs, n1 + n_new);
+    n2 = dedup_records(c, keys, locs, keys_alt, locs_alt, n1 + n_new, next_of(ends, R, N));
+  }
+
+  // 5. rebalance: rank r takes the global entries [r*chunk, (r+1)*chunk), chunk a multiple of 512,
+  //    so every rank's bit vectors start on a bitcount group boundary and concatenate as they are
+  uint64_t Nt = 0, first_global = 0;
+  {
+    ScopedStage st(c, "rebalance");
+    uint64_t mine = n2;
+    std::vector<uint64_t> cnts(N), goff(N + 1);
+    dist_allgather_host_u64(c, &mine, 1, cnts.data());
+    goff[0] = 0;
+    for (int r = 0; r < N; ++r) goff[r + 1] = goff[r] + cnts[r];
+    Nt = goff[N];
+    const uint64_t chunk = std::max<uint64_t>(512, ((Nt + N - 1) / N + 511) / 512 * 512);
+    auto lo_of = [&](int r) { return std::min<uint64_t>((uint64_t)r * chunk, Nt); };
+    std::vector<uint64_t> send_off(N), send_cnt(N), recv_off(N), recv_cnt(N);
+    uint64_t m = 0;
+    for (int d = 0; d < N; ++d) {
+      uint64_t a = std::max<uint64_t>(goff[R], lo_of(d)), b = std::min<uint64_t>(goff[R + 1], lo_of(d + 1));
+      send_cnt[d] = b > a ? b - a : 0;
+      send_off[d] = b > a ? a - goff[R] : 0;
+    }
+    for (int src = 0; src < N; ++src) {
+      uint64_t a = std::max<uint64_t>(goff[src], lo_of(R)), b = std::min<uint64_t>(goff[src + 1], lo_of(R + 1));
+      recv_cnt[src] = b > a ? b - a : 0;
+      recv_off[src] = m;
+      m += recv_cnt[src];
+    }
+    DevBuf<uint64_t> k2(std::max<uint64_t>(m, 1), s), l2(std::max<uint64_t>(m, 1), s);
+    dist_alltoallv(c, keys.p, send_off.data(), send_cnt.data(), k2.p, recv_off.data(), recv_cnt.data(), 8);
+    dist_alltoallv(c, locs.p, send_off.data(), send_cnt.data(), l2.p, recv_off.data(), recv_cnt.data(), 8);
+    BGX_CUDA(cudaStreamSynchronize(s));
+    keys = std::move(k2);
+    locs = std::move(l2);
+    keys_alt.release();
+    locs_alt.release();
+    n2 = (uint32_t)m;
+    first_global = lo_of(R);
+    st.stop();
+  }
+  c->n_entries = n2;
+  c->n_entries_global = Nt;
+  c->first_entry_global = first_global;
+  c->set_stat("entries", n2);
+  c->set_stat("entries_global", (double)Nt);
+
+  // 6. tables of the owned range
+  {
+    ScopedStage st(c, "tables");
+    ends = exchange_ends(c, keys, locs, n2);
+    const NextRec next = next_of(ends, R, N), prev = prev_of(ends, R);
+    int last_owner = 0;
+    for (int r = 0; r < N; ++r)
+      if (ends.has(r)) last_owner = r;
+    Splitters sp2;
+    sp2.n = N - 1;
+    for (int r = 1; r < N; ++r) {
+      sp2.key[r - 1] = ends.has(r) ? ends.first(r).key : ~0ULL;
+      sp2.loc[r - 1] = ends.has(r) ? ends.first(r).loc : ~0ULL;
+    }
+    const uint64_t nb = n2;
+    c->prev_words = (nb + 63) / 64;
+    c->sub_words = (nb + 511) / 512;
+    c->acc_words = R == last_owner ? (Nt + 1 + 511) / 512 - first_global / 512 : c->sub_words;
+    c->sizes.alloc(std::max<uint64_t>(nb, 1), s);
+    c->shared.alloc(std::max<uint64_t>(nb, 1), s);
+    c->prev_bits.alloc(std::max<uint64_t>(4 * c->prev_words, 1), s);
+    c->prev_sub.alloc(std::max<uint64_t>(4 * c->sub_words, 1), s);
+    c->prev_acc.alloc(std::max<uint64_t>(4 * c->acc_words, 1), s);
+    BGX_CUDA(cudaMemsetAsync(c->prev_bits.p, 0, std::max<uint64_t>(4 * c->prev_words, 1) * 8, s));
+    BGX_CUDA(cudaMemsetAsync(c->prev_acc.p, 0, std::max<uint64_t>(4 * c->acc_words, 1) * 8, s));
+    unsigned long long* bits = reinterpret_cast<unsigned long long*>(c->prev_bits.p);
+    DevBuf<unsigned int> max_len(1, s);
+    DevBuf<int> flags(9, s);  // [0..3] carry to the next rank's entry 0, [4..7] single-base entries, [8] missing
+    BGX_CUDA(cudaMemsetAsync(max_len.p, 0, 4, s));
+    BGX_CUDA(cudaMemsetAsync(flags.p, 0, 9 * 4, s));
+    if (nb) KLAUNCH(tables_local_kernel)<<<grid_for(nb, 128), 128, 0, s>>>(store, keys.p, locs.p, n2, prev, c->sizes.p, c->shared.p,
+                                                                   max_len.p);
+    // prev bits: pop_front(e) tagged with e's first base, routed to the rank whose range holds
+    // the first entry it is a prefix of (bs/builder.cpp:85-107)
+    {
+      DevBuf<uint64_t> qk(std::max<uint32_t>(n2, 1), s), ql(std::max<uint32_t>(n2, 1), s);
+      DevBuf<unsigned long long> nq_d(1, s);
+      BGX_CUDA(cudaMemsetAsync(nq_d.p, 0, 8, s));
+      if (n2) {
+        KLAUNCH(pop_queries_kernel)<<<grid_for(n2, 256), 256, 0, s>>>(store, keys.p, locs.p, n2, 1, qk.p, ql.p, nq_d.p);
+        KLAUNCH(single_base_kernel)<<<grid_for(n2, 256), 256, 0, s>>>(keys.p, locs.p, n2, flags.p + 4);
+      }
+      uint32_t nq = (uint32_t)read_u64(nq_d.p, s);
+      Routed q = route_records(c, qk.p, ql.p, nq, sp2);
+      if (q.n) KLAUNCH(prev_apply_kernel)<<<grid_for(q.n, 128), 128, 0, s>>>(store, keys.p, locs.p, n2, next, q.keys.p, q.locs.p, q.n,
+                                                                     bits, c->prev_words, flags.p, flags.p + 8);
+      BGX_CUDA(cudaGetLastError());
+    }
+    // carries, single-base entries, missing flag, max length: tiny all-gather
+    {
+      int hf[9];
+      unsigned int h_max;
+      BGX_CUDA(cudaMemcpyAsync(hf, flags.p, sizeof(hf), cudaMemcpyDeviceToHost, s));
+      BGX_CUDA(cudaMemcpyAsync(&h_max, max_len.p, 4, cudaMemcpyDeviceToHost, s));
+      BGX_CUDA(cudaStreamSynchronize(s));
+      uint64_t mine[10];
+      for (int i = 0; i < 9; ++i) mine[i] = (uint64_t)hf[i];
+      mine[9] = h_max;
+      std::vector<uint64_t> all((size_t)N * 10);
+      dist_allgather_host_u64(c, mine, 10, all.data());
+      bool missing = false;
+      uint64_t mx = 0;
+      int first_owner = -1;
+      for (int r = 0; r < N; ++r) {
+        missing = missing || all[(size_t)r * 10 + 8];
+        mx = std::max(mx, all[(size_t)r * 10 + 9]);
+        if (first_owner < 0 && ends.has(r)) first_owner = r;
+      }
+      BGX_CHECK(!missing, "Missing expansion?");  // bs/builder.cpp:96
+      c->max_entry_len = (uint32_t)mx;
+      if (nb) {
+        for (int b = 0; b < 4; ++b) {
+          bool set0 = false;
+          for (int r = R - 1; r >= 0; --r) {  // carries from the ranks right before this one
+            if (all[(size_t)r * 10 + b]) set0 = true;
+            if (ends.has(r)) break;
+          }
+          if (R == first_owner)
+            for (int r = 0; r < N; ++r) set0 = set0 || all[(size_t)r * 10 + 4 + b];
+          if (set0) KLAUNCH(set_bit0_kernel)<<<1, 1, 0, s>>>(bits, c->prev_words, b);
+        }
+      }
+    }
+    // bitcount index over the global bit vector (modules/io/bitcount.cpp:84-123)
+    {
+      uint64_t pops[4] = {0, 0, 0, 0};
+      DevBuf<uint32_t> gpop(std::max<uint64_t>(c->sub_words, 1), s), gex(std::max<uint64_t>(4 * c->sub_words, 1), s), tot(4, s);
+      BGX_CUDA(cudaMemsetAsync(tot.p, 0, 16, s));
+      for (int b = 0; b < 4 && nb; ++b) {
+        KLAUNCH(bitcount_groups_kernel)<<<grid_for(c->sub_words, 256), 256, 0, s>>>(
+            bits + b * c->prev_words, c->prev_words, c->sub_words, gpop.p,
+            reinterpret_cast<unsigned long long*>(c->prev_sub.p) + b * c->sub_words);
+        exclusive_scan_u32(gpop.p, gex.p + b * c->sub_words, c->sub_words, tot.p + b, s);
+      }
+      uint32_t h_tot[4];
+      BGX_CUDA(cudaMemcpyAsync(h_tot, tot.p, 16, cudaMemcpyDeviceToHost, s));
+      BGX_CUDA(cudaStreamSynchronize(s));
+      for (int b = 0; b < 4; ++b) pops[b] = h_tot[b];
+      std::vector<uint64_t> all((size_t)N * 4);
+      dist_allgather_host_u64(c, pops, 4, all.data());
+      uint64_t off = 0;
+      for (int b = 0; b < 4; ++b) {
+        uint64_t before = 0, total = 0;
+        for (int r = 0; r < N; ++r) {
+          if (r < R) before += all[(size_t)r * 4 + b];
+          total += all[(size_t)r * 4 + b];
+        }
+        if (c->acc_words)
+          KLAUNCH(bitcount_accum_offset_kernel)<<<grid_for(c->acc_words, 256), 256, 0, s>>>(
+              gex.p + b * c->sub_words, tot.p + b, c->sub_words, c->acc_words, before,
+              reinterpret_cast<unsigned long long*>(c->prev_acc.p) + b * c->acc_words);
+        c->fixed[b] = off;
+        off += total;
+      }
+      c->fixed[4] = off;
+      BGX_CUDA(cudaGetLastError());
+      BGX_CUDA(cudaStreamSynchronize(s));
+      // seqset::finalize (seqset.cpp:123-126)
+      BGX_CHECK(c->fixed[4] == Nt, "Invalid seqset in finalize: prev bit totals != entries");
+    }
+    st.stop();
+  }
+  c->ent_key = std::move(keys);
+  c->ent_loc = std::move(locs);
+  c->built = true;
+  st_all.stop();
+}
+
 void export_entries_ascii(Context* c, uint64_t first, uint64_t count, char** bases, uint64_t** offs_out) {
   BGX_CHECK(c->built, "bgx_export_entries_ascii: call bgx_build_seqset first");
   BGX_CHECK(first + count <= c->n_entries, "bgx_export_entries_ascii: range out of bounds");
@@ -702,7 +1350,7 @@ void export_entries_ascii(Context* c, uint64_t first, uint64_t count, char** bas
     DevBuf<uint64_t> d_offs(count + 1, s);
     DevBuf<char> d_out(std::max<uint64_t>(offs[count], 1), s);
     BGX_CUDA(cudaMemcpyAsync(d_offs.p, offs, (count + 1) * 8, cudaMemcpyHostToDevice, s));
-    KLAUNCH(entries_ascii_kernel)<<<grid_for(count, 128), 128, 0, s>>>(c->store.p, c->ent_loc.p, d_offs.p, first, count, d_out.p);
+    KLAUNCH(entries_ascii_kernel)<<<grid_for(count, 128), 128, 0, s>>>(c->seq_store(), c->ent_loc.p, d_offs.p, first, count, d_out.p);
     BGX_CUDA(cudaMemcpyAsync(out, d_out.p, offs[count], cudaMemcpyDeviceToHost, s));
     BGX_CUDA(cudaStreamSynchronize(s));
   }

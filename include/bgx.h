@@ -114,6 +114,23 @@ int bgx_export_seqset(bgx_ctx* ctx, uint64_t* n_entries, uint32_t* max_entry_len
 int bgx_export_entries_ascii(bgx_ctx* ctx, uint64_t first, uint64_t count, char** bases,
                              uint64_t** offs);
 
+/* ---- multi-GPU (no reference analogue: the reference is one process) -------------------
+ * One context per GPU, one process per GPU.  Rank 0 obtains an id with bgx_dist_unique_id and hands
+ * it to every rank out of band (torch.distributed broadcast, MPI, a file); every rank then calls
+ * bgx_dist_init before adding its share of the reads.  From then on bgx_count_kmers, bgx_correct,
+ * bgx_build_seqset and bgx_run are COLLECTIVE: every rank must call them.  K-mer instances travel
+ * to the owner of their hash partition, suffix records to the owner of their prefix range (NCCL
+ * all-to-all over NVLink); each rank ends up with a contiguous range of the final seqset whose
+ * length is a multiple of 512 entries (except the last), so the per-rank tables returned by
+ * bgx_export_seqset concatenate in rank order into exactly the single-GPU tables.
+ * bgx_export_kmers returns the k-mers this rank owns; bgx_export_corrected its own reads. */
+int bgx_dist_unique_id(uint8_t id[128]);
+int bgx_dist_init(bgx_ctx* ctx, int32_t world_size, int32_t rank, const uint8_t id[128]);
+/* layout[0] entries held by this rank, [1] entries over all ranks, [2] global index of this rank's
+ * first entry, [3..5] number of uint64 words per base in prev_bits / prev_subaccum / prev_accum as
+ * returned by bgx_export_seqset on this rank. */
+int bgx_seqset_layout(bgx_ctx* ctx, uint64_t layout[6]);
+
 /* Whole path on resident reads: count -> correct -> seqset.  Equivalent to the three calls. */
 int bgx_run(bgx_ctx* ctx);
 
