@@ -41,9 +41,16 @@ def make_workload(name, rank=0, reads_override=None, genome_prefix_reads=None):
     prefix of the genome sized to give that many reads (the bounded CPU-baseline sample)."""
     from biograph_b200 import synth
     w = WORKLOADS[name]
-    if w["genome"] == "ecoli":
+    if w["genome"] == "ecoli" and rank > 0:
+        # weak scaling: rank r sequences its OWN genome of the same size (random, 5 % repeats), so the
+        # sharded build over all ranks sees N genomes: k-mers, seeds and entries all grow with N
+        genome = synth.random_genome(4938920, seed=5000 + rank, repeat_frac=0.05, repeat_seed=6000 + rank)
+    elif w["genome"] == "ecoli":
         z = np.load(os.path.join(ROOT, "tests", "golden", "e_coli_genome.npz"))
         genome = synth.unpack_genome(z["packed"], int(z["length"]))
+    elif rank > 0:
+        _, glen, s1, s2 = w["genome"]
+        genome = synth.random_genome(glen, seed=s1 + 100 * rank, repeat_frac=0.05, repeat_seed=s2 + 100 * rank)
     else:
         _, glen, s1, s2 = w["genome"]
         genome = synth.random_genome(glen, seed=s1, repeat_frac=0.05, repeat_seed=s2)
@@ -53,7 +60,7 @@ def make_workload(name, rank=0, reads_override=None, genome_prefix_reads=None):
     n_reads = -(-w["coverage"] * len(genome) // w["read_len"])
     if reads_override:
         n_reads = reads_override
-    # weak scaling: every rank builds its own read set of the same shape (different seed)
+    # weak scaling: every rank brings a read set of the same shape from its own genome
     reads = synth.simulate_reads(genome, n_reads, read_len=w["read_len"], error_rate=w["error"],
                                  seed=w["seed"] + 1000 * rank, paired=w["paired"])
     return reads
@@ -228,6 +235,11 @@ def main():
     del packed
 
     g = B.Bgx(device=local)
+    if world > 1:
+        # ONE sharded build over all ranks' reads: NCCL inside libbgx, id carried by torch.distributed
+        ids = [B.Bgx.unique_id() if rank == 0 else None]
+        dist.broadcast_object_list(ids, src=0)
+        g.dist_init(world, rank, ids[0])
     flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")  # > 126 MB L2
 
     def flush_l2():
@@ -267,7 +279,7 @@ def main():
     total_bases = sum_over_ranks(bases)
     value = total_bases / (ms_per_step / 1e3)
     st_mean = {k_: v / args.steps for k_, v in stats_acc.items()}
-    ss_n = int(st_mean.get("entries", 0))
+    ss_n = int(sum_over_ranks(st_mean.get("entries", 0)))
 
     # ---- end-to-end arm: host buffers in, host tables out ------------------------------------------------
     e2e_ms = 0.0
@@ -335,7 +347,9 @@ def main():
             "scaling": "weak", "vs_baseline": None, "dtype": "u64", "data": "synthetic",
             "config": {"workload": args.workload, "reads_per_gpu": int(n_reads), "read_len": int(read_len),
                        "bases_per_gpu": bases, "kmer_size": 30, "entries": ss_n,
-                       "parallelism": f"replicas x{world} (independent read sets; sharded build is DESIGN.md 'next')" if world > 1 else "1 gpu",
+                       "parallelism": (f"one sharded build over {world} GPUs: reads split by rank ({world} genomes of this size), k-mers "
+                                       "routed by hash partition, suffix records by prefix range (NCCL all-to-all)")
+                       if world > 1 else "1 gpu",
                        "l2": "flushed between steps (256 MiB memset); working set >> L2"},
             "e2e": {"value": e2e_val, "unit": "bases/s", "ms_per_step": e2e_ms_step, "h2d_bytes_per_step": int(h2d),
                     "d2h_bytes_per_step": int(d2h)},

@@ -121,11 +121,23 @@ void dist_p2p_batch(Context* c, const std::vector<P2P>& sends, const std::vector
     }
     return;
   }
+  // messages to self are plain device copies (pairing the i-th self send with the i-th self recv);
+  // only peer traffic goes through NCCL
+  {
+    size_t ri = 0;
+    for (const P2P& sd : sends) {
+      if (sd.peer != c->dist.rank) continue;
+      while (ri < recvs.size() && recvs[ri].peer != c->dist.rank) ++ri;
+      BGX_CHECK(ri < recvs.size() && recvs[ri].bytes == sd.bytes, "dist_p2p_batch: unmatched self message");
+      if (sd.bytes) BGX_CUDA(cudaMemcpyAsync(recvs[ri].recv, sd.send, sd.bytes, cudaMemcpyDeviceToDevice, c->stream));
+      ++ri;
+    }
+  }
   BGX_NCCL(nccl().GroupStart());
-  for (const P2P& s : sends)
-    if (s.bytes) BGX_NCCL(nccl().Send(s.send, s.bytes, ncclUint8, s.peer, comm_of(c), c->stream));
+  for (const P2P& sd : sends)
+    if (sd.bytes && sd.peer != c->dist.rank) BGX_NCCL(nccl().Send(sd.send, sd.bytes, ncclUint8, sd.peer, comm_of(c), c->stream));
   for (const P2P& r : recvs)
-    if (r.bytes) BGX_NCCL(nccl().Recv(r.recv, r.bytes, ncclUint8, r.peer, comm_of(c), c->stream));
+    if (r.bytes && r.peer != c->dist.rank) BGX_NCCL(nccl().Recv(r.recv, r.bytes, ncclUint8, r.peer, comm_of(c), c->stream));
   BGX_NCCL(nccl().GroupEnd());
 }
 

@@ -200,8 +200,7 @@ kmer_partition_kernel(const uint64_t* __restrict__ words, const uint32_t* __rest
 // sees the table exactly twice (first touch, final write-back).
 constexpr int kUpsItems = 4;
 constexpr int kUpsTile = 256 * kUpsItems;
-__global__ void __launch_bounds__(256, 4) kmer_upsert_kernel(const unsigned long long* __restrict__ pk,
-                                                             const unsigned long long* __restrict__ part_base,
+__global__ void __launch_bounds__(256, 4) kmer_upsert_kernel(const unsigned long long* const* __restrict__ part_ptr,
                                                              const unsigned long long* __restrict__ part_count,
                                                              uint32_t tiles_per_part, int k,
                                                              CountEntry* __restrict__ table, int log2_slots,
@@ -210,7 +209,7 @@ __global__ void __launch_bounds__(256, 4) kmer_upsert_kernel(const unsigned long
   const unsigned long long cnt = part_count[p];
   const unsigned long long first = (unsigned long long)t * kUpsTile;
   if (first >= cnt) return;
-  const unsigned long long* src = pk + part_base[p];
+  const unsigned long long* src = part_ptr[p];
   const uint64_t slot_mask = (1ULL << log2_slots) - 1;
   // lock-step phases over the thread's items keep kUpsItems L2 round trips in flight per thread:
   // A) instance words  B) first-probe keys  C) CAS claims of empty slots  D) counters (RED)
@@ -277,14 +276,13 @@ __global__ void __launch_bounds__(256, 4) kmer_upsert_kernel(const unsigned long
 
 // Distinct estimate over partitioned instance words (multi-GPU: run by the owner after the
 // exchange, because the fused estimate of pass 1 only saw this rank's own reads).
-__global__ void __launch_bounds__(256) kmer_estimate_words_kernel(const unsigned long long* __restrict__ pk,
-                                                                  const unsigned long long* __restrict__ part_base,
+__global__ void __launch_bounds__(256) kmer_estimate_words_kernel(const unsigned long long* const* __restrict__ part_ptr,
                                                                   const unsigned long long* __restrict__ part_count,
                                                                   uint32_t tiles_per_part, int k,
                                                                   unsigned int* __restrict__ bitmap, uint64_t bit_mask) {
   const uint32_t p = blockIdx.x / tiles_per_part, t = blockIdx.x % tiles_per_part;
   const unsigned long long cnt = part_count[p];
-  const unsigned long long* src = pk + part_base[p];
+  const unsigned long long* src = part_ptr[p];
 #pragma unroll
   for (int i = 0; i < kUpsItems; ++i) {
     const unsigned long long idx = (unsigned long long)t * kUpsTile + (unsigned long long)i * 256 + threadIdx.x;
@@ -523,6 +521,7 @@ void stage_count_kmers(Context* c) {
   BGX_CUDA(cudaMemsetAsync(ones.p, 0, 8, s));
   unsigned long long h_ones = 0;
   int h_over = 0;
+  bool reran = false;
   st_alloc.stop();
   {
     ScopedStage st(c, "count_partition");
@@ -552,67 +551,120 @@ void stage_count_kmers(Context* c) {
       BGX_CUDA(cudaStreamSynchronize(s));
       BGX_CHECK(!h_over, "internal: exact partition pass overflowed");
       c->add_stat("count_partition_reruns", 1);
+      reran = true;
     }
     st.stop();
   }
 
-  // ---- multi-GPU: every partition goes to its owner (NCCL all-to-all over NVLink) ------------------
-  // After this block (pk, part_base, cursors) describe the Pl partitions this rank owns, each one
-  // contiguous and holding the instances of ALL ranks' reads.
-  int Pl = P;
-  if (N > 1) {
-    ScopedStage st(c, "count_exchange");
-    Pl = P / N;
-    const int p0 = R * Pl;
-    std::vector<uint64_t> mine(h_count.begin(), h_count.end()), all((size_t)N * P);
-    dist_allgather_host_u64(c, mine.data(), P, all.data());
-    std::vector<unsigned long long> l_base(Pl), l_count(Pl);
-    uint64_t total = 0;
-    std::vector<P2P> sends, recvs;
+  // ---- the partitions this rank will count: (device address, instance count) each ----------------
+  // Single GPU: the P partitions where pass 1 left them.  Multi-GPU: every partition goes to its
+  // owner over NVLink; partition p of source rank s arrives as its own "virtual partition", listed
+  // partition-major so pass 2 still walks the table slice by slice.
+  std::vector<unsigned long long> v_ptr, v_cnt;
+  DevBuf<unsigned long long> rbuf;
+  if (N == 1) {
     for (int p = 0; p < P; ++p) {
-      P2P x;
-      x.send = pk.p + h_base[p];
-      x.bytes = (size_t)h_count[p] * 8;
-      x.peer = p / Pl;
-      sends.push_back(x);
+      v_ptr.push_back((unsigned long long)(uintptr_t)(pk.p + h_base[p]));
+      v_cnt.push_back(h_count[p]);
     }
-    for (int pl = 0; pl < Pl; ++pl) {
-      l_base[pl] = total;
-      for (int src = 0; src < N; ++src) total += all[(size_t)src * P + p0 + pl];
-      l_count[pl] = total - l_base[pl];
-    }
-    DevBuf<unsigned long long> rbuf(std::max<uint64_t>(total, 1), s);
-    // recvs from one peer must be posted in the order that peer sends: ascending partition
-    for (int src = 0; src < N; ++src) {
+  } else {
+    ScopedStage st(c, "count_exchange");
+    const int Pl = P / N, p0 = R * Pl;
+    std::vector<uint64_t> mine(P + 2), all((size_t)N * (P + 2));
+    for (int p = 0; p < P; ++p) mine[p] = h_count[p];
+    mine[P] = cap;
+    mine[P + 1] = reran ? 1 : 0;  // exact layout: not cap-strided
+    dist_allgather_host_u64(c, mine.data(), P + 2, all.data());
+    auto cnt_of = [&](int src, int p) { return all[(size_t)src * (P + 2) + p]; };
+    bool strided = true;
+    for (int r = 0; r < N; ++r) strided = strided && all[(size_t)r * (P + 2) + P + 1] == 0;
+    std::vector<P2P> sends, recvs;
+    if (strided) {
+      // fast path: ONE message per peer -- the cap-strided block of the peer's partitions as it
+      // lies in memory (the ~11 % slack travels too; NCCL p2p costs ~17 us per message, measured)
+      std::vector<uint64_t> src_off(N, 0);
+      uint64_t total = 0;
+      for (int src = 0; src < N; ++src) {
+        if (src == R) continue;
+        src_off[src] = total;
+        total += (uint64_t)Pl * all[(size_t)src * (P + 2) + P];
+      }
+      rbuf.alloc(std::max<uint64_t>(total, 1), s);
+      for (int d = 0; d < N; ++d) {
+        if (d == R) continue;
+        P2P x, y;
+        x.send = pk.p + (uint64_t)d * Pl * cap;
+        x.bytes = (size_t)Pl * cap * 8;
+        x.peer = d;
+        sends.push_back(x);
+        y.recv = rbuf.p + src_off[d];
+        y.bytes = (size_t)Pl * all[(size_t)d * (P + 2) + P] * 8;
+        y.peer = d;
+        recvs.push_back(y);
+      }
+      for (int pl = 0; pl < Pl; ++pl)
+        for (int src = 0; src < N; ++src) {
+          const uint64_t cap_s = all[(size_t)src * (P + 2) + P];
+          const unsigned long long* ptr = src == R ? pk.p + (uint64_t)(p0 + pl) * cap : rbuf.p + src_off[src] + (uint64_t)pl * cap_s;
+          v_ptr.push_back((unsigned long long)(uintptr_t)ptr);
+          v_cnt.push_back(cnt_of(src, p0 + pl));
+        }
+    } else {
+      // general path (some rank re-ran pass 1 with exact offsets): one message per partition
+      uint64_t total = 0;
+      std::vector<uint64_t> l_base(Pl);
       for (int pl = 0; pl < Pl; ++pl) {
-        uint64_t off = l_base[pl];
-        for (int q = 0; q < src; ++q) off += all[(size_t)q * P + p0 + pl];
+        l_base[pl] = total;
+        for (int src = 0; src < N; ++src) total += cnt_of(src, p0 + pl);
+      }
+      rbuf.alloc(std::max<uint64_t>(total, 1), s);
+      for (int p = 0; p < P; ++p) {
         P2P x;
-        x.recv = rbuf.p + off;
-        x.bytes = (size_t)all[(size_t)src * P + p0 + pl] * 8;
-        x.peer = src;
-        recvs.push_back(x);
+        x.send = pk.p + h_base[p];
+        x.bytes = (size_t)h_count[p] * 8;
+        x.peer = p / Pl;
+        sends.push_back(x);
+      }
+      // recvs from one peer must be posted in the order that peer sends: ascending partition
+      for (int src = 0; src < N; ++src)
+        for (int pl = 0; pl < Pl; ++pl) {
+          uint64_t off = l_base[pl];
+          for (int q = 0; q < src; ++q) off += cnt_of(q, p0 + pl);
+          P2P x;
+          x.recv = rbuf.p + off;
+          x.bytes = (size_t)cnt_of(src, p0 + pl) * 8;
+          x.peer = src;
+          recvs.push_back(x);
+        }
+      for (int pl = 0; pl < Pl; ++pl) {
+        uint64_t cnt = 0;
+        for (int src = 0; src < N; ++src) cnt += cnt_of(src, p0 + pl);
+        v_ptr.push_back((unsigned long long)(uintptr_t)(rbuf.p + l_base[pl]));
+        v_cnt.push_back(cnt);
       }
     }
     dist_p2p_batch(c, sends, recvs);
-    pk = std::move(rbuf);
-    part_base.alloc(Pl, s);
-    cursors.alloc(Pl, s);
-    h_base.assign(l_base.begin(), l_base.end());
-    h_count.assign(l_count.begin(), l_count.end());
-    BGX_CUDA(cudaMemcpyAsync(part_base.p, h_base.data(), Pl * 8, cudaMemcpyHostToDevice, s));
-    BGX_CUDA(cudaMemcpyAsync(cursors.p, h_count.data(), Pl * 8, cudaMemcpyHostToDevice, s));
-    c->add_stat("count_exchange_bytes_out", 8.0 * (double)std::accumulate(mine.begin(), mine.end(), (uint64_t)0));
+    uint64_t out_bytes = 0;
+    for (const P2P& x : sends)
+      if (x.peer != R) out_bytes += x.bytes;
+    c->add_stat("count_exchange_bytes_out", (double)out_bytes);
     st.stop();
   }
+  const uint32_t V = (uint32_t)v_ptr.size();
+  DevBuf<unsigned long long> d_ptr(V, s), d_cnt(V, s);
+  BGX_CUDA(cudaMemcpyAsync(d_ptr.p, v_ptr.data(), V * 8, cudaMemcpyHostToDevice, s));
+  BGX_CUDA(cudaMemcpyAsync(d_cnt.p, v_cnt.data(), V * 8, cudaMemcpyHostToDevice, s));
   uint64_t n_inst = 0, max_count = 0;
-  for (int p = 0; p < Pl; ++p) { n_inst += h_count[p]; max_count = std::max<uint64_t>(max_count, h_count[p]); }
+  for (uint32_t p = 0; p < V; ++p) { n_inst += v_cnt[p]; max_count = std::max<uint64_t>(max_count, v_cnt[p]); }
   const uint32_t tiles_per_part = (uint32_t)std::max<uint64_t>(1, (max_count + kUpsTile - 1) / kUpsTile);
-  BGX_CHECK((uint64_t)tiles_per_part * Pl < (1ull << 31), "too many k-mer tiles for one launch");
+  BGX_CHECK((uint64_t)tiles_per_part * V < (1ull << 31), "too many k-mer tiles for one launch");
+  const unsigned long long* const* part_ptr = reinterpret_cast<const unsigned long long* const*>(d_ptr.p);
   if (N > 1) {
-    // the owner estimates the distinct count of what it received
-    KLAUNCH(kmer_estimate_words_kernel)<<<tiles_per_part * (uint32_t)Pl, 256, 0, s>>>(pk.p, part_base.p, cursors.p,
-                                                                             tiles_per_part, k, bitmap.p, bits - 1);
+    // the owner estimates the distinct count of what it received (pass 1 filled the bitmap with
+    // this rank's own reads over the whole hash space: start over)
+    BGX_CUDA(cudaMemsetAsync(bitmap.p, 0, bits / 8, s));
+    KLAUNCH(kmer_estimate_words_kernel)<<<tiles_per_part * V, 256, 0, s>>>(part_ptr, d_cnt.p, tiles_per_part, k, bitmap.p,
+                                                                    bits - 1);
     KLAUNCH(popcount_kernel)<<<(unsigned)((bits / 32 + 255) / 256), 256, 0, s>>>(bitmap.p, bits / 32, ones.p);
     BGX_CUDA(cudaGetLastError());
     BGX_CUDA(cudaMemcpyAsync(&h_ones, ones.p, 8, cudaMemcpyDeviceToHost, s));
@@ -641,8 +693,8 @@ void stage_count_kmers(Context* c) {
     BGX_CUDA(cudaMemsetAsync(overflow.p, 0, sizeof(int), s));
     {
       ScopedStage st(c, "count_kernel");
-      KLAUNCH(kmer_upsert_kernel)<<<tiles_per_part * (uint32_t)Pl, 256, 0, s>>>(pk.p, part_base.p, cursors.p, tiles_per_part, k,
-                                                                       c->table.p, log2_exact(slots), rank_bits, overflow.p);
+      KLAUNCH(kmer_upsert_kernel)<<<tiles_per_part * V, 256, 0, s>>>(part_ptr, d_cnt.p, tiles_per_part, k, c->table.p,
+                                                              log2_exact(slots), rank_bits, overflow.p);
       BGX_CUDA(cudaGetLastError());
       st.stop();
     }
@@ -655,6 +707,7 @@ void stage_count_kmers(Context* c) {
     slots *= 2;
   }
   pk.release();
+  rbuf.release();
 
   // filter (kmer_passes: fwd+rev >= min_count) and build the solid set: ONE sweep into buffers
   // sized by the bound #solid <= instances / min_count.

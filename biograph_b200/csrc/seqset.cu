@@ -559,23 +559,35 @@ __global__ void __launch_bounds__(128) uncovered_kernel(const uint64_t* __restri
                                                         const uint64_t* __restrict__ locs, uint32_t n, NextRec next,
                                                         const uint64_t* __restrict__ xkeys,
                                                         const uint64_t* __restrict__ xlocs, uint32_t m,
-                                                        int emit_suffixes, uint32_t* __restrict__ cnt) {
+                                                        int emit_suffixes, uint32_t* __restrict__ cnt,
+                                                        uint32_t* __restrict__ list,
+                                                        unsigned long long* __restrict__ n_list) {
   uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
-  if (j >= m) return;
-  uint32_t where;
-  bool cov = covered_next(store, keys, locs, n, next, xkeys[j], xlocs[j], &where);
-  cnt[j] = cov ? 0u : (emit_suffixes ? loc_len(xlocs[j]) : 1u);
+  bool unc = false;
+  if (j < m) {
+    uint32_t where;
+    unc = !covered_next(store, keys, locs, n, next, xkeys[j], xlocs[j], &where);
+    cnt[j] = unc ? (emit_suffixes ? loc_len(xlocs[j]) : 1u) : 0u;
+  }
+  // the (few) uncovered ones go on a list so the emit kernel only visits them
+  unsigned mask = __ballot_sync(0xffffffffu, unc);
+  if (!mask) return;
+  unsigned lane = lane_id();
+  unsigned long long base = 0;
+  if (lane == 0) base = atomicAdd(n_list, (unsigned long long)__popc(mask));
+  base = __shfl_sync(0xffffffffu, base, 0);
+  if (unc) list[base + __popc(mask & ((1u << lane) - 1))] = j;
 }
 
 // emit record j itself (and, when emit_suffixes, every further suffix of it) at off[j]
 __global__ void emit_uncovered_kernel(const uint64_t* __restrict__ store, const uint64_t* __restrict__ xkeys,
                                       const uint64_t* __restrict__ xlocs, const uint32_t* __restrict__ cnt,
-                                      const uint32_t* __restrict__ off, uint32_t m, uint64_t* __restrict__ okeys,
-                                      uint64_t* __restrict__ olocs) {
-  uint32_t j = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-  if (j >= m) return;
+                                      const uint32_t* __restrict__ off, const uint32_t* __restrict__ list,
+                                      uint32_t n_list, uint64_t* __restrict__ okeys, uint64_t* __restrict__ olocs) {
+  uint32_t w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  if (w >= n_list) return;
+  uint32_t j = list[w];
   uint32_t c = cnt[j];
-  if (!c) return;
   uint64_t addr = loc_addr(xlocs[j]);
   int len = (int)loc_len(xlocs[j]);
   uint32_t o = off[j];
@@ -937,6 +949,7 @@ Routed route_records(Context* c, const uint64_t* keys, const uint64_t* locs, uin
   DevBuf<uint8_t> dest(std::max<uint32_t>(n, 1), s);
   DevBuf<unsigned long long> counts(kMaxRanks, s);
   BGX_CUDA(cudaMemsetAsync(counts.p, 0, kMaxRanks * 8, s));
+  ScopedStage st_k(c, "route_kernels");
   if (n) KLAUNCH(route_count_kernel)<<<grid_for(n, 256), 256, 0, s>>>(c->seq_store(), keys, locs, n, sp, dest.p, counts.p);
   std::vector<uint64_t> send_cnt(N), send_off(N), all((size_t)N * N), recv_cnt(N), recv_off(N);
   {
@@ -953,6 +966,8 @@ Routed route_records(Context* c, const uint64_t* keys, const uint64_t* locs, uin
     if (n) KLAUNCH(route_scatter_kernel)<<<grid_for(n, 256), 256, 0, s>>>(keys, locs, dest.p, n, N, counts.p, skeys.p, slocs.p);
     BGX_CUDA(cudaGetLastError());
   }
+  st_k.stop();
+  ScopedStage st_x(c, "route_exchange");
   dist_allgather_host_u64(c, send_cnt.data(), N, all.data());
   uint64_t m = 0;
   for (int src = 0; src < N; ++src) { recv_cnt[src] = all[(size_t)src * N + R]; recv_off[src] = m; m += recv_cnt[src]; }
@@ -964,6 +979,7 @@ Routed route_records(Context* c, const uint64_t* keys, const uint64_t* locs, uin
   dist_alltoallv(c, skeys.p, send_off.data(), send_cnt.data(), out.keys.p, recv_off.data(), recv_cnt.data(), 8);
   dist_alltoallv(c, slocs.p, send_off.data(), send_cnt.data(), out.locs.p, recv_off.data(), recv_cnt.data(), 8);
   BGX_CUDA(cudaStreamSynchronize(s));  // the send buffers die with this scope
+  st_x.stop();
   c->add_stat("route_records_out", (double)n - (double)send_cnt[R]);
   c->add_stat("route_bytes_out", 16.0 * ((double)n - (double)send_cnt[R]));
   st.stop();
@@ -1121,27 +1137,34 @@ void stage_build_seqset_dist(Context* c) {
     qk.release();
     ql.release();
     // uncovered queries -> themselves + all their suffixes
-    DevBuf<uint32_t> cnt(std::max<uint32_t>(q.n, 1), s), off(std::max<uint32_t>(q.n, 1), s), tot(1, s);
+    ScopedStage st_u(c, "walk_uncovered");
+    DevBuf<uint32_t> cnt(std::max<uint32_t>(q.n, 1), s), off(std::max<uint32_t>(q.n, 1), s), list(std::max<uint32_t>(q.n, 1), s), tot(1, s);
+    DevBuf<unsigned long long> nl_d(1, s);
+    BGX_CUDA(cudaMemsetAsync(nl_d.p, 0, 8, s));
     if (q.n) KLAUNCH(uncovered_kernel)<<<grid_for(q.n, 128), 128, 0, s>>>(store, keys.p, locs.p, n1, next, q.keys.p, q.locs.p, q.n,
-                                                                  1, cnt.p);
+                                                                  1, cnt.p, list.p, nl_d.p);
     exclusive_scan_u32(cnt.p, off.p, q.n, tot.p, s);
     uint32_t n_cand = read_u32(tot.p, s);
+    uint32_t n_list = (uint32_t)read_u64(nl_d.p, s);
+    st_u.stop();
+    c->set_stat("walk_chains", n_list);
     c->set_stat("walk_candidates", n_cand);
     DevBuf<uint64_t> ck(std::max<uint32_t>(n_cand, 1), s), cl(std::max<uint32_t>(n_cand, 1), s);
-    if (q.n) KLAUNCH(emit_uncovered_kernel)<<<grid_for((uint64_t)q.n * 32, 128), 128, 0, s>>>(store, q.keys.p, q.locs.p, cnt.p,
-                                                                                       off.p, q.n, ck.p, cl.p);
+    if (n_list) KLAUNCH(emit_uncovered_kernel)<<<grid_for((uint64_t)n_list * 32, 128), 128, 0, s>>>(store, q.keys.p, q.locs.p, cnt.p,
+                                                                                         off.p, list.p, n_list, ck.p, cl.p);
     BGX_CUDA(cudaGetLastError());
     Routed cd = route_records(c, ck.p, cl.p, n_cand, sp);
     // owners keep the candidates nothing covers yet
-    DevBuf<uint32_t> cnt2(std::max<uint32_t>(cd.n, 1), s), off2(std::max<uint32_t>(cd.n, 1), s);
+    DevBuf<uint32_t> cnt2(std::max<uint32_t>(cd.n, 1), s), off2(std::max<uint32_t>(cd.n, 1), s), list2(std::max<uint32_t>(cd.n, 1), s);
+    BGX_CUDA(cudaMemsetAsync(nl_d.p, 0, 8, s));
     if (cd.n) KLAUNCH(uncovered_kernel)<<<grid_for(cd.n, 128), 128, 0, s>>>(store, keys.p, locs.p, n1, next, cd.keys.p, cd.locs.p,
-                                                                    cd.n, 0, cnt2.p);
+                                                                    cd.n, 0, cnt2.p, list2.p, nl_d.p);
     exclusive_scan_u32(cnt2.p, off2.p, cd.n, tot.p, s);
     n_new = read_u32(tot.p, s);
     nkeys.alloc(std::max<uint32_t>(n_new, 1), s);
     nlocs.alloc(std::max<uint32_t>(n_new, 1), s);
-    if (cd.n) KLAUNCH(emit_uncovered_kernel)<<<grid_for((uint64_t)cd.n * 32, 128), 128, 0, s>>>(store, cd.keys.p, cd.locs.p, cnt2.p,
-                                                                                        off2.p, cd.n, nkeys.p, nlocs.p);
+    if (n_new) KLAUNCH(emit_uncovered_kernel)<<<grid_for((uint64_t)n_new * 32, 128), 128, 0, s>>>(store, cd.keys.p, cd.locs.p, cnt2.p,
+                                                                                        off2.p, list2.p, n_new, nkeys.p, nlocs.p);
     BGX_CUDA(cudaGetLastError());
     st.stop();
   }
@@ -1247,9 +1270,11 @@ void stage_build_seqset_dist(Context* c) {
       }
       uint32_t nq = (uint32_t)read_u64(nq_d.p, s);
       Routed q = route_records(c, qk.p, ql.p, nq, sp2);
+      ScopedStage st_p(c, "tables_prev_apply");
       if (q.n) KLAUNCH(prev_apply_kernel)<<<grid_for(q.n, 128), 128, 0, s>>>(store, keys.p, locs.p, n2, next, q.keys.p, q.locs.p, q.n,
                                                                      bits, c->prev_words, flags.p, flags.p + 8);
       BGX_CUDA(cudaGetLastError());
+      st_p.stop();
     }
     // carries, single-base entries, missing flag, max length: tiny all-gather
     {
