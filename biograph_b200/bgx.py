@@ -41,7 +41,7 @@ EXPORTS = ["bgx_default_options", "bgx_last_error", "bgx_version", "bgx_device_c
            "bgx_free", "bgx_add_reads_ascii", "bgx_add_reads_packed", "bgx_count_kmers", "bgx_export_kmers",
            "bgx_correct", "bgx_export_corrected", "bgx_build_seqset", "bgx_export_seqset",
            "bgx_export_entries_ascii", "bgx_run", "bgx_reset_results", "bgx_clear_reads", "bgx_stats_json", "bgx_timer_start", "bgx_timer_stop",
-           "bgx_launch_count", "bgx_debug_sort_pairs", "bgx_dist_unique_id", "bgx_dist_init", "bgx_seqset_layout"]
+           "bgx_launch_count", "bgx_debug_sort_pairs", "bgx_dist_unique_id", "bgx_dist_init", "bgx_seqset_layout", "bgx_seed_uncorrected", "bgx_export_varbit"]
 
 
 def load_library():
@@ -82,6 +82,8 @@ def load_library():
     L.bgx_dist_unique_id.argtypes = [vp]
     L.bgx_dist_init.argtypes = [vp, C.c_int32, C.c_int32, vp]
     L.bgx_seqset_layout.argtypes = [vp, C.c_uint64 * 6]
+    L.bgx_seed_uncorrected.argtypes = [vp]
+    L.bgx_export_varbit.argtypes = [vp, C.c_int32, C.POINTER(vp), u64p, C.POINTER(C.c_uint32), u64p]
     _LIB = L
     return L
 
@@ -250,6 +252,16 @@ class Bgx:
     # -- correct_reads::correct ------------------------------------------------------------------
     def correct(self):
         self._ck(self.L.bgx_correct(self.h))
+
+    def seed_uncorrected(self):
+        """seqset_for_reads seeding (no k-mer stage, no correction)"""
+        self._ck(self.L.bgx_seed_uncorrected(self.h))
+
+    def export_varbit(self, which):
+        """packed_varbit_vector of entry_sizes (which=0) / shared (which=1)"""
+        p, nw, b, mv = C.c_void_p(), C.c_uint64(), C.c_uint32(), C.c_uint64()
+        self._ck(self.L.bgx_export_varbit(self.h, which, C.byref(p), C.byref(nw), C.byref(b), C.byref(mv)))
+        return {"elements": self._take(p, nw.value, np.uint64), "bits_per_value": b.value, "max_value": mv.value}
 
     def export_corrected(self):
         n, nb = C.c_uint64(), C.c_uint64()

@@ -159,6 +159,13 @@ int bgx_export_kmers(bgx_ctx* x, uint32_t min_count, uint64_t* n, uint64_t** kme
 
 int bgx_correct(bgx_ctx* x) { CTX_GUARD({ stage_correct(c); }) }
 
+int bgx_seed_uncorrected(bgx_ctx* x) { CTX_GUARD({ stage_seed_uncorrected(c); }) }
+
+int bgx_export_varbit(bgx_ctx* x, int32_t which, uint64_t** words, uint64_t* n_words, uint32_t* bits_per_value,
+                      uint64_t* max_value) {
+  CTX_GUARD({ export_varbit(c, which, words, n_words, bits_per_value, max_value); })
+}
+
 int bgx_export_corrected(bgx_ctx* x, uint64_t* n_reads, uint16_t** lens, char** bases, uint64_t* n_bases,
                          uint8_t** corrections, uint16_t** next_fwd, uint16_t** next_rev) {
   CTX_GUARD({

@@ -351,7 +351,76 @@ __global__ void __launch_bounds__(128) correct_kernel(const uint64_t* __restrict
   }
 }
 
+// seqset_for_reads seeding: the read as it is + its reverse complement, one seed each
+__global__ void __launch_bounds__(128) passthrough_kernel(const uint64_t* __restrict__ words,
+                                                          const uint32_t* __restrict__ word_off,
+                                                          const uint16_t* __restrict__ lens, uint32_t n_reads,
+                                                          uint64_t* __restrict__ store, uint64_t rc_word_base,
+                                                          uint16_t* __restrict__ clen, uint8_t* __restrict__ ncorr,
+                                                          uint16_t* __restrict__ next_fwd, uint16_t* __restrict__ next_rev,
+                                                          unsigned long long* __restrict__ totals) {
+  const uint32_t r = blockIdx.x * blockDim.x + threadIdx.x;
+  int L = 0;
+  if (r < n_reads) {
+    L = lens[r];
+    const int nw = (L + 31) >> 5;
+    const uint32_t base = word_off[r];
+    uint64_t w[kMaxWords];
+#pragma unroll
+    for (int i = 0; i < kMaxWords; ++i) w[i] = i < nw ? words[base + i] : 0;
+    for (int i = 0; i < nw; ++i) store[base + i] = w[i];
+    for (int q = 0; q < nw; ++q) {
+      int mcount = min(32, L - 32 * q);
+      int lo_pos = L - 32 * q - mcount;
+      uint64_t x = local_window(w, lo_pos) >> (64 - 2 * mcount);
+      store[rc_word_base + base + q] = revcomp_kmer(x, mcount) << (64 - 2 * mcount);
+    }
+    clen[r] = (uint16_t)L;
+    ncorr[r] = 0;
+    next_fwd[r] = L ? 1 : 0;
+    next_rev[r] = L ? 1 : 0;
+  }
+  unsigned kept = warp_sum(L ? 1u : 0u), kb = warp_sum((unsigned)L);
+  if (lane_id() == 0 && kept) {
+    atomicAdd(&totals[0], (unsigned long long)kept);
+    atomicAdd(&totals[1], (unsigned long long)kb);
+    atomicAdd(&totals[2], 2ULL * kept);
+  }
+}
+
 }  // namespace
+
+void stage_seed_uncorrected(Context* c) {
+  BGX_CHECK(!c->has_n, "bgx_seed_uncorrected: reads must not contain N");
+  cudaStream_t s = c->stream;
+  ScopedStage st_all(c, "correct_total");
+  const uint64_t n = c->n_reads;
+  c->store.alloc(2 * c->n_words + 1, s);
+  c->clen.alloc(std::max<uint64_t>(n, 1), s);
+  c->ncorr.alloc(std::max<uint64_t>(n, 1), s);
+  c->next_fwd.alloc(std::max<uint64_t>(n, 1), s);
+  c->next_rev.alloc(std::max<uint64_t>(n, 1), s);
+  DevBuf<unsigned long long> totals(3, s);
+  BGX_CUDA(cudaMemsetAsync(totals.p, 0, 3 * sizeof(unsigned long long), s));
+  BGX_CUDA(cudaMemsetAsync(c->store.p + 2 * c->n_words, 0, sizeof(uint64_t), s));
+  if (n)
+    KLAUNCH(passthrough_kernel)<<<(unsigned)((n + 127) / 128), 128, 0, s>>>(c->words.p, c->word_off.p, c->lens.p, (uint32_t)n,
+                                                                  c->store.p, c->n_words, c->clen.p, c->ncorr.p,
+                                                                  c->next_fwd.p, c->next_rev.p, totals.p);
+  BGX_CUDA(cudaGetLastError());
+  unsigned long long h[3];
+  BGX_CUDA(cudaMemcpyAsync(h, totals.p, sizeof(h), cudaMemcpyDeviceToHost, s));
+  BGX_CUDA(cudaStreamSynchronize(s));
+  c->n_kept = h[0];
+  c->kept_bases = h[1];
+  c->n_seeds = h[2];
+  c->corrected = true;
+  c->built = false;
+  st_all.stop();
+  c->set_stat("reads_kept", (double)h[0]);
+  c->set_stat("corrected_bases", (double)h[1]);
+  c->set_stat("seeds", (double)h[2]);
+}
 
 void stage_correct(Context* c) {
   BGX_CHECK(c->counted, "bgx_correct: call bgx_count_kmers first");

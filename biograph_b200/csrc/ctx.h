@@ -123,6 +123,8 @@ void stage_count_kmers(Context* c);
 void export_kmers(Context* c, uint32_t min_count, uint64_t* n, uint64_t** kmers, uint32_t** fwd, uint32_t** rev,
                   uint8_t** flags);
 void stage_correct(Context* c);
+void stage_seed_uncorrected(Context* c);
+void export_varbit(Context* c, int which, uint64_t** words, uint64_t* n_words, uint32_t* bits, uint64_t* max_value);
 void stage_build_seqset(Context* c);
 
 }  // namespace bgx

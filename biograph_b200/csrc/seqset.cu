@@ -668,6 +668,22 @@ __global__ void bitcount_accum_offset_kernel(const uint32_t* __restrict__ group_
   accum[g] = before + (g < groups ? group_excl[g] : *total);
 }
 
+// packed_varbit_vector elements (modules/io/packed_varbit_vector.cpp:80-139): value i occupies bits
+// [i*b, (i+1)*b) of the little-endian word stream.  One thread per output word.
+__global__ void varbit_pack_kernel(const uint16_t* __restrict__ vals, uint64_t n, unsigned b, uint64_t n_words,
+                                   unsigned long long* __restrict__ out) {
+  uint64_t w = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (w >= n_words) return;
+  const uint64_t bit0 = w * 64;
+  unsigned long long acc = 0;
+  for (uint64_t i = bit0 / b; i < n && i * b < bit0 + 64; ++i) {
+    const unsigned long long v = vals[i];
+    const int64_t sh = (int64_t)(i * b) - (int64_t)bit0;
+    acc |= sh >= 0 ? (v << sh) : (v >> (-sh));
+  }
+  out[w] = acc;
+}
+
 inline unsigned grid_for(uint64_t n, unsigned block) { return (unsigned)std::max<uint64_t>(1, (n + block - 1) / block); }
 
 uint32_t read_u32(const uint32_t* d, cudaStream_t s) {
@@ -1354,6 +1370,28 @@ void stage_build_seqset_dist(Context* c) {
   c->ent_loc = std::move(locs);
   c->built = true;
   st_all.stop();
+}
+
+void export_varbit(Context* c, int which, uint64_t** words, uint64_t* n_words, uint32_t* bits, uint64_t* max_value) {
+  BGX_CHECK(c->built, "bgx_export_varbit: call bgx_build_seqset first");
+  BGX_CHECK(which == 0 || which == 1, "bgx_export_varbit: which must be 0 (entry_sizes) or 1 (shared)");
+  cudaStream_t s = c->stream;
+  // seqset ctor (modules/bio_base/seqset.cpp:27-33): max_value = max_entry_len, resp. max_entry_len - 1
+  const uint64_t mv = which == 0 ? c->max_entry_len : (c->max_entry_len ? c->max_entry_len - 1 : 0);
+  unsigned b = 0;  // bits_for_value (packed_varbit_vector.cpp:174-182): bit length of max_value (0 for 0)
+  while ((mv >> b) != 0) ++b;
+  const uint64_t n = c->n_entries, nw = (n * b + 63) / 64;
+  DevBuf<unsigned long long> d(std::max<uint64_t>(nw, 1), s);
+  if (nw)
+    KLAUNCH(varbit_pack_kernel)<<<grid_for(nw, 256), 256, 0, s>>>(which == 0 ? c->sizes.p : c->shared.p, n, b, nw, d.p);
+  BGX_CUDA(cudaGetLastError());
+  uint64_t* h = (uint64_t*)malloc(std::max<uint64_t>(nw, 1) * 8);
+  if (nw) BGX_CUDA(cudaMemcpyAsync(h, d.p, nw * 8, cudaMemcpyDeviceToHost, s));
+  BGX_CUDA(cudaStreamSynchronize(s));
+  *words = h;
+  *n_words = nw;
+  *bits = b;
+  *max_value = mv;
 }
 
 void export_entries_ascii(Context* c, uint64_t first, uint64_t count, char** bases, uint64_t** offs_out) {

@@ -89,6 +89,13 @@ int bgx_export_kmers(bgx_ctx* ctx, uint32_t min_count, uint64_t* n, uint64_t** k
  * fast_read_correct (modules/bio_base/fast_read_correct.cpp) and the seed counts. */
 int bgx_correct(bgx_ctx* ctx);
 
+/* replaces: the seeding of seqset_for_reads (modules/bio_base/seqset_testutil.cpp:19-59:
+ * part_repo::write(read, 1, 1) for every read, no correction) -- "the simplest whole-stage-3
+ * operator" (SURVEY 8b).  Treats the resident reads as already corrected: every read and its
+ * reverse complement seed exactly one suffix record.  Reads must not contain 'N'.  Replaces
+ * bgx_count_kmers + bgx_correct; follow with bgx_build_seqset. */
+int bgx_seed_uncorrected(bgx_ctx* ctx);
+
 /* Parity hook + make_readmap input (corrected_reads kv sink, biograph_create.cpp:868-893).
  * lens[r] = corrected length, 0 if the read was dropped; bases = ASCII of kept reads
  * concatenated in input order; corrections[r], next_fwd[r], next_rev[r] as in
@@ -109,6 +116,14 @@ int bgx_build_seqset(bgx_ctx* ctx);
 int bgx_export_seqset(bgx_ctx* ctx, uint64_t* n_entries, uint32_t* max_entry_len, uint16_t** sizes,
                       uint16_t** shared, uint64_t* prev_bits[4], uint64_t* prev_subaccum[4],
                       uint64_t* prev_accum[4], uint64_t fixed[5]);
+
+/* replaces: mutable_packed_varbit_vector (modules/io/packed_varbit_vector.cpp:174-228), the
+ * `elements` member of entry_sizes (which = 0, max_value = max entry length) and shared
+ * (which = 1, max_value = max entry length - 1): values packed LSB-first into little-endian uint64
+ * words at bits_per_value = bit_length(max_value).  Multi-GPU: each rank packs its own range;
+ * ranges are multiples of 512 entries, so the word arrays concatenate. */
+int bgx_export_varbit(bgx_ctx* ctx, int32_t which, uint64_t** words, uint64_t* n_words, uint32_t* bits_per_value,
+                      uint64_t* max_value);
 
 /* Debug/parity hook: entry i as ASCII (entries are <= BGX_MAX_READ_LEN bases). */
 int bgx_export_entries_ascii(bgx_ctx* ctx, uint64_t first, uint64_t count, char** bases,

@@ -1,0 +1,477 @@
+// bgx_build_seqset.hpp -- C++ host façade over the bgx C ABI (include/bgx.h) with the class and
+// method names of the reference's build_seqset stages, so that SEQSETMain
+// (modules/biograph/biograph_create.cpp:431-950) keeps its call sites.  Header-only, C++17, no
+// CUDA types: link with -lbgx.  INTEGRATION.md shows the edits to biograph_create.cpp.
+//
+//   reference (CPU, threads + temp files)                      this façade (one GPU per context)
+//   --------------------------------------------------------   -----------------------------------------
+//   build_seqset::kmer_counter + prob_pass_processor::add      kmer_counter::prob_pass_processor::add
+//     (bs/kmer_counter.h:123-155, 297-326)                       -> bgx_add_reads_ascii (batched)
+//   run_kmerize_subtask (bio_mapred/kmerize_bf.h:81-84)        run_kmerize_subtask -> bgx_count_kmers
+//   kmer_set (bio_mapred/kmer_set.h)                           kmer_set (sorted canonical k-mers + flags)
+//   build_seqset::correct_reads::correct                       correct_reads::correct_all -> bgx_correct
+//     (bs/correct_reads.h:14-22, .cpp:154-231)
+//   build_seqset::expander::sort_and_dedup / expand            expander (rounds collapse into one closure
+//     (bs/expand.h:9-46)                                         walk on the GPU; counts are reported)
+//   build_seqset::builder::build_chunks / make_seqset          builder -> bgx_build_seqset / bgx_export_*
+//     (bs/builder.h:9-15)
+//   seqset_for_reads (bio_base/seqset_testutil.h:13)           seqset_for_reads
+//   spiral_file_create_mmap + seqset ctor/finalize             seqset_file_writer (stored zip, members in the
+//     (io/spiral_file_mmap.cpp, bio_base/seqset.cpp:19-44)       reference's order and byte layout)
+//
+// Errors: the reference throws io_exception; every failing C-ABI call is rethrown here as
+// bgx_bs::io_exception carrying bgx_last_error().
+#pragma once
+
+#include <algorithm>
+#include <cstdint>
+#include <cstdio>
+#include <cstring>
+#include <ctime>
+#include <functional>
+#include <memory>
+#include <mutex>
+#include <stdexcept>
+#include <string>
+#include <utility>
+#include <vector>
+
+#include "bgx.h"
+
+namespace bgx_bs {
+
+using kmer_t = uint64_t;                                   // modules/bio_base/dna_sequence.h:13
+using progress_handler_t = std::function<void(double)>;    // modules/io/progress.h
+inline void null_progress_handler(double) {}
+
+struct io_exception : std::runtime_error {                 // modules/io/io.h
+  using std::runtime_error::runtime_error;
+};
+
+namespace detail {
+inline void ck(int rc) {
+  if (rc) throw io_exception(bgx_last_error());
+}
+template <typename T>
+struct host_array {  // library-owned host buffer, released with bgx_free
+  T* p = nullptr;
+  uint64_t n = 0;
+  host_array() = default;
+  host_array(const host_array&) = delete;
+  host_array& operator=(const host_array&) = delete;
+  host_array(host_array&& o) noexcept : p(o.p), n(o.n) { o.p = nullptr; }
+  host_array& operator=(host_array&& o) noexcept {
+    if (this != &o) { bgx_free(p); p = o.p; n = o.n; o.p = nullptr; }
+    return *this;
+  }
+  ~host_array() { bgx_free(p); }
+  const T& operator[](uint64_t i) const { return p[i]; }
+};
+}  // namespace detail
+
+// `biograph create` flags that reach the path (biograph_create.cpp:258-335); defaults as the CLI
+struct count_kmer_options {        // bs/kmer_counter.h: count_kmer_options (subset that affects results)
+  unsigned kmer_size = 30;
+  unsigned min_count = 5;          // kmerize_bf_params::min_count
+  int device = 0;
+};
+
+struct read_correction_params {    // modules/bio_mapred/read_correction.h:9-60 (fields the fast path reads)
+  float trim_after_portion = 0.7f;
+  unsigned frc_max_corrections = 8;
+  unsigned frc_min_good_run = 2;
+};
+
+// One build = one GPU context, shared by the stage objects below (the reference shares a
+// part_repo and a kmer_set between its stages the same way).
+class session {
+ public:
+  explicit session(const count_kmer_options& ko = count_kmer_options(),
+                   const read_correction_params& rp = read_correction_params()) {
+    bgx_options o;
+    bgx_default_options(&o);
+    o.kmer_size = (int32_t)ko.kmer_size;
+    o.min_kmer_count = (int32_t)ko.min_count;
+    o.max_corrections = (int32_t)rp.frc_max_corrections;
+    o.min_good_run = (int32_t)rp.frc_min_good_run;
+    o.trim_after_portion = rp.trim_after_portion;
+    o.device = ko.device;
+    m_ko = ko;
+    detail::ck(bgx_create(&o, &m_ctx));
+  }
+  const count_kmer_options& kmer_options() const { return m_ko; }
+  ~session() { bgx_destroy(m_ctx); }
+  session(const session&) = delete;
+  session& operator=(const session&) = delete;
+  bgx_ctx* ctx() const { return m_ctx; }
+  // multi-GPU: one session per rank; see bgx.h
+  static std::vector<uint8_t> unique_id() {
+    std::vector<uint8_t> id(128);
+    detail::ck(bgx_dist_unique_id(id.data()));
+    return id;
+  }
+  void dist_init(int world_size, int rank, const std::vector<uint8_t>& id) {
+    detail::ck(bgx_dist_init(m_ctx, world_size, rank, id.data()));
+  }
+  std::mutex& add_mutex() { return m_add_mu; }
+  // the seqset stage runs once per session, whichever stage object asks first
+  void ensure_seqset_built() {
+    if (!m_built) { detail::ck(bgx_build_seqset(m_ctx)); m_built = true; }
+  }
+
+ private:
+  bool m_built = false;
+  bgx_ctx* m_ctx = nullptr;
+  count_kmer_options m_ko;
+  std::mutex m_add_mu;
+};
+
+// ---- k-mer counting ---------------------------------------------------------------------------------
+class kmer_counter {
+ public:
+  struct element {  // bs/kmer_counter.h:127-137
+    kmer_t kmer = ~kmer_t(0);
+    uint32_t fwd_count = 0, rev_count = 0;
+    bool fwd_starts_read = false, rev_starts_read = false;
+  };
+  explicit kmer_counter(session& s) : m_s(s) {}
+  void start_prob_pass() {}   // no probabilistic pre-pass on the GPU (result-invisible)
+  void close_prob_pass() {}
+  // Per-thread processor (bs/kmer_counter.h:349-357).  add() buffers reads and hands full batches
+  // to the device; many processors may run concurrently on one counter, one add() at a time each.
+  class prob_pass_processor {
+   public:
+    explicit prob_pass_processor(kmer_counter& k, size_t batch_bases = size_t(64) << 20) : m_k(k), m_batch(batch_bases) {
+      m_offs.push_back(0);
+    }
+    ~prob_pass_processor() { flush_all(); }
+    void add(const char* seq, size_t len) {  // the reference takes a string_view
+      m_bases.append(seq, len);
+      m_offs.push_back(m_bases.size());
+      if (m_bases.size() >= m_batch) flush_all();
+    }
+    void add(const std::string& seq) { add(seq.data(), seq.size()); }
+    void flush_all() {  // bs/kmer_counter.cpp:214-223
+      if (m_offs.size() > 1) {
+        std::lock_guard<std::mutex> l(m_k.m_s.add_mutex());  // the C ABI serialises appends per context
+        detail::ck(bgx_add_reads_ascii(m_k.m_s.ctx(), m_bases.data(), m_offs.data(), m_offs.size() - 1));
+      }
+      m_bases.clear();
+      m_offs.assign(1, 0);
+    }
+
+   private:
+    kmer_counter& m_k;
+    size_t m_batch;
+    std::string m_bases;
+    std::vector<uint64_t> m_offs;
+  };
+  // kmer_counter::extract_exact_counts (bs/kmer_counter.h:110-120): every k-mer with
+  // fwd+rev >= min_count, ascending
+  void extract_exact_counts(const std::function<void(const element*, const element*)>& output_f, uint32_t min_count = 1) {
+    uint64_t n = 0;
+    uint64_t* k = nullptr;
+    uint32_t *f = nullptr, *r = nullptr;
+    uint8_t* fl = nullptr;
+    detail::ck(bgx_export_kmers(m_s.ctx(), min_count, &n, &k, &f, &r, &fl));
+    std::vector<element> el(n);
+    for (uint64_t i = 0; i < n; ++i) {
+      el[i].kmer = k[i];
+      el[i].fwd_count = f[i];
+      el[i].rev_count = r[i];
+      el[i].fwd_starts_read = fl[i] & BGX_FLAG_FWD_STARTS_READ;
+      el[i].rev_starts_read = fl[i] & BGX_FLAG_REV_STARTS_READ;
+    }
+    bgx_free(k); bgx_free(f); bgx_free(r); bgx_free(fl);
+    output_f(el.data(), el.data() + n);
+  }
+  void close() {}
+  session& sess() { return m_s; }
+
+ private:
+  session& m_s;
+};
+
+// kmer_set (modules/bio_mapred/kmer_set.h:14-186): the sorted solid k-mers; index = rank
+class kmer_set {
+ public:
+  static constexpr unsigned k_fwd_starts_read = BGX_FLAG_FWD_STARTS_READ;
+  static constexpr unsigned k_rev_starts_read = BGX_FLAG_REV_STARTS_READ;
+  size_t size() const { return m_kmers.size(); }
+  unsigned kmer_size() const { return m_kmer_size; }
+  static constexpr size_t k_not_present = ~size_t(0);
+  size_t find_table_index(kmer_t canonical) const {  // kmer_set.cpp:296-360
+    auto it = std::lower_bound(m_kmers.begin(), m_kmers.end(), canonical);
+    return (it != m_kmers.end() && *it == canonical) ? size_t(it - m_kmers.begin()) : k_not_present;
+  }
+  unsigned get_flags(size_t index) const { return m_flags[index]; }
+  kmer_t operator[](size_t index) const { return m_kmers[index]; }
+
+ private:
+  friend std::unique_ptr<kmer_set> run_kmerize_subtask(kmer_counter*, progress_handler_t);
+  std::vector<kmer_t> m_kmers;
+  std::vector<uint8_t> m_flags;
+  unsigned m_kmer_size = 0;
+};
+
+// run_kmerize_subtask (modules/bio_mapred/kmerize_bf.h:81-84): exact counts, min-count filter,
+// k-mer set.  (The reference also returns count/histogram manifests for the QC report; the
+// histogram can be rebuilt from extract_exact_counts.)
+inline std::unique_ptr<kmer_set> run_kmerize_subtask(kmer_counter* counter, progress_handler_t progress = null_progress_handler) {
+  bgx_ctx* c = counter->sess().ctx();
+  detail::ck(bgx_count_kmers(c));
+  progress(0.9);
+  std::unique_ptr<kmer_set> ks(new kmer_set());
+  ks->m_kmer_size = counter->sess().kmer_options().kmer_size;
+  uint64_t n = 0;
+  uint64_t* k = nullptr;
+  uint32_t *f = nullptr, *r = nullptr;
+  uint8_t* fl = nullptr;
+  // kmer_passes (kmerize_bf.cpp:290-318): fwd + rev >= min_count
+  detail::ck(bgx_export_kmers(c, counter->sess().kmer_options().min_count, &n, &k, &f, &r, &fl));
+  ks->m_kmers.assign(k, k + n);
+  ks->m_flags.assign(fl, fl + n);
+  bgx_free(k); bgx_free(f); bgx_free(r); bgx_free(fl);
+  progress(1.0);
+  return ks;
+}
+
+// ---- read correction ------------------------------------------------------------------------------------
+struct corrected_read {  // modules/bio_base/corrected_read.h (fields this path fills)
+  std::string corrected;   // empty = read dropped
+  unsigned corrections = 0;
+};
+
+class correct_reads {
+ public:
+  correct_reads(session& s, kmer_set& /*ks*/, const read_correction_params& /*params: in the session*/) : m_s(s) {}
+  void add_initial_repo(progress_handler_t = null_progress_handler) {}  // compression only
+  // All resident reads at once; replaces the parallel_for over temp read files
+  // (biograph_create.cpp:858-903).  Afterwards correct(i, cr) reads back read i.
+  void correct_all() {
+    detail::ck(bgx_correct(m_s.ctx()));
+    uint64_t n = 0, nb = 0;
+    uint16_t* lens = nullptr;
+    char* bases = nullptr;
+    uint8_t* corr = nullptr;
+    detail::ck(bgx_export_corrected(m_s.ctx(), &n, &lens, &bases, &nb, &corr, nullptr, nullptr));
+    m_lens.assign(lens, lens + n);
+    m_corr.assign(corr, corr + n);
+    m_bases.assign(bases, bases + nb);
+    m_offs.assign(n + 1, 0);
+    for (uint64_t i = 0; i < n; ++i) m_offs[i + 1] = m_offs[i] + lens[i];
+    bgx_free(lens); bgx_free(bases); bgx_free(corr);
+  }
+  size_t size() const { return m_lens.size(); }
+  // bool correct(const unaligned_read&, corrected_read&) by read index: false = dropped
+  bool correct(size_t read_index, corrected_read& cr) const {
+    cr.corrected.assign(m_bases.data() + m_offs[read_index], m_lens[read_index]);
+    cr.corrections = m_corr[read_index];
+    return m_lens[read_index] != 0;
+  }
+
+ private:
+  session& m_s;
+  std::vector<uint16_t> m_lens;
+  std::vector<uint8_t> m_corr;
+  std::vector<uint64_t> m_offs;
+  std::string m_bases;
+};
+
+// ---- expand / sort / dedup ---------------------------------------------------------------------------------
+// The reference runs three sort_and_dedup rounds with stride-7/255 and stride-1/6 expansions in
+// between (biograph_create.cpp:921-931); they are an I/O schedule for temp files, and the final
+// set is their fixed point.  The GPU build reaches it with one closure walk, so the first call
+// does the whole build and every call reports the matching count.
+class expander {
+ public:
+  expander(session& s, bool /*keep_tmp*/) : m_s(s) {}
+  size_t sort_and_dedup(const std::string& /*already_sorted_pass*/, const std::string& /*new_entries_pass*/,
+                        const std::string& result_sorted_pass, const std::string& /*result_expanded_pass*/,
+                        unsigned /*stride*/, unsigned /*count*/, progress_handler_t progress = null_progress_handler) {
+    ensure_built();
+    progress(1.0);
+    return result_sorted_pass == "init_sorted" ? stat("entries_round1") : stat("entries");
+  }
+  size_t expand(const std::string&, const std::string&, unsigned, unsigned, progress_handler_t progress = null_progress_handler) {
+    ensure_built();
+    progress(1.0);
+    return stat("walk_new_records");
+  }
+
+ private:
+  void ensure_built() { m_s.ensure_seqset_built(); }
+  size_t stat(const char* key) {
+    char buf[1 << 16];
+    detail::ck(bgx_stats_json(m_s.ctx(), buf, sizeof(buf)));
+    std::string pat = std::string("\"") + key + "\":";
+    const char* p = strstr(buf, pat.c_str());
+    return p ? (size_t)strtod(p + pat.size(), nullptr) : 0;
+  }
+  session& m_s;
+};
+
+// ---- output: the seqset tables and the spiral file ---------------------------------------------------------
+struct seqset_tables {  // what seqset's members hold (modules/bio_base/seqset.cpp:19-44)
+  uint64_t num_entries = 0;
+  uint32_t max_entry_len = 0;
+  uint64_t fixed[5] = {0, 0, 0, 0, 0};
+  detail::host_array<uint64_t> sizes_elements, shared_elements;  // packed_varbit_vector `elements`
+  uint32_t sizes_bits = 0, shared_bits = 0;
+  uint64_t sizes_max = 0, shared_max = 0;
+  detail::host_array<uint64_t> prev_bits[4], prev_subaccum[4], prev_accum[4];
+};
+
+// Minimal "spiral file" writer: an uncompressed zip whose members are the reference's, in the
+// reference's creation order (modules/io/spiral_file.h:9-27, seqset.cpp:19-44).  file_info.json
+// carries a timestamp/uuid/command line in the reference, so whole-file identity is impossible
+// even between two reference runs; the parity contract is every other member byte for byte.
+class seqset_file_writer {
+ public:
+  explicit seqset_file_writer(const std::string& path) : m_f(fopen(path.c_str(), "wb")) {
+    if (!m_f) throw io_exception("cannot create " + path);
+  }
+  ~seqset_file_writer() { if (m_f) fclose(m_f); }
+  void add(const std::string& name, const void* data, uint64_t size) {
+    entry e;
+    e.name = name;
+    e.offset = (uint64_t)ftell(m_f);
+    e.size = size;
+    e.crc = crc32(data, size);
+    if (size >= 0xffffffffull || e.offset >= 0xffffffffull) throw io_exception("member too large for the plain zip writer");
+    put32(0x04034b50); put16(20); put16(0); put16(0); put16(0); put16(0);
+    put32(e.crc); put32((uint32_t)size); put32((uint32_t)size); put16((uint16_t)name.size()); put16(0);
+    fwrite(name.data(), 1, name.size(), m_f);
+    if (size) fwrite(data, 1, size, m_f);
+    m_entries.push_back(e);
+  }
+  void add(const std::string& name, const std::string& text) { add(name, text.data(), text.size()); }
+  void finish() {
+    uint64_t cd = (uint64_t)ftell(m_f);
+    for (const entry& e : m_entries) {
+      put32(0x02014b50); put16(20); put16(20); put16(0); put16(0); put16(0); put16(0);
+      put32(e.crc); put32((uint32_t)e.size); put32((uint32_t)e.size); put16((uint16_t)e.name.size());
+      put16(0); put16(0); put16(0); put16(0); put32(0); put32((uint32_t)e.offset);
+      fwrite(e.name.data(), 1, e.name.size(), m_f);
+    }
+    uint64_t end = (uint64_t)ftell(m_f);
+    put32(0x06054b50); put16(0); put16(0); put16((uint16_t)m_entries.size()); put16((uint16_t)m_entries.size());
+    put32((uint32_t)(end - cd)); put32((uint32_t)cd); put16(0);
+    fclose(m_f);
+    m_f = nullptr;
+  }
+
+ private:
+  struct entry { std::string name; uint64_t offset, size; uint32_t crc; };
+  static uint32_t crc32(const void* data, uint64_t n) {
+    static uint32_t table[256];
+    static bool init = false;
+    if (!init) {
+      for (uint32_t i = 0; i < 256; ++i) {
+        uint32_t c = i;
+        for (int k = 0; k < 8; ++k) c = (c & 1) ? 0xEDB88320u ^ (c >> 1) : (c >> 1);
+        table[i] = c;
+      }
+      init = true;
+    }
+    uint32_t c = 0xffffffffu;
+    const uint8_t* p = static_cast<const uint8_t*>(data);
+    for (uint64_t i = 0; i < n; ++i) c = table[(c ^ p[i]) & 0xff] ^ (c >> 8);
+    return c ^ 0xffffffffu;
+  }
+  void put16(uint16_t v) { fwrite(&v, 2, 1, m_f); }
+  void put32(uint32_t v) { fwrite(&v, 4, 1, m_f); }
+  FILE* m_f;
+  std::vector<entry> m_entries;
+};
+
+class builder {
+ public:
+  explicit builder(session& s) : m_s(s) {}
+  // builder::build_chunks (bs/builder.cpp:8-164): sizes, shared, prev bits of the "complete" pass
+  void build_chunks(const std::string& /*pass_name*/ = "complete", bool /*keep_tmp*/ = true,
+                    progress_handler_t progress = null_progress_handler) {
+    m_s.ensure_seqset_built();
+    progress(1.0);
+  }
+  // builder::make_seqset (bs/builder.cpp:207-263) + seqset::finalize: the tables in host memory
+  seqset_tables tables() {
+    seqset_tables t;
+    uint16_t *sizes = nullptr, *shared = nullptr;
+    uint64_t *pb[4], *ps[4], *pa[4];
+    detail::ck(bgx_export_seqset(m_s.ctx(), &t.num_entries, &t.max_entry_len, &sizes, &shared, pb, ps, pa, t.fixed));
+    bgx_free(sizes);
+    bgx_free(shared);
+    uint64_t lay[6];
+    detail::ck(bgx_seqset_layout(m_s.ctx(), lay));
+    for (int b = 0; b < 4; ++b) {
+      t.prev_bits[b].p = pb[b]; t.prev_bits[b].n = lay[3];
+      t.prev_subaccum[b].p = ps[b]; t.prev_subaccum[b].n = lay[4];
+      t.prev_accum[b].p = pa[b]; t.prev_accum[b].n = lay[5];
+    }
+    detail::ck(bgx_export_varbit(m_s.ctx(), 0, &t.sizes_elements.p, &t.sizes_elements.n, &t.sizes_bits, &t.sizes_max));
+    detail::ck(bgx_export_varbit(m_s.ctx(), 1, &t.shared_elements.p, &t.shared_elements.n, &t.shared_bits, &t.shared_max));
+    return t;
+  }
+  // writes the seqset spiral file; returns the tables it wrote
+  seqset_tables make_seqset(const std::string& path, progress_handler_t progress = null_progress_handler) {
+    seqset_tables t = tables();
+    seqset_file_writer w(path);
+    char ts[64];
+    time_t now = time(nullptr);
+    strftime(ts, sizeof(ts), "%a %b %e %H:%M:%S %Y", localtime(&now));
+    w.add("file_info.json", std::string("{\"build_host\":\"bgx\",\"build_is_clean\":true,\"build_revision\":\"") + bgx_version() +
+                                "\",\"build_timestamp\":0,\"build_timestamp_text\":\"\",\"build_user\":\"\",\"command_line\":[],"
+                                "\"create_timestamp\":" + std::to_string((long long)now) + ",\"create_timestamp_text\":\"" + ts +
+                                "\",\"uuid\":\"\"}");
+    w.add("part_info.json", part_info("seqset", 1, 1, 0));  // seqset::seqset_version 1.1.0 (seqset.cpp:12)
+    w.add("seqset.json", "{\"num_entries\":" + std::to_string(t.num_entries) + "}");
+    w.add("fixed", t.fixed, sizeof(t.fixed));
+    add_varbit(w, "entry_sizes", t.sizes_elements, t.sizes_bits, t.num_entries, t.sizes_max);
+    add_varbit(w, "shared", t.shared_elements, t.shared_bits, t.num_entries, t.shared_max);
+    for (int b = 0; b < 4; ++b) {
+      std::string dir = std::string("prev_") + "ACGT"[b] + "/";
+      w.add(dir + "part_info.json", part_info("bitcount", 1, 0, 0));  // bitcount.cpp:10
+      w.add(dir + "bitcount.json", "{\"nbits\":" + std::to_string(t.num_entries) + "}");
+      w.add(dir + "bits", t.prev_bits[b].p, t.prev_bits[b].n * 8);
+      w.add(dir + "subaccum", t.prev_subaccum[b].p, t.prev_subaccum[b].n * 8);
+      w.add(dir + "accum", t.prev_accum[b].p, t.prev_accum[b].n * 8);
+    }
+    w.finish();
+    progress(1.0);
+    return t;
+  }
+
+ private:
+  static std::string part_info(const char* type, int major, int minor, int patch) {
+    return std::string("{\"part_type\":\"") + type + "\",\"version\":{\"build\":\"\",\"major\":" + std::to_string(major) +
+           ",\"minor\":" + std::to_string(minor) + ",\"patch\":" + std::to_string(patch) + ",\"pre\":\"\"}}";
+  }
+  static void add_varbit(seqset_file_writer& w, const std::string& name, const detail::host_array<uint64_t>& el, uint32_t bits,
+                         uint64_t count, uint64_t max_value) {
+    w.add(name + "/part_info.json", part_info("packed_varbit_vector", 1, 0, 0));  // packed_varbit_vector.cpp:7
+    w.add(name + "/packed_varbit_vector.json", "{\"bits_per_value\":" + std::to_string(bits) + ",\"element_count\":" +
+                                                   std::to_string(count) + ",\"max_value\":" + std::to_string(max_value) + "}");
+    w.add(name + "/elements", el.p, el.n * 8);
+  }
+  session& m_s;
+};
+
+// seqset_for_reads (modules/bio_base/seqset_testutil.h:13): reads in, seqset file out, no
+// correction -- the simplest whole-stage-3 operator.  Returns the tables; writes `path` if given.
+inline seqset_tables seqset_for_reads(const std::vector<std::string>& reads, const std::string& path = "", int device = 0) {
+  count_kmer_options ko;
+  ko.device = device;
+  session s(ko);
+  {
+    kmer_counter kc(s);
+    kmer_counter::prob_pass_processor p(kc);
+    for (const std::string& r : reads) p.add(r);
+  }
+  detail::ck(bgx_seed_uncorrected(s.ctx()));
+  builder b(s);
+  b.build_chunks();
+  return path.empty() ? b.tables() : b.make_seqset(path);
+}
+
+}  // namespace bgx_bs

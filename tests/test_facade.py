@@ -1,0 +1,70 @@
+"""The C++ host façade (include/bgx_build_seqset.hpp): reference-named stage classes over the C ABI.
+
+CPU: the header and its test driver compile and link against libbgx.so.
+GPU: tests/cpp/facade_test runs the reference's builder_test known answers through
+seqset_for_reads, then the whole `biograph create` stage sequence on the reference's golden reads,
+and writes a seqset spiral file whose members are compared with the golden .bg and the oracle."""
+import json
+import os
+import subprocess
+import zipfile
+
+import numpy as np
+import pytest
+
+from oracle import oracle as O
+from tests import refseqset as RS
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+BIN = os.path.join(ROOT, "tests", "cpp", "facade_test")
+
+
+def build_facade_test():
+    src = os.path.join(ROOT, "tests", "cpp", "facade_test.cpp")
+    hdr = os.path.join(ROOT, "include", "bgx_build_seqset.hpp")
+    lib = os.path.join(ROOT, "biograph_b200", "libbgx.so")
+    assert os.path.exists(lib), "build libbgx.so first (python -c 'import __graft_entry__ as g; g.build()')"
+    if not os.path.exists(BIN) or os.path.getmtime(BIN) < max(os.path.getmtime(src), os.path.getmtime(hdr), os.path.getmtime(lib)):
+        subprocess.check_call(["g++", "-std=c++17", "-O2", "-Wall", "-I" + os.path.join(ROOT, "include"), src, "-o", BIN,
+                               "-L" + os.path.join(ROOT, "biograph_b200"), "-lbgx",
+                               "-Wl,-rpath," + os.path.join(ROOT, "biograph_b200")])
+    return BIN
+
+
+def test_facade_compiles_and_links():
+    assert os.path.exists(build_facade_test())
+
+
+@pytest.mark.gpu
+def test_facade_create_flow_on_golden(tmp_path, golden, golden_reads):
+    exe = build_facade_test()
+    reads_txt = tmp_path / "reads.txt"
+    reads_txt.write_text("\n".join(golden_reads) + "\n")
+    out = subprocess.run([exe, str(reads_txt), str(tmp_path)], capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0, out.stdout + out.stderr
+    lines = [json.loads(l) for l in out.stdout.splitlines() if l.startswith("{")]
+    for l in lines[:6]:
+        assert l["ok"] and l["entries"] == l["expected"]      # bs/builder_test.cpp:52-122
+    c = lines[-1]
+    # golden/e_coli_10000snp.bg/qc/create_log.txt (normative counts)
+    assert (c["reads"], c["kmers"], c["corrected_reads"], c["corrected_bases"], c["entries"], c["written_entries"]) == \
+        (10000, 7108, 8444, 288464, 19935, 19935)
+    z = zipfile.ZipFile(tmp_path / "seqset")
+    assert z.testzip() is None
+    names = z.namelist()
+    assert names[:4] == ["file_info.json", "part_info.json", "seqset.json", "fixed"]
+    assert json.loads(z.read("seqset.json")) == {"num_entries": 19935}
+    assert z.read("part_info.json") == b'{"part_type":"seqset","version":{"build":"","major":1,"minor":1,"patch":0,"pre":""}}'
+    assert z.read("fixed") == np.asarray(golden["fixed"], dtype="<u8").tobytes()
+    for b in "ACGT":
+        assert z.read(f"prev_{b}/bits") == np.asarray(golden[f"prev_{b}_bits"]).tobytes()
+        assert z.read(f"prev_{b}/subaccum") == np.asarray(golden[f"prev_{b}_subaccum"]).tobytes()
+        assert z.read(f"prev_{b}/accum") == np.asarray(golden[f"prev_{b}_accum"]).tobytes()
+        assert z.read(f"prev_{b}/bitcount.json") == b'{"nbits":19935}'
+    # the 2018 golden stores entry_sizes/shared as raw uint8; this commit's layout is a varbit part
+    for part, gold in (("entry_sizes", "entry_sizes"), ("shared", "shared")):
+        meta = json.loads(z.read(f"{part}/packed_varbit_vector.json"))
+        vals = RS.varbit_decode(z.read(f"{part}/elements"), meta["bits_per_value"], 19935)
+        assert np.array_equal(vals, np.asarray(golden[gold]).astype(np.uint16))
+        el, bits = O.varbit_pack(np.asarray(golden[gold]).astype(np.uint16), meta["max_value"])
+        assert bits == meta["bits_per_value"] and z.read(f"{part}/elements") == el.astype("<u8").tobytes()
