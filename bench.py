@@ -231,7 +231,7 @@ def main():
     if nmask is not None:
         pinned_mask = torch.empty(nmask.nbytes, dtype=torch.uint8).pin_memory()
         pinned_mask.numpy()[:] = nmask.view(np.uint8)
-    h2d = packed.nbytes + (nmask.nbytes if nmask is not None else 0) + woffs.nbytes // 2 + lens.nbytes
+    h2d = packed.nbytes + (nmask.nbytes if nmask is not None else 0) + lens.nbytes
     del packed
 
     g = B.Bgx(device=local)
@@ -246,9 +246,12 @@ def main():
         flush.zero_()
         torch.cuda.synchronize()
 
+    pinned_lens = torch.empty(lens.nbytes, dtype=torch.uint8).pin_memory()
+    pinned_lens.numpy()[:] = lens.view(np.uint8)
+
     def upload():
         g.add_reads_packed_ptr(pinned.data_ptr(), None if pinned_mask is None else pinned_mask.data_ptr(),
-                               woffs.ctypes.data, lens.ctypes.data, n_reads)
+                               None, pinned_lens.data_ptr(), n_reads)
 
     # ---- device-resident arm ----------------------------------------------------------------------
     upload()

@@ -7,6 +7,7 @@ import ctypes as C
 import json
 import os
 import subprocess
+import weakref
 
 import numpy as np
 
@@ -203,13 +204,14 @@ class Bgx:
             raise BgxError(self.L.bgx_last_error().decode())
 
     def _take(self, ptr, n, dtype):
+        """numpy view of a library-owned (pinned) host buffer; bgx_free runs when the last view dies"""
         n = int(n)
-        if n:
-            a = np.frombuffer((C.c_char * (n * np.dtype(dtype).itemsize)).from_address(ptr.value), dtype=dtype).copy()
-        else:
-            a = np.zeros(0, dtype=dtype)
-        self.L.bgx_free(ptr)
-        return a
+        if not n:
+            self.L.bgx_free(ptr)
+            return np.zeros(0, dtype=dtype)
+        buf = (C.c_char * (n * np.dtype(dtype).itemsize)).from_address(ptr.value)
+        weakref.finalize(buf, self.L.bgx_free, C.c_void_p(ptr.value))
+        return np.frombuffer(buf, dtype=dtype)
 
     # -- prob_pass_processor::add ------------------------------------------------------------
     def add_reads(self, reads):

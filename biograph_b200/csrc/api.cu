@@ -41,7 +41,7 @@ __global__ void corrected_ascii_kernel(const uint64_t* __restrict__ store, const
 
 template <typename T>
 T* to_host(const T* d, size_t n, cudaStream_t s) {
-  T* h = (T*)malloc(std::max<size_t>(n, 1) * sizeof(T));
+  T* h = (T*)host_alloc(std::max<size_t>(n, 1) * sizeof(T));
   if (n) BGX_CUDA(cudaMemcpyAsync(h, d, n * sizeof(T), cudaMemcpyDeviceToHost, s));
   return h;
 }
@@ -130,7 +130,7 @@ void bgx_destroy(bgx_ctx* x) {
   delete x;
 }
 
-void bgx_free(void* p) { free(p); }
+void bgx_free(void* p) { host_free(p); }
 
 #define CTX_GUARD(...)                          \
   if (!x) { g_last_error = "null context"; return 1; } \
@@ -183,7 +183,7 @@ int bgx_export_corrected(bgx_ctx* x, uint64_t* n_reads, uint16_t** lens, char** 
     for (uint64_t r = 0; r < n; ++r) off[r + 1] = off[r] + h_len[r];
     if (n_bases) *n_bases = off[n];
     if (bases) {
-      char* out = (char*)malloc(std::max<uint64_t>(off[n], 1));
+      char* out = (char*)host_alloc(std::max<uint64_t>(off[n], 1));
       DevBuf<uint64_t> d_off(n + 1, s);
       DevBuf<char> d_out(std::max<uint64_t>(off[n], 1), s);
       BGX_CUDA(cudaMemcpyAsync(d_off.p, off.data(), (n + 1) * 8, cudaMemcpyHostToDevice, s));
@@ -194,7 +194,7 @@ int bgx_export_corrected(bgx_ctx* x, uint64_t* n_reads, uint16_t** lens, char** 
       BGX_CUDA(cudaStreamSynchronize(s));
       *bases = out;
     }
-    if (lens) *lens = h_len; else free(h_len);
+    if (lens) *lens = h_len; else host_free(h_len);
   })
 }
 

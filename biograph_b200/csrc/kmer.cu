@@ -780,10 +780,10 @@ void export_kmers(Context* c, uint32_t min_count, uint64_t* n_out, uint64_t** km
   uint64_t n = h_cnt[1];
   *n_out = n;
   size_t na = std::max<uint64_t>(n, 1);
-  *kmers = (uint64_t*)malloc(na * 8);
-  *fwd = (uint32_t*)malloc(na * 4);
-  *rev = (uint32_t*)malloc(na * 4);
-  *flags = (uint8_t*)malloc(na);
+  *kmers = (uint64_t*)host_alloc(na * 8);
+  *fwd = (uint32_t*)host_alloc(na * 4);
+  *rev = (uint32_t*)host_alloc(na * 4);
+  *flags = (uint8_t*)host_alloc(na);
   if (n == 0) return;
   DevBuf<unsigned long long> ek(n, s), ec(n, s);
   BGX_CUDA(cudaMemsetAsync(counters.p, 0, 2 * sizeof(unsigned long long), s));

@@ -97,6 +97,74 @@ void dev_trim(cudaStream_t s) {
   a.trim_locked(s, false);
 }
 
+// ---- pinned host arena ------------------------------------------------------------------------------
+namespace {
+struct HostArena {
+  std::mutex mu;
+  std::multimap<size_t, void*> free_blocks;
+  std::unordered_map<void*, size_t> live;
+  size_t cached_bytes = 0;
+};
+HostArena& host_arena() {
+  static HostArena a;
+  return a;
+}
+constexpr size_t kHostCacheLimit = size_t(8) << 30;  // keep at most 8 GiB of idle pinned memory
+}  // namespace
+
+void* host_alloc(size_t bytes) {
+  HostArena& a = host_arena();
+  bytes = (std::max<size_t>(bytes, 1) + 4095) & ~(size_t)4095;
+  std::lock_guard<std::mutex> lk(a.mu);
+  auto it = a.free_blocks.find(bytes);
+  void* p = nullptr;
+  if (it != a.free_blocks.end()) {
+    p = it->second;
+    a.cached_bytes -= bytes;
+    a.free_blocks.erase(it);
+  } else {
+    if (cudaHostAlloc(&p, bytes, cudaHostAllocDefault) != cudaSuccess) {
+      cudaGetLastError();
+      for (auto& kv : a.free_blocks) cudaFreeHost(kv.second);
+      a.free_blocks.clear();
+      a.cached_bytes = 0;
+      if (cudaHostAlloc(&p, bytes, cudaHostAllocDefault) != cudaSuccess) {
+        cudaGetLastError();
+        throw Error("out of pinned host memory allocating " + std::to_string(bytes) + " bytes");
+      }
+    }
+  }
+  a.live[p] = bytes;
+  return p;
+}
+
+void host_free(void* p) {
+  if (!p) return;
+  HostArena& a = host_arena();
+  std::lock_guard<std::mutex> lk(a.mu);
+  auto it = a.live.find(p);
+  if (it == a.live.end()) {  // not ours (defensive): plain heap memory
+    free(p);
+    return;
+  }
+  size_t bytes = it->second;
+  a.live.erase(it);
+  if (a.cached_bytes + bytes > kHostCacheLimit) {
+    cudaFreeHost(p);
+  } else {
+    a.free_blocks.emplace(bytes, p);
+    a.cached_bytes += bytes;
+  }
+}
+
+void host_trim() {
+  HostArena& a = host_arena();
+  std::lock_guard<std::mutex> lk(a.mu);
+  for (auto& kv : a.free_blocks) cudaFreeHost(kv.second);
+  a.free_blocks.clear();
+  a.cached_bytes = 0;
+}
+
 size_t dev_peak_bytes(bool reset) {
   Arena& a = arena();
   std::lock_guard<std::mutex> lk(a.mu);

@@ -43,6 +43,12 @@ struct DevBuf {
   size_t bytes() const { return n * sizeof(T); }
 };
 
+// Host buffers handed to the caller (every bgx_export_* output): page-locked, so device-to-host
+// copies run at PCIe speed, and recycled by size like the device blocks.  bgx_free -> host_free.
+void* host_alloc(size_t bytes);
+void host_free(void* p);
+void host_trim();
+
 // out[i] = sum(in[0..i)), in place allowed.  If total_out != nullptr the grand total is written
 // there (device pointer).
 void exclusive_scan_u32(const uint32_t* in, uint32_t* out, size_t n, uint32_t* total_out, cudaStream_t s);

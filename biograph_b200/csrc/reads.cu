@@ -146,36 +146,89 @@ void reads_append_ascii(Context* c, const char* bases, const uint64_t* offs, uin
   finish_append(c, lens, woff, d_flag.p);
 }
 
+namespace {
+
+// lengths -> words per read + totals, on the device (no host loop over the reads)
+// tot: [0] words [1] bases [2] k-mer instances [3] max length [4] reads longer than 255
+__global__ void geometry_kernel(const uint16_t* __restrict__ lens, uint64_t n, int k, uint32_t* __restrict__ nwords,
+                                unsigned long long* __restrict__ tot) {
+  uint64_t r = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  unsigned L = r < n ? lens[r] : 0;
+  unsigned nw = (L + 31) >> 5;
+  if (r < n) nwords[r] = nw;
+  unsigned kin = L >= (unsigned)k ? L - k + 1 : 0;
+  unsigned sw = __reduce_add_sync(0xffffffffu, nw), sb = __reduce_add_sync(0xffffffffu, L),
+           sk = __reduce_add_sync(0xffffffffu, kin), mx = __reduce_max_sync(0xffffffffu, L),
+           bad = __reduce_add_sync(0xffffffffu, L > BGX_MAX_READ_LEN ? 1u : 0u);
+  if (lane_id() == 0) {
+    if (sw) atomicAdd(&tot[0], (unsigned long long)sw);
+    if (sb) atomicAdd(&tot[1], (unsigned long long)sb);
+    if (sk) atomicAdd(&tot[2], (unsigned long long)sk);
+    if (mx) atomicMax(&tot[3], (unsigned long long)mx);
+    if (bad) atomicAdd(&tot[4], (unsigned long long)bad);
+  }
+}
+
+__global__ void add_base_kernel(uint32_t* __restrict__ off, uint64_t n, uint32_t base) {
+  uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) off[i] += base;
+}
+
+}  // namespace
+
 void reads_append_packed(Context* c, const uint8_t* packed, const uint32_t* n_mask, const uint64_t* word_offs,
                          const uint16_t* lens_in, uint64_t n) {
   if (n == 0) return;
   cudaStream_t s = c->stream;
-  std::vector<uint16_t> lens(lens_in, lens_in + n);
-  for (uint64_t r = 0; r < n; ++r) {
-    BGX_CHECK(lens[r] <= BGX_MAX_READ_LEN, "read longer than 255 bases");
-    BGX_CHECK(word_offs[r + 1] - word_offs[r] == ((uint64_t)lens[r] + 31) / 32,
-              "bgx_add_reads_packed: reads must be densely word-packed");
-  }
-  std::vector<uint32_t> woff;
-  uint64_t words_before = c->n_words;
-  append_geometry(c, lens, &woff);
-  uint64_t new_words = woff[n] - words_before;
-  ensure_capacity(c, n, new_words);
+  const int k = c->opt.kmer_size;
+  // lengths go straight to the device; word offsets, totals and the length check are computed there
+  grow(c->word_off, c->n_reads + (c->n_reads ? 1 : 0), c->n_reads + n + 1, s);
+  grow(c->lens, c->n_reads, c->n_reads + n, s);
+  BGX_CUDA(cudaMemcpyAsync(c->lens.p + c->n_reads, lens_in, n * sizeof(uint16_t), cudaMemcpyHostToDevice, s));
+  DevBuf<uint32_t> nwords(n + 1, s);
+  DevBuf<unsigned long long> tot(5, s);
+  BGX_CUDA(cudaMemsetAsync(tot.p, 0, 5 * 8, s));
+  BGX_CUDA(cudaMemsetAsync(nwords.p + n, 0, 4, s));
+  KLAUNCH(geometry_kernel)<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(c->lens.p + c->n_reads, n, k, nwords.p, tot.p);
+  exclusive_scan_u32(nwords.p, c->word_off.p + c->n_reads, n + 1, nullptr, s);
+  unsigned long long h[5];
+  BGX_CUDA(cudaMemcpyAsync(h, tot.p, sizeof(h), cudaMemcpyDeviceToHost, s));
+  BGX_CUDA(cudaStreamSynchronize(s));
+  BGX_CHECK(h[4] == 0, "read longer than 255 bases");
+  const uint64_t new_words = h[0], words_before = c->n_words;
+  const uint64_t src_word0 = word_offs ? word_offs[0] : 0;
+  if (word_offs)
+    BGX_CHECK(word_offs[n] - word_offs[0] == new_words, "bgx_add_reads_packed: reads must be densely word-packed");
+  BGX_CHECK(words_before + new_words < (1ull << 32) - 2, "too many bases for one GPU shard (word offsets are 32-bit)");
+  if (words_before)
+    KLAUNCH(add_base_kernel)<<<(unsigned)((n + 1 + 255) / 256), 256, 0, s>>>(c->word_off.p + c->n_reads, n + 1, (uint32_t)words_before);
+  grow(c->words, words_before + (words_before ? 1 : 0), words_before + new_words + 1, s);
+  grow(c->nmask, words_before + (words_before ? 1 : 0), words_before + new_words + 1, s);
   DevBuf<int> d_flag(1, s);
   BGX_CUDA(cudaMemsetAsync(d_flag.p, 0, sizeof(int), s));
-  BGX_CUDA(cudaMemcpyAsync(c->words.p + words_before, packed + 8 * word_offs[0], new_words * 8,
-                           cudaMemcpyHostToDevice, s));
+  BGX_CUDA(cudaMemcpyAsync(c->words.p + words_before, packed + 8 * src_word0, new_words * 8, cudaMemcpyHostToDevice, s));
   if (new_words) KLAUNCH(bswap_words_kernel)<<<(unsigned)((new_words + 255) / 256), 256, 0, s>>>(c->words.p + words_before, new_words);
   if (n_mask) {
-    BGX_CUDA(cudaMemcpyAsync(c->nmask.p + words_before, n_mask + word_offs[0], new_words * 4,
-                             cudaMemcpyHostToDevice, s));
+    BGX_CUDA(cudaMemcpyAsync(c->nmask.p + words_before, n_mask + src_word0, new_words * 4, cudaMemcpyHostToDevice, s));
     if (new_words) KLAUNCH(any_nonzero_kernel)<<<(unsigned)((new_words + 255) / 256), 256, 0, s>>>(c->nmask.p + words_before, new_words, d_flag.p);
   } else {
     BGX_CUDA(cudaMemsetAsync(c->nmask.p + words_before, 0, new_words * 4, s));
   }
+  // zero the pad word that load_window may touch
+  BGX_CUDA(cudaMemsetAsync(c->words.p + words_before + new_words, 0, sizeof(uint64_t), s));
+  BGX_CUDA(cudaMemsetAsync(c->nmask.p + words_before + new_words, 0, sizeof(uint32_t), s));
   BGX_CUDA(cudaGetLastError());
-  c->add_stat("h2d_bytes", (double)new_words * (n_mask ? 12 : 8) + (double)(n + 1) * 4 + (double)n * 2);
-  finish_append(c, lens, woff, d_flag.p);
+  int flag = 0;
+  BGX_CUDA(cudaMemcpyAsync(&flag, d_flag.p, sizeof(int), cudaMemcpyDeviceToHost, s));
+  BGX_CUDA(cudaStreamSynchronize(s));
+  c->add_stat("h2d_bytes", (double)new_words * (n_mask ? 12 : 8) + (double)n * 2);
+  c->has_n = c->has_n || flag != 0;
+  c->n_reads += n;
+  c->n_words = words_before + new_words;
+  c->n_bases += h[1];
+  c->n_kmer_instances += h[2];
+  c->max_len = std::max<uint32_t>(c->max_len, (uint32_t)h[3]);
+  c->counted = c->corrected = c->built = false;
 }
 
 }  // namespace bgx

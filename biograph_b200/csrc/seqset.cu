@@ -1385,7 +1385,7 @@ void export_varbit(Context* c, int which, uint64_t** words, uint64_t* n_words, u
   if (nw)
     KLAUNCH(varbit_pack_kernel)<<<grid_for(nw, 256), 256, 0, s>>>(which == 0 ? c->sizes.p : c->shared.p, n, b, nw, d.p);
   BGX_CUDA(cudaGetLastError());
-  uint64_t* h = (uint64_t*)malloc(std::max<uint64_t>(nw, 1) * 8);
+  uint64_t* h = (uint64_t*)host_alloc(std::max<uint64_t>(nw, 1) * 8);
   if (nw) BGX_CUDA(cudaMemcpyAsync(h, d.p, nw * 8, cudaMemcpyDeviceToHost, s));
   BGX_CUDA(cudaStreamSynchronize(s));
   *words = h;
@@ -1405,10 +1405,10 @@ void export_entries_ascii(Context* c, uint64_t first, uint64_t count, char** bas
     BGX_CUDA(cudaMemcpyAsync(lens.data(), d_lens.p, count * 4, cudaMemcpyDeviceToHost, s));
     BGX_CUDA(cudaStreamSynchronize(s));
   }
-  uint64_t* offs = (uint64_t*)malloc((count + 1) * 8);
+  uint64_t* offs = (uint64_t*)host_alloc((count + 1) * 8);
   offs[0] = 0;
   for (uint64_t i = 0; i < count; ++i) offs[i + 1] = offs[i] + lens[i];
-  char* out = (char*)malloc(std::max<uint64_t>(offs[count], 1));
+  char* out = (char*)host_alloc(std::max<uint64_t>(offs[count], 1));
   if (count) {
     DevBuf<uint64_t> d_offs(count + 1, s);
     DevBuf<char> d_out(std::max<uint64_t>(offs[count], 1), s);

@@ -69,8 +69,11 @@ int bgx_add_reads_ascii(bgx_ctx* ctx, const char* bases, const uint64_t* offs, u
  *              occupies ceil(lens[r]/32) 8-byte words; unused trailing bits must be zero.
  *   n_mask   : optional (NULL = no N anywhere); one uint32 per 8-byte word of `packed`; bit
  *              (31 - j%32) set means base j of the read is 'N' (its 2-bit code must be 0).
- *   word_offs: n_reads+1 entries; word_offs[n_reads] = total words.
- * Pinned host memory makes the copy asynchronous; pageable memory works too. */
+ *   word_offs: n_reads+1 entries, word_offs[n_reads] = total words; or NULL for "read 0 starts at
+ *              word 0" (reads are always dense, so the offsets follow from lens; only the first
+ *              and last entry are looked at).
+ * Word offsets, base / k-mer totals and the length check are computed on the device: no host
+ * loop over the reads.  Pinned host memory makes the copies asynchronous; pageable works too. */
 int bgx_add_reads_packed(bgx_ctx* ctx, const uint8_t* packed, const uint32_t* n_mask,
                          const uint64_t* word_offs, const uint16_t* lens, uint64_t n_reads);
 
