@@ -4,9 +4,20 @@
 // (modules/bio_base/fast_read_correct.cpp:94-182, :16-90) and correct_reads::correct
 // (bs/correct_reads.cpp:154-231, kmer_starts_read :308-311).
 //
-// One thread per read.  The reference's recursive DFS is run iteratively with an explicit
-// frame stack; a partial result is (length, substitutions[<=16]) instead of a copied sequence,
-// because a corrected read is always the input with a few substituted bases, truncated.
+// Two kernels.
+//   probe_kernel  : one warp per read.  The lanes look up ALL k-mers of the read at once (32
+//                   independent probe sequences per step instead of one dependent chain), giving
+//                   the read's "solid mask" plus the two starts-read flag masks.  A read whose
+//                   k-mers are all solid is its own correction (fast_read_correct extends to the
+//                   end without a substitution): its store words, rc copy and seed counts are
+//                   written right here.  A read with no solid k-mer is dropped here.  The rest
+//                   go on the slow list with their solid mask.
+//   correct_kernel: one thread per slow read.  The reference's recursive DFS is run iteratively
+//                   with an explicit frame stack; a partial result is (length, substitutions[<=16])
+//                   instead of a copied sequence, because a corrected read is always the input
+//                   with a few substituted bases, truncated.  A k-mer window that no substitution
+//                   of the current path touches is answered from the solid mask, so only the
+//                   <= k windows after each tried substitution probe the set.
 // k-mer membership = one probe sequence in the 8-byte-slot solid hash set (L2 resident for
 // bacterial genomes, one DRAM sector per probe otherwise).
 #include <algorithm>
@@ -47,6 +58,13 @@ struct Params {
   uint64_t set_mask;
 };
 
+// solid mask of one read: bit (p & 31) of word (p >> 5) = the k-mer starting at read position p is
+// in the solid set (windows holding an 'N' are 0)
+struct SolidMask {
+  const uint32_t* bits;
+  __device__ __forceinline__ bool at(int p) const { return (bits[p >> 5] >> (p & 31)) & 1u; }
+};
+
 // logical view of a stretch of the read: forward from `origin`, or reverse-complemented
 // walking down from `origin`
 struct Input {
@@ -55,6 +73,8 @@ struct Input {
   int origin;
   int n;
   bool rev;
+  // read position of the first base of the k-mer formed by shifting in logical base i
+  __device__ __forceinline__ int kmer_pos(int i, int k) const { return rev ? origin - i : origin + i - k + 1; }
   __device__ __forceinline__ int get(int i) const {  // 0..3, 4 = 'N'
     int pos = rev ? origin - i : origin + i;
     if (m != nullptr && ((m[pos >> 5] >> (31 - (pos & 31))) & 1u)) return 4;
@@ -88,8 +108,11 @@ __device__ __forceinline__ uint64_t shift_in(uint64_t kmer, int b, uint64_t mask
 
 // correct_internal (fast_read_correct.cpp:16-90), iteratively.  Returns the result for the
 // whole input `in` starting from k-mer `kmer0`.
-__device__ void correct_internal(const Params& P, const Input& in, uint64_t kmer0, int min_run0, int budget0,
-                                 bool require_run_at_end, Frame* st, Res* out) {
+// A window is "fresh" when no substitution of the current DFS path lies inside it: its membership
+// is the probe kernel's mask bit.  The substitutions of the path are the frames' e (ascending),
+// so only the innermost one can be within k of the running position.
+__device__ void correct_internal(const Params& P, const Input& in, const SolidMask& sm, uint64_t kmer0, int min_run0,
+                                 int budget0, bool require_run_at_end, Frame* st, Res* out) {
   const uint64_t kmask = kmer_low_mask(P.k);
   int depth = 0;
   st[0].start = 0;
@@ -105,10 +128,11 @@ __device__ void correct_internal(const Params& P, const Input& in, uint64_t kmer
       int it = f.start, run = 0;
       uint64_t kmer = f.kmer;
       bool finished = false;
+      const int last_sub = depth ? st[depth - 1].e : -P.k;  // innermost substitution of the path
       int c = in.get(it);
       if (c != 4) {
         uint64_t nk = shift_in(kmer, c, kmask);
-        while (solid_has(P, nk)) {
+        while (it - last_sub >= P.k ? sm.at(in.kmer_pos(it, P.k)) : solid_has(P, nk)) {
           ++run;
           ++it;
           if (it == in.n) { finished = true; break; }
@@ -149,9 +173,10 @@ __device__ void correct_internal(const Params& P, const Input& in, uint64_t kmer
     {
       Frame& f = st[depth];
       bool pushed = false;
+      const int orig = in.get(f.e);  // the base the extension stopped on: already known not to extend
       while (f.b < 4) {
         uint64_t tk = shift_in(f.kmer, f.b, kmask);
-        if (!solid_has(P, tk)) { ++f.b; continue; }
+        if (f.b == orig || !solid_has(P, tk)) { ++f.b; continue; }
         if (f.e + 1 != in.n) {
           Frame& g = st[depth + 1];
           g.start = f.e + 1;
@@ -205,25 +230,160 @@ __device__ __forceinline__ uint64_t local_window(const uint64_t* w, int a) {
 
 __device__ __forceinline__ unsigned warp_sum(unsigned v) { return __reduce_add_sync(0xffffffffu, v); }
 
+// totals: [0] reads kept [1] bases kept [2] seeds [3] substitutions [4] reads truncated
+// Pass 1: one warp per read; see the file comment.  MAXIT = ceil(max k-mers per read / 32).
+constexpr int kProbeThreads = 256;
+template <int MAXIT, bool HAS_N>
+__global__ void __launch_bounds__(kProbeThreads) probe_kernel(const uint64_t* __restrict__ words,
+                                                              const uint32_t* __restrict__ nmask,
+                                                              const uint32_t* __restrict__ word_off,
+                                                              const uint16_t* __restrict__ lens, uint32_t n_reads, Params P,
+                                                              uint64_t* __restrict__ store, uint64_t rc_word_base,
+                                                              uint16_t* __restrict__ clen, uint8_t* __restrict__ ncorr,
+                                                              uint16_t* __restrict__ next_fwd, uint16_t* __restrict__ next_rev,
+                                                              unsigned long long* __restrict__ totals,
+                                                              uint32_t* __restrict__ slow_list,
+                                                              uint32_t* __restrict__ slow_mask /*[slot][MAXIT]*/,
+                                                              unsigned int* __restrict__ n_slow) {
+  const uint32_t r = (blockIdx.x * kProbeThreads + threadIdx.x) >> 5;
+  if (r >= n_reads) return;  // whole warps leave together
+  const unsigned lane = lane_id();
+  const int k = P.k;
+  const int L = lens[r];
+  const int nw = (L + 31) >> 5;
+  const uint32_t base = word_off[r];
+  const int nk = L >= k ? L - k + 1 : 0;
+  // lane i holds word i of the read (lane nw: the word after it; the store ends with a pad word)
+  const uint64_t wv = (int)lane <= nw ? words[base + lane] : 0;
+  uint32_t mv = 0;
+  if (HAS_N) mv = (int)lane <= nw ? nmask[base + lane] : 0;
+
+  // ---- all k-mers at once: first probes of every step issued back to back ----------------------
+  uint64_t canon[MAXIT], slot[MAXIT];
+  unsigned long long cur[MAXIT];
+  bool live[MAXIT], flip[MAXIT];
+#pragma unroll
+  for (int it = 0; it < MAXIT; ++it) {
+    const int p = it * 32 + (int)lane;
+    const uint64_t hi = __shfl_sync(0xffffffffu, wv, it), lo = __shfl_sync(0xffffffffu, wv, it + 1);
+    const unsigned s = lane * 2;
+    const uint64_t win = s ? ((hi << s) | (lo >> (64 - s))) : hi;
+    bool has_n = false;
+    if (HAS_N) {
+      const uint32_t mh = __shfl_sync(0xffffffffu, mv, it), ml = __shfl_sync(0xffffffffu, mv, it + 1);
+      const uint32_t mwin = lane ? ((mh << lane) | (ml >> (32 - lane))) : mh;
+      has_n = (mwin >> (32 - k)) != 0;
+    }
+    live[it] = p < nk && !has_n;
+    bool fl;
+    canon[it] = canonicalize(win >> (64 - 2 * k), k, fl);
+    flip[it] = fl;
+    slot[it] = mix64(canon[it]) & P.set_mask;
+    cur[it] = live[it] ? __ldg(&P.set[slot[it]]) : kEmptyKey;
+  }
+  uint32_t my_mask = 0;       // lane it keeps the solid mask word of step it
+  bool all_solid = nk > 0, any_solid = false;
+  int first_f = -1, last_g = -1;  // first p >= 1 whose k-mer starts a read (as seen), last p <= nk-2 (rc view)
+#pragma unroll
+  for (int it = 0; it < MAXIT; ++it) {
+    const int p = it * 32 + (int)lane;
+    unsigned long long e = cur[it];
+    if (live[it]) {
+      while (e != kEmptyKey && (e & kKmerMask) != canon[it]) {
+        slot[it] = (slot[it] + 1) & P.set_mask;
+        e = __ldg(&P.set[slot[it]]);
+      }
+    }
+    const bool found = live[it] && e != kEmptyKey;
+    const unsigned bm = __ballot_sync(0xffffffffu, found);
+    if ((int)lane == it) my_mask = bm;
+    const int in_range = min(32, max(0, nk - it * 32));
+    const unsigned want = in_range >= 32 ? 0xffffffffu : ((1u << in_range) - 1);
+    all_solid = all_solid && bm == want;
+    any_solid = any_solid || bm != 0;
+    // kmer_starts_read as the read sees it (bs/correct_reads.cpp:195-210, :308-311)
+    unsigned fm = __ballot_sync(0xffffffffu, found && (e & (flip[it] ? kRevFlag : kFwdFlag)) != 0 && p >= 1);
+    unsigned gm = __ballot_sync(0xffffffffu, found && (e & (flip[it] ? kFwdFlag : kRevFlag)) != 0 && p <= nk - 2);
+    if (first_f < 0 && fm) first_f = it * 32 + __ffs(fm) - 1;
+    if (gm) last_g = it * 32 + 31 - __clz(gm);
+  }
+
+  if (all_solid) {
+    // the read is its own correction: store it forward and reverse-complemented
+    if ((int)lane < nw) {
+      uint64_t v = wv;
+      const int rem = L - 32 * (int)lane;
+      if (rem < 32) v &= top_bases_mask(rem);
+      store[base + lane] = v;
+    }
+    {
+      // rc word q = revcomp of read[L - 32q - mcount, L - 32q)
+      const int q = (int)lane;
+      const int mcount = min(32, max(0, L - 32 * q));
+      const int lo_pos = max(0, L - 32 * q - mcount);
+      const uint64_t hi = __shfl_sync(0xffffffffu, wv, lo_pos >> 5), lo = __shfl_sync(0xffffffffu, wv, (lo_pos >> 5) + 1);
+      const unsigned s = (unsigned)(lo_pos & 31) * 2;
+      const uint64_t win = s ? ((hi << s) | (lo >> (64 - s))) : hi;
+      const int mc = max(mcount, 1);  // lanes past the read compute a dummy
+      if (q < nw) store[rc_word_base + base + q] = revcomp_kmer(win >> (64 - 2 * mc), mc) << (64 - 2 * mc);
+    }
+    if (lane == 0) {
+      const int nf = first_f >= 0 ? first_f : nk;
+      const int nr = last_g >= 0 ? nk - 1 - last_g : nk;
+      clen[r] = (uint16_t)L;
+      ncorr[r] = 0;
+      next_fwd[r] = (uint16_t)nf;
+      next_rev[r] = (uint16_t)nr;
+      atomicAdd(&totals[0], 1ULL);
+      atomicAdd(&totals[1], (unsigned long long)L);
+      atomicAdd(&totals[2], (unsigned long long)(nf + nr));
+    }
+  } else if (!any_solid) {
+    // shorter than k, or no solid k-mer to anchor on (fast_read_correct.cpp:108-123): dropped
+    if ((int)lane < nw) {
+      store[base + lane] = 0;
+      store[rc_word_base + base + lane] = 0;
+    }
+    if (lane == 0) {
+      clen[r] = 0;
+      ncorr[r] = 0;
+      next_fwd[r] = 0;
+      next_rev[r] = 0;
+    }
+  } else {
+    unsigned idx = 0;
+    if (lane == 0) idx = atomicAdd(n_slow, 1u);
+    idx = __shfl_sync(0xffffffffu, idx, 0);
+    if (lane == 0) slow_list[idx] = r;
+    if ((int)lane < MAXIT) slow_mask[(size_t)idx * MAXIT + lane] = my_mask;
+  }
+}
+
+// Pass 2: one thread per read on the slow list.
 __global__ void __launch_bounds__(128) correct_kernel(const uint64_t* __restrict__ words,
                                                       const uint32_t* __restrict__ nmask,
                                                       const uint32_t* __restrict__ word_off,
-                                                      const uint16_t* __restrict__ lens, uint32_t n_reads, Params P,
+                                                      const uint16_t* __restrict__ lens, Params P,
+                                                      const uint32_t* __restrict__ slow_list,
+                                                      const uint32_t* __restrict__ slow_mask, int mask_words,
+                                                      const unsigned int* __restrict__ n_slow_p,
                                                       uint64_t* __restrict__ store, uint64_t rc_word_base,
                                                       uint16_t* __restrict__ clen, uint8_t* __restrict__ ncorr,
                                                       uint16_t* __restrict__ next_fwd, uint16_t* __restrict__ next_rev,
-                                                      uint32_t* __restrict__ seed_cnt,
                                                       unsigned long long* __restrict__ totals) {
-  const uint32_t r = blockIdx.x * blockDim.x + threadIdx.x;
+  const uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
+  const uint32_t n_slow = *n_slow_p;
+  const bool active = j < n_slow;
+  const uint32_t r = active ? slow_list[j] : 0;
   uint64_t w[kMaxWords];
   uint32_t m[kMaxWords];
+  uint32_t smw[kMaxWords - 1];
   Frame st[kMaxCorr + 1];
   int out_len = 0, corrections = 0, nf = 0, nr = 0;
   const int k = P.k;
-  const uint64_t kmask = kmer_low_mask(k);
   int L = 0, nw = 0;
   uint32_t base = 0;
-  if (r < n_reads) {
+  if (active) {
     L = lens[r];
     nw = (L + 31) >> 5;
     base = word_off[r];
@@ -232,29 +392,23 @@ __global__ void __launch_bounds__(128) correct_kernel(const uint64_t* __restrict
       w[i] = i < nw ? words[base + i] : 0;
       m[i] = (nmask != nullptr && i < nw) ? nmask[base + i] : 0;
     }
+#pragma unroll
+    for (int i = 0; i < kMaxWords - 1; ++i) smw[i] = i < mask_words ? slow_mask[(size_t)j * mask_words + i] : 0;
   }
-  bool ok = r < n_reads && L >= k;
+  const SolidMask sm{smw};
+  bool ok = active;  // on the list: L >= k and at least one solid k-mer
   if (ok) {
-    Input whole{w, nmask ? m : nullptr, 0, L, false};
-    // scan right to the first solid k-mer (fast_read_correct.cpp:108-123)
-    int it = 0, left = k;
-    uint64_t kmer = 0;
-    for (;;) {
-      if (!left && solid_has(P, kmer)) break;
-      if (it == L) { ok = false; break; }
-      int c = whole.get(it);
-      ++it;
-      if (c == 4) { left = k; continue; }
-      kmer = shift_in(kmer, c, kmask);
-      if (left) --left;
-    }
+    // the first solid k-mer (fast_read_correct.cpp:108-123): lowest set mask bit
+    int kmer_start = 0;
+    while (!sm.at(kmer_start)) ++kmer_start;
+    const int it = kmer_start + k;
+    const uint64_t kmer = local_window(w, kmer_start) >> (64 - 2 * k);
     int budget = P.max_corr;
-    if (ok && it != k) {
+    if (kmer_start != 0) {
       // left side: correct the reverse complement of read[0, kmer_start) (:135-167)
-      int kmer_start = it - k;
       Input lin{w, nmask ? m : nullptr, kmer_start - 1, kmer_start, true};
       Res lres;
-      correct_internal(P, lin, revcomp_kmer(kmer, k), 0, budget, false, st, &lres);
+      correct_internal(P, lin, sm, revcomp_kmer(kmer, k), 0, budget, false, st, &lres);
       if (lres.len != kmer_start) {
         ok = false;  // left correction failed (:150-153)
       } else {
@@ -272,7 +426,7 @@ __global__ void __launch_bounds__(128) correct_kernel(const uint64_t* __restrict
       if (it != L) {
         Input rin{w, nmask ? m : nullptr, it, L - it, false};
         Res rres;
-        correct_internal(P, rin, kmer, 0, budget, true, st, &rres);
+        correct_internal(P, rin, sm, kmer, 0, budget, true, st, &rres);
         for (int i = 0; i < rres.ncorr; ++i) set_base(w, it + rres.pos[i], rres.base[i]);
         corrections += rres.ncorr;
         out_len = it + rres.len;
@@ -282,7 +436,7 @@ __global__ void __launch_bounds__(128) correct_kernel(const uint64_t* __restrict
       if ((unsigned)out_len < needed) ok = false;
     }
   }
-  if (r < n_reads) {
+  if (active) {
     if (!ok) { out_len = 0; corrections = 0; }
     // truncate and store forward + reverse-complement copies
     int nwc = (out_len + 31) >> 5;
@@ -335,7 +489,6 @@ __global__ void __launch_bounds__(128) correct_kernel(const uint64_t* __restrict
     ncorr[r] = (uint8_t)corrections;
     next_fwd[r] = (uint16_t)nf;
     next_rev[r] = (uint16_t)nr;
-    seed_cnt[r] = (uint32_t)(nf + nr);
   }
   unsigned kept = warp_sum(ok ? 1u : 0u);
   unsigned kb = warp_sum((unsigned)out_len);
@@ -433,7 +586,6 @@ void stage_correct(Context* c) {
   c->ncorr.alloc(n, s);
   c->next_fwd.alloc(n, s);
   c->next_rev.alloc(n, s);
-  DevBuf<uint32_t> seed_cnt(n, s);
   DevBuf<unsigned long long> totals(5, s);
   BGX_CUDA(cudaMemsetAsync(totals.p, 0, 5 * sizeof(unsigned long long), s));
   BGX_CUDA(cudaMemsetAsync(c->store.p + 2 * c->n_words, 0, sizeof(uint64_t), s));
@@ -444,15 +596,45 @@ void stage_correct(Context* c) {
   P.trim = (double)c->opt.trim_after_portion;  // float widened to double (biograph_create.cpp:489-490,731)
   P.set = c->solid.p;
   P.set_mask = c->solid_slots - 1;
+  const int max_kmers = std::max<int>((int)c->max_len - P.k + 1, 1);
+  const int mask_words = max_kmers <= 128 ? 4 : 8;
+  BGX_CHECK(max_kmers <= 256, "read longer than 255 bases");
+  DevBuf<uint32_t> slow_list(n, s), slow_mask((size_t)n * mask_words, s);
+  DevBuf<unsigned int> n_slow(1, s);
+  BGX_CUDA(cudaMemsetAsync(n_slow.p, 0, sizeof(unsigned int), s));
+  unsigned int h_slow = 0;
   {
-    ScopedStage st(c, "correct_kernel");
-    KLAUNCH(correct_kernel)<<<(unsigned)((n + 127) / 128), 128, 0, s>>>(c->words.p, c->has_n ? c->nmask.p : nullptr,
-                                                              c->word_off.p, c->lens.p, (uint32_t)n, P, c->store.p,
-                                                              c->n_words, c->clen.p, c->ncorr.p, c->next_fwd.p,
-                                                              c->next_rev.p, seed_cnt.p, totals.p);
+    ScopedStage st(c, "correct_probe");
+    const unsigned grid = (unsigned)((n * 32 + kProbeThreads - 1) / kProbeThreads);
+    const uint32_t* nm = c->has_n ? c->nmask.p : nullptr;
+#define BGX_PROBE(MAXIT, HASN)                                                                                          \
+  note_launch();                                                                                                        \
+  probe_kernel<MAXIT, HASN><<<grid, kProbeThreads, 0, s>>>(c->words.p, nm, c->word_off.p, c->lens.p, (uint32_t)n, P, \
+                                                                     c->store.p, c->n_words, c->clen.p, c->ncorr.p,   \
+                                                                     c->next_fwd.p, c->next_rev.p, totals.p,          \
+                                                                     slow_list.p, slow_mask.p, n_slow.p)
+    if (mask_words == 4 && c->has_n) { BGX_PROBE(4, true); }
+    else if (mask_words == 4) { BGX_PROBE(4, false); }
+    else if (c->has_n) { BGX_PROBE(8, true); }
+    else { BGX_PROBE(8, false); }
+#undef BGX_PROBE
     BGX_CUDA(cudaGetLastError());
     st.stop();
   }
+  {
+    ScopedStage st(c, "correct_kernel");
+    // sized for the worst case (every read slow); threads past the device-side count leave at once
+    BGX_CUDA(cudaMemcpyAsync(&h_slow, n_slow.p, sizeof(h_slow), cudaMemcpyDeviceToHost, s));
+    BGX_CUDA(cudaStreamSynchronize(s));
+    if (h_slow)
+      KLAUNCH(correct_kernel)<<<(h_slow + 127) / 128, 128, 0, s>>>(c->words.p, c->has_n ? c->nmask.p : nullptr, c->word_off.p,
+                                                                   c->lens.p, P, slow_list.p, slow_mask.p, mask_words, n_slow.p,
+                                                                   c->store.p, c->n_words, c->clen.p, c->ncorr.p,
+                                                                   c->next_fwd.p, c->next_rev.p, totals.p);
+    BGX_CUDA(cudaGetLastError());
+    st.stop();
+  }
+  c->set_stat("reads_slow_path", (double)h_slow);
   unsigned long long h[5];
   BGX_CUDA(cudaMemcpyAsync(h, totals.p, sizeof(h), cudaMemcpyDeviceToHost, s));
   BGX_CUDA(cudaStreamSynchronize(s));

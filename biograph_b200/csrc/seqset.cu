@@ -29,6 +29,7 @@ namespace bgx {
 namespace {
 
 constexpr int kSmallGroup = 32;   // tie groups up to this size are sorted by one thread
+constexpr int kMediumGroup = 512; // ... up to this size by one warp (rank sort); larger ones are refined chunk by chunk
 constexpr int kChunkBases = 12;   // bases resolved per refinement round for big tie groups
 
 // ---- comparisons ----------------------------------------------------------------------------
@@ -60,6 +61,15 @@ __device__ __forceinline__ bool rec_less(const uint64_t* __restrict__ store, uin
   int na = (int)loc_len(la), nb = (int)loc_len(lb);
   if (na <= 32 || nb <= 32) return na < nb;  // equal padded keys: the shorter one is a prefix
   return compare_from(store, la, lb, 32, nullptr) < 0;
+}
+
+// three-way order of two records (<0, 0, >0); 0 = the same sequence
+__device__ __forceinline__ int rec_cmp(const uint64_t* __restrict__ store, uint64_t ka, uint64_t la, uint64_t kb,
+                                       uint64_t lb) {
+  if (ka != kb) return ka < kb ? -1 : 1;
+  int na = (int)loc_len(la), nb = (int)loc_len(lb);
+  if (na <= 32 || nb <= 32) return na - nb;
+  return compare_from(store, la, lb, 32, nullptr);
 }
 
 // a prefix of / equal to b ?
@@ -166,6 +176,67 @@ __global__ void refine_init_kernel(const uint32_t* __restrict__ big_flag, const 
   const int sh = 64 - sbits;
   bool is_head = (i == 0) || !big_flag[i - 1] || (keys[i - 1] >> sh) != (keys[i] >> sh);
   head[j] = is_head ? 1u : 0u;
+}
+
+// Medium tie groups: one warp per member, only the warp of a group's head works.  It measures
+// the group (members are contiguous in the array), and if it has at most `limit` records sorts it
+// by rank: every record counts the records that order before it (ties by position, so the result
+// is stable), is written to its rank in the alt buffers and copied back.  Larger groups are
+// left for the refinement rounds: tied = 1 on all their members.
+__global__ void __launch_bounds__(128) tie_medium_kernel(const uint64_t* __restrict__ store, uint64_t* __restrict__ keys,
+                                                         uint64_t* __restrict__ locs, uint64_t* __restrict__ keys_alt,
+                                                         uint64_t* __restrict__ locs_alt,
+                                                         const uint32_t* __restrict__ midx,
+                                                         const uint32_t* __restrict__ head, uint32_t m, int limit,
+                                                         uint32_t* __restrict__ tied, uint32_t* __restrict__ new_head) {
+  const uint32_t j = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  if (j >= m || !head[j]) return;
+  const unsigned lane = lane_id();
+  // group size, measured up to limit + 1
+  uint32_t g = 1;
+  for (;;) {
+    const uint32_t q = j + g + lane;
+    const bool stop = q >= m || head[q] != 0;
+    const unsigned sm = __ballot_sync(0xffffffffu, stop);
+    if (sm) { g += __ffs(sm) - 1; break; }
+    g += 32;
+    if (g > (uint32_t)limit) break;
+  }
+  if (g > (uint32_t)limit) {
+    // the whole group (however long) goes to the refinement path: every member marks itself
+    // through its head's warp in strides, the head flag stays
+    uint32_t q = j;
+    for (;;) {
+      const uint32_t t = q + lane;
+      const bool in = t < m && (t == j || head[t] == 0);
+      const unsigned im = __ballot_sync(0xffffffffu, in);
+      // members are the leading run of lanes that are still inside the group
+      const unsigned run = im == 0xffffffffu ? 32 : (unsigned)__ffs(~im) - 1;
+      if (lane < run) { tied[t] = 1u; new_head[t] = t == j ? 1u : 0u; }
+      if (run < 32) break;
+      q += 32;
+    }
+    return;
+  }
+  const uint32_t pos0 = midx[j];
+  for (uint32_t e = lane; e < g; e += 32) {
+    const uint64_t ke = keys[pos0 + e], le = locs[pos0 + e];
+    uint32_t rank = 0;
+    for (uint32_t f = 0; f < g; ++f) {
+      if (f == e) continue;
+      const int cmp = rec_cmp(store, keys[pos0 + f], locs[pos0 + f], ke, le);
+      rank += (cmp < 0 || (cmp == 0 && f < e)) ? 1u : 0u;
+    }
+    keys_alt[pos0 + rank] = ke;
+    locs_alt[pos0 + rank] = le;
+    tied[j + e] = 0u;
+    new_head[j + e] = 0u;
+  }
+  __syncwarp();
+  for (uint32_t e = lane; e < g; e += 32) {
+    keys[pos0 + e] = keys_alt[pos0 + e];
+    locs[pos0 + e] = locs_alt[pos0 + e];
+  }
 }
 
 __global__ void refine_key_kernel(const uint64_t* __restrict__ store, const uint64_t* __restrict__ locs,
@@ -736,6 +807,25 @@ void sort_records(Context* c, DevBuf<uint64_t>& keys, DevBuf<uint64_t>& locs, De
     exclusive_scan_u32(big_flag.p, big_pos.p, n, nullptr, s);
     DevBuf<uint32_t> midx(m, s), head(m, s);
     KLAUNCH(refine_init_kernel)<<<grid_for(n, 256), 256, 0, s>>>(big_flag.p, big_pos.p, keys.p, n, sbits, midx.p, head.p);
+    {
+      // medium groups are finished by one warp each; what is left goes through the refinement rounds
+      int medium_limit = kMediumGroup;
+      if (const char* e = getenv("BGX_MEDIUM_GROUP")) medium_limit = std::max(0, atoi(e));  // test hook (0: refinement only)
+      DevBuf<uint32_t> tied(m, s), nhead(m, s), tpos(m, s), tot(1, s);
+      KLAUNCH(tie_medium_kernel)<<<grid_for((uint64_t)m * 32, 128), 128, 0, s>>>(c->seq_store(), keys.p, locs.p, keys_alt.p, locs_alt.p,
+                                                                        midx.p, head.p, m, medium_limit, tied.p, nhead.p);
+      exclusive_scan_u32(tied.p, tpos.p, m, tot.p, s);
+      BGX_CUDA(cudaGetLastError());
+      uint32_t m2 = read_u32(tot.p, s);
+      if (m2 != m) {
+        DevBuf<uint32_t> midx2(std::max<uint32_t>(m2, 1), s), head2(std::max<uint32_t>(m2, 1), s);
+        if (m2) KLAUNCH(refine_compact_kernel)<<<grid_for(m, 256), 256, 0, s>>>(tied.p, tpos.p, midx.p, nhead.p, m, midx2.p, head2.p);
+        midx = std::move(midx2);
+        head = std::move(head2);
+      }
+      c->add_stat("tie_refined_records_" + tag, m2);
+      m = m2;
+    }
     int D = sbits / 2;
     int rounds = 0;
     while (m) {
