@@ -5,7 +5,7 @@
 // (bs/correct_reads.cpp:154-231, kmer_starts_read :308-311).
 //
 // Two kernels.
-//   probe_kernel  : one warp per read.  The lanes look up ALL k-mers of the read at once (32
+//   probe_kernel  : a warp per read (4 reads in turn).  The lanes look up ALL k-mers of the read at once (32
 //                   independent probe sequences per step instead of one dependent chain), giving
 //                   the read's "solid mask" plus the two starts-read flag masks.  A read whose
 //                   k-mers are all solid is its own correction (fast_read_correct extends to the
@@ -231,8 +231,12 @@ __device__ __forceinline__ uint64_t local_window(const uint64_t* w, int a) {
 __device__ __forceinline__ unsigned warp_sum(unsigned v) { return __reduce_add_sync(0xffffffffu, v); }
 
 // totals: [0] reads kept [1] bases kept [2] seeds [3] substitutions [4] reads truncated
-// Pass 1: one warp per read; see the file comment.  MAXIT = ceil(max k-mers per read / 32).
+// Pass 1: a warp takes kProbeRPW reads, one at a time; see the file comment.
+// MAXIT = ceil(max k-mers per read / 32).  Counters are summed per block (the totals and the
+// slow-list cursor would otherwise be one same-address atomic per read).
 constexpr int kProbeThreads = 256;
+constexpr int kProbeWarps = kProbeThreads / 32;
+constexpr int kProbeRPW = 4;
 template <int MAXIT, bool HAS_N>
 __global__ void __launch_bounds__(kProbeThreads) probe_kernel(const uint64_t* __restrict__ words,
                                                               const uint32_t* __restrict__ nmask,
@@ -245,117 +249,152 @@ __global__ void __launch_bounds__(kProbeThreads) probe_kernel(const uint64_t* __
                                                               uint32_t* __restrict__ slow_list,
                                                               uint32_t* __restrict__ slow_mask /*[slot][MAXIT]*/,
                                                               unsigned int* __restrict__ n_slow) {
-  const uint32_t r = (blockIdx.x * kProbeThreads + threadIdx.x) >> 5;
-  if (r >= n_reads) return;  // whole warps leave together
-  const unsigned lane = lane_id();
+  __shared__ unsigned int blk_kept, blk_bases, blk_seeds, blk_slow, blk_slow_base;
+  if (threadIdx.x == 0) blk_kept = blk_bases = blk_seeds = blk_slow = 0;
+  __syncthreads();
+  const unsigned lane = lane_id(), warp = threadIdx.x >> 5;
   const int k = P.k;
-  const int L = lens[r];
-  const int nw = (L + 31) >> 5;
-  const uint32_t base = word_off[r];
-  const int nk = L >= k ? L - k + 1 : 0;
-  // lane i holds word i of the read (lane nw: the word after it; the store ends with a pad word)
-  const uint64_t wv = (int)lane <= nw ? words[base + lane] : 0;
-  uint32_t mv = 0;
-  if (HAS_N) mv = (int)lane <= nw ? nmask[base + lane] : 0;
+  uint32_t slow_r[kProbeRPW], slow_m[kProbeRPW], slow_i[kProbeRPW];  // slow reads of this warp: read, my mask word, block-local slot
+  int n_my_slow = 0;
+  unsigned w_kept = 0, w_bases = 0, w_seeds = 0;  // lane 0 only
 
-  // ---- all k-mers at once: first probes of every step issued back to back ----------------------
-  uint64_t canon[MAXIT], slot[MAXIT];
-  unsigned long long cur[MAXIT];
-  bool live[MAXIT], flip[MAXIT];
-#pragma unroll
-  for (int it = 0; it < MAXIT; ++it) {
-    const int p = it * 32 + (int)lane;
-    const uint64_t hi = __shfl_sync(0xffffffffu, wv, it), lo = __shfl_sync(0xffffffffu, wv, it + 1);
-    const unsigned s = lane * 2;
-    const uint64_t win = s ? ((hi << s) | (lo >> (64 - s))) : hi;
-    bool has_n = false;
-    if (HAS_N) {
-      const uint32_t mh = __shfl_sync(0xffffffffu, mv, it), ml = __shfl_sync(0xffffffffu, mv, it + 1);
-      const uint32_t mwin = lane ? ((mh << lane) | (ml >> (32 - lane))) : mh;
-      has_n = (mwin >> (32 - k)) != 0;
-    }
-    live[it] = p < nk && !has_n;
-    bool fl;
-    canon[it] = canonicalize(win >> (64 - 2 * k), k, fl);
-    flip[it] = fl;
-    slot[it] = mix64(canon[it]) & P.set_mask;
-    cur[it] = live[it] ? __ldg(&P.set[slot[it]]) : kEmptyKey;
-  }
-  uint32_t my_mask = 0;       // lane it keeps the solid mask word of step it
-  bool all_solid = nk > 0, any_solid = false;
-  int first_f = -1, last_g = -1;  // first p >= 1 whose k-mer starts a read (as seen), last p <= nk-2 (rc view)
-#pragma unroll
-  for (int it = 0; it < MAXIT; ++it) {
-    const int p = it * 32 + (int)lane;
-    unsigned long long e = cur[it];
-    if (live[it]) {
-      while (e != kEmptyKey && (e & kKmerMask) != canon[it]) {
-        slot[it] = (slot[it] + 1) & P.set_mask;
-        e = __ldg(&P.set[slot[it]]);
-      }
-    }
-    const bool found = live[it] && e != kEmptyKey;
-    const unsigned bm = __ballot_sync(0xffffffffu, found);
-    if ((int)lane == it) my_mask = bm;
-    const int in_range = min(32, max(0, nk - it * 32));
-    const unsigned want = in_range >= 32 ? 0xffffffffu : ((1u << in_range) - 1);
-    all_solid = all_solid && bm == want;
-    any_solid = any_solid || bm != 0;
-    // kmer_starts_read as the read sees it (bs/correct_reads.cpp:195-210, :308-311)
-    unsigned fm = __ballot_sync(0xffffffffu, found && (e & (flip[it] ? kRevFlag : kFwdFlag)) != 0 && p >= 1);
-    unsigned gm = __ballot_sync(0xffffffffu, found && (e & (flip[it] ? kFwdFlag : kRevFlag)) != 0 && p <= nk - 2);
-    if (first_f < 0 && fm) first_f = it * 32 + __ffs(fm) - 1;
-    if (gm) last_g = it * 32 + 31 - __clz(gm);
-  }
+#pragma unroll 1
+  for (int q = 0; q < kProbeRPW; ++q) {
+    const uint32_t r = (blockIdx.x * kProbeWarps + warp) * kProbeRPW + q;
+    if (r >= n_reads) break;  // warp-uniform
+    const int L = lens[r];
+    const int nw = (L + 31) >> 5;
+    const uint32_t base = word_off[r];
+    const int nk = L >= k ? L - k + 1 : 0;
+    // lane i holds word i of the read (lane nw: the word after it; the store ends with a pad word)
+    const uint64_t wv = (int)lane <= nw ? words[base + lane] : 0;
+    uint32_t mv = 0;
+    if (HAS_N) mv = (int)lane <= nw ? nmask[base + lane] : 0;
 
-  if (all_solid) {
-    // the read is its own correction: store it forward and reverse-complemented
-    if ((int)lane < nw) {
-      uint64_t v = wv;
-      const int rem = L - 32 * (int)lane;
-      if (rem < 32) v &= top_bases_mask(rem);
-      store[base + lane] = v;
-    }
-    {
-      // rc word q = revcomp of read[L - 32q - mcount, L - 32q)
-      const int q = (int)lane;
-      const int mcount = min(32, max(0, L - 32 * q));
-      const int lo_pos = max(0, L - 32 * q - mcount);
-      const uint64_t hi = __shfl_sync(0xffffffffu, wv, lo_pos >> 5), lo = __shfl_sync(0xffffffffu, wv, (lo_pos >> 5) + 1);
-      const unsigned s = (unsigned)(lo_pos & 31) * 2;
+    // ---- all k-mers at once: first probes of every step issued back to back ----------------------
+    uint64_t canon[MAXIT], slot[MAXIT];
+    unsigned long long cur[MAXIT];
+    bool live[MAXIT], flip[MAXIT];
+#pragma unroll
+    for (int it = 0; it < MAXIT; ++it) {
+      const int p = it * 32 + (int)lane;
+      const uint64_t hi = __shfl_sync(0xffffffffu, wv, it), lo = __shfl_sync(0xffffffffu, wv, it + 1);
+      const unsigned s = lane * 2;
       const uint64_t win = s ? ((hi << s) | (lo >> (64 - s))) : hi;
-      const int mc = max(mcount, 1);  // lanes past the read compute a dummy
-      if (q < nw) store[rc_word_base + base + q] = revcomp_kmer(win >> (64 - 2 * mc), mc) << (64 - 2 * mc);
+      bool has_n = false;
+      if (HAS_N) {
+        const uint32_t mh = __shfl_sync(0xffffffffu, mv, it), ml = __shfl_sync(0xffffffffu, mv, it + 1);
+        const uint32_t mwin = lane ? ((mh << lane) | (ml >> (32 - lane))) : mh;
+        has_n = (mwin >> (32 - k)) != 0;
+      }
+      live[it] = p < nk && !has_n;
+      bool fl;
+      canon[it] = canonicalize(win >> (64 - 2 * k), k, fl);
+      flip[it] = fl;
+      slot[it] = mix64(canon[it]) & P.set_mask;
+      cur[it] = live[it] ? __ldg(&P.set[slot[it]]) : kEmptyKey;
     }
-    if (lane == 0) {
-      const int nf = first_f >= 0 ? first_f : nk;
-      const int nr = last_g >= 0 ? nk - 1 - last_g : nk;
-      clen[r] = (uint16_t)L;
-      ncorr[r] = 0;
-      next_fwd[r] = (uint16_t)nf;
-      next_rev[r] = (uint16_t)nr;
-      atomicAdd(&totals[0], 1ULL);
-      atomicAdd(&totals[1], (unsigned long long)L);
-      atomicAdd(&totals[2], (unsigned long long)(nf + nr));
+    uint32_t my_mask = 0;       // lane it keeps the solid mask word of step it
+    bool all_solid = nk > 0, any_solid = false;
+    int first_f = -1, last_g = -1;  // first p >= 1 whose k-mer starts a read (as seen), last p <= nk-2 (rc view)
+#pragma unroll
+    for (int it = 0; it < MAXIT; ++it) {
+      const int p = it * 32 + (int)lane;
+      unsigned long long e = cur[it];
+      if (live[it]) {
+        while (e != kEmptyKey && (e & kKmerMask) != canon[it]) {
+          slot[it] = (slot[it] + 1) & P.set_mask;
+          e = __ldg(&P.set[slot[it]]);
+        }
+      }
+      const bool found = live[it] && e != kEmptyKey;
+      const unsigned bm = __ballot_sync(0xffffffffu, found);
+      if ((int)lane == it) my_mask = bm;
+      const int in_range = min(32, max(0, nk - it * 32));
+      const unsigned want = in_range >= 32 ? 0xffffffffu : ((1u << in_range) - 1);
+      all_solid = all_solid && bm == want;
+      any_solid = any_solid || bm != 0;
+      // kmer_starts_read as the read sees it (bs/correct_reads.cpp:195-210, :308-311)
+      unsigned fm = __ballot_sync(0xffffffffu, found && (e & (flip[it] ? kRevFlag : kFwdFlag)) != 0 && p >= 1);
+      unsigned gm = __ballot_sync(0xffffffffu, found && (e & (flip[it] ? kFwdFlag : kRevFlag)) != 0 && p <= nk - 2);
+      if (first_f < 0 && fm) first_f = it * 32 + __ffs(fm) - 1;
+      if (gm) last_g = it * 32 + 31 - __clz(gm);
     }
-  } else if (!any_solid) {
-    // shorter than k, or no solid k-mer to anchor on (fast_read_correct.cpp:108-123): dropped
-    if ((int)lane < nw) {
-      store[base + lane] = 0;
-      store[rc_word_base + base + lane] = 0;
+
+    if (all_solid) {
+      // the read is its own correction: store it forward and reverse-complemented
+      if ((int)lane < nw) {
+        uint64_t v = wv;
+        const int rem = L - 32 * (int)lane;
+        if (rem < 32) v &= top_bases_mask(rem);
+        store[base + lane] = v;
+      }
+      {
+        // rc word j = revcomp of read[L - 32j - mcount, L - 32j)
+        const int j = (int)lane;
+        const int mcount = min(32, max(0, L - 32 * j));
+        const int lo_pos = max(0, L - 32 * j - mcount);
+        const uint64_t hi = __shfl_sync(0xffffffffu, wv, lo_pos >> 5), lo = __shfl_sync(0xffffffffu, wv, (lo_pos >> 5) + 1);
+        const unsigned s = (unsigned)(lo_pos & 31) * 2;
+        const uint64_t win = s ? ((hi << s) | (lo >> (64 - s))) : hi;
+        const int mc = max(mcount, 1);  // lanes past the read compute a dummy
+        if (j < nw) store[rc_word_base + base + j] = revcomp_kmer(win >> (64 - 2 * mc), mc) << (64 - 2 * mc);
+      }
+      if (lane == 0) {
+        const int nf = first_f >= 0 ? first_f : nk;
+        const int nr = last_g >= 0 ? nk - 1 - last_g : nk;
+        clen[r] = (uint16_t)L;
+        ncorr[r] = 0;
+        next_fwd[r] = (uint16_t)nf;
+        next_rev[r] = (uint16_t)nr;
+        w_kept += 1;
+        w_bases += (unsigned)L;
+        w_seeds += (unsigned)(nf + nr);
+      }
+    } else if (!any_solid) {
+      // shorter than k, or no solid k-mer to anchor on (fast_read_correct.cpp:108-123): dropped
+      if ((int)lane < nw) {
+        store[base + lane] = 0;
+        store[rc_word_base + base + lane] = 0;
+      }
+      if (lane == 0) {
+        clen[r] = 0;
+        ncorr[r] = 0;
+        next_fwd[r] = 0;
+        next_rev[r] = 0;
+      }
+    } else {
+      unsigned idx = 0;
+      if (lane == 0) idx = atomicAdd(&blk_slow, 1u);
+      slow_r[n_my_slow] = r;
+      slow_m[n_my_slow] = my_mask;
+      slow_i[n_my_slow] = __shfl_sync(0xffffffffu, idx, 0);
+      ++n_my_slow;
     }
-    if (lane == 0) {
-      clen[r] = 0;
-      ncorr[r] = 0;
-      next_fwd[r] = 0;
-      next_rev[r] = 0;
+  }
+  if (lane == 0 && w_kept) {
+    atomicAdd(&blk_kept, w_kept);
+    atomicAdd(&blk_bases, w_bases);
+    atomicAdd(&blk_seeds, w_seeds);
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    if (blk_kept) {
+      atomicAdd(&totals[0], (unsigned long long)blk_kept);
+      atomicAdd(&totals[1], (unsigned long long)blk_bases);
+      atomicAdd(&totals[2], (unsigned long long)blk_seeds);
     }
-  } else {
-    unsigned idx = 0;
-    if (lane == 0) idx = atomicAdd(n_slow, 1u);
-    idx = __shfl_sync(0xffffffffu, idx, 0);
-    if (lane == 0) slow_list[idx] = r;
-    if ((int)lane < MAXIT) slow_mask[(size_t)idx * MAXIT + lane] = my_mask;
+    blk_slow_base = blk_slow ? atomicAdd(n_slow, blk_slow) : 0u;
+  }
+  __syncthreads();
+  const unsigned sbase = blk_slow_base;
+#pragma unroll
+  for (int q = 0; q < kProbeRPW; ++q) {
+    if (q < n_my_slow) {
+      const unsigned idx = sbase + slow_i[q];
+      if (lane == 0) slow_list[idx] = slow_r[q];
+      if ((int)lane < MAXIT) slow_mask[(size_t)idx * MAXIT + lane] = slow_m[q];
+    }
   }
 }
 
@@ -605,7 +644,7 @@ void stage_correct(Context* c) {
   unsigned int h_slow = 0;
   {
     ScopedStage st(c, "correct_probe");
-    const unsigned grid = (unsigned)((n * 32 + kProbeThreads - 1) / kProbeThreads);
+    const unsigned grid = (unsigned)((n + kProbeWarps * kProbeRPW - 1) / (kProbeWarps * kProbeRPW));
     const uint32_t* nm = c->has_n ? c->nmask.p : nullptr;
 #define BGX_PROBE(MAXIT, HASN)                                                                                          \
   note_launch();                                                                                                        \

@@ -741,7 +741,9 @@ void stage_count_kmers(Context* c) {
       c->set_stat("kmer_solid_owned", (double)n_solid_local);
     }
     // "Too many kmers for kmer table!" (kmer_set.cpp:554-556) has no analogue: the set is sized to fit.
-    c->solid_slots = pow2_ceil(std::max<uint64_t>(1024, c->n_solid * 2));  // load factor in (1/4, 1/2]: short probe runs matter more than L2 residency (measured)
+    double solid_factor = 2.0;  // load factor in (1/4, 1/2]: short probe runs matter more than L2 residency (measured)
+    if (const char* e = getenv("BGX_SOLID_FACTOR")) solid_factor = std::max(1.05, atof(e));  // experiment hook
+    c->solid_slots = pow2_ceil(std::max<uint64_t>(1024, (uint64_t)((double)c->n_solid * solid_factor)));
     c->solid.alloc(c->solid_slots, s);
     KLAUNCH(fill_u64_kernel)<<<(unsigned)((c->solid_slots + 255) / 256), 256, 0, s>>>(c->solid.p, c->solid_slots, kEmptyKey);
     if (c->n_solid)

@@ -96,6 +96,33 @@ __device__ __forceinline__ uint32_t lower_bound_rec(const uint64_t* __restrict__
   return lo;
 }
 
+// Prefix-bucket index over a sorted record array: start[b] = first record whose top key bits are
+// >= b (start[2^bits] = n).  A lower_bound then only searches the few records of the query's own
+// bucket: one L2-resident table read + a search inside one or two DRAM sectors of keys, instead of
+// log2(n) dependent probes over the whole array (the reference's merge-joins stream both sides;
+// a GPU thread per query wants the range narrowed instead).
+struct BucketIndex {
+  const uint32_t* start;
+  int shift;  // 64 - bits
+};
+
+__global__ void bucket_index_kernel(const uint64_t* __restrict__ keys, uint32_t n, int shift, uint32_t n_buckets,
+                                    uint32_t* __restrict__ start) {
+  uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i > n) return;  // thread n closes the table
+  const int64_t b_prev = i == 0 ? -1 : (int64_t)(keys[i - 1] >> shift);
+  const int64_t b_cur = i == n ? (int64_t)n_buckets : (int64_t)(keys[i] >> shift);
+  for (int64_t b = b_prev + 1; b <= b_cur; ++b) start[b] = i;
+}
+
+__device__ __forceinline__ uint32_t lower_bound_idx(const uint64_t* __restrict__ store,
+                                                    const uint64_t* __restrict__ keys,
+                                                    const uint64_t* __restrict__ locs, const BucketIndex& bi,
+                                                    uint64_t xk, uint64_t xl) {
+  const uint64_t b = xk >> bi.shift;
+  return lower_bound_rec(store, keys, locs, bi.start[b], bi.start[b + 1], xk, xl);
+}
+
 // ---- seeds ------------------------------------------------------------------------------------
 __global__ void seed_count_kernel(const uint16_t* __restrict__ clen, const uint16_t* __restrict__ nf,
                                   const uint16_t* __restrict__ nr, uint32_t n_reads, uint32_t* __restrict__ cnt) {
@@ -319,26 +346,29 @@ __global__ void compact_pairs_kernel(const uint64_t* __restrict__ keys, const ui
 
 // ---- closure walk ------------------------------------------------------------------------------------
 __device__ __forceinline__ bool covered(const uint64_t* __restrict__ store, const uint64_t* __restrict__ keys,
-                                        const uint64_t* __restrict__ locs, uint32_t n, uint64_t addr, int len,
-                                        uint32_t* where) {
+                                        const uint64_t* __restrict__ locs, uint32_t n, const BucketIndex& bi,
+                                        uint64_t addr, int len, uint32_t* where) {
   if (len == 0) { if (where) *where = 0; return true; }  // the empty sequence is a prefix of everything
   uint64_t xk = suffix_key(store, addr, len), xl = make_loc(addr, len);
-  uint32_t lb = lower_bound_rec(store, keys, locs, 0, n, xk, xl);
+  uint32_t lb = lower_bound_idx(store, keys, locs, bi, xk, xl);
   if (where) *where = lb;
-  return lb < n && prefix_or_equal(store, xk, xl, keys[lb], locs[lb]);
+  if (lb >= n) return false;
+  const uint64_t el = locs[lb];
+  if (el == xl) return true;  // the very same suffix of the same read (the common case): nothing to compare
+  return prefix_or_equal(store, xk, xl, keys[lb], el);
 }
 
 // phase 1: one thread per entry; entries whose pop_front is not covered start a chain
 __global__ void __launch_bounds__(128) walk_phase1_kernel(const uint64_t* __restrict__ store,
                                                           const uint64_t* __restrict__ keys,
                                                           const uint64_t* __restrict__ locs, uint32_t n,
-                                                          uint32_t* __restrict__ chains,
+                                                          BucketIndex bi, uint32_t* __restrict__ chains,
                                                           unsigned long long* __restrict__ n_chains) {
   uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
   bool start = false;
   if (i < n) {
     uint64_t l = locs[i];
-    start = !covered(store, keys, locs, n, loc_addr(l) + 1, (int)loc_len(l) - 1, nullptr);
+    start = !covered(store, keys, locs, n, bi, loc_addr(l) + 1, (int)loc_len(l) - 1, nullptr);
   }
   unsigned mask = __ballot_sync(0xffffffffu, start);
   if (!mask) return;
@@ -354,8 +384,8 @@ __global__ void __launch_bounds__(128) walk_phase1_kernel(const uint64_t* __rest
 __global__ void __launch_bounds__(128) walk_phase2_kernel(const uint64_t* __restrict__ store,
                                                           const uint64_t* __restrict__ keys,
                                                           const uint64_t* __restrict__ locs, uint32_t n,
-                                                          const uint32_t* __restrict__ chains, uint32_t n_chains,
-                                                          uint32_t* __restrict__ chain_stop) {
+                                                          BucketIndex bi, const uint32_t* __restrict__ chains,
+                                                          uint32_t n_chains, uint32_t* __restrict__ chain_stop) {
   uint32_t c = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   if (c >= n_chains) return;
   unsigned lane = lane_id();
@@ -365,7 +395,7 @@ __global__ void __launch_bounds__(128) walk_phase2_kernel(const uint64_t* __rest
   int stop = len;
   for (int j0 = 2; j0 < len; j0 += 32) {  // j = 1 is known uncovered
     int j = j0 + (int)lane;
-    bool cov = j < len && covered(store, keys, locs, n, addr + j, len - j, nullptr);
+    bool cov = j < len && covered(store, keys, locs, n, bi, addr + j, len - j, nullptr);
     unsigned mask = __ballot_sync(0xffffffffu, cov);
     if (mask) { stop = j0 + __ffs(mask) - 1; break; }
   }
@@ -394,12 +424,12 @@ __global__ void walk_emit_kernel(const uint64_t* __restrict__ store, const uint6
 // rank[j] = number of old records that sort before new record j; marks[r] counts the new records
 // inserted in front of old record r.
 __global__ void merge_rank_kernel(const uint64_t* __restrict__ store, const uint64_t* __restrict__ okeys,
-                                  const uint64_t* __restrict__ olocs, uint32_t n_old,
+                                  const uint64_t* __restrict__ olocs, uint32_t n_old, BucketIndex bi,
                                   const uint64_t* __restrict__ nkeys, const uint64_t* __restrict__ nlocs,
                                   uint32_t n_new, uint32_t* __restrict__ rank, uint32_t* __restrict__ marks) {
   uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
   if (j >= n_new) return;
-  uint32_t r = lower_bound_rec(store, okeys, olocs, 0, n_old, nkeys[j], nlocs[j]);
+  uint32_t r = lower_bound_idx(store, okeys, olocs, bi, nkeys[j], nlocs[j]);
   rank[j] = r;
   atomicAdd(&marks[r], 1u);
 }
@@ -428,7 +458,7 @@ __global__ void merge_scatter_new_kernel(const uint64_t* __restrict__ nkeys, con
 // ---- tables ---------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(128) tables_kernel(const uint64_t* __restrict__ store,
                                                      const uint64_t* __restrict__ keys,
-                                                     const uint64_t* __restrict__ locs, uint32_t n,
+                                                     const uint64_t* __restrict__ locs, uint32_t n, BucketIndex bi,
                                                      uint16_t* __restrict__ sizes, uint16_t* __restrict__ shared,
                                                      unsigned long long* __restrict__ prev_bits, uint64_t prev_words,
                                                      unsigned int* __restrict__ max_len, int* __restrict__ missing) {
@@ -451,7 +481,7 @@ __global__ void __launch_bounds__(128) tables_kernel(const uint64_t* __restrict_
     shared[i] = (uint16_t)lcp;
     // prev bit: first entry having pop_front(e) as a prefix (bs/builder.cpp:85-107)
     uint32_t where;
-    bool cov = covered(store, keys, locs, n, loc_addr(l) + 1, (int)len - 1, &where);
+    bool cov = covered(store, keys, locs, n, bi, loc_addr(l) + 1, (int)len - 1, &where);
     if (!cov) {
       *missing = 1;  // LOG(FATAL) << "Missing expansion?" (bs/builder.cpp:96)
     } else {
@@ -583,11 +613,14 @@ __global__ void __launch_bounds__(256) route_scatter_kernel(const uint64_t* __re
 
 // covered() against this rank's sorted range plus the record that follows it globally
 __device__ __forceinline__ bool covered_next(const uint64_t* __restrict__ store, const uint64_t* __restrict__ keys,
-                                             const uint64_t* __restrict__ locs, uint32_t n, const NextRec& next,
-                                             uint64_t xk, uint64_t xl, uint32_t* where) {
-  uint32_t lb = lower_bound_rec(store, keys, locs, 0, n, xk, xl);
+                                             const uint64_t* __restrict__ locs, uint32_t n, const BucketIndex& bi,
+                                             const NextRec& next, uint64_t xk, uint64_t xl, uint32_t* where) {
+  uint32_t lb = lower_bound_idx(store, keys, locs, bi, xk, xl);
   *where = lb;
-  if (lb < n) return prefix_or_equal(store, xk, xl, keys[lb], locs[lb]);
+  if (lb < n) {
+    const uint64_t el = locs[lb];
+    return el == xl || prefix_or_equal(store, xk, xl, keys[lb], el);
+  }
   return next.has && prefix_or_equal(store, xk, xl, next.key, next.loc);
 }
 
@@ -627,8 +660,8 @@ __global__ void pop_queries_kernel(const uint64_t* __restrict__ store, const uin
 // it will emit (all its suffixes when emit_suffixes, else itself)
 __global__ void __launch_bounds__(128) uncovered_kernel(const uint64_t* __restrict__ store,
                                                         const uint64_t* __restrict__ keys,
-                                                        const uint64_t* __restrict__ locs, uint32_t n, NextRec next,
-                                                        const uint64_t* __restrict__ xkeys,
+                                                        const uint64_t* __restrict__ locs, uint32_t n, BucketIndex bi,
+                                                        NextRec next, const uint64_t* __restrict__ xkeys,
                                                         const uint64_t* __restrict__ xlocs, uint32_t m,
                                                         int emit_suffixes, uint32_t* __restrict__ cnt,
                                                         uint32_t* __restrict__ list,
@@ -637,7 +670,7 @@ __global__ void __launch_bounds__(128) uncovered_kernel(const uint64_t* __restri
   bool unc = false;
   if (j < m) {
     uint32_t where;
-    unc = !covered_next(store, keys, locs, n, next, xkeys[j], xlocs[j], &where);
+    unc = !covered_next(store, keys, locs, n, bi, next, xkeys[j], xlocs[j], &where);
     cnt[j] = unc ? (emit_suffixes ? loc_len(xlocs[j]) : 1u) : 0u;
   }
   // the (few) uncovered ones go on a list so the emit kernel only visits them
@@ -699,8 +732,8 @@ __global__ void __launch_bounds__(128) tables_local_kernel(const uint64_t* __res
 // the first local entry having x as a prefix; where == n means the next rank's entry 0 (carry).
 __global__ void __launch_bounds__(128) prev_apply_kernel(const uint64_t* __restrict__ store,
                                                          const uint64_t* __restrict__ keys,
-                                                         const uint64_t* __restrict__ locs, uint32_t n, NextRec next,
-                                                         const uint64_t* __restrict__ xkeys,
+                                                         const uint64_t* __restrict__ locs, uint32_t n, BucketIndex bi,
+                                                         NextRec next, const uint64_t* __restrict__ xkeys,
                                                          const uint64_t* __restrict__ xlocs, uint32_t m,
                                                          unsigned long long* __restrict__ prev_bits, uint64_t prev_words,
                                                          int* __restrict__ carry /*[4]*/, int* __restrict__ missing) {
@@ -710,7 +743,7 @@ __global__ void __launch_bounds__(128) prev_apply_kernel(const uint64_t* __restr
   unsigned b = (unsigned)((xl >> 14) & 3);
   xl &= ~0xC000ULL;
   uint32_t where;
-  if (!covered_next(store, keys, locs, n, next, xkeys[j], xl, &where)) {
+  if (!covered_next(store, keys, locs, n, bi, next, xkeys[j], xl, &where)) {
     *missing = 1;  // LOG(FATAL) << "Missing expansion?" (bs/builder.cpp:96)
   } else if (where < n) {
     atomicOr(&prev_bits[(uint64_t)b * prev_words + (where >> 6)], 1ULL << (where & 63));
@@ -768,6 +801,20 @@ unsigned long long read_u64(const unsigned long long* d, cudaStream_t s) {
   BGX_CUDA(cudaMemcpyAsync(&h, d, sizeof(h), cudaMemcpyDeviceToHost, s));
   BGX_CUDA(cudaStreamSynchronize(s));
   return h;
+}
+
+// bucket index over n sorted records: about 8 records per bucket, at most 2^24 buckets
+BucketIndex build_bucket_index(Context* c, const uint64_t* keys, uint32_t n, DevBuf<uint32_t>& buf) {
+  cudaStream_t s = c->stream;
+  int bits = 0;
+  while ((2ull << bits) <= (uint64_t)std::max<uint32_t>(n, 1)) ++bits;  // floor(log2(n))
+  bits = std::max(4, std::min(24, bits - 3));
+  if (const char* e = getenv("BGX_INDEX_BITS")) bits = std::max(1, std::min(28, atoi(e)));  // experiment hook
+  const uint32_t nb = 1u << bits;
+  buf.alloc((size_t)nb + 1, s);
+  KLAUNCH(bucket_index_kernel)<<<grid_for((uint64_t)n + 1, 256), 256, 0, s>>>(keys, n, 64 - bits, nb, buf.p);
+  BGX_CUDA(cudaGetLastError());
+  return BucketIndex{buf.p, 64 - bits};
 }
 
 // Sort n records completely.  keys/locs and the alt buffers all hold >= n elements; the sorted
@@ -878,7 +925,7 @@ uint32_t dedup_records(Context* c, DevBuf<uint64_t>& keys, DevBuf<uint64_t>& loc
 // merge n_new sorted records into the n1 sorted records of (keys, locs) by rank; the result
 // (n1 + n_new records) ends in (keys, locs); the alt buffers are grown to hold as many.
 void merge_new_records(Context* c, DevBuf<uint64_t>& keys, DevBuf<uint64_t>& locs, DevBuf<uint64_t>& keys_alt,
-                       DevBuf<uint64_t>& locs_alt, uint32_t n1, const DevBuf<uint64_t>& nkeys,
+                       DevBuf<uint64_t>& locs_alt, uint32_t n1, const BucketIndex& bi, const DevBuf<uint64_t>& nkeys,
                        const DevBuf<uint64_t>& nlocs, uint32_t n_new) {
   cudaStream_t s = c->stream;
   const uint32_t nm = n1 + n_new;
@@ -889,7 +936,7 @@ void merge_new_records(Context* c, DevBuf<uint64_t>& keys, DevBuf<uint64_t>& loc
   }
   DevBuf<uint32_t> rank(n_new, s), marks((size_t)n1 + 2, s);
   BGX_CUDA(cudaMemsetAsync(marks.p, 0, ((size_t)n1 + 2) * 4, s));
-  KLAUNCH(merge_rank_kernel)<<<grid_for(n_new, 128), 128, 0, s>>>(c->seq_store(), keys.p, locs.p, n1, nkeys.p, nlocs.p, n_new,
+  KLAUNCH(merge_rank_kernel)<<<grid_for(n_new, 128), 128, 0, s>>>(c->seq_store(), keys.p, locs.p, n1, bi, nkeys.p, nlocs.p, n_new,
                                                          rank.p, marks.p);
   exclusive_scan_u32(marks.p, marks.p, (size_t)n1 + 2, nullptr, s);
   if (n1) KLAUNCH(merge_scatter_old_kernel)<<<grid_for(n1, 256), 256, 0, s>>>(keys.p, locs.p, n1, marks.p, keys_alt.p, locs_alt.p);
@@ -940,18 +987,21 @@ void stage_build_seqset(Context* c) {
   // 3. closure walk: the new records are emitted into their own buffers
   uint32_t n_new = 0;
   DevBuf<uint64_t> nkeys, nlocs;
+  DevBuf<uint32_t> index_buf;
+  BucketIndex bi1;
   {
     ScopedStage st(c, "walk");
+    bi1 = build_bucket_index(c, keys.p, n1, index_buf);
     DevBuf<uint32_t> chains(std::max<uint32_t>(n1, 1), s);
     DevBuf<unsigned long long> n_chains_d(1, s);
     BGX_CUDA(cudaMemsetAsync(n_chains_d.p, 0, 8, s));
-    KLAUNCH(walk_phase1_kernel)<<<grid_for(n1, 128), 128, 0, s>>>(c->store.p, keys.p, locs.p, n1, chains.p, n_chains_d.p);
+    KLAUNCH(walk_phase1_kernel)<<<grid_for(n1, 128), 128, 0, s>>>(c->store.p, keys.p, locs.p, n1, bi1, chains.p, n_chains_d.p);
     BGX_CUDA(cudaGetLastError());
     uint32_t n_chains = (uint32_t)read_u64(n_chains_d.p, s);
     c->set_stat("walk_chains", n_chains);
     if (n_chains) {
       DevBuf<uint32_t> ccnt(n_chains, s), coff(n_chains, s), tot(1, s);
-      KLAUNCH(walk_phase2_kernel)<<<grid_for((uint64_t)n_chains * 32, 128), 128, 0, s>>>(c->store.p, keys.p, locs.p, n1, chains.p,
+      KLAUNCH(walk_phase2_kernel)<<<grid_for((uint64_t)n_chains * 32, 128), 128, 0, s>>>(c->store.p, keys.p, locs.p, n1, bi1, chains.p,
                                                                                 n_chains, ccnt.p);
       exclusive_scan_u32(ccnt.p, coff.p, n_chains, tot.p, s);
       BGX_CUDA(cudaGetLastError());
@@ -975,7 +1025,7 @@ void stage_build_seqset(Context* c) {
       sort_records(c, nkeys, nlocs, nkeys_alt, nlocs_alt, n_new, "r2");
     }
     const uint32_t nm = n1 + n_new;
-    merge_new_records(c, keys, locs, keys_alt, locs_alt, n1, nkeys, nlocs, n_new);
+    merge_new_records(c, keys, locs, keys_alt, locs_alt, n1, bi1, nkeys, nlocs, n_new);
     n2 = dedup_records(c, keys, locs, keys_alt, locs_alt, nm);
   }
   c->n_entries = n2;
@@ -1002,7 +1052,8 @@ void stage_build_seqset(Context* c) {
     BGX_CUDA(cudaMemsetAsync(max_len.p, 0, 4, s));
     BGX_CUDA(cudaMemsetAsync(missing.p, 0, 4, s));
     if (nb) {
-      KLAUNCH(tables_kernel)<<<grid_for(nb, 128), 128, 0, s>>>(c->store.p, keys.p, locs.p, n2, c->sizes.p, c->shared.p,
+      const BucketIndex bi2 = n2 == n1 && n_new == 0 ? bi1 : build_bucket_index(c, keys.p, n2, index_buf);
+      KLAUNCH(tables_kernel)<<<grid_for(nb, 128), 128, 0, s>>>(c->store.p, keys.p, locs.p, n2, bi2, c->sizes.p, c->shared.p,
                                                       reinterpret_cast<unsigned long long*>(c->prev_bits.p),
                                                       c->prev_words, max_len.p, missing.p);
       DevBuf<uint32_t> gpop(c->sub_words, s), gex(c->sub_words, s), tot(1, s);
@@ -1230,10 +1281,13 @@ void stage_build_seqset_dist(Context* c) {
   //    One round reaches the fixed point: every suffix of anything new was itself a candidate.
   uint32_t n_new = 0;
   DevBuf<uint64_t> nkeys, nlocs;
+  DevBuf<uint32_t> index_buf;
+  BucketIndex bi1;
   {
     ScopedStage st(c, "walk");
     ends = exchange_ends(c, keys, locs, n1);
     NextRec next = next_of(ends, R, N);
+    bi1 = build_bucket_index(c, keys.p, n1, index_buf);
     DevBuf<uint64_t> qk(std::max<uint32_t>(n1, 1), s), ql(std::max<uint32_t>(n1, 1), s);
     DevBuf<unsigned long long> nq_d(1, s);
     BGX_CUDA(cudaMemsetAsync(nq_d.p, 0, 8, s));
@@ -1247,7 +1301,7 @@ void stage_build_seqset_dist(Context* c) {
     DevBuf<uint32_t> cnt(std::max<uint32_t>(q.n, 1), s), off(std::max<uint32_t>(q.n, 1), s), list(std::max<uint32_t>(q.n, 1), s), tot(1, s);
     DevBuf<unsigned long long> nl_d(1, s);
     BGX_CUDA(cudaMemsetAsync(nl_d.p, 0, 8, s));
-    if (q.n) KLAUNCH(uncovered_kernel)<<<grid_for(q.n, 128), 128, 0, s>>>(store, keys.p, locs.p, n1, next, q.keys.p, q.locs.p, q.n,
+    if (q.n) KLAUNCH(uncovered_kernel)<<<grid_for(q.n, 128), 128, 0, s>>>(store, keys.p, locs.p, n1, bi1, next, q.keys.p, q.locs.p, q.n,
                                                                   1, cnt.p, list.p, nl_d.p);
     exclusive_scan_u32(cnt.p, off.p, q.n, tot.p, s);
     uint32_t n_cand = read_u32(tot.p, s);
@@ -1263,7 +1317,7 @@ void stage_build_seqset_dist(Context* c) {
     // owners keep the candidates nothing covers yet
     DevBuf<uint32_t> cnt2(std::max<uint32_t>(cd.n, 1), s), off2(std::max<uint32_t>(cd.n, 1), s), list2(std::max<uint32_t>(cd.n, 1), s);
     BGX_CUDA(cudaMemsetAsync(nl_d.p, 0, 8, s));
-    if (cd.n) KLAUNCH(uncovered_kernel)<<<grid_for(cd.n, 128), 128, 0, s>>>(store, keys.p, locs.p, n1, next, cd.keys.p, cd.locs.p,
+    if (cd.n) KLAUNCH(uncovered_kernel)<<<grid_for(cd.n, 128), 128, 0, s>>>(store, keys.p, locs.p, n1, bi1, next, cd.keys.p, cd.locs.p,
                                                                     cd.n, 0, cnt2.p, list2.p, nl_d.p);
     exclusive_scan_u32(cnt2.p, off2.p, cd.n, tot.p, s);
     n_new = read_u32(tot.p, s);
@@ -1282,7 +1336,7 @@ void stage_build_seqset_dist(Context* c) {
     if (n_new) {
       DevBuf<uint64_t> nkeys_alt(n_new, s), nlocs_alt(n_new, s);
       sort_records(c, nkeys, nlocs, nkeys_alt, nlocs_alt, n_new, "r2");
-      merge_new_records(c, keys, locs, keys_alt, locs_alt, n1, nkeys, nlocs, n_new);
+      merge_new_records(c, keys, locs, keys_alt, locs_alt, n1, bi1, nkeys, nlocs, n_new);
     }
     ends = exchange_ends(c, keys, locs, n1 + n_new);
     n2 = dedup_records(c, keys, locs, keys_alt, locs_alt, n1 + n_new, next_of(ends, R, N));
@@ -1377,7 +1431,8 @@ void stage_build_seqset_dist(Context* c) {
       uint32_t nq = (uint32_t)read_u64(nq_d.p, s);
       Routed q = route_records(c, qk.p, ql.p, nq, sp2);
       ScopedStage st_p(c, "tables_prev_apply");
-      if (q.n) KLAUNCH(prev_apply_kernel)<<<grid_for(q.n, 128), 128, 0, s>>>(store, keys.p, locs.p, n2, next, q.keys.p, q.locs.p, q.n,
+      const BucketIndex bi2 = build_bucket_index(c, keys.p, n2, index_buf);
+      if (q.n) KLAUNCH(prev_apply_kernel)<<<grid_for(q.n, 128), 128, 0, s>>>(store, keys.p, locs.p, n2, bi2, next, q.keys.p, q.locs.p, q.n,
                                                                      bits, c->prev_words, flags.p, flags.p + 8);
       BGX_CUDA(cudaGetLastError());
       st_p.stop();
