@@ -323,7 +323,6 @@ struct OnesweepSmem {
   uint32_t warp_cnt[RS_WARPS][RADIX];
   uint32_t digit_start[RADIX];
   uint32_t glob_base[RADIX];
-  uint8_t stage_digit[RS_TILE];
   uint64_t bar_keys, bar_vals;
   uint32_t tile;
 };
@@ -430,10 +429,21 @@ onesweep_kernel(const uint64_t* __restrict__ keys_in, const uint64_t* __restrict
     const uint32_t r = (packed_rank[i >> 1] >> (16 * (i & 1))) & 0xffffu;
     const uint32_t pos = sm.digit_start[d] + sm.warp_cnt[warp][d] + r;
     sm.keys[pos] = k[i];
-    sm.stage_digit[pos] = (uint8_t)d;
   }
   __syncthreads();
-  for (uint32_t j = tid; j < nvalid; j += RS_THREADS) keys_out[sm.glob_base[sm.stage_digit[j]] + j] = sm.keys[j];
+  // element j of the reordered tile names its own digit; the thread keeps it for the value it writes next
+  uint32_t out_digs[RS_ITEMS / 4];
+#pragma unroll
+  for (int i = 0; i < RS_ITEMS; ++i) {
+    const uint32_t j = tid + i * RS_THREADS;
+    unsigned d = 0;
+    if (j < nvalid) {
+      const uint64_t key = sm.keys[j];
+      d = (unsigned)(key >> shift) & (RADIX - 1);
+      keys_out[sm.glob_base[d] + j] = key;
+    }
+    if (i & 3) out_digs[i >> 2] |= d << (8 * (i & 3)); else out_digs[i >> 2] = d;
+  }
   // ---- values: same permutation -----------------------------------------------------------------------
   mbar_wait(&sm.bar_vals, 0);
 #pragma unroll
@@ -446,7 +456,11 @@ onesweep_kernel(const uint64_t* __restrict__ keys_in, const uint64_t* __restrict
     sm.vals[sm.digit_start[d] + sm.warp_cnt[warp][d] + r] = k[i];
   }
   __syncthreads();
-  for (uint32_t j = tid; j < nvalid; j += RS_THREADS) vals_out[sm.glob_base[sm.stage_digit[j]] + j] = sm.vals[j];
+#pragma unroll
+  for (int i = 0; i < RS_ITEMS; ++i) {
+    const uint32_t j = tid + i * RS_THREADS;
+    if (j < nvalid) vals_out[sm.glob_base[(out_digs[i >> 2] >> (8 * (i & 3))) & 0xffu] + j] = sm.vals[j];
+  }
 }
 
 }  // namespace

@@ -824,6 +824,7 @@ void sort_records(Context* c, DevBuf<uint64_t>& keys, DevBuf<uint64_t>& locs, De
   cudaStream_t s = c->stream;
   if (n == 0) return;
   int sbits = c->opt.sort_key_bits;
+  if (const char* e = getenv("BGX_SORT_BITS")) sbits = std::max(16, std::min(64, atoi(e) / 8 * 8));  // experiment hook
   int passes = 0;
   {
     ScopedStage st(c, "sort_radix");
