@@ -235,23 +235,28 @@ __global__ void __launch_bounds__(SC_THREADS) scan_final_kernel(const uint32_t* 
 // LSD radix sort of (uint64 key, uint64 value) pairs, 8-bit digits, "one sweep" per digit:
 //   radix_hist_kernel   : ONE read of the keys builds the global digit histograms of every pass
 //   radix_bases_kernel  : exclusive scan of each pass's 256 bins -> first output index per digit
-//   onesweep_kernel     : per pass, per tile of 4096 records:
+//   onesweep_kernel     : per pass, per tile of 4096 records (256 threads x 16 records, 3 CTAs per SM):
 //       - the tile's keys and values are pulled into shared memory by TMA bulk copies
 //         (cp.async.bulk.shared::cluster.global + mbarrier complete_tx), no registers held
-//       - stable in-tile ranking: warp-striped items, match_any per digit, per-warp counters
-//       - the tile's digit counts are published and the exclusive prefix over earlier tiles is
-//         fetched by decoupled look-back (one thread per digit), so a pass reads and writes every
-//         record exactly once (2*N*16 bytes per pass)
-//       - records are reordered in shared memory and leave as coalesced per-digit runs
+//       - stable in-tile ranking: warp-striped items, match_any per digit, per-warp counters bumped
+//         with shared-memory atomics by the group leaders; the 16 items of a thread are independent
+//         instruction streams (loads, matches and atomics pipeline instead of forming one chain)
+//       - thread d owns digit d: it publishes the tile's count, and fetches the exclusive prefix
+//         over earlier tiles by decoupled look-back, several predecessors per round trip; the loads
+//         are issued before the in-tile reorder and consumed after it
+//       - records are reordered in shared memory and leave as coalesced per-digit runs, so a pass
+//         reads and writes every record exactly once (2*N*16 bytes per pass)
 // Tiles are handed out by an atomic ticket, so every tile a block can wait on has started.
-constexpr int RS_THREADS = 512;
+constexpr int RS_THREADS = 256;
 constexpr int RS_WARPS = RS_THREADS / 32;
-constexpr int RS_ITEMS = 8;
+constexpr int RS_ITEMS = 16;
 constexpr int RS_TILE = RS_THREADS * RS_ITEMS;  // 4096 records
 constexpr int RADIX = 256;
+constexpr int RS_LOOKBACK = 4;           // predecessor tiles fetched per look-back round trip
 constexpr uint32_t ST_AGG = 1u << 30;    // tile aggregate available
 constexpr uint32_t ST_INCL = 1u << 31;   // inclusive prefix available
 constexpr uint32_t ST_VAL = (1u << 30) - 1;
+static_assert(RS_THREADS == RADIX, "one thread per digit");
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
@@ -281,6 +286,14 @@ __device__ __forceinline__ void tma_load_1d(void* dst, const void* src, uint32_t
                    smem_u32(dst)),
                "l"(src), "r"(bytes), "r"(smem_u32(bar))
                : "memory");
+}
+__device__ __forceinline__ uint32_t ld_status(const uint32_t* p) {
+  uint32_t v;
+  asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_status(uint32_t* p, uint32_t v) {
+  asm volatile("st.relaxed.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
 
 constexpr int RH_THREADS = 256;
@@ -318,16 +331,17 @@ __global__ void __launch_bounds__(RADIX) radix_bases_kernel(uint32_t* __restrict
 }
 
 struct OnesweepSmem {
-  uint64_t keys[RS_TILE];    // TMA destination, then the reorder stage
+  uint64_t keys[RS_TILE];    // TMA destination; then the reorder stage of the keys, then of the values
   uint64_t vals[RS_TILE];    // TMA destination
   uint32_t warp_cnt[RS_WARPS][RADIX];
   uint32_t digit_start[RADIX];
   uint32_t glob_base[RADIX];
+  uint32_t warp_part[RS_WARPS];
   uint64_t bar_keys, bar_vals;
   uint32_t tile;
 };
 
-__global__ void __launch_bounds__(RS_THREADS, 2)
+__global__ void __launch_bounds__(RS_THREADS, 3)
 onesweep_kernel(const uint64_t* __restrict__ keys_in, const uint64_t* __restrict__ vals_in,
                 uint64_t* __restrict__ keys_out, uint64_t* __restrict__ vals_out,
                 const uint32_t* __restrict__ digit_base /*[256] exclusive*/, uint32_t* __restrict__ status /*[ntiles][256]*/,
@@ -342,7 +356,11 @@ onesweep_kernel(const uint64_t* __restrict__ keys_in, const uint64_t* __restrict
     mbar_init(&sm.bar_vals, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  for (int i = tid; i < RS_WARPS * RADIX; i += RS_THREADS) (&sm.warp_cnt[0][0])[i] = 0;
+  {
+    uint4* z = reinterpret_cast<uint4*>(&sm.warp_cnt[0][0]);
+#pragma unroll
+    for (int i = 0; i < RS_WARPS * RADIX / 4 / RS_THREADS; ++i) z[tid + i * RS_THREADS] = make_uint4(0, 0, 0, 0);
+  }
   __syncthreads();
   const uint32_t tile = sm.tile;
   const uint32_t tile_base = tile * RS_TILE;
@@ -359,78 +377,115 @@ onesweep_kernel(const uint64_t* __restrict__ keys_in, const uint64_t* __restrict
   // ---- stable ranking: item (i, lane) of warp w is tile element w*512 + i*32 + lane ------------
   const uint32_t warp_base = warp * (RS_ITEMS * 32);
   const unsigned lt_mask = (1u << lane) - 1;
-  uint32_t packed_rank[RS_ITEMS / 2];  // two 16-bit ranks per register
+  uint64_t k[RS_ITEMS];
+  uint32_t packed_rank[RS_ITEMS / 2];  // two 16-bit ranks per register; later two 16-bit stage positions
   uint32_t digs[RS_ITEMS / 4];         // four 8-bit digits per register
 #pragma unroll
-  for (int i = 0; i < RS_ITEMS; ++i) {
-    const uint32_t e = warp_base + i * 32 + lane;
-    // pads (beyond nvalid) rank as digit 255 after every real record of their warp
-    const unsigned d = e < nvalid ? (unsigned)(sm.keys[e] >> shift) & (RADIX - 1) : (RADIX - 1);
-    const unsigned peers = __match_any_sync(0xffffffffu, d);
-    const int leader = __ffs(peers) - 1;
-    uint32_t old = 0;
-    if ((int)lane == leader) {
-      old = sm.warp_cnt[warp][d];
-      sm.warp_cnt[warp][d] = old + __popc(peers);
-    }
-    old = __shfl_sync(0xffffffffu, old, leader);
-    const uint32_t r = old + __popc(peers & lt_mask);
-    if (i & 1) packed_rank[i >> 1] |= r << 16; else packed_rank[i >> 1] = r;
-    if (i & 3) digs[i >> 2] |= d << (8 * (i & 3)); else digs[i >> 2] = d;
-    __syncwarp();
-  }
-  __syncthreads();
-
-  // ---- per-digit: warp offsets, tile count, decoupled look-back ---------------------------------
-  {
-    const unsigned d = tid;  // threads [0, 256) own one digit each
-    uint32_t sum = 0, excl = 0;
-    if (d < RADIX) {
-#pragma unroll
-      for (int w = 0; w < RS_WARPS; ++w) {
-        const uint32_t c = sm.warp_cnt[w][d];
-        sm.warp_cnt[w][d] = sum;
-        sum += c;
-      }
-      // pads were counted as digit 255: remove them from the published count
-      const uint32_t real = (d == RADIX - 1) ? sum - (RS_TILE - nvalid) : sum;
-      volatile uint32_t* st = status + (size_t)tile * RADIX + d;
-      if (tile == 0) {
-        *st = ST_INCL | real;
-      } else {
-        *st = ST_AGG | real;
-        for (int64_t j = (int64_t)tile - 1;; --j) {
-          volatile uint32_t* sp = status + (size_t)j * RADIX + d;
-          uint32_t v;
-          do { v = *sp; } while (v == 0);
-          excl += v & ST_VAL;
-          if (v & ST_INCL) break;
-        }
-        *st = ST_INCL | (excl + real);
-      }
-    }
-    uint32_t tot;
-    const uint32_t ex = block_excl_scan_u32(sum, &tot);
-    if (d < RADIX) {
-      sm.digit_start[d] = ex;
-      sm.glob_base[d] = digit_base[d] + excl - ex;
-    }
-  }
-  __syncthreads();
-
-  // ---- keys: shared (tile order) -> registers -> shared (digit order) -> global ------------------
-  uint64_t k[RS_ITEMS];
-#pragma unroll
   for (int i = 0; i < RS_ITEMS; ++i) k[i] = sm.keys[warp_base + i * 32 + lane];
+  uint32_t* my_cnt = sm.warp_cnt[warp];
+#pragma unroll
+  for (int h = 0; h < RS_ITEMS; h += 8) {
+    unsigned peers[8];
+    uint32_t old[8];
+#pragma unroll
+    for (int q = 0; q < 8; ++q) {
+      const int i = h + q;
+      const uint32_t e = warp_base + i * 32 + lane;
+      // pads (beyond nvalid) rank as digit 255 after every real record of the tile
+      const unsigned d = e < nvalid ? (unsigned)(k[i] >> shift) & (RADIX - 1) : (RADIX - 1);
+      if (i & 3) digs[i >> 2] |= d << (8 * (i & 3)); else digs[i >> 2] = d;
+      peers[q] = __match_any_sync(0xffffffffu, d);
+    }
+#pragma unroll
+    for (int q = 0; q < 8; ++q) {
+      const int i = h + q;
+      const unsigned d = (digs[i >> 2] >> (8 * (i & 3))) & 0xffu;
+      old[q] = 0;
+      // the lowest lane of each digit group bumps the warp's counter; groups of one instruction
+      // have different digits, successive instructions are ordered by the warp barrier
+      if ((peers[q] & lt_mask) == 0) old[q] = atomicAdd(&my_cnt[d], (uint32_t)__popc(peers[q]));
+      __syncwarp();
+    }
+#pragma unroll
+    for (int q = 0; q < 8; ++q) {
+      const int i = h + q;
+      const uint32_t r = __shfl_sync(0xffffffffu, old[q], __ffs(peers[q]) - 1) + __popc(peers[q] & lt_mask);
+      if (i & 1) packed_rank[i >> 1] |= r << 16; else packed_rank[i >> 1] = r;
+    }
+  }
   __syncthreads();
+
+  // ---- thread d owns digit d: warp offsets, tile count, look-back loads, in-tile digit starts -------
+  const unsigned d_own = tid;
+  uint32_t sum = 0;
+#pragma unroll
+  for (int w = 0; w < RS_WARPS; ++w) {
+    const uint32_t c = sm.warp_cnt[w][d_own];
+    sm.warp_cnt[w][d_own] = sum;
+    sum += c;
+  }
+  // pads were counted as digit 255: remove them from the published count
+  const uint32_t real = (d_own == RADIX - 1) ? sum - (RS_TILE - nvalid) : sum;
+  uint32_t* const st_mine = status + (size_t)tile * RADIX + d_own;
+  st_status(st_mine, (tile == 0 ? ST_INCL : ST_AGG) | real);
+  uint32_t lb[RS_LOOKBACK];
+#pragma unroll
+  for (int q = 0; q < RS_LOOKBACK; ++q)
+    lb[q] = tile > (uint32_t)q ? ld_status(status + (size_t)(tile - 1 - q) * RADIX + d_own) : ST_INCL;
+  uint32_t ex;
+  {
+    const uint32_t inc = warp_incl_scan_u32(sum);
+    if (lane == 31) sm.warp_part[warp] = inc;
+    __syncthreads();
+    uint32_t before = 0;
+#pragma unroll
+    for (int w = 0; w < RS_WARPS; ++w) before += w < (int)warp ? sm.warp_part[w] : 0u;
+    ex = before + inc - sum;
+    sm.digit_start[d_own] = ex;
+  }
+  __syncthreads();
+
+  // ---- keys: registers -> shared (digit order) ---------------------------------------------------------
 #pragma unroll
   for (int i = 0; i < RS_ITEMS; ++i) {
     const unsigned d = (digs[i >> 2] >> (8 * (i & 3))) & 0xffu;
     const uint32_t r = (packed_rank[i >> 1] >> (16 * (i & 1))) & 0xffffu;
-    const uint32_t pos = sm.digit_start[d] + sm.warp_cnt[warp][d] + r;
+    const uint32_t pos = sm.digit_start[d] + my_cnt[d] + r;
     sm.keys[pos] = k[i];
+    if (i & 1) packed_rank[i >> 1] = (packed_rank[i >> 1] & 0xffffu) | (pos << 16);
+    else packed_rank[i >> 1] = (packed_rank[i >> 1] & 0xffff0000u) | pos;
+  }
+  // ---- finish the look-back: exclusive prefix of this digit over the earlier tiles -------------------
+  {
+    uint32_t excl = 0;
+    if (tile != 0) {
+      int64_t j = (int64_t)tile - 1;  // tile whose status lb[0] holds
+      for (;;) {
+        bool done = false;
+#pragma unroll
+        for (int q = 0; q < RS_LOOKBACK; ++q) {
+          if (!done) {
+            uint32_t v = lb[q];
+            if (j - q >= 0) {
+              while (v == 0) v = ld_status(status + (size_t)(j - q) * RADIX + d_own);
+              excl += v & ST_VAL;
+            }
+            done = (v & ST_INCL) != 0;
+          }
+        }
+        if (done) break;
+        j -= RS_LOOKBACK;
+#pragma unroll
+        for (int q = 0; q < RS_LOOKBACK; ++q)
+          lb[q] = j - q >= 0 ? ld_status(status + (size_t)(j - q) * RADIX + d_own) : ST_INCL;
+      }
+      st_status(st_mine, ST_INCL | (excl + real));
+    }
+    sm.glob_base[d_own] = digit_base[d_own] + excl - ex;
   }
   __syncthreads();
+
+  // ---- keys: shared -> global, coalesced per-digit runs ------------------------------------------------
   // element j of the reordered tile names its own digit; the thread keeps it for the value it writes next
   uint32_t out_digs[RS_ITEMS / 4];
 #pragma unroll
@@ -444,22 +499,18 @@ onesweep_kernel(const uint64_t* __restrict__ keys_in, const uint64_t* __restrict
     }
     if (i & 3) out_digs[i >> 2] |= d << (8 * (i & 3)); else out_digs[i >> 2] = d;
   }
-  // ---- values: same permutation -----------------------------------------------------------------------
+  // ---- values: same permutation, staged through the (now free) key buffer ------------------------------
   mbar_wait(&sm.bar_vals, 0);
 #pragma unroll
   for (int i = 0; i < RS_ITEMS; ++i) k[i] = sm.vals[warp_base + i * 32 + lane];
   __syncthreads();
 #pragma unroll
-  for (int i = 0; i < RS_ITEMS; ++i) {
-    const unsigned d = (digs[i >> 2] >> (8 * (i & 3))) & 0xffu;
-    const uint32_t r = (packed_rank[i >> 1] >> (16 * (i & 1))) & 0xffffu;
-    sm.vals[sm.digit_start[d] + sm.warp_cnt[warp][d] + r] = k[i];
-  }
+  for (int i = 0; i < RS_ITEMS; ++i) sm.keys[(packed_rank[i >> 1] >> (16 * (i & 1))) & 0xffffu] = k[i];
   __syncthreads();
 #pragma unroll
   for (int i = 0; i < RS_ITEMS; ++i) {
     const uint32_t j = tid + i * RS_THREADS;
-    if (j < nvalid) vals_out[sm.glob_base[(out_digs[i >> 2] >> (8 * (i & 3))) & 0xffu] + j] = sm.vals[j];
+    if (j < nvalid) vals_out[sm.glob_base[(out_digs[i >> 2] >> (8 * (i & 3))) & 0xffu] + j] = sm.keys[j];
   }
 }
 
