@@ -307,7 +307,7 @@ def main():
     kern_ms = {k_[3:]: v for k_, v in st_mean.items() if k_.startswith("ms_")}
     kernel_of = {"count_partition": "kmer_partition_kernel", "count_kernel": "kmer_upsert_kernel",
                  "correct": "probe_kernel + correct_kernel (reads with errors)",
-                 "sort_radix": "radix_hist_kernel + onesweep_kernel x passes"}
+                 "sort_radix": "radix_hist_kernel + onesweep_kernel x passes", "dedup": "dedup_flag_kernel + scan + compact_pairs_kernel (2 rounds)"}
     # correction = the warp-parallel probe pass over every read + the DFS pass over the reads it could not finish
     kern_ms["correct"] = kern_ms.get("correct_probe", 0.0) + kern_ms.get("correct_kernel", 0.0)
     # algorithmic bytes per launch, as defined in DESIGN.md section 3 (reported by the library per run)
@@ -316,6 +316,7 @@ def main():
         "count_kernel": st_mean.get("alg_bytes_count_kernel", 0.0),
         "correct": st_mean.get("alg_bytes_correct", 0.0),
         "sort_radix": st_mean.get("alg_bytes_sort_radix", 0.0),
+        "dedup": st_mean.get("alg_bytes_dedup", 0.0),
     }
     stages = {}
     for name, b_ in alg.items():

@@ -22,7 +22,7 @@ class BgxError(RuntimeError):
 class Options(C.Structure):
     _fields_ = [("kmer_size", C.c_int32), ("min_kmer_count", C.c_int32), ("max_corrections", C.c_int32),
                 ("min_good_run", C.c_int32), ("trim_after_portion", C.c_float), ("device", C.c_int32),
-                ("sort_key_bits", C.c_int32), ("reserved", C.c_int32)]
+                ("sort_key_bits", C.c_int32), ("count_batch_reads", C.c_int32)]
 
 
 def lib_path():
@@ -171,13 +171,14 @@ class Bgx:
     """One seqset build on one GPU.  Method names follow the reference stages they replace."""
 
     def __init__(self, kmer_size=30, min_kmer_count=5, max_corrections=8, min_good_run=2, trim_after_portion=0.7,
-                 device=0, sort_key_bits=48):
+                 device=0, sort_key_bits=48, count_batch_reads=0):
         self.L = load_library()
         o = Options()
         self.L.bgx_default_options(C.byref(o))
         o.kmer_size, o.min_kmer_count, o.max_corrections = kmer_size, min_kmer_count, max_corrections
         o.min_good_run, o.trim_after_portion, o.device, o.sort_key_bits = min_good_run, trim_after_portion, device, \
             sort_key_bits
+        o.count_batch_reads = count_batch_reads
         self.h = C.c_void_p()
         if self.L.bgx_create(C.byref(o), C.byref(self.h)):
             raise BgxError(self.L.bgx_last_error().decode())

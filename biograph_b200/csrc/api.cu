@@ -106,6 +106,11 @@ int bgx_create(const bgx_options* opts, bgx_ctx** out) {
     bgx_ctx* x = new bgx_ctx();
     x->c.opt = o;
     x->c.device = o.device;
+    {
+      size_t free_b = 0, total_b = 0;
+      BGX_CUDA(cudaMemGetInfo(&free_b, &total_b));
+      x->c.total_mem = total_b;
+    }
     BGX_CUDA(cudaStreamCreateWithFlags(&x->c.stream, cudaStreamNonBlocking));
     *out = x;
   });

@@ -141,6 +141,30 @@ __device__ __forceinline__ uint4 ld_stream_u4(const uint4* p) {
   return r;
 }
 
+// ---- solid k-mer set: open addressing over 32-byte buckets of four 8-byte slots (key | flags) ----
+// One bucket = one DRAM sector = one 256-bit load.  A key lives in the first bucket, walking
+// linearly from its home bucket, that had a free slot when it was inserted; buckets fill in slot
+// order and nothing is ever deleted, so a lookup stops at the first bucket with an empty slot.
+__device__ __forceinline__ void ld_bucket4(const unsigned long long* __restrict__ set, uint64_t bucket,
+                                           unsigned long long (&k)[4]) {
+  asm volatile("ld.global.nc.L1::no_allocate.v4.u64 {%0,%1,%2,%3}, [%4];"
+               : "=l"(k[0]), "=l"(k[1]), "=l"(k[2]), "=l"(k[3])
+               : "l"(set + 4 * bucket));
+}
+// the stored word of `canon` if the bucket holds it, else kEmptyKey; *more = the bucket is full
+// and does not hold it (the key may sit in the next bucket)
+__device__ __forceinline__ unsigned long long bucket4_match(const unsigned long long (&k)[4], uint64_t canon, bool* more) {
+  unsigned long long e = kEmptyKey;
+  bool full = true;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    if (k[i] == kEmptyKey) full = false;
+    else if ((k[i] & kKmerMask) == canon) e = k[i];
+  }
+  *more = full && e == kEmptyKey;
+  return e;
+}
+
 #endif  // __CUDACC__
 
 }  // namespace bgx

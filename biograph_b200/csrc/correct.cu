@@ -55,7 +55,7 @@ struct Params {
   int min_run;
   double trim;
   const unsigned long long* set;
-  uint64_t set_mask;
+  uint64_t set_mask;   // buckets - 1 (a bucket = 4 slots = one 32-byte sector)
 };
 
 // solid mask of one read: bit (p & 31) of word (p >> 5) = the k-mer starting at read position p is
@@ -89,12 +89,14 @@ __device__ __forceinline__ unsigned long long solid_find(const Params& P, uint64
   bool fl;
   uint64_t canon = canonicalize(kmer, P.k, fl);
   *flipped = fl;
-  uint64_t slot = mix64(canon) & P.set_mask;
+  uint64_t b = mix64(canon) & P.set_mask;
   for (;;) {
-    unsigned long long cur = __ldg(&P.set[slot]);
-    if (cur == kEmptyKey) return kEmptyKey;
-    if ((cur & kKmerMask) == canon) return cur;
-    slot = (slot + 1) & P.set_mask;
+    unsigned long long kk[4];
+    ld_bucket4(P.set, b, kk);
+    bool more;
+    const unsigned long long e = bucket4_match(kk, canon, &more);
+    if (!more) return e;
+    b = (b + 1) & P.set_mask;
   }
 }
 __device__ __forceinline__ bool solid_has(const Params& P, uint64_t kmer) {
@@ -238,7 +240,7 @@ constexpr int kProbeThreads = 256;
 constexpr int kProbeWarps = kProbeThreads / 32;
 constexpr int kProbeRPW = 4;
 template <int MAXIT, bool HAS_N>
-__global__ void __launch_bounds__(kProbeThreads) probe_kernel(const uint64_t* __restrict__ words,
+__global__ void __launch_bounds__(kProbeThreads, (MAXIT <= 4 ? 3 : 1)) probe_kernel(const uint64_t* __restrict__ words,
                                                               const uint32_t* __restrict__ nmask,
                                                               const uint32_t* __restrict__ word_off,
                                                               const uint16_t* __restrict__ lens, uint32_t n_reads, Params P,
@@ -273,7 +275,7 @@ __global__ void __launch_bounds__(kProbeThreads) probe_kernel(const uint64_t* __
 
     // ---- all k-mers at once: first probes of every step issued back to back ----------------------
     uint64_t canon[MAXIT], slot[MAXIT];
-    unsigned long long cur[MAXIT];
+    unsigned long long cur[MAXIT][4];   // the home bucket of every k-mer: one 256-bit load each
     bool live[MAXIT], flip[MAXIT];
 #pragma unroll
     for (int it = 0; it < MAXIT; ++it) {
@@ -292,7 +294,8 @@ __global__ void __launch_bounds__(kProbeThreads) probe_kernel(const uint64_t* __
       canon[it] = canonicalize(win >> (64 - 2 * k), k, fl);
       flip[it] = fl;
       slot[it] = mix64(canon[it]) & P.set_mask;
-      cur[it] = live[it] ? __ldg(&P.set[slot[it]]) : kEmptyKey;
+      if (live[it]) ld_bucket4(P.set, slot[it], cur[it]);
+      else cur[it][0] = cur[it][1] = cur[it][2] = cur[it][3] = kEmptyKey;
     }
     uint32_t my_mask = 0;       // lane it keeps the solid mask word of step it
     bool all_solid = nk > 0, any_solid = false;
@@ -300,12 +303,12 @@ __global__ void __launch_bounds__(kProbeThreads) probe_kernel(const uint64_t* __
 #pragma unroll
     for (int it = 0; it < MAXIT; ++it) {
       const int p = it * 32 + (int)lane;
-      unsigned long long e = cur[it];
-      if (live[it]) {
-        while (e != kEmptyKey && (e & kKmerMask) != canon[it]) {
-          slot[it] = (slot[it] + 1) & P.set_mask;
-          e = __ldg(&P.set[slot[it]]);
-        }
+      bool more;
+      unsigned long long e = bucket4_match(cur[it], canon[it], &more);
+      while (live[it] && more) {  // home bucket full without the key: rare at load factor <= 0.71
+        slot[it] = (slot[it] + 1) & P.set_mask;
+        ld_bucket4(P.set, slot[it], cur[it]);
+        e = bucket4_match(cur[it], canon[it], &more);
       }
       const bool found = live[it] && e != kEmptyKey;
       const unsigned bm = __ballot_sync(0xffffffffu, found);
@@ -634,7 +637,7 @@ void stage_correct(Context* c) {
   P.min_run = c->opt.min_good_run;
   P.trim = (double)c->opt.trim_after_portion;  // float widened to double (biograph_create.cpp:489-490,731)
   P.set = c->solid.p;
-  P.set_mask = c->solid_slots - 1;
+  P.set_mask = c->solid_slots / 4 - 1;
   const int max_kmers = std::max<int>((int)c->max_len - P.k + 1, 1);
   const int mask_words = max_kmers <= 128 ? 4 : 8;
   BGX_CHECK(max_kmers <= 256, "read longer than 255 bases");

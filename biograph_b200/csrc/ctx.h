@@ -24,6 +24,7 @@ struct StageTimer {
 struct Context {
   bgx_options opt{};
   int device = 0;
+  size_t total_mem = 0;                    // HBM of the device (read once at creation)
   cudaStream_t stream = nullptr;
   cudaEvent_t t0 = nullptr, t1 = nullptr;  // bgx_timer_start/stop
   Dist dist;                               // multi-GPU: world size, rank, NCCL communicator

@@ -47,7 +47,7 @@ __device__ __forceinline__ uint64_t table_slot(uint64_t h, int log2_slots, int r
 //     bs/kmer_counter.h:297-326: a window containing 'N' is skipped)
 //   * rank within (tile, partition) from a shared-memory histogram, tile staged in partition
 //     order, one global cursor bump per (block, partition), coalesced per-partition runs out
-//   * fused distinct-k-mer estimate: linear counting over the 1/16 of hash space whose low 4
+//   * fused distinct-k-mer estimate: linear counting over the 2^-samp_shift of hash space whose low
 //     hash bits are zero (sizes the table; sampling by hash value is unbiased for distinct counts)
 // Partition p owns out[part_base[p] .. part_base[p] + cap).  cursors[] keep counting past cap, so
 // after an overflowing run they are the exact histogram for the exact re-run.
@@ -58,7 +58,7 @@ kmer_partition_kernel(const uint64_t* __restrict__ words, const uint32_t* __rest
                       int k, int part_bits, unsigned long long* __restrict__ cursors,
                       const unsigned long long* __restrict__ part_base, unsigned long long cap,
                       unsigned long long* __restrict__ out, unsigned int* __restrict__ bitmap, uint64_t bit_mask,
-                      int* __restrict__ overflow) {
+                      int samp_shift, int* __restrict__ overflow) {
   constexpr int kTileReads = kPartWarps * RPW;
   constexpr int kTileKmers = kTileReads * MAXIT * 32;
   constexpr int kWordsPerRead = MAXIT + 1;          // MAXIT*32 k-mers of k<=31 bases span <= MAXIT+1 words
@@ -134,8 +134,8 @@ kmer_partition_kernel(const uint64_t* __restrict__ words, const uint32_t* __rest
             const uint32_t rank = atomicAdd(&hist[bin], 1u);
             code = (bin << 16) | rank;
             word = kmer | (p == 0 ? kPkFirst : 0ULL) | (p == nk - 1 ? kPkLast : 0ULL);
-            if ((h & 15) == 0) {
-              const uint64_t bit = (h >> 4) & bit_mask;
+            if (bitmap != nullptr && (h & ((1ULL << samp_shift) - 1)) == 0) {
+              const uint64_t bit = (h >> samp_shift) & bit_mask;
               atomicOr(&bitmap[bit >> 5], 1u << (bit & 31));  // RED: fire and forget, no read-back stall
             }
           }
@@ -200,6 +200,7 @@ kmer_partition_kernel(const uint64_t* __restrict__ words, const uint32_t* __rest
 // sees the table exactly twice (first touch, final write-back).
 constexpr int kUpsItems = 4;
 constexpr int kUpsTile = 256 * kUpsItems;
+template <bool CAS_FIRST>
 __global__ void __launch_bounds__(256, 4) kmer_upsert_kernel(const unsigned long long* const* __restrict__ part_ptr,
                                                              const unsigned long long* __restrict__ part_count,
                                                              uint32_t tiles_per_part, int k,
@@ -236,13 +237,22 @@ __global__ void __launch_bounds__(256, 4) kmer_upsert_kernel(const unsigned long
     key[i] = valid ? (canon | f) : ~0ULL;
     slot[i] = (uint32_t)table_slot(mix64(canon), log2_slots, rank_bits);
   }
+  if (CAS_FIRST) {
+    // the claim attempt doubles as the read of the slot: one CAS + one RED per instance.  Measured
+    // (tools/micro/l2_atomics, 16 MB slice): failing CAS + RED 88 G/s against load + RED 81 G/s,
+    // and the separate CAS of the first-touch instances (14 % at 0.5 % error) is gone.
 #pragma unroll
-  for (int i = 0; i < kUpsItems; ++i)
-    cur[i] = key[i] != ~0ULL ? *reinterpret_cast<volatile unsigned long long*>(&table[slot[i]].key) : 0ULL;
+    for (int i = 0; i < kUpsItems; ++i)
+      cur[i] = key[i] != ~0ULL ? atomicCAS(&table[slot[i]].key, (unsigned long long)kEmptyKey, key[i]) : 0ULL;
+  } else {
 #pragma unroll
-  for (int i = 0; i < kUpsItems; ++i)
-    if (key[i] != ~0ULL && cur[i] == kEmptyKey)
-      cur[i] = atomicCAS(&table[slot[i]].key, (unsigned long long)kEmptyKey, key[i]);  // returns kEmptyKey when claimed
+    for (int i = 0; i < kUpsItems; ++i)
+      cur[i] = key[i] != ~0ULL ? *reinterpret_cast<volatile unsigned long long*>(&table[slot[i]].key) : 0ULL;
+#pragma unroll
+    for (int i = 0; i < kUpsItems; ++i)
+      if (key[i] != ~0ULL && cur[i] == kEmptyKey)
+        cur[i] = atomicCAS(&table[slot[i]].key, (unsigned long long)kEmptyKey, key[i]);  // returns kEmptyKey when claimed
+  }
 #pragma unroll
   for (int i = 0; i < kUpsItems; ++i) {
     if (key[i] == ~0ULL) continue;
@@ -294,6 +304,49 @@ __global__ void __launch_bounds__(256) kmer_estimate_words_kernel(const unsigned
       atomicOr(&bitmap[bit >> 5], 1u << (bit & 31));
     }
   }
+}
+
+// Distinct estimate straight from the packed reads (batched counting: the table must be sized
+// before the first batch is upserted, so the estimate cannot ride on pass 1).  A warp per read,
+// lane l takes the k-mers l, l+32, ...; same sampling rule as the fused estimate.
+__global__ void __launch_bounds__(256) kmer_estimate_reads_kernel(const uint64_t* __restrict__ words,
+                                                                  const uint32_t* __restrict__ nmask,
+                                                                  const uint32_t* __restrict__ word_off,
+                                                                  const uint16_t* __restrict__ lens, uint32_t n_reads,
+                                                                  int k, unsigned int* __restrict__ bitmap,
+                                                                  uint64_t bit_mask, int samp_shift) {
+  const uint32_t r = blockIdx.x * (256 / 32) + (threadIdx.x >> 5);
+  if (r >= n_reads) return;
+  const unsigned lane = lane_id();
+  const int nk = (int)lens[r] - k + 1;
+  const uint32_t wb = word_off[r];
+  for (int p = (int)lane; p < nk; p += 32) {
+    const int w = p >> 5;
+    const unsigned sft = lane * 2;
+    const uint64_t hi = words[wb + w], lo = words[wb + w + 1];  // the store has one pad word
+    const uint64_t win = sft ? ((hi << sft) | (lo >> (64 - sft))) : hi;
+    if (nmask != nullptr) {
+      const uint32_t mh = nmask[wb + w], ml = nmask[wb + w + 1];
+      const uint32_t mwin = lane ? ((mh << lane) | (ml >> (32 - lane))) : mh;
+      if ((mwin >> (32 - k)) != 0) continue;
+    }
+    bool fl;
+    const uint64_t h = mix64(canonicalize(win >> (64 - 2 * k), k, fl));
+    if ((h & ((1ULL << samp_shift) - 1)) == 0) {
+      const uint64_t bit = (h >> samp_shift) & bit_mask;
+      atomicOr(&bitmap[bit >> 5], 1u << (bit & 31));
+    }
+  }
+}
+
+// out[i] = OR over the N gathered bitmaps (multi-GPU batched counting: union of every rank's sample)
+__global__ void bitmap_or_kernel(const unsigned int* __restrict__ gathered, int n_maps, uint64_t n_words,
+                                 unsigned int* __restrict__ out) {
+  uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n_words) return;
+  unsigned v = 0;
+  for (int m = 0; m < n_maps; ++m) v |= gathered[(uint64_t)m * n_words + i];
+  out[i] = v;
 }
 
 __global__ void popcount_kernel(const unsigned int* __restrict__ w, uint64_t n, unsigned long long* __restrict__ total) {
@@ -384,14 +437,20 @@ __global__ void __launch_bounds__(256) table_sweep_kernel(const CountEntry* __re
   }
 }
 
-// insert into the solid set (8-byte slots).  Keys are distinct, so a plain CAS claim suffices.
+// insert into the solid set (32-byte buckets of four 8-byte slots, common.cuh).  Keys are distinct,
+// so a plain CAS claim suffices; a bucket fills in slot order, a full one sends the key onwards.
 __global__ void solid_insert_kernel(const unsigned long long* __restrict__ keys, uint64_t n,
-                                    unsigned long long* __restrict__ set, uint64_t slot_mask) {
+                                    unsigned long long* __restrict__ set, uint64_t bucket_mask) {
   uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   unsigned long long kf = keys[i];
-  uint64_t slot = mix64(kf & kKmerMask) & slot_mask;
-  while (atomicCAS(&set[slot], (unsigned long long)kEmptyKey, kf) != kEmptyKey) slot = (slot + 1) & slot_mask;
+  uint64_t b = mix64(kf & kKmerMask) & bucket_mask;
+  for (;;) {
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+      if (atomicCAS(&set[4 * b + j], (unsigned long long)kEmptyKey, kf) == kEmptyKey) return;
+    b = (b + 1) & bucket_mask;
+  }
 }
 
 // sort key for export: the canonical k-mer without flag bits; value = index into the compacted list
@@ -428,15 +487,10 @@ uint64_t pow2_ceil(uint64_t x) {
 
 namespace {
 
-struct PartitionLaunch {
-  int maxit, rpw;
-  size_t smem;
-};
-
 template <int MAXIT, int RPW>
-void launch_partition(Context* c, unsigned n_tiles_hint, int part_bits, unsigned long long* cursors,
+void launch_partition(Context* c, uint64_t r0, uint64_t n_reads, int part_bits, unsigned long long* cursors,
                       const unsigned long long* part_base, unsigned long long cap, unsigned long long* out,
-                      unsigned int* bitmap, uint64_t bit_mask, int* overflow) {
+                      unsigned int* bitmap, uint64_t bit_mask, int samp_shift, int* overflow) {
   constexpr int tile_reads = kPartWarps * RPW;
   constexpr int tile_kmers = tile_reads * MAXIT * 32;
   constexpr int wpr = MAXIT + 1;
@@ -454,23 +508,23 @@ void launch_partition(Context* c, unsigned n_tiles_hint, int part_bits, unsigned
                                                          kPartThreads, smem));
   blocks_per_sm = std::max(blocks_per_sm, 1);
   // persistent grid: every SM fully occupied, tiles handed out grid-stride
-  const unsigned n_tiles = (unsigned)((c->n_reads + tile_reads - 1) / tile_reads);
+  const unsigned n_tiles = (unsigned)((n_reads + tile_reads - 1) / tile_reads);
   const unsigned grid = std::min<unsigned>(n_tiles, (unsigned)(kNumSMs * blocks_per_sm));
-  (void)n_tiles_hint;
   note_launch();
+  // a batch is a range of reads: word offsets are absolute, so only the per-read arrays shift
   kmer_partition_kernel<MAXIT, RPW><<<grid, kPartThreads, smem, c->stream>>>(
-      c->words.p, c->has_n ? c->nmask.p : nullptr, c->word_off.p, c->lens.p, (uint32_t)c->n_reads, c->opt.kmer_size,
-      part_bits, cursors, part_base, cap, out, bitmap, bit_mask, overflow);
+      c->words.p, c->has_n ? c->nmask.p : nullptr, c->word_off.p + r0, c->lens.p + r0, (uint32_t)n_reads,
+      c->opt.kmer_size, part_bits, cursors, part_base, cap, out, bitmap, bit_mask, samp_shift, overflow);
   BGX_CUDA(cudaGetLastError());
 }
 
-void run_partition(Context* c, int maxit, unsigned grid, int part_bits, unsigned long long* cursors,
+void run_partition(Context* c, int maxit, uint64_t r0, uint64_t n_reads, int part_bits, unsigned long long* cursors,
                    const unsigned long long* part_base, unsigned long long cap, unsigned long long* out,
-                   unsigned int* bitmap, uint64_t bit_mask, int* overflow) {
+                   unsigned int* bitmap, uint64_t bit_mask, int samp_shift, int* overflow) {
   if (maxit <= 4)
-    launch_partition<4, 4>(c, grid, part_bits, cursors, part_base, cap, out, bitmap, bit_mask, overflow);
+    launch_partition<4, 4>(c, r0, n_reads, part_bits, cursors, part_base, cap, out, bitmap, bit_mask, samp_shift, overflow);
   else
-    launch_partition<8, 2>(c, grid, part_bits, cursors, part_base, cap, out, bitmap, bit_mask, overflow);
+    launch_partition<8, 2>(c, r0, n_reads, part_bits, cursors, part_base, cap, out, bitmap, bit_mask, samp_shift, overflow);
 }
 
 int log2_exact(uint64_t x) {
@@ -479,101 +533,122 @@ int log2_exact(uint64_t x) {
   return l;
 }
 
-}  // namespace
+// the linear-counting sample: bit (h >> shift) & (bits - 1) of the bitmap for hashes with `shift` low zero bits
+struct Estimator {
+  DevBuf<unsigned int> bitmap;
+  DevBuf<unsigned long long> ones;
+  uint64_t bits = 0;
+  int shift = 4;
+  void init(uint64_t bits_, int shift_, cudaStream_t s) {
+    bits = bits_;
+    shift = shift_;
+    bitmap.alloc(bits / 32, s);
+    ones.alloc(1, s);
+    BGX_CUDA(cudaMemsetAsync(bitmap.p, 0, bits / 8, s));
+  }
+  // number of distinct k-mers the sample stands for (synchronises the stream)
+  uint64_t estimate(cudaStream_t s) {
+    unsigned long long h_ones = 0;
+    BGX_CUDA(cudaMemsetAsync(ones.p, 0, 8, s));
+    KLAUNCH(popcount_kernel)<<<(unsigned)((bits / 32 + 255) / 256), 256, 0, s>>>(bitmap.p, bits / 32, ones.p);
+    BGX_CUDA(cudaGetLastError());
+    BGX_CUDA(cudaMemcpyAsync(&h_ones, ones.p, 8, cudaMemcpyDeviceToHost, s));
+    BGX_CUDA(cudaStreamSynchronize(s));
+    const double zero_frac = std::max(1.0 / (double)bits, 1.0 - (double)h_ones / (double)bits);
+    return (uint64_t)((double)(1ULL << shift) * -(double)bits * std::log(zero_frac));
+  }
+};
 
-void stage_count_kmers(Context* c) {
+// pass-1 output for a range of reads
+struct Partitioned {
+  DevBuf<unsigned long long> pk;
+  std::vector<unsigned long long> base, count;  // per partition: first word, words
+  unsigned long long cap = 0;                   // stride between partitions unless `exact`
+  bool exact = false;                           // re-run with exact offsets (a heavy hitter overfilled a partition)
+};
+
+// Pass 1 over reads [r0, r0 + n): K = their k-mer instances.  est (optional) receives the fused sample.
+void partition_reads(Context* c, uint64_t r0, uint64_t n, uint64_t K, int part_bits, int maxit, Estimator* est,
+                     Partitioned* out) {
   cudaStream_t s = c->stream;
-  const int k = c->opt.kmer_size;
-  const int N = c->dist.nranks, R = c->dist.rank;
-  const int rank_bits = log2_exact((uint64_t)N);
-  BGX_CHECK(c->n_reads > 0 || N > 1, "bgx_count_kmers: no reads");
-  ScopedStage st_all(c, "count_total");
-  const uint64_t K = c->n_kmer_instances;  // this rank's reads
-  uint64_t K_all = K;                      // all ranks' reads
-  dist_allreduce_sum_host_u64(c, &K_all, 1);
-  const uint64_t K_share = K_all / N;      // instances this rank will own (hash-uniform)
-
-  // ---- pass 1: extract + hash-partition every k-mer instance; fused distinct estimate -------------
-  // P partitions so that one partition's slice of the owner's table (~4 B per instance at typical
-  // coverage) is at most ~64 MB = half of L2; measured on B200: fewer, larger partitions make
-  // pass 1 faster (longer coalesced runs) and pass 2 is insensitive down to 64 MB slices.
-  // Rank r owns the contiguous block of partitions [r*P/N, (r+1)*P/N) (same P on every rank).
-  int part_bits = 7;
-  while (part_bits < kMaxPartBits && (K_all * 4 >> part_bits) > (64ull << 20)) ++part_bits;
-  if (const char* e = getenv("BGX_PART_BITS")) part_bits = std::max(1, std::min(kMaxPartBits, atoi(e)));
-  part_bits = std::max(part_bits, rank_bits);
   const int P = 1 << part_bits;
-  const int maxit = (int)((std::max<int64_t>((int64_t)c->max_len - k + 1, 1) + 31) / 32);
-  BGX_CHECK(maxit <= 8, "read longer than 255 bases");
   unsigned long long cap = K / P + K / (8ull * P) + 4096;  // hash partitions are near uniform
   ScopedStage st_alloc(c, "count_setup");
-  DevBuf<unsigned long long> pk((size_t)cap * P, s), cursors(P, s), part_base(P, s);
-  std::vector<unsigned long long> h_base(P), h_count(P);
-  for (int p = 0; p < P; ++p) h_base[p] = (unsigned long long)p * cap;
-  BGX_CUDA(cudaMemcpyAsync(part_base.p, h_base.data(), P * 8, cudaMemcpyHostToDevice, s));
+  out->pk.alloc((size_t)cap * P, s);
+  DevBuf<unsigned long long> cursors(P, s), part_base(P, s);
+  out->base.assign(P, 0);
+  out->count.assign(P, 0);
+  for (int p = 0; p < P; ++p) out->base[p] = (unsigned long long)p * cap;
+  BGX_CUDA(cudaMemcpyAsync(part_base.p, out->base.data(), P * 8, cudaMemcpyHostToDevice, s));
   BGX_CUDA(cudaMemsetAsync(cursors.p, 0, P * 8, s));
   DevBuf<int> overflow(1, s);
   BGX_CUDA(cudaMemsetAsync(overflow.p, 0, sizeof(int), s));
-  const uint64_t bits = pow2_ceil(std::max<uint64_t>(1 << 20, std::max(K, K_share) / 8));
-  DevBuf<unsigned int> bitmap(bits / 32, s);
-  DevBuf<unsigned long long> ones(1, s);
-  BGX_CUDA(cudaMemsetAsync(bitmap.p, 0, bits / 8, s));
-  BGX_CUDA(cudaMemsetAsync(ones.p, 0, 8, s));
-  unsigned long long h_ones = 0;
   int h_over = 0;
-  bool reran = false;
   st_alloc.stop();
-  {
-    ScopedStage st(c, "count_partition");
-    if (c->n_reads) run_partition(c, maxit, 0, part_bits, cursors.p, part_base.p, cap, pk.p, bitmap.p, bits - 1, overflow.p);
-    if (N == 1) KLAUNCH(popcount_kernel)<<<(unsigned)((bits / 32 + 255) / 256), 256, 0, s>>>(bitmap.p, bits / 32, ones.p);
-    BGX_CUDA(cudaGetLastError());
-    BGX_CUDA(cudaMemcpyAsync(&h_ones, ones.p, 8, cudaMemcpyDeviceToHost, s));
-    BGX_CUDA(cudaMemcpyAsync(&h_over, overflow.p, sizeof(int), cudaMemcpyDeviceToHost, s));
-    BGX_CUDA(cudaMemcpyAsync(h_count.data(), cursors.p, P * 8, cudaMemcpyDeviceToHost, s));
-    BGX_CUDA(cudaStreamSynchronize(s));
-    if (h_over) {
-      // a heavy-hitter k-mer overfilled its partition: the cursors are now the exact histogram,
-      // so re-run with exact offsets (the reference has no analogue; its tables are sized up front)
-      uint64_t total = 0;
-      cap = 0;
-      for (int p = 0; p < P; ++p) { h_base[p] = total; total += h_count[p]; cap = std::max<unsigned long long>(cap, h_count[p]); }
-      pk.alloc(std::max<uint64_t>(total, 1), s);
-      BGX_CUDA(cudaMemcpyAsync(part_base.p, h_base.data(), P * 8, cudaMemcpyHostToDevice, s));
-      BGX_CUDA(cudaMemsetAsync(cursors.p, 0, P * 8, s));
-      BGX_CUDA(cudaMemsetAsync(overflow.p, 0, sizeof(int), s));
-      BGX_CUDA(cudaMemsetAsync(bitmap.p, 0, bits / 8, s));
-      BGX_CUDA(cudaMemsetAsync(ones.p, 0, 8, s));
-      run_partition(c, maxit, 0, part_bits, cursors.p, part_base.p, cap, pk.p, bitmap.p, bits - 1, overflow.p);
-      if (N == 1) KLAUNCH(popcount_kernel)<<<(unsigned)((bits / 32 + 255) / 256), 256, 0, s>>>(bitmap.p, bits / 32, ones.p);
-      BGX_CUDA(cudaMemcpyAsync(&h_ones, ones.p, 8, cudaMemcpyDeviceToHost, s));
-      BGX_CUDA(cudaMemcpyAsync(&h_over, overflow.p, sizeof(int), cudaMemcpyDeviceToHost, s));
-      BGX_CUDA(cudaStreamSynchronize(s));
-      BGX_CHECK(!h_over, "internal: exact partition pass overflowed");
-      c->add_stat("count_partition_reruns", 1);
-      reran = true;
+  ScopedStage st(c, "count_partition");
+  unsigned int* bitmap = est ? est->bitmap.p : nullptr;
+  const uint64_t bit_mask = est ? est->bits - 1 : 0;
+  const int shift = est ? est->shift : 4;
+  if (n) run_partition(c, maxit, r0, n, part_bits, cursors.p, part_base.p, cap, out->pk.p, bitmap, bit_mask, shift, overflow.p);
+  BGX_CUDA(cudaMemcpyAsync(&h_over, overflow.p, sizeof(int), cudaMemcpyDeviceToHost, s));
+  BGX_CUDA(cudaMemcpyAsync(out->count.data(), cursors.p, P * 8, cudaMemcpyDeviceToHost, s));
+  BGX_CUDA(cudaStreamSynchronize(s));
+  out->cap = cap;
+  out->exact = false;
+  if (h_over) {
+    // a heavy-hitter k-mer overfilled its partition: the cursors are now the exact histogram,
+    // so re-run with exact offsets (the reference has no analogue; its tables are sized up front).
+    // The sample bitmap is only OR-ed into, so the second run leaves it as it is.
+    uint64_t total = 0;
+    cap = 0;
+    for (int p = 0; p < P; ++p) {
+      out->base[p] = total;
+      total += out->count[p];
+      cap = std::max<unsigned long long>(cap, out->count[p]);
     }
-    st.stop();
+    out->pk.alloc(std::max<uint64_t>(total, 1), s);
+    BGX_CUDA(cudaMemcpyAsync(part_base.p, out->base.data(), P * 8, cudaMemcpyHostToDevice, s));
+    BGX_CUDA(cudaMemsetAsync(cursors.p, 0, P * 8, s));
+    BGX_CUDA(cudaMemsetAsync(overflow.p, 0, sizeof(int), s));
+    run_partition(c, maxit, r0, n, part_bits, cursors.p, part_base.p, cap, out->pk.p, bitmap, bit_mask, shift, overflow.p);
+    BGX_CUDA(cudaMemcpyAsync(&h_over, overflow.p, sizeof(int), cudaMemcpyDeviceToHost, s));
+    BGX_CUDA(cudaStreamSynchronize(s));
+    BGX_CHECK(!h_over, "internal: exact partition pass overflowed");
+    c->add_stat("count_partition_reruns", 1);
+    out->cap = cap;
+    out->exact = true;
   }
+  st.stop();
+}
 
-  // ---- the partitions this rank will count: (device address, instance count) each ----------------
-  // Single GPU: the P partitions where pass 1 left them.  Multi-GPU: every partition goes to its
-  // owner over NVLink; partition p of source rank s arrives as its own "virtual partition", listed
-  // partition-major so pass 2 still walks the table slice by slice.
-  std::vector<unsigned long long> v_ptr, v_cnt;
-  DevBuf<unsigned long long> rbuf;
+// the partitions this rank will count: (device address, instance count) each
+struct Owned {
+  std::vector<unsigned long long> ptr, cnt;
+  DevBuf<unsigned long long> rbuf;  // what arrived from the peers
+  uint64_t n_inst = 0;
+};
+
+// Single GPU: the P partitions where pass 1 left them.  Multi-GPU: every partition goes to its
+// owner over NVLink; partition p of source rank s arrives as its own "virtual partition", listed
+// partition-major so pass 2 still walks the table slice by slice.
+void exchange_partitions(Context* c, const Partitioned& pt, int P, Owned* own) {
+  cudaStream_t s = c->stream;
+  const int N = c->dist.nranks, R = c->dist.rank;
+  own->ptr.clear();
+  own->cnt.clear();
   if (N == 1) {
     for (int p = 0; p < P; ++p) {
-      v_ptr.push_back((unsigned long long)(uintptr_t)(pk.p + h_base[p]));
-      v_cnt.push_back(h_count[p]);
+      own->ptr.push_back((unsigned long long)(uintptr_t)(pt.pk.p + pt.base[p]));
+      own->cnt.push_back(pt.count[p]);
     }
   } else {
     ScopedStage st(c, "count_exchange");
     const int Pl = P / N, p0 = R * Pl;
+    const unsigned long long cap = pt.cap;
     std::vector<uint64_t> mine(P + 2), all((size_t)N * (P + 2));
-    for (int p = 0; p < P; ++p) mine[p] = h_count[p];
+    for (int p = 0; p < P; ++p) mine[p] = pt.count[p];
     mine[P] = cap;
-    mine[P + 1] = reran ? 1 : 0;  // exact layout: not cap-strided
+    mine[P + 1] = pt.exact ? 1 : 0;  // exact layout: not cap-strided
     dist_allgather_host_u64(c, mine.data(), P + 2, all.data());
     auto cnt_of = [&](int src, int p) { return all[(size_t)src * (P + 2) + p]; };
     bool strided = true;
@@ -589,15 +664,15 @@ void stage_count_kmers(Context* c) {
         src_off[src] = total;
         total += (uint64_t)Pl * all[(size_t)src * (P + 2) + P];
       }
-      rbuf.alloc(std::max<uint64_t>(total, 1), s);
+      own->rbuf.alloc(std::max<uint64_t>(total, 1), s);
       for (int d = 0; d < N; ++d) {
         if (d == R) continue;
         P2P x, y;
-        x.send = pk.p + (uint64_t)d * Pl * cap;
+        x.send = pt.pk.p + (uint64_t)d * Pl * cap;
         x.bytes = (size_t)Pl * cap * 8;
         x.peer = d;
         sends.push_back(x);
-        y.recv = rbuf.p + src_off[d];
+        y.recv = own->rbuf.p + src_off[d];
         y.bytes = (size_t)Pl * all[(size_t)d * (P + 2) + P] * 8;
         y.peer = d;
         recvs.push_back(y);
@@ -605,23 +680,25 @@ void stage_count_kmers(Context* c) {
       for (int pl = 0; pl < Pl; ++pl)
         for (int src = 0; src < N; ++src) {
           const uint64_t cap_s = all[(size_t)src * (P + 2) + P];
-          const unsigned long long* ptr = src == R ? pk.p + (uint64_t)(p0 + pl) * cap : rbuf.p + src_off[src] + (uint64_t)pl * cap_s;
-          v_ptr.push_back((unsigned long long)(uintptr_t)ptr);
-          v_cnt.push_back(cnt_of(src, p0 + pl));
+          const unsigned long long* ptr =
+              src == R ? pt.pk.p + (uint64_t)(p0 + pl) * cap : own->rbuf.p + src_off[src] + (uint64_t)pl * cap_s;
+          own->ptr.push_back((unsigned long long)(uintptr_t)ptr);
+          own->cnt.push_back(cnt_of(src, p0 + pl));
         }
     } else {
-      // general path (some rank re-ran pass 1 with exact offsets): one message per partition
+      // general path (some rank re-ran pass 1 with exact offsets): one message per partition.
+      // A rank that did NOT re-run still holds its partitions cap-strided: base[p] says where.
       uint64_t total = 0;
       std::vector<uint64_t> l_base(Pl);
       for (int pl = 0; pl < Pl; ++pl) {
         l_base[pl] = total;
         for (int src = 0; src < N; ++src) total += cnt_of(src, p0 + pl);
       }
-      rbuf.alloc(std::max<uint64_t>(total, 1), s);
+      own->rbuf.alloc(std::max<uint64_t>(total, 1), s);
       for (int p = 0; p < P; ++p) {
         P2P x;
-        x.send = pk.p + h_base[p];
-        x.bytes = (size_t)h_count[p] * 8;
+        x.send = pt.pk.p + pt.base[p];
+        x.bytes = (size_t)pt.count[p] * 8;
         x.peer = p / Pl;
         sends.push_back(x);
       }
@@ -631,7 +708,7 @@ void stage_count_kmers(Context* c) {
           uint64_t off = l_base[pl];
           for (int q = 0; q < src; ++q) off += cnt_of(q, p0 + pl);
           P2P x;
-          x.recv = rbuf.p + off;
+          x.recv = own->rbuf.p + off;
           x.bytes = (size_t)cnt_of(src, p0 + pl) * 8;
           x.peer = src;
           recvs.push_back(x);
@@ -639,8 +716,8 @@ void stage_count_kmers(Context* c) {
       for (int pl = 0; pl < Pl; ++pl) {
         uint64_t cnt = 0;
         for (int src = 0; src < N; ++src) cnt += cnt_of(src, p0 + pl);
-        v_ptr.push_back((unsigned long long)(uintptr_t)(rbuf.p + l_base[pl]));
-        v_cnt.push_back(cnt);
+        own->ptr.push_back((unsigned long long)(uintptr_t)(own->rbuf.p + l_base[pl]));
+        own->cnt.push_back(cnt);
       }
     }
     dist_p2p_batch(c, sends, recvs);
@@ -650,64 +727,220 @@ void stage_count_kmers(Context* c) {
     c->add_stat("count_exchange_bytes_out", (double)out_bytes);
     st.stop();
   }
-  const uint32_t V = (uint32_t)v_ptr.size();
-  DevBuf<unsigned long long> d_ptr(V, s), d_cnt(V, s);
-  BGX_CUDA(cudaMemcpyAsync(d_ptr.p, v_ptr.data(), V * 8, cudaMemcpyHostToDevice, s));
-  BGX_CUDA(cudaMemcpyAsync(d_cnt.p, v_cnt.data(), V * 8, cudaMemcpyHostToDevice, s));
-  uint64_t n_inst = 0, max_count = 0;
-  for (uint32_t p = 0; p < V; ++p) { n_inst += v_cnt[p]; max_count = std::max<uint64_t>(max_count, v_cnt[p]); }
-  const uint32_t tiles_per_part = (uint32_t)std::max<uint64_t>(1, (max_count + kUpsTile - 1) / kUpsTile);
-  BGX_CHECK((uint64_t)tiles_per_part * V < (1ull << 31), "too many k-mer tiles for one launch");
-  const unsigned long long* const* part_ptr = reinterpret_cast<const unsigned long long* const*>(d_ptr.p);
-  if (N > 1) {
-    // the owner estimates the distinct count of what it received (pass 1 filled the bitmap with
-    // this rank's own reads over the whole hash space: start over)
-    BGX_CUDA(cudaMemsetAsync(bitmap.p, 0, bits / 8, s));
-    KLAUNCH(kmer_estimate_words_kernel)<<<tiles_per_part * V, 256, 0, s>>>(part_ptr, d_cnt.p, tiles_per_part, k, bitmap.p,
-                                                                    bits - 1);
-    KLAUNCH(popcount_kernel)<<<(unsigned)((bits / 32 + 255) / 256), 256, 0, s>>>(bitmap.p, bits / 32, ones.p);
-    BGX_CUDA(cudaGetLastError());
-    BGX_CUDA(cudaMemcpyAsync(&h_ones, ones.p, 8, cudaMemcpyDeviceToHost, s));
-    BGX_CUDA(cudaStreamSynchronize(s));
-  }
+  own->n_inst = 0;
+  for (unsigned long long v : own->cnt) own->n_inst += v;
+}
 
-  // ---- size the table: load factor in (1/3, 2/3] of the estimated distinct count -----------------
-  const double zero_frac = std::max(1.0 / (double)bits, 1.0 - (double)h_ones / (double)bits);
-  uint64_t est_distinct = (uint64_t)(16.0 * -(double)bits * std::log(zero_frac));
-  est_distinct = std::min<uint64_t>(est_distinct + est_distinct / 16 + 4096, n_inst + 1);
-  c->set_stat("kmer_distinct_estimate", (double)est_distinct);
+// device-side view of an Owned list, ready for the tile kernels
+struct OwnedDev {
+  DevBuf<unsigned long long> ptr, cnt;
+  uint32_t V = 0, tiles_per_part = 1;
+  const unsigned long long* const* part_ptr() const { return reinterpret_cast<const unsigned long long* const*>(ptr.p); }
+};
+
+void upload_owned(Context* c, const Owned& own, OwnedDev* d) {
+  cudaStream_t s = c->stream;
+  d->V = (uint32_t)own.ptr.size();
+  d->ptr.alloc(d->V, s);
+  d->cnt.alloc(d->V, s);
+  BGX_CUDA(cudaMemcpyAsync(d->ptr.p, own.ptr.data(), d->V * 8, cudaMemcpyHostToDevice, s));
+  BGX_CUDA(cudaMemcpyAsync(d->cnt.p, own.cnt.data(), d->V * 8, cudaMemcpyHostToDevice, s));
+  uint64_t max_count = 0;
+  for (unsigned long long v : own.cnt) max_count = std::max<uint64_t>(max_count, v);
+  d->tiles_per_part = (uint32_t)std::max<uint64_t>(1, (max_count + kUpsTile - 1) / kUpsTile);
+  BGX_CHECK((uint64_t)d->tiles_per_part * d->V < (1ull << 31), "too many k-mer tiles for one launch");
+  // the host vectors must outlive the copies
+  BGX_CUDA(cudaStreamSynchronize(s));
+}
+
+// table slots for an estimated distinct count: load factor in (1/3, 2/3]
+uint64_t slots_for(uint64_t est_distinct) {
   uint64_t slots = pow2_ceil(std::max<uint64_t>(1024, est_distinct + est_distinct / 2));
   if (const char* e = getenv("BGX_TABLE_SLOTS_LOG2")) slots = 1ull << atoi(e);  // experiment hook
-  int tries = 0;
-  for (;;) {
-    ScopedStage st_sz(c, "count_table_alloc");
-    BGX_CHECK(slots <= (1ull << 32), "k-mer table too large for one GPU shard (slot index is 32-bit)");
-    c->table_slots = slots;
-    c->table.alloc(slots, s);  // throws "out of device memory" if the table cannot fit
-    st_sz.stop();
-    {
-      ScopedStage st(c, "count_init");
-      KLAUNCH(fill_empty_kernel)<<<(unsigned)((slots + 255) / 256), 256, 0, s>>>(reinterpret_cast<uint4*>(c->table.p), slots);
-      st.stop();
-    }
-    BGX_CUDA(cudaMemsetAsync(overflow.p, 0, sizeof(int), s));
-    {
-      ScopedStage st(c, "count_kernel");
-      KLAUNCH(kmer_upsert_kernel)<<<tiles_per_part * V, 256, 0, s>>>(part_ptr, d_cnt.p, tiles_per_part, k, c->table.p,
-                                                              log2_exact(slots), rank_bits, overflow.p);
-      BGX_CUDA(cudaGetLastError());
-      st.stop();
-    }
-    BGX_CUDA(cudaMemcpyAsync(&h_over, overflow.p, sizeof(int), cudaMemcpyDeviceToHost, s));
-    BGX_CUDA(cudaStreamSynchronize(s));
-    if (!h_over) break;
-    // estimate was off (cannot happen for slots > distinct; belt and braces): double and redo.
-    // The reference throws io_exception("Kmer table (...) too small") (bs/kmer_count_table.h:75).
-    BGX_CHECK(++tries < 4, "Kmer table too small");
-    slots *= 2;
+  return slots;
+}
+
+void alloc_table(Context* c, uint64_t slots) {
+  cudaStream_t s = c->stream;
+  ScopedStage st_sz(c, "count_table_alloc");
+  BGX_CHECK(slots <= (1ull << 32), "k-mer table too large for one GPU shard (slot index is 32-bit)");
+  c->table_slots = slots;
+  c->table.alloc(slots, s);  // throws "out of device memory" if the table cannot fit
+  st_sz.stop();
+  ScopedStage st(c, "count_init");
+  KLAUNCH(fill_empty_kernel)<<<(unsigned)((slots + 255) / 256), 256, 0, s>>>(reinterpret_cast<uint4*>(c->table.p), slots);
+  BGX_CUDA(cudaGetLastError());
+  st.stop();
+}
+
+void upsert_owned(Context* c, const OwnedDev& od, int rank_bits, int* overflow) {
+  ScopedStage st(c, "count_kernel");
+  static const bool cas_first = [] { const char* e = getenv("BGX_UPSERT_CAS_FIRST"); return e ? atoi(e) != 0 : true; }();  // experiment hook
+  note_launch();
+  if (cas_first)
+    kmer_upsert_kernel<true><<<od.tiles_per_part * od.V, 256, 0, c->stream>>>(
+        od.part_ptr(), od.cnt.p, od.tiles_per_part, c->opt.kmer_size, c->table.p, log2_exact(c->table_slots), rank_bits, overflow);
+  else
+    kmer_upsert_kernel<false><<<od.tiles_per_part * od.V, 256, 0, c->stream>>>(
+      od.part_ptr(), od.cnt.p, od.tiles_per_part, c->opt.kmer_size, c->table.p, log2_exact(c->table_slots), rank_bits, overflow);
+  BGX_CUDA(cudaGetLastError());
+  st.stop();
+}
+
+int read_flag(const int* d, cudaStream_t s) {
+  int h = 0;
+  BGX_CUDA(cudaMemcpyAsync(&h, d, sizeof(int), cudaMemcpyDeviceToHost, s));
+  BGX_CUDA(cudaStreamSynchronize(s));
+  return h;
+}
+
+// How many batches of reads pass 1 + pass 2 run in.  One batch keeps all K instance words (and,
+// multi-GPU, what the peers send) in HBM next to the table; the batched form bounds those buffers
+// to ~40 % of the device so that inputs like GRCh38 30x on 8 GPUs (84 + 66 GB of words per GPU
+// next to a 69 GB table) still fit.  Every rank must use the same count (each batch is a
+// collective exchange).
+uint64_t choose_batches(Context* c, uint64_t K_local, uint64_t K_share) {
+  const int N = c->dist.nranks;
+  uint64_t batches = 1;
+  uint64_t batch_reads = c->opt.count_batch_reads > 0 ? (uint64_t)c->opt.count_batch_reads : 0;
+  if (const char* e = getenv("BGX_COUNT_BATCH_READS")) batch_reads = strtoull(e, nullptr, 10);  // test hook
+  if (batch_reads) {
+    batches = std::max<uint64_t>(1, (c->n_reads + batch_reads - 1) / batch_reads);
+  } else {
+    const double budget = 0.4 * (double)c->total_mem;
+    const double need = 9.0 * (double)K_local + (N > 1 ? 9.0 * (double)K_share : 0.0);  // 8 B per word + 1/8 slack
+    batches = std::max<uint64_t>(1, (uint64_t)std::ceil(need / budget));
   }
-  pk.release();
-  rbuf.release();
+  if (N > 1) {
+    std::vector<uint64_t> all(N);
+    dist_allgather_host_u64(c, &batches, 1, all.data());
+    for (uint64_t v : all) batches = std::max(batches, v);
+  }
+  return batches;
+}
+
+}  // namespace
+
+void stage_count_kmers(Context* c) {
+  cudaStream_t s = c->stream;
+  const int k = c->opt.kmer_size;
+  const int N = c->dist.nranks;
+  const int rank_bits = log2_exact((uint64_t)N);
+  BGX_CHECK(c->n_reads > 0 || N > 1, "bgx_count_kmers: no reads");
+  ScopedStage st_all(c, "count_total");
+  const uint64_t K = c->n_kmer_instances;  // this rank's reads
+  uint64_t K_all = K;                      // all ranks' reads
+  dist_allreduce_sum_host_u64(c, &K_all, 1);
+  const uint64_t K_share = K_all / N;      // instances this rank will own (hash-uniform)
+
+  // P partitions so that one partition's slice of the owner's table (~4 B per instance at typical
+  // coverage) is at most ~64 MB = half of L2; measured on B200: fewer, larger partitions make
+  // pass 1 faster (longer coalesced runs) and pass 2 is insensitive down to 64 MB slices.
+  // Rank r owns the contiguous block of partitions [r*P/N, (r+1)*P/N) (same P on every rank).
+  int part_bits = 7;
+  while (part_bits < kMaxPartBits && (K_all * 4 >> part_bits) > (64ull << 20)) ++part_bits;
+  if (const char* e = getenv("BGX_PART_BITS")) part_bits = std::max(1, std::min(kMaxPartBits, atoi(e)));
+  part_bits = std::max(part_bits, rank_bits);
+  const int P = 1 << part_bits;
+  const int maxit = (int)((std::max<int64_t>((int64_t)c->max_len - k + 1, 1) + 31) / 32);
+  BGX_CHECK(maxit <= 8, "read longer than 255 bases");
+  const uint64_t batches = choose_batches(c, K, K_share);
+  c->set_stat("count_batches", (double)batches);
+  DevBuf<int> overflow(1, s);
+  uint64_t n_inst = 0;   // instances this rank counted
+  uint64_t slots = 0;
+
+  if (batches == 1) {
+    // ---- everything at once: pass 1 carries the distinct estimate, then the table is sized ---------
+    Estimator est;
+    est.init(pow2_ceil(std::max<uint64_t>(1 << 20, std::max(K, K_share) / 8)), 4, s);
+    Partitioned pt;
+    partition_reads(c, 0, c->n_reads, K, part_bits, maxit, &est, &pt);
+    Owned own;
+    exchange_partitions(c, pt, P, &own);
+    OwnedDev od;
+    upload_owned(c, own, &od);
+    n_inst = own.n_inst;
+    if (N > 1) {
+      // the owner estimates the distinct count of what it received (pass 1 filled the bitmap with
+      // this rank's own reads over the whole hash space: start over)
+      BGX_CUDA(cudaMemsetAsync(est.bitmap.p, 0, est.bits / 8, s));
+      KLAUNCH(kmer_estimate_words_kernel)<<<od.tiles_per_part * od.V, 256, 0, s>>>(od.part_ptr(), od.cnt.p, od.tiles_per_part, k,
+                                                                           est.bitmap.p, est.bits - 1);
+      BGX_CUDA(cudaGetLastError());
+    }
+    uint64_t est_distinct = est.estimate(s);
+    est_distinct = std::min<uint64_t>(est_distinct + est_distinct / 16 + 4096, n_inst + 1);
+    c->set_stat("kmer_distinct_estimate", (double)est_distinct);
+    slots = slots_for(est_distinct);
+    for (int tries = 0;; ++tries) {
+      alloc_table(c, slots);
+      BGX_CUDA(cudaMemsetAsync(overflow.p, 0, sizeof(int), s));
+      upsert_owned(c, od, rank_bits, overflow.p);
+      if (!read_flag(overflow.p, s)) break;
+      // estimate was off (cannot happen for slots > distinct; belt and braces): double and redo.
+      // The reference throws io_exception("Kmer table (...) too small") (bs/kmer_count_table.h:75).
+      BGX_CHECK(tries < 3, "Kmer table too small");
+      slots *= 2;
+    }
+  } else {
+    // ---- batched: estimate from the reads first, then partition / exchange / upsert batch by batch ---
+    Estimator est;
+    {
+      ScopedStage st(c, "count_estimate");
+      // sample so thinly that at most ~2^29 instances are expected in it; the bitmap has twice as many bits
+      int shift = 4;
+      while ((K_all >> shift) > (1ull << 29)) ++shift;
+      est.init(pow2_ceil(std::max<uint64_t>(1 << 20, (K_all >> shift) * 2)), shift, s);
+      if (c->n_reads)
+        KLAUNCH(kmer_estimate_reads_kernel)<<<(unsigned)((c->n_reads + 7) / 8), 256, 0, s>>>(
+            c->words.p, c->has_n ? c->nmask.p : nullptr, c->word_off.p, c->lens.p, (uint32_t)c->n_reads, k, est.bitmap.p,
+            est.bits - 1, est.shift);
+      BGX_CUDA(cudaGetLastError());
+      if (N > 1) {
+        // union of every rank's sample; an owner then holds 1/N of the distinct k-mers (hash-uniform)
+        DevBuf<unsigned int> gathered((size_t)N * (est.bits / 32), s);
+        dist_allgather_bytes(c, est.bitmap.p, gathered.p, est.bits / 8);
+        KLAUNCH(bitmap_or_kernel)<<<(unsigned)((est.bits / 32 + 255) / 256), 256, 0, s>>>(gathered.p, N, est.bits / 32, est.bitmap.p);
+        BGX_CUDA(cudaGetLastError());
+      }
+      st.stop();
+    }
+    uint64_t est_distinct = est.estimate(s) / N;
+    est_distinct = est_distinct + est_distinct / 16 + 4096;
+    c->set_stat("kmer_distinct_estimate", (double)est_distinct);
+    est.bitmap.release();
+    slots = slots_for(est_distinct);
+    // per-read instance counts are not kept on the host: a batch's K is bounded by its share of the bases
+    for (int tries = 0;; ++tries) {
+      alloc_table(c, slots);
+      BGX_CUDA(cudaMemsetAsync(overflow.p, 0, sizeof(int), s));
+      n_inst = 0;
+      bool over = false;
+      for (uint64_t b = 0; b < batches && !over; ++b) {
+        const uint64_t r0 = c->n_reads * b / batches, r1 = c->n_reads * (b + 1) / batches;
+        // instances of the batch: at most (max_len - k + 1) per read
+        const uint64_t Kb = std::min<uint64_t>(K, (r1 - r0) * (uint64_t)std::max<int64_t>((int64_t)c->max_len - k + 1, 0));
+        Partitioned pt;
+        partition_reads(c, r0, r1 - r0, Kb, part_bits, maxit, nullptr, &pt);
+        Owned own;
+        exchange_partitions(c, pt, P, &own);
+        OwnedDev od;
+        upload_owned(c, own, &od);
+        n_inst += own.n_inst;
+        upsert_owned(c, od, rank_bits, overflow.p);
+        over = read_flag(overflow.p, s) != 0;  // also: the batch's buffers are free to go
+      }
+      if (N > 1) {  // every rank must take the same branch: the batches are collective
+        uint64_t any = over ? 1 : 0;
+        dist_allreduce_sum_host_u64(c, &any, 1);
+        over = any != 0;
+      }
+      if (!over) break;
+      BGX_CHECK(tries < 3, "Kmer table too small");
+      slots *= 2;
+    }
+  }
 
   // filter (kmer_passes: fwd+rev >= min_count) and build the solid set: ONE sweep into buffers
   // sized by the bound #solid <= instances / min_count.
@@ -741,14 +974,16 @@ void stage_count_kmers(Context* c) {
       c->set_stat("kmer_solid_owned", (double)n_solid_local);
     }
     // "Too many kmers for kmer table!" (kmer_set.cpp:554-556) has no analogue: the set is sized to fit.
-    double solid_factor = 2.0;  // load factor in (1/4, 1/2]: short probe runs matter more than L2 residency (measured)
+    // load factor in (0.36, 0.71]: with 4-slot buckets a lookup is one sector read for all but the few
+    // keys of overfull buckets, so the set can be dense (E. coli: 64 MB, L2 resident; human: 34 GB)
+    double solid_factor = 1.4;
     if (const char* e = getenv("BGX_SOLID_FACTOR")) solid_factor = std::max(1.05, atof(e));  // experiment hook
     c->solid_slots = pow2_ceil(std::max<uint64_t>(1024, (uint64_t)((double)c->n_solid * solid_factor)));
     c->solid.alloc(c->solid_slots, s);
     KLAUNCH(fill_u64_kernel)<<<(unsigned)((c->solid_slots + 255) / 256), 256, 0, s>>>(c->solid.p, c->solid_slots, kEmptyKey);
     if (c->n_solid)
       KLAUNCH(solid_insert_kernel)<<<(unsigned)((c->n_solid + 255) / 256), 256, 0, s>>>(all_keys, c->n_solid, c->solid.p,
-                                                                             c->solid_slots - 1);
+                                                                             c->solid_slots / 4 - 1);
     BGX_CUDA(cudaGetLastError());
     st.stop();
   }

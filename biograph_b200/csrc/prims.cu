@@ -165,6 +165,12 @@ void host_trim() {
   a.cached_bytes = 0;
 }
 
+size_t dev_live_bytes() {
+  Arena& a = arena();
+  std::lock_guard<std::mutex> lk(a.mu);
+  return a.live_bytes;
+}
+
 size_t dev_peak_bytes(bool reset) {
   Arena& a = arena();
   std::lock_guard<std::mutex> lk(a.mu);

@@ -15,6 +15,7 @@ void* dev_alloc(size_t bytes, cudaStream_t s);
 void dev_free(void* p, cudaStream_t s);
 void dev_trim(cudaStream_t s);         // return the cached blocks of stream s to the driver
 size_t dev_peak_bytes(bool reset);     // high-water mark of live bytes
+size_t dev_live_bytes();               // bytes currently handed out
 
 template <typename T>
 struct DevBuf {

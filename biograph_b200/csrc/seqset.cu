@@ -335,6 +335,12 @@ __global__ void dedup_flag_kernel(const uint64_t* __restrict__ store, const uint
   keep[i] = drop ? 0u : 1u;
 }
 
+// Flag, scan and compaction stay three steps on purpose: the flag step is bound by the random
+// reads of the corrected store that decide "prefix of / equal to" for records whose 32-base keys
+// agree (a third of the seeds at 30x), and wants one record per thread at full occupancy.  A
+// single-pass version (tile-local ranks + decoupled look-back across tiles) was measured slower
+// on B200 in every tile shape (chr20 30x, 155 M records: 7.9-12.5 ms against 6.4 ms): every tile
+// is as slow as its slowest probe chain and holds up the look-back of the tiles behind it.
 __global__ void compact_pairs_kernel(const uint64_t* __restrict__ keys, const uint64_t* __restrict__ locs,
                                      const uint32_t* __restrict__ keep, const uint32_t* __restrict__ pos, uint32_t n,
                                      uint64_t* __restrict__ okeys, uint64_t* __restrict__ olocs) {

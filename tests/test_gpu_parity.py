@@ -209,6 +209,28 @@ def test_sort_key_bits_do_not_change_result(B, bits):
     full_compare(B, reads, sort_key_bits=bits)
 
 
+@pytest.mark.parametrize("batch", [1, 700, 2500, 100000])
+def test_batched_counting_does_not_change_result(B, batch):
+    """count_batch_reads bounds the k-mer instance buffers (inputs whose instances do not fit HBM next
+    to the table): the table is sized from a sampled estimate over the reads, then every batch is
+    partitioned and upserted in turn.  Counts, flags and everything downstream must be unchanged."""
+    reads = _sim(10000, 5000, 150, 0.01, 91, n_rate=0.001)
+    ss, st = full_compare(B, reads, count_batch_reads=batch)
+    assert st["count_batches"] == max(1, -(-5000 // batch))
+
+
+def test_batched_counting_with_heavy_hitter(B):
+    """a homopolymer run overfills its hash partition in every batch: the exact-offset re-run of pass 1"""
+    buf, offs = _sim(4000, 2000, 150, 0.005, 92)
+    sim = [buf[offs[i]:offs[i + 1]].decode() for i in range(len(offs) - 1)]
+    reads = []
+    for i in range(5):  # every batch of 1000 reads gets 600 copies of the homopolymer
+        reads += ["A" * 150] * 600 + sim[400 * i:400 * (i + 1)]
+    ss, st = full_compare(B, reads, count_batch_reads=1000)
+    assert st["count_batches"] == 5
+    assert st.get("count_partition_reruns", 0) >= 1
+
+
 def test_packed_input_equals_ascii_input(B):
     from biograph_b200 import bgx
     reads = _sim(8000, 4000, 150, 0.01, 31, n_rate=0.002)

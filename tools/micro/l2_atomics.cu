@@ -67,6 +67,47 @@ __global__ void __launch_bounds__(256, 4) bench(Slot* __restrict__ t, uint64_t m
 #pragma unroll
     for (int j = 0; j < ILP; ++j) acc += v[j];
   }
+  if (V == 8) {  // load and RED independent: the RED does not wait for the load
+#pragma unroll
+    for (int j = 0; j < ILP; ++j) v[j] = *reinterpret_cast<volatile unsigned long long*>(&t[s[j]].key);
+#pragma unroll
+    for (int j = 0; j < ILP; ++j) atomicAdd(reinterpret_cast<unsigned int*>(&t[s[j]].cnt), 1u);
+#pragma unroll
+    for (int j = 0; j < ILP; ++j) acc += v[j];
+  }
+  if (V == 9) {  // relaxed.gpu load, then dependent RED
+#pragma unroll
+    for (int j = 0; j < ILP; ++j) asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(v[j]) : "l"(&t[s[j]].key));
+#pragma unroll
+    for (int j = 0; j < ILP; ++j) acc += v[j];
+#pragma unroll
+    for (int j = 0; j < ILP; ++j) atomicAdd(reinterpret_cast<unsigned int*>(&t[s[j]].cnt) + (acc == 77 ? 1 : 0), 1u);
+  }
+  if (V == 10) {  // failing CAS as the load, then dependent RED
+#pragma unroll
+    for (int j = 0; j < ILP; ++j) v[j] = atomicCAS(&t[s[j]].key, ~0ULL, 5ULL);
+#pragma unroll
+    for (int j = 0; j < ILP; ++j) acc += v[j];
+#pragma unroll
+    for (int j = 0; j < ILP; ++j) atomicAdd(reinterpret_cast<unsigned int*>(&t[s[j]].cnt) + (acc == 77 ? 1 : 0), 1u);
+  }
+  if (V == 11) {  // load, then a dependent RED PER ITEM (each RED waits only for its own load)
+#pragma unroll
+    for (int j = 0; j < ILP; ++j) v[j] = *reinterpret_cast<volatile unsigned long long*>(&t[s[j]].key);
+#pragma unroll
+    for (int j = 0; j < ILP; ++j) {
+      atomicAdd(reinterpret_cast<unsigned int*>(&t[s[j]].cnt) + (v[j] == 77 ? 1 : 0), 1u);
+    }
+  }
+  if (V == 12) {  // load of the key, RED on a counter in a DIFFERENT array (separate sector)
+#pragma unroll
+    for (int j = 0; j < ILP; ++j) v[j] = *reinterpret_cast<volatile unsigned long long*>(&t[s[j]].key);
+#pragma unroll
+    for (int j = 0; j < ILP; ++j) acc += v[j];
+#pragma unroll
+    for (int j = 0; j < ILP; ++j)
+      atomicAdd(reinterpret_cast<unsigned int*>(&t[(s[j] + (mask >> 1) + 1) & mask].cnt) + (acc == 77 ? 1 : 0), 1u);
+  }
   if (acc == 0x1234567) out[0] = acc;
 }
 
@@ -75,9 +116,8 @@ __global__ void fill(Slot* t, uint64_t n) {
   if (i < n) { t[i].key = i * 0x9E3779B97F4A7C15ULL | 1; t[i].cnt = 0; }
 }
 
-template <int V>
+template <int V, int ILP = 4>
 void run(const char* name, Slot* t, uint64_t mask, uint64_t n, unsigned long long* out) {
-  constexpr int ILP = 4;
   cudaEvent_t a, b;
   cudaEventCreate(&a); cudaEventCreate(&b);
   unsigned grid = (unsigned)((n + 256 * ILP - 1) / (256 * ILP));
@@ -110,5 +150,15 @@ int main(int argc, char** argv) {
   run<5>("load + RED.add.u32 + RED.or.u64", t, slots - 1, n, out);
   run<3>("ATOM.add.u64 with return", t, slots - 1, n, out);
   run<4>("CAS.u64 (fails)", t, slots - 1, n, out);
+  run<8>("load + independent RED", t, slots - 1, n, out);
+  run<9>("ld.relaxed.gpu + RED", t, slots - 1, n, out);
+  run<10>("CAS (fails) + RED", t, slots - 1, n, out);
+  run<11>("load + RED, per-item dependency", t, slots - 1, n, out);
+  run<12>("load + RED on another sector", t, slots - 1, n, out);
+  run<2, 1>("load key + RED.add.u32, ILP 1", t, slots - 1, n, out);
+  run<2, 2>("load key + RED.add.u32, ILP 2", t, slots - 1, n, out);
+  run<2, 8>("load key + RED.add.u32, ILP 8", t, slots - 1, n, out);
+  run<11, 8>("load + RED per-item dep, ILP 8", t, slots - 1, n, out);
+  run<0, 8>("volatile load key, ILP 8", t, slots - 1, n, out);
   return 0;
 }
