@@ -366,6 +366,10 @@ def main():
             "clocks": clocks,
             "wall_s_timed_region": wall_s,
             "stage_ms": {k_: round(v, 3) for k_, v in sorted(kern_ms.items())},
+            # host wall clock over the same spans: a gap to the device time is host-side stall (syncs, NCCL setup)
+            "host_stage_ms": {k_[7:]: round(v, 3) for k_, v in sorted(st_mean.items()) if k_.startswith("hostms_")},
+            "counters": {k_: v for k_, v in sorted(st_mean.items())
+                         if not k_.startswith(("ms_", "hostms_", "alg_bytes_"))},
         }
         print(json.dumps(line))
     g.close()

@@ -171,7 +171,7 @@ class Bgx:
     """One seqset build on one GPU.  Method names follow the reference stages they replace."""
 
     def __init__(self, kmer_size=30, min_kmer_count=5, max_corrections=8, min_good_run=2, trim_after_portion=0.7,
-                 device=0, sort_key_bits=48, count_batch_reads=0):
+                 device=0, sort_key_bits=0, count_batch_reads=0):
         self.L = load_library()
         o = Options()
         self.L.bgx_default_options(C.byref(o))

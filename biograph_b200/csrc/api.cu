@@ -65,7 +65,7 @@ void bgx_default_options(bgx_options* o) {
   o->min_good_run = 2;
   o->trim_after_portion = 0.7f;
   o->device = 0;
-  o->sort_key_bits = 48;
+  o->sort_key_bits = 0;  // auto
 }
 
 const char* bgx_last_error(void) { return g_last_error.c_str(); }
@@ -82,15 +82,14 @@ int bgx_create(const bgx_options* opts, bgx_ctx** out) {
   return guard([&] {
     bgx_options o;
     if (opts) o = *opts; else bgx_default_options(&o);
-    if (o.sort_key_bits == 0) o.sort_key_bits = 48;
     // bs/kmer_counter.cpp:52-54: k in [16,31] (k-mer + 2 flag bits must fit 64 bits)
     BGX_CHECK(o.kmer_size >= 16 && o.kmer_size <= 31, "kmer_size must be in [16,31]");
     BGX_CHECK(o.min_kmer_count >= 1, "min_kmer_count must be >= 1");
     BGX_CHECK(o.max_corrections >= 0 && o.max_corrections <= 16, "max_corrections must be in [0,16]");
     BGX_CHECK(o.min_good_run >= 0, "min_good_run must be >= 0");
     BGX_CHECK(o.trim_after_portion >= 0.f && o.trim_after_portion <= 1.f, "trim_after_portion must be in [0,1]");
-    BGX_CHECK(o.sort_key_bits >= 16 && o.sort_key_bits <= 64 && o.sort_key_bits % 8 == 0,
-              "sort_key_bits must be a multiple of 8 in [16,64]");
+    BGX_CHECK(o.sort_key_bits == 0 || (o.sort_key_bits >= 16 && o.sort_key_bits <= 64 && o.sort_key_bits % 8 == 0),
+              "sort_key_bits must be 0 (auto) or a multiple of 8 in [16,64]");
     int ndev = 0;
     cudaError_t e = cudaGetDeviceCount(&ndev);
     BGX_CHECK(e == cudaSuccess && ndev > 0, "no CUDA device: bgx has no CPU fallback");

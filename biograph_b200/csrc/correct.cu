@@ -305,7 +305,9 @@ __global__ void __launch_bounds__(kProbeThreads, (MAXIT <= 4 ? 3 : 1)) probe_ker
       const int p = it * 32 + (int)lane;
       bool more;
       unsigned long long e = bucket4_match(cur[it], canon[it], &more);
-      while (live[it] && more) {  // home bucket full without the key: rare at load factor <= 0.71
+      // home bucket full without the key: rare at load factor <= 1/2.  (Running these follow-up probes
+      // in rounds over all steps at once was measured slower: 5.5 against 4.4 ms on E. coli 100x.)
+      while (live[it] && more) {
         slot[it] = (slot[it] + 1) & P.set_mask;
         ld_bucket4(P.set, slot[it], cur[it]);
         e = bucket4_match(cur[it], canon[it], &more);

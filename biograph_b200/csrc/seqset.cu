@@ -829,7 +829,17 @@ void sort_records(Context* c, DevBuf<uint64_t>& keys, DevBuf<uint64_t>& locs, De
                   DevBuf<uint64_t>& locs_alt, uint32_t n, const std::string& tag) {
   cudaStream_t s = c->stream;
   if (n == 0) return;
+  // key bits the radix passes sort on.  Auto: 2 bases more than log4(n), rounded up to whole passes
+  // -- a few percent of the records then share their top bits with a non-duplicate (duplicates
+  // and repeats tie at any width; the tie kernels resolve both), and every 8 bits less is one
+  // pass over all records less.  Measured, radix + ties: E. coli 100x 2.29 ms at 48 bits, 2.06 at
+  // 32; chr20 30x 16.1 ms at 48, 14.6 at 40, 13.1 at 32.
   int sbits = c->opt.sort_key_bits;
+  if (sbits == 0) {
+    int bases = 2;
+    while (bases < 32 && (1ull << (2 * (bases - 2))) < (uint64_t)n) ++bases;
+    sbits = std::max(24, std::min(64, (2 * bases + 7) / 8 * 8));
+  }
   if (const char* e = getenv("BGX_SORT_BITS")) sbits = std::max(16, std::min(64, atoi(e) / 8 * 8));  // experiment hook
   int passes = 0;
   {

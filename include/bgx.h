@@ -38,7 +38,7 @@ typedef struct bgx_options {
   int32_t min_good_run;       /* --min-good-run, default 2 */
   float trim_after_portion;   /* --trim-after-portion, default 0.7f (parsed as float: :489-490) */
   int32_t device;             /* CUDA device ordinal */
-  int32_t sort_key_bits;      /* radix-sorted key bits per round (multiple of 8, 16..64); 0 = default */
+  int32_t sort_key_bits;      /* radix-sorted key bits per round (multiple of 8, 16..64); 0 = auto from the record count */
   int32_t count_batch_reads;  /* k-mer counting: reads per batch; 0 = auto (one batch unless the k-mer
                                * instance buffers would not fit next to the table) */
 } bgx_options;

@@ -34,7 +34,7 @@ def test_options_struct_layout(B):
     o = B.Options()
     B.load_library().bgx_default_options(C.byref(o))
     assert (o.kmer_size, o.min_kmer_count, o.max_corrections, o.min_good_run) == (30, 5, 8, 2)
-    assert abs(o.trim_after_portion - 0.7) < 1e-6 and o.sort_key_bits == 48
+    assert abs(o.trim_after_portion - 0.7) < 1e-6 and o.sort_key_bits == 0 and o.count_batch_reads == 0
     assert C.sizeof(B.Options) == 32
 
 

@@ -203,7 +203,7 @@ def test_refinement_path_equals_small_group_path(B):
     check_seqset_equal(ss_a, ss_b)
 
 
-@pytest.mark.parametrize("bits", [16, 32, 48, 64])
+@pytest.mark.parametrize("bits", [0, 16, 32, 48, 64])
 def test_sort_key_bits_do_not_change_result(B, bits):
     reads = _sim(10000, 5000, 150, 0.005, 78)
     full_compare(B, reads, sort_key_bits=bits)
