@@ -1005,7 +1005,9 @@ void stage_count_kmers(Context* c) {
 
 void export_kmers(Context* c, uint32_t min_count, uint64_t* n_out, uint64_t** kmers, uint32_t** fwd, uint32_t** rev,
                   uint8_t** flags) {
-  BGX_CHECK(c->counted && c->table.p, "bgx_export_kmers: call bgx_count_kmers first (and before bgx_reset_results)");
+  BGX_CHECK(c->counted && c->table.p,
+            "bgx_export_kmers: call bgx_count_kmers first (and before bgx_reset_results; on inputs whose k-mer tables "
+            "exceed a quarter of the device memory also before bgx_build_seqset, which releases them)");
   cudaStream_t s = c->stream;
   uint64_t slots = c->table_slots;
   DevBuf<unsigned long long> counters(2, s);

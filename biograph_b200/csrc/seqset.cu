@@ -975,6 +975,15 @@ void stage_build_seqset_dist(Context* c);
 
 void stage_build_seqset(Context* c) {
   BGX_CHECK(c->corrected, "bgx_build_seqset: call bgx_correct first");
+  // Large inputs: the count table and the solid set (69 GB each per GPU at GRCh38 30x on 8 GPUs) are
+  // dead weight from here on; give them back so the corrected store and the records fit.
+  // Small inputs keep them, so bgx_export_kmers still works after the build.
+  if (c->table.bytes() + c->solid.bytes() > c->total_mem / 4) {
+    c->table.release();
+    c->solid.release();
+    c->counted = false;
+    c->set_stat("kmer_tables_released", 1);
+  }
   if (c->dist.nranks > 1) return stage_build_seqset_dist(c);
   cudaStream_t s = c->stream;
   ScopedStage st_all(c, "seqset_total");
