@@ -39,7 +39,7 @@ def build_library(force=False):
 
 
 EXPORTS = ["bgx_default_options", "bgx_last_error", "bgx_version", "bgx_device_count", "bgx_create", "bgx_destroy",
-           "bgx_free", "bgx_add_reads_ascii", "bgx_add_reads_packed", "bgx_count_kmers", "bgx_export_kmers",
+           "bgx_free", "bgx_add_reads_ascii", "bgx_add_reads_packed", "bgx_add_reads_packed_async", "bgx_count_kmers", "bgx_export_kmers",
            "bgx_correct", "bgx_export_corrected", "bgx_build_seqset", "bgx_export_seqset",
            "bgx_export_entries_ascii", "bgx_run", "bgx_reset_results", "bgx_clear_reads", "bgx_stats_json", "bgx_timer_start", "bgx_timer_stop",
            "bgx_launch_count", "bgx_debug_sort_pairs", "bgx_dist_unique_id", "bgx_dist_init", "bgx_seqset_layout", "bgx_seed_uncorrected", "bgx_export_varbit"]
@@ -63,6 +63,7 @@ def load_library():
     L.bgx_free.argtypes = [vp]
     L.bgx_add_reads_ascii.argtypes = [vp, vp, vp, C.c_uint64]
     L.bgx_add_reads_packed.argtypes = [vp, vp, vp, vp, vp, C.c_uint64]
+    L.bgx_add_reads_packed_async.argtypes = [vp, vp, vp, vp, vp, C.c_uint64]
     L.bgx_count_kmers.argtypes = [vp]
     L.bgx_export_kmers.argtypes = [vp, C.c_uint32, u64p, C.POINTER(vp), C.POINTER(vp), C.POINTER(vp), C.POINTER(vp)]
     L.bgx_correct.argtypes = [vp]
@@ -237,8 +238,10 @@ class Bgx:
         self._ck(self.L.bgx_add_reads_packed(self.h, packed.ctypes.data, None if nmask is None else nmask.ctypes.data,
                                              word_offs.ctypes.data, lens.ctypes.data, len(lens)))
 
-    def add_reads_packed_ptr(self, packed_ptr, nmask_ptr, word_offs_ptr, lens_ptr, n):
-        self._ck(self.L.bgx_add_reads_packed(self.h, packed_ptr, nmask_ptr, word_offs_ptr, lens_ptr, n))
+    def add_reads_packed_ptr(self, packed_ptr, nmask_ptr, word_offs_ptr, lens_ptr, n, overlap=False):
+        """overlap=True: bgx_add_reads_packed_async (the buffers must outlive the next count_kmers / run)"""
+        f = self.L.bgx_add_reads_packed_async if overlap else self.L.bgx_add_reads_packed
+        self._ck(f(self.h, packed_ptr, nmask_ptr, word_offs_ptr, lens_ptr, n))
 
     # -- kmer_counter / run_kmerize_subtask ----------------------------------------------------
     def count_kmers(self):

@@ -119,6 +119,12 @@ void bgx_destroy(bgx_ctx* x) {
   if (!x) return;
   cudaSetDevice(x->c.device);
   cudaStream_t s = x->c.stream;
+  if (x->c.copy_stream) {
+    cudaStreamSynchronize(x->c.copy_stream);
+    for (Context::UploadChunk& ch : x->c.upload) cudaEventDestroy(ch.ev);
+    x->c.upload.clear();
+    cudaStreamDestroy(x->c.copy_stream);
+  }
   cudaStreamSynchronize(s);
   {
     Context& c = x->c;
@@ -152,6 +158,11 @@ int bgx_add_reads_ascii(bgx_ctx* x, const char* bases, const uint64_t* offs, uin
 int bgx_add_reads_packed(bgx_ctx* x, const uint8_t* packed, const uint32_t* n_mask, const uint64_t* word_offs,
                          const uint16_t* lens, uint64_t n_reads) {
   CTX_GUARD({ reads_append_packed(c, packed, n_mask, word_offs, lens, n_reads); })
+}
+
+int bgx_add_reads_packed_async(bgx_ctx* x, const uint8_t* packed, const uint32_t* n_mask, const uint64_t* word_offs,
+                               const uint16_t* lens, uint64_t n_reads) {
+  CTX_GUARD({ reads_append_packed(c, packed, n_mask, word_offs, lens, n_reads, true); })
 }
 
 int bgx_count_kmers(bgx_ctx* x) { CTX_GUARD({ stage_count_kmers(c); }) }
@@ -250,6 +261,7 @@ int bgx_reset_results(bgx_ctx* x) {
 
 int bgx_clear_reads(bgx_ctx* x) {
   CTX_GUARD({
+    reads_ready(c);  // copies still in flight are ordered before the buffers can be reused
     c->words.release(); c->nmask.release(); c->word_off.release(); c->lens.release();
     c->n_reads = c->n_words = c->n_bases = c->n_kmer_instances = 0;
     c->has_n = false;

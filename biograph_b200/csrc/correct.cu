@@ -588,6 +588,7 @@ __global__ void __launch_bounds__(128) passthrough_kernel(const uint64_t* __rest
 }  // namespace
 
 void stage_seed_uncorrected(Context* c) {
+  reads_ready(c);
   BGX_CHECK(!c->has_n, "bgx_seed_uncorrected: reads must not contain N");
   cudaStream_t s = c->stream;
   ScopedStage st_all(c, "correct_total");
@@ -620,6 +621,7 @@ void stage_seed_uncorrected(Context* c) {
 }
 
 void stage_correct(Context* c) {
+  reads_ready(c);
   BGX_CHECK(c->counted, "bgx_correct: call bgx_count_kmers first");
   BGX_CHECK(c->opt.max_corrections <= kMaxCorr, "max_corrections > 16 is not supported");
   cudaStream_t s = c->stream;

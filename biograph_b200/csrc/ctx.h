@@ -41,6 +41,14 @@ struct Context {
   DevBuf<uint32_t> word_off;     // n_reads + 1
   DevBuf<uint16_t> lens;         // n_reads
   size_t cap_words = 0, cap_reads = 0;
+  // bgx_add_reads_packed_async: the packed words travel on their own stream in chunks of reads;
+  // pass 1 of counting starts on a chunk as soon as it has landed (PCIe copy under compute)
+  struct UploadChunk {
+    uint64_t r0, r1;   // reads [r0, r1)
+    cudaEvent_t ev;    // recorded on copy_stream after the chunk's words are in place
+  };
+  cudaStream_t copy_stream = nullptr;
+  std::vector<UploadChunk> upload;  // chunks not yet ordered before the main stream, ascending
 
   // ---- k-mer stage -----------------------------------------------------------------------
   bool counted = false;
@@ -119,7 +127,9 @@ struct ScopedStage {
 // stage entry points (each in its own .cu)
 void reads_append_ascii(Context* c, const char* bases, const uint64_t* offs, uint64_t n);
 void reads_append_packed(Context* c, const uint8_t* packed, const uint32_t* n_mask, const uint64_t* word_offs,
-                         const uint16_t* lens, uint64_t n);
+                         const uint16_t* lens, uint64_t n, bool async = false);
+// orders every pending upload chunk before whatever the main stream does next (and forgets them)
+void reads_ready(Context* c);
 void stage_count_kmers(Context* c);
 void export_kmers(Context* c, uint32_t min_count, uint64_t* n, uint64_t** kmers, uint32_t** fwd, uint32_t** rev,
                   uint8_t** flags);

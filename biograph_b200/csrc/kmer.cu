@@ -589,7 +589,26 @@ void partition_reads(Context* c, uint64_t r0, uint64_t n, uint64_t K, int part_b
   unsigned int* bitmap = est ? est->bitmap.p : nullptr;
   const uint64_t bit_mask = est ? est->bits - 1 : 0;
   const int shift = est ? est->shift : 4;
-  if (n) run_partition(c, maxit, r0, n, part_bits, cursors.p, part_base.p, cap, out->pk.p, bitmap, bit_mask, shift, overflow.p);
+  if (n && !c->upload.empty() && r0 == 0 && n == c->n_reads) {
+    // the reads are still arriving (bgx_add_reads_packed_async): one launch per upload chunk, each
+    // ordered after its own copy only, all appending to the same partitions through the cursors
+    uint64_t pos = 0;
+    for (Context::UploadChunk& ch : c->upload) {
+      if (ch.r0 > pos)
+        run_partition(c, maxit, pos, ch.r0 - pos, part_bits, cursors.p, part_base.p, cap, out->pk.p, bitmap, bit_mask, shift, overflow.p);
+      BGX_CUDA(cudaStreamWaitEvent(s, ch.ev, 0));
+      cudaEventDestroy(ch.ev);
+      if (ch.r1 > ch.r0)
+        run_partition(c, maxit, ch.r0, ch.r1 - ch.r0, part_bits, cursors.p, part_base.p, cap, out->pk.p, bitmap, bit_mask, shift, overflow.p);
+      pos = ch.r1;
+    }
+    c->upload.clear();
+    if (pos < n)
+      run_partition(c, maxit, pos, n - pos, part_bits, cursors.p, part_base.p, cap, out->pk.p, bitmap, bit_mask, shift, overflow.p);
+  } else if (n) {
+    reads_ready(c);
+    run_partition(c, maxit, r0, n, part_bits, cursors.p, part_base.p, cap, out->pk.p, bitmap, bit_mask, shift, overflow.p);
+  }
   BGX_CUDA(cudaMemcpyAsync(&h_over, overflow.p, sizeof(int), cudaMemcpyDeviceToHost, s));
   BGX_CUDA(cudaMemcpyAsync(out->count.data(), cursors.p, P * 8, cudaMemcpyDeviceToHost, s));
   BGX_CUDA(cudaStreamSynchronize(s));
@@ -885,6 +904,7 @@ void stage_count_kmers(Context* c) {
     }
   } else {
     // ---- batched: estimate from the reads first, then partition / exchange / upsert batch by batch ---
+    reads_ready(c);
     Estimator est;
     {
       ScopedStage st(c, "count_estimate");

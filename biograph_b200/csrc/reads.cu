@@ -112,8 +112,17 @@ void finish_append(Context* c, const std::vector<uint16_t>& lens, const std::vec
 
 }  // namespace
 
+void reads_ready(Context* c) {
+  for (Context::UploadChunk& ch : c->upload) {
+    BGX_CUDA(cudaStreamWaitEvent(c->stream, ch.ev, 0));
+    cudaEventDestroy(ch.ev);
+  }
+  c->upload.clear();
+}
+
 void reads_append_ascii(Context* c, const char* bases, const uint64_t* offs, uint64_t n) {
   if (n == 0) return;
+  reads_ready(c);
   cudaStream_t s = c->stream;
   std::vector<uint16_t> lens(n);
   for (uint64_t r = 0; r < n; ++r) {
@@ -177,9 +186,15 @@ __global__ void add_base_kernel(uint32_t* __restrict__ off, uint64_t n, uint32_t
 }  // namespace
 
 void reads_append_packed(Context* c, const uint8_t* packed, const uint32_t* n_mask, const uint64_t* word_offs,
-                         const uint16_t* lens_in, uint64_t n) {
+                         const uint16_t* lens_in, uint64_t n, bool async) {
   if (n == 0) return;
+  reads_ready(c);
   cudaStream_t s = c->stream;
+  // the chunked form pays off for big appends only, and the N mask (needed up front: has_n picks
+  // the kernel variants) keeps the synchronous path
+  constexpr int kChunks = 8;
+  async = async && n_mask == nullptr && n >= (1u << 18);
+  uint32_t h_bound[kChunks + 1];  // first word of every chunk, relative to this append
   const int k = c->opt.kmer_size;
   // lengths go straight to the device; word offsets, totals and the length check are computed there
   grow(c->word_off, c->n_reads + (c->n_reads ? 1 : 0), c->n_reads + n + 1, s);
@@ -193,6 +208,9 @@ void reads_append_packed(Context* c, const uint8_t* packed, const uint32_t* n_ma
   exclusive_scan_u32(nwords.p, c->word_off.p + c->n_reads, n + 1, nullptr, s);
   unsigned long long h[5];
   BGX_CUDA(cudaMemcpyAsync(h, tot.p, sizeof(h), cudaMemcpyDeviceToHost, s));
+  if (async)
+    for (int j = 0; j <= kChunks; ++j)
+      BGX_CUDA(cudaMemcpyAsync(&h_bound[j], c->word_off.p + c->n_reads + n * j / kChunks, 4, cudaMemcpyDeviceToHost, s));
   BGX_CUDA(cudaStreamSynchronize(s));
   BGX_CHECK(h[4] == 0, "read longer than 255 bases");
   const uint64_t new_words = h[0], words_before = c->n_words;
@@ -206,6 +224,34 @@ void reads_append_packed(Context* c, const uint8_t* packed, const uint32_t* n_ma
   grow(c->nmask, words_before + (words_before ? 1 : 0), words_before + new_words + 1, s);
   DevBuf<int> d_flag(1, s);
   BGX_CUDA(cudaMemsetAsync(d_flag.p, 0, sizeof(int), s));
+  if (async) {
+    // words travel on the copy stream, chunk by chunk; everything queued so far on the main stream
+    // (buffer growth, the N-mask memset) is ordered before the first copy
+    if (!c->copy_stream) BGX_CUDA(cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
+    BGX_CUDA(cudaMemsetAsync(c->nmask.p + words_before, 0, (new_words + 1) * 4, s));
+    cudaEvent_t ready;
+    BGX_CUDA(cudaEventCreateWithFlags(&ready, cudaEventDisableTiming));
+    BGX_CUDA(cudaEventRecord(ready, s));
+    BGX_CUDA(cudaStreamWaitEvent(c->copy_stream, ready, 0));
+    cudaEventDestroy(ready);
+    cudaStream_t cs = c->copy_stream;
+    for (int j = 0; j < kChunks; ++j) {
+      const uint64_t w0 = h_bound[j], w1 = h_bound[j + 1];
+      if (w1 > w0) {
+        BGX_CUDA(cudaMemcpyAsync(c->words.p + words_before + w0, packed + 8 * (src_word0 + w0), (w1 - w0) * 8,
+                                 cudaMemcpyHostToDevice, cs));
+        KLAUNCH(bswap_words_kernel)<<<(unsigned)((w1 - w0 + 255) / 256), 256, 0, cs>>>(c->words.p + words_before + w0, w1 - w0);
+      }
+      if (j == kChunks - 1) BGX_CUDA(cudaMemsetAsync(c->words.p + words_before + new_words, 0, sizeof(uint64_t), cs));
+      Context::UploadChunk ch;
+      ch.r0 = c->n_reads + n * j / kChunks;
+      ch.r1 = c->n_reads + n * (j + 1) / kChunks;
+      BGX_CUDA(cudaEventCreateWithFlags(&ch.ev, cudaEventDisableTiming));
+      BGX_CUDA(cudaEventRecord(ch.ev, cs));
+      c->upload.push_back(ch);
+    }
+    BGX_CUDA(cudaGetLastError());
+  } else {
   BGX_CUDA(cudaMemcpyAsync(c->words.p + words_before, packed + 8 * src_word0, new_words * 8, cudaMemcpyHostToDevice, s));
   if (new_words) KLAUNCH(bswap_words_kernel)<<<(unsigned)((new_words + 255) / 256), 256, 0, s>>>(c->words.p + words_before, new_words);
   if (n_mask) {
@@ -218,9 +264,12 @@ void reads_append_packed(Context* c, const uint8_t* packed, const uint32_t* n_ma
   BGX_CUDA(cudaMemsetAsync(c->words.p + words_before + new_words, 0, sizeof(uint64_t), s));
   BGX_CUDA(cudaMemsetAsync(c->nmask.p + words_before + new_words, 0, sizeof(uint32_t), s));
   BGX_CUDA(cudaGetLastError());
+  }
   int flag = 0;
-  BGX_CUDA(cudaMemcpyAsync(&flag, d_flag.p, sizeof(int), cudaMemcpyDeviceToHost, s));
-  BGX_CUDA(cudaStreamSynchronize(s));
+  if (!async) {
+    BGX_CUDA(cudaMemcpyAsync(&flag, d_flag.p, sizeof(int), cudaMemcpyDeviceToHost, s));
+    BGX_CUDA(cudaStreamSynchronize(s));
+  }
   c->add_stat("h2d_bytes", (double)new_words * (n_mask ? 12 : 8) + (double)n * 2);
   c->has_n = c->has_n || flag != 0;
   c->n_reads += n;

@@ -78,6 +78,14 @@ int bgx_add_reads_ascii(bgx_ctx* ctx, const char* bases, const uint64_t* offs, u
 int bgx_add_reads_packed(bgx_ctx* ctx, const uint8_t* packed, const uint32_t* n_mask,
                          const uint64_t* word_offs, const uint16_t* lens, uint64_t n_reads);
 
+/* Same arguments and result as bgx_add_reads_packed, but the packed words are copied on a second
+ * stream in chunks of reads and the call returns without waiting for them: pass 1 of
+ * bgx_count_kmers starts on each chunk as it lands, so the PCIe copy runs under compute.
+ * `packed` must stay valid and unchanged until the next bgx_count_kmers / bgx_run / bgx_correct
+ * returns.  With an N mask, or for small appends, it is the synchronous call. */
+int bgx_add_reads_packed_async(bgx_ctx* ctx, const uint8_t* packed, const uint32_t* n_mask,
+                               const uint64_t* word_offs, const uint16_t* lens, uint64_t n_reads);
+
 /* replaces: kmer_counter::close_prob_pass + run_kmerize_subtask (bs/kmer_counter.cpp:234-404,
  * modules/bio_mapred/kmerize_bf.h:81-84): exact canonical k-mer counts with fwd/rev counts and
  * starts-read flags, min-count filter, and the device k-mer set used by correction. */

@@ -247,6 +247,34 @@ def test_packed_input_equals_ascii_input(B):
     g2.close()
 
 
+def test_async_upload_equals_sync_upload(B):
+    """bgx_add_reads_packed_async: chunked copy on a second stream, pass 1 of counting launched per
+    chunk; also appended after a synchronous batch, and followed by stages other than count."""
+    from biograph_b200 import bgx
+    reads = _sim(60000, 300000, 150, 0.005, 33)   # >= 2^18 reads: the chunked path is taken
+    packed, nmask, woffs, lens = bgx.pack_reads_2bit(reads)
+    assert nmask is None
+    g1 = B.Bgx()
+    g1.add_reads_packed(packed, None, woffs, lens)
+    g1.run()
+    ss1 = g1.export_seqset()
+    km1 = g1.export_kmers(1)
+    g2 = B.Bgx()
+    g2.add_reads_packed_ptr(packed.ctypes.data, None, woffs.ctypes.data, lens.ctypes.data, len(lens), overlap=True)
+    g2.run()
+    check_seqset_equal(ss1, g2.export_seqset())
+    km2 = g2.export_kmers(1)
+    for f in ("kmers", "fwd", "rev", "flags"):
+        assert np.array_equal(km1[f], km2[f]), f
+    # batched counting and a second (async) append on top of resident reads
+    g3 = B.Bgx(count_batch_reads=100000)
+    g3.add_reads_packed_ptr(packed.ctypes.data, None, woffs.ctypes.data, lens.ctypes.data, len(lens), overlap=True)
+    g3.run()
+    check_seqset_equal(ss1, g3.export_seqset())
+    for g in (g1, g2, g3):
+        g.close()
+
+
 def test_incremental_add_reads(B):
     reads = _sim(8000, 4000, 150, 0.01, 32)
     buf, offs = reads

@@ -13,6 +13,7 @@ from biograph_b200 import bgx as bgxmod  # noqa: E402
 
 wl = sys.argv[1] if len(sys.argv) > 1 else "ecoli100x"
 runs = int(sys.argv[2]) if len(sys.argv) > 2 else 4
+overlap = len(sys.argv) > 3 and sys.argv[3] == "overlap"
 reads = bench.make_workload(wl)
 packed, nmask, woffs, lens = bgxmod.pack_reads_2bit(reads)
 pinned = torch.empty(packed.nbytes, dtype=torch.uint8).pin_memory()
@@ -25,7 +26,7 @@ for i in range(runs):
     torch.cuda.synchronize()
     t0 = time.perf_counter()
     g.timer_start()
-    g.add_reads_packed_ptr(pinned.data_ptr(), None, None, pl.data_ptr(), len(lens))
+    g.add_reads_packed_ptr(pinned.data_ptr(), None, None, pl.data_ptr(), len(lens), overlap=overlap)
     t1 = time.perf_counter()
     g.run()
     t2 = time.perf_counter()
