@@ -63,6 +63,32 @@ struct Params {
 struct SolidMask {
   const uint32_t* bits;
   __device__ __forceinline__ bool at(int p) const { return (bits[p >> 5] >> (p & 31)) & 1u; }
+  // number of consecutive set bits at p, p+1, ... (at most lim)
+  __device__ __forceinline__ int run_up(int p, int lim) const {
+    int cnt = 0;
+    while (cnt < lim) {
+      const uint32_t inv = ~(bits[p >> 5] >> (p & 31));
+      const int avail = min(32 - (p & 31), lim - cnt);
+      const int ones = inv ? __ffs(inv) - 1 : 32;
+      if (ones < avail) return cnt + ones;
+      cnt += avail;
+      p += avail;
+    }
+    return cnt;
+  }
+  // ... at p, p-1, ... (at most lim; p - lim + 1 >= 0)
+  __device__ __forceinline__ int run_down(int p, int lim) const {
+    int cnt = 0;
+    while (cnt < lim) {
+      const uint32_t inv = ~(bits[p >> 5] << (31 - (p & 31)));
+      const int avail = min((p & 31) + 1, lim - cnt);
+      const int ones = inv ? __clz(inv) : 32;
+      if (ones < avail) return cnt + ones;
+      cnt += avail;
+      p -= avail;
+    }
+    return cnt;
+  }
 };
 
 // logical view of a stretch of the read: forward from `origin`, or reverse-complemented
@@ -75,6 +101,16 @@ struct Input {
   bool rev;
   // read position of the first base of the k-mer formed by shifting in logical base i
   __device__ __forceinline__ int kmer_pos(int i, int k) const { return rev ? origin - i : origin + i - k + 1; }
+  // the k-mer of logical bases i-k .. i-1, straight from the read words (valid when none of them
+  // is a substitution of the current path)
+  __device__ __forceinline__ uint64_t kmer_before(int i, int k) const {
+    const int a = rev ? origin - i + 1 : origin + i - k;
+    const int q = a >> 5;
+    const unsigned s = (unsigned)(a & 31) * 2;
+    const uint64_t win = s ? ((w[q] << s) | (w[q + 1] >> (64 - s))) : w[q];
+    const uint64_t x = win >> (64 - 2 * k);
+    return rev ? revcomp_kmer(x, k) : x;
+  }
   __device__ __forceinline__ int get(int i) const {  // 0..3, 4 = 'N'
     int pos = rev ? origin - i : origin + i;
     if (m != nullptr && ((m[pos >> 5] >> (31 - (pos & 31))) & 1u)) return 4;
@@ -134,7 +170,23 @@ __device__ void correct_internal(const Params& P, const Input& in, const SolidMa
       int c = in.get(it);
       if (c != 4) {
         uint64_t nk = shift_in(kmer, c, kmask);
-        while (it - last_sub >= P.k ? sm.at(in.kmer_pos(it, P.k)) : solid_has(P, nk)) {
+        for (;;) {
+          if (in.m == nullptr && it - last_sub >= P.k) {
+            // every window from here on is free of substitutions (and the read set has no N): the
+            // probe pass already answered them all, so the run is a bit scan of the solid mask
+            // instead of a loop over the bases
+            const int lim = in.n - it;
+            const int p0 = in.kmer_pos(it, P.k);
+            const int cnt = in.rev ? sm.run_down(p0, lim) : sm.run_up(p0, lim);
+            if (cnt > 0) {
+              run += cnt;
+              it += cnt;
+              if (it == in.n) finished = true;
+              else kmer = in.kmer_before(it, P.k);
+            }
+            break;
+          }
+          if (!(it - last_sub >= P.k ? sm.at(in.kmer_pos(it, P.k)) : solid_has(P, nk))) break;
           ++run;
           ++it;
           if (it == in.n) { finished = true; break; }

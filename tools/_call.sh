@@ -1,7 +1,6 @@
 set -x
 mkdir -p gpurun_out
-( timeout 900 python -m pytest tests -m gpu -x -q 2>&1 | tail -15; echo "pytest exit ${PIPESTATUS[0]}" ) > gpurun_out/l_pytest.log 2>&1
-timeout 300 python tools/e2e_times.py ecoli100x 4 > gpurun_out/l_e2e_sync.log 2>&1
-timeout 300 python tools/e2e_times.py ecoli100x 4 overlap > gpurun_out/l_e2e_overlap.log 2>&1
-timeout 400 python bench.py --no-cpu-baseline > gpurun_out/l_bench.json 2> gpurun_out/l_bench.err
-tail -3 gpurun_out/l_pytest.log; tail -3 gpurun_out/l_e2e_sync.log; tail -3 gpurun_out/l_e2e_overlap.log
+( timeout 900 python -m pytest tests -m gpu -x -q 2>&1 | tail -15; echo "pytest exit ${PIPESTATUS[0]}" ) > gpurun_out/n_pytest.log 2>&1
+timeout 300 python tools/stage_times.py ecoli100x 3 2>&1 | grep "^run 2" >> gpurun_out/n_ab.log
+timeout 300 python tools/stage_times.py chr20_30x 2 2>&1 | grep "^run 1" >> gpurun_out/n_ab.log
+tail -3 gpurun_out/n_pytest.log; cut -c1-330 gpurun_out/n_ab.log
