@@ -328,7 +328,7 @@ def main():
             "unit": "GB/s", "frac": stages.get(dom, {}).get("frac"), "traffic": None, "peak_source": peak_src,
             "stages": stages, "share_of_step": kern_ms.get(dom, 0.0) / (dev_ms / args.steps)}
     tr = os.path.join(ROOT, "profiles", "traffic.json")
-    if os.path.exists(tr):
+    if os.path.exists(tr) and args.workload == "ecoli100x" and world == 1:  # the capture is of that workload on one GPU
         try:
             roof["traffic"] = json.load(open(tr)).get(dom)
         except Exception:
