@@ -56,6 +56,7 @@ struct Params {
   double trim;
   const unsigned long long* set;
   uint64_t set_mask;   // buckets - 1 (a bucket = 4 slots = one 32-byte sector)
+  int set_shift;       // 64 - log2(buckets): the home bucket is the TOP bits of the hash
 };
 
 // solid mask of one read: bit (p & 31) of word (p >> 5) = the k-mer starting at read position p is
@@ -125,7 +126,7 @@ __device__ __forceinline__ unsigned long long solid_find(const Params& P, uint64
   bool fl;
   uint64_t canon = canonicalize(kmer, P.k, fl);
   *flipped = fl;
-  uint64_t b = mix64(canon) & P.set_mask;
+  uint64_t b = mix64(canon) >> P.set_shift;
   for (;;) {
     unsigned long long kk[4];
     ld_bucket4(P.set, b, kk);
@@ -171,10 +172,10 @@ __device__ void correct_internal(const Params& P, const Input& in, const SolidMa
       if (c != 4) {
         uint64_t nk = shift_in(kmer, c, kmask);
         for (;;) {
-          if (in.m == nullptr && it - last_sub >= P.k) {
-            // every window from here on is free of substitutions (and the read set has no N): the
-            // probe pass already answered them all, so the run is a bit scan of the solid mask
-            // instead of a loop over the bases
+          if (it - last_sub >= P.k) {
+            // every window from here on is free of substitutions: the probe pass already answered
+            // them all (a window holding an 'N' has a 0 bit, and ends the run at the same base as
+            // the base-by-base loop would), so the run is a bit scan of the solid mask
             const int lim = in.n - it;
             const int p0 = in.kmer_pos(it, P.k);
             const int cnt = in.rev ? sm.run_down(p0, lim) : sm.run_up(p0, lim);
@@ -345,7 +346,7 @@ __global__ void __launch_bounds__(kProbeThreads, (MAXIT <= 4 ? 3 : 1)) probe_ker
       bool fl;
       canon[it] = canonicalize(win >> (64 - 2 * k), k, fl);
       flip[it] = fl;
-      slot[it] = mix64(canon[it]) & P.set_mask;
+      slot[it] = mix64(canon[it]) >> P.set_shift;
       if (live[it]) ld_bucket4(P.set, slot[it], cur[it]);
       else cur[it][0] = cur[it][1] = cur[it][2] = cur[it][3] = kEmptyKey;
     }
@@ -694,6 +695,8 @@ void stage_correct(Context* c) {
   P.trim = (double)c->opt.trim_after_portion;  // float widened to double (biograph_create.cpp:489-490,731)
   P.set = c->solid.p;
   P.set_mask = c->solid_slots / 4 - 1;
+  P.set_shift = 64;
+  for (uint64_t b = c->solid_slots / 4; b > 1; b >>= 1) --P.set_shift;
   const int max_kmers = std::max<int>((int)c->max_len - P.k + 1, 1);
   const int mask_words = max_kmers <= 128 ? 4 : 8;
   BGX_CHECK(max_kmers <= 256, "read longer than 255 bases");

@@ -439,12 +439,15 @@ __global__ void __launch_bounds__(256) table_sweep_kernel(const CountEntry* __re
 
 // insert into the solid set (32-byte buckets of four 8-byte slots, common.cuh).  Keys are distinct,
 // so a plain CAS claim suffices; a bucket fills in slot order, a full one sends the key onwards.
+// The home bucket is the TOP bits of the same hash whose top bits order the count table, and the
+// sweep emits the solid k-mers in table order: consecutive threads insert into consecutive
+// buckets, so building the set is a near-sequential write instead of one random DRAM CAS per key.
 __global__ void solid_insert_kernel(const unsigned long long* __restrict__ keys, uint64_t n,
-                                    unsigned long long* __restrict__ set, uint64_t bucket_mask) {
+                                    unsigned long long* __restrict__ set, uint64_t bucket_mask, int bucket_shift) {
   uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   unsigned long long kf = keys[i];
-  uint64_t b = mix64(kf & kKmerMask) & bucket_mask;
+  uint64_t b = mix64(kf & kKmerMask) >> bucket_shift;
   for (;;) {
 #pragma unroll
     for (int j = 0; j < 4; ++j)
@@ -1004,7 +1007,8 @@ void stage_count_kmers(Context* c) {
     KLAUNCH(fill_u64_kernel)<<<(unsigned)((c->solid_slots + 255) / 256), 256, 0, s>>>(c->solid.p, c->solid_slots, kEmptyKey);
     if (c->n_solid)
       KLAUNCH(solid_insert_kernel)<<<(unsigned)((c->n_solid + 255) / 256), 256, 0, s>>>(all_keys, c->n_solid, c->solid.p,
-                                                                             c->solid_slots / 4 - 1);
+                                                                             c->solid_slots / 4 - 1,
+                                                                             64 - log2_exact(c->solid_slots / 4));
     BGX_CUDA(cudaGetLastError());
     st.stop();
   }

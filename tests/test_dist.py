@@ -78,12 +78,13 @@ def test_rank_layout_rule():
             assert a % 512 == 0 or a == n_total  # every non-empty range starts on a bitcount group boundary
 
 
-def test_assemble_over_gloo_world2():
+@pytest.mark.parametrize("world", [2, 4])
+def test_assemble_over_gloo(world):
     import torch.multiprocessing as mp
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
-    port = 29500 + os.getpid() % 2000
-    procs = [ctx.Process(target=_gloo_worker, args=(r, 2, port, q)) for r in range(2)]
+    port = 29500 + (os.getpid() + 7 * world) % 2000
+    procs = [ctx.Process(target=_gloo_worker, args=(r, world, port, q)) for r in range(world)]
     for p in procs:
         p.start()
     for p in procs:
@@ -93,14 +94,14 @@ def test_assemble_over_gloo_world2():
 
 
 @pytest.mark.gpu
+@pytest.mark.parametrize("world", [2, 4])
 @pytest.mark.parametrize("case", ["small", "tiny", "n_and_ragged"])
-def test_two_gpu_build_matches_oracle(case):
+def test_multi_gpu_build_matches_oracle(case, world):
     import torch
     ngpu = torch.cuda.device_count()
-    if ngpu < 2:
-        pytest.skip("needs >= 2 GPUs (run under gpurun --gpus 2)")
-    world = 2
-    port = 29600 + os.getpid() % 2000
+    if ngpu < world:
+        pytest.skip(f"needs >= {world} GPUs (run under gpurun --gpus {world})")
+    port = 29600 + (os.getpid() + 11 * world) % 2000
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={world}",
            "--master-addr", "127.0.0.1", "--master-port", str(port), os.path.join(ROOT, "tests", "dist_worker.py"), case]
     r = subprocess.run(cmd, capture_output=True, text=True, timeout=900)
