@@ -18,8 +18,9 @@
 //                   with a few substituted bases, truncated.  A k-mer window that no substitution
 //                   of the current path touches is answered from the solid mask, so only the
 //                   <= k windows after each tried substitution probe the set.
-// k-mer membership = one probe sequence in the 8-byte-slot solid hash set (L2 resident for
-// bacterial genomes, one DRAM sector per probe otherwise).
+// k-mer membership = one 256-bit load of the k-mer's home bucket in the solid hash set (32-byte
+// buckets of four key|flags slots; a full bucket without the key sends the probe on to the next
+// one): one DRAM sector per probe once the set outgrows L2.
 #include <algorithm>
 
 #include "ctx.h"

@@ -5,12 +5,20 @@
 // kmerizer::run's min-count filter (modules/bio_mapred/kmerize_bf.cpp:290-318) and kmer_set
 // (modules/bio_mapred/kmer_set.cpp:522-631, lookup :296-360).
 //
-// B200 design: one pass (no probabilistic pre-pass, no temp files): a warp takes one read, its
-// lanes pull the read's words once (coalesced), every lane forms the k-mers at positions
-// lane, lane+32, ... by funnel shifts out of warp-shuffled words, canonicalises with brev, and
-// upserts into ONE open-addressing table in HBM (16-byte slots: key|flags + both counters in the
-// same 32-byte DRAM sector) with atomicCAS / atomicAdd / atomicOr.  The filter pass sweeps the
-// table once and builds the 8-byte-slot solid hash set that correction probes.
+// B200 design: two passes, no probabilistic pre-pass, no temp files.
+//   pass 1  kmer_partition_kernel: a block pulls a tile of packed reads into shared memory with
+//           128-bit coalesced loads; lane l forms the k-mers l, l+32, ... of a read by funnel
+//           shifts, canonicalises with brev and hashes; the instances leave bucketed by the top
+//           hash bits as coalesced per-partition runs.  A fused linear-counting sample sizes the
+//           table.
+//   pass 2  kmer_upsert_kernel: the slot of a k-mer is the TOP bits of its hash, so a partition is
+//           one contiguous slice of the table that stays in L2 while its tiles are upserted
+//           (CAS claim that doubles as the read, RED.add on the counter, RED.or for the flags):
+//           16-byte slots, key|flags + both counters in one 32-byte sector.
+//   filter  one sweep of the table; the solid k-mers are inserted into the bucketed hash set that
+//           correction probes (32-byte buckets of four slots, home bucket = top hash bits).
+// Inputs whose instance buffers would not fit next to the table are counted in batches of reads
+// (count_batch_reads); multi-GPU, every partition travels to the rank that owns its hash range.
 #include <algorithm>
 #include <cmath>
 #include <numeric>
