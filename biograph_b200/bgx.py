@@ -41,7 +41,7 @@ def build_library(force=False):
 EXPORTS = ["bgx_default_options", "bgx_last_error", "bgx_version", "bgx_device_count", "bgx_create", "bgx_destroy",
            "bgx_free", "bgx_add_reads_ascii", "bgx_add_reads_packed", "bgx_add_reads_packed_async", "bgx_count_kmers", "bgx_export_kmers",
            "bgx_correct", "bgx_export_corrected", "bgx_build_seqset", "bgx_export_seqset",
-           "bgx_export_entries_ascii", "bgx_run", "bgx_reset_results", "bgx_clear_reads", "bgx_stats_json", "bgx_timer_start", "bgx_timer_stop",
+           "bgx_export_entries_ascii", "bgx_lookup_reads", "bgx_run", "bgx_reset_results", "bgx_clear_reads", "bgx_stats_json", "bgx_timer_start", "bgx_timer_stop",
            "bgx_launch_count", "bgx_debug_sort_pairs", "bgx_dist_unique_id", "bgx_dist_init", "bgx_seqset_layout", "bgx_seed_uncorrected", "bgx_export_varbit"]
 
 
@@ -73,6 +73,7 @@ def load_library():
     L.bgx_export_seqset.argtypes = [vp, u64p, C.POINTER(C.c_uint32), C.POINTER(vp), C.POINTER(vp), vp * 4, vp * 4,
                                     vp * 4, C.c_uint64 * 5]
     L.bgx_export_entries_ascii.argtypes = [vp, C.c_uint64, C.c_uint64, C.POINTER(vp), C.POINTER(vp)]
+    L.bgx_lookup_reads.argtypes = [vp, u64p, C.POINTER(vp), C.POINTER(vp)]
     L.bgx_run.argtypes = [vp]
     L.bgx_reset_results.argtypes = [vp]
     L.bgx_clear_reads.argtypes = [vp]
@@ -335,6 +336,13 @@ class Bgx:
         offs = self._take(po, count + 1, np.uint64)
         seq = self._take(pb, int(offs[-1]) if count else 0, np.uint8).tobytes().decode()
         return [seq[int(offs[i]):int(offs[i + 1])] for i in range(count)]
+
+    def lookup_reads(self):
+        """make_readmap's entry lookups: (fwd_entry, rc_entry) uint64[n_reads], 2^64-1 for dropped reads"""
+        n = C.c_uint64()
+        pf, pr = C.c_void_p(), C.c_void_p()
+        self._ck(self.L.bgx_lookup_reads(self.h, C.byref(n), C.byref(pf), C.byref(pr)))
+        return self._take(pf, n.value, np.uint64), self._take(pr, n.value, np.uint64)
 
     def reset_results(self):
         self._ck(self.L.bgx_reset_results(self.h))

@@ -236,6 +236,10 @@ int bgx_export_seqset(bgx_ctx* x, uint64_t* n_entries, uint32_t* max_entry_len, 
   })
 }
 
+int bgx_lookup_reads(bgx_ctx* x, uint64_t* n_reads, uint64_t** fwd_entry, uint64_t** rc_entry) {
+  CTX_GUARD({ lookup_reads(c, n_reads, fwd_entry, rc_entry); })
+}
+
 int bgx_export_entries_ascii(bgx_ctx* x, uint64_t first, uint64_t count, char** bases, uint64_t** offs) {
   CTX_GUARD({ export_entries_ascii(c, first, count, bases, offs); })
 }

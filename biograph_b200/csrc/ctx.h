@@ -137,5 +137,6 @@ void stage_correct(Context* c);
 void stage_seed_uncorrected(Context* c);
 void export_varbit(Context* c, int which, uint64_t** words, uint64_t* n_words, uint32_t* bits, uint64_t* max_value);
 void stage_build_seqset(Context* c);
+void lookup_reads(Context* c, uint64_t* n_reads, uint64_t** fwd_entry, uint64_t** rc_entry);
 
 }  // namespace bgx

@@ -426,6 +426,31 @@ __global__ void walk_emit_kernel(const uint64_t* __restrict__ store, const uint6
   }
 }
 
+// ---- read -> entry lookup (the lookup half of make_readmap) -----------------------------
+// For every kept read: the id of the first entry that has the corrected read (resp. its reverse
+// complement) as a prefix -- seqset::find_existing_unique as make_readmap calls it
+// (modules/bio_mapred/make_readmap.cpp:137-167, modules/bio_base/seqset.cpp:173-188).  Every kept
+// read is a seed, so the entry exists; a miss sets *missing ("... was not found in seqset").
+__global__ void __launch_bounds__(128) lookup_reads_kernel(const uint64_t* __restrict__ store,
+                                                           const uint64_t* __restrict__ keys,
+                                                           const uint64_t* __restrict__ locs, uint32_t n, BucketIndex bi,
+                                                           const uint32_t* __restrict__ word_off,
+                                                           const uint16_t* __restrict__ clen, uint64_t rc_word_base,
+                                                           uint32_t n_reads, unsigned long long* __restrict__ fwd_entry,
+                                                           unsigned long long* __restrict__ rc_entry, int* __restrict__ missing) {
+  const uint32_t r = blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= n_reads) return;
+  const int L = clen[r];
+  unsigned long long f = ~0ULL, v = ~0ULL;
+  if (L) {
+    uint32_t where;
+    if (covered(store, keys, locs, n, bi, (uint64_t)word_off[r] * 32, L, &where)) f = where; else *missing = 1;
+    if (covered(store, keys, locs, n, bi, (rc_word_base + word_off[r]) * 32, L, &where)) v = where; else *missing = 1;
+  }
+  fwd_entry[r] = f;
+  rc_entry[r] = v;
+}
+
 // ---- merge of the (few) new records into the sorted survivors ----------------------------------------
 // rank[j] = number of old records that sort before new record j; marks[r] counts the new records
 // inserted in front of old record r.
@@ -1563,6 +1588,35 @@ void export_varbit(Context* c, int which, uint64_t** words, uint64_t* n_words, u
   *n_words = nw;
   *bits = b;
   *max_value = mv;
+}
+
+void lookup_reads(Context* c, uint64_t* n_reads, uint64_t** fwd_entry, uint64_t** rc_entry) {
+  BGX_CHECK(c->built, "bgx_lookup_reads: call bgx_build_seqset first");
+  BGX_CHECK(c->dist.nranks == 1, "bgx_lookup_reads: single-GPU builds only (a sharded build would route the reads like the "
+                                 "pop_front queries; not built yet)");
+  cudaStream_t s = c->stream;
+  const uint64_t n = c->n_reads;
+  *n_reads = n;
+  *fwd_entry = (uint64_t*)host_alloc(std::max<uint64_t>(n, 1) * 8);
+  *rc_entry = (uint64_t*)host_alloc(std::max<uint64_t>(n, 1) * 8);
+  if (n == 0) return;
+  ScopedStage st(c, "lookup_reads");
+  DevBuf<unsigned long long> d_f(n, s), d_v(n, s);
+  DevBuf<int> missing(1, s);
+  BGX_CUDA(cudaMemsetAsync(missing.p, 0, sizeof(int), s));
+  DevBuf<uint32_t> index_buf;
+  const BucketIndex bi = build_bucket_index(c, c->ent_key.p, (uint32_t)c->n_entries, index_buf);
+  KLAUNCH(lookup_reads_kernel)<<<grid_for(n, 128), 128, 0, s>>>(c->store.p, c->ent_key.p, c->ent_loc.p, (uint32_t)c->n_entries, bi,
+                                                        c->word_off.p, c->clen.p, c->n_words, (uint32_t)n, d_f.p, d_v.p,
+                                                        missing.p);
+  BGX_CUDA(cudaGetLastError());
+  int h_missing = 0;
+  BGX_CUDA(cudaMemcpyAsync(*fwd_entry, d_f.p, n * 8, cudaMemcpyDeviceToHost, s));
+  BGX_CUDA(cudaMemcpyAsync(*rc_entry, d_v.p, n * 8, cudaMemcpyDeviceToHost, s));
+  BGX_CUDA(cudaMemcpyAsync(&h_missing, missing.p, sizeof(int), cudaMemcpyDeviceToHost, s));
+  BGX_CUDA(cudaStreamSynchronize(s));
+  st.stop();
+  BGX_CHECK(!h_missing, "a corrected read was not found in seqset");  // make_readmap.cpp:150-154
 }
 
 void export_entries_ascii(Context* c, uint64_t first, uint64_t count, char** bases, uint64_t** offs_out) {

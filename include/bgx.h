@@ -137,6 +137,14 @@ int bgx_export_seqset(bgx_ctx* ctx, uint64_t* n_entries, uint32_t* max_entry_len
 int bgx_export_varbit(bgx_ctx* ctx, int32_t which, uint64_t** words, uint64_t* n_words, uint32_t* bits_per_value,
                       uint64_t* max_value);
 
+/* First step beyond the path: the entry lookups of make_readmap -- for every read,
+ * in input order, the seqset entry id of its corrected sequence and of its reverse complement
+ * (seqset::find_existing_unique as called from parallel_mate_loop_table_builder::operator(),
+ * modules/bio_mapred/make_readmap.cpp:137-167; modules/bio_base/seqset.cpp:173-188), UINT64_MAX for
+ * a dropped read.  The mate-loop table and the readmap file are not built.  Single GPU only.
+ * Arrays are bgx_free()'d by the caller. */
+int bgx_lookup_reads(bgx_ctx* ctx, uint64_t* n_reads, uint64_t** fwd_entry, uint64_t** rc_entry);
+
 /* Debug/parity hook: entry i as ASCII (entries are <= BGX_MAX_READ_LEN bases). */
 int bgx_export_entries_ascii(bgx_ctx* ctx, uint64_t first, uint64_t count, char** bases,
                              uint64_t** offs);

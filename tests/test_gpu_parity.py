@@ -247,6 +247,36 @@ def test_packed_input_equals_ascii_input(B):
     g2.close()
 
 
+@pytest.mark.parametrize("which", ["golden", "synthetic_with_n"])
+def test_lookup_reads_matches_bisect(B, golden_reads, which):
+    """bgx_lookup_reads (the entry lookups of make_readmap, make_readmap.cpp:137-167): the id of the first
+    entry having the corrected read / its reverse complement as a prefix, checked against a
+    bisect over the (parity-checked) sorted entry list."""
+    import bisect
+    reads = golden_reads if which == "golden" else _sim(6000, 3000, 120, 0.01, 55, n_rate=0.002)
+    g, km, cr, ss, st = run_gpu(B, reads)
+    ents = g.export_entries()
+    fwd, rc = g.lookup_reads()
+    kept = cr["kept"]
+    assert len(fwd) == len(kept) == len(rc)
+    seqs = O.corrected_list(cr)
+    j = 0
+    n_checked = 0
+    for r in range(len(kept)):
+        if not kept[r]:
+            assert fwd[r] == 2**64 - 1 and rc[r] == 2**64 - 1
+            continue
+        s_ = seqs[j]
+        j += 1
+        for seq, got in ((s_, int(fwd[r])), (O.revcomp(s_), int(rc[r]))):
+            want = bisect.bisect_left(ents, seq)
+            assert want < len(ents) and ents[want].startswith(seq)
+            assert got == want
+            n_checked += 1
+    assert n_checked == 2 * int(kept.sum()) > 0
+    g.close()
+
+
 def test_async_upload_equals_sync_upload(B):
     """bgx_add_reads_packed_async: chunked copy on a second stream, pass 1 of counting launched per
     chunk; also appended after a synchronous batch, and followed by stages other than count."""
