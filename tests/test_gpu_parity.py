@@ -247,6 +247,28 @@ def test_packed_input_equals_ascii_input(B):
     g2.close()
 
 
+def test_correct_reads_test_known_answers_gpu(B):
+    """The reference's own correct_reads_test.cpp:121-223 (tests/crt_cases.py): which suffixes get
+    seeded.  The k-mer set of each case is produced the way the counter would: every add_kmers
+    sequence goes in as a read (min_count 1), which marks its first k-mer fwd_starts_read and its
+    last one rev_starts_read -- exactly the flags start_correction builds."""
+    from tests import crt_cases as T
+    for name, kmer_seqs, reads, expected, exact in T.CASES:
+        all_reads = list(reads) + [s_ for s_ in kmer_seqs if s_ not in reads]
+        g = B.Bgx(kmer_size=T.K, min_kmer_count=1)
+        g.add_reads(all_reads)
+        g.count_kmers()
+        g.correct()
+        cr = g.export_corrected()
+        seqs = O.corrected_list(cr)
+        got = set()
+        for i, r in enumerate(reads):
+            assert cr["kept"][i] and seqs[i] == r, name
+            got |= T.seeds_of(r, int(cr["next_fwd"][i]), int(cr["next_rev"][i]))
+        assert (got == expected) if exact else (expected <= got), name
+        g.close()
+
+
 @pytest.mark.parametrize("which", ["golden", "synthetic_with_n"])
 def test_lookup_reads_matches_bisect(B, golden_reads, which):
     """bgx_lookup_reads (the entry lookups of make_readmap, make_readmap.cpp:137-167): the id of the first
