@@ -41,7 +41,7 @@ def build_library(force=False):
 EXPORTS = ["bgx_default_options", "bgx_last_error", "bgx_version", "bgx_device_count", "bgx_create", "bgx_destroy",
            "bgx_free", "bgx_add_reads_ascii", "bgx_add_reads_packed", "bgx_add_reads_packed_async", "bgx_count_kmers", "bgx_export_kmers",
            "bgx_correct", "bgx_export_corrected", "bgx_build_seqset", "bgx_export_seqset",
-           "bgx_export_entries_ascii", "bgx_lookup_reads", "bgx_run", "bgx_reset_results", "bgx_clear_reads", "bgx_stats_json", "bgx_timer_start", "bgx_timer_stop",
+           "bgx_export_entries_ascii", "bgx_lookup_reads", "bgx_build_readmap_unpaired", "bgx_run", "bgx_reset_results", "bgx_clear_reads", "bgx_stats_json", "bgx_timer_start", "bgx_timer_stop",
            "bgx_launch_count", "bgx_debug_sort_pairs", "bgx_dist_unique_id", "bgx_dist_init", "bgx_seqset_layout", "bgx_seed_uncorrected", "bgx_export_varbit"]
 
 
@@ -74,6 +74,8 @@ def load_library():
                                     vp * 4, C.c_uint64 * 5]
     L.bgx_export_entries_ascii.argtypes = [vp, C.c_uint64, C.c_uint64, C.POINTER(vp), C.POINTER(vp)]
     L.bgx_lookup_reads.argtypes = [vp, u64p, C.POINTER(vp), C.POINTER(vp)]
+    L.bgx_build_readmap_unpaired.argtypes = [vp, u64p, C.POINTER(vp), C.POINTER(vp), C.POINTER(vp), C.POINTER(vp * 3),
+                                             C.POINTER(vp * 3)]
     L.bgx_run.argtypes = [vp]
     L.bgx_reset_results.argtypes = [vp]
     L.bgx_clear_reads.argtypes = [vp]
@@ -343,6 +345,24 @@ class Bgx:
         pf, pr = C.c_void_p(), C.c_void_p()
         self._ck(self.L.bgx_lookup_reads(self.h, C.byref(n), C.byref(pf), C.byref(pr)))
         return self._take(pf, n.value, np.uint64), self._take(pr, n.value, np.uint64)
+
+    def build_readmap_unpaired(self):
+        """make_readmap::create_from_reads for unpaired reads: dict of the readmap's payload arrays"""
+        m = C.c_uint64()
+        pl, pp, pf = C.c_void_p(), C.c_void_p(), C.c_void_p()
+        src, dst = (C.c_void_p * 3)(), (C.c_void_p * 3)()
+        self._ck(self.L.bgx_build_readmap_unpaired(self.h, C.byref(m), C.byref(pl), C.byref(pp), C.byref(pf), C.byref(src),
+                                                   C.byref(dst)))
+        rows = int(m.value)
+        n_ent = int(self.stats().get("entries", 0))
+
+        def bc(arr, nbits):
+            return {"bits": self._take(C.c_void_p(arr[0]), (nbits + 63) // 64, np.uint64),
+                    "subaccum": self._take(C.c_void_p(arr[1]), (nbits + 511) // 512, np.uint64),
+                    "accum": self._take(C.c_void_p(arr[2]), (nbits + 1 + 511) // 512, np.uint64)}
+        return {"n_rows": rows, "read_lengths": self._take(pl, rows, np.uint16), "mate_loop_ptr": self._take(pp, rows, np.uint64),
+                "is_forward": self._take(pf, (rows + 63) // 64, np.uint64), "source_to_mid": bc(src, n_ent),
+                "dest_to_mid": bc(dst, rows)}
 
     def reset_results(self):
         self._ck(self.L.bgx_reset_results(self.h))

@@ -451,6 +451,82 @@ __global__ void __launch_bounds__(128) lookup_reads_kernel(const uint64_t* __res
   rc_entry[r] = v;
 }
 
+// ---- readmap tables for unpaired reads (make_readmap::create_from_reads) --------------------
+// Row key = entry_id << 12 | type << 10 | read_length: the order of make_readmap.h:187-205 for
+// unpaired reads (mate_read_length is 0 throughout, and rows that tie on the key are identical:
+// equal entry and length mean equal sequence, hence an equal loop entry).
+constexpr unsigned long long kNoLoopEntry = (1ULL << 37) - 1;  // make_readmap::k_no_loop_entry
+
+__global__ void readmap_rows_kernel(const unsigned long long* __restrict__ fwd_entry,
+                                    const unsigned long long* __restrict__ rc_entry,
+                                    const uint16_t* __restrict__ clen, const uint32_t* __restrict__ pos,
+                                    uint32_t n_reads, uint64_t* __restrict__ keys, uint64_t* __restrict__ vals) {
+  const uint32_t r = blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= n_reads) return;
+  const unsigned long long L = clen[r];
+  if (!L) return;
+  const uint32_t j = pos[r];
+  keys[2 * j] = (fwd_entry[r] << 12) | (0ULL << 10) | L;  // LOOP_START: loops to the entry of the reverse complement
+  vals[2 * j] = rc_entry[r];
+  keys[2 * j + 1] = (rc_entry[r] << 12) | (1ULL << 10) | L;  // RC: no mate
+  vals[2 * j + 1] = kNoLoopEntry;
+}
+
+__global__ void single_kept_kernel(const uint16_t* __restrict__ clen, uint32_t n, uint32_t* __restrict__ kept) {
+  const uint32_t r = blockIdx.x * blockDim.x + threadIdx.x;
+  if (r < n) kept[r] = clen[r] ? 1u : 0u;
+}
+
+__device__ __forceinline__ uint32_t lower_bound_u64(const uint64_t* __restrict__ a, uint32_t n, uint64_t x) {
+  uint32_t lo = 0, hi = n;
+  while (lo < hi) {
+    const uint32_t mid = lo + ((hi - lo) >> 1);
+    if (a[mid] < x) lo = mid + 1; else hi = mid;
+  }
+  return lo;
+}
+
+// One thread per sorted row: sparse_multi bits (modules/io/sparse_multi.cpp:90-113), read_lengths,
+// is_forward, and the mate loop: the j-th of a run of identical LOOP_START rows takes the j-th row of
+// the matching run of RC rows (what the sequential claim pass of make_readmap.cpp:302-360 produces),
+// and that RC row points back.
+__global__ void __launch_bounds__(256) readmap_fill_kernel(const uint64_t* __restrict__ keys,
+                                                           const uint64_t* __restrict__ vals, uint32_t m,
+                                                           unsigned long long* __restrict__ src_bits,
+                                                           uint32_t* __restrict__ dst_bits32,
+                                                           uint32_t* __restrict__ fwd_bits32,
+                                                           uint16_t* __restrict__ read_lengths,
+                                                           unsigned long long* __restrict__ ptr, int* __restrict__ missing) {
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  bool opens = false, is_fwd = false;
+  if (i < m) {
+    const uint64_t key = keys[i];
+    const uint64_t entry = key >> 12;
+    const unsigned type = (unsigned)(key >> 10) & 3u;
+    const uint64_t len = key & 1023u;
+    opens = i == 0 || (keys[i - 1] >> 12) != entry;
+    is_fwd = type == 0;
+    read_lengths[i] = (uint16_t)len;
+    if (opens) atomicOr(&src_bits[entry >> 6], 1ULL << (entry & 63));
+    if (is_fwd) {
+      const uint32_t rank = i - lower_bound_u64(keys, m, key);
+      const uint64_t want = (vals[i] << 12) | (1ULL << 10) | len;
+      const uint32_t tgt = lower_bound_u64(keys, m, want) + rank;
+      if (tgt >= m || keys[tgt] != want) {
+        *missing = 1;
+      } else {
+        ptr[i] = tgt;
+        ptr[tgt] = i;
+      }
+    }
+  }
+  const unsigned d = __ballot_sync(0xffffffffu, opens), f = __ballot_sync(0xffffffffu, is_fwd);
+  if (lane_id() == 0 && (i >> 5) < ((m + 31) >> 5)) {
+    dst_bits32[i >> 5] = d;
+    fwd_bits32[i >> 5] = f;
+  }
+}
+
 // ---- merge of the (few) new records into the sorted survivors ----------------------------------------
 // rank[j] = number of old records that sort before new record j; marks[r] counts the new records
 // inserted in front of old record r.
@@ -1617,6 +1693,104 @@ void lookup_reads(Context* c, uint64_t* n_reads, uint64_t** fwd_entry, uint64_t*
   BGX_CUDA(cudaStreamSynchronize(s));
   st.stop();
   BGX_CHECK(!h_missing, "a corrected read was not found in seqset");  // make_readmap.cpp:150-154
+}
+
+static int read_flag_i(const int* d, cudaStream_t s) {
+  int h = 0;
+  BGX_CUDA(cudaMemcpyAsync(&h, d, sizeof(int), cudaMemcpyDeviceToHost, s));
+  BGX_CUDA(cudaStreamSynchronize(s));
+  return h;
+}
+
+// bitcount::finalize of one bit vector of nbits bits (modules/io/bitcount.cpp:84-123) into host arrays
+static void bitcount_to_host(Context* c, const unsigned long long* bits, uint64_t nbits, uint64_t* out[3]) {
+  cudaStream_t s = c->stream;
+  const uint64_t words = (nbits + 63) / 64, sub_words = (nbits + 511) / 512, acc_words = (nbits + 1 + 511) / 512;
+  DevBuf<uint32_t> gpop(std::max<uint64_t>(sub_words, 1), s), gex(std::max<uint64_t>(sub_words, 1), s), tot(1, s);
+  DevBuf<unsigned long long> sub(std::max<uint64_t>(sub_words, 1), s), acc(std::max<uint64_t>(acc_words, 1), s);
+  BGX_CUDA(cudaMemsetAsync(tot.p, 0, 4, s));
+  BGX_CUDA(cudaMemsetAsync(acc.p, 0, std::max<uint64_t>(acc_words, 1) * 8, s));
+  if (sub_words) {
+    KLAUNCH(bitcount_groups_kernel)<<<grid_for(sub_words, 256), 256, 0, s>>>(bits, words, sub_words, gpop.p, sub.p);
+    exclusive_scan_u32(gpop.p, gex.p, sub_words, tot.p, s);
+  }
+  if (acc_words) KLAUNCH(bitcount_accum_kernel)<<<grid_for(acc_words, 256), 256, 0, s>>>(gex.p, tot.p, sub_words, acc_words, acc.p);
+  BGX_CUDA(cudaGetLastError());
+  out[0] = (uint64_t*)host_alloc(std::max<uint64_t>(words, 1) * 8);
+  out[1] = (uint64_t*)host_alloc(std::max<uint64_t>(sub_words, 1) * 8);
+  out[2] = (uint64_t*)host_alloc(std::max<uint64_t>(acc_words, 1) * 8);
+  if (words) BGX_CUDA(cudaMemcpyAsync(out[0], bits, words * 8, cudaMemcpyDeviceToHost, s));
+  if (sub_words) BGX_CUDA(cudaMemcpyAsync(out[1], sub.p, sub_words * 8, cudaMemcpyDeviceToHost, s));
+  if (acc_words) BGX_CUDA(cudaMemcpyAsync(out[2], acc.p, acc_words * 8, cudaMemcpyDeviceToHost, s));
+  BGX_CUDA(cudaStreamSynchronize(s));
+}
+
+void build_readmap_unpaired(Context* c, uint64_t* n_rows, uint16_t** read_lengths, uint64_t** mate_loop_ptr,
+                            uint64_t** is_forward, uint64_t* read_ids_source[3], uint64_t* read_ids_dest[3]) {
+  BGX_CHECK(c->built, "bgx_build_readmap_unpaired: call bgx_build_seqset first");
+  BGX_CHECK(c->dist.nranks == 1, "bgx_build_readmap_unpaired: single-GPU builds only");
+  BGX_CHECK(c->n_entries < kNoLoopEntry, "Entry id too long to fit in mate loop table entry");  // make_readmap.h:77
+  cudaStream_t s = c->stream;
+  ScopedStage st(c, "readmap");
+  const uint64_t n = c->n_reads;
+  const uint32_t n_ent = (uint32_t)c->n_entries;
+  // 1. the entry of every read and of its reverse complement (find_existing_unique, make_readmap.cpp:137-167)
+  DevBuf<unsigned long long> d_f(std::max<uint64_t>(n, 1), s), d_v(std::max<uint64_t>(n, 1), s);
+  DevBuf<int> missing(1, s);
+  BGX_CUDA(cudaMemsetAsync(missing.p, 0, sizeof(int), s));
+  DevBuf<uint32_t> index_buf;
+  DevBuf<uint32_t> kept(std::max<uint64_t>(n, 1), s), pos(std::max<uint64_t>(n, 1), s), tot(1, s);
+  BGX_CUDA(cudaMemsetAsync(tot.p, 0, 4, s));
+  if (n) {
+    const BucketIndex bi = build_bucket_index(c, c->ent_key.p, n_ent, index_buf);
+    KLAUNCH(lookup_reads_kernel)<<<grid_for(n, 128), 128, 0, s>>>(c->store.p, c->ent_key.p, c->ent_loc.p, n_ent, bi, c->word_off.p,
+                                                          c->clen.p, c->n_words, (uint32_t)n, d_f.p, d_v.p, missing.p);
+    // seed_count_kernel with next_fwd = next_rev = clen would do; a kept flag is all that is needed
+    KLAUNCH(single_kept_kernel)<<<grid_for(n, 256), 256, 0, s>>>(c->clen.p, (uint32_t)n, kept.p);
+    exclusive_scan_u32(kept.p, pos.p, n, tot.p, s);
+    BGX_CUDA(cudaGetLastError());
+  }
+  const uint32_t n_kept = read_u32(tot.p, s);
+  BGX_CHECK(!read_flag_i(missing.p, s), "a corrected read was not found in seqset");  // make_readmap.cpp:150-154
+  const uint32_t m = 2 * n_kept;
+  BGX_CHECK((uint64_t)n_kept * 2 < (1ull << 32), "too many reads for one readmap shard");
+  *n_rows = m;
+  // 2. rows, sorted
+  DevBuf<uint64_t> k0((size_t)m + 1, s), v0((size_t)m + 1, s), k1((size_t)m + 1, s), v1((size_t)m + 1, s);
+  const uint64_t *keys = k0.p, *vals = v0.p;
+  if (m) {
+    KLAUNCH(readmap_rows_kernel)<<<grid_for(n, 256), 256, 0, s>>>(d_f.p, d_v.p, c->clen.p, pos.p, (uint32_t)n, k0.p, v0.p);
+    BGX_CUDA(cudaGetLastError());
+    if (radix_sort_pairs(k0.p, v0.p, k1.p, v1.p, m, 0, 56, s)) { keys = k1.p; vals = v1.p; }  // 37 + 2 + 10 key bits
+  }
+  // 3. tables
+  const uint64_t src_words = ((uint64_t)n_ent + 63) / 64, row_words = ((uint64_t)m + 63) / 64;
+  DevBuf<unsigned long long> src_bits(std::max<uint64_t>(src_words, 1), s), dst_bits(std::max<uint64_t>(row_words, 1), s),
+      fwd_bits(std::max<uint64_t>(row_words, 1), s), ptr(std::max<uint32_t>(m, 1), s);
+  DevBuf<uint16_t> lens(std::max<uint32_t>(m, 1), s);
+  BGX_CUDA(cudaMemsetAsync(src_bits.p, 0, std::max<uint64_t>(src_words, 1) * 8, s));
+  BGX_CUDA(cudaMemsetAsync(dst_bits.p, 0, std::max<uint64_t>(row_words, 1) * 8, s));
+  BGX_CUDA(cudaMemsetAsync(fwd_bits.p, 0, std::max<uint64_t>(row_words, 1) * 8, s));
+  if (m) {
+    KLAUNCH(readmap_fill_kernel)<<<grid_for(m, 256), 256, 0, s>>>(keys, vals, m, src_bits.p, reinterpret_cast<uint32_t*>(dst_bits.p),
+                                                          reinterpret_cast<uint32_t*>(fwd_bits.p), lens.p, ptr.p, missing.p);
+    BGX_CUDA(cudaGetLastError());
+  }
+  BGX_CHECK(!read_flag_i(missing.p, s), "internal: a LOOP_START row has no RC row to claim");
+  // 4. out
+  bitcount_to_host(c, src_bits.p, n_ent, read_ids_source);
+  bitcount_to_host(c, dst_bits.p, m, read_ids_dest);
+  *read_lengths = (uint16_t*)host_alloc(std::max<uint32_t>(m, 1) * 2);
+  *mate_loop_ptr = (uint64_t*)host_alloc(std::max<uint32_t>(m, 1) * 8);
+  *is_forward = (uint64_t*)host_alloc(std::max<uint64_t>(row_words, 1) * 8);
+  if (m) {
+    BGX_CUDA(cudaMemcpyAsync(*read_lengths, lens.p, (size_t)m * 2, cudaMemcpyDeviceToHost, s));
+    BGX_CUDA(cudaMemcpyAsync(*mate_loop_ptr, ptr.p, (size_t)m * 8, cudaMemcpyDeviceToHost, s));
+    BGX_CUDA(cudaMemcpyAsync(*is_forward, fwd_bits.p, row_words * 8, cudaMemcpyDeviceToHost, s));
+  }
+  BGX_CUDA(cudaStreamSynchronize(s));
+  st.stop();
+  c->set_stat("readmap_rows", m);
 }
 
 void export_entries_ascii(Context* c, uint64_t first, uint64_t count, char** bases, uint64_t** offs_out) {

@@ -299,6 +299,43 @@ def test_lookup_reads_matches_bisect(B, golden_reads, which):
     g.close()
 
 
+@pytest.mark.parametrize("which", ["golden", "synthetic_dups"])
+def test_readmap_unpaired(B, golden_reads, which):
+    """bgx_build_readmap_unpaired against the CPU restatement (oracle/readmap.py, pinned to the
+    reference's golden readmap) and, for the golden reads, against the golden members themselves."""
+    from oracle import readmap as RM
+    if which == "golden":
+        reads = golden_reads
+    else:  # many identical reads: long runs of identical rows exercise the claim order
+        buf, offs = _sim(3000, 6000, 100, 0.003, 56)
+        sim = [buf[offs[i]:offs[i + 1]].decode() for i in range(len(offs) - 1)]
+        reads = sim + sim[:500] * 3 + [O.revcomp(r) for r in sim[:300]]
+    g, km, cr, ss, st = run_gpu(B, reads)
+    fwd, rc = g.lookup_reads()
+    got = g.build_readmap_unpaired()
+    kept = cr["kept"].astype(bool)
+    want = RM.readmap_tables(fwd[kept], rc[kept], cr["lens"][kept], ss["n"])
+    assert got["n_rows"] == want["n_rows"] == 2 * int(kept.sum())
+    assert np.array_equal(got["read_lengths"], want["read_lengths"])
+    assert np.array_equal(got["mate_loop_ptr"], want["mate_loop_ptr"])
+    assert np.array_equal(got["is_forward"], RM.pack_bits(want["is_forward"]))
+    for name, nbits in (("source_to_mid", ss["n"]), ("dest_to_mid", want["n_rows"])):
+        words = RM.pack_bits(want[name])
+        assert np.array_equal(got[name]["bits"], words), name
+        sub, acc, _ = O.bitcount_finalize(words, nbits)
+        assert np.array_equal(got[name]["subaccum"], sub), name
+        assert np.array_equal(got[name]["accum"], acc), name
+    if which == "golden":
+        z = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "e_coli_10000snp_readmap.npz"))
+        assert np.array_equal(got["read_lengths"].astype(np.uint8), z["read_lengths"])
+        assert np.array_equal(got["mate_loop_ptr"].astype("<u4"), z["mate_loop_ptr|packed_data"].view("<u4"))
+        assert np.array_equal(got["is_forward"], z["is_forward|packed_data"].view("<u8"))
+        for name in ("source_to_mid", "dest_to_mid"):
+            for part in ("bits", "subaccum", "accum"):
+                assert np.array_equal(got[name][part], z[f"read_ids|{name}|{part}"].view("<u8")), (name, part)
+    g.close()
+
+
 def test_async_upload_equals_sync_upload(B):
     """bgx_add_reads_packed_async: chunked copy on a second stream, pass 1 of counting launched per
     chunk; also appended after a synchronous batch, and followed by stages other than count."""
