@@ -474,4 +474,97 @@ inline seqset_tables seqset_for_reads(const std::vector<std::string>& reads, con
   return path.empty() ? b.tables() : b.make_seqset(path);
 }
 
+// make_readmap::do_make (modules/bio_mapred/make_readmap.{h,cpp}; called at biograph_create.cpp:818-831) for
+// UNPAIRED inputs: the tables come from bgx_build_readmap_unpaired, the spiral file is written here in
+// the reference's member order (readmap 1.2.0: readmap.cpp:13; sparse_multi 1.0.0; packed_varbit_vector
+// 1.0.0; packed_vector 1.0.0).  A paired input throws: the MATE / MATE_RC loops are not built.
+class make_readmap {
+ public:
+  struct tables {
+    uint64_t n_rows = 0, n_entries = 0;
+    detail::host_array<uint16_t> read_lengths;
+    detail::host_array<uint64_t> mate_loop_ptr, is_forward;
+    detail::host_array<uint64_t> source[3], dest[3];  // bits, subaccum, accum
+  };
+  static tables build(session& s) {
+    tables t;
+    uint64_t* src[3];
+    uint64_t* dst[3];
+    detail::ck(bgx_build_readmap_unpaired(s.ctx(), &t.n_rows, &t.read_lengths.p, &t.mate_loop_ptr.p, &t.is_forward.p, src, dst));
+    uint64_t lay[6];
+    detail::ck(bgx_seqset_layout(s.ctx(), lay));
+    t.n_entries = lay[1];
+    t.read_lengths.n = t.mate_loop_ptr.n = t.n_rows;
+    t.is_forward.n = (t.n_rows + 63) / 64;
+    const uint64_t nb[2] = {t.n_entries, t.n_rows};
+    for (int i = 0; i < 3; ++i) {
+      t.source[i].p = src[i];
+      t.dest[i].p = dst[i];
+    }
+    for (int w = 0; w < 2; ++w) {
+      detail::host_array<uint64_t>* a = w ? t.dest : t.source;
+      a[0].n = (nb[w] + 63) / 64;
+      a[1].n = (nb[w] + 511) / 512;
+      a[2].n = (nb[w] + 1 + 511) / 512;
+    }
+    return t;
+  }
+  static tables do_make(const std::string& readmap_file_path, session& s, const std::string& seqset_uuid, bool is_paired,
+                        unsigned max_read_len, progress_handler_t progress = null_progress_handler) {
+    if (is_paired) throw io_exception("make_readmap: paired mate loops are not built on the GPU path");
+    tables t = build(s);
+    seqset_file_writer w(readmap_file_path);
+    w.add("file_info.json", std::string("{\"build_host\":\"bgx\",\"build_is_clean\":true,\"build_revision\":\"") + bgx_version() +
+                                "\",\"build_timestamp\":0,\"build_timestamp_text\":\"\",\"build_user\":\"\",\"command_line\":[],"
+                                "\"create_timestamp\":" + std::to_string((long long)time(nullptr)) +
+                                ",\"create_timestamp_text\":\"\",\"uuid\":\"\"}");
+    w.add("part_info.json", part_info("readmap", 1, 2, 0));
+    w.add("readmap.json", "{\"seqset_uuid\":\"" + seqset_uuid + "\"}");
+    w.add("read_ids/part_info.json", part_info("sparse_multi", 1, 0, 0));
+    const char* dirs[2] = {"read_ids/source_to_mid/", "read_ids/dest_to_mid/"};
+    const uint64_t nb[2] = {t.n_entries, t.n_rows};
+    for (int k = 0; k < 2; ++k) {
+      const detail::host_array<uint64_t>* a = k ? t.dest : t.source;
+      w.add(std::string(dirs[k]) + "part_info.json", part_info("bitcount", 1, 0, 0));
+      w.add(std::string(dirs[k]) + "bitcount.json", "{\"nbits\":" + std::to_string(nb[k]) + "}");
+      w.add(std::string(dirs[k]) + "bits", a[0].p, a[0].n * 8);
+      w.add(std::string(dirs[k]) + "subaccum", a[1].p, a[1].n * 8);
+      w.add(std::string(dirs[k]) + "accum", a[2].p, a[2].n * 8);
+    }
+    // mutable_packed_varbit_vector(state, num_reads, max_read_len) / (state, n, n) (make_readmap.cpp:226-227,254-255)
+    std::vector<uint64_t> lens(t.n_rows);
+    for (uint64_t i = 0; i < t.n_rows; ++i) lens[i] = t.read_lengths.p[i];
+    add_varbit(w, "read_lengths", lens.data(), t.n_rows, max_read_len);
+    add_varbit(w, "mate_loop_ptr", t.mate_loop_ptr.p, t.n_rows, t.n_rows);
+    w.add("is_forward/part_info.json", part_info("packed_vector", 1, 0, 0));
+    w.add("is_forward/packed_data", t.is_forward.p, t.is_forward.n * 8);
+    w.add("is_forward/packed_vector.json", "{\"value_count\":" + std::to_string(t.n_rows) + ",\"value_width_bits\":1}");
+    w.finish();
+    progress(1.0);
+    return t;
+  }
+
+ private:
+  static std::string part_info(const char* type, int major, int minor, int patch) {
+    return std::string("{\"part_type\":\"") + type + "\",\"version\":{\"build\":\"\",\"major\":" + std::to_string(major) +
+           ",\"minor\":" + std::to_string(minor) + ",\"patch\":" + std::to_string(patch) + ",\"pre\":\"\"}}";
+  }
+  // packed_varbit_vector (modules/io/packed_varbit_vector.cpp:174-228): bits_per_value = bit_length(max_value),
+  // values packed LSB-first into little-endian uint64 words
+  static void add_varbit(seqset_file_writer& w, const std::string& name, const uint64_t* vals, uint64_t n, uint64_t max_value) {
+    unsigned bits = 0;
+    while (bits < 64 && (max_value >> bits)) ++bits;
+    std::vector<uint64_t> el((n * bits + 63) / 64, 0);
+    for (uint64_t i = 0; i < n; ++i) {
+      const uint64_t pos = i * bits, q = pos >> 6, sh = pos & 63;
+      el[q] |= vals[i] << sh;
+      if (sh + bits > 64) el[q + 1] |= vals[i] >> (64 - sh);
+    }
+    w.add(name + "/part_info.json", part_info("packed_varbit_vector", 1, 0, 0));
+    w.add(name + "/packed_varbit_vector.json", "{\"bits_per_value\":" + std::to_string(bits) + ",\"element_count\":" +
+                                                   std::to_string(n) + ",\"max_value\":" + std::to_string(max_value) + "}");
+    w.add(name + "/elements", el.data(), el.size() * 8);
+  }
+};
+
 }  // namespace bgx_bs

@@ -80,6 +80,9 @@ int main(int argc, char** argv) {
       size_t fin = expand.sort_and_dedup("pass2_sorted", "pass2_expanded", "complete", "", 0, 0);
       bs::builder b(s);
       bs::seqset_tables t = b.make_seqset(std::string(argv[2]) + "/seqset");           // :944-947
+      // make_readmap::do_make (biograph_create.cpp:818-831), unpaired
+      bs::make_readmap::tables rm = bs::make_readmap::do_make(std::string(argv[2]) + "/readmap", s, "test-uuid", false, 35);
+      std::cout << "{\"case\":\"readmap\",\"rows\":" << rm.n_rows << ",\"entries\":" << rm.n_entries << "}" << std::endl;
       std::cout << "{\"case\":\"create\",\"reads\":" << n_in << ",\"kmers\":" << ks->size() << ",\"corrected_reads\":" << kept
                 << ",\"corrected_bases\":" << bases << ",\"round1\":" << r1 << ",\"entries\":" << fin
                 << ",\"written_entries\":" << t.num_entries << "}" << std::endl;

@@ -46,6 +46,8 @@ def test_facade_create_flow_on_golden(tmp_path, golden, golden_reads):
     for l in lines[:6]:
         assert l["ok"] and l["entries"] == l["expected"]      # bs/builder_test.cpp:52-122
     c = lines[-1]
+    rm = [l for l in lines if l.get("case") == "readmap"][0]
+    assert (rm["rows"], rm["entries"]) == (16888, 19935)
     # golden/e_coli_10000snp.bg/qc/create_log.txt (normative counts)
     assert (c["reads"], c["kmers"], c["corrected_reads"], c["corrected_bases"], c["entries"], c["written_entries"]) == \
         (10000, 7108, 8444, 288464, 19935, 19935)
@@ -68,3 +70,36 @@ def test_facade_create_flow_on_golden(tmp_path, golden, golden_reads):
         assert np.array_equal(vals, np.asarray(golden[gold]).astype(np.uint16))
         el, bits = O.varbit_pack(np.asarray(golden[gold]).astype(np.uint16), meta["max_value"])
         assert bits == meta["bits_per_value"] and z.read(f"{part}/elements") == el.astype("<u8").tobytes()
+
+    # ---- the readmap spiral file (make_readmap::do_make, unpaired) against the golden readmap -----------------
+    gz = np.load(os.path.join(ROOT, "tests", "golden", "e_coli_10000snp_readmap.npz"))
+    zr = zipfile.ZipFile(tmp_path / "readmap")
+    assert zr.testzip() is None
+    assert zr.namelist() == [
+        "file_info.json", "part_info.json", "readmap.json", "read_ids/part_info.json",
+        "read_ids/source_to_mid/part_info.json", "read_ids/source_to_mid/bitcount.json", "read_ids/source_to_mid/bits",
+        "read_ids/source_to_mid/subaccum", "read_ids/source_to_mid/accum",
+        "read_ids/dest_to_mid/part_info.json", "read_ids/dest_to_mid/bitcount.json", "read_ids/dest_to_mid/bits",
+        "read_ids/dest_to_mid/subaccum", "read_ids/dest_to_mid/accum",
+        "read_lengths/part_info.json", "read_lengths/packed_varbit_vector.json", "read_lengths/elements",
+        "mate_loop_ptr/part_info.json", "mate_loop_ptr/packed_varbit_vector.json", "mate_loop_ptr/elements",
+        "is_forward/part_info.json", "is_forward/packed_data", "is_forward/packed_vector.json"]  # order of a reference-built v1.2.0 file
+    assert zr.read("part_info.json") == b'{"part_type":"readmap","version":{"build":"","major":1,"minor":2,"patch":0,"pre":""}}'
+    assert zr.read("readmap.json") == b'{"seqset_uuid":"test-uuid"}'
+    for fn in ("read_ids/part_info.json", "read_ids/source_to_mid/part_info.json", "read_ids/source_to_mid/bitcount.json",
+               "read_ids/dest_to_mid/part_info.json", "read_ids/dest_to_mid/bitcount.json", "is_forward/part_info.json",
+               "is_forward/packed_vector.json"):
+        assert zr.read(fn) == gz[fn.replace("/", "|")].tobytes(), fn
+    for d in ("source_to_mid", "dest_to_mid"):
+        for part in ("bits", "subaccum", "accum"):
+            assert zr.read(f"read_ids/{d}/{part}") == gz[f"read_ids|{d}|{part}"].tobytes(), (d, part)
+    assert zr.read("is_forward/packed_data") == gz["is_forward|packed_data"].tobytes()
+    # the 2018 golden stores read_lengths raw and mate_loop_ptr as 32-bit values; this layout is varbit
+    ml = json.loads(zr.read("read_lengths/packed_varbit_vector.json"))
+    assert ml == {"bits_per_value": 6, "element_count": 16888, "max_value": 35}
+    assert np.array_equal(RS.varbit_decode(zr.read("read_lengths/elements"), 6, 16888), gz["read_lengths"].astype(np.uint16))
+    mp = json.loads(zr.read("mate_loop_ptr/packed_varbit_vector.json"))
+    assert mp == {"bits_per_value": 15, "element_count": 16888, "max_value": 16888}
+    want_ptr = gz["mate_loop_ptr|packed_data"].view("<u4")
+    el, bits = O.varbit_pack(want_ptr.astype(np.uint16), 16888)
+    assert bits == 15 and zr.read("mate_loop_ptr/elements") == el.astype("<u8").tobytes()
