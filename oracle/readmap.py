@@ -14,12 +14,19 @@ Follows modules/bio_mapred/make_readmap.cpp:
             the RC row points back -- for unpaired reads the j-th of a run of identical
             LOOP_START rows gets the j-th row of the matching run of RC rows.
 Pinned against the reference's golden readmap (tests/golden/e_coli_10000snp_readmap.npz, made by
-tests/golden/make_golden_readmap.py): every payload member reproduced.  Paired reads (the MATE /
-MATE_RC rows and the four-row loops) are not restated."""
+tests/golden/make_golden_readmap.py): every payload member reproduced.
+
+Paired reads: readmap_tables_paired is the parallel form (what the GPU computes), and
+readmap_tables_paired_literal transcribes the reference's two passes statement by statement
+(:168-188 rows, :262-300 first pass, :302-360 the sequential claim pass with its `claimed` bit
+vector); tests check the two against each other.  PARITY OF THE PAIRED FORM IS UNPINNED: the only
+readmap in the reference tree that follows the current row order is the unpaired golden (the paired
+readmaps under datasets/ were written by an older build), so the paired form rests on
+the transcription and on the properties the reference's readmap_test.cpp:53-168 checks."""
 import numpy as np
 
 K_NO_LOOP_ENTRY = (1 << 37) - 1
-LOOP_START, RC = 0, 1
+LOOP_START, RC, MATE, MATE_RC = 0, 1, 2, 3
 
 
 def readmap_tables(fwd_entry, rc_entry, lens, n_entries):
@@ -68,3 +75,140 @@ def pack_bits(bits01):
     b = np.asarray(bits01, dtype=np.uint8)
     pad = (-len(b)) % 64
     return np.packbits(np.concatenate([b, np.zeros(pad, np.uint8)]), bitorder="little").view("<u8")
+
+
+def pair_records(fwd_entry, rc_entry, lens, kept):
+    """Reads 2i and 2i+1 are mates (one record per pair, as corrected_reads holds them).  Returns the
+    per-record columns (e, rc_e, ln, me, rc_me, ml) in the reference's canonical orientation:
+    a pair with one read dropped is a single read (read_pair.size() == 1, :157-158), a pair with
+    both dropped is no record, and the read with the smaller sequence is the LOOP_START (:170-175;
+    sequence order == (entry id, length) order, because the entry of a read is the first entry
+    it is a prefix of)."""
+    fwd_entry, rc_entry = np.asarray(fwd_entry, dtype=np.uint64), np.asarray(rc_entry, dtype=np.uint64)
+    lens, kept = np.asarray(lens, dtype=np.uint64), np.asarray(kept, dtype=bool)
+    assert len(lens) % 2 == 0
+    a, b = np.arange(0, len(lens), 2), np.arange(1, len(lens), 2)
+    both = kept[a] & kept[b]
+    swap = both & ((fwd_entry[a] > fwd_entry[b]) | ((fwd_entry[a] == fwd_entry[b]) & (lens[a] > lens[b])))
+    first = np.where(kept[a] & ~swap, a, b)   # the LOOP_START read of the record
+    second = np.where(first == a, b, a)
+    rec = kept[a] | kept[b]
+    first, second, both = first[rec], second[rec], both[rec]
+    z = np.zeros(len(first), np.uint64)
+    return (fwd_entry[first], rc_entry[first], lens[first], np.where(both, fwd_entry[second], z),
+            np.where(both, rc_entry[second], z), np.where(both, lens[second], z))
+
+
+def _paired_rows(e, rc_e, ln, me, rc_me, ml):
+    u = np.uint64
+    e, rc_e, ln = np.asarray(e, dtype=u), np.asarray(rc_e, dtype=u), np.asarray(ln, dtype=u)
+    me, rc_me, ml = np.asarray(me, dtype=u), np.asarray(rc_me, dtype=u), np.asarray(ml, dtype=u)
+    has = ml > 0
+    none = np.full(len(e), K_NO_LOOP_ENTRY, u)
+    zero = np.zeros(len(e), u)
+    k = int(has.sum())
+    entry = np.concatenate([e, rc_e, me[has], rc_me[has]])
+    typ = np.concatenate([np.full(len(e), LOOP_START, u), np.full(len(e), RC, u), np.full(k, MATE, u), np.full(k, MATE_RC, u)])
+    rlen = np.concatenate([ln, ln, ml[has], ml[has]])
+    mlen = np.concatenate([zero, np.where(has, ml, zero), zero[has], zero[has]])
+    loop = np.concatenate([rc_e, np.where(has, me, none), rc_me[has], none[has]])
+    order = np.lexsort((loop, mlen, rlen, typ, entry))  # make_readmap.h:187-205
+    return entry[order], typ[order], rlen[order], mlen[order], loop[order]
+
+
+def _common_tables(entry, rlen, n_entries):
+    m = len(entry)
+    src = np.zeros(n_entries, dtype=np.uint8)
+    src[entry.astype(np.int64)] = 1
+    dst = np.ones(m, dtype=np.uint8)
+    if m:
+        dst[1:] = entry[1:] != entry[:-1]
+    return src, dst
+
+
+def readmap_tables_paired(e, rc_e, ln, me, rc_me, ml, n_entries):
+    """Parallel form.  One element per record; ml == 0: the record is a single read."""
+    u = np.uint64
+    entry, typ, rlen, mlen, loop = _paired_rows(e, rc_e, ln, me, rc_me, ml)
+    m = len(entry)
+    src, dst = _common_tables(entry, rlen, n_entries)
+    idx = np.arange(m, dtype=np.int64)
+    key = (entry << u(12)) | (typ << u(10)) | rlen  # (entry, type, length): what find_first_of searches for
+    ptr = np.zeros(m, dtype=np.int64)
+    # LOOP_START -> RC: the j-th row of a run of identical LOOP_START rows takes the j-th RC row of (loop, length)
+    ls = np.flatnonzero(typ == LOOP_START)
+    rc_idx = np.searchsorted(key, (loop[ls] << u(12)) | (u(RC) << u(10)) | rlen[ls]) + (ls - np.searchsorted(key, key[ls]))
+    assert np.all((typ[rc_idx] == RC) & (entry[rc_idx] == loop[ls]) & (rlen[rc_idx] == rlen[ls]))
+    ptr[ls] = rc_idx
+    solo = loop[rc_idx] == u(K_NO_LOOP_ENTRY)
+    ptr[rc_idx[solo]] = ls[solo]
+    # RC -> MATE: the MATE rows of (loop, mate length) go to their claimers in LOOP_START row order
+    ls_p, rc_p = ls[~solo], rc_idx[~solo]
+    first_mate = np.searchsorted(key, (loop[rc_p] << u(12)) | (u(MATE) << u(10)) | mlen[rc_p])
+    o = np.lexsort((ls_p, first_mate))
+    ls_p, rc_p, first_mate = ls_p[o], rc_p[o], first_mate[o]
+    j = np.arange(len(o), dtype=np.int64)
+    rank = j - np.searchsorted(first_mate, first_mate)
+    mate_idx = first_mate + rank
+    assert np.all((typ[mate_idx] == MATE) & (entry[mate_idx] == loop[rc_p]) & (rlen[mate_idx] == mlen[rc_p]))
+    ptr[rc_p] = mate_idx
+    # MATE -> MATE_RC: same claimers in the same order; MATE_RC -> LOOP_START
+    mrc_idx = np.searchsorted(key, (loop[mate_idx] << u(12)) | (u(MATE_RC) << u(10)) | mlen[rc_p]) + rank
+    assert np.all((typ[mrc_idx] == MATE_RC) & (entry[mrc_idx] == loop[mate_idx]) & (rlen[mrc_idx] == mlen[rc_p]))
+    ptr[mate_idx] = mrc_idx
+    ptr[mrc_idx] = ls_p
+    is_fwd = ((typ == LOOP_START) | (typ == MATE)).astype(np.uint8)
+    return {"n_rows": m, "entry_id": entry, "type": typ, "read_lengths": rlen.astype(np.uint16), "source_to_mid": src,
+            "dest_to_mid": dst, "mate_loop_ptr": ptr.astype(np.uint64), "is_forward": is_fwd, "idx": idx}
+
+
+def readmap_tables_paired_literal(e, rc_e, ln, me, rc_me, ml, n_entries):
+    """make_readmap.cpp:262-360 statement by statement (python loops: small inputs only)."""
+    import bisect
+    entry, typ, rlen, mlen, loop = _paired_rows(e, rc_e, ln, me, rc_me, ml)
+    m = len(entry)
+    src, dst = _common_tables(entry, rlen, n_entries)
+    rows = [(int(entry[i]), int(typ[i]), int(rlen[i]), int(mlen[i]), int(loop[i])) for i in range(m)]
+    ptr = [0] * m
+    is_fwd = [0] * m
+
+    def find_first_of(t, ent, length):
+        return bisect.bisect_left(rows, (ent, t, length, 0, 0))
+
+    for i, (ent, t, length, mlength, lp) in enumerate(rows):  # first pass
+        if t == LOOP_START:
+            is_fwd[i] = 1
+            ptr[i] = find_first_of(RC, lp, length)
+        elif t == RC:
+            if lp != K_NO_LOOP_ENTRY:
+                ptr[i] = find_first_of(MATE, lp, mlength)
+        elif t == MATE:
+            is_fwd[i] = 1
+            ptr[i] = find_first_of(MATE_RC, lp, length)
+    claimed = [False] * m
+
+    def claim_next(try_idx, t, ent, length):
+        assert try_idx < m and rows[try_idx][:3] == (ent, t, length)
+        while claimed[try_idx]:  # claim_next_available
+            try_idx += 1
+        claimed[try_idx] = True
+        assert try_idx < m and rows[try_idx][:3] == (ent, t, length)
+        return try_idx
+
+    for i, (ent, t, length, mlength, lp) in enumerate(rows):  # second pass, in row order
+        if t != LOOP_START:
+            continue
+        rc_i = claim_next(ptr[i], RC, lp, length)
+        ptr[i] = rc_i
+        r = rows[rc_i]
+        if r[4] == K_NO_LOOP_ENTRY:
+            ptr[rc_i] = i
+            continue
+        mate_i = claim_next(ptr[rc_i], MATE, r[4], r[3])
+        ptr[rc_i] = mate_i
+        mr = rows[mate_i]
+        mrc_i = claim_next(ptr[mate_i], MATE_RC, mr[4], r[3])
+        ptr[mate_i] = mrc_i
+        ptr[mrc_i] = i
+    return {"n_rows": m, "entry_id": entry, "type": typ, "read_lengths": rlen.astype(np.uint16), "source_to_mid": src,
+            "dest_to_mid": dst, "mate_loop_ptr": np.array(ptr, dtype=np.uint64), "is_forward": np.array(is_fwd, dtype=np.uint8)}
