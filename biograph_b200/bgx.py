@@ -41,7 +41,7 @@ def build_library(force=False):
 EXPORTS = ["bgx_default_options", "bgx_last_error", "bgx_version", "bgx_device_count", "bgx_create", "bgx_destroy",
            "bgx_free", "bgx_add_reads_ascii", "bgx_add_reads_packed", "bgx_add_reads_packed_async", "bgx_count_kmers", "bgx_export_kmers",
            "bgx_correct", "bgx_export_corrected", "bgx_build_seqset", "bgx_export_seqset",
-           "bgx_export_entries_ascii", "bgx_lookup_reads", "bgx_build_readmap_unpaired", "bgx_run", "bgx_reset_results", "bgx_clear_reads", "bgx_stats_json", "bgx_timer_start", "bgx_timer_stop",
+           "bgx_export_entries_ascii", "bgx_lookup_reads", "bgx_build_readmap", "bgx_run", "bgx_reset_results", "bgx_clear_reads", "bgx_stats_json", "bgx_timer_start", "bgx_timer_stop",
            "bgx_launch_count", "bgx_debug_sort_pairs", "bgx_dist_unique_id", "bgx_dist_init", "bgx_seqset_layout", "bgx_seed_uncorrected", "bgx_export_varbit"]
 
 
@@ -74,7 +74,7 @@ def load_library():
                                     vp * 4, C.c_uint64 * 5]
     L.bgx_export_entries_ascii.argtypes = [vp, C.c_uint64, C.c_uint64, C.POINTER(vp), C.POINTER(vp)]
     L.bgx_lookup_reads.argtypes = [vp, u64p, C.POINTER(vp), C.POINTER(vp)]
-    L.bgx_build_readmap_unpaired.argtypes = [vp, u64p, C.POINTER(vp), C.POINTER(vp), C.POINTER(vp), C.POINTER(vp * 3),
+    L.bgx_build_readmap.argtypes = [vp, C.c_int32, u64p, C.POINTER(vp), C.POINTER(vp), C.POINTER(vp), C.POINTER(vp * 3),
                                              C.POINTER(vp * 3)]
     L.bgx_run.argtypes = [vp]
     L.bgx_reset_results.argtypes = [vp]
@@ -346,12 +346,12 @@ class Bgx:
         self._ck(self.L.bgx_lookup_reads(self.h, C.byref(n), C.byref(pf), C.byref(pr)))
         return self._take(pf, n.value, np.uint64), self._take(pr, n.value, np.uint64)
 
-    def build_readmap_unpaired(self):
-        """make_readmap::create_from_reads for unpaired reads: dict of the readmap's payload arrays"""
+    def build_readmap(self, paired=False):
+        """make_readmap::create_from_reads: dict of the readmap's payload arrays (paired: reads 2i, 2i+1 are mates)"""
         m = C.c_uint64()
         pl, pp, pf = C.c_void_p(), C.c_void_p(), C.c_void_p()
         src, dst = (C.c_void_p * 3)(), (C.c_void_p * 3)()
-        self._ck(self.L.bgx_build_readmap_unpaired(self.h, C.byref(m), C.byref(pl), C.byref(pp), C.byref(pf), C.byref(src),
+        self._ck(self.L.bgx_build_readmap(self.h, 1 if paired else 0, C.byref(m), C.byref(pl), C.byref(pp), C.byref(pf), C.byref(src),
                                                    C.byref(dst)))
         rows = int(m.value)
         n_ent = int(self.stats().get("entries", 0))

@@ -240,9 +240,9 @@ int bgx_lookup_reads(bgx_ctx* x, uint64_t* n_reads, uint64_t** fwd_entry, uint64
   CTX_GUARD({ lookup_reads(c, n_reads, fwd_entry, rc_entry); })
 }
 
-int bgx_build_readmap_unpaired(bgx_ctx* x, uint64_t* n_rows, uint16_t** read_lengths, uint64_t** mate_loop_ptr,
-                               uint64_t** is_forward, uint64_t* read_ids_source[3], uint64_t* read_ids_dest[3]) {
-  CTX_GUARD({ build_readmap_unpaired(c, n_rows, read_lengths, mate_loop_ptr, is_forward, read_ids_source, read_ids_dest); })
+int bgx_build_readmap(bgx_ctx* x, int32_t paired, uint64_t* n_rows, uint16_t** read_lengths, uint64_t** mate_loop_ptr,
+                      uint64_t** is_forward, uint64_t* read_ids_source[3], uint64_t* read_ids_dest[3]) {
+  CTX_GUARD({ build_readmap(c, paired, n_rows, read_lengths, mate_loop_ptr, is_forward, read_ids_source, read_ids_dest); })
 }
 
 int bgx_export_entries_ascii(bgx_ctx* x, uint64_t first, uint64_t count, char** bases, uint64_t** offs) {

@@ -138,7 +138,7 @@ void stage_seed_uncorrected(Context* c);
 void export_varbit(Context* c, int which, uint64_t** words, uint64_t* n_words, uint32_t* bits, uint64_t* max_value);
 void stage_build_seqset(Context* c);
 void lookup_reads(Context* c, uint64_t* n_reads, uint64_t** fwd_entry, uint64_t** rc_entry);
-void build_readmap_unpaired(Context* c, uint64_t* n_rows, uint16_t** read_lengths, uint64_t** mate_loop_ptr,
-                            uint64_t** is_forward, uint64_t* read_ids_source[3], uint64_t* read_ids_dest[3]);
+void build_readmap(Context* c, int paired, uint64_t* n_rows, uint16_t** read_lengths, uint64_t** mate_loop_ptr,
+                   uint64_t** is_forward, uint64_t* read_ids_source[3], uint64_t* read_ids_dest[3]);
 
 }  // namespace bgx

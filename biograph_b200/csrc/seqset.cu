@@ -457,24 +457,50 @@ __global__ void __launch_bounds__(128) lookup_reads_kernel(const uint64_t* __res
 // equal entry and length mean equal sequence, hence an equal loop entry).
 constexpr unsigned long long kNoLoopEntry = (1ULL << 37) - 1;  // make_readmap::k_no_loop_entry
 
+// Rows of one record (make_readmap.cpp:168-188).  Unpaired: a record is a read.  Paired: reads 2i and
+// 2i+1 are mates; a pair with one read dropped is a single read, and the read with the smaller
+// sequence is the LOOP_START (:170-175) -- sequence order is (entry id, length) order, because the
+// entry of a read is the first entry it is a prefix of.
+//   prim = entry << 12 | type << 10 | length      sec = mate_length << 37 | loop entry
+// (prim, sec) ascending is the row order of make_readmap.h:187-205.
 __global__ void readmap_rows_kernel(const unsigned long long* __restrict__ fwd_entry,
                                     const unsigned long long* __restrict__ rc_entry,
                                     const uint16_t* __restrict__ clen, const uint32_t* __restrict__ pos,
-                                    uint32_t n_reads, uint64_t* __restrict__ keys, uint64_t* __restrict__ vals) {
-  const uint32_t r = blockIdx.x * blockDim.x + threadIdx.x;
-  if (r >= n_reads) return;
-  const unsigned long long L = clen[r];
-  if (!L) return;
-  const uint32_t j = pos[r];
-  keys[2 * j] = (fwd_entry[r] << 12) | (0ULL << 10) | L;  // LOOP_START: loops to the entry of the reverse complement
-  vals[2 * j] = rc_entry[r];
-  keys[2 * j + 1] = (rc_entry[r] << 12) | (1ULL << 10) | L;  // RC: no mate
-  vals[2 * j + 1] = kNoLoopEntry;
+                                    uint32_t n_records, int paired, uint64_t* __restrict__ prim,
+                                    uint64_t* __restrict__ sec) {
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n_records) return;
+  uint32_t a = paired ? 2 * i : i, b = paired ? 2 * i + 1 : i;
+  unsigned long long la = clen[a], lb = paired ? clen[b] : 0ULL;
+  if (!la && !lb) return;
+  if (!la || (lb && (fwd_entry[a] > fwd_entry[b] || (fwd_entry[a] == fwd_entry[b] && la > lb)))) {
+    const uint32_t t = a; a = b; b = t;
+    const unsigned long long tl = la; la = lb; lb = tl;
+  }
+  const uint32_t o = pos[i];
+  const unsigned long long e = fwd_entry[a], re = rc_entry[a];
+  prim[o] = (e << 12) | (0ULL << 10) | la;              // LOOP_START -> its reverse complement
+  sec[o] = re;
+  prim[o + 1] = (re << 12) | (1ULL << 10) | la;         // RC -> the mate, if any
+  if (!lb) {
+    sec[o + 1] = kNoLoopEntry;
+    return;
+  }
+  const unsigned long long me = fwd_entry[b], mre = rc_entry[b];
+  sec[o + 1] = (lb << 37) | me;
+  prim[o + 2] = (me << 12) | (2ULL << 10) | lb;         // MATE -> its reverse complement
+  sec[o + 2] = mre;
+  prim[o + 3] = (mre << 12) | (3ULL << 10) | lb;        // MATE_RC -> back to the LOOP_START (claim pass)
+  sec[o + 3] = kNoLoopEntry;
 }
 
-__global__ void single_kept_kernel(const uint16_t* __restrict__ clen, uint32_t n, uint32_t* __restrict__ kept) {
-  const uint32_t r = blockIdx.x * blockDim.x + threadIdx.x;
-  if (r < n) kept[r] = clen[r] ? 1u : 0u;
+// rows per record: 0, 2 or 4
+__global__ void readmap_count_kernel(const uint16_t* __restrict__ clen, uint32_t n_records, int paired,
+                                     uint32_t* __restrict__ cnt) {
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n_records) return;
+  const int ka = clen[paired ? 2 * i : i] != 0, kb = paired ? clen[2 * i + 1] != 0 : 0;
+  cnt[i] = 2u * (uint32_t)(ka + kb);
 }
 
 __device__ __forceinline__ uint32_t lower_bound_u64(const uint64_t* __restrict__ a, uint32_t n, uint64_t x) {
@@ -487,36 +513,50 @@ __device__ __forceinline__ uint32_t lower_bound_u64(const uint64_t* __restrict__
 }
 
 // One thread per sorted row: sparse_multi bits (modules/io/sparse_multi.cpp:90-113), read_lengths,
-// is_forward, and the mate loop: the j-th of a run of identical LOOP_START rows takes the j-th row of
-// the matching run of RC rows (what the sequential claim pass of make_readmap.cpp:302-360 produces),
-// and that RC row points back.
-__global__ void __launch_bounds__(256) readmap_fill_kernel(const uint64_t* __restrict__ keys,
-                                                           const uint64_t* __restrict__ vals, uint32_t m,
+// is_forward, and the start of every mate loop.  The sequential claim pass of make_readmap.cpp:302-360
+// hands the rows of a run of identical rows out in the order in which the LOOP_START rows come by:
+//   * the j-th of a run of identical LOOP_START rows takes the j-th RC row of (loop entry, length);
+//     a single read's RC row points back, a pair's RC row becomes a claimer of its mate's MATE run
+//   * readmap_claim_kernel: the claimers of a MATE run, sorted by LOOP_START row, take its rows in
+//     order; the MATE_RC rows go to the same claimers in the same order and close the loops.
+__global__ void __launch_bounds__(256) readmap_fill_kernel(const uint64_t* __restrict__ prim,
+                                                           const uint64_t* __restrict__ sec, uint32_t m,
                                                            unsigned long long* __restrict__ src_bits,
                                                            uint32_t* __restrict__ dst_bits32,
                                                            uint32_t* __restrict__ fwd_bits32,
                                                            uint16_t* __restrict__ read_lengths,
-                                                           unsigned long long* __restrict__ ptr, int* __restrict__ missing) {
+                                                           unsigned long long* __restrict__ ptr,
+                                                           uint64_t* __restrict__ claim_key, uint64_t* __restrict__ claim_val,
+                                                           unsigned int* __restrict__ n_claims, int* __restrict__ missing) {
   const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
   bool opens = false, is_fwd = false;
   if (i < m) {
-    const uint64_t key = keys[i];
+    const uint64_t key = prim[i];
     const uint64_t entry = key >> 12;
     const unsigned type = (unsigned)(key >> 10) & 3u;
     const uint64_t len = key & 1023u;
-    opens = i == 0 || (keys[i - 1] >> 12) != entry;
-    is_fwd = type == 0;
+    opens = i == 0 || (prim[i - 1] >> 12) != entry;
+    is_fwd = type == 0 || type == 2;
     read_lengths[i] = (uint16_t)len;
     if (opens) atomicOr(&src_bits[entry >> 6], 1ULL << (entry & 63));
-    if (is_fwd) {
-      const uint32_t rank = i - lower_bound_u64(keys, m, key);
-      const uint64_t want = (vals[i] << 12) | (1ULL << 10) | len;
-      const uint32_t tgt = lower_bound_u64(keys, m, want) + rank;
-      if (tgt >= m || keys[tgt] != want) {
+    if (type == 0) {
+      const uint32_t rank = i - lower_bound_u64(prim, m, key);
+      const uint64_t want = ((sec[i] & kNoLoopEntry) << 12) | (1ULL << 10) | len;
+      const uint32_t rc = lower_bound_u64(prim, m, want) + rank;
+      if (rc >= m || prim[rc] != want) {
         *missing = 1;
       } else {
-        ptr[i] = tgt;
-        ptr[tgt] = i;
+        ptr[i] = rc;
+        const uint64_t rsec = sec[rc];
+        if ((rsec & kNoLoopEntry) == kNoLoopEntry) {
+          ptr[rc] = i;  // no mate: just point back to the original
+        } else {
+          const uint64_t mwant = ((rsec & kNoLoopEntry) << 12) | (2ULL << 10) | (rsec >> 37);
+          const uint32_t first_mate = lower_bound_u64(prim, m, mwant);
+          const unsigned c = atomicAdd(n_claims, 1u);
+          claim_key[c] = ((uint64_t)first_mate << 32) | i;
+          claim_val[c] = rc;
+        }
       }
     }
   }
@@ -525,6 +565,27 @@ __global__ void __launch_bounds__(256) readmap_fill_kernel(const uint64_t* __res
     dst_bits32[i >> 5] = d;
     fwd_bits32[i >> 5] = f;
   }
+}
+
+__global__ void readmap_claim_kernel(const uint64_t* __restrict__ prim, const uint64_t* __restrict__ sec, uint32_t m,
+                                     const uint64_t* __restrict__ claim_key, const uint64_t* __restrict__ claim_val,
+                                     uint32_t n_claims, unsigned long long* __restrict__ ptr, int* __restrict__ missing) {
+  const uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= n_claims) return;
+  const uint64_t ck = claim_key[j];
+  const uint32_t first_mate = (uint32_t)(ck >> 32), ls = (uint32_t)ck, rc = (uint32_t)claim_val[j];
+  const uint32_t rank = j - lower_bound_u64(claim_key, n_claims, (uint64_t)first_mate << 32);
+  const uint64_t rsec = sec[rc];
+  const uint64_t mlen = rsec >> 37;
+  const uint32_t mate = first_mate + rank;
+  const uint64_t mwant = ((rsec & kNoLoopEntry) << 12) | (2ULL << 10) | mlen;
+  if (mate >= m || prim[mate] != mwant) { *missing = 1; return; }
+  const uint64_t rwant = ((sec[mate] & kNoLoopEntry) << 12) | (3ULL << 10) | mlen;
+  const uint32_t mrc = lower_bound_u64(prim, m, rwant) + rank;
+  if (mrc >= m || prim[mrc] != rwant) { *missing = 1; return; }
+  ptr[rc] = mate;
+  ptr[mate] = mrc;
+  ptr[mrc] = ls;  // save loop back to the beginning
 }
 
 // ---- merge of the (few) new records into the sorted survivors ----------------------------------------
@@ -1725,43 +1786,49 @@ static void bitcount_to_host(Context* c, const unsigned long long* bits, uint64_
   BGX_CUDA(cudaStreamSynchronize(s));
 }
 
-void build_readmap_unpaired(Context* c, uint64_t* n_rows, uint16_t** read_lengths, uint64_t** mate_loop_ptr,
-                            uint64_t** is_forward, uint64_t* read_ids_source[3], uint64_t* read_ids_dest[3]) {
-  BGX_CHECK(c->built, "bgx_build_readmap_unpaired: call bgx_build_seqset first");
-  BGX_CHECK(c->dist.nranks == 1, "bgx_build_readmap_unpaired: single-GPU builds only");
+void build_readmap(Context* c, int paired, uint64_t* n_rows, uint16_t** read_lengths, uint64_t** mate_loop_ptr,
+                   uint64_t** is_forward, uint64_t* read_ids_source[3], uint64_t* read_ids_dest[3]) {
+  BGX_CHECK(c->built, "bgx_build_readmap: call bgx_build_seqset first");
+  BGX_CHECK(c->dist.nranks == 1, "bgx_build_readmap: single-GPU builds only");
   BGX_CHECK(c->n_entries < kNoLoopEntry, "Entry id too long to fit in mate loop table entry");  // make_readmap.h:77
+  BGX_CHECK(!paired || c->n_reads % 2 == 0, "bgx_build_readmap: paired input needs an even number of reads (mates are reads 2i, 2i+1)");
   cudaStream_t s = c->stream;
   ScopedStage st(c, "readmap");
   const uint64_t n = c->n_reads;
+  const uint64_t n_rec = paired ? n / 2 : n;
   const uint32_t n_ent = (uint32_t)c->n_entries;
   // 1. the entry of every read and of its reverse complement (find_existing_unique, make_readmap.cpp:137-167)
   DevBuf<unsigned long long> d_f(std::max<uint64_t>(n, 1), s), d_v(std::max<uint64_t>(n, 1), s);
   DevBuf<int> missing(1, s);
   BGX_CUDA(cudaMemsetAsync(missing.p, 0, sizeof(int), s));
   DevBuf<uint32_t> index_buf;
-  DevBuf<uint32_t> kept(std::max<uint64_t>(n, 1), s), pos(std::max<uint64_t>(n, 1), s), tot(1, s);
+  DevBuf<uint32_t> cnt(std::max<uint64_t>(n_rec, 1), s), pos(std::max<uint64_t>(n_rec, 1), s), tot(1, s);
   BGX_CUDA(cudaMemsetAsync(tot.p, 0, 4, s));
   if (n) {
     const BucketIndex bi = build_bucket_index(c, c->ent_key.p, n_ent, index_buf);
     KLAUNCH(lookup_reads_kernel)<<<grid_for(n, 128), 128, 0, s>>>(c->store.p, c->ent_key.p, c->ent_loc.p, n_ent, bi, c->word_off.p,
                                                           c->clen.p, c->n_words, (uint32_t)n, d_f.p, d_v.p, missing.p);
-    // seed_count_kernel with next_fwd = next_rev = clen would do; a kept flag is all that is needed
-    KLAUNCH(single_kept_kernel)<<<grid_for(n, 256), 256, 0, s>>>(c->clen.p, (uint32_t)n, kept.p);
-    exclusive_scan_u32(kept.p, pos.p, n, tot.p, s);
+    KLAUNCH(readmap_count_kernel)<<<grid_for(n_rec, 256), 256, 0, s>>>(c->clen.p, (uint32_t)n_rec, paired, cnt.p);
+    exclusive_scan_u32(cnt.p, pos.p, n_rec, tot.p, s);
     BGX_CUDA(cudaGetLastError());
   }
-  const uint32_t n_kept = read_u32(tot.p, s);
+  const uint32_t m = read_u32(tot.p, s);
   BGX_CHECK(!read_flag_i(missing.p, s), "a corrected read was not found in seqset");  // make_readmap.cpp:150-154
-  const uint32_t m = 2 * n_kept;
-  BGX_CHECK((uint64_t)n_kept * 2 < (1ull << 32), "too many reads for one readmap shard");
   *n_rows = m;
-  // 2. rows, sorted
+  // 2. rows, sorted by (prim, sec): LSD, the secondary key first
   DevBuf<uint64_t> k0((size_t)m + 1, s), v0((size_t)m + 1, s), k1((size_t)m + 1, s), v1((size_t)m + 1, s);
-  const uint64_t *keys = k0.p, *vals = v0.p;
+  const uint64_t *prim = k0.p, *sec = v0.p;
   if (m) {
-    KLAUNCH(readmap_rows_kernel)<<<grid_for(n, 256), 256, 0, s>>>(d_f.p, d_v.p, c->clen.p, pos.p, (uint32_t)n, k0.p, v0.p);
+    KLAUNCH(readmap_rows_kernel)<<<grid_for(n_rec, 256), 256, 0, s>>>(d_f.p, d_v.p, c->clen.p, pos.p, (uint32_t)n_rec, paired, k0.p,
+                                                              v0.p);
     BGX_CUDA(cudaGetLastError());
-    if (radix_sort_pairs(k0.p, v0.p, k1.p, v1.p, m, 0, 56, s)) { keys = k1.p; vals = v1.p; }  // 37 + 2 + 10 key bits
+    // pass A: key = sec (10 + 37 bits), value = prim
+    uint64_t *sk = v0.p, *sv = k0.p, *sk_alt = v1.p, *sv_alt = k1.p;
+    if (radix_sort_pairs(sk, sv, sk_alt, sv_alt, m, 0, 48, s)) { std::swap(sk, sk_alt); std::swap(sv, sv_alt); }
+    // pass B: key = prim (37 + 2 + 10 bits), value = sec; stable, so ties keep the order of pass A
+    if (radix_sort_pairs(sv, sk, sv_alt, sk_alt, m, 0, 56, s)) { std::swap(sk, sk_alt); std::swap(sv, sv_alt); }
+    prim = sv;
+    sec = sk;
   }
   // 3. tables
   const uint64_t src_words = ((uint64_t)n_ent + 63) / 64, row_words = ((uint64_t)m + 63) / 64;
@@ -1772,11 +1839,25 @@ void build_readmap_unpaired(Context* c, uint64_t* n_rows, uint16_t** read_length
   BGX_CUDA(cudaMemsetAsync(dst_bits.p, 0, std::max<uint64_t>(row_words, 1) * 8, s));
   BGX_CUDA(cudaMemsetAsync(fwd_bits.p, 0, std::max<uint64_t>(row_words, 1) * 8, s));
   if (m) {
-    KLAUNCH(readmap_fill_kernel)<<<grid_for(m, 256), 256, 0, s>>>(keys, vals, m, src_bits.p, reinterpret_cast<uint32_t*>(dst_bits.p),
-                                                          reinterpret_cast<uint32_t*>(fwd_bits.p), lens.p, ptr.p, missing.p);
+    const uint32_t max_claims = m / 4 + 1;  // one per pair
+    DevBuf<uint64_t> ck0(max_claims, s), cv0(max_claims, s), ck1(max_claims, s), cv1(max_claims, s);
+    DevBuf<unsigned int> n_claims_d(1, s);
+    BGX_CUDA(cudaMemsetAsync(n_claims_d.p, 0, 4, s));
+    KLAUNCH(readmap_fill_kernel)<<<grid_for(m, 256), 256, 0, s>>>(prim, sec, m, src_bits.p, reinterpret_cast<uint32_t*>(dst_bits.p),
+                                                          reinterpret_cast<uint32_t*>(fwd_bits.p), lens.p, ptr.p, ck0.p, cv0.p,
+                                                          n_claims_d.p, missing.p);
     BGX_CUDA(cudaGetLastError());
+    const uint32_t n_claims = read_u32(n_claims_d.p, s);
+    BGX_CHECK(n_claims < max_claims, "internal: more mate claims than pairs");
+    if (n_claims) {
+      const uint64_t *ck = ck0.p, *cv = cv0.p;
+      if (radix_sort_pairs(ck0.p, cv0.p, ck1.p, cv1.p, n_claims, 0, 64, s)) { ck = ck1.p; cv = cv1.p; }
+      KLAUNCH(readmap_claim_kernel)<<<grid_for(n_claims, 256), 256, 0, s>>>(prim, sec, m, ck, cv, n_claims, ptr.p, missing.p);
+      BGX_CUDA(cudaGetLastError());
+    }
+    c->set_stat("readmap_pairs", n_claims);
   }
-  BGX_CHECK(!read_flag_i(missing.p, s), "internal: a LOOP_START row has no RC row to claim");
+  BGX_CHECK(!read_flag_i(missing.p, s), "internal: a mate loop row has no row to claim");
   // 4. out
   bitcount_to_host(c, src_bits.p, n_ent, read_ids_source);
   bitcount_to_host(c, dst_bits.p, m, read_ids_dest);

@@ -145,16 +145,23 @@ int bgx_export_varbit(bgx_ctx* ctx, int32_t which, uint64_t** words, uint64_t* n
  * Arrays are bgx_free()'d by the caller. */
 int bgx_lookup_reads(bgx_ctx* ctx, uint64_t* n_reads, uint64_t** fwd_entry, uint64_t** rc_entry);
 
-/* replaces, for UNPAIRED reads: make_readmap::create_from_reads (modules/bio_mapred/make_readmap.cpp:229-362;
- * rows and their order make_readmap.h:53-76,187-205; sparse_multi_builder modules/io/sparse_multi.cpp:90-113).
- * Two rows per kept read (the read, its reverse complement), sorted by (entry id, type, length):
- *   read_lengths[i], mate_loop_ptr[i] (the row of the other strand of the same read), is_forward
- *   (bit i, uint64 words LSB-first), and the two bitcount vectors of `read_ids` as
- *   {bits, subaccum, accum}: source_to_mid over the seqset entries, dest_to_mid over the rows.
- * The payload members of the readmap spiral file are these arrays (read_lengths and mate_loop_ptr
- * go through packed_varbit_vector on the host).  Paired mate loops are not built.  Single GPU only. */
-int bgx_build_readmap_unpaired(bgx_ctx* ctx, uint64_t* n_rows, uint16_t** read_lengths, uint64_t** mate_loop_ptr,
-                               uint64_t** is_forward, uint64_t* read_ids_source[3], uint64_t* read_ids_dest[3]);
+/* replaces: make_readmap::create_from_reads (modules/bio_mapred/make_readmap.cpp:229-362; rows and their
+ * order make_readmap.h:53-76,187-205; sparse_multi_builder modules/io/sparse_multi.cpp:90-113).
+ * paired = 0: every read is a record (two rows: the read, its reverse complement).
+ * paired != 0: reads 2i and 2i+1 are mates (four rows; a pair with one read dropped is a single
+ *   read; the read with the smaller sequence starts the loop, make_readmap.cpp:170-175).
+ * Rows sorted by (entry id, type, length, mate length, loop entry):
+ *   read_lengths[i], mate_loop_ptr[i] (next row of the read's mate loop: read -> its reverse
+ *   complement [-> mate -> mate's reverse complement] -> read, rows of identical reads handed
+ *   out in the order of the reference's claim pass, :302-360), is_forward (bit i, uint64 words
+ *   LSB-first), and the two bitcount vectors of `read_ids` as {bits, subaccum, accum}:
+ *   source_to_mid over the seqset entries, dest_to_mid over the rows.
+ * These are the payload members of the readmap spiral file (read_lengths and mate_loop_ptr go
+ * through packed_varbit_vector on the host).  Single GPU only.  Parity: the unpaired form is
+ * pinned to the reference's golden readmap; the paired form to a transcription of the reference
+ * code (no reference-built paired readmap in the current row order exists in its tree). */
+int bgx_build_readmap(bgx_ctx* ctx, int32_t paired, uint64_t* n_rows, uint16_t** read_lengths, uint64_t** mate_loop_ptr,
+                      uint64_t** is_forward, uint64_t* read_ids_source[3], uint64_t* read_ids_dest[3]);
 
 /* Debug/parity hook: entry i as ASCII (entries are <= BGX_MAX_READ_LEN bases). */
 int bgx_export_entries_ascii(bgx_ctx* ctx, uint64_t first, uint64_t count, char** bases,

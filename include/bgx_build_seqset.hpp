@@ -474,10 +474,10 @@ inline seqset_tables seqset_for_reads(const std::vector<std::string>& reads, con
   return path.empty() ? b.tables() : b.make_seqset(path);
 }
 
-// make_readmap::do_make (modules/bio_mapred/make_readmap.{h,cpp}; called at biograph_create.cpp:818-831) for
-// UNPAIRED inputs: the tables come from bgx_build_readmap_unpaired, the spiral file is written here in
-// the reference's member order (readmap 1.2.0: readmap.cpp:13; sparse_multi 1.0.0; packed_varbit_vector
-// 1.0.0; packed_vector 1.0.0).  A paired input throws: the MATE / MATE_RC loops are not built.
+// make_readmap::do_make (modules/bio_mapred/make_readmap.{h,cpp}; called at biograph_create.cpp:818-831):
+// the tables come from bgx_build_readmap, the spiral file is written here in the reference's member
+// order (readmap 1.2.0: readmap.cpp:13; sparse_multi 1.0.0; packed_varbit_vector 1.0.0; packed_vector
+// 1.0.0).
 class make_readmap {
  public:
   struct tables {
@@ -486,11 +486,11 @@ class make_readmap {
     detail::host_array<uint64_t> mate_loop_ptr, is_forward;
     detail::host_array<uint64_t> source[3], dest[3];  // bits, subaccum, accum
   };
-  static tables build(session& s) {
+  static tables build(session& s, bool is_paired = false) {
     tables t;
     uint64_t* src[3];
     uint64_t* dst[3];
-    detail::ck(bgx_build_readmap_unpaired(s.ctx(), &t.n_rows, &t.read_lengths.p, &t.mate_loop_ptr.p, &t.is_forward.p, src, dst));
+    detail::ck(bgx_build_readmap(s.ctx(), is_paired ? 1 : 0, &t.n_rows, &t.read_lengths.p, &t.mate_loop_ptr.p, &t.is_forward.p, src, dst));
     uint64_t lay[6];
     detail::ck(bgx_seqset_layout(s.ctx(), lay));
     t.n_entries = lay[1];
@@ -511,8 +511,7 @@ class make_readmap {
   }
   static tables do_make(const std::string& readmap_file_path, session& s, const std::string& seqset_uuid, bool is_paired,
                         unsigned max_read_len, progress_handler_t progress = null_progress_handler) {
-    if (is_paired) throw io_exception("make_readmap: paired mate loops are not built on the GPU path");
-    tables t = build(s);
+    tables t = build(s, is_paired);  // paired: reads 2i and 2i+1 of the session are mates
     seqset_file_writer w(readmap_file_path);
     w.add("file_info.json", std::string("{\"build_host\":\"bgx\",\"build_is_clean\":true,\"build_revision\":\"") + bgx_version() +
                                 "\",\"build_timestamp\":0,\"build_timestamp_text\":\"\",\"build_user\":\"\",\"command_line\":[],"

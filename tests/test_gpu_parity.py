@@ -301,7 +301,7 @@ def test_lookup_reads_matches_bisect(B, golden_reads, which):
 
 @pytest.mark.parametrize("which", ["golden", "synthetic_dups"])
 def test_readmap_unpaired(B, golden_reads, which):
-    """bgx_build_readmap_unpaired against the CPU restatement (oracle/readmap.py, pinned to the
+    """bgx_build_readmap (unpaired) against the CPU restatement (oracle/readmap.py, pinned to the
     reference's golden readmap) and, for the golden reads, against the golden members themselves."""
     from oracle import readmap as RM
     if which == "golden":
@@ -312,7 +312,7 @@ def test_readmap_unpaired(B, golden_reads, which):
         reads = sim + sim[:500] * 3 + [O.revcomp(r) for r in sim[:300]]
     g, km, cr, ss, st = run_gpu(B, reads)
     fwd, rc = g.lookup_reads()
-    got = g.build_readmap_unpaired()
+    got = g.build_readmap()
     kept = cr["kept"].astype(bool)
     want = RM.readmap_tables(fwd[kept], rc[kept], cr["lens"][kept], ss["n"])
     assert got["n_rows"] == want["n_rows"] == 2 * int(kept.sum())
@@ -333,6 +333,47 @@ def test_readmap_unpaired(B, golden_reads, which):
         for name in ("source_to_mid", "dest_to_mid"):
             for part in ("bits", "subaccum", "accum"):
                 assert np.array_equal(got[name][part], z[f"read_ids|{name}|{part}"].view("<u8")), (name, part)
+    g.close()
+
+
+def test_readmap_paired(B):
+    """bgx_build_readmap(paired): reads 2i, 2i+1 are mates.  Against oracle/readmap.py's paired form (which
+    tests/test_oracle_readmap.py checks against a literal transcription of the reference's claim pass):
+    identical reads with different mates, duplicate pairs, pairs with a dropped read."""
+    from oracle import readmap as RM
+    buf, offs = _sim(4000, 3000, 100, 0.004, 57)   # paired simulation: reads 2i, 2i+1 are the two ends of a fragment
+    sim = [buf[offs[i]:offs[i + 1]].decode() for i in range(len(offs) - 1)]
+    reads = list(sim)
+    rng = np.random.default_rng(58)
+    for _ in range(400):   # same first read, another pair's mate
+        i, j = int(rng.integers(0, len(sim) // 2)), int(rng.integers(0, len(sim) // 2))
+        reads += [sim[2 * i], sim[2 * j + 1]]
+    for _ in range(400):   # exact duplicate pairs, and pairs given the other way round
+        i = int(rng.integers(0, len(sim) // 2))
+        reads += [sim[2 * i], sim[2 * i + 1], sim[2 * i + 1], sim[2 * i]]
+    reads += ["ACGT" * 5, sim[0], sim[1], "TTTTTTTTTTTTTTTTTTTTTTTTTTTTTTTTTTT"]  # pairs with a read the corrector drops
+    assert len(reads) % 2 == 0
+    g, km, cr, ss, st = run_gpu(B, reads)
+    kept = cr["kept"].astype(bool)
+    assert (~kept).any() and kept.any()
+    fwd, rc = g.lookup_reads()
+    cols = RM.pair_records(fwd, rc, cr["lens"], kept)
+    want = RM.readmap_tables_paired(*cols, ss["n"])
+    got = g.build_readmap(paired=True)
+    assert st is not None and got["n_rows"] == want["n_rows"] > 0
+    assert int((cols[5] > 0).sum()) > 1000   # real pairs present
+    assert np.array_equal(got["read_lengths"], want["read_lengths"])
+    assert np.array_equal(got["is_forward"], RM.pack_bits(want["is_forward"]))
+    assert np.array_equal(got["mate_loop_ptr"], want["mate_loop_ptr"])
+    for name, nbits in (("source_to_mid", ss["n"]), ("dest_to_mid", want["n_rows"])):
+        words = RM.pack_bits(want[name])
+        assert np.array_equal(got[name]["bits"], words), name
+        sub, acc, _ = O.bitcount_finalize(words, nbits)
+        assert np.array_equal(got[name]["subaccum"], sub) and np.array_equal(got[name]["accum"], acc), name
+    # unpaired build of the same reads still matches the unpaired restatement
+    got_u = g.build_readmap()
+    want_u = RM.readmap_tables(fwd[kept], rc[kept], cr["lens"][kept], ss["n"])
+    assert np.array_equal(got_u["mate_loop_ptr"], want_u["mate_loop_ptr"])
     g.close()
 
 
