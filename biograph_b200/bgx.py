@@ -39,7 +39,7 @@ def build_library(force=False):
 
 
 EXPORTS = ["bgx_default_options", "bgx_last_error", "bgx_version", "bgx_device_count", "bgx_create", "bgx_destroy",
-           "bgx_free", "bgx_add_reads_ascii", "bgx_add_reads_packed", "bgx_add_reads_packed_async", "bgx_count_kmers", "bgx_export_kmers",
+           "bgx_free", "bgx_add_reads_ascii", "bgx_add_reads_fastq", "bgx_add_reads_packed", "bgx_add_reads_packed_async", "bgx_count_kmers", "bgx_export_kmers",
            "bgx_correct", "bgx_export_corrected", "bgx_build_seqset", "bgx_export_seqset",
            "bgx_export_entries_ascii", "bgx_lookup_reads", "bgx_build_readmap", "bgx_run", "bgx_reset_results", "bgx_clear_reads", "bgx_stats_json", "bgx_timer_start", "bgx_timer_stop",
            "bgx_launch_count", "bgx_debug_sort_pairs", "bgx_dist_unique_id", "bgx_dist_init", "bgx_seqset_layout", "bgx_seed_uncorrected", "bgx_export_varbit"]
@@ -62,6 +62,7 @@ def load_library():
     L.bgx_destroy.argtypes = [vp]
     L.bgx_free.argtypes = [vp]
     L.bgx_add_reads_ascii.argtypes = [vp, vp, vp, C.c_uint64]
+    L.bgx_add_reads_fastq.argtypes = [vp, C.c_char_p, C.c_uint64, u64p]
     L.bgx_add_reads_packed.argtypes = [vp, vp, vp, vp, vp, C.c_uint64]
     L.bgx_add_reads_packed_async.argtypes = [vp, vp, vp, vp, vp, C.c_uint64]
     L.bgx_count_kmers.argtypes = [vp]
@@ -236,6 +237,12 @@ class Bgx:
             self._keep = C.create_string_buffer(buf, len(buf)) if len(buf) else C.create_string_buffer(1)
             p = C.addressof(self._keep)
         self._ck(self.L.bgx_add_reads_ascii(self.h, p, offs.ctypes.data, len(offs) - 1))
+
+    def add_reads_fastq(self, text):
+        """text: bytes of uncompressed FASTQ (whole records); returns the number of reads added"""
+        n = C.c_uint64()
+        self._ck(self.L.bgx_add_reads_fastq(self.h, text, len(text), C.byref(n)))
+        return int(n.value)
 
     def add_reads_packed(self, packed, nmask, word_offs, lens):
         self._ck(self.L.bgx_add_reads_packed(self.h, packed.ctypes.data, None if nmask is None else nmask.ctypes.data,

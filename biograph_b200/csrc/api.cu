@@ -155,6 +155,10 @@ int bgx_add_reads_ascii(bgx_ctx* x, const char* bases, const uint64_t* offs, uin
   CTX_GUARD({ reads_append_ascii(c, bases, offs, n_reads); })
 }
 
+int bgx_add_reads_fastq(bgx_ctx* x, const char* text, uint64_t size, uint64_t* n_reads) {
+  CTX_GUARD({ reads_append_fastq(c, text, size, n_reads); })
+}
+
 int bgx_add_reads_packed(bgx_ctx* x, const uint8_t* packed, const uint32_t* n_mask, const uint64_t* word_offs,
                          const uint16_t* lens, uint64_t n_reads) {
   CTX_GUARD({ reads_append_packed(c, packed, n_mask, word_offs, lens, n_reads); })

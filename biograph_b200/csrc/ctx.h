@@ -128,6 +128,7 @@ struct ScopedStage {
 void reads_append_ascii(Context* c, const char* bases, const uint64_t* offs, uint64_t n);
 void reads_append_packed(Context* c, const uint8_t* packed, const uint32_t* n_mask, const uint64_t* word_offs,
                          const uint16_t* lens, uint64_t n, bool async = false);
+void reads_append_fastq(Context* c, const char* text, uint64_t size, uint64_t* n_added);
 // orders every pending upload chunk before whatever the main stream does next (and forgets them)
 void reads_ready(Context* c);
 void stage_count_kmers(Context* c);

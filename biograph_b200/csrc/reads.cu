@@ -14,11 +14,13 @@ __global__ void __launch_bounds__(256) pack_ascii_kernel(const char* __restrict_
                                                          const uint64_t* __restrict__ offs, uint64_t n_reads,
                                                          const uint32_t* __restrict__ word_off,
                                                          uint64_t* __restrict__ words, uint32_t* __restrict__ nmask,
-                                                         int* __restrict__ any_n) {
+                                                         int* __restrict__ any_n,
+                                                         const uint16_t* __restrict__ lens16) {
   uint64_t r = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   if (r >= n_reads) return;
   unsigned lane = lane_id();
-  uint64_t b0 = offs[r], len = offs[r + 1] - b0;
+  // lens16 given: offs[r] is where read r starts in the text (FASTQ: the reads are not contiguous)
+  uint64_t b0 = offs[r], len = lens16 ? (uint64_t)lens16[r] : offs[r + 1] - b0;
   unsigned nw = (unsigned)((len + 31) >> 5);
   bool sawn = false;
   for (unsigned w = lane; w < nw; w += 32) {
@@ -43,6 +45,72 @@ __global__ void __launch_bounds__(256) pack_ascii_kernel(const char* __restrict_
     sawn |= (m != 0);
   }
   if (sawn) *any_n = 1;
+}
+
+// ---- FASTQ text -> reads (semantics of fastq_reader::read, modules/bio_format/fastq.cpp:40-126) --
+// Line ends are found in two passes over the text (count per 256-byte chunk, scan, write), then
+// one thread per record checks its four lines the way the reference does and hands the position
+// and length of the sequence line to the packing kernel.  The first failing line wins
+// (line number << 4 | error code, atomicMin).
+constexpr int kFqChunk = 256;
+enum FqError : unsigned {
+  FQ_ID_SHORT = 1, FQ_ID_AT, FQ_SEQ_EMPTY, FQ_SEQ_CHARS, FQ_PLUS_EMPTY, FQ_PLUS, FQ_QUAL_LEN, FQ_TOO_LONG, FQ_BLANK
+};
+
+__global__ void fq_count_kernel(const char* __restrict__ text, uint64_t size, uint32_t* __restrict__ cnt) {
+  const uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const uint64_t b = t * kFqChunk;
+  if (b >= size) return;
+  const uint64_t e = min(size, b + kFqChunk);
+  uint32_t n = 0;
+  for (uint64_t i = b; i < e; ++i) n += text[i] == '\n';
+  cnt[t] = n;
+}
+
+__global__ void fq_positions_kernel(const char* __restrict__ text, uint64_t size, const uint32_t* __restrict__ first,
+                                    uint64_t* __restrict__ nl_pos) {
+  const uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const uint64_t b = t * kFqChunk;
+  if (b >= size) return;
+  const uint64_t e = min(size, b + kFqChunk);
+  uint32_t o = first[t];
+  for (uint64_t i = b; i < e; ++i)
+    if (text[i] == '\n') nl_pos[o++] = i;
+}
+
+__global__ void fq_records_kernel(const char* __restrict__ text, const uint64_t* __restrict__ nl_pos, uint64_t n_records,
+                                  uint64_t* __restrict__ seq_start, uint16_t* __restrict__ seq_len,
+                                  unsigned long long* __restrict__ first_error) {
+  const uint64_t r = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= n_records) return;
+  uint64_t st[4], ln[4];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const uint64_t li = 4 * r + j;
+    st[j] = li ? nl_pos[li - 1] + 1 : 0;
+    ln[j] = nl_pos[li] - st[j];
+  }
+  unsigned err = 0;
+  int bad_line = 0;
+  if (ln[0] == 0) { err = FQ_BLANK; bad_line = 0; }
+  else if (ln[0] < 2) { err = FQ_ID_SHORT; bad_line = 0; }
+  else if (text[st[0]] != '@') { err = FQ_ID_AT; bad_line = 0; }
+  else if (ln[1] == 0) { err = FQ_SEQ_EMPTY; bad_line = 1; }
+  else if (ln[1] > BGX_MAX_READ_LEN) { err = FQ_TOO_LONG; bad_line = 1; }
+  else {
+    for (uint64_t i = 0; i < ln[1]; ++i) {
+      const char ch = text[st[1] + i];
+      if (ch != 'A' && ch != 'C' && ch != 'G' && ch != 'T' && ch != 'N') { err = FQ_SEQ_CHARS; bad_line = 1; break; }
+    }
+    if (!err) {
+      if (ln[2] == 0) { err = FQ_PLUS_EMPTY; bad_line = 2; }
+      else if (text[st[2]] != '+') { err = FQ_PLUS; bad_line = 2; }
+      else if (ln[3] != ln[1]) { err = FQ_QUAL_LEN; bad_line = 3; }
+    }
+  }
+  if (err) atomicMin(first_error, ((unsigned long long)(4 * r + bad_line + 1) << 4) | err);
+  seq_start[r] = st[1];
+  seq_len[r] = (uint16_t)min(ln[1], (uint64_t)BGX_MAX_READ_LEN);
 }
 
 __global__ void bswap_words_kernel(uint64_t* __restrict__ w, uint64_t n) {
@@ -149,9 +217,75 @@ void reads_append_ascii(Context* c, const char* bases, const uint64_t* offs, uin
   uint64_t threads = n * 32;
   KLAUNCH(pack_ascii_kernel)<<<(unsigned)((threads + 255) / 256), 256, 0, s>>>(d_bases.p, d_offs.p, n,
                                                                       c->word_off.p + c->n_reads, c->words.p,
-                                                                      c->nmask.p, d_flag.p);
+                                                                      c->nmask.p, d_flag.p, nullptr);
   BGX_CUDA(cudaGetLastError());
   c->add_stat("h2d_bytes", (double)nbytes + (double)(n + 1) * 12 + (double)n * 2);
+  finish_append(c, lens, woff, d_flag.p);
+}
+
+void reads_append_fastq(Context* c, const char* text, uint64_t size, uint64_t* n_added) {
+  *n_added = 0;
+  if (size == 0) return;
+  reads_ready(c);
+  cudaStream_t s = c->stream;
+  // a last line without its newline: the reference's readline fails on it (fastq.cpp:49-53,70-73,...)
+  BGX_CHECK(text[size - 1] == '\n', "Partial line in fastq file (the text must end with a newline)");
+  DevBuf<char> d_text(size, s);
+  BGX_CUDA(cudaMemcpyAsync(d_text.p, text, size, cudaMemcpyHostToDevice, s));
+  const uint64_t n_chunks = (size + kFqChunk - 1) / kFqChunk;
+  BGX_CHECK(n_chunks < (1ull << 32), "FASTQ text too large for one call (split it at a record boundary)");
+  DevBuf<uint32_t> cnt(n_chunks, s), first(n_chunks, s), tot(1, s);
+  KLAUNCH(fq_count_kernel)<<<(unsigned)((n_chunks + 255) / 256), 256, 0, s>>>(d_text.p, size, cnt.p);
+  exclusive_scan_u32(cnt.p, first.p, n_chunks, tot.p, s);
+  uint32_t n_lines = 0;
+  BGX_CUDA(cudaMemcpyAsync(&n_lines, tot.p, 4, cudaMemcpyDeviceToHost, s));
+  BGX_CUDA(cudaStreamSynchronize(s));
+  DevBuf<uint64_t> nl_pos(std::max<uint32_t>(n_lines, 1), s);
+  KLAUNCH(fq_positions_kernel)<<<(unsigned)((n_chunks + 255) / 256), 256, 0, s>>>(d_text.p, size, first.p, nl_pos.p);
+  BGX_CUDA(cudaGetLastError());
+  // blank lines after the last record are skipped like the reference skips them before a record
+  // (fastq.cpp:45-58); blank lines between records are not supported here and reported as such
+  uint64_t trailing = 0;
+  while (trailing + 1 < size && text[size - 2 - trailing] == '\n') ++trailing;
+  if (size == 1 || trailing + 1 == size) return;  // nothing but newlines
+  const uint64_t lines = (uint64_t)n_lines - trailing;
+  const uint64_t n = lines / 4;  // whole records; a cut-off last record is reported after the records before it
+  DevBuf<uint64_t> seq_start(std::max<uint64_t>(n, 1), s);
+  DevBuf<uint16_t> seq_len(std::max<uint64_t>(n, 1), s);
+  DevBuf<unsigned long long> first_error(1, s);
+  BGX_CUDA(cudaMemsetAsync(first_error.p, 0xff, 8, s));
+  if (n) KLAUNCH(fq_records_kernel)<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(d_text.p, nl_pos.p, n, seq_start.p, seq_len.p, first_error.p);
+  BGX_CUDA(cudaGetLastError());
+  unsigned long long h_err = 0;
+  std::vector<uint16_t> lens(n);
+  BGX_CUDA(cudaMemcpyAsync(&h_err, first_error.p, 8, cudaMemcpyDeviceToHost, s));
+  if (n) BGX_CUDA(cudaMemcpyAsync(lens.data(), seq_len.p, n * 2, cudaMemcpyDeviceToHost, s));
+  BGX_CUDA(cudaStreamSynchronize(s));
+  if (h_err != ~0ULL) {
+    static const char* msg[] = {"", "Sequence id too short", "Sequence id missing @", "Expecting sequence, found empty line",
+                                "Sequence contains unexpected characters", "Expecting +, found empty line",
+                                "Expecting + as first char of line", "Quality line not same length as sequence",
+                                "read longer than 255 bases (the reference needs --allow-long-reads)",
+                                "blank line between records (only trailing blank lines are supported)"};
+    throw Error("line " + std::to_string(h_err >> 4) + ": " + msg[h_err & 15]);
+  }
+  if (lines % 4 != 0) {
+    static const char* what[4] = {"", "sequence", "+", "quality"};
+    throw Error("line " + std::to_string(lines + 1) + ": End of file while reading " + what[lines % 4] + " line");
+  }
+  if (n == 0) return;
+  std::vector<uint32_t> woff;
+  const uint64_t words_before = c->n_words;
+  append_geometry(c, lens, &woff);
+  ensure_capacity(c, n, woff[n] - words_before);
+  DevBuf<int> d_flag(1, s);
+  BGX_CUDA(cudaMemsetAsync(d_flag.p, 0, sizeof(int), s));
+  BGX_CUDA(cudaMemcpyAsync(c->word_off.p + c->n_reads, woff.data(), (n + 1) * sizeof(uint32_t), cudaMemcpyHostToDevice, s));
+  KLAUNCH(pack_ascii_kernel)<<<(unsigned)((n * 32 + 255) / 256), 256, 0, s>>>(d_text.p, seq_start.p, n, c->word_off.p + c->n_reads,
+                                                                     c->words.p, c->nmask.p, d_flag.p, seq_len.p);
+  BGX_CUDA(cudaGetLastError());
+  c->add_stat("h2d_bytes", (double)size + (double)(n + 1) * 4);
+  *n_added = n;
   finish_append(c, lens, woff, d_flag.p);
 }
 

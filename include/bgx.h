@@ -64,6 +64,14 @@ void bgx_free(void* host_ptr);
  * Thread-compatible, not thread-safe: serialise calls on one context. */
 int bgx_add_reads_ascii(bgx_ctx* ctx, const char* bases, const uint64_t* offs, uint64_t n_reads);
 
+/* Second step beyond the path (read import): a chunk of uncompressed FASTQ text, split
+ * and checked on the GPU with the semantics and error texts of fastq_reader::read
+ * (modules/bio_format/fastq.cpp:40-126: four lines per record, '@' id line, sequence over ACGTN,
+ * '+' line, quality line as long as the sequence), then packed like bgx_add_reads_ascii.  The text
+ * must hold whole records and end with a newline; blank lines are accepted after the last record
+ * only.  *n_reads = records added.  gzip, BAM/CRAM and read names/pairing stay with the importer. */
+int bgx_add_reads_fastq(bgx_ctx* ctx, const char* text, uint64_t size, uint64_t* n_reads);
+
 /* Same, for reads already 2-bit packed (T0 of the benchmark clock).
  *   packed   : dna_sequence byte order (4 bases/byte, first base in the high bits,
  *              modules/bio_base/dna_sequence.h:95-99); read r starts at byte 8*word_offs[r] and

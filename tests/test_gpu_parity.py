@@ -377,6 +377,57 @@ def test_readmap_paired(B):
     g.close()
 
 
+def _fastq(reads, blank_tail=0):
+    out = []
+    for i, r in enumerate(reads):
+        out.append(f"@read{i}/1\n{r}\n+\n{'I' * len(r)}\n")
+    return ("".join(out) + "\n" * blank_tail).encode()
+
+
+def test_fastq_import_equals_ascii_import(B, golden_reads):
+    """bgx_add_reads_fastq (fastq_reader::read semantics, modules/bio_format/fastq.cpp:40-126): same reads,
+    same result as bgx_add_reads_ascii; ragged lengths, N calls, several appends, trailing blank lines."""
+    buf, offs = _sim(6000, 3000, 120, 0.01, 61, n_rate=0.003)
+    sim = [buf[offs[i]:offs[i + 1]].decode() for i in range(len(offs) - 1)]
+    reads = sim + [r[:40 + i % 60] for i, r in enumerate(sim[:500])] + ["N" * 50, "ACGTN" * 7]
+    g1, km1, cr1, ss1, _ = run_gpu(B, reads)
+    g2 = B.Bgx()
+    assert g2.add_reads_fastq(_fastq(reads[:1000])) == 1000
+    assert g2.add_reads_fastq(_fastq(reads[1000:], blank_tail=3)) == len(reads) - 1000
+    assert g2.add_reads_fastq(b"\n\n") == 0
+    g2.run()
+    check_seqset_equal(ss1, g2.export_seqset())
+    cr2 = g2.export_corrected()
+    assert cr2["seq"] == cr1["seq"] and np.array_equal(cr2["offs"], cr1["offs"])
+    g3 = B.Bgx()
+    assert g3.add_reads_fastq(_fastq(golden_reads)) == 10000
+    g3.run()
+    assert g3.export_seqset()["n"] == 19935
+    for g in (g1, g2, g3):
+        g.close()
+
+
+@pytest.mark.parametrize("text,msg", [
+    (b"@r\nACGT\n+\nIIII", "Partial line in fastq file"),
+    (b"@r\nACGT\n+\n", "End of file while reading quality line"),
+    (b"@r\nACGT\n", "End of file while reading + line"),
+    (b"r1\nACGT\n+\nIIII\n", "line 1: Sequence id missing @"),
+    (b"@\nACGT\n+\nIIII\n", "line 1: Sequence id too short"),
+    (b"@r\nACGT\n+\nIIII\n@s\nACXT\n+\nIIII\n", "line 6: Sequence contains unexpected characters"),
+    (b"@r\nacgt\n+\nIIII\n", "line 2: Sequence contains unexpected characters"),
+    (b"@r\nACGT\n-\nIIII\n", "line 3: Expecting + as first char of line"),
+    (b"@r\nACGT\n+\nIII\n", "line 4: Quality line not same length as sequence"),
+    (b"@r\n\n+\nII\n", "line 2: Expecting sequence, found empty line"),
+    (b"@r\nACGT\n+\nIIII\n\n@s\nACGT\n+\nIIII\n", "blank line between records"),
+])
+def test_fastq_errors_follow_the_reference(B, text, msg):
+    g = B.Bgx()
+    with pytest.raises(B.BgxError) as e:
+        g.add_reads_fastq(text)
+    assert msg in str(e.value)
+    g.close()
+
+
 def test_async_upload_equals_sync_upload(B):
     """bgx_add_reads_packed_async: chunked copy on a second stream, pass 1 of counting launched per
     chunk; also appended after a synchronous batch, and followed by stages other than count."""
