@@ -164,7 +164,9 @@ def run_reference(args):
     line = {"impl": "reference", "metric": "input bases/sec to finished seqset", "value": val, "unit": "bases/s",
             "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u64", "data": "synthetic",
-            "config": {"workload": args.workload, "reads": int(total), "read_len": int(reads.shape[1])},
+            "config": {"workload": args.workload, "reads_per_gpu": int(total), "read_len": int(reads.shape[1]),
+                       "bases_per_gpu": int(total) * int(reads.shape[1]), "kmer_size": 30,
+                       "parallelism": f"{threads} host threads (CPU path; no GPU)"},
             "cpu_baseline": {"value": val, "unit": "bases/s", "cores": threads, "kind": "port",
                              "sample": f"{sample} reads at the workload's coverage over a genome prefix "
                                        f"(workload has {total}), whole path (count+correct+staged seqset), "
