@@ -274,7 +274,10 @@ int bgx_reset_results(bgx_ctx* x) {
 
 int bgx_clear_reads(bgx_ctx* x) {
   CTX_GUARD({
-    reads_ready(c);  // copies still in flight are ordered before the buffers can be reused
+    // copies of an async append still in flight read the caller's host buffer: wait for them here, so
+    // that "clear, then free the host buffer" is safe, and order them before the buffers are reused
+    if (c->copy_stream && !c->upload.empty()) BGX_CUDA(cudaStreamSynchronize(c->copy_stream));
+    reads_ready(c);
     c->words.release(); c->nmask.release(); c->word_off.release(); c->lens.release();
     c->n_reads = c->n_words = c->n_bases = c->n_kmer_instances = 0;
     c->has_n = false;

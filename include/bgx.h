@@ -89,8 +89,8 @@ int bgx_add_reads_packed(bgx_ctx* ctx, const uint8_t* packed, const uint32_t* n_
 /* Same arguments and result as bgx_add_reads_packed, but the packed words are copied on a second
  * stream in chunks of reads and the call returns without waiting for them: pass 1 of
  * bgx_count_kmers starts on each chunk as it lands, so the PCIe copy runs under compute.
- * `packed` must stay valid and unchanged until the next bgx_count_kmers / bgx_run / bgx_correct
- * returns.  With an N mask, or for small appends, it is the synchronous call. */
+ * `packed` must stay valid and unchanged until the next bgx_count_kmers / bgx_run / bgx_correct /
+ * bgx_clear_reads / bgx_destroy returns.  With an N mask, or for small appends, it is the synchronous call. */
 int bgx_add_reads_packed_async(bgx_ctx* ctx, const uint8_t* packed, const uint32_t* n_mask,
                                const uint64_t* word_offs, const uint16_t* lens, uint64_t n_reads);
 

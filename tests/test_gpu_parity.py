@@ -447,6 +447,14 @@ def test_async_upload_equals_sync_upload(B):
     km2 = g2.export_kmers(1)
     for f in ("kmers", "fwd", "rev", "flags"):
         assert np.array_equal(km1[f], km2[f]), f
+    # clearing right after an async append (copies still in flight) must be safe
+    g4 = B.Bgx()
+    g4.add_reads_packed_ptr(packed.ctypes.data, None, woffs.ctypes.data, lens.ctypes.data, len(lens), overlap=True)
+    g4.clear_reads()
+    g4.add_reads_packed_ptr(packed.ctypes.data, None, woffs.ctypes.data, lens.ctypes.data, len(lens), overlap=True)
+    g4.run()
+    check_seqset_equal(ss1, g4.export_seqset())
+    g4.close()
     # batched counting and a second (async) append on top of resident reads
     g3 = B.Bgx(count_batch_reads=100000)
     g3.add_reads_packed_ptr(packed.ctypes.data, None, woffs.ctypes.data, lens.ctypes.data, len(lens), overlap=True)
