@@ -13,7 +13,11 @@
 // Collisions, saturation and the spill table are left out on purpose (a few percent of the work);
 // the claim race of B is handled correctly so the counts can be checked (sum of counters == n).
 // build: nvcc -O3 -gencode arch=compute_100a,code=sm_100a -o tools/micro/upsert_one_atomic tools/micro/upsert_one_atomic.cu
-// usage: upsert_one_atomic [log2_slots=20] [n=2^26] [solid_permille=860]
+// usage: upsert_one_atomic [log2_slots=20] [parts=64] [solid_permille=860]
+// Every part is one slice of 2^log2_slots slots with 3 instances per slot (as the real table at 100x:
+// ~0.42 distinct error keys and ~0.03 solid keys per slot, the solid ones ~86 times each); the
+// parts run back to back, like the partitions of kmer_upsert_kernel.
+// (First attempt, r1g: 2^26 instances into ONE 2^20-slot slice overfilled the table and never finished.)
 #include <cstdint>
 #include <cstdio>
 #include <cstdlib>
@@ -117,45 +121,53 @@ __global__ void sum_b(const unsigned long long* t, uint64_t slots, unsigned long
 
 int main(int argc, char** argv) {
   const int log2_slots = argc > 1 ? atoi(argv[1]) : 20;
-  const uint64_t n = argc > 2 ? strtoull(argv[2], 0, 10) : (1ull << 26);
+  const int parts = argc > 2 ? atoi(argv[2]) : 64;
   const unsigned solid_permille = argc > 3 ? (unsigned)atoi(argv[3]) : 860;
   const uint64_t slots = 1ull << log2_slots, mask = slots - 1;
-  // distinct keys ~ 45 % of the slots, as the real table: errors n*(1-solid) + solid keys
-  const uint64_t n_err = n / 1000 * (1000 - solid_permille);
-  const uint64_t n_solid = slots * 45 / 100 > n_err ? slots * 45 / 100 - n_err : 1024;
-  printf("slice 2^%d slots, %llu instances, %u permille solid over %llu keys, ~%llu error keys\n", log2_slots,
+  const uint64_t n = 3 * slots;                                   // instances per part
+  const uint64_t n_err = n / 1000 * (1000 - solid_permille);      // distinct error keys per part
+  const uint64_t n_solid = n / 1000 * solid_permille / 86;        // solid keys per part, ~86 instances each
+  printf("%d parts x (2^%d slots, %llu instances: %u permille solid over %llu keys, ~%llu error keys)\n", parts, log2_slots,
          (unsigned long long)n, solid_permille, (unsigned long long)n_solid, (unsigned long long)n_err);
-  void* buf;
+  fflush(stdout);
+  char* buf;
   unsigned long long* out;
-  cudaMalloc(&buf, slots * 16);
+  cudaMalloc(&buf, (size_t)parts * slots * 16);
   cudaMalloc(&out, 8);
   cudaEvent_t a, b;
   cudaEventCreate(&a); cudaEventCreate(&b);
   const unsigned grid = (unsigned)((n + 1023) / 1024);
+  const char* names[] = {"A: CAS + RED, 16-byte slots (current)", "B: one ATOM.add with return, 8-byte slots",
+                         "C: one ATOM.add with return, 16-byte stride"};
   for (int v = 0; v < 3; ++v) {
     float best = 1e30f;
     unsigned long long total = 0;
+    const size_t slice_bytes = slots * (v == 1 ? 8 : 16);
     for (int rep = 0; rep < 3; ++rep) {
-      cudaMemset(buf, 0, slots * 16);
+      cudaMemset(buf, 0, (size_t)parts * slots * 16);
       cudaMemset(out, 0, 8);
       cudaEventRecord(a);
-      if (v == 0) upsert_a<<<grid, 256>>>((SlotA*)buf, mask, n, n_solid, solid_permille);
-      if (v == 1) upsert_b<1><<<grid, 256>>>((unsigned long long*)buf, mask, n, n_solid, solid_permille);
-      if (v == 2) upsert_b<2><<<grid, 256>>>((unsigned long long*)buf, mask, n, n_solid, solid_permille);
+      for (int p = 0; p < parts; ++p) {
+        char* slice = buf + (size_t)p * slice_bytes;
+        if (v == 0) upsert_a<<<grid, 256>>>((SlotA*)slice, mask, n, n_solid, solid_permille);
+        if (v == 1) upsert_b<1><<<grid, 256>>>((unsigned long long*)slice, mask, n, n_solid, solid_permille);
+        if (v == 2) upsert_b<2><<<grid, 256>>>((unsigned long long*)slice, mask, n, n_solid, solid_permille);
+      }
       cudaEventRecord(b);
       cudaEventSynchronize(b);
       float ms;
       cudaEventElapsedTime(&ms, a, b);
       best = ms < best ? ms : best;
-      if (v == 0) sum_a<<<(unsigned)((slots + 255) / 256), 256>>>((SlotA*)buf, slots, out);
-      if (v == 1) sum_b<1><<<(unsigned)((slots + 255) / 256), 256>>>((unsigned long long*)buf, slots, out);
-      if (v == 2) sum_b<2><<<(unsigned)((slots + 255) / 256), 256>>>((unsigned long long*)buf, slots, out);
+      const uint64_t all = (uint64_t)parts * slots;
+      if (v == 0) sum_a<<<(unsigned)((all + 255) / 256), 256>>>((SlotA*)buf, all, out);
+      if (v == 1) sum_b<1><<<(unsigned)((all + 255) / 256), 256>>>((unsigned long long*)buf, all, out);
+      if (v == 2) sum_b<2><<<(unsigned)((all + 255) / 256), 256>>>((unsigned long long*)buf, all, out);
       cudaMemcpy(&total, out, 8, cudaMemcpyDeviceToHost);
     }
-    const char* names[] = {"A: CAS + RED, 16-byte slots (current)", "B: one ATOM.add with return, 8-byte slots",
-                           "C: one ATOM.add with return, 16-byte stride"};
-    printf("%-48s %8.3f ms  %7.2f G instances/s   counted %llu of %llu%s\n", names[v], best, n / best / 1e6, total,
-           (unsigned long long)n, total == n ? "" : "  (MISMATCH)");
+    const uint64_t tot_n = (uint64_t)parts * n;
+    printf("%-48s %8.3f ms  %7.2f G instances/s   counted %llu of %llu%s\n", names[v], best, tot_n / best / 1e6, total,
+           (unsigned long long)tot_n, total == tot_n ? "" : "  (MISMATCH)");
+    fflush(stdout);
   }
   return 0;
 }
