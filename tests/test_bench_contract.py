@@ -1,0 +1,43 @@
+"""bench.py's JSON contract: the reference arm run here on a tiny sample (CPU only), and the last
+committed GPU-arm line under profiles/ (written by `python bench.py` on a B200)."""
+import json
+import os
+import subprocess
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+BASE = ["metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling", "vs_baseline",
+        "dtype", "data", "config", "e2e", "cpu_baseline"]
+
+
+def test_reference_arm_line():
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "0",
+                          "--cpu-sample-reads", "3000"], capture_output=True, text=True, timeout=600, cwd=ROOT)
+    assert out.returncode == 0, out.stderr[-2000:]
+    line = json.loads([l for l in out.stdout.splitlines() if l.startswith("{")][-1])
+    for k in BASE:
+        assert k in line, k
+    assert line["impl"] == "reference" and line["metric"] == "input bases/sec to finished seqset" and line["unit"] == "bases/s"
+    assert line["higher_is_better"] is True and line["vs_baseline"] is None and line["value"] > 0
+    assert line["config"]["workload"] == "ecoli100x"
+    assert line["e2e"] == {"value": line["value"], "unit": "bases/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+    cb = line["cpu_baseline"]
+    assert cb["kind"] == "port" and cb["cores"] >= 1 and cb["value"] == line["value"] and "sample" in cb
+
+
+def test_committed_gpu_line_has_every_contract_key():
+    path = os.path.join(ROOT, "profiles", "r1g_bench_ecoli100x.json")
+    line = json.loads([l for l in open(path).read().splitlines() if l.startswith("{")][-1])
+    for k in BASE + ["gpu_launches", "roofline", "clocks"]:
+        assert k in line, k
+    assert line["n_gpus"] == 1 and line["warmup"] >= 3 and line["gpu_launches"] > 0 and line["dtype"] == "u64"
+    assert line["config"]["workload"] == "ecoli100x" and "l2" in line["config"]
+    e = line["e2e"]
+    assert e["h2d_bytes_per_step"] > 0 and e["d2h_bytes_per_step"] > 0 and 0 < e["value"] < line["value"]
+    r = line["roofline"]
+    assert r["bound"] == "hbm" and r["unit"] == "GB/s" and abs(r["frac"] - r["achieved"] / r["peak"]) < 1e-9
+    assert r["traffic"] is None or r["traffic"] > 0
+    cb = line["cpu_baseline"]
+    assert cb["kind"] == "port" and cb["cores"] >= 1 and cb["value"] > 0
+    c = line["clocks"]
+    assert not set(c["reasons"]) & {"hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown"}
