@@ -57,7 +57,7 @@ struct Params {
   double trim;
   const unsigned long long* set;
   uint64_t set_mask;   // buckets - 1 (a bucket = 4 slots = one 32-byte sector)
-  int set_shift;       // 64 - log2(buckets): the home bucket is the TOP bits of the hash
+  int set_shift;       // 2k - log2(buckets): the home bucket is the TOP bits of the (2k-bit) hash
 };
 
 // solid mask of one read: bit (p & 31) of word (p >> 5) = the k-mer starting at read position p is
@@ -127,7 +127,7 @@ __device__ __forceinline__ unsigned long long solid_find(const Params& P, uint64
   bool fl;
   uint64_t canon = canonicalize(kmer, P.k, fl);
   *flipped = fl;
-  uint64_t b = mix64(canon) >> P.set_shift;
+  uint64_t b = khash(canon, P.k) >> P.set_shift;
   for (;;) {
     unsigned long long kk[4];
     ld_bucket4(P.set, b, kk);
@@ -347,7 +347,7 @@ __global__ void __launch_bounds__(kProbeThreads, (MAXIT <= 4 ? 3 : 1)) probe_ker
       bool fl;
       canon[it] = canonicalize(win >> (64 - 2 * k), k, fl);
       flip[it] = fl;
-      slot[it] = mix64(canon[it]) >> P.set_shift;
+      slot[it] = khash(canon[it], k) >> P.set_shift;
       if (live[it]) ld_bucket4(P.set, slot[it], cur[it]);
       else cur[it][0] = cur[it][1] = cur[it][2] = cur[it][3] = kEmptyKey;
     }
@@ -682,10 +682,10 @@ void stage_correct(Context* c) {
   ScopedStage st_all(c, "correct_total");
   const uint64_t n = c->n_reads;
   c->store.alloc(2 * c->n_words + 1, s);
-  c->clen.alloc(n, s);
-  c->ncorr.alloc(n, s);
-  c->next_fwd.alloc(n, s);
-  c->next_rev.alloc(n, s);
+  c->clen.alloc(std::max<uint64_t>(n, 1), s);
+  c->ncorr.alloc(std::max<uint64_t>(n, 1), s);
+  c->next_fwd.alloc(std::max<uint64_t>(n, 1), s);
+  c->next_rev.alloc(std::max<uint64_t>(n, 1), s);
   DevBuf<unsigned long long> totals(5, s);
   BGX_CUDA(cudaMemsetAsync(totals.p, 0, 5 * sizeof(unsigned long long), s));
   BGX_CUDA(cudaMemsetAsync(c->store.p + 2 * c->n_words, 0, sizeof(uint64_t), s));
@@ -696,12 +696,12 @@ void stage_correct(Context* c) {
   P.trim = (double)c->opt.trim_after_portion;  // float widened to double (biograph_create.cpp:489-490,731)
   P.set = c->solid.p;
   P.set_mask = c->solid_slots / 4 - 1;
-  P.set_shift = 64;
+  P.set_shift = 2 * P.k;
   for (uint64_t b = c->solid_slots / 4; b > 1; b >>= 1) --P.set_shift;
   const int max_kmers = std::max<int>((int)c->max_len - P.k + 1, 1);
   const int mask_words = max_kmers <= 128 ? 4 : 8;
   BGX_CHECK(max_kmers <= 256, "read longer than 255 bases");
-  DevBuf<uint32_t> slow_list(n, s), slow_mask((size_t)n * mask_words, s);
+  DevBuf<uint32_t> slow_list(std::max<uint64_t>(n, 1), s), slow_mask(std::max<uint64_t>(n, 1) * mask_words, s);
   DevBuf<unsigned int> n_slow(1, s);
   BGX_CUDA(cudaMemsetAsync(n_slow.p, 0, sizeof(unsigned int), s));
   unsigned int h_slow = 0;
@@ -709,6 +709,9 @@ void stage_correct(Context* c) {
     ScopedStage st(c, "correct_probe");
     const unsigned grid = (unsigned)((n + kProbeWarps * kProbeRPW - 1) / (kProbeWarps * kProbeRPW));
     const uint32_t* nm = c->has_n ? c->nmask.p : nullptr;
+    if (n == 0) {
+      // a rank without reads (sharded build): nothing to launch, but it still takes part in the exchanges
+    } else
 #define BGX_PROBE(MAXIT, HASN)                                                                                          \
   note_launch();                                                                                                        \
   probe_kernel<MAXIT, HASN><<<grid, kProbeThreads, 0, s>>>(c->words.p, nm, c->word_off.p, c->lens.p, (uint32_t)n, P, \

@@ -5,20 +5,27 @@
 // kmerizer::run's min-count filter (modules/bio_mapred/kmerize_bf.cpp:290-318) and kmer_set
 // (modules/bio_mapred/kmer_set.cpp:522-631, lookup :296-360).
 //
-// B200 design: two passes, no probabilistic pre-pass, no temp files.
+// B200 design: hash-partition twice, then count in shared memory.  No global
+// atomics on the counting path, no count table in HBM, no probabilistic pre-pass, no temp files.
 //   pass 1  kmer_partition_kernel: a block pulls a tile of packed reads into shared memory with
 //           128-bit coalesced loads; lane l forms the k-mers l, l+32, ... of a read by funnel
-//           shifts, canonicalises with brev and hashes; the instances leave bucketed by the top
-//           hash bits as coalesced per-partition runs.  A fused linear-counting sample sizes the
-//           table.
-//   pass 2  kmer_upsert_kernel: the slot of a k-mer is the TOP bits of its hash, so a partition is
-//           one contiguous slice of the table that stays in L2 while its tiles are upserted
-//           (CAS claim that doubles as the read, RED.add on the counter, RED.or for the flags):
-//           16-byte slots, key|flags + both counters in one 32-byte sector.
-//   filter  one sweep of the table; the solid k-mers are inserted into the bucketed hash set that
-//           correction probes (32-byte buckets of four slots, home bucket = top hash bits).
-// Inputs whose instance buffers would not fit next to the table are counted in batches of reads
-// (count_batch_reads); multi-GPU, every partition travels to the rank that owns its hash range.
+//           shifts, canonicalises with brev and hashes with khash (a BIJECTION on 2k bits); the
+//           instances leave as 8-byte words [remaining hash bits | flipped | rev flag | fwd flag]
+//           bucketed by the top hash bits, as coalesced per-partition runs.  A fused linear-counting
+//           sample estimates the distinct count.
+//   pass 2  kmer_subhist_kernel + kmer_split_kernel: every partition is split by the next hash bits
+//           into sub-bins that hold ~2 k distinct k-mers each (exact offsets from a histogram, tiles
+//           staged in shared memory, coalesced runs out).
+//   pass 3  kmer_count_bins_kernel: one block per sub-bin counts its words in a shared-memory hash
+//           table (kmer_count_table::increment semantics: fwd/rev counters, starts-read flags OR-ed,
+//           swapped when flipped), then writes every distinct k-mer once -- the hash is inverted to
+//           recover the k-mer -- and the k-mers with fwd+rev >= min_count a second time as the solid
+//           list.
+//   solid   the solid k-mers are inserted into the bucketed hash set that correction probes
+//           (32-byte buckets of four slots, home bucket = top hash bits = arrival order).
+// Inputs whose instance words would not fit HBM are counted in batches of HASH RANGE (every batch
+// re-reads the reads and keeps the k-mers whose top hash bits name the batch); multi-GPU, every
+// partition travels to the rank that owns its hash range.
 #include <algorithm>
 #include <cmath>
 #include <numeric>
@@ -30,25 +37,22 @@
 namespace bgx {
 namespace {
 
-// ---- partitioned counting -------------------------------------------------------------------
-// A k-mer instance travels between the two kernels as one 8-byte word:
-//   bits 0..2k-1 the k-mer as seen in the read (NOT canonical), bit 63 = first k-mer of its read,
-//   bit 62 = last k-mer of its read (bs/kmer_counter.h:318-321).  k <= 31, so the fields never meet.
-constexpr uint64_t kPkFirst = 1ULL << 63;
-constexpr uint64_t kPkLast = 1ULL << 62;
-constexpr int kMaxPartBits = 10;            // <= 1024 hash partitions
+// ---- instance words ---------------------------------------------------------------------------
+// A k-mer instance travels between the passes as one 8-byte word:
+//   bits 3..  the hash of the canonical k-mer WITHOUT its top `drop` bits (batch + partition bits:
+//             they are the same for every word of a partition)
+//   bit 2     flipped (the instance was the reverse complement of the canonical k-mer -> rev_count)
+//   bit 1     rev_starts_read, bit 0 fwd_starts_read: first / last k-mer of its read, swapped when
+//             flipped (bs/kmer_counter.h:318-321, bs/kmer_count_table.h:82-86)
+// 2k - drop + 3 <= 62 - 7 + 3 bits, so k = 31 fits too.
+constexpr uint64_t kWFwd = 1, kWRev = 2, kWFlip = 4;
+constexpr int kMinPartBits = 7;
+constexpr int kMaxPartBits = 10;            // <= 1024 hash partitions per batch
+constexpr int kMaxSubBits = 10;             // <= 1024 sub-bins per partition
 constexpr int kPartThreads = 256;
 constexpr int kPartWarps = kPartThreads / 32;
 
-// The table slot of a k-mer is the TOP bits of its hash, so the top part_bits bits (its partition)
-// select a contiguous 1/P slice of the table.
-// With 2^rank_bits GPUs the top rank_bits bits of the hash name the owning rank (a contiguous block
-// of partitions) and are dropped before indexing that rank's table.
-__device__ __forceinline__ uint64_t table_slot(uint64_t h, int log2_slots, int rank_bits) {
-  return (h << rank_bits) >> (64 - log2_slots);
-}
-
-// Pass 1: extract every k-mer instance, bucket it by hash partition.
+// Pass 1: extract every k-mer instance of the batch, bucket it by hash partition.
 //   * the block's reads (kPartWarps*RPW consecutive reads) are pulled into shared memory with
 //     128-bit coalesced loads; a warp takes one read at a time, lane l forms the k-mers at
 //     positions l, l+32, ... by funnel shifts (semantics of pass_processor::add,
@@ -56,14 +60,21 @@ __device__ __forceinline__ uint64_t table_slot(uint64_t h, int log2_slots, int r
 //   * rank within (tile, partition) from a shared-memory histogram, tile staged in partition
 //     order, one global cursor bump per (block, partition), coalesced per-partition runs out
 //   * fused distinct-k-mer estimate: linear counting over the 2^-samp_shift of hash space whose low
-//     hash bits are zero (sizes the table; sampling by hash value is unbiased for distinct counts)
+//     hash bits are zero (sampling by hash value is unbiased for distinct counts)
 // Partition p owns out[part_base[p] .. part_base[p] + cap).  cursors[] keep counting past cap, so
 // after an overflowing run they are the exact histogram for the exact re-run.
+struct PartGeom {
+  int k;
+  int batch_bits;   // the batch keeps the k-mers whose top batch_bits hash bits == batch
+  uint32_t batch;
+  int part_bits;    // next part_bits bits = partition
+};
+
 template <int MAXIT, int RPW>
 __global__ void __launch_bounds__(kPartThreads, (MAXIT <= 4 ? 4 : 2))
 kmer_partition_kernel(const uint64_t* __restrict__ words, const uint32_t* __restrict__ nmask,
                       const uint32_t* __restrict__ word_off, const uint16_t* __restrict__ lens, uint32_t n_reads,
-                      int k, int part_bits, unsigned long long* __restrict__ cursors,
+                      PartGeom G, unsigned long long* __restrict__ cursors,
                       const unsigned long long* __restrict__ part_base, unsigned long long cap,
                       unsigned long long* __restrict__ out, unsigned int* __restrict__ bitmap, uint64_t bit_mask,
                       int samp_shift, int* __restrict__ overflow) {
@@ -75,6 +86,7 @@ kmer_partition_kernel(const uint64_t* __restrict__ words, const uint32_t* __rest
   uint64_t* rwords = reinterpret_cast<uint64_t*>(stage + kTileKmers);                     // kTileReads*kWordsPerRead + 2
   uint32_t* rmask = reinterpret_cast<uint32_t*>(rwords + kTileReads * kWordsPerRead + 2); // same count
   uint16_t* stage_bin = reinterpret_cast<uint16_t*>(rmask + kTileReads * kWordsPerRead + 2);  // kTileKmers
+  const int k = G.k, part_bits = G.part_bits;
   const int P = 1 << part_bits;
   unsigned long long* gdst = reinterpret_cast<unsigned long long*>(stage_bin + kTileKmers);   // P
   uint32_t* hist = reinterpret_cast<uint32_t*>(gdst + P);                                     // P
@@ -83,6 +95,8 @@ kmer_partition_kernel(const uint64_t* __restrict__ words, const uint32_t* __rest
 
   const unsigned tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const uint32_t n_tiles = (n_reads + kTileReads - 1) / kTileReads;
+  const int low_bits = 2 * k - G.batch_bits - part_bits;   // hash bits a word keeps
+  const uint64_t low_mask = (1ULL << low_bits) - 1;
 
   for (uint32_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
     const uint32_t r0 = tile * kTileReads;
@@ -137,14 +151,20 @@ kmer_partition_kernel(const uint64_t* __restrict__ words, const uint32_t* __rest
             const uint64_t kmer = win >> (64 - 2 * k);
             bool flipped;
             const uint64_t canon = canonicalize(kmer, k, flipped);
-            const uint64_t h = mix64(canon);
-            const uint32_t bin = (uint32_t)(h >> (64 - part_bits));
-            const uint32_t rank = atomicAdd(&hist[bin], 1u);
-            code = (bin << 16) | rank;
-            word = kmer | (p == 0 ? kPkFirst : 0ULL) | (p == nk - 1 ? kPkLast : 0ULL);
-            if (bitmap != nullptr && (h & ((1ULL << samp_shift) - 1)) == 0) {
-              const uint64_t bit = (h >> samp_shift) & bit_mask;
-              atomicOr(&bitmap[bit >> 5], 1u << (bit & 31));  // RED: fire and forget, no read-back stall
+            const uint64_t h = khash(canon, k);
+            const uint64_t hp = h >> low_bits;   // batch | partition
+            if ((uint32_t)(hp >> part_bits) == G.batch) {
+              const uint32_t bin = (uint32_t)hp & (uint32_t)(P - 1);
+              const uint32_t rank = atomicAdd(&hist[bin], 1u);
+              code = (bin << 16) | rank;
+              // fwd_flag = first k-mer of the read, rev_flag = last; swapped when flipped
+              const bool is_first = p == 0, is_last = p == nk - 1;
+              word = ((h & low_mask) << 3) | (flipped ? kWFlip : 0ULL) |
+                     ((flipped ? is_last : is_first) ? kWFwd : 0ULL) | ((flipped ? is_first : is_last) ? kWRev : 0ULL);
+              if (bitmap != nullptr && (h & ((1ULL << samp_shift) - 1)) == 0) {
+                const uint64_t bit = ((h & low_mask) >> samp_shift) & bit_mask;
+                atomicOr(&bitmap[bit >> 5], 1u << (bit & 31));  // RED: fire and forget, no read-back stall
+              }
             }
           }
         }
@@ -201,160 +221,317 @@ kmer_partition_kernel(const uint64_t* __restrict__ words, const uint32_t* __rest
   }
 }
 
-// Pass 2: upsert the partitioned instances into the table.  Block (p, t) handles tile t of
-// partition p; blocks are dispatched in index order, so at any moment the resident blocks work
-// on one or two partitions = a few MB of table that stay in L2: the CAS / atomicAdd / atomicOr
-// traffic (kmer_count_table::increment, bs/kmer_count_table.h:54-103) never leaves L2, and DRAM
-// sees the table exactly twice (first touch, final write-back).
-constexpr int kUpsItems = 4;
-constexpr int kUpsTile = 256 * kUpsItems;
-template <bool CAS_FIRST>
-__global__ void __launch_bounds__(256, 4) kmer_upsert_kernel(const unsigned long long* const* __restrict__ part_ptr,
-                                                             const unsigned long long* __restrict__ part_count,
-                                                             uint32_t tiles_per_part, int k,
-                                                             CountEntry* __restrict__ table, int log2_slots,
-                                                             int rank_bits, int* __restrict__ overflow) {
-  const uint32_t p = blockIdx.x / tiles_per_part, t = blockIdx.x % tiles_per_part;
-  const unsigned long long cnt = part_count[p];
-  const unsigned long long first = (unsigned long long)t * kUpsTile;
+// ---- pass 2: split every partition into sub-bins by the next hash bits -----------------------------
+// A "virtual partition" is a run of words of one partition from one source (single GPU: the
+// partition itself; multi-GPU: what one rank sent for it): vptr / vcnt / vpl (its local partition
+// index).  Block (v, t) takes tile t of virtual partition v.  sub-bin of a word = bits
+// [sub_shift, sub_shift + sub_bits) of its hash field.
+constexpr int kSplitThreads = 512;
+constexpr int kSplitItems = 16;
+constexpr int kSplitTile = kSplitThreads * kSplitItems;  // 8192 words
+constexpr int kHistTiles = 4;                            // the histogram kernel takes 4 tiles per block
+
+__global__ void __launch_bounds__(kSplitThreads) kmer_subhist_kernel(const unsigned long long* const* __restrict__ vptr,
+                                                                     const unsigned long long* __restrict__ vcnt,
+                                                                     const uint32_t* __restrict__ vpl,
+                                                                     uint32_t blocks_per_part, int sub_shift, int sub_bits,
+                                                                     unsigned long long* __restrict__ hist) {
+  __shared__ uint32_t h[1 << kMaxSubBits];
+  const uint32_t v = blockIdx.x / blocks_per_part, t = blockIdx.x % blocks_per_part;
+  const unsigned long long cnt = vcnt[v];
+  const unsigned long long first = (unsigned long long)t * (kSplitTile * kHistTiles);
   if (first >= cnt) return;
-  const unsigned long long* src = part_ptr[p];
-  const uint64_t slot_mask = (1ULL << log2_slots) - 1;
-  // lock-step phases over the thread's items keep kUpsItems L2 round trips in flight per thread:
-  // A) instance words  B) first-probe keys  C) CAS claims of empty slots  D) counters (RED)
-  unsigned long long w[kUpsItems], key[kUpsItems], cur[kUpsItems];
-  uint32_t slot[kUpsItems];   // offset from the partition-aligned base (fits 32 bits: slots < 2^32 per call)
-  bool flip[kUpsItems];
+  const int S = 1 << sub_bits;
+  for (int d = threadIdx.x; d < S; d += kSplitThreads) h[d] = 0;
+  __syncthreads();
+  const unsigned long long* src = vptr[v];
+  const unsigned long long last = min(cnt, first + (unsigned long long)kSplitTile * kHistTiles);
+  const uint32_t smask = (uint32_t)S - 1;
+#pragma unroll 4
+  for (unsigned long long i = first + threadIdx.x; i < last; i += kSplitThreads)
+    atomicAdd(&h[(uint32_t)(src[i] >> (3 + sub_shift)) & smask], 1u);
+  __syncthreads();
+  unsigned long long* g = hist + (size_t)vpl[v] * S;
+  for (int d = threadIdx.x; d < S; d += kSplitThreads)
+    if (h[d]) atomicAdd(&g[d], (unsigned long long)h[d]);
+}
+
+// bin_off = exclusive scan of the sub-bin histogram (one block; n <= 2^20), total -> *total_out
+__global__ void __launch_bounds__(1024) scan_u64_kernel(const unsigned long long* __restrict__ in, uint64_t n,
+                                                        unsigned long long* __restrict__ out,
+                                                        unsigned long long* __restrict__ total_out,
+                                                        unsigned long long* __restrict__ max_out) {
+  __shared__ unsigned long long wsum[32];
+  __shared__ unsigned long long carry_s;
+  if (threadIdx.x == 0) carry_s = 0;
+  __syncthreads();
+  const unsigned lane = lane_id(), warp = threadIdx.x >> 5;
+  unsigned long long mx = 0;
+  for (uint64_t base = 0; base < n; base += 1024) {
+    const uint64_t i = base + threadIdx.x;
+    const unsigned long long v = i < n ? in[i] : 0ULL;
+    mx = max(mx, v);
+    unsigned long long inc = v;
 #pragma unroll
-  for (int i = 0; i < kUpsItems; ++i) {
-    const unsigned long long idx = first + (unsigned long long)i * 256 + threadIdx.x;
-    w[i] = idx < cnt ? src[idx] : ~0ULL;   // ~0 = no item (a real word never has all k-mer bits and both flags set for k<=31)
-  }
-#pragma unroll
-  for (int i = 0; i < kUpsItems; ++i) {
-    const bool valid = w[i] != ~0ULL;
-    bool fl;
-    const uint64_t canon = canonicalize(w[i] & kKmerMask, k, fl);
-    flip[i] = fl;
-    // fwd_flag = first k-mer of the read, rev_flag = last; swapped when flipped
-    // (bs/kmer_counter.h:318-321, bs/kmer_count_table.h:82-86)
-    const bool is_first = (w[i] & kPkFirst) != 0, is_last = (w[i] & kPkLast) != 0;
-    uint64_t f = 0;
-    if (fl ? is_last : is_first) f |= kFwdFlag;
-    if (fl ? is_first : is_last) f |= kRevFlag;
-    key[i] = valid ? (canon | f) : ~0ULL;
-    slot[i] = (uint32_t)table_slot(mix64(canon), log2_slots, rank_bits);
-  }
-  if (CAS_FIRST) {
-    // the claim attempt doubles as the read of the slot: one CAS + one RED per instance.  Measured
-    // (tools/micro/l2_atomics, 16 MB slice): failing CAS + RED 88 G/s against load + RED 81 G/s,
-    // and the separate CAS of the first-touch instances (14 % at 0.5 % error) is gone.
-#pragma unroll
-    for (int i = 0; i < kUpsItems; ++i)
-      cur[i] = key[i] != ~0ULL ? atomicCAS(&table[slot[i]].key, (unsigned long long)kEmptyKey, key[i]) : 0ULL;
-  } else {
-#pragma unroll
-    for (int i = 0; i < kUpsItems; ++i)
-      cur[i] = key[i] != ~0ULL ? *reinterpret_cast<volatile unsigned long long*>(&table[slot[i]].key) : 0ULL;
-#pragma unroll
-    for (int i = 0; i < kUpsItems; ++i)
-      if (key[i] != ~0ULL && cur[i] == kEmptyKey)
-        cur[i] = atomicCAS(&table[slot[i]].key, (unsigned long long)kEmptyKey, key[i]);  // returns kEmptyKey when claimed
-  }
-#pragma unroll
-  for (int i = 0; i < kUpsItems; ++i) {
-    if (key[i] == ~0ULL) continue;
-    const uint64_t canon = key[i] & kKmerMask;
-    uint64_t f = key[i] & ~kKmerMask;
-    uint64_t s = slot[i];
-    unsigned long long c = cur[i];
-    if (c == kEmptyKey) {
-      f = 0;  // claimed by the CAS above: key and flags are in place
-    } else if ((c & kKmerMask) == canon) {
-      f &= ~c;
-    } else {
-      // collision: linear probing (rare at load factor <= 2/3)
-      bool done = false;
-      for (uint64_t probes = 0; probes <= slot_mask; ++probes) {
-        s = (s + 1) & slot_mask;
-        c = *reinterpret_cast<volatile unsigned long long*>(&table[s].key);
-        if (c == kEmptyKey) {
-          c = atomicCAS(&table[s].key, (unsigned long long)kEmptyKey, key[i]);
-          if (c == kEmptyKey) { f = 0; done = true; break; }
-        }
-        if ((c & kKmerMask) == canon) { f &= ~c; done = true; break; }
-      }
-      if (!done) { *overflow = 1; continue; }
+    for (int o = 1; o < 32; o <<= 1) {
+      const unsigned long long u = __shfl_up_sync(0xffffffffu, inc, o);
+      if (lane >= (unsigned)o) inc += u;
     }
-    if (f) atomicOr(&table[s].key, (unsigned long long)f);
-    // one 32-bit RED on the fwd (low) or rev (high) half of the counter word
-    atomicAdd(reinterpret_cast<unsigned int*>(&table[s].cnt) + (flip[i] ? 1 : 0), 1u);
+    if (lane == 31) wsum[warp] = inc;
+    __syncthreads();
+    if (warp == 0) {
+      const unsigned long long w = wsum[lane];
+      unsigned long long wi = w;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const unsigned long long u = __shfl_up_sync(0xffffffffu, wi, o);
+        if (lane >= (unsigned)o) wi += u;
+      }
+      wsum[lane] = wi - w;
+    }
+    __syncthreads();
+    const unsigned long long carry = carry_s;
+    if (i < n) out[i] = carry + wsum[warp] + inc - v;
+    __syncthreads();
+    if (threadIdx.x == 1023) carry_s = carry + wsum[31] + inc;
+    __syncthreads();
+  }
+  // block max of the bin sizes (the longest bin bounds pass 3's tail)
+  for (int o = 16; o; o >>= 1) mx = max(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+  if (lane == 0) wsum[warp] = mx;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    for (int w = 1; w < 32; ++w) mx = max(mx, wsum[w]);
+    *total_out = carry_s;
+    *max_out = mx;
+  }
+}
+
+__global__ void __launch_bounds__(kSplitThreads, 2) kmer_split_kernel(const unsigned long long* const* __restrict__ vptr,
+                                                                      const unsigned long long* __restrict__ vcnt,
+                                                                      const uint32_t* __restrict__ vpl,
+                                                                      uint32_t tiles_per_part, int sub_shift, int sub_bits,
+                                                                      unsigned long long* __restrict__ cursors,
+                                                                      const unsigned long long* __restrict__ bin_off,
+                                                                      unsigned long long* __restrict__ out) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  unsigned long long* stage = reinterpret_cast<unsigned long long*>(smem_raw);     // kSplitTile
+  uint16_t* stage_bin = reinterpret_cast<uint16_t*>(stage + kSplitTile);           // kSplitTile
+  const int S = 1 << sub_bits;
+  unsigned long long* gdst = reinterpret_cast<unsigned long long*>(stage_bin + kSplitTile);  // S
+  uint32_t* hist = reinterpret_cast<uint32_t*>(gdst + S);                          // S
+  uint32_t* bin_start = hist + S;                                                  // S
+  __shared__ uint32_t n_tile_s;
+
+  const uint32_t v = blockIdx.x / tiles_per_part, t = blockIdx.x % tiles_per_part;
+  const unsigned long long cnt = vcnt[v];
+  const unsigned long long first = (unsigned long long)t * kSplitTile;
+  if (first >= cnt) return;
+  const unsigned tid = threadIdx.x;
+  for (int d = tid; d < S; d += kSplitThreads) hist[d] = 0;
+  __syncthreads();
+  const unsigned long long* src = vptr[v] + first;
+  const uint32_t n_tile = (uint32_t)min((unsigned long long)kSplitTile, cnt - first);
+  const uint32_t smask = (uint32_t)S - 1;
+  unsigned long long w[kSplitItems];
+  uint32_t rk[kSplitItems / 2];  // two 16-bit ranks per register (rank < 8192); the bin is recomputed from the word
+#pragma unroll
+  for (int i = 0; i < kSplitItems; ++i) {
+    const uint32_t j = i * kSplitThreads + tid;
+    w[i] = j < n_tile ? src[j] : 0ULL;
+  }
+#pragma unroll
+  for (int i = 0; i < kSplitItems; ++i) {
+    const uint32_t j = i * kSplitThreads + tid;
+    uint32_t r = 0;
+    if (j < n_tile) r = atomicAdd(&hist[(uint32_t)(w[i] >> (3 + sub_shift)) & smask], 1u);
+    if (i & 1) rk[i >> 1] |= r << 16; else rk[i >> 1] = r;
+  }
+  __syncthreads();
+  {
+    const int per = (S + kSplitThreads - 1) / kSplitThreads;  // 1..2
+    uint32_t loc[2];
+    uint32_t sum = 0;
+#pragma unroll
+    for (int j = 0; j < 2; ++j) {
+      const int d = (int)tid * per + j;
+      loc[j] = (j < per && d < S) ? hist[d] : 0u;
+      sum += loc[j];
+    }
+    uint32_t tot;
+    uint32_t ex = block_excl_scan_u32(sum, &tot);
+    const size_t gb = (size_t)vpl[v] * S;
+#pragma unroll
+    for (int j = 0; j < 2; ++j) {
+      const int d = (int)tid * per + j;
+      if (j < per && d < S) {
+        bin_start[d] = ex;
+        if (loc[j]) gdst[d] = bin_off[gb + d] + atomicAdd(&cursors[gb + d], (unsigned long long)loc[j]);
+        ex += loc[j];
+      }
+    }
+    if (tid == 0) n_tile_s = tot;
+  }
+  __syncthreads();
+#pragma unroll
+  for (int i = 0; i < kSplitItems; ++i) {
+    const uint32_t j = i * kSplitThreads + tid;
+    if (j < n_tile) {
+      const uint32_t bin = (uint32_t)(w[i] >> (3 + sub_shift)) & smask;
+      const uint32_t pos = bin_start[bin] + ((rk[i >> 1] >> (16 * (i & 1))) & 0xffffu);
+      stage[pos] = w[i];
+      stage_bin[pos] = (uint16_t)bin;
+    }
+  }
+  __syncthreads();
+  const uint32_t n_staged = n_tile_s;
+  for (uint32_t j = tid; j < n_staged; j += kSplitThreads) {
+    const uint32_t bin = stage_bin[j];
+    out[gdst[bin] + (j - bin_start[bin])] = stage[j];
+  }
+}
+
+// ---- pass 3: count one sub-bin per block in a shared-memory hash table ----------------------------------
+// Table of C = 2^c_log2 slots: keys[s] = hash field | fwd/rev flag bits (63/62, as
+// kmer_count_table.h:21-30), cnt[0][s] = fwd_count, cnt[1][s] = rev_count (uint32: the reference's
+// uint8 counters + uint32 overflow table, bs/kmer_counter.cpp:680-685).  Open addressing, linear
+// probing; the slot is the hash bits right below the sub-bin bits.  When the bin is done every used
+// slot is written once: {canonical k-mer | flags, rev << 32 | fwd} to the distinct list, and the
+// k-mer | flags again to the solid list if fwd + rev >= min_count (kmer_passes,
+// modules/bio_mapred/kmerize_bf.cpp:290-318).
+constexpr int kBinThreads = 256;
+constexpr int kBinItems = 4;
+struct BinGeom {
+  int k;
+  int low_bits;       // hash bits a word keeps (2k - batch_bits - part_bits)
+  int sub_bits;
+  int c_log2;
+  uint64_t prefix0;   // (batch << part_bits | first partition of this rank): hash bits above the word's, for bin 0
+  uint32_t min_count;
+};
+
+__global__ void __launch_bounds__(kBinThreads) kmer_count_bins_kernel(const unsigned long long* __restrict__ words,
+                                                                      const unsigned long long* __restrict__ bin_off,
+                                                                      const unsigned long long* __restrict__ bin_cnt,
+                                                                      BinGeom G, CountEntry* __restrict__ out_all,
+                                                                      unsigned long long cap_all,
+                                                                      unsigned long long* __restrict__ out_solid,
+                                                                      unsigned long long cap_solid,
+                                                                      unsigned long long* __restrict__ counters /*[0] distinct [1] solid*/,
+                                                                      int* __restrict__ overflow) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const uint32_t C = 1u << G.c_log2;
+  unsigned long long* keys = reinterpret_cast<unsigned long long*>(smem_raw);  // C
+  unsigned int* cnt = reinterpret_cast<unsigned int*>(keys + C);               // 2 * C
+  __shared__ unsigned long long base_all, base_solid;
+  const uint32_t bin = blockIdx.x;
+  const unsigned long long n = bin_cnt[bin];
+  if (n == 0) return;
+  const unsigned tid = threadIdx.x;
+  for (uint32_t s = tid; s < C; s += kBinThreads) {
+    keys[s] = kEmptyKey;
+    cnt[s] = 0;
+    cnt[C + s] = 0;
+  }
+  __syncthreads();
+  const unsigned long long* src = words + bin_off[bin];
+  const int slot_shift = max(G.low_bits - G.sub_bits - G.c_log2, 0);
+  const uint32_t cmask = C - 1;
+  const uint64_t field_mask = (1ULL << G.low_bits) - 1;
+  bool full = false;
+  for (unsigned long long i0 = 0; i0 < n; i0 += (unsigned long long)kBinThreads * kBinItems) {
+    unsigned long long w[kBinItems];
+    bool valid[kBinItems];
+#pragma unroll
+    for (int j = 0; j < kBinItems; ++j) {
+      const unsigned long long i = i0 + (unsigned long long)j * kBinThreads + tid;
+      valid[j] = i < n;
+      w[j] = valid[j] ? src[i] : 0ULL;
+    }
+#pragma unroll
+    for (int j = 0; j < kBinItems; ++j) {
+      if (!valid[j]) continue;
+      const uint64_t hl = w[j] >> 3;
+      const uint64_t flags = ((w[j] & kWFwd) ? kFwdFlag : 0ULL) | ((w[j] & kWRev) ? kRevFlag : 0ULL);
+      uint32_t s = (uint32_t)(hl >> slot_shift) & cmask;
+      bool done = false;
+      for (uint32_t probes = 0; probes < C; ++probes) {
+        unsigned long long cur = *reinterpret_cast<volatile unsigned long long*>(&keys[s]);
+        if (cur == kEmptyKey) {
+          cur = atomicCAS(&keys[s], (unsigned long long)kEmptyKey, (unsigned long long)(hl | flags));
+          if (cur == kEmptyKey) { done = true; break; }   // claimed: key and flags are in place
+        }
+        if ((cur & field_mask) == hl) {
+          if (flags & ~cur) atomicOr(&keys[s], (unsigned long long)flags);
+          done = true;
+          break;
+        }
+        s = (s + 1) & cmask;
+      }
+      if (!done) { full = true; continue; }
+      atomicAdd(&cnt[((w[j] & kWFlip) ? C : 0u) + s], 1u);
+    }
+  }
+  if (full) *overflow = 1;   // more distinct k-mers than slots: the host re-runs with finer sub-bins
+  __syncthreads();
+  // ---- write-out: thread t owns the slots [t * per, (t + 1) * per) ---------------------------------------
+  const uint32_t per = C / kBinThreads;
+  uint32_t n_used = 0, n_solid = 0;
+  for (uint32_t s = tid * per; s < (tid + 1) * per; ++s) {
+    if (keys[s] != kEmptyKey) {
+      ++n_used;
+      if ((unsigned long long)cnt[s] + cnt[C + s] >= G.min_count) ++n_solid;
+    }
+  }
+  uint32_t tot_used, tot_solid;
+  uint32_t ex_used = block_excl_scan_u32(n_used, &tot_used);
+  uint32_t ex_solid = block_excl_scan_u32(n_solid, &tot_solid);
+  if (tid == 0) {
+    base_all = atomicAdd(&counters[0], (unsigned long long)tot_used);
+    base_solid = tot_solid ? atomicAdd(&counters[1], (unsigned long long)tot_solid) : 0ULL;
+    if (base_all + tot_used > cap_all || (tot_solid && base_solid + tot_solid > cap_solid)) *overflow = 2;
+  }
+  __syncthreads();
+  unsigned long long oa = base_all + ex_used, os = base_solid + ex_solid;
+  const uint64_t prefix = (G.prefix0 + (bin >> G.sub_bits)) << G.low_bits;
+  for (uint32_t s = tid * per; s < (tid + 1) * per; ++s) {
+    const unsigned long long kf = keys[s];
+    if (kf == kEmptyKey) continue;
+    const uint64_t canon = khash_inv(prefix | (kf & field_mask), G.k);
+    const unsigned long long key = canon | (kf & (kFwdFlag | kRevFlag));
+    const unsigned long long f = cnt[s], r = cnt[C + s];
+    if (oa < cap_all) {
+      uint4 e;
+      e.x = (unsigned)key; e.y = (unsigned)(key >> 32); e.z = (unsigned)f; e.w = (unsigned)r;
+      reinterpret_cast<uint4*>(out_all)[oa] = e;
+    }
+    ++oa;
+    if (f + r >= G.min_count) {
+      if (os < cap_solid) out_solid[os] = key;
+      ++os;
+    }
   }
 }
 
 // Distinct estimate over partitioned instance words (multi-GPU: run by the owner after the
 // exchange, because the fused estimate of pass 1 only saw this rank's own reads).
-__global__ void __launch_bounds__(256) kmer_estimate_words_kernel(const unsigned long long* const* __restrict__ part_ptr,
-                                                                  const unsigned long long* __restrict__ part_count,
-                                                                  uint32_t tiles_per_part, int k,
+__global__ void __launch_bounds__(256) kmer_estimate_words_kernel(const unsigned long long* const* __restrict__ vptr,
+                                                                  const unsigned long long* __restrict__ vcnt,
+                                                                  uint32_t tiles_per_part, int samp_shift,
                                                                   unsigned int* __restrict__ bitmap, uint64_t bit_mask) {
-  const uint32_t p = blockIdx.x / tiles_per_part, t = blockIdx.x % tiles_per_part;
-  const unsigned long long cnt = part_count[p];
-  const unsigned long long* src = part_ptr[p];
+  const uint32_t v = blockIdx.x / tiles_per_part, t = blockIdx.x % tiles_per_part;
+  const unsigned long long cnt = vcnt[v];
+  const unsigned long long* src = vptr[v];
 #pragma unroll
-  for (int i = 0; i < kUpsItems; ++i) {
-    const unsigned long long idx = (unsigned long long)t * kUpsTile + (unsigned long long)i * 256 + threadIdx.x;
+  for (int i = 0; i < 16; ++i) {
+    const unsigned long long idx = (unsigned long long)t * 4096 + (unsigned long long)i * 256 + threadIdx.x;
     if (idx >= cnt) continue;
-    bool fl;
-    const uint64_t h = mix64(canonicalize(src[idx] & kKmerMask, k, fl));
-    if ((h & 15) == 0) {
-      const uint64_t bit = (h >> 4) & bit_mask;
+    const uint64_t hl = src[idx] >> 3;
+    if ((hl & ((1ULL << samp_shift) - 1)) == 0) {
+      const uint64_t bit = (hl >> samp_shift) & bit_mask;
       atomicOr(&bitmap[bit >> 5], 1u << (bit & 31));
     }
   }
-}
-
-// Distinct estimate straight from the packed reads (batched counting: the table must be sized
-// before the first batch is upserted, so the estimate cannot ride on pass 1).  A warp per read,
-// lane l takes the k-mers l, l+32, ...; same sampling rule as the fused estimate.
-__global__ void __launch_bounds__(256) kmer_estimate_reads_kernel(const uint64_t* __restrict__ words,
-                                                                  const uint32_t* __restrict__ nmask,
-                                                                  const uint32_t* __restrict__ word_off,
-                                                                  const uint16_t* __restrict__ lens, uint32_t n_reads,
-                                                                  int k, unsigned int* __restrict__ bitmap,
-                                                                  uint64_t bit_mask, int samp_shift) {
-  const uint32_t r = blockIdx.x * (256 / 32) + (threadIdx.x >> 5);
-  if (r >= n_reads) return;
-  const unsigned lane = lane_id();
-  const int nk = (int)lens[r] - k + 1;
-  const uint32_t wb = word_off[r];
-  for (int p = (int)lane; p < nk; p += 32) {
-    const int w = p >> 5;
-    const unsigned sft = lane * 2;
-    const uint64_t hi = words[wb + w], lo = words[wb + w + 1];  // the store has one pad word
-    const uint64_t win = sft ? ((hi << sft) | (lo >> (64 - sft))) : hi;
-    if (nmask != nullptr) {
-      const uint32_t mh = nmask[wb + w], ml = nmask[wb + w + 1];
-      const uint32_t mwin = lane ? ((mh << lane) | (ml >> (32 - lane))) : mh;
-      if ((mwin >> (32 - k)) != 0) continue;
-    }
-    bool fl;
-    const uint64_t h = mix64(canonicalize(win >> (64 - 2 * k), k, fl));
-    if ((h & ((1ULL << samp_shift) - 1)) == 0) {
-      const uint64_t bit = (h >> samp_shift) & bit_mask;
-      atomicOr(&bitmap[bit >> 5], 1u << (bit & 31));
-    }
-  }
-}
-
-// out[i] = OR over the N gathered bitmaps (multi-GPU batched counting: union of every rank's sample)
-__global__ void bitmap_or_kernel(const unsigned int* __restrict__ gathered, int n_maps, uint64_t n_words,
-                                 unsigned int* __restrict__ out) {
-  uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n_words) return;
-  unsigned v = 0;
-  for (int m = 0; m < n_maps; ++m) v |= gathered[(uint64_t)m * n_words + i];
-  out[i] = v;
 }
 
 __global__ void popcount_kernel(const unsigned int* __restrict__ w, uint64_t n, unsigned long long* __restrict__ total) {
@@ -371,19 +548,14 @@ __global__ void popcount_kernel(const unsigned int* __restrict__ w, uint64_t n, 
   }
 }
 
-__global__ void fill_empty_kernel(uint4* __restrict__ t, uint64_t n_slots) {
-  uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < n_slots) t[i] = make_uint4(0xffffffffu, 0xffffffffu, 0u, 0u);
-}
-
 __global__ void fill_u64_kernel(unsigned long long* __restrict__ t, uint64_t n, unsigned long long v) {
   uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) t[i] = v;
 }
 
-// Sweep: one pass over the table.  Each 256-thread block covers kSweepPerBlock slots, stages its
-// passing entries (fwd+rev >= min_count) in shared memory and appends them with ONE global atomic
-// per block; distinct/passing totals are block-reduced the same way.
+// Sweep of the distinct list (export only).  Each 256-thread block covers kSweepPerBlock entries,
+// stages the passing ones (fwd+rev >= min_count) in shared memory and appends them with ONE global
+// atomic per block.
 constexpr int kSweepIters = 8;
 constexpr int kSweepPerBlock = 256 * kSweepIters;
 __global__ void __launch_bounds__(256) table_sweep_kernel(const CountEntry* __restrict__ table, uint64_t n_slots,
@@ -447,15 +619,15 @@ __global__ void __launch_bounds__(256) table_sweep_kernel(const CountEntry* __re
 
 // insert into the solid set (32-byte buckets of four 8-byte slots, common.cuh).  Keys are distinct,
 // so a plain CAS claim suffices; a bucket fills in slot order, a full one sends the key onwards.
-// The home bucket is the TOP bits of the same hash whose top bits order the count table, and the
-// sweep emits the solid k-mers in table order: consecutive threads insert into consecutive
-// buckets, so building the set is a near-sequential write instead of one random DRAM CAS per key.
-__global__ void solid_insert_kernel(const unsigned long long* __restrict__ keys, uint64_t n,
+// The home bucket is the TOP bits of the hash that orders the counting bins, and pass 3 emits the
+// solid k-mers roughly bin by bin: consecutive threads insert into nearby buckets, so building the
+// set is a near-sequential write instead of one random DRAM CAS per key.
+__global__ void solid_insert_kernel(const unsigned long long* __restrict__ keys, uint64_t n, int k,
                                     unsigned long long* __restrict__ set, uint64_t bucket_mask, int bucket_shift) {
   uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   unsigned long long kf = keys[i];
-  uint64_t b = mix64(kf & kKmerMask) >> bucket_shift;
+  uint64_t b = khash(kf & kKmerMask, k) >> bucket_shift;
   for (;;) {
 #pragma unroll
     for (int j = 0; j < 4; ++j)
@@ -494,26 +666,23 @@ uint64_t pow2_ceil(uint64_t x) {
   return p;
 }
 
-}  // namespace
-
-namespace {
+int log2_exact(uint64_t x) {
+  int l = 0;
+  while ((1ULL << l) < x) ++l;
+  return l;
+}
 
 template <int MAXIT, int RPW>
-void launch_partition(Context* c, uint64_t r0, uint64_t n_reads, int part_bits, unsigned long long* cursors,
+void launch_partition(Context* c, uint64_t r0, uint64_t n_reads, const PartGeom& G, unsigned long long* cursors,
                       const unsigned long long* part_base, unsigned long long cap, unsigned long long* out,
                       unsigned int* bitmap, uint64_t bit_mask, int samp_shift, int* overflow) {
   constexpr int tile_reads = kPartWarps * RPW;
   constexpr int tile_kmers = tile_reads * MAXIT * 32;
   constexpr int wpr = MAXIT + 1;
   const size_t smem = (size_t)tile_kmers * 8 + (size_t)(tile_reads * wpr + 2) * 12 + (size_t)tile_kmers * 2 +
-                      ((size_t)16 << part_bits);
-  static bool attr_set = false;
-  if (!attr_set) {
-    const size_t smem_max = (size_t)tile_kmers * 10 + (size_t)(tile_reads * wpr + 2) * 12 + ((size_t)16 << kMaxPartBits);
-    BGX_CUDA(cudaFuncSetAttribute(kmer_partition_kernel<MAXIT, RPW>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                  (int)smem_max));
-    attr_set = true;
-  }
+                      ((size_t)16 << G.part_bits);
+  // the opt-in is per device: set it on every launch (cheap) rather than once per process
+  BGX_CUDA(cudaFuncSetAttribute(kmer_partition_kernel<MAXIT, RPW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   int blocks_per_sm = 1;
   BGX_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, kmer_partition_kernel<MAXIT, RPW>,
                                                          kPartThreads, smem));
@@ -522,26 +691,20 @@ void launch_partition(Context* c, uint64_t r0, uint64_t n_reads, int part_bits, 
   const unsigned n_tiles = (unsigned)((n_reads + tile_reads - 1) / tile_reads);
   const unsigned grid = std::min<unsigned>(n_tiles, (unsigned)(kNumSMs * blocks_per_sm));
   note_launch();
-  // a batch is a range of reads: word offsets are absolute, so only the per-read arrays shift
+  // a range of reads: word offsets are absolute, so only the per-read arrays shift
   kmer_partition_kernel<MAXIT, RPW><<<grid, kPartThreads, smem, c->stream>>>(
-      c->words.p, c->has_n ? c->nmask.p : nullptr, c->word_off.p + r0, c->lens.p + r0, (uint32_t)n_reads,
-      c->opt.kmer_size, part_bits, cursors, part_base, cap, out, bitmap, bit_mask, samp_shift, overflow);
+      c->words.p, c->has_n ? c->nmask.p : nullptr, c->word_off.p + r0, c->lens.p + r0, (uint32_t)n_reads, G, cursors,
+      part_base, cap, out, bitmap, bit_mask, samp_shift, overflow);
   BGX_CUDA(cudaGetLastError());
 }
 
-void run_partition(Context* c, int maxit, uint64_t r0, uint64_t n_reads, int part_bits, unsigned long long* cursors,
+void run_partition(Context* c, int maxit, uint64_t r0, uint64_t n_reads, const PartGeom& G, unsigned long long* cursors,
                    const unsigned long long* part_base, unsigned long long cap, unsigned long long* out,
                    unsigned int* bitmap, uint64_t bit_mask, int samp_shift, int* overflow) {
   if (maxit <= 4)
-    launch_partition<4, 4>(c, r0, n_reads, part_bits, cursors, part_base, cap, out, bitmap, bit_mask, samp_shift, overflow);
+    launch_partition<4, 4>(c, r0, n_reads, G, cursors, part_base, cap, out, bitmap, bit_mask, samp_shift, overflow);
   else
-    launch_partition<8, 2>(c, r0, n_reads, part_bits, cursors, part_base, cap, out, bitmap, bit_mask, samp_shift, overflow);
-}
-
-int log2_exact(uint64_t x) {
-  int l = 0;
-  while ((1ULL << l) < x) ++l;
-  return l;
+    launch_partition<8, 2>(c, r0, n_reads, G, cursors, part_base, cap, out, bitmap, bit_mask, samp_shift, overflow);
 }
 
 // the linear-counting sample: bit (h >> shift) & (bits - 1) of the bitmap for hashes with `shift` low zero bits
@@ -570,7 +733,7 @@ struct Estimator {
   }
 };
 
-// pass-1 output for a range of reads
+// pass-1 output for one batch
 struct Partitioned {
   DevBuf<unsigned long long> pk;
   std::vector<unsigned long long> base, count;  // per partition: first word, words
@@ -578,11 +741,12 @@ struct Partitioned {
   bool exact = false;                           // re-run with exact offsets (a heavy hitter overfilled a partition)
 };
 
-// Pass 1 over reads [r0, r0 + n): K = their k-mer instances.  est (optional) receives the fused sample.
-void partition_reads(Context* c, uint64_t r0, uint64_t n, uint64_t K, int part_bits, int maxit, Estimator* est,
-                     Partitioned* out) {
+// Pass 1 over all reads for one batch: K = the k-mer instances expected in it.  est (optional)
+// receives the fused sample.
+void partition_reads(Context* c, uint64_t K, const PartGeom& G, int maxit, Estimator* est, Partitioned* out) {
   cudaStream_t s = c->stream;
-  const int P = 1 << part_bits;
+  const uint64_t n = c->n_reads;
+  const int P = 1 << G.part_bits;
   unsigned long long cap = K / P + K / (8ull * P) + 4096;  // hash partitions are near uniform
   ScopedStage st_alloc(c, "count_setup");
   out->pk.alloc((size_t)cap * P, s);
@@ -600,25 +764,25 @@ void partition_reads(Context* c, uint64_t r0, uint64_t n, uint64_t K, int part_b
   unsigned int* bitmap = est ? est->bitmap.p : nullptr;
   const uint64_t bit_mask = est ? est->bits - 1 : 0;
   const int shift = est ? est->shift : 4;
-  if (n && !c->upload.empty() && r0 == 0 && n == c->n_reads) {
+  if (n && !c->upload.empty()) {
     // the reads are still arriving (bgx_add_reads_packed_async): one launch per upload chunk, each
     // ordered after its own copy only, all appending to the same partitions through the cursors
     uint64_t pos = 0;
     for (Context::UploadChunk& ch : c->upload) {
       if (ch.r0 > pos)
-        run_partition(c, maxit, pos, ch.r0 - pos, part_bits, cursors.p, part_base.p, cap, out->pk.p, bitmap, bit_mask, shift, overflow.p);
+        run_partition(c, maxit, pos, ch.r0 - pos, G, cursors.p, part_base.p, cap, out->pk.p, bitmap, bit_mask, shift, overflow.p);
       BGX_CUDA(cudaStreamWaitEvent(s, ch.ev, 0));
       cudaEventDestroy(ch.ev);
       if (ch.r1 > ch.r0)
-        run_partition(c, maxit, ch.r0, ch.r1 - ch.r0, part_bits, cursors.p, part_base.p, cap, out->pk.p, bitmap, bit_mask, shift, overflow.p);
+        run_partition(c, maxit, ch.r0, ch.r1 - ch.r0, G, cursors.p, part_base.p, cap, out->pk.p, bitmap, bit_mask, shift, overflow.p);
       pos = ch.r1;
     }
     c->upload.clear();
     if (pos < n)
-      run_partition(c, maxit, pos, n - pos, part_bits, cursors.p, part_base.p, cap, out->pk.p, bitmap, bit_mask, shift, overflow.p);
+      run_partition(c, maxit, pos, n - pos, G, cursors.p, part_base.p, cap, out->pk.p, bitmap, bit_mask, shift, overflow.p);
   } else if (n) {
     reads_ready(c);
-    run_partition(c, maxit, r0, n, part_bits, cursors.p, part_base.p, cap, out->pk.p, bitmap, bit_mask, shift, overflow.p);
+    run_partition(c, maxit, 0, n, G, cursors.p, part_base.p, cap, out->pk.p, bitmap, bit_mask, shift, overflow.p);
   }
   BGX_CUDA(cudaMemcpyAsync(&h_over, overflow.p, sizeof(int), cudaMemcpyDeviceToHost, s));
   BGX_CUDA(cudaMemcpyAsync(out->count.data(), cursors.p, P * 8, cudaMemcpyDeviceToHost, s));
@@ -640,7 +804,7 @@ void partition_reads(Context* c, uint64_t r0, uint64_t n, uint64_t K, int part_b
     BGX_CUDA(cudaMemcpyAsync(part_base.p, out->base.data(), P * 8, cudaMemcpyHostToDevice, s));
     BGX_CUDA(cudaMemsetAsync(cursors.p, 0, P * 8, s));
     BGX_CUDA(cudaMemsetAsync(overflow.p, 0, sizeof(int), s));
-    run_partition(c, maxit, r0, n, part_bits, cursors.p, part_base.p, cap, out->pk.p, bitmap, bit_mask, shift, overflow.p);
+    run_partition(c, maxit, 0, n, G, cursors.p, part_base.p, cap, out->pk.p, bitmap, bit_mask, shift, overflow.p);
     BGX_CUDA(cudaMemcpyAsync(&h_over, overflow.p, sizeof(int), cudaMemcpyDeviceToHost, s));
     BGX_CUDA(cudaStreamSynchronize(s));
     BGX_CHECK(!h_over, "internal: exact partition pass overflowed");
@@ -651,25 +815,28 @@ void partition_reads(Context* c, uint64_t r0, uint64_t n, uint64_t K, int part_b
   st.stop();
 }
 
-// the partitions this rank will count: (device address, instance count) each
+// the partitions this rank will count: (device address, instance count, local partition) each
 struct Owned {
   std::vector<unsigned long long> ptr, cnt;
+  std::vector<uint32_t> pl;
   DevBuf<unsigned long long> rbuf;  // what arrived from the peers
   uint64_t n_inst = 0;
 };
 
 // Single GPU: the P partitions where pass 1 left them.  Multi-GPU: every partition goes to its
 // owner over NVLink; partition p of source rank s arrives as its own "virtual partition", listed
-// partition-major so pass 2 still walks the table slice by slice.
+// partition-major.
 void exchange_partitions(Context* c, const Partitioned& pt, int P, Owned* own) {
   cudaStream_t s = c->stream;
   const int N = c->dist.nranks, R = c->dist.rank;
   own->ptr.clear();
   own->cnt.clear();
+  own->pl.clear();
   if (N == 1) {
     for (int p = 0; p < P; ++p) {
       own->ptr.push_back((unsigned long long)(uintptr_t)(pt.pk.p + pt.base[p]));
       own->cnt.push_back(pt.count[p]);
+      own->pl.push_back((uint32_t)p);
     }
   } else {
     ScopedStage st(c, "count_exchange");
@@ -714,6 +881,7 @@ void exchange_partitions(Context* c, const Partitioned& pt, int P, Owned* own) {
               src == R ? pt.pk.p + (uint64_t)(p0 + pl) * cap : own->rbuf.p + src_off[src] + (uint64_t)pl * cap_s;
           own->ptr.push_back((unsigned long long)(uintptr_t)ptr);
           own->cnt.push_back(cnt_of(src, p0 + pl));
+          own->pl.push_back((uint32_t)pl);
         }
     } else {
       // general path (some rank re-ran pass 1 with exact offsets): one message per partition.
@@ -748,6 +916,7 @@ void exchange_partitions(Context* c, const Partitioned& pt, int P, Owned* own) {
         for (int src = 0; src < N; ++src) cnt += cnt_of(src, p0 + pl);
         own->ptr.push_back((unsigned long long)(uintptr_t)(own->rbuf.p + l_base[pl]));
         own->cnt.push_back(cnt);
+        own->pl.push_back((uint32_t)pl);
       }
     }
     dist_p2p_batch(c, sends, recvs);
@@ -764,8 +933,11 @@ void exchange_partitions(Context* c, const Partitioned& pt, int P, Owned* own) {
 // device-side view of an Owned list, ready for the tile kernels
 struct OwnedDev {
   DevBuf<unsigned long long> ptr, cnt;
-  uint32_t V = 0, tiles_per_part = 1;
+  DevBuf<uint32_t> pl;
+  uint32_t V = 0;
+  uint64_t max_count = 0;
   const unsigned long long* const* part_ptr() const { return reinterpret_cast<const unsigned long long* const*>(ptr.p); }
+  uint32_t blocks(uint64_t tile) const { return (uint32_t)std::max<uint64_t>(1, (max_count + tile - 1) / tile); }
 };
 
 void upload_owned(Context* c, const Owned& own, OwnedDev* d) {
@@ -773,62 +945,23 @@ void upload_owned(Context* c, const Owned& own, OwnedDev* d) {
   d->V = (uint32_t)own.ptr.size();
   d->ptr.alloc(d->V, s);
   d->cnt.alloc(d->V, s);
+  d->pl.alloc(d->V, s);
   BGX_CUDA(cudaMemcpyAsync(d->ptr.p, own.ptr.data(), d->V * 8, cudaMemcpyHostToDevice, s));
   BGX_CUDA(cudaMemcpyAsync(d->cnt.p, own.cnt.data(), d->V * 8, cudaMemcpyHostToDevice, s));
-  uint64_t max_count = 0;
-  for (unsigned long long v : own.cnt) max_count = std::max<uint64_t>(max_count, v);
-  d->tiles_per_part = (uint32_t)std::max<uint64_t>(1, (max_count + kUpsTile - 1) / kUpsTile);
-  BGX_CHECK((uint64_t)d->tiles_per_part * d->V < (1ull << 31), "too many k-mer tiles for one launch");
+  BGX_CUDA(cudaMemcpyAsync(d->pl.p, own.pl.data(), d->V * 4, cudaMemcpyHostToDevice, s));
+  d->max_count = 0;
+  for (unsigned long long v : own.cnt) d->max_count = std::max<uint64_t>(d->max_count, v);
+  BGX_CHECK((uint64_t)d->blocks(4096) * d->V < (1ull << 31), "too many k-mer tiles for one launch");
   // the host vectors must outlive the copies
   BGX_CUDA(cudaStreamSynchronize(s));
 }
 
-// table slots for an estimated distinct count: load factor in (1/3, 2/3]
-uint64_t slots_for(uint64_t est_distinct) {
-  uint64_t slots = pow2_ceil(std::max<uint64_t>(1024, est_distinct + est_distinct / 2));
-  if (const char* e = getenv("BGX_TABLE_SLOTS_LOG2")) slots = 1ull << atoi(e);  // experiment hook
-  return slots;
-}
-
-void alloc_table(Context* c, uint64_t slots) {
-  cudaStream_t s = c->stream;
-  ScopedStage st_sz(c, "count_table_alloc");
-  BGX_CHECK(slots <= (1ull << 32), "k-mer table too large for one GPU shard (slot index is 32-bit)");
-  c->table_slots = slots;
-  c->table.alloc(slots, s);  // throws "out of device memory" if the table cannot fit
-  st_sz.stop();
-  ScopedStage st(c, "count_init");
-  KLAUNCH(fill_empty_kernel)<<<(unsigned)((slots + 255) / 256), 256, 0, s>>>(reinterpret_cast<uint4*>(c->table.p), slots);
-  BGX_CUDA(cudaGetLastError());
-  st.stop();
-}
-
-void upsert_owned(Context* c, const OwnedDev& od, int rank_bits, int* overflow) {
-  ScopedStage st(c, "count_kernel");
-  static const bool cas_first = [] { const char* e = getenv("BGX_UPSERT_CAS_FIRST"); return e ? atoi(e) != 0 : true; }();  // experiment hook
-  note_launch();
-  if (cas_first)
-    kmer_upsert_kernel<true><<<od.tiles_per_part * od.V, 256, 0, c->stream>>>(
-        od.part_ptr(), od.cnt.p, od.tiles_per_part, c->opt.kmer_size, c->table.p, log2_exact(c->table_slots), rank_bits, overflow);
-  else
-    kmer_upsert_kernel<false><<<od.tiles_per_part * od.V, 256, 0, c->stream>>>(
-      od.part_ptr(), od.cnt.p, od.tiles_per_part, c->opt.kmer_size, c->table.p, log2_exact(c->table_slots), rank_bits, overflow);
-  BGX_CUDA(cudaGetLastError());
-  st.stop();
-}
-
-int read_flag(const int* d, cudaStream_t s) {
-  int h = 0;
-  BGX_CUDA(cudaMemcpyAsync(&h, d, sizeof(int), cudaMemcpyDeviceToHost, s));
-  BGX_CUDA(cudaStreamSynchronize(s));
-  return h;
-}
-
-// How many batches of reads pass 1 + pass 2 run in.  One batch keeps all K instance words (and,
-// multi-GPU, what the peers send) in HBM next to the table; the batched form bounds those buffers
-// to ~40 % of the device so that inputs like GRCh38 30x on 8 GPUs (84 + 66 GB of words per GPU
-// next to a 69 GB table) still fit.  Every rank must use the same count (each batch is a
-// collective exchange).
+// How many hash-range batches the counting runs in (a power of two).  One batch keeps all K instance
+// words twice (pass-1 output and the split copy; multi-GPU also what the peers send) in HBM; more
+// batches bound those buffers to ~45 % of the device so that inputs like GRCh38 30x on 8 GPUs
+// (3 x 75 GB of words per GPU) still fit.  Every rank must use the same count (each batch is a
+// collective exchange).  count_batch_reads (option / BGX_COUNT_BATCH_READS) asks for at least
+// ceil(reads / that) batches.
 uint64_t choose_batches(Context* c, uint64_t K_local, uint64_t K_share) {
   const int N = c->dist.nranks;
   uint64_t batches = 1;
@@ -837,8 +970,9 @@ uint64_t choose_batches(Context* c, uint64_t K_local, uint64_t K_share) {
   if (batch_reads) {
     batches = std::max<uint64_t>(1, (c->n_reads + batch_reads - 1) / batch_reads);
   } else {
-    const double budget = 0.4 * (double)c->total_mem;
-    const double need = 9.0 * (double)K_local + (N > 1 ? 9.0 * (double)K_share : 0.0);  // 8 B per word + 1/8 slack
+    const double budget = 0.45 * (double)c->total_mem;
+    // 8 B per word + 1/8 slack out of pass 1, what arrives from the peers, the split copy
+    const double need = 9.0 * (double)K_local + (N > 1 ? 9.0 : 0.0) * (double)K_share + 8.0 * (double)K_share;
     batches = std::max<uint64_t>(1, (uint64_t)std::ceil(need / budget));
   }
   if (N > 1) {
@@ -846,151 +980,195 @@ uint64_t choose_batches(Context* c, uint64_t K_local, uint64_t K_share) {
     dist_allgather_host_u64(c, &batches, 1, all.data());
     for (uint64_t v : all) batches = std::max(batches, v);
   }
+  batches = pow2_ceil(batches);
+  BGX_CHECK(batches <= 4096, "k-mer counting would need more than 4096 batches");
   return batches;
 }
+
+// results of one batch, appended to the lists of the whole run at the end
+struct BatchOut {
+  DevBuf<CountEntry> all;
+  DevBuf<unsigned long long> solid;
+  uint64_t n_all = 0, n_solid = 0;
+};
 
 }  // namespace
 
 void stage_count_kmers(Context* c) {
   cudaStream_t s = c->stream;
   const int k = c->opt.kmer_size;
-  const int N = c->dist.nranks;
+  const int N = c->dist.nranks, R = c->dist.rank;
   const int rank_bits = log2_exact((uint64_t)N);
   BGX_CHECK(c->n_reads > 0 || N > 1, "bgx_count_kmers: no reads");
   ScopedStage st_all(c, "count_total");
+  c->table.release();
+  c->solid.release();
   const uint64_t K = c->n_kmer_instances;  // this rank's reads
   uint64_t K_all = K;                      // all ranks' reads
   dist_allreduce_sum_host_u64(c, &K_all, 1);
   const uint64_t K_share = K_all / N;      // instances this rank will own (hash-uniform)
-
-  // P partitions so that one partition's slice of the owner's table (~4 B per instance at typical
-  // coverage) is at most ~64 MB = half of L2; measured on B200: fewer, larger partitions make
-  // pass 1 faster (longer coalesced runs) and pass 2 is insensitive down to 64 MB slices.
-  // Rank r owns the contiguous block of partitions [r*P/N, (r+1)*P/N) (same P on every rank).
-  int part_bits = 7;
-  while (part_bits < kMaxPartBits && (K_all * 4 >> part_bits) > (64ull << 20)) ++part_bits;
-  if (const char* e = getenv("BGX_PART_BITS")) part_bits = std::max(1, std::min(kMaxPartBits, atoi(e)));
-  part_bits = std::max(part_bits, rank_bits);
-  const int P = 1 << part_bits;
   const int maxit = (int)((std::max<int64_t>((int64_t)c->max_len - k + 1, 1) + 31) / 32);
   BGX_CHECK(maxit <= 8, "read longer than 255 bases");
   const uint64_t batches = choose_batches(c, K, K_share);
+  const int batch_bits = log2_exact(batches);
   c->set_stat("count_batches", (double)batches);
-  DevBuf<int> overflow(1, s);
-  uint64_t n_inst = 0;   // instances this rank counted
-  uint64_t slots = 0;
 
-  if (batches == 1) {
-    // ---- everything at once: pass 1 carries the distinct estimate, then the table is sized ---------
+  // Partitions per batch: pass 1 writes longer coalesced runs with fewer partitions (128 measured
+  // best on B200), but every rank needs at least one, and a partition should stay well below 2^31
+  // words.  Rank r owns the contiguous block [r*P/N, (r+1)*P/N) (same P on every rank).
+  int part_bits = kMinPartBits;
+  while (part_bits < kMaxPartBits && ((K_all / batches) >> part_bits) > (8ull << 20)) ++part_bits;
+  if (const char* e = getenv("BGX_PART_BITS")) part_bits = std::max(1, std::min(kMaxPartBits, atoi(e)));
+  part_bits = std::max(part_bits, rank_bits);
+  BGX_CHECK(2 * k - batch_bits - part_bits >= 16, "k-mer too short for this many batches / partitions");
+  int c_log2 = 12;  // 4096 slots = 64 KB of shared memory per block, three blocks per SM
+  if (const char* e = getenv("BGX_BIN_SLOTS_LOG2")) c_log2 = std::max(8, std::min(13, atoi(e)));  // experiment hook
+
+  DevBuf<int> overflow(1, s);
+  std::vector<BatchOut> outs(batches);
+  uint64_t n_inst = 0, total_all = 0, total_solid = 0;
+  double alg_part = 0, alg_split = 0, alg_bins = 0;
+  int sub_bits_used = 0;
+
+  for (uint64_t b = 0; b < batches; ++b) {
+    PartGeom G{k, batch_bits, (uint32_t)b, part_bits};
+    int P = 1 << part_bits;
+    const int low_bits = 2 * k - batch_bits - part_bits;
+    // ---- pass 1 (+ exchange) -----------------------------------------------------------------------
     Estimator est;
-    est.init(pow2_ceil(std::max<uint64_t>(1 << 20, std::max(K, K_share) / 8)), 4, s);
+    const uint64_t Kb = K / batches + K / (16 * batches) + 1024;  // this rank's instances in the batch (hash-uniform)
+    est.init(pow2_ceil(std::max<uint64_t>(1 << 20, std::max(Kb, K_share / batches) / 8)), 4, s);
     Partitioned pt;
-    partition_reads(c, 0, c->n_reads, K, part_bits, maxit, &est, &pt);
+    partition_reads(c, Kb, G, maxit, N == 1 ? &est : nullptr, &pt);
     Owned own;
     exchange_partitions(c, pt, P, &own);
     OwnedDev od;
     upload_owned(c, own, &od);
-    n_inst = own.n_inst;
+    n_inst += own.n_inst;
+    alg_part += (double)c->n_bases / 4 + 8.0 * (double)own.n_inst;
     if (N > 1) {
-      // the owner estimates the distinct count of what it received (pass 1 filled the bitmap with
-      // this rank's own reads over the whole hash space: start over)
-      BGX_CUDA(cudaMemsetAsync(est.bitmap.p, 0, est.bits / 8, s));
-      KLAUNCH(kmer_estimate_words_kernel)<<<od.tiles_per_part * od.V, 256, 0, s>>>(od.part_ptr(), od.cnt.p, od.tiles_per_part, k,
-                                                                           est.bitmap.p, est.bits - 1);
+      // the owner estimates the distinct count of what it received
+      KLAUNCH(kmer_estimate_words_kernel)<<<od.blocks(4096) * od.V, 256, 0, s>>>(od.part_ptr(), od.cnt.p, od.blocks(4096),
+                                                                          est.shift, est.bitmap.p, est.bits - 1);
       BGX_CUDA(cudaGetLastError());
     }
     uint64_t est_distinct = est.estimate(s);
-    est_distinct = std::min<uint64_t>(est_distinct + est_distinct / 16 + 4096, n_inst + 1);
-    c->set_stat("kmer_distinct_estimate", (double)est_distinct);
-    slots = slots_for(est_distinct);
-    for (int tries = 0;; ++tries) {
-      alloc_table(c, slots);
-      BGX_CUDA(cudaMemsetAsync(overflow.p, 0, sizeof(int), s));
-      upsert_owned(c, od, rank_bits, overflow.p);
-      if (!read_flag(overflow.p, s)) break;
-      // estimate was off (cannot happen for slots > distinct; belt and braces): double and redo.
-      // The reference throws io_exception("Kmer table (...) too small") (bs/kmer_count_table.h:75).
-      BGX_CHECK(tries < 3, "Kmer table too small");
-      slots *= 2;
-    }
-  } else {
-    // ---- batched: estimate from the reads first, then partition / exchange / upsert batch by batch ---
-    reads_ready(c);
-    Estimator est;
-    {
-      ScopedStage st(c, "count_estimate");
-      // sample so thinly that at most ~2^29 instances are expected in it; the bitmap has twice as many bits
-      int shift = 4;
-      while ((K_all >> shift) > (1ull << 29)) ++shift;
-      est.init(pow2_ceil(std::max<uint64_t>(1 << 20, (K_all >> shift) * 2)), shift, s);
-      if (c->n_reads)
-        KLAUNCH(kmer_estimate_reads_kernel)<<<(unsigned)((c->n_reads + 7) / 8), 256, 0, s>>>(
-            c->words.p, c->has_n ? c->nmask.p : nullptr, c->word_off.p, c->lens.p, (uint32_t)c->n_reads, k, est.bitmap.p,
-            est.bits - 1, est.shift);
-      BGX_CUDA(cudaGetLastError());
-      if (N > 1) {
-        // union of every rank's sample; an owner then holds 1/N of the distinct k-mers (hash-uniform)
-        DevBuf<unsigned int> gathered((size_t)N * (est.bits / 32), s);
-        dist_allgather_bytes(c, est.bitmap.p, gathered.p, est.bits / 8);
-        KLAUNCH(bitmap_or_kernel)<<<(unsigned)((est.bits / 32 + 255) / 256), 256, 0, s>>>(gathered.p, N, est.bits / 32, est.bitmap.p);
-        BGX_CUDA(cudaGetLastError());
-      }
-      st.stop();
-    }
-    uint64_t est_distinct = est.estimate(s) / N;
-    est_distinct = est_distinct + est_distinct / 16 + 4096;
-    c->set_stat("kmer_distinct_estimate", (double)est_distinct);
+    est_distinct = std::min<uint64_t>(est_distinct + est_distinct / 16 + 4096, own.n_inst + 1);
+    c->add_stat("kmer_distinct_estimate", (double)est_distinct);
     est.bitmap.release();
-    slots = slots_for(est_distinct);
-    // per-read instance counts are not kept on the host: a batch's K is bounded by its share of the bases
+
+    // ---- pass 2 + 3, finer sub-bins if a bin overflows its table -------------------------------------
+    const int Pl = P / N;
+    // sub-bins so that a bin holds ~half a table of distinct k-mers on average
+    const uint64_t per_bin = (1ull << c_log2) / 2;
+    int sub_bits = 0;
+    while (sub_bits < kMaxSubBits && ((uint64_t)Pl << sub_bits) * per_bin < est_distinct) ++sub_bits;
+    if (const char* e = getenv("BGX_SUB_BITS")) sub_bits = std::max(0, std::min(kMaxSubBits, atoi(e)));  // test hook
+    BatchOut& bo = outs[b];
     for (int tries = 0;; ++tries) {
-      alloc_table(c, slots);
+      sub_bits = std::min(sub_bits, low_bits - 1);
+      const int S = 1 << sub_bits;
+      const size_t n_bins = (size_t)Pl * S;
+      const int sub_shift = low_bits - sub_bits;
+      DevBuf<unsigned long long> hist(n_bins, s), bin_off(n_bins, s), cursors(n_bins, s), scal(2, s);
+      DevBuf<unsigned long long> split(std::max<uint64_t>(own.n_inst, 1), s);
+      {
+        ScopedStage st(c, "count_split");
+        BGX_CUDA(cudaMemsetAsync(hist.p, 0, n_bins * 8, s));
+        BGX_CUDA(cudaMemsetAsync(cursors.p, 0, n_bins * 8, s));
+        if (own.n_inst) {
+          const uint32_t hb = od.blocks((uint64_t)kSplitTile * kHistTiles);
+          KLAUNCH(kmer_subhist_kernel)<<<hb * od.V, kSplitThreads, 0, s>>>(od.part_ptr(), od.cnt.p, od.pl.p, hb, sub_shift, sub_bits,
+                                                                     hist.p);
+        }
+        KLAUNCH(scan_u64_kernel)<<<1, 1024, 0, s>>>(hist.p, n_bins, bin_off.p, scal.p, scal.p + 1);
+        if (own.n_inst) {
+          const size_t smem = (size_t)kSplitTile * 10 + (size_t)S * 16;
+          BGX_CUDA(cudaFuncSetAttribute(kmer_split_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+          const uint32_t tb = od.blocks(kSplitTile);
+          KLAUNCH(kmer_split_kernel)<<<tb * od.V, kSplitThreads, smem, s>>>(od.part_ptr(), od.cnt.p, od.pl.p, tb, sub_shift, sub_bits,
+                                                                      cursors.p, bin_off.p, split.p);
+        }
+        BGX_CUDA(cudaGetLastError());
+        st.stop();
+      }
+      unsigned long long h_scal[2] = {0, 0};
+      BGX_CUDA(cudaMemcpyAsync(h_scal, scal.p, 16, cudaMemcpyDeviceToHost, s));
+      BGX_CUDA(cudaStreamSynchronize(s));
+      BGX_CHECK(h_scal[0] == own.n_inst, "internal: sub-bin histogram does not add up");
+      c->set_stat("count_largest_bin", (double)h_scal[1]);
+
+      ScopedStage st(c, "count_kernel");
+      const uint64_t cap_all = est_distinct + est_distinct / 8 + 65536;
+      const uint64_t cap_solid = std::min<uint64_t>(cap_all, own.n_inst / (uint64_t)c->opt.min_kmer_count + 1);
+      bo.all.alloc(cap_all, s);
+      bo.solid.alloc(cap_solid, s);
+      DevBuf<unsigned long long> counters(2, s);
+      BGX_CUDA(cudaMemsetAsync(counters.p, 0, 16, s));
       BGX_CUDA(cudaMemsetAsync(overflow.p, 0, sizeof(int), s));
-      n_inst = 0;
-      bool over = false;
-      for (uint64_t b = 0; b < batches && !over; ++b) {
-        const uint64_t r0 = c->n_reads * b / batches, r1 = c->n_reads * (b + 1) / batches;
-        // instances of the batch: at most (max_len - k + 1) per read
-        const uint64_t Kb = std::min<uint64_t>(K, (r1 - r0) * (uint64_t)std::max<int64_t>((int64_t)c->max_len - k + 1, 0));
-        Partitioned pt;
-        partition_reads(c, r0, r1 - r0, Kb, part_bits, maxit, nullptr, &pt);
-        Owned own;
-        exchange_partitions(c, pt, P, &own);
-        OwnedDev od;
-        upload_owned(c, own, &od);
-        n_inst += own.n_inst;
-        upsert_owned(c, od, rank_bits, overflow.p);
-        over = read_flag(overflow.p, s) != 0;  // also: the batch's buffers are free to go
+      BinGeom BG{k, low_bits, sub_bits, c_log2, ((uint64_t)b << part_bits) | (uint64_t)(R * Pl), (uint32_t)c->opt.min_kmer_count};
+      const size_t smem = (size_t)16 << c_log2;
+      BGX_CUDA(cudaFuncSetAttribute(kmer_count_bins_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      KLAUNCH(kmer_count_bins_kernel)<<<(unsigned)n_bins, kBinThreads, smem, s>>>(split.p, bin_off.p, hist.p, BG, bo.all.p, cap_all,
+                                                                          bo.solid.p, cap_solid, counters.p, overflow.p);
+      BGX_CUDA(cudaGetLastError());
+      unsigned long long h_cnt[2];
+      int h_over = 0;
+      BGX_CUDA(cudaMemcpyAsync(h_cnt, counters.p, 16, cudaMemcpyDeviceToHost, s));
+      BGX_CUDA(cudaMemcpyAsync(&h_over, overflow.p, sizeof(int), cudaMemcpyDeviceToHost, s));
+      BGX_CUDA(cudaStreamSynchronize(s));
+      st.stop();
+      alg_split += 24.0 * (double)own.n_inst;
+      alg_bins += 8.0 * (double)own.n_inst + 16.0 * (double)h_cnt[0] + 8.0 * (double)h_cnt[1];
+      if (!h_over) {
+        bo.n_all = h_cnt[0];
+        bo.n_solid = h_cnt[1];
+        sub_bits_used = std::max(sub_bits_used, sub_bits);
+        break;
       }
-      if (N > 1) {  // every rank must take the same branch: the batches are collective
-        uint64_t any = over ? 1 : 0;
-        dist_allreduce_sum_host_u64(c, &any, 1);
-        over = any != 0;
-      }
-      if (!over) break;
-      BGX_CHECK(tries < 3, "Kmer table too small");
-      slots *= 2;
+      // a sub-bin had more distinct k-mers than table slots, or the estimate was low: finer bins,
+      // then larger tables, larger lists.  The reference throws io_exception("Kmer table (...) too
+      // small") when ITS table fills (bs/kmer_count_table.h:75).
+      BGX_CHECK(tries < 6, "Kmer table too small");
+      c->add_stat("count_bin_reruns", 1);
+      if (h_over == 2) est_distinct = std::max<uint64_t>(est_distinct * 2, h_cnt[0] + h_cnt[0] / 8);
+      else if (sub_bits < std::min(kMaxSubBits, low_bits - 1)) ++sub_bits;
+      else if (c_log2 < 13) ++c_log2;
+      else BGX_CHECK(false, "Kmer table too small");
     }
+    total_all += bo.n_all;
+    total_solid += bo.n_solid;
   }
 
-  // filter (kmer_passes: fwd+rev >= min_count) and build the solid set: ONE sweep into buffers
-  // sized by the bound #solid <= instances / min_count.
-  DevBuf<unsigned long long> counters(2, s);
-  unsigned long long h_cnt[2];
+  // ---- the lists of the whole run: batch 0's buffers as they are, or the batches concatenated ---------
+  DevBuf<unsigned long long> solid_list;
   {
     ScopedStage st(c, "count_filter");
-    uint64_t capf = std::min<uint64_t>(slots, n_inst / (uint64_t)c->opt.min_kmer_count + 1);
-    DevBuf<unsigned long long> sk(capf, s), sc(capf, s);
-    BGX_CUDA(cudaMemsetAsync(counters.p, 0, 2 * sizeof(unsigned long long), s));
-    KLAUNCH(table_sweep_kernel)<<<(unsigned)((slots + kSweepPerBlock - 1) / kSweepPerBlock), 256, 0, s>>>(
-        c->table.p, slots, (uint32_t)c->opt.min_kmer_count, counters.p, sk.p, sc.p, capf);
-    BGX_CUDA(cudaMemcpyAsync(h_cnt, counters.p, sizeof(h_cnt), cudaMemcpyDeviceToHost, s));
-    BGX_CUDA(cudaStreamSynchronize(s));
-    c->n_distinct = h_cnt[0];
-    uint64_t n_solid_local = h_cnt[1];
-    BGX_CHECK(n_solid_local <= capf, "internal: solid k-mer bound violated");
+    if (batches == 1) {
+      c->table = std::move(outs[0].all);
+      solid_list = std::move(outs[0].solid);
+    } else {
+      // huge inputs do not keep the per-k-mer counts (bgx_export_kmers then refuses)
+      const bool keep_all = (double)total_all * 16.0 < 0.2 * (double)c->total_mem;
+      if (keep_all) c->table.alloc(std::max<uint64_t>(total_all, 1), s);
+      solid_list.alloc(std::max<uint64_t>(total_solid, 1), s);
+      uint64_t oa = 0, os = 0;
+      for (BatchOut& bo : outs) {
+        if (keep_all && bo.n_all)
+          BGX_CUDA(cudaMemcpyAsync(c->table.p + oa, bo.all.p, bo.n_all * sizeof(CountEntry), cudaMemcpyDeviceToDevice, s));
+        if (bo.n_solid) BGX_CUDA(cudaMemcpyAsync(solid_list.p + os, bo.solid.p, bo.n_solid * 8, cudaMemcpyDeviceToDevice, s));
+        oa += bo.n_all;
+        os += bo.n_solid;
+        bo.all.release();
+        bo.solid.release();
+      }
+      c->set_stat("kmer_counts_dropped", keep_all ? 0 : 1);
+    }
+    c->table_slots = c->table.p ? total_all : 0;
+    c->n_distinct = total_all;
+    uint64_t n_solid_local = total_solid;
     // multi-GPU: every rank needs the whole solid set for correction -> all-gather the owners' lists
-    const unsigned long long* all_keys = sk.p;
+    const unsigned long long* all_keys = solid_list.p;
     DevBuf<unsigned long long> gathered;
     c->n_solid = n_solid_local;
     if (N > 1) {
@@ -999,7 +1177,7 @@ void stage_count_kmers(Context* c) {
       uint64_t tot = 0;
       for (int r = 0; r < N; ++r) { offs[r] = tot; tot += cnts[r]; }
       gathered.alloc(std::max<uint64_t>(tot, 1), s);
-      dist_alltoallv(c, sk.p, zero.data(), mine_cnt.data(), gathered.p, offs.data(), cnts.data(), 8);
+      dist_alltoallv(c, solid_list.p, zero.data(), mine_cnt.data(), gathered.p, offs.data(), cnts.data(), 8);
       all_keys = gathered.p;
       c->n_solid = tot;
       c->set_stat("kmer_solid_owned", (double)n_solid_local);
@@ -1014,10 +1192,11 @@ void stage_count_kmers(Context* c) {
     c->solid.alloc(c->solid_slots, s);
     KLAUNCH(fill_u64_kernel)<<<(unsigned)((c->solid_slots + 255) / 256), 256, 0, s>>>(c->solid.p, c->solid_slots, kEmptyKey);
     if (c->n_solid)
-      KLAUNCH(solid_insert_kernel)<<<(unsigned)((c->n_solid + 255) / 256), 256, 0, s>>>(all_keys, c->n_solid, c->solid.p,
+      KLAUNCH(solid_insert_kernel)<<<(unsigned)((c->n_solid + 255) / 256), 256, 0, s>>>(all_keys, c->n_solid, k, c->solid.p,
                                                                              c->solid_slots / 4 - 1,
-                                                                             64 - log2_exact(c->solid_slots / 4));
+                                                                             2 * k - log2_exact(c->solid_slots / 4));
     BGX_CUDA(cudaGetLastError());
+    BGX_CUDA(cudaStreamSynchronize(s));  // the lists die with this scope
     st.stop();
   }
   c->counted = true;
@@ -1026,26 +1205,28 @@ void stage_count_kmers(Context* c) {
   c->set_stat("kmer_instances", (double)n_inst);
   c->set_stat("kmer_distinct", (double)c->n_distinct);
   c->set_stat("kmer_solid", (double)c->n_solid);
-  c->set_stat("count_table_slots", (double)slots);
-  c->set_stat("count_partitions", (double)P);
-  // partition pass: reads in, one 8-byte word per instance out; upsert pass: the words back in,
-  // the table touched twice (first touch + write-back), 16 B per slot
-  c->set_stat("alg_bytes_count_partition", (double)c->n_bases / 4 + 8.0 * (double)K);
-  c->set_stat("alg_bytes_count_kernel", 8.0 * (double)n_inst + 32.0 * (double)slots);
-  c->set_stat("alg_bytes_count", (double)c->n_bases / 4 + 8.0 * (double)K + 8.0 * (double)n_inst + 48.0 * (double)slots);
+  c->set_stat("count_partitions", (double)(1 << part_bits));
+  c->set_stat("count_sub_bins", (double)(1 << sub_bits_used));
+  // partition pass: reads in, one 8-byte word per instance out; split: the words in twice (histogram,
+  // scatter) and out once; bins: the words in once, every distinct k-mer out once (16 B) + the solid list
+  c->set_stat("alg_bytes_count_partition", alg_part);
+  c->set_stat("alg_bytes_count_split", alg_split);
+  c->set_stat("alg_bytes_count_kernel", alg_bins);
+  c->set_stat("alg_bytes_count", alg_part + alg_split + alg_bins);
 }
 
 void export_kmers(Context* c, uint32_t min_count, uint64_t* n_out, uint64_t** kmers, uint32_t** fwd, uint32_t** rev,
                   uint8_t** flags) {
   BGX_CHECK(c->counted && c->table.p,
-            "bgx_export_kmers: call bgx_count_kmers first (and before bgx_reset_results; on inputs whose k-mer tables "
-            "exceed a quarter of the device memory also before bgx_build_seqset, which releases them)");
+            "bgx_export_kmers: call bgx_count_kmers first (and before bgx_reset_results; on inputs whose k-mer lists "
+            "exceed a quarter of the device memory also before bgx_build_seqset, which releases them; inputs counted in "
+            "batches that would not fit do not keep per-k-mer counts at all)");
   cudaStream_t s = c->stream;
   uint64_t slots = c->table_slots;
   DevBuf<unsigned long long> counters(2, s);
   unsigned long long h_cnt[2];
   BGX_CUDA(cudaMemsetAsync(counters.p, 0, 2 * sizeof(unsigned long long), s));
-  const unsigned sweep_grid = (unsigned)((slots + kSweepPerBlock - 1) / kSweepPerBlock);
+  const unsigned sweep_grid = (unsigned)std::max<uint64_t>(1, (slots + kSweepPerBlock - 1) / kSweepPerBlock);
   KLAUNCH(table_sweep_kernel)<<<sweep_grid, 256, 0, s>>>(c->table.p, slots, min_count, counters.p, nullptr, nullptr, 0);
   BGX_CUDA(cudaMemcpyAsync(h_cnt, counters.p, sizeof(h_cnt), cudaMemcpyDeviceToHost, s));
   BGX_CUDA(cudaStreamSynchronize(s));

@@ -259,9 +259,10 @@ constexpr int RS_ITEMS = 16;
 constexpr int RS_TILE = RS_THREADS * RS_ITEMS;  // 4096 records
 constexpr int RADIX = 256;
 constexpr int RS_LOOKBACK = 4;           // predecessor tiles fetched per look-back round trip
-constexpr uint32_t ST_AGG = 1u << 30;    // tile aggregate available
-constexpr uint32_t ST_INCL = 1u << 31;   // inclusive prefix available
-constexpr uint32_t ST_VAL = (1u << 30) - 1;
+// tile status words are 64-bit (2 flag bits + count) so that a sort may hold up to 2^32 records
+constexpr uint64_t ST_AGG = 1ull << 62;    // tile aggregate available
+constexpr uint64_t ST_INCL = 1ull << 63;   // inclusive prefix available
+constexpr uint64_t ST_VAL = (1ull << 62) - 1;
 static_assert(RS_THREADS == RADIX, "one thread per digit");
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -293,13 +294,13 @@ __device__ __forceinline__ void tma_load_1d(void* dst, const void* src, uint32_t
                "l"(src), "r"(bytes), "r"(smem_u32(bar))
                : "memory");
 }
-__device__ __forceinline__ uint32_t ld_status(const uint32_t* p) {
-  uint32_t v;
-  asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+__device__ __forceinline__ uint64_t ld_status(const uint64_t* p) {
+  uint64_t v;
+  asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
   return v;
 }
-__device__ __forceinline__ void st_status(uint32_t* p, uint32_t v) {
-  asm volatile("st.relaxed.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+__device__ __forceinline__ void st_status(uint64_t* p, uint64_t v) {
+  asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
 }
 
 constexpr int RH_THREADS = 256;
@@ -350,7 +351,7 @@ struct OnesweepSmem {
 __global__ void __launch_bounds__(RS_THREADS, 3)
 onesweep_kernel(const uint64_t* __restrict__ keys_in, const uint64_t* __restrict__ vals_in,
                 uint64_t* __restrict__ keys_out, uint64_t* __restrict__ vals_out,
-                const uint32_t* __restrict__ digit_base /*[256] exclusive*/, uint32_t* __restrict__ status /*[ntiles][256]*/,
+                const uint32_t* __restrict__ digit_base /*[256] exclusive*/, uint64_t* __restrict__ status /*[ntiles][256]*/,
                 uint32_t* __restrict__ ticket, uint32_t n, int shift) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   OnesweepSmem& sm = *reinterpret_cast<OnesweepSmem*>(smem_raw);
@@ -432,9 +433,9 @@ onesweep_kernel(const uint64_t* __restrict__ keys_in, const uint64_t* __restrict
   }
   // pads were counted as digit 255: remove them from the published count
   const uint32_t real = (d_own == RADIX - 1) ? sum - (RS_TILE - nvalid) : sum;
-  uint32_t* const st_mine = status + (size_t)tile * RADIX + d_own;
-  st_status(st_mine, (tile == 0 ? ST_INCL : ST_AGG) | real);
-  uint32_t lb[RS_LOOKBACK];
+  uint64_t* const st_mine = status + (size_t)tile * RADIX + d_own;
+  st_status(st_mine, (tile == 0 ? ST_INCL : ST_AGG) | (uint64_t)real);
+  uint64_t lb[RS_LOOKBACK];
 #pragma unroll
   for (int q = 0; q < RS_LOOKBACK; ++q)
     lb[q] = tile > (uint32_t)q ? ld_status(status + (size_t)(tile - 1 - q) * RADIX + d_own) : ST_INCL;
@@ -471,10 +472,10 @@ onesweep_kernel(const uint64_t* __restrict__ keys_in, const uint64_t* __restrict
 #pragma unroll
         for (int q = 0; q < RS_LOOKBACK; ++q) {
           if (!done) {
-            uint32_t v = lb[q];
+            uint64_t v = lb[q];
             if (j - q >= 0) {
               while (v == 0) v = ld_status(status + (size_t)(j - q) * RADIX + d_own);
-              excl += v & ST_VAL;
+              excl += (uint32_t)(v & ST_VAL);
             }
             done = (v & ST_INCL) != 0;
           }
@@ -485,7 +486,7 @@ onesweep_kernel(const uint64_t* __restrict__ keys_in, const uint64_t* __restrict
         for (int q = 0; q < RS_LOOKBACK; ++q)
           lb[q] = j - q >= 0 ? ld_status(status + (size_t)(j - q) * RADIX + d_own) : ST_INCL;
       }
-      st_status(st_mine, ST_INCL | (excl + real));
+      st_status(st_mine, ST_INCL | (uint64_t)(excl + real));
     }
     sm.glob_base[d_own] = digit_base[d_own] + excl - ex;
   }
@@ -537,22 +538,21 @@ void exclusive_scan_u32(const uint32_t* in, uint32_t* out, size_t n, uint32_t* t
 
 bool radix_sort_pairs(uint64_t* keys, uint64_t* vals, uint64_t* keys_alt, uint64_t* vals_alt, size_t n,
                       int begin_bit, int end_bit, cudaStream_t s, int* passes_out) {
-  BGX_CHECK(n < (1ull << 30), "radix_sort_pairs: n must be < 2^30");
+  BGX_CHECK(n < kMaxSortRecords, "radix_sort_pairs: too many records for one sort");
   BGX_CHECK(begin_bit >= 0 && end_bit <= 64 && begin_bit <= end_bit, "radix_sort_pairs: bad bit range");
   const int passes = (end_bit - begin_bit + 7) / 8;
   if (passes_out) *passes_out = n ? passes : 0;
   if (n == 0 || passes == 0) return false;
   const uint32_t ntiles = (uint32_t)((n + RS_TILE - 1) / RS_TILE);
-  // one zeroed scratch block: [passes][256] histograms | [passes] tickets | [passes][ntiles][256] status
+  // zeroed scratch: [passes][256] histograms | [passes] tickets, and [passes][ntiles][256] 64-bit status words
   const size_t hist_words = (size_t)passes * RADIX, status_words = (size_t)ntiles * RADIX;
-  const size_t ticket_off = hist_words, status_off = (hist_words + passes + 63) & ~(size_t)63;
-  DevBuf<uint32_t> scratch(status_off + status_words * passes, s);
+  const size_t ticket_off = hist_words;
+  DevBuf<uint32_t> scratch(hist_words + passes, s);
+  DevBuf<uint64_t> status(status_words * passes, s);
   BGX_CUDA(cudaMemsetAsync(scratch.p, 0, scratch.n * sizeof(uint32_t), s));
-  static bool attr_set = false;
-  if (!attr_set) {
-    BGX_CUDA(cudaFuncSetAttribute(onesweep_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(OnesweepSmem)));
-    attr_set = true;
-  }
+  BGX_CUDA(cudaMemsetAsync(status.p, 0, status.n * sizeof(uint64_t), s));
+  // the opt-in is per device: set it on every call (cheap) rather than once per process
+  BGX_CUDA(cudaFuncSetAttribute(onesweep_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(OnesweepSmem)));
   const unsigned hist_grid = (unsigned)std::min<size_t>((n + RH_THREADS * RH_ITEMS - 1) / (RH_THREADS * RH_ITEMS), (size_t)kNumSMs * 8);
   KLAUNCH(radix_hist_kernel)<<<hist_grid, RH_THREADS, 0, s>>>(keys, (uint32_t)n, begin_bit, passes, scratch.p);
   KLAUNCH(radix_bases_kernel)<<<passes, RADIX, 0, s>>>(scratch.p);
@@ -563,7 +563,7 @@ bool radix_sort_pairs(uint64_t* keys, uint64_t* vals, uint64_t* keys_alt, uint64
     uint64_t* ko = in_alt ? keys : keys_alt;
     uint64_t* vo = in_alt ? vals : vals_alt;
     KLAUNCH(onesweep_kernel)<<<ntiles, RS_THREADS, sizeof(OnesweepSmem), s>>>(
-        ki, vi, ko, vo, scratch.p + (size_t)p * RADIX, scratch.p + status_off + status_words * p,
+        ki, vi, ko, vo, scratch.p + (size_t)p * RADIX, status.p + status_words * p,
         scratch.p + ticket_off + p, (uint32_t)n, begin_bit + 8 * p);
     in_alt = !in_alt;
   }

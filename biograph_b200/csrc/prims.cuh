@@ -54,9 +54,13 @@ void host_trim();
 // there (device pointer).
 void exclusive_scan_u32(const uint32_t* in, uint32_t* out, size_t n, uint32_t* total_out, cudaStream_t s);
 
+// most records one sort / one GPU shard may hold: indices are 32-bit everywhere, with headroom for
+// the tile rounding of the kernels
+constexpr uint64_t kMaxSortRecords = 0xFFF00000ull;
+
 // Stable LSD radix sort of n (key, value) pairs on key bits [begin_bit, end_bit), 8 bits per
 // pass.  Ping-pongs between (keys, vals) and (keys_alt, vals_alt); returns true if the sorted
-// data ended up in the *_alt buffers.  n < 2^32.
+// data ended up in the *_alt buffers.  n < kMaxSortRecords.
 // passes_out (optional) receives the number of passes run.
 bool radix_sort_pairs(uint64_t* keys, uint64_t* vals, uint64_t* keys_alt, uint64_t* vals_alt, size_t n,
                       int begin_bit, int end_bit, cudaStream_t s, int* passes_out = nullptr);

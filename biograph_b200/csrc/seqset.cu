@@ -28,6 +28,8 @@
 namespace bgx {
 namespace {
 
+// records one GPU shard may hold at any time (32-bit indices; the refinement keys keep 31 bits for a group id)
+constexpr uint64_t kMaxShardRecords = 1ull << 31;
 constexpr int kSmallGroup = 32;   // tie groups up to this size are sorted by one thread
 constexpr int kMediumGroup = 512; // ... up to this size by one warp (rank sort); larger ones are refined chunk by chunk
 constexpr int kChunkBases = 12;   // bases resolved per refinement round for big tie groups
@@ -1150,7 +1152,7 @@ void stage_build_seqset(Context* c) {
   cudaStream_t s = c->stream;
   ScopedStage st_all(c, "seqset_total");
   const uint32_t n_reads = (uint32_t)c->n_reads;
-  BGX_CHECK(c->n_seeds < (1ull << 30), "too many seed records for one GPU shard");
+  BGX_CHECK(c->n_seeds < kMaxShardRecords, "too many seed records for one GPU shard");
 
   // 1. seeds
   uint32_t n = (uint32_t)c->n_seeds;
@@ -1194,7 +1196,7 @@ void stage_build_seqset(Context* c) {
       exclusive_scan_u32(ccnt.p, coff.p, n_chains, tot.p, s);
       BGX_CUDA(cudaGetLastError());
       n_new = read_u32(tot.p, s);
-      BGX_CHECK((uint64_t)n1 + n_new < (1ull << 30), "too many records for one GPU shard");
+      BGX_CHECK((uint64_t)n1 + n_new < kMaxShardRecords, "too many records for one GPU shard");
       nkeys.alloc(std::max<uint32_t>(n_new, 1), s);
       nlocs.alloc(std::max<uint32_t>(n_new, 1), s);
       KLAUNCH(walk_emit_kernel)<<<grid_for((uint64_t)n_chains * 32, 128), 128, 0, s>>>(c->store.p, locs.p, chains.p, ccnt.p, coff.p,
@@ -1316,7 +1318,7 @@ Routed route_records(Context* c, const uint64_t* keys, const uint64_t* locs, uin
   dist_allgather_host_u64(c, send_cnt.data(), N, all.data());
   uint64_t m = 0;
   for (int src = 0; src < N; ++src) { recv_cnt[src] = all[(size_t)src * N + R]; recv_off[src] = m; m += recv_cnt[src]; }
-  BGX_CHECK(m < (1ull << 30), "too many records for one GPU shard");
+  BGX_CHECK(m < kMaxShardRecords, "too many records for one GPU shard");
   Routed out;
   out.n = (uint32_t)m;
   out.keys.alloc(m + 1024, s);  // slack: the sort / dedup ping-pong buffers are sized alike
@@ -1374,7 +1376,7 @@ void stage_build_seqset_dist(Context* c) {
   const int N = c->dist.nranks, R = c->dist.rank;
   ScopedStage st_all(c, "seqset_total");
   const uint32_t n_reads = (uint32_t)c->n_reads;
-  BGX_CHECK(c->n_seeds < (1ull << 30), "too many seed records for one GPU shard");
+  BGX_CHECK(c->n_seeds < kMaxShardRecords, "too many seed records for one GPU shard");
 
   // 0. replicate the corrected stores: comparisons past the 32-base key read the sequence, and a
   //    record may be compared on any rank (peer-memory reads are the planned alternative)
@@ -1517,7 +1519,7 @@ void stage_build_seqset_dist(Context* c) {
     st.stop();
   }
   c->set_stat("walk_new_records", n_new);
-  BGX_CHECK((uint64_t)n1 + n_new < (1ull << 30), "too many records for one GPU shard");
+  BGX_CHECK((uint64_t)n1 + n_new < kMaxShardRecords, "too many records for one GPU shard");
   uint32_t n2 = n1;
   {
     // every rank takes part in the exchanges below even with nothing new of its own
