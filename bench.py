@@ -1,8 +1,14 @@
 #!/usr/bin/env python
 """bench.py -- seqset construction throughput (input bases/sec to finished seqset) on B200.
 
-  python bench.py [--gpus N] [--steps K] [--warmup W] [--workload ecoli100x|chr20_30x|small]
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--workload chr20_30x|ecoli100x|small] [--no-verify]
   python bench.py --impl reference ...      # the restated CPU path (oracle) on the host cores
+
+The default workload is BASELINE.json configs[2], the largest single-GPU configuration (synthetic human
+chr20 at 30x); configs[1] (E. coli 100x) is --workload ecoli100x.  After the timed region the output
+of the whole workload is checked (--no-verify skips it): at N=1 against the CPU oracle run over the
+WHOLE workload (its time is the cpu_baseline), at N>1 against a 1-GPU build over the concatenated
+reads of all ranks; the JSON line carries the verdict and a sha256 per seqset member ("parity").
 
 A "step" is one pass of the hot path (k-mer count -> correct -> seqset tables) over the whole
 synthetic read set of the workload.
@@ -122,20 +128,94 @@ def measured_peak_gbs():
     return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
 
 
-def cpu_port_run(reads2d, threads, k=30):
-    """The restated CPU path (oracle port) on a read sample: count -> filter -> correct -> staged
-    seqset (seed + stride-7/255 + stride-1/6 rounds, as the reference).  Returns seconds."""
+def host_threads():
+    """all the host cores this process may use -- regardless of OMP_NUM_THREADS (torchrun sets it to 1)"""
+    try:
+        return max(1, len(os.sched_getaffinity(0)))
+    except Exception:
+        return max(1, os.cpu_count() or 1)
+
+
+def cpu_port_run(reads2d, threads, k=30, keep=False):
+    """The restated CPU path (oracle port) on a read set, the reference's way: two-stage k-mer counter
+    (probabilistic pass, then exact CAS table) -> filter -> recursive correction -> staged seqset (seed +
+    stride-7/255 + stride-1/6 rounds).  Returns (seconds, entries[, results])."""
     from oracle import oracle as O
     from biograph_b200 import synth
     buf, offs = synth.as_buffer(reads2d)
     rb = (buf.tobytes(), offs)
+    del buf
     t0 = time.perf_counter()
-    counts = O.count_kmers(rb, k, threads=threads)
+    counts = O.count_kmers(rb, k, threads=threads, prefilter_min=5)
     solid = O.solid_set(counts, 5)
+    del counts
     cr = O.correct_reads(rb, solid, k, 8, 2, 0.7, threads=threads)
     ss = O.seqset_staged((cr["seq"], cr["offs"]), cr["next_fwd"], cr["next_rev"], threads=threads)
     dt = time.perf_counter() - t0
+    if keep:
+        return dt, ss["n"], {"solid": solid, "corrected": cr, "seqset": ss}
     return dt, ss["n"]
+
+
+def sha(a):
+    import hashlib
+    a = np.ascontiguousarray(a)
+    return hashlib.sha256(a.view(np.uint8).reshape(-1).data if a.size else b"").hexdigest()[:16]
+
+
+def seqset_members(ss, lo=None, n=None, lay=None):
+    """(name, array) of every payload member of a seqset (or of the slice a rank of a sharded build
+    holds: entries [lo, lo + n), bit vectors and their bitcount index from the same 512-entry groups)"""
+    if lo is None:
+        out = [("sizes", ss["sizes"]), ("shared", ss["shared"]), ("fixed", ss["fixed"])]
+        for b in range(4):
+            out += [(f"prev_{'ACGT'[b]}/bits", ss["prev"][b]), (f"prev_{'ACGT'[b]}/subaccum", ss["subaccum"][b]),
+                    (f"prev_{'ACGT'[b]}/accum", ss["accum"][b])]
+        return out
+    w0, g0 = lo // 64, lo // 512
+    out = [("sizes", ss["sizes"][lo:lo + n]), ("shared", ss["shared"][lo:lo + n]), ("fixed", ss["fixed"])]
+    for b in range(4):
+        out += [(f"prev_{'ACGT'[b]}/bits", ss["prev"][b][w0:w0 + lay["prev_words"]]),
+                (f"prev_{'ACGT'[b]}/subaccum", ss["subaccum"][b][g0:g0 + lay["sub_words"]]),
+                (f"prev_{'ACGT'[b]}/accum", ss["accum"][b][g0:g0 + lay["acc_words"]])]
+    return out
+
+
+def verify_against_oracle(g, reads, threads):
+    """N=1: the oracle over the WHOLE workload, once; compares the solid k-mers (counts, flags), the
+    corrected reads (+ seed counts) and every seqset member.  Returns (parity dict, cpu seconds)."""
+    from oracle import oracle as O
+    dt, n_ent, ref = cpu_port_run(reads, threads, keep=True)
+    mism = []
+    gs = g.export_kmers(5)
+    for f in ("kmers", "fwd", "rev", "flags"):
+        if not np.array_equal(ref["solid"][f], gs[f]):
+            mism.append("solid_kmers/" + f)
+    digests = {"solid_kmers": sha(gs["kmers"]), "solid_counts": sha(np.stack([gs["fwd"], gs["rev"]]))}
+    del gs
+    cr, ocr = g.export_corrected(), ref["corrected"]
+    if ocr["seq"] != cr["seq"]:
+        mism.append("corrected/bases")
+    for f in ("offs", "kept", "next_fwd", "next_rev", "corrections"):
+        if not np.array_equal(ocr[f], cr[f]):
+            mism.append("corrected/" + f)
+    digests["corrected_bases"] = sha(np.frombuffer(cr["seq"], dtype=np.uint8))
+    del cr, ocr
+    ss, oss = g.export_seqset(), ref["seqset"]
+    if oss["n"] != ss["n"]:
+        mism.append("seqset/num_entries")
+    oss["subaccum"], oss["accum"] = [], []
+    for b in range(4):
+        sub, acc, _ = O.bitcount_finalize(oss["prev"][b], oss["n"])
+        oss["subaccum"].append(sub)
+        oss["accum"].append(acc)
+    for (name, a), (_, b_) in zip(seqset_members(ss), seqset_members(oss)):
+        digests["seqset/" + name] = sha(a)
+        if not np.array_equal(a, b_):
+            mism.append("seqset/" + name)
+    par = {"checked": True, "against": "oracle port, full workload", "members_equal": not mism, "mismatches": mism,
+           "entries": int(ss["n"]), "sha256_16": digests}
+    return par, dt
 
 
 def run_reference(args):
@@ -146,7 +226,7 @@ def run_reference(args):
         return
     from oracle import oracle as O
     O.build()
-    threads = O.max_threads()
+    threads = host_threads()
     w = WORKLOADS[args.workload]
     total = args.reads or -(-w["coverage"] * (4938920 if w["genome"] == "ecoli" else w["genome"][1]) // w["read_len"])
     # bounded sample: the workload's read model at the workload's coverage over a genome prefix
@@ -169,10 +249,66 @@ def run_reference(args):
                        "parallelism": f"{threads} host threads (CPU path; no GPU)"},
             "cpu_baseline": {"value": val, "unit": "bases/s", "cores": threads, "kind": "port",
                              "sample": f"{sample} reads at the workload's coverage over a genome prefix "
-                                       f"(workload has {total}), whole path (count+correct+staged seqset), "
+                                       f"(workload has {total}), whole path (2-stage count+correct+staged seqset), "
                                        "oracle port (reference binary not buildable offline)"},
             "e2e": {"value": val, "unit": "bases/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line))
+
+
+def verify_against_single_gpu(g, B, dist, rank, world, local, pinned, pinned_mask, pinned_lens, n_reads):
+    """N>1: the tables the sharded build left on the ranks against ONE single-GPU build (rank 0's GPU,
+    a fresh context without NCCL) over all ranks' reads concatenated in rank order.  Every rank hashes
+    the members of its slice; rank 0 hashes the same slices of the single-GPU tables."""
+    import torch
+    part = g.export_seqset()
+    lay = g.seqset_layout()
+    mine = {"first": int(part["first"]), "n": int(part["n"]), "lay": lay,
+            "sha": {name: sha(a) for name, a in seqset_members(part)}}
+    del part
+    g.clear_reads(); g.reset_results()
+    torch.cuda.empty_cache()
+    parts = [None] * world
+    dist.all_gather_object(parts, mine)
+    # all ranks' packed reads to rank 0 (equal sizes by construction of the weak-scaling workload)
+    have_mask = torch.tensor([0 if pinned_mask is None else 1], device="cuda")
+    dist.all_reduce(have_mask, op=dist.ReduceOp.MAX)
+    if have_mask.item():
+        return {"checked": False, "why": "reads with N: the gather below assumes no N mask"}
+    bufs = []
+    for t in (pinned, pinned_lens):
+        d = t.cuda(non_blocking=True)
+        lst = [torch.empty_like(d) for _ in range(world)] if rank == 0 else None
+        dist.gather(d, lst, dst=0)
+        if rank == 0:
+            bufs.append(torch.cat(lst).cpu().numpy())
+        del d, lst
+    torch.cuda.empty_cache()
+    res = None
+    if rank == 0:
+        try:
+            g1 = B.Bgx(device=local)
+            lens_all = bufs[1].view(np.uint16)
+            g1.add_reads_packed(bufs[0], None, None, lens_all)
+            g1.run()
+            ss = g1.export_seqset()
+            mism = []
+            total = sum(p_["n"] for p_ in parts)
+            if ss["n"] != total:
+                mism.append(f"num_entries {total} != {ss['n']}")
+            else:
+                for r_, p_ in enumerate(parts):
+                    for name, a in seqset_members(ss, p_["first"], p_["n"], p_["lay"]):
+                        if sha(a) != p_["sha"][name]:
+                            mism.append(f"rank{r_}/{name}")
+            res = {"checked": True, "against": f"1-GPU build over the {world * n_reads} concatenated reads (same library, no NCCL)",
+                   "members_equal": not mism, "mismatches": mism[:16], "entries": int(ss["n"]),
+                   "sha256_16": {name: sha(a) for name, a in seqset_members(ss)}}
+            g1.close()
+        except Exception as e:  # e.g. the concatenated input does not fit one GPU
+            res = {"checked": False, "why": f"1-GPU build of the concatenated reads failed: {e}"}
+    out = [res]
+    dist.broadcast_object_list(out, src=0)
+    return out[0]
 
 
 def main():
@@ -181,7 +317,8 @@ def main():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="bgx", choices=["bgx", "reference"])
-    ap.add_argument("--workload", default="ecoli100x", choices=sorted(WORKLOADS))
+    ap.add_argument("--workload", default="chr20_30x", choices=sorted(WORKLOADS))
+    ap.add_argument("--no-verify", action="store_true", help="skip the parity check of the whole workload")
     ap.add_argument("--reads", type=int, default=None, help="override the read count (debug)")
     ap.add_argument("--cpu-sample-reads", type=int, default=600000)
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -336,18 +473,30 @@ def main():
         except Exception:
             pass
 
-    # ---- CPU baseline on a bounded sample (rank 0, N=1 only) -------------------------------------------------------
+    # ---- parity of the whole workload + CPU baseline (outside the timed region) ---------------------------------
+    # The last end-to-end step left its results resident.  N=1: the oracle runs over the WHOLE workload
+    # once: it is the checker and, timed, the cpu_baseline (same config).  N>1: a 1-GPU build over the
+    # concatenated reads of all ranks must give the same tables as the sharded build just timed.
     cpu = None
-    if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        from oracle import oracle as O
-        threads = O.max_threads()
+    parity = {"checked": False, "why": "--no-verify"}
+    if world == 1 and not args.no_verify:
+        threads = host_threads()
+        parity, dt = verify_against_oracle(g, reads, threads)
+        cpu = {"value": n_reads * read_len / dt, "unit": "bases/s", "cores": threads, "kind": "port", "same_config": True,
+               "sample": f"the whole workload ({n_reads} reads) once, whole path (2-stage count + correct + staged "
+                         f"seqset), {dt:.1f} s; oracle port (reference binary not buildable offline); this run is "
+                         "also the parity check"}
+    elif world == 1 and not args.no_cpu_baseline:
+        threads = host_threads()
         sub = make_workload(args.workload, 0, None, genome_prefix_reads=min(n_reads, args.cpu_sample_reads))
         sample = sub.shape[0]
         dt, _ = cpu_port_run(sub, threads)
-        cpu = {"value": sample * read_len / dt, "unit": "bases/s", "cores": threads, "kind": "port",
+        cpu = {"value": sample * read_len / dt, "unit": "bases/s", "cores": threads, "kind": "port", "same_config": False,
                "sample": f"{sample} reads at the workload's coverage over a genome prefix (workload has {n_reads}), "
-                         f"whole path (count+correct+staged seqset) once, {dt:.1f} s; oracle port "
+                         f"whole path (2-stage count + correct + staged seqset) once, {dt:.1f} s; oracle port "
                          "(reference binary not buildable offline)"}
+    elif world > 1 and not args.no_verify:
+        parity = verify_against_single_gpu(g, B, dist, rank, world, local, pinned, pinned_mask, pinned_lens, n_reads)
 
     if rank == 0:
         line = {
@@ -365,6 +514,7 @@ def main():
             "gpu_launches": int(launches),
             "roofline": roof,
             "cpu_baseline": cpu,
+            "parity": parity,
             "clocks": clocks,
             "wall_s_timed_region": wall_s,
             "stage_ms": {k_: round(v, 3) for k_, v in sorted(kern_ms.items())},

@@ -246,7 +246,8 @@ class Bgx:
 
     def add_reads_packed(self, packed, nmask, word_offs, lens):
         self._ck(self.L.bgx_add_reads_packed(self.h, packed.ctypes.data, None if nmask is None else nmask.ctypes.data,
-                                             word_offs.ctypes.data, lens.ctypes.data, len(lens)))
+                                             None if word_offs is None else word_offs.ctypes.data, lens.ctypes.data,
+                                             len(lens)))
 
     def add_reads_packed_ptr(self, packed_ptr, nmask_ptr, word_offs_ptr, lens_ptr, n, overlap=False):
         """overlap=True: bgx_add_reads_packed_async (the buffers must outlive the next count_kmers / run)"""

@@ -98,27 +98,22 @@ __device__ __forceinline__ uint64_t mix64(uint64_t x) {
   return x;
 }
 
-// Bijective hash of a canonical k-mer on its own 2k-bit domain (the murmur3 finaliser restricted
-// to 2k bits: xor-shift by half the width is an involution there, the odd multipliers are
-// invertible mod 2^2k).  Because it is a bijection, a table that is indexed by the top bits of the
-// hash only has to remember the remaining bits, and the k-mer comes back with khash_inv().
-// The counting passes partition by successive top bits; the solid set's home bucket is the top
-// bits too.
+// Bijective hash of a canonical k-mer on its own 2k-bit domain: fold the high half onto the low
+// half (xor-shift by half the width is an involution on 2k bits), multiply by an odd constant mod
+// 2^2k (invertible), fold again.  Every input bit reaches the low half through the first fold and
+// from there all higher product bits, so the TOP bits -- the ones the counting passes partition by,
+// and the home bucket of the solid set -- are well mixed (measured on E. coli k-mers: bin sizes are
+// Poisson); the second fold mixes the low half.  Because it is a bijection, a table indexed by the
+// top bits only has to remember the remaining bits, and the k-mer comes back with khash_inv().
 __host__ __device__ __forceinline__ uint64_t khash(uint64_t x, int k) {
-  const uint64_t m = kmer_low_mask(k);
   x ^= x >> k;
-  x = (x * 0xff51afd7ed558ccdULL) & m;
-  x ^= x >> k;
-  x = (x * 0xc4ceb9fe1a85ec53ULL) & m;
+  x = (x * 0xff51afd7ed558ccdULL) & kmer_low_mask(k);
   x ^= x >> k;
   return x;
 }
 __host__ __device__ __forceinline__ uint64_t khash_inv(uint64_t x, int k) {
-  const uint64_t m = kmer_low_mask(k);
   x ^= x >> k;
-  x = (x * 0x9cb4b2f8129337dbULL) & m;  // inverse of 0xc4ceb9fe1a85ec53 mod 2^64
-  x ^= x >> k;
-  x = (x * 0x4f74430c22a54005ULL) & m;  // inverse of 0xff51afd7ed558ccd mod 2^64
+  x = (x * 0x4f74430c22a54005ULL) & kmer_low_mask(k);  // inverse of 0xff51afd7ed558ccd mod 2^64
   x ^= x >> k;
   return x;
 }

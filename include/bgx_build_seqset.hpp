@@ -16,14 +16,18 @@
 //   build_seqset::builder::build_chunks / make_seqset          builder -> bgx_build_seqset / bgx_export_*
 //     (bs/builder.h:9-15)
 //   seqset_for_reads (bio_base/seqset_testutil.h:13)           seqset_for_reads
-//   spiral_file_create_mmap + seqset ctor/finalize             seqset_file_writer (stored zip, members in the
+//   spiral_file_create_mmap + seqset ctor/finalize             seqset_file_writer (stored ZIP64, members in the
 //     (io/spiral_file_mmap.cpp, bio_base/seqset.cpp:19-44)       reference's order and byte layout)
 //
 // Errors: the reference throws io_exception; every failing C-ABI call is rethrown here as
 // bgx_bs::io_exception carrying bgx_last_error().
 #pragma once
 
+#include <fcntl.h>
+#include <unistd.h>
+
 #include <algorithm>
+#include <cerrno>
 #include <cstdint>
 #include <cstdio>
 #include <cstring>
@@ -322,47 +326,110 @@ struct seqset_tables {  // what seqset's members hold (modules/bio_base/seqset.c
   detail::host_array<uint64_t> prev_bits[4], prev_subaccum[4], prev_accum[4];
 };
 
-// Minimal "spiral file" writer: an uncompressed zip whose members are the reference's, in the
-// reference's creation order (modules/io/spiral_file.h:9-27, seqset.cpp:19-44).  file_info.json
-// carries a timestamp/uuid/command line in the reference, so whole-file identity is impossible
-// even between two reference runs; the parity contract is every other member byte for byte.
+// "Spiral file" writer: an uncompressed ZIP64 archive whose members are the reference's, in the
+// reference's creation order (modules/io/spiral_file.h:9-27, seqset.cpp:19-44), framed byte for byte
+// as spiral_file_create_mmap frames them through the vendored minizip
+// (modules/io/spiral_file_mmap.cpp:361-450: every member is opened with zip64 = 1, method 0):
+//   local header   : version needed 45, flag 0, method 0, dos date 0, crc, sizes, name, and a 20-byte
+//                    extra field 0x0001 / 16 / uncompressed / compressed (vendor/minizip/zip.c:1089-1150).
+//                    Sizes below 4 GiB are patched into the 32-bit fields and the extra field keeps its
+//                    zeros; from 4 GiB on the 32-bit fields stay 0xFFFFFFFF and the extra field holds
+//                    the sizes (zip.c:1857-1895).
+//   crc            : JSON members (create_path_contents, non-raw) carry their CRC-32; array members
+//                    (create_path, raw: the data is written through an mmap afterwards) carry 0
+//                    ("don't bother to fill crc", spiral_file_mmap.cpp:421-423) -- which is why generic
+//                    unzip tools report CRC errors on a .bg and readers go by offset.
+//   central header : version made by 0 / needed 20, raised to 45 / 45 for a member that needs ZIP64; a
+//                    0x0001 extra field with only the values that overflow 32 bits (zip.c:1753-1810)
+//   end            : ZIP64 end-of-central-directory record + locator only when the central directory
+//                    starts at or beyond 4 GiB (zip.c:1980-2030), then the classic end record.
+// file_info.json carries a timestamp/uuid/command line in the reference, so whole-file identity is
+// impossible even between two reference runs; the parity contract is every other member byte for byte.
 class seqset_file_writer {
  public:
-  explicit seqset_file_writer(const std::string& path) : m_f(fopen(path.c_str(), "wb")) {
-    if (!m_f) throw io_exception("cannot create " + path);
+  explicit seqset_file_writer(const std::string& path) : m_fd(::open(path.c_str(), O_CREAT | O_RDWR | O_TRUNC, 0666)) {
+    if (m_fd < 0) throw io_exception("Could not open zip for writing: " + path + ": " + strerror(errno));
   }
-  ~seqset_file_writer() { if (m_f) fclose(m_f); }
+  ~seqset_file_writer() { if (m_fd >= 0) ::close(m_fd); }
+  seqset_file_writer(const seqset_file_writer&) = delete;
+  seqset_file_writer& operator=(const seqset_file_writer&) = delete;
+
+  // spiral_file_create_state::create_membuf -> create_path: an array member (crc field 0)
   void add(const std::string& name, const void* data, uint64_t size) {
-    entry e;
-    e.name = name;
-    e.offset = (uint64_t)ftell(m_f);
-    e.size = size;
-    e.crc = crc32(data, size);
-    if (size >= 0xffffffffull || e.offset >= 0xffffffffull) throw io_exception("member too large for the plain zip writer");
-    put32(0x04034b50); put16(20); put16(0); put16(0); put16(0); put16(0);
-    put32(e.crc); put32((uint32_t)size); put32((uint32_t)size); put16((uint16_t)name.size()); put16(0);
-    fwrite(name.data(), 1, name.size(), m_f);
-    if (size) fwrite(data, 1, size, m_f);
-    m_entries.push_back(e);
+    const uint64_t off = begin_member(name, size, 0);
+    write_at(off, data, size);
   }
-  void add(const std::string& name, const std::string& text) { add(name, text.data(), text.size()); }
-  void finish() {
-    uint64_t cd = (uint64_t)ftell(m_f);
-    for (const entry& e : m_entries) {
-      put32(0x02014b50); put16(20); put16(20); put16(0); put16(0); put16(0); put16(0);
-      put32(e.crc); put32((uint32_t)e.size); put32((uint32_t)e.size); put16((uint16_t)e.name.size());
-      put16(0); put16(0); put16(0); put16(0); put32(0); put32((uint32_t)e.offset);
-      fwrite(e.name.data(), 1, e.name.size(), m_f);
+  // create_json -> create_path_contents: a JSON member (real CRC-32)
+  void add(const std::string& name, const std::string& text) {
+    const uint64_t off = begin_member(name, text.size(), crc32(text.data(), text.size()));
+    write_at(off, text.data(), text.size());
+  }
+  // create_path without contents: the member's bytes are zeros (a hole) until written with write_at;
+  // returns the offset of its data in the file
+  uint64_t reserve(const std::string& name, uint64_t size) { return begin_member(name, size, 0); }
+  void write_at(uint64_t offset, const void* data, uint64_t size) {
+    const char* p = static_cast<const char*>(data);
+    while (size) {
+      const ssize_t n = ::pwrite(m_fd, p, (size_t)std::min<uint64_t>(size, 1ull << 30), (off_t)offset);
+      if (n <= 0) throw io_exception(std::string("write to zip: ") + strerror(errno));
+      p += n; offset += (uint64_t)n; size -= (uint64_t)n;
     }
-    uint64_t end = (uint64_t)ftell(m_f);
-    put32(0x06054b50); put16(0); put16(0); put16((uint16_t)m_entries.size()); put16((uint16_t)m_entries.size());
-    put32((uint32_t)(end - cd)); put32((uint32_t)cd); put16(0);
-    fclose(m_f);
-    m_f = nullptr;
+  }
+  // zipClose_64; returns the size of the file
+  uint64_t finish() {
+    const uint64_t cd = m_end;
+    std::string dir;
+    for (const entry& e : m_entries) {
+      const bool big_size = e.size >= 0xffffffffull, big_off = e.offset >= 0xffffffffull;
+      const bool z64 = big_size || big_off;
+      std::string x;  // 0x0001 extra field: only what overflows
+      if (big_size) { put64(x, e.size); put64(x, e.size); }
+      if (big_off) put64(x, e.offset);
+      put32(dir, 0x02014b50); put16(dir, z64 ? 45 : 0); put16(dir, z64 ? 45 : 20); put16(dir, 0); put16(dir, 0); put32(dir, 0);
+      put32(dir, e.crc); put32(dir, big_size ? 0xffffffffu : (uint32_t)e.size); put32(dir, big_size ? 0xffffffffu : (uint32_t)e.size);
+      put16(dir, (uint16_t)e.name.size()); put16(dir, x.empty() ? 0 : (uint16_t)(x.size() + 4)); put16(dir, 0);
+      put16(dir, 0); put16(dir, 0); put32(dir, 0); put32(dir, big_off ? 0xffffffffu : (uint32_t)e.offset);
+      dir += e.name;
+      if (!x.empty()) { put16(dir, 1); put16(dir, (uint16_t)x.size()); dir += x; }
+    }
+    std::string tail;
+    const uint64_t n = m_entries.size();
+    if (cd >= 0xffffffffull) {
+      const uint64_t z64_pos = cd + dir.size();
+      put32(tail, 0x06064b50); put64(tail, 44); put16(tail, 0); put16(tail, 45); put32(tail, 0); put32(tail, 0);
+      put64(tail, n); put64(tail, n); put64(tail, dir.size()); put64(tail, cd);
+      put32(tail, 0x07064b50); put32(tail, 0); put64(tail, z64_pos); put32(tail, 1);
+    }
+    put32(tail, 0x06054b50); put16(tail, 0); put16(tail, 0);
+    put16(tail, n >= 0xffff ? 0xffff : (uint16_t)n); put16(tail, n >= 0xffff ? 0xffff : (uint16_t)n);
+    put32(tail, (uint32_t)dir.size()); put32(tail, cd >= 0xffffffffull ? 0xffffffffu : (uint32_t)cd); put16(tail, 0);
+    write_at(cd, dir.data(), dir.size());
+    write_at(cd + dir.size(), tail.data(), tail.size());
+    m_end = cd + dir.size() + tail.size();
+    ::close(m_fd);
+    m_fd = -1;
+    return m_end;
   }
 
  private:
-  struct entry { std::string name; uint64_t offset, size; uint32_t crc; };
+  struct entry { std::string name; uint64_t offset /* of the local header */, size; uint32_t crc; };
+  // local header (final, "patched" form) + room for `size` bytes; returns where the data goes
+  uint64_t begin_member(const std::string& name, uint64_t size, uint32_t crc) {
+    entry e{name, m_end, size, crc};
+    const bool big = size >= 0xffffffffull;
+    std::string h;
+    put32(h, 0x04034b50); put16(h, 45); put16(h, 0); put16(h, 0); put32(h, 0);
+    put32(h, crc); put32(h, big ? 0xffffffffu : (uint32_t)size); put32(h, big ? 0xffffffffu : (uint32_t)size);
+    put16(h, (uint16_t)name.size()); put16(h, 20);
+    h += name;
+    put16(h, 1); put16(h, 16); put64(h, big ? size : 0); put64(h, big ? size : 0);
+    write_at(m_end, h.data(), h.size());
+    const uint64_t data_off = m_end + h.size();
+    m_end = data_off + size;
+    if (::ftruncate(m_fd, (off_t)m_end) < 0) throw io_exception(std::string("ftruncate to extend zip: ") + strerror(errno));
+    m_entries.push_back(e);
+    return data_off;
+  }
   static uint32_t crc32(const void* data, uint64_t n) {
     static uint32_t table[256];
     static bool init = false;
@@ -379,9 +446,11 @@ class seqset_file_writer {
     for (uint64_t i = 0; i < n; ++i) c = table[(c ^ p[i]) & 0xff] ^ (c >> 8);
     return c ^ 0xffffffffu;
   }
-  void put16(uint16_t v) { fwrite(&v, 2, 1, m_f); }
-  void put32(uint32_t v) { fwrite(&v, 4, 1, m_f); }
-  FILE* m_f;
+  static void put16(std::string& o, uint16_t v) { o.append(reinterpret_cast<const char*>(&v), 2); }
+  static void put32(std::string& o, uint32_t v) { o.append(reinterpret_cast<const char*>(&v), 4); }
+  static void put64(std::string& o, uint64_t v) { o.append(reinterpret_cast<const char*>(&v), 8); }
+  int m_fd;
+  uint64_t m_end = 0;
   std::vector<entry> m_entries;
 };
 

@@ -19,6 +19,7 @@
 
 #include <algorithm>
 #include <atomic>
+#include <cmath>
 #include <cstdint>
 #include <cstdio>
 #include <cstdlib>
@@ -99,13 +100,41 @@ struct KmerSet {  // modules/bio_mapred/kmer_set.h: sorted canonical k-mers; ind
   const uint8_t* flags;  // bit0 fwd_starts_read, bit1 rev_starts_read
   int64_t n;
   int k;
-  // kmer_set::find_table_index (modules/bio_mapred/kmer_set.cpp:296-360): binary search.
+  // kmer_set's lookup table (modules/bio_mapred/kmer_set.cpp:401-481): lookup[p] = first index whose
+  // leading prefix_bits bits are >= p; optional (nullptr: plain binary search over the whole set)
+  const uint32_t* lookup = nullptr;
+  int prefix_bits = 0;
+  // kmer_set::find_table_index (modules/bio_mapred/kmer_set.cpp:296-360): prefix lookup, then binary
+  // search of the tails in that range.
   int64_t find(uint64_t canon) const {
-    const uint64_t* p = std::lower_bound(kmers, kmers + n, canon);
-    if (p == kmers + n || *p != canon) return -1;
+    const uint64_t *lo = kmers, *hi = kmers + n;
+    if (lookup) {
+      uint64_t pfx = canon >> (2 * k - prefix_bits);
+      lo = kmers + lookup[pfx];
+      hi = kmers + lookup[pfx + 1];
+    }
+    const uint64_t* p = std::lower_bound(lo, hi, canon);
+    if (p == hi || *p != canon) return -1;
     return p - kmers;
   }
 };
+
+// the lookup table of a sorted set (empty when the set is too small to bother)
+inline std::vector<uint32_t> build_kmer_lookup(const uint64_t* kmers, int64_t n, int k, int* prefix_bits) {
+  int pb = 0;
+  while (pb < 2 * k && pb < 26 && (1LL << pb) < n) ++pb;
+  *prefix_bits = pb;
+  std::vector<uint32_t> lk;
+  if (pb == 0 || n >= (1LL << 32)) { *prefix_bits = 0; return lk; }
+  lk.assign((size_t(1) << pb) + 1, 0);
+  const int sh = 2 * k - pb;
+  int64_t i = 0;
+  for (uint64_t p = 0; p <= (uint64_t(1) << pb); ++p) {
+    while (i < n && (kmers[i] >> sh) < p) ++i;
+    lk[p] = (uint32_t)i;
+  }
+  return lk;
+}
 
 struct FrcKmer { bool flipped; int64_t index; };
 
@@ -464,64 +493,165 @@ int orc_max_threads() {
 
 uint64_t orc_rev_comp(uint64_t kmer, int k) { return rev_comp_kmer(kmer, k); }
 
-// Exact canonical k-mer counts with flags.  Semantics: bs/kmer_counter.cpp:629-697
-// (exact_pass_processor::flush_part) + bs/kmer_count_table.h:54-103 (increment): per canonical
-// k-mer, fwd_count (+1 when the instance was not flipped), rev_count (+1 when flipped), and the
-// OR of fwd_starts_read / rev_starts_read where (first,last) are swapped for flipped instances.
-// Output: all distinct canonical k-mers ascending.  flags bit0 = fwd_starts_read, bit1 =
-// rev_starts_read.  Implementation: sort + run-length aggregate (result-equivalent to the
-// reference's two-stage hash counter, whose first stage is result-invisible).
+// Exact canonical k-mer counts with flags, the reference's way: every thread walks its share of the
+// reads and increments a shared open-addressing table with compare-and-swap
+// (kmer_count_table::increment, bs/kmer_count_table.h:54-103: claim the slot with CAS, OR the
+// starts-read flags -- swapped when the instance is flipped --, CAS-increment fwd_count or
+// rev_count; exact_pass_processor::flush_part, bs/kmer_counter.cpp:629-697).  The reference's uint8
+// counters + uint32 overflow table (:680-685) are one uint32 here (same value).  Its 256 hash
+// partitions and multiple exact passes only bound memory; one table does the same work.
+//   prefilter_min == 0: every distinct k-mer is counted (the parity oracle).
+//   prefilter_min  > 0: the reference's stage 1 first (prob_pass_processor::flush_part, :579-617):
+//                       2-bit saturating counters at canon * 11304120250909662091 mod size; stage 2
+//                       then only counts k-mers whose cell reached min(3, prefilter_min)
+//                       (:243-247, :296-302, :668).  Result-invisible for the solid set;
+//                       this is the form the CPU baseline times.
+// Output: the counted canonical k-mers ascending.  flags bit0 = fwd_starts_read, bit1 = rev_starts_read.
+namespace {
+struct CountSlot {
+  std::atomic<uint64_t> key;   // canonical k-mer | flags (bits 63/62); ~0 = unused
+  std::atomic<uint32_t> fwd, rev;
+};
+constexpr uint64_t kUnused = ~0ULL, kKmerBits = ~0ULL >> 2, kFwdBit = 1ULL << 63, kRevBit = 1ULL << 62;
+inline uint64_t table_hash(uint64_t kmer) { return kmer * 15674341118187572551ULL; }  // kmer_count_table::hash_kmer
+inline uint64_t pt_hash(uint64_t kmer) { return kmer * 11304120250909662091ULL; }      // bs/kmer_counter.cpp pt_hash_kmer
+}  // namespace
+
+int64_t orc_count_kmers2(const char* seq, const int64_t* offs, int64_t n, int k, int threads, int prefilter_min,
+                         uint64_t** out_kmers, uint32_t** out_fwd, uint32_t** out_rev, uint8_t** out_flags) {
+  set_threads(threads);
+  if (k < 1 || k > 31) return -1;
+  int64_t total = 0;
+  for (int64_t r = 0; r < n; ++r) { int64_t L = offs[r + 1] - offs[r]; if (L >= k) total += L - k + 1; }
+  // ---- stage 1 (optional): probabilistic 2-bit counters ------------------------------------------------
+  std::vector<std::atomic<uint8_t>> prob;
+  uint64_t prob_size = 0;
+  unsigned prob_need = 0;
+  if (prefilter_min > 0) {
+    prob_need = (unsigned)std::min(3, prefilter_min);
+    prob_size = std::max<uint64_t>(512 * 1024, (uint64_t)total);   // one cell per instance (reference: memory budget)
+    prob = std::vector<std::atomic<uint8_t>>(prob_size);
+    for (auto& c : prob) c.store(0, std::memory_order_relaxed);
+#pragma omp parallel for schedule(dynamic, 512)
+    for (int64_t r = 0; r < n; ++r) {
+      for_each_kmer(seq + offs[r], offs[r + 1] - offs[r], k, [&](uint64_t kmer, bool, bool) {
+        bool fl;
+        uint64_t canon = canonicalize(kmer, k, &fl);
+        std::atomic<uint8_t>& c = prob[pt_hash(canon) % prob_size];
+        uint8_t v = c.load(std::memory_order_relaxed);
+        while (v < 3 && !c.compare_exchange_weak(v, (uint8_t)(v + 1), std::memory_order_relaxed)) {}
+      });
+    }
+  }
+  auto passes = [&](uint64_t canon) {
+    return !prob_need || prob[pt_hash(canon) % prob_size].load(std::memory_order_relaxed) >= prob_need;
+  };
+  // ---- distinct estimate (linear counting over the 1/16 of hash space with 4 low zero bits) -------------
+  uint64_t est;
+  {
+    uint64_t bits = 1;
+    while (bits < (uint64_t)std::max<int64_t>(1 << 20, total / 8)) bits <<= 1;
+    std::vector<std::atomic<uint64_t>> bm(bits / 64);
+    for (auto& w : bm) w.store(0, std::memory_order_relaxed);
+#pragma omp parallel for schedule(dynamic, 512)
+    for (int64_t r = 0; r < n; ++r) {
+      for_each_kmer(seq + offs[r], offs[r + 1] - offs[r], k, [&](uint64_t kmer, bool, bool) {
+        bool fl;
+        uint64_t canon = canonicalize(kmer, k, &fl);
+        uint64_t h = table_hash(canon);
+        h ^= h >> 29;
+        if ((h & 15) == 0 && passes(canon)) {
+          uint64_t b = (h >> 4) & (bits - 1);
+          bm[b >> 6].fetch_or(1ULL << (b & 63), std::memory_order_relaxed);
+        }
+      });
+    }
+    uint64_t ones = 0;
+    for (auto& w : bm) ones += __builtin_popcountll(w.load(std::memory_order_relaxed));
+    double zf = std::max(1.0 / (double)bits, 1.0 - (double)ones / (double)bits);
+    est = (uint64_t)(16.0 * -(double)bits * std::log(zf));
+  }
+  uint64_t slots = 1024;
+  while (slots < est + est / 2 + 4096) slots <<= 1;
+  for (;;) {
+    std::vector<CountSlot> table(slots);
+#pragma omp parallel for schedule(static)
+    for (int64_t i = 0; i < (int64_t)slots; ++i) {
+      table[i].key.store(kUnused, std::memory_order_relaxed);
+      table[i].fwd.store(0, std::memory_order_relaxed);
+      table[i].rev.store(0, std::memory_order_relaxed);
+    }
+    std::atomic<bool> full{false};
+    const uint64_t mask = slots - 1;
+    int slot_shift = 64;
+    for (uint64_t t = slots; t > 1; t >>= 1) --slot_shift;   // top bits of the multiplicative hash
+#pragma omp parallel for schedule(dynamic, 512)
+    for (int64_t r = 0; r < n; ++r) {
+      if (full.load(std::memory_order_relaxed)) continue;
+      for_each_kmer(seq + offs[r], offs[r + 1] - offs[r], k, [&](uint64_t kmer, bool first, bool last) {
+        bool fl;
+        uint64_t canon = canonicalize(kmer, k, &fl);
+        if (!passes(canon)) return;
+        uint64_t pos = table_hash(canon) >> slot_shift;
+        uint64_t probes = 0;
+        for (;;) {
+          uint64_t cur = table[pos].key.load(std::memory_order_relaxed);
+          if (cur == kUnused) {
+            if (table[pos].key.compare_exchange_strong(cur, canon, std::memory_order_relaxed)) cur = canon;
+          }
+          if ((cur & kKmerBits) == canon) break;
+          pos = (pos + 1) & mask;
+          if (++probes > mask) { full.store(true); return; }   // "Kmer table (...) too small"
+        }
+        bool ff = first, rf = last;
+        if (fl) std::swap(ff, rf);
+        uint64_t nf = (ff ? kFwdBit : 0) | (rf ? kRevBit : 0);
+        if (nf) table[pos].key.fetch_or(nf, std::memory_order_relaxed);
+        std::atomic<uint32_t>& c = fl ? table[pos].rev : table[pos].fwd;
+        uint32_t v = c.load(std::memory_order_relaxed);
+        while (v != 0xFFFFFFFFu && !c.compare_exchange_weak(v, v + 1, std::memory_order_relaxed)) {}
+      });
+    }
+    if (full.load()) { slots <<= 1; continue; }
+    // ---- gather, order by k-mer (256 buckets on the leading 4 bases, sorted in parallel) -----------------
+    const int shift = 2 * k - 8;
+    std::vector<uint64_t> bucket_n(257, 0);
+    for (uint64_t i = 0; i < slots; ++i) {
+      uint64_t key = table[i].key.load(std::memory_order_relaxed);
+      if (key != kUnused) ++bucket_n[((key & kKmerBits) >> shift) + 1];
+    }
+    for (int b = 0; b < 256; ++b) bucket_n[b + 1] += bucket_n[b];
+    const uint64_t distinct = bucket_n[256];
+    std::vector<uint64_t> idx(distinct), cur(bucket_n.begin(), bucket_n.end() - 1);
+    for (uint64_t i = 0; i < slots; ++i) {
+      uint64_t key = table[i].key.load(std::memory_order_relaxed);
+      if (key != kUnused) idx[cur[(key & kKmerBits) >> shift]++] = i;
+    }
+#pragma omp parallel for schedule(dynamic, 1)
+    for (int b = 0; b < 256; ++b)
+      std::sort(idx.begin() + bucket_n[b], idx.begin() + bucket_n[b + 1], [&](uint64_t x, uint64_t y) {
+        return (table[x].key.load(std::memory_order_relaxed) & kKmerBits) < (table[y].key.load(std::memory_order_relaxed) & kKmerBits);
+      });
+    *out_kmers = (uint64_t*)malloc(std::max<size_t>(1, distinct) * 8);
+    *out_fwd = (uint32_t*)malloc(std::max<size_t>(1, distinct) * 4);
+    *out_rev = (uint32_t*)malloc(std::max<size_t>(1, distinct) * 4);
+    *out_flags = (uint8_t*)malloc(std::max<size_t>(1, distinct));
+#pragma omp parallel for schedule(static)
+    for (int64_t w = 0; w < (int64_t)distinct; ++w) {
+      const CountSlot& e = table[idx[w]];
+      uint64_t key = e.key.load(std::memory_order_relaxed);
+      (*out_kmers)[w] = key & kKmerBits;
+      (*out_fwd)[w] = e.fwd.load(std::memory_order_relaxed);
+      (*out_rev)[w] = e.rev.load(std::memory_order_relaxed);
+      (*out_flags)[w] = (uint8_t)(((key & kFwdBit) ? 1 : 0) | ((key & kRevBit) ? 2 : 0));
+    }
+    return (int64_t)distinct;
+  }
+}
+
 int64_t orc_count_kmers(const char* seq, const int64_t* offs, int64_t n, int k, int threads,
                         uint64_t** out_kmers, uint32_t** out_fwd, uint32_t** out_rev, uint8_t** out_flags) {
-  set_threads(threads);
-  // instance word: canon<<3 | flipped<<2 | rev_flag<<1 | fwd_flag   (k<=30 -> 60+3 bits; for k=31 use 2 arrays)
-  if (k < 1 || k > 31) return -1;
-  std::vector<uint64_t> inst;
-  std::vector<uint8_t> aux;
-  {
-    int64_t total = 0;
-    for (int64_t r = 0; r < n; ++r) { int64_t L = offs[r + 1] - offs[r]; if (L >= k) total += L - k + 1; }
-    inst.reserve(total);
-    aux.reserve(total);
-  }
-  for (int64_t r = 0; r < n; ++r) {
-    for_each_kmer(seq + offs[r], offs[r + 1] - offs[r], k, [&](uint64_t kmer, bool first, bool last) {
-      bool fl;
-      uint64_t canon = canonicalize(kmer, k, &fl);
-      bool ff = first, rf = last;
-      if (fl) std::swap(ff, rf);
-      inst.push_back(canon);
-      aux.push_back((uint8_t)((fl ? 4 : 0) | (rf ? 2 : 0) | (ff ? 1 : 0)));
-    });
-  }
-  size_t m = inst.size();
-  // sort (canon, aux) pairs: pack aux into a parallel permutation-free sort by combining when possible
-  std::vector<std::pair<uint64_t, uint8_t>> pairs(m);
-  for (size_t i = 0; i < m; ++i) pairs[i] = {inst[i], aux[i]};
-  inst.clear(); inst.shrink_to_fit(); aux.clear(); aux.shrink_to_fit();
-  std::sort(pairs.begin(), pairs.end(), [](const auto& a, const auto& b) { return a.first < b.first; });
-  size_t distinct = 0;
-  for (size_t i = 0; i < m; ++i) if (i == 0 || pairs[i].first != pairs[i - 1].first) ++distinct;
-  *out_kmers = (uint64_t*)malloc(std::max<size_t>(1, distinct) * 8);
-  *out_fwd = (uint32_t*)malloc(std::max<size_t>(1, distinct) * 4);
-  *out_rev = (uint32_t*)malloc(std::max<size_t>(1, distinct) * 4);
-  *out_flags = (uint8_t*)malloc(std::max<size_t>(1, distinct));
-  size_t w = 0;
-  for (size_t i = 0; i < m;) {
-    size_t j = i;
-    uint64_t f = 0, r = 0; uint8_t fl = 0;
-    while (j < m && pairs[j].first == pairs[i].first) {
-      if (pairs[j].second & 4) ++r; else ++f;
-      fl |= pairs[j].second & 3;
-      ++j;
-    }
-    (*out_kmers)[w] = pairs[i].first;
-    (*out_fwd)[w] = (uint32_t)std::min<uint64_t>(f, 0xFFFFFFFFu);
-    (*out_rev)[w] = (uint32_t)std::min<uint64_t>(r, 0xFFFFFFFFu);
-    (*out_flags)[w] = fl;
-    ++w; i = j;
-  }
-  return (int64_t)distinct;
+  return orc_count_kmers2(seq, offs, n, k, threads, 0, out_kmers, out_fwd, out_rev, out_flags);
 }
 
 // Single-read correction (parity hook for modules/bio_base/fast_read_correct_test.cpp).
@@ -549,6 +679,9 @@ int64_t orc_correct_reads(const char* seq, const int64_t* offs, int64_t n, const
                           int32_t* next_rev) {
   set_threads(threads);
   KmerSet ks{solid, flags, n_solid, k};
+  int pb = 0;
+  std::vector<uint32_t> lookup = build_kmer_lookup(solid, n_solid, k, &pb);
+  if (!lookup.empty()) { ks.lookup = lookup.data(); ks.prefix_bits = pb; }
   FrcParams p{(unsigned)max_corrections, (unsigned)min_good_run, k, &ks};
   const double portion = (double)trim_after_portion;
   std::vector<int32_t> out_len(n, 0);

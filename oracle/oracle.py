@@ -33,6 +33,9 @@ def lib():
         L.orc_count_kmers.restype = C.c_int64
         L.orc_count_kmers.argtypes = [C.c_char_p, C.c_void_p, C.c_int64, C.c_int, C.c_int,
                                       p(C.c_void_p), p(C.c_void_p), p(C.c_void_p), p(C.c_void_p)]
+        L.orc_count_kmers2.restype = C.c_int64
+        L.orc_count_kmers2.argtypes = [C.c_char_p, C.c_void_p, C.c_int64, C.c_int, C.c_int, C.c_int,
+                                       p(C.c_void_p), p(C.c_void_p), p(C.c_void_p), p(C.c_void_p)]
         L.orc_fast_read_correct.restype = C.c_int
         L.orc_fast_read_correct.argtypes = [C.c_char_p, C.c_int, C.c_void_p, C.c_int64, C.c_int, C.c_int,
                                             C.c_int, C.c_char_p, p(C.c_int)]
@@ -79,13 +82,14 @@ def _take(ptr, n, dtype):
     return arr
 
 
-def count_kmers(reads, k, threads=0):
-    """All distinct canonical k-mers, ascending, with exact fwd/rev counts and flag bits
-    (bit0 fwd_starts_read, bit1 rev_starts_read)."""
+def count_kmers(reads, k, threads=0, prefilter_min=0):
+    """The distinct canonical k-mers, ascending, with exact fwd/rev counts and flag bits
+    (bit0 fwd_starts_read, bit1 rev_starts_read).  prefilter_min > 0: the reference's two-stage form
+    (probabilistic 2-bit pass first; only k-mers that pass it are counted exactly) -- same solid set."""
     buf, offs = reads if isinstance(reads, tuple) else pack_reads(reads)
     pk, pf, pr, pfl = C.c_void_p(), C.c_void_p(), C.c_void_p(), C.c_void_p()
-    n = lib().orc_count_kmers(buf, offs.ctypes.data, len(offs) - 1, k, threads, C.byref(pk), C.byref(pf),
-                              C.byref(pr), C.byref(pfl))
+    n = lib().orc_count_kmers2(buf, offs.ctypes.data, len(offs) - 1, k, threads, prefilter_min, C.byref(pk),
+                               C.byref(pf), C.byref(pr), C.byref(pfl))
     if n < 0:
         raise ValueError("orc_count_kmers failed")
     return {"kmers": _take(pk, n, np.uint64), "fwd": _take(pf, n, np.uint32), "rev": _take(pr, n, np.uint32),

@@ -12,7 +12,7 @@ BASE = ["metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "
 
 def test_reference_arm_line():
     out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "0",
-                          "--cpu-sample-reads", "3000"], capture_output=True, text=True, timeout=600, cwd=ROOT)
+                          "--workload", "ecoli100x", "--cpu-sample-reads", "3000"], capture_output=True, text=True, timeout=600, cwd=ROOT)
     assert out.returncode == 0, out.stderr[-2000:]
     line = json.loads([l for l in out.stdout.splitlines() if l.startswith("{")][-1])
     for k in BASE:
@@ -22,7 +22,20 @@ def test_reference_arm_line():
     assert line["config"]["workload"] == "ecoli100x"
     assert line["e2e"] == {"value": line["value"], "unit": "bases/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
     cb = line["cpu_baseline"]
-    assert cb["kind"] == "port" and cb["cores"] >= 1 and cb["value"] == line["value"] and "sample" in cb
+    assert cb["kind"] == "port" and cb["value"] == line["value"] and "sample" in cb
+    # all the host cores, whatever OMP_NUM_THREADS says (torchrun exports OMP_NUM_THREADS=1)
+    assert cb["cores"] == len(os.sched_getaffinity(0))
+
+
+def test_reference_arm_ignores_omp_num_threads():
+    env = dict(os.environ, OMP_NUM_THREADS="1")
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "0",
+                          "--workload", "small", "--cpu-sample-reads", "2000"], capture_output=True, text=True, timeout=600,
+                         cwd=ROOT, env=env)
+    assert out.returncode == 0, out.stderr[-2000:]
+    line = json.loads([l for l in out.stdout.splitlines() if l.startswith("{")][-1])
+    assert line["cpu_baseline"]["cores"] == len(os.sched_getaffinity(0))
+    assert line["config"]["workload"] == "small"
 
 
 def test_committed_gpu_line_has_every_contract_key():

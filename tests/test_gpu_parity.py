@@ -209,26 +209,54 @@ def test_sort_key_bits_do_not_change_result(B, bits):
     full_compare(B, reads, sort_key_bits=bits)
 
 
-@pytest.mark.parametrize("batch", [1, 700, 2500, 100000])
+@pytest.mark.parametrize("batch", [40, 700, 2500, 100000])
 def test_batched_counting_does_not_change_result(B, batch):
-    """count_batch_reads bounds the k-mer instance buffers (inputs whose instances do not fit HBM next
-    to the table): the table is sized from a sampled estimate over the reads, then every batch is
-    partitioned and upserted in turn.  Counts, flags and everything downstream must be unchanged."""
+    """count_batch_reads bounds the k-mer instance buffers (inputs whose instance words do not fit
+    HBM): the counting runs in a power-of-two number of HASH-RANGE batches, at least reads / that;
+    every batch is partitioned, split and counted in turn.  Counts, flags and everything downstream
+    must be unchanged."""
     reads = _sim(10000, 5000, 150, 0.01, 91, n_rate=0.001)
     ss, st = full_compare(B, reads, count_batch_reads=batch)
-    assert st["count_batches"] == max(1, -(-5000 // batch))
+    want = max(1, -(-5000 // batch))
+    assert st["count_batches"] == 1 << (want - 1).bit_length()
 
 
 def test_batched_counting_with_heavy_hitter(B):
-    """a homopolymer run overfills its hash partition in every batch: the exact-offset re-run of pass 1"""
+    """a homopolymer run (363 000 instances of one k-mer) overfills its hash partition in the batch that
+    owns its hash: the exact-offset re-run of pass 1, and one sub-bin far longer than the others"""
     buf, offs = _sim(4000, 2000, 150, 0.005, 92)
     sim = [buf[offs[i]:offs[i + 1]].decode() for i in range(len(offs) - 1)]
     reads = []
-    for i in range(5):  # every batch of 1000 reads gets 600 copies of the homopolymer
+    for i in range(5):
         reads += ["A" * 150] * 600 + sim[400 * i:400 * (i + 1)]
     ss, st = full_compare(B, reads, count_batch_reads=1000)
-    assert st["count_batches"] == 5
+    assert st["count_batches"] == 8
     assert st.get("count_partition_reruns", 0) >= 1
+
+
+def test_overfull_count_bins_are_split_finer(B):
+    """a sub-bin with more distinct k-mers than its shared-memory table has slots: the split and
+    count passes are re-run with finer sub-bins (then larger tables) until every bin fits"""
+    reads = _sim(20000, 6000, 150, 0.01, 93)
+    os.environ["BGX_BIN_SLOTS_LOG2"] = "8"
+    os.environ["BGX_SUB_BITS"] = "0"
+    try:
+        ss, st = full_compare(B, reads)
+        assert st.get("count_bin_reruns", 0) >= 1
+    finally:
+        del os.environ["BGX_BIN_SLOTS_LOG2"], os.environ["BGX_SUB_BITS"]
+
+
+def test_k31_read_of_all_t(B):
+    """k = 31: a 31-base read of T is one k-mer that is both first and last of its read and has every
+    k-mer bit set (no value of the instance word may serve as a 'no item' sentinel)"""
+    reads = ["T" * 31] * 7 + ["A" * 31] * 3 + ["ACGT" * 10][:1] + ["T" * 40] * 2
+    g, km, cr, ss, st = run_gpu(B, reads, kmer_size=31, min_kmer_count=5)
+    oc = O.count_kmers(reads, 31)
+    for f in ("kmers", "fwd", "rev", "flags"):
+        assert np.array_equal(oc[f], km[f]), f
+    assert int(km["fwd"].sum() + km["rev"].sum()) == 7 + 3 + 10 + 2 * 10
+    g.close()
 
 
 def test_packed_input_equals_ascii_input(B):
