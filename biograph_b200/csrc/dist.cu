@@ -87,7 +87,36 @@ void dist_init(Context* c, int nranks, int rank, const uint8_t id[128]) {
   c->dist.comm = comm;
 }
 
+void dist_map_peers(Context* c, void* local, void** peer) {
+  const int N = c->dist.nranks, R = c->dist.rank;
+  peer[R] = local;
+  if (N == 1) return;
+  static_assert(sizeof(cudaIpcMemHandle_t) == 64, "cudaIpcMemHandle_t is 64 bytes");
+  cudaIpcMemHandle_t h;
+  BGX_CUDA(cudaIpcGetMemHandle(&h, local));
+  uint64_t mine[8];
+  memcpy(mine, &h, 64);
+  std::vector<uint64_t> all((size_t)N * 8);
+  dist_allgather_host_u64(c, mine, 8, all.data());
+  for (int r = 0; r < N; ++r) {
+    if (r == R) continue;
+    std::string key(reinterpret_cast<const char*>(&all[(size_t)r * 8]), 64);
+    key.push_back((char)r);
+    auto it = c->dist.ipc_cache.find(key);
+    if (it == c->dist.ipc_cache.end()) {
+      cudaIpcMemHandle_t hr;
+      memcpy(&hr, &all[(size_t)r * 8], 64);
+      void* p = nullptr;
+      BGX_CUDA(cudaIpcOpenMemHandle(&p, hr, cudaIpcMemLazyEnablePeerAccess));
+      it = c->dist.ipc_cache.emplace(key, p).first;
+    }
+    peer[r] = it->second;
+  }
+}
+
 void dist_destroy(Context* c) {
+  for (auto& kv : c->dist.ipc_cache) cudaIpcCloseMemHandle(kv.second);
+  c->dist.ipc_cache.clear();
   if (c->dist.comm) {
     nccl().CommDestroy(comm_of(c));
     c->dist.comm = nullptr;

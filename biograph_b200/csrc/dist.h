@@ -9,6 +9,8 @@
 
 #include <cstddef>
 #include <cstdint>
+#include <map>
+#include <string>
 #include <vector>
 
 #include <cuda_runtime.h>
@@ -21,6 +23,8 @@ struct Dist {
   int nranks = 1;
   int rank = 0;
   void* comm = nullptr;  // ncclComm_t
+  // peers' device blocks mapped into this process (cudaIpcOpenMemHandle), keyed by the 64-byte handle
+  std::map<std::string, void*> ipc_cache;
 };
 
 // rank 0: a fresh NCCL unique id (128 bytes) to hand to every rank out of band
@@ -45,6 +49,14 @@ struct P2P {
   int peer = 0;
 };
 void dist_p2p_batch(Context* c, const std::vector<P2P>& sends, const std::vector<P2P>& recvs);
+
+// ---- peer memory (one node: NVLink / NVSwitch) ------------------------------------------------------------
+// Collective.  Every rank passes one whole block of the device arena; on return peer[r] is rank r's
+// block as THIS process can address it (peer[rank] = local).  A kernel may then store straight into
+// the other GPUs' memory over NVLink -- the k-mer exchange is done by the partition pass itself.
+// Mappings are cached per handle (the arena hands out the same blocks run after run).  Doubles as a
+// barrier: when it returns, every rank has passed the point of the call on its stream.
+void dist_map_peers(Context* c, void* local, void** peer);
 
 // ---- small host-side metadata (counts, boundaries): staged through the device, synchronous -------------
 // out[r * n .. (r+1) * n) = rank r's in[0..n)

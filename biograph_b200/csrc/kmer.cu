@@ -30,6 +30,7 @@
 #include <cmath>
 #include <numeric>
 #include <cstdlib>
+#include <string>
 #include <vector>
 
 #include "ctx.h"
@@ -61,8 +62,11 @@ constexpr int kPartWarps = kPartThreads / 32;
 //     order, one global cursor bump per (block, partition), coalesced per-partition runs out
 //   * fused distinct-k-mer estimate: linear counting over the 2^-samp_shift of hash space whose low
 //     hash bits are zero (sampling by hash value is unbiased for distinct counts)
-// Partition p owns out[part_base[p] .. part_base[p] + cap).  cursors[] keep counting past cap, so
-// after an overflowing run they are the exact histogram for the exact re-run.
+// Partition p owns the cap words at the device address part_addr[p] -- in this GPU's memory or,
+// multi-GPU, in the memory of the GPU that owns the partition (mapped with CUDA IPC): the runs then
+// leave over NVLink as they are produced, and the k-mer exchange IS this kernel (no send buffer, no
+// separate all-to-all).  cursors[] keep counting past cap, so after an overflowing run they are the
+// exact histogram for the exact re-run.
 struct PartGeom {
   int k;
   int batch_bits;   // the batch keeps the k-mers whose top batch_bits hash bits == batch
@@ -75,9 +79,8 @@ __global__ void __launch_bounds__(kPartThreads, (MAXIT <= 4 ? 4 : 2))
 kmer_partition_kernel(const uint64_t* __restrict__ words, const uint32_t* __restrict__ nmask,
                       const uint32_t* __restrict__ word_off, const uint16_t* __restrict__ lens, uint32_t n_reads,
                       PartGeom G, unsigned long long* __restrict__ cursors,
-                      const unsigned long long* __restrict__ part_base, unsigned long long cap,
-                      unsigned long long* __restrict__ out, unsigned int* __restrict__ bitmap, uint64_t bit_mask,
-                      int samp_shift, int* __restrict__ overflow) {
+                      const unsigned long long* __restrict__ part_addr, unsigned long long cap,
+                      unsigned int* __restrict__ bitmap, uint64_t bit_mask, int samp_shift, int* __restrict__ overflow) {
   constexpr int kTileReads = kPartWarps * RPW;
   constexpr int kTileKmers = kTileReads * MAXIT * 32;
   constexpr int kWordsPerRead = MAXIT + 1;          // MAXIT*32 k-mers of k<=31 bases span <= MAXIT+1 words
@@ -88,8 +91,8 @@ kmer_partition_kernel(const uint64_t* __restrict__ words, const uint32_t* __rest
   uint16_t* stage_bin = reinterpret_cast<uint16_t*>(rmask + kTileReads * kWordsPerRead + 2);  // kTileKmers
   const int k = G.k, part_bits = G.part_bits;
   const int P = 1 << part_bits;
-  unsigned long long* gdst = reinterpret_cast<unsigned long long*>(stage_bin + kTileKmers);   // P
-  uint32_t* hist = reinterpret_cast<uint32_t*>(gdst + P);                                     // P
+  unsigned long long* gdst = reinterpret_cast<unsigned long long*>(stage_bin + kTileKmers);   // P: address of staged element 0
+  uint32_t* hist = reinterpret_cast<uint32_t*>(gdst + P);                                     // P; later: staged index limit
   uint32_t* bin_start = hist + P;                                                             // P
   __shared__ uint32_t tile_word0, tile_nwords;
 
@@ -194,7 +197,10 @@ kmer_partition_kernel(const uint64_t* __restrict__ words, const uint32_t* __rest
           if (loc[j]) {
             const unsigned long long g = atomicAdd(&cursors[d], (unsigned long long)loc[j]);
             if (g + loc[j] > cap) *overflow = 1;
-            gdst[d] = g;
+            // staged element i of this partition (ex <= i < ex + loc) goes to part_addr + 8 * (g + i - ex);
+            // the ones past the partition's cap are dropped (the exact re-run places them)
+            gdst[d] = part_addr[d] + 8ull * (g - ex);
+            hist[d] = g >= cap ? 0u : ex + (uint32_t)min((unsigned long long)loc[j], cap - g);
           }
           ex += loc[j];
         }
@@ -214,8 +220,7 @@ kmer_partition_kernel(const uint64_t* __restrict__ words, const uint32_t* __rest
     const uint32_t n_staged = tile_nwords;
     for (uint32_t j = tid; j < n_staged; j += kPartThreads) {
       const uint32_t bin = stage_bin[j];
-      const unsigned long long o = gdst[bin] + (j - bin_start[bin]);
-      if (o < cap) out[part_base[bin] + o] = stage[j];
+      if (j < hist[bin]) *reinterpret_cast<unsigned long long*>(gdst[bin] + 8ull * j) = stage[j];
     }
     __syncthreads();
   }
@@ -366,7 +371,10 @@ __global__ void __launch_bounds__(kSplitThreads, 2) kmer_split_kernel(const unsi
       const int d = (int)tid * per + j;
       if (j < per && d < S) {
         bin_start[d] = ex;
-        if (loc[j]) gdst[d] = bin_off[gb + d] + atomicAdd(&cursors[gb + d], (unsigned long long)loc[j]);
+        // staged element i of this sub-bin goes to out + (bin_off + cursor + i - ex)
+        if (loc[j])
+          gdst[d] = (unsigned long long)(uintptr_t)out +
+                    8ull * (bin_off[gb + d] + atomicAdd(&cursors[gb + d], (unsigned long long)loc[j]) - ex);
         ex += loc[j];
       }
     }
@@ -385,10 +393,8 @@ __global__ void __launch_bounds__(kSplitThreads, 2) kmer_split_kernel(const unsi
   }
   __syncthreads();
   const uint32_t n_staged = n_tile_s;
-  for (uint32_t j = tid; j < n_staged; j += kSplitThreads) {
-    const uint32_t bin = stage_bin[j];
-    out[gdst[bin] + (j - bin_start[bin])] = stage[j];
-  }
+  for (uint32_t j = tid; j < n_staged; j += kSplitThreads)
+    *reinterpret_cast<unsigned long long*>(gdst[stage_bin[j]] + 8ull * j) = stage[j];
 }
 
 // ---- pass 3: count one sub-bin per block in a shared-memory hash table ----------------------------------
@@ -399,7 +405,6 @@ __global__ void __launch_bounds__(kSplitThreads, 2) kmer_split_kernel(const unsi
 // slot is written once: {canonical k-mer | flags, rev << 32 | fwd} to the distinct list, and the
 // k-mer | flags again to the solid list if fwd + rev >= min_count (kmer_passes,
 // modules/bio_mapred/kmerize_bf.cpp:290-318).
-constexpr int kBinThreads = 256;
 constexpr int kBinItems = 4;
 struct BinGeom {
   int k;
@@ -410,49 +415,57 @@ struct BinGeom {
   uint32_t min_count;
 };
 
-__global__ void __launch_bounds__(kBinThreads) kmer_count_bins_kernel(const unsigned long long* __restrict__ words,
-                                                                      const unsigned long long* __restrict__ bin_off,
-                                                                      const unsigned long long* __restrict__ bin_cnt,
-                                                                      BinGeom G, CountEntry* __restrict__ out_all,
-                                                                      unsigned long long cap_all,
-                                                                      unsigned long long* __restrict__ out_solid,
-                                                                      unsigned long long cap_solid,
-                                                                      unsigned long long* __restrict__ counters /*[0] distinct [1] solid*/,
-                                                                      int* __restrict__ overflow) {
+template <int THREADS>
+__global__ void __launch_bounds__(THREADS) kmer_count_bins_kernel(const unsigned long long* __restrict__ words,
+                                                                  const unsigned long long* __restrict__ bin_off,
+                                                                  const unsigned long long* __restrict__ bin_cnt,
+                                                                  BinGeom G, CountEntry* __restrict__ out_all,
+                                                                  unsigned long long cap_all,
+                                                                  unsigned long long* __restrict__ out_solid,
+                                                                  unsigned long long cap_solid,
+                                                                  unsigned long long* __restrict__ counters /*[0] distinct [1] solid*/,
+                                                                  int* __restrict__ overflow) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const uint32_t C = 1u << G.c_log2;
   unsigned long long* keys = reinterpret_cast<unsigned long long*>(smem_raw);  // C
   unsigned int* cnt = reinterpret_cast<unsigned int*>(keys + C);               // 2 * C
   __shared__ unsigned long long base_all, base_solid;
+  __shared__ unsigned int blk_used, blk_solid, cur_all, cur_solid;
   const uint32_t bin = blockIdx.x;
   const unsigned long long n = bin_cnt[bin];
   if (n == 0) return;
-  const unsigned tid = threadIdx.x;
-  for (uint32_t s = tid; s < C; s += kBinThreads) {
+  const unsigned tid = threadIdx.x, lane = tid & 31;
+  const unsigned long long* src = words + bin_off[bin];
+  // the first tile is on its way while the table is cleared
+  unsigned long long w[kBinItems], wn[kBinItems];
+#pragma unroll
+  for (int j = 0; j < kBinItems; ++j) {
+    const unsigned long long i = (unsigned long long)j * THREADS + tid;
+    w[j] = i < n ? src[i] : ~0ULL;
+  }
+  for (uint32_t s = tid; s < C; s += THREADS) {
     keys[s] = kEmptyKey;
     cnt[s] = 0;
     cnt[C + s] = 0;
   }
+  if (tid == 0) { blk_used = 0; blk_solid = 0; cur_all = 0; cur_solid = 0; }
   __syncthreads();
-  const unsigned long long* src = words + bin_off[bin];
   const int slot_shift = max(G.low_bits - G.sub_bits - G.c_log2, 0);
   const uint32_t cmask = C - 1;
   const uint64_t field_mask = (1ULL << G.low_bits) - 1;
   bool full = false;
-  for (unsigned long long i0 = 0; i0 < n; i0 += (unsigned long long)kBinThreads * kBinItems) {
-    unsigned long long w[kBinItems];
-    bool valid[kBinItems];
+  // an instance word never has all 64 bits set (at most 2k - 7 + 3 <= 58 are used): ~0 = no item
+  for (unsigned long long i0 = 0; i0 < n; i0 += (unsigned long long)THREADS * kBinItems) {
 #pragma unroll
-    for (int j = 0; j < kBinItems; ++j) {
-      const unsigned long long i = i0 + (unsigned long long)j * kBinThreads + tid;
-      valid[j] = i < n;
-      w[j] = valid[j] ? src[i] : 0ULL;
+    for (int j = 0; j < kBinItems; ++j) {   // next tile: in flight while this one is counted
+      const unsigned long long i = i0 + (unsigned long long)(kBinItems + j) * THREADS + tid;
+      wn[j] = i < n ? src[i] : ~0ULL;
     }
 #pragma unroll
     for (int j = 0; j < kBinItems; ++j) {
-      if (!valid[j]) continue;
+      if (w[j] == ~0ULL) continue;
       const uint64_t hl = w[j] >> 3;
-      const uint64_t flags = ((w[j] & kWFwd) ? kFwdFlag : 0ULL) | ((w[j] & kWRev) ? kRevFlag : 0ULL);
+      const uint64_t flags = ((w[j] & kWFwd) << 63) | ((w[j] & kWRev) << 61);   // -> kFwdFlag (bit 63), kRevFlag (bit 62)
       uint32_t s = (uint32_t)(hl >> slot_shift) & cmask;
       bool done = false;
       for (uint32_t probes = 0; probes < C; ++probes) {
@@ -471,44 +484,66 @@ __global__ void __launch_bounds__(kBinThreads) kmer_count_bins_kernel(const unsi
       if (!done) { full = true; continue; }
       atomicAdd(&cnt[((w[j] & kWFlip) ? C : 0u) + s], 1u);
     }
+#pragma unroll
+    for (int j = 0; j < kBinItems; ++j) w[j] = wn[j];
   }
   if (full) *overflow = 1;   // more distinct k-mers than slots: the host re-runs with finer sub-bins
   __syncthreads();
-  // ---- write-out: thread t owns the slots [t * per, (t + 1) * per) ---------------------------------------
-  const uint32_t per = C / kBinThreads;
+  // ---- write-out: every used slot once.  Count (strided, conflict-free), reserve the block's ranges of
+  // the two lists with one global atomic each, then hand out positions warp by warp. -------------------
   uint32_t n_used = 0, n_solid = 0;
-  for (uint32_t s = tid * per; s < (tid + 1) * per; ++s) {
+  for (uint32_t s = tid; s < C; s += THREADS) {
     if (keys[s] != kEmptyKey) {
       ++n_used;
       if ((unsigned long long)cnt[s] + cnt[C + s] >= G.min_count) ++n_solid;
     }
   }
-  uint32_t tot_used, tot_solid;
-  uint32_t ex_used = block_excl_scan_u32(n_used, &tot_used);
-  uint32_t ex_solid = block_excl_scan_u32(n_solid, &tot_solid);
-  if (tid == 0) {
-    base_all = atomicAdd(&counters[0], (unsigned long long)tot_used);
-    base_solid = tot_solid ? atomicAdd(&counters[1], (unsigned long long)tot_solid) : 0ULL;
-    if (base_all + tot_used > cap_all || (tot_solid && base_solid + tot_solid > cap_solid)) *overflow = 2;
+  n_used = __reduce_add_sync(0xffffffffu, n_used);
+  n_solid = __reduce_add_sync(0xffffffffu, n_solid);
+  if (lane == 0) {
+    if (n_used) atomicAdd(&blk_used, n_used);
+    if (n_solid) atomicAdd(&blk_solid, n_solid);
   }
   __syncthreads();
-  unsigned long long oa = base_all + ex_used, os = base_solid + ex_solid;
+  if (tid == 0) {
+    const unsigned long long a = atomicAdd(&counters[0], (unsigned long long)blk_used);
+    const unsigned long long b = blk_solid ? atomicAdd(&counters[1], (unsigned long long)blk_solid) : 0ULL;
+    base_all = a;
+    base_solid = b;
+    if (a + blk_used > cap_all || (blk_solid && b + blk_solid > cap_solid)) *overflow = 2;
+  }
+  __syncthreads();
+  const unsigned long long ba = base_all, bs = base_solid;
   const uint64_t prefix = (G.prefix0 + (bin >> G.sub_bits)) << G.low_bits;
-  for (uint32_t s = tid * per; s < (tid + 1) * per; ++s) {
+  const unsigned lt = (1u << lane) - 1;
+  for (uint32_t s0 = 0; s0 < C; s0 += THREADS) {
+    const uint32_t s = s0 + tid;
     const unsigned long long kf = keys[s];
-    if (kf == kEmptyKey) continue;
-    const uint64_t canon = khash_inv(prefix | (kf & field_mask), G.k);
-    const unsigned long long key = canon | (kf & (kFwdFlag | kRevFlag));
+    const bool used = kf != kEmptyKey;
     const unsigned long long f = cnt[s], r = cnt[C + s];
-    if (oa < cap_all) {
-      uint4 e;
-      e.x = (unsigned)key; e.y = (unsigned)(key >> 32); e.z = (unsigned)f; e.w = (unsigned)r;
-      reinterpret_cast<uint4*>(out_all)[oa] = e;
+    const bool solid = used && f + r >= G.min_count;
+    const unsigned um = __ballot_sync(0xffffffffu, used), sm = __ballot_sync(0xffffffffu, solid);
+    if (!um) continue;
+    unsigned wa = 0, ws = 0;
+    if (lane == 0) {
+      wa = atomicAdd(&cur_all, (unsigned)__popc(um));
+      if (sm) ws = atomicAdd(&cur_solid, (unsigned)__popc(sm));
     }
-    ++oa;
-    if (f + r >= G.min_count) {
-      if (os < cap_solid) out_solid[os] = key;
-      ++os;
+    wa = __shfl_sync(0xffffffffu, wa, 0);
+    ws = __shfl_sync(0xffffffffu, ws, 0);
+    if (used) {
+      const uint64_t canon = khash_inv(prefix | (kf & field_mask), G.k);
+      const unsigned long long key = canon | (kf & (kFwdFlag | kRevFlag));
+      const unsigned long long oa = ba + wa + __popc(um & lt);
+      if (oa < cap_all) {
+        uint4 e;
+        e.x = (unsigned)key; e.y = (unsigned)(key >> 32); e.z = (unsigned)f; e.w = (unsigned)r;
+        reinterpret_cast<uint4*>(out_all)[oa] = e;
+      }
+      if (solid) {
+        const unsigned long long os = bs + ws + __popc(sm & lt);
+        if (os < cap_solid) out_solid[os] = key;
+      }
     }
   }
 }
@@ -674,8 +709,8 @@ int log2_exact(uint64_t x) {
 
 template <int MAXIT, int RPW>
 void launch_partition(Context* c, uint64_t r0, uint64_t n_reads, const PartGeom& G, unsigned long long* cursors,
-                      const unsigned long long* part_base, unsigned long long cap, unsigned long long* out,
-                      unsigned int* bitmap, uint64_t bit_mask, int samp_shift, int* overflow) {
+                      const unsigned long long* part_addr, unsigned long long cap, unsigned int* bitmap, uint64_t bit_mask,
+                      int samp_shift, int* overflow) {
   constexpr int tile_reads = kPartWarps * RPW;
   constexpr int tile_kmers = tile_reads * MAXIT * 32;
   constexpr int wpr = MAXIT + 1;
@@ -694,17 +729,17 @@ void launch_partition(Context* c, uint64_t r0, uint64_t n_reads, const PartGeom&
   // a range of reads: word offsets are absolute, so only the per-read arrays shift
   kmer_partition_kernel<MAXIT, RPW><<<grid, kPartThreads, smem, c->stream>>>(
       c->words.p, c->has_n ? c->nmask.p : nullptr, c->word_off.p + r0, c->lens.p + r0, (uint32_t)n_reads, G, cursors,
-      part_base, cap, out, bitmap, bit_mask, samp_shift, overflow);
+      part_addr, cap, bitmap, bit_mask, samp_shift, overflow);
   BGX_CUDA(cudaGetLastError());
 }
 
 void run_partition(Context* c, int maxit, uint64_t r0, uint64_t n_reads, const PartGeom& G, unsigned long long* cursors,
-                   const unsigned long long* part_base, unsigned long long cap, unsigned long long* out,
-                   unsigned int* bitmap, uint64_t bit_mask, int samp_shift, int* overflow) {
+                   const unsigned long long* part_addr, unsigned long long cap, unsigned int* bitmap, uint64_t bit_mask,
+                   int samp_shift, int* overflow) {
   if (maxit <= 4)
-    launch_partition<4, 4>(c, r0, n_reads, G, cursors, part_base, cap, out, bitmap, bit_mask, samp_shift, overflow);
+    launch_partition<4, 4>(c, r0, n_reads, G, cursors, part_addr, cap, bitmap, bit_mask, samp_shift, overflow);
   else
-    launch_partition<8, 2>(c, r0, n_reads, G, cursors, part_base, cap, out, bitmap, bit_mask, samp_shift, overflow);
+    launch_partition<8, 2>(c, r0, n_reads, G, cursors, part_addr, cap, bitmap, bit_mask, samp_shift, overflow);
 }
 
 // the linear-counting sample: bit (h >> shift) & (bits - 1) of the bitmap for hashes with `shift` low zero bits
@@ -733,7 +768,7 @@ struct Estimator {
   }
 };
 
-// pass-1 output for one batch
+// pass-1 output for one batch (single GPU, or the NCCL form of the exchange)
 struct Partitioned {
   DevBuf<unsigned long long> pk;
   std::vector<unsigned long long> base, count;  // per partition: first word, words
@@ -741,25 +776,18 @@ struct Partitioned {
   bool exact = false;                           // re-run with exact offsets (a heavy hitter overfilled a partition)
 };
 
-// Pass 1 over all reads for one batch: K = the k-mer instances expected in it.  est (optional)
-// receives the fused sample.
-void partition_reads(Context* c, uint64_t K, const PartGeom& G, int maxit, Estimator* est, Partitioned* out) {
+// One sweep of pass 1 over all reads: partition p goes to the cap words at addr[p].  Returns the
+// overflow flag; counts[p] = instances of partition p (exact even when the sweep overflowed).
+int sweep_partition(Context* c, const PartGeom& G, int maxit, Estimator* est, const std::vector<unsigned long long>& addr,
+                    unsigned long long cap, std::vector<unsigned long long>* counts) {
   cudaStream_t s = c->stream;
   const uint64_t n = c->n_reads;
   const int P = 1 << G.part_bits;
-  unsigned long long cap = K / P + K / (8ull * P) + 4096;  // hash partitions are near uniform
-  ScopedStage st_alloc(c, "count_setup");
-  out->pk.alloc((size_t)cap * P, s);
-  DevBuf<unsigned long long> cursors(P, s), part_base(P, s);
-  out->base.assign(P, 0);
-  out->count.assign(P, 0);
-  for (int p = 0; p < P; ++p) out->base[p] = (unsigned long long)p * cap;
-  BGX_CUDA(cudaMemcpyAsync(part_base.p, out->base.data(), P * 8, cudaMemcpyHostToDevice, s));
-  BGX_CUDA(cudaMemsetAsync(cursors.p, 0, P * 8, s));
+  DevBuf<unsigned long long> cursors(P, s), part_addr(P, s);
   DevBuf<int> overflow(1, s);
+  BGX_CUDA(cudaMemcpyAsync(part_addr.p, addr.data(), P * 8, cudaMemcpyHostToDevice, s));
+  BGX_CUDA(cudaMemsetAsync(cursors.p, 0, P * 8, s));
   BGX_CUDA(cudaMemsetAsync(overflow.p, 0, sizeof(int), s));
-  int h_over = 0;
-  st_alloc.stop();
   ScopedStage st(c, "count_partition");
   unsigned int* bitmap = est ? est->bitmap.p : nullptr;
   const uint64_t bit_mask = est ? est->bits - 1 : 0;
@@ -769,24 +797,41 @@ void partition_reads(Context* c, uint64_t K, const PartGeom& G, int maxit, Estim
     // ordered after its own copy only, all appending to the same partitions through the cursors
     uint64_t pos = 0;
     for (Context::UploadChunk& ch : c->upload) {
-      if (ch.r0 > pos)
-        run_partition(c, maxit, pos, ch.r0 - pos, G, cursors.p, part_base.p, cap, out->pk.p, bitmap, bit_mask, shift, overflow.p);
+      if (ch.r0 > pos) run_partition(c, maxit, pos, ch.r0 - pos, G, cursors.p, part_addr.p, cap, bitmap, bit_mask, shift, overflow.p);
       BGX_CUDA(cudaStreamWaitEvent(s, ch.ev, 0));
       cudaEventDestroy(ch.ev);
-      if (ch.r1 > ch.r0)
-        run_partition(c, maxit, ch.r0, ch.r1 - ch.r0, G, cursors.p, part_base.p, cap, out->pk.p, bitmap, bit_mask, shift, overflow.p);
+      if (ch.r1 > ch.r0) run_partition(c, maxit, ch.r0, ch.r1 - ch.r0, G, cursors.p, part_addr.p, cap, bitmap, bit_mask, shift, overflow.p);
       pos = ch.r1;
     }
     c->upload.clear();
-    if (pos < n)
-      run_partition(c, maxit, pos, n - pos, G, cursors.p, part_base.p, cap, out->pk.p, bitmap, bit_mask, shift, overflow.p);
+    if (pos < n) run_partition(c, maxit, pos, n - pos, G, cursors.p, part_addr.p, cap, bitmap, bit_mask, shift, overflow.p);
   } else if (n) {
     reads_ready(c);
-    run_partition(c, maxit, 0, n, G, cursors.p, part_base.p, cap, out->pk.p, bitmap, bit_mask, shift, overflow.p);
+    run_partition(c, maxit, 0, n, G, cursors.p, part_addr.p, cap, bitmap, bit_mask, shift, overflow.p);
   }
+  int h_over = 0;
+  counts->assign(P, 0);
   BGX_CUDA(cudaMemcpyAsync(&h_over, overflow.p, sizeof(int), cudaMemcpyDeviceToHost, s));
-  BGX_CUDA(cudaMemcpyAsync(out->count.data(), cursors.p, P * 8, cudaMemcpyDeviceToHost, s));
+  BGX_CUDA(cudaMemcpyAsync(counts->data(), cursors.p, P * 8, cudaMemcpyDeviceToHost, s));
   BGX_CUDA(cudaStreamSynchronize(s));
+  st.stop();
+  return h_over;
+}
+
+// Pass 1 into a buffer of this GPU: K = the k-mer instances expected in the batch.  est (optional)
+// receives the fused sample.
+void partition_reads(Context* c, uint64_t K, const PartGeom& G, int maxit, Estimator* est, Partitioned* out) {
+  cudaStream_t s = c->stream;
+  const int P = 1 << G.part_bits;
+  unsigned long long cap = K / P + K / (8ull * P) + 4096;  // hash partitions are near uniform
+  out->pk.alloc((size_t)cap * P, s);
+  out->base.assign(P, 0);
+  std::vector<unsigned long long> addr(P);
+  for (int p = 0; p < P; ++p) {
+    out->base[p] = (unsigned long long)p * cap;
+    addr[p] = (unsigned long long)(uintptr_t)(out->pk.p + out->base[p]);
+  }
+  int h_over = sweep_partition(c, G, maxit, est, addr, cap, &out->count);
   out->cap = cap;
   out->exact = false;
   if (h_over) {
@@ -801,18 +846,13 @@ void partition_reads(Context* c, uint64_t K, const PartGeom& G, int maxit, Estim
       cap = std::max<unsigned long long>(cap, out->count[p]);
     }
     out->pk.alloc(std::max<uint64_t>(total, 1), s);
-    BGX_CUDA(cudaMemcpyAsync(part_base.p, out->base.data(), P * 8, cudaMemcpyHostToDevice, s));
-    BGX_CUDA(cudaMemsetAsync(cursors.p, 0, P * 8, s));
-    BGX_CUDA(cudaMemsetAsync(overflow.p, 0, sizeof(int), s));
-    run_partition(c, maxit, 0, n, G, cursors.p, part_base.p, cap, out->pk.p, bitmap, bit_mask, shift, overflow.p);
-    BGX_CUDA(cudaMemcpyAsync(&h_over, overflow.p, sizeof(int), cudaMemcpyDeviceToHost, s));
-    BGX_CUDA(cudaStreamSynchronize(s));
+    for (int p = 0; p < P; ++p) addr[p] = (unsigned long long)(uintptr_t)(out->pk.p + out->base[p]);
+    h_over = sweep_partition(c, G, maxit, est, addr, cap, &out->count);
     BGX_CHECK(!h_over, "internal: exact partition pass overflowed");
     c->add_stat("count_partition_reruns", 1);
     out->cap = cap;
     out->exact = true;
   }
-  st.stop();
 }
 
 // the partitions this rank will count: (device address, instance count, local partition) each
@@ -930,6 +970,90 @@ void exchange_partitions(Context* c, const Partitioned& pt, int P, Owned* own) {
   for (unsigned long long v : own->cnt) own->n_inst += v;
 }
 
+// Multi-GPU, the default: pass 1 stores every run straight into the memory of the GPU that owns its
+// partition (peer mapping over NVLink), so counting and exchange are ONE kernel and nothing is staged
+// on the sender.  The owner's buffer has one region of `cap` words per (source rank, local partition);
+// K_max = the most instances any rank brings to this batch (the same value on every rank).  If a
+// region overflows anywhere (a heavy hitter), every rank re-runs the sweep against exact offsets.
+void partition_direct(Context* c, uint64_t K_max, const PartGeom& G, int maxit, Owned* own) {
+  cudaStream_t s = c->stream;
+  const int N = c->dist.nranks, R = c->dist.rank;
+  const int P = 1 << G.part_bits, Pl = P / N;
+  unsigned long long cap = K_max / P + K_max / (8ull * P) + 4096;
+  void* peer[64];
+  std::vector<unsigned long long> addr(P), counts;
+  {
+    ScopedStage st(c, "count_exchange");
+    own->rbuf.alloc((size_t)N * Pl * cap, s);
+    dist_map_peers(c, own->rbuf.p, peer);   // also: every owner's buffer is ready to be written
+    st.stop();
+  }
+  for (int p = 0; p < P; ++p)
+    addr[p] = (unsigned long long)(uintptr_t)(static_cast<unsigned long long*>(peer[p / Pl]) + ((size_t)R * Pl + p % Pl) * cap);
+  int h_over = sweep_partition(c, G, maxit, nullptr, addr, cap, &counts);
+  ScopedStage st(c, "count_exchange");
+  std::vector<uint64_t> mine(P + 1), all((size_t)N * (P + 1));
+  for (int p = 0; p < P; ++p) mine[p] = counts[p];
+  mine[P] = h_over ? 1 : 0;
+  dist_allgather_host_u64(c, mine.data(), P + 1, all.data());   // also: every rank's stores have landed
+  auto cnt_of = [&](int src, int p) { return all[(size_t)src * (P + 1) + p]; };
+  bool any_over = false;
+  for (int r = 0; r < N; ++r) any_over = any_over || all[(size_t)r * (P + 1) + P] != 0;
+  std::vector<uint64_t> off((size_t)N * Pl, 0);   // [src][pl] -> first word in this owner's buffer
+  if (!any_over) {
+    for (int src = 0; src < N; ++src)
+      for (int pl = 0; pl < Pl; ++pl) off[(size_t)src * Pl + pl] = ((size_t)src * Pl + pl) * cap;
+  } else {
+    // exact layout, identical arithmetic on every rank: owner d lays its regions out partition-major
+    auto layout = [&](int d, std::vector<uint64_t>* o) {
+      uint64_t total = 0;
+      for (int pl = 0; pl < Pl; ++pl)
+        for (int src = 0; src < N; ++src) {
+          (*o)[(size_t)src * Pl + pl] = total;
+          total += cnt_of(src, d * Pl + pl);
+        }
+      return total;
+    };
+    const uint64_t total = layout(R, &off);
+    own->rbuf.alloc(std::max<uint64_t>(total, 1), s);
+    dist_map_peers(c, own->rbuf.p, peer);
+    cap = 0;
+    std::vector<uint64_t> od((size_t)N * Pl);
+    for (int d = 0; d < N; ++d) {
+      layout(d, &od);
+      for (int pl = 0; pl < Pl; ++pl) {
+        addr[d * Pl + pl] = (unsigned long long)(uintptr_t)(static_cast<unsigned long long*>(peer[d]) + od[(size_t)R * Pl + pl]);
+        cap = std::max<unsigned long long>(cap, counts[d * Pl + pl]);
+      }
+    }
+    st.stop();
+    h_over = sweep_partition(c, G, maxit, nullptr, addr, cap, &counts);
+    BGX_CHECK(!h_over, "internal: exact partition pass overflowed");
+    c->add_stat("count_partition_reruns", 1);
+    ScopedStage st2(c, "count_exchange");
+    uint64_t dummy = 0;
+    std::vector<uint64_t> dummies(N);
+    dist_allgather_host_u64(c, &dummy, 1, dummies.data());   // every rank's stores have landed
+    st2.stop();
+  }
+  own->ptr.clear();
+  own->cnt.clear();
+  own->pl.clear();
+  uint64_t out_words = 0;
+  for (int pl = 0; pl < Pl; ++pl)
+    for (int src = 0; src < N; ++src) {
+      own->ptr.push_back((unsigned long long)(uintptr_t)(own->rbuf.p + off[(size_t)src * Pl + pl]));
+      own->cnt.push_back(cnt_of(src, R * Pl + pl));
+      own->pl.push_back((uint32_t)pl);
+    }
+  for (int p = 0; p < P; ++p)
+    if (p / Pl != R) out_words += counts[p];
+  c->add_stat("count_exchange_bytes_out", 8.0 * (double)out_words);
+  own->n_inst = 0;
+  for (unsigned long long v : own->cnt) own->n_inst += v;
+  st.stop();
+}
+
 // device-side view of an Owned list, ready for the tile kernels
 struct OwnedDev {
   DevBuf<unsigned long long> ptr, cnt;
@@ -1007,6 +1131,14 @@ void stage_count_kmers(Context* c) {
   uint64_t K_all = K;                      // all ranks' reads
   dist_allreduce_sum_host_u64(c, &K_all, 1);
   const uint64_t K_share = K_all / N;      // instances this rank will own (hash-uniform)
+  uint64_t K_max = K;                      // the most any rank brings
+  if (N > 1) {
+    std::vector<uint64_t> ks(N);
+    dist_allgather_host_u64(c, &K, 1, ks.data());
+    for (uint64_t v : ks) K_max = std::max(K_max, v);
+  }
+  // BGX_EXCHANGE=nccl: partition locally, then one NCCL send/recv per peer (the round-1 form; A/B hook)
+  static const bool direct_exchange = [] { const char* e = getenv("BGX_EXCHANGE"); return !(e && std::string(e) == "nccl"); }();
   const int maxit = (int)((std::max<int64_t>((int64_t)c->max_len - k + 1, 1) + 31) / 32);
   BGX_CHECK(maxit <= 8, "read longer than 255 bases");
   const uint64_t batches = choose_batches(c, K, K_share);
@@ -1022,7 +1154,7 @@ void stage_count_kmers(Context* c) {
   part_bits = std::max(part_bits, rank_bits);
   BGX_CHECK(2 * k - batch_bits - part_bits >= 16, "k-mer too short for this many batches / partitions");
   int c_log2 = 12;  // 4096 slots = 64 KB of shared memory per block, three blocks per SM
-  if (const char* e = getenv("BGX_BIN_SLOTS_LOG2")) c_log2 = std::max(8, std::min(13, atoi(e)));  // experiment hook
+  if (const char* e = getenv("BGX_BIN_SLOTS_LOG2")) c_log2 = std::max(9, std::min(13, atoi(e)));  // experiment hook
 
   DevBuf<int> overflow(1, s);
   std::vector<BatchOut> outs(batches);
@@ -1039,9 +1171,13 @@ void stage_count_kmers(Context* c) {
     const uint64_t Kb = K / batches + K / (16 * batches) + 1024;  // this rank's instances in the batch (hash-uniform)
     est.init(pow2_ceil(std::max<uint64_t>(1 << 20, std::max(Kb, K_share / batches) / 8)), 4, s);
     Partitioned pt;
-    partition_reads(c, Kb, G, maxit, N == 1 ? &est : nullptr, &pt);
     Owned own;
-    exchange_partitions(c, pt, P, &own);
+    if (N > 1 && direct_exchange) {
+      partition_direct(c, K_max / batches + K_max / (16 * batches) + 1024, G, maxit, &own);
+    } else {
+      partition_reads(c, Kb, G, maxit, N == 1 ? &est : nullptr, &pt);
+      exchange_partitions(c, pt, P, &own);
+    }
     OwnedDev od;
     upload_owned(c, own, &od);
     n_inst += own.n_inst;
@@ -1108,9 +1244,17 @@ void stage_count_kmers(Context* c) {
       BGX_CUDA(cudaMemsetAsync(overflow.p, 0, sizeof(int), s));
       BinGeom BG{k, low_bits, sub_bits, c_log2, ((uint64_t)b << part_bits) | (uint64_t)(R * Pl), (uint32_t)c->opt.min_kmer_count};
       const size_t smem = (size_t)16 << c_log2;
-      BGX_CUDA(cudaFuncSetAttribute(kmer_count_bins_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-      KLAUNCH(kmer_count_bins_kernel)<<<(unsigned)n_bins, kBinThreads, smem, s>>>(split.p, bin_off.p, hist.p, BG, bo.all.p, cap_all,
-                                                                          bo.solid.p, cap_solid, counters.p, overflow.p);
+      static const int bin_threads = [] { const char* e = getenv("BGX_BIN_THREADS"); return e ? atoi(e) : 512; }();  // experiment hook
+      note_launch();
+      if (bin_threads == 256) {
+        BGX_CUDA(cudaFuncSetAttribute(kmer_count_bins_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        kmer_count_bins_kernel<256><<<(unsigned)n_bins, 256, smem, s>>>(split.p, bin_off.p, hist.p, BG, bo.all.p, cap_all, bo.solid.p,
+                                                                      cap_solid, counters.p, overflow.p);
+      } else {
+        BGX_CUDA(cudaFuncSetAttribute(kmer_count_bins_kernel<512>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        kmer_count_bins_kernel<512><<<(unsigned)n_bins, 512, smem, s>>>(split.p, bin_off.p, hist.p, BG, bo.all.p, cap_all, bo.solid.p,
+                                                                      cap_solid, counters.p, overflow.p);
+      }
       BGX_CUDA(cudaGetLastError());
       unsigned long long h_cnt[2];
       int h_over = 0;

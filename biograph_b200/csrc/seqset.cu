@@ -1379,20 +1379,26 @@ void stage_build_seqset_dist(Context* c) {
   BGX_CHECK(c->n_seeds < kMaxShardRecords, "too many seed records for one GPU shard");
 
   // 0. replicate the corrected stores: comparisons past the 32-base key read the sequence, and a
-  //    record may be compared on any rank (peer-memory reads are the planned alternative)
+  //    record may be compared on any rank.  Every rank's store sits in an equal-sized slice (the
+  //    largest rank's size), so ONE in-place ncclAllGather moves everything (NVSwitch multicast /
+  //    ring at NVLink rate) instead of N-1 send/recv pairs.
   {
     ScopedStage st(c, "store_allgather");
     uint64_t mine = 2 * c->n_words + 1;
-    std::vector<uint64_t> words(N), base(N);
+    std::vector<uint64_t> words(N);
     dist_allgather_host_u64(c, &mine, 1, words.data());
-    uint64_t tot = 0;
-    for (int r = 0; r < N; ++r) { base[r] = tot; tot += words[r]; }
+    uint64_t slice = 0;
+    for (int r = 0; r < N; ++r) slice = std::max(slice, words[r]);
+    slice = (slice + 1) & ~1ull;  // 16-byte multiple
+    const uint64_t tot = slice * N;
     BGX_CHECK(tot * 32 < (1ull << 47), "corrected store too large for 48-bit suffix locators");
     c->gstore.alloc(tot + 1, s);
+    uint64_t* my_slice = c->gstore.p + (uint64_t)R * slice;
+    BGX_CUDA(cudaMemcpyAsync(my_slice, c->store.p, mine * 8, cudaMemcpyDeviceToDevice, s));
+    if (slice > mine) BGX_CUDA(cudaMemsetAsync(my_slice + mine, 0, (slice - mine) * 8, s));
     BGX_CUDA(cudaMemsetAsync(c->gstore.p + tot, 0, 8, s));
-    std::vector<uint64_t> zero(N, 0), send_cnt(N, mine);
-    dist_alltoallv(c, c->store.p, zero.data(), send_cnt.data(), c->gstore.p, base.data(), words.data(), 8);
-    c->gstore_word_base = base[R];
+    dist_allgather_bytes(c, my_slice, c->gstore.p, slice * 8);
+    c->gstore_word_base = (uint64_t)R * slice;
     c->add_stat("store_allgather_bytes", 8.0 * (double)tot);
     st.stop();
   }

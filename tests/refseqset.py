@@ -26,6 +26,36 @@ def member(name, fn):
     return fixture()[f"{name}|{fn}"].tobytes()
 
 
+class SpiralZip:
+    """Member access by offset, the way the reference reads a spiral file (unzGetCurrentFileZStreamPos64,
+    modules/io/spiral_file_mmap.cpp:82-125).  Array members carry a CRC field of 0 ("don't bother to fill
+    crc", :421-423), so zipfile.read() -- which verifies the CRC -- only works for the JSON members."""
+
+    def __init__(self, path):
+        import struct
+        import zipfile
+        self.path = str(path)
+        self.info = {i.filename: i for i in zipfile.ZipFile(self.path).infolist()}
+        self.order = [i.filename for i in zipfile.ZipFile(self.path).infolist()]
+        self._struct = struct
+
+    def namelist(self):
+        return list(self.order)
+
+    def read(self, name):
+        i = self.info[name]
+        with open(self.path, "rb") as f:
+            f.seek(i.header_offset)
+            h = f.read(30)
+            n, e = self._struct.unpack("<HH", h[26:30])
+            f.seek(i.header_offset + 30 + n + e)
+            return f.read(i.file_size)
+
+    def crc_ok(self, name):
+        import zlib
+        return (zlib.crc32(self.read(name)) & 0xffffffff) == self.info[name].CRC
+
+
 def varbit_decode(elements, bits, n):
     w = np.frombuffer(elements, dtype="<u8")
     if bits == 8:

@@ -238,7 +238,7 @@ def test_overfull_count_bins_are_split_finer(B):
     """a sub-bin with more distinct k-mers than its shared-memory table has slots: the split and
     count passes are re-run with finer sub-bins (then larger tables) until every bin fits"""
     reads = _sim(20000, 6000, 150, 0.01, 93)
-    os.environ["BGX_BIN_SLOTS_LOG2"] = "8"
+    os.environ["BGX_BIN_SLOTS_LOG2"] = "9"
     os.environ["BGX_SUB_BITS"] = "0"
     try:
         ss, st = full_compare(B, reads)
