@@ -40,7 +40,7 @@ def build_library(force=False):
 
 EXPORTS = ["bgx_default_options", "bgx_last_error", "bgx_version", "bgx_device_count", "bgx_create", "bgx_destroy",
            "bgx_free", "bgx_add_reads_ascii", "bgx_add_reads_fastq", "bgx_add_reads_packed", "bgx_add_reads_packed_async", "bgx_count_kmers", "bgx_export_kmers",
-           "bgx_correct", "bgx_export_corrected", "bgx_build_seqset", "bgx_export_seqset",
+           "bgx_correct", "bgx_export_corrected", "bgx_export_reads", "bgx_build_seqset", "bgx_export_seqset",
            "bgx_export_entries_ascii", "bgx_lookup_reads", "bgx_build_readmap", "bgx_run", "bgx_reset_results", "bgx_clear_reads", "bgx_stats_json", "bgx_timer_start", "bgx_timer_stop",
            "bgx_launch_count", "bgx_debug_sort_pairs", "bgx_dist_unique_id", "bgx_dist_init", "bgx_seqset_layout", "bgx_seed_uncorrected", "bgx_export_varbit"]
 
@@ -70,6 +70,7 @@ def load_library():
     L.bgx_correct.argtypes = [vp]
     L.bgx_export_corrected.argtypes = [vp, u64p, C.POINTER(vp), C.POINTER(vp), u64p, C.POINTER(vp), C.POINTER(vp),
                                        C.POINTER(vp)]
+    L.bgx_export_reads.argtypes = [vp, u64p, C.POINTER(vp), C.POINTER(vp), u64p]
     L.bgx_build_seqset.argtypes = [vp]
     L.bgx_export_seqset.argtypes = [vp, u64p, C.POINTER(C.c_uint32), C.POINTER(vp), C.POINTER(vp), vp * 4, vp * 4,
                                     vp * 4, C.c_uint64 * 5]
@@ -293,6 +294,14 @@ class Bgx:
                 "corrections": self._take(pc, n.value, np.uint8).astype(np.int32),
                 "next_fwd": self._take(pf, n.value, np.uint16).astype(np.int32),
                 "next_rev": self._take(pr, n.value, np.uint16).astype(np.int32), "n_kept": int((lens > 0).sum())}
+
+    def export_reads(self):
+        """the resident reads back as ASCII: (bytes, lens uint16[n])"""
+        n, nb = C.c_uint64(), C.c_uint64()
+        pl, pb = C.c_void_p(), C.c_void_p()
+        self._ck(self.L.bgx_export_reads(self.h, C.byref(n), C.byref(pl), C.byref(pb), C.byref(nb)))
+        lens = self._take(pl, n.value, np.uint16)
+        return self._take(pb, nb.value, np.uint8).tobytes(), lens
 
     # -- expander + builder -----------------------------------------------------------------------
     def build_seqset(self):

@@ -1,0 +1,540 @@
+// bgx-create -- `biograph create` for the seqset-construction path on a B200: reads in, .bg out.
+//
+// Takes the flags of SEQSETMain (modules/biograph/biograph_create.cpp:258-335), validates them with
+// the reference's rules and messages (:345-430, :483-519), runs the stages through the facade
+// (include/bgx_build_seqset.hpp -> C ABI -> CUDA) in the reference's order
+//   import -> kmerization -> read_correction -> make_seqset -> make_readmap -> metadata
+// (:540-811) and writes the BioGraph directory the way biograph_dir does
+// (modules/bio_base/biograph_dir.cpp:11-80):
+//   <out>/seqset                         spiral file (ZIP64, members as seqset.cpp:19-44)
+//   <out>/coverage/<sha1>.readmap        spiral file, named by its SHA-1 (biograph_create.cpp:820-828)
+//   <out>/metadata/bg_info.json          biograph_metadata: version, biograph_id, accession_id, samples
+//   <out>/qc/create_stats.json           the counters of :796-808 + stage timings
+//   <out>/qc/create_log.txt, <out>/qc/kmer_quality_report.html, <out>/analysis/
+// Inputs: FASTQ, plain or gzip (zlib), single, --pair <second file> or --interleaved.  BAM/CRAM
+// (htslib in the reference) are rejected with a message.  There is no CPU fallback: the stages need
+// a CUDA device.
+#include <sys/stat.h>
+#include <zlib.h>
+
+#include <chrono>
+#include <cstdarg>
+#include <fstream>
+#include <iostream>
+#include <map>
+#include <random>
+#include <set>
+#include <sstream>
+
+#include "bgx_build_seqset.hpp"
+
+namespace {
+
+const char* kVersion = "7.1.2-dev";  // versions.bzl:12 BIOGRAPH_VERSION of the reference commit
+
+struct Args {
+  std::string out, ref, id, format = "auto", tmp, stats_file;
+  std::vector<std::string> reads, pairs;
+  bool interleaved = false, force = false, allow_long_reads = false, keep_tmp = false;
+  std::string min_kmer_count = "5", kmer_size = "30", trim_after_portion = "0.7", max_corrections = "8", min_good_run = "2",
+              min_reads = "0.4", warn_reads = "0.7", tmp_encoding = "gzip1", sample_reads = "0", cut_reads, overrep = "0";
+  int device = 0;
+};
+
+[[noreturn]] void die(const std::string& msg) {
+  std::cerr << msg << "\n";
+  exit(1);
+}
+
+std::string fmt(const char* f, ...) {
+  char buf[1024];
+  va_list ap;
+  va_start(ap, f);
+  vsnprintf(buf, sizeof(buf), f, ap);
+  va_end(ap);
+  return buf;
+}
+
+// validate_param / validate_float_param (biograph_create.cpp:337-375): same messages
+size_t validate_param(const std::string& param, const std::string& value, size_t lo, size_t hi) {
+  size_t v;
+  try {
+    size_t pos = 0;
+    v = std::stoull(value, &pos);
+  } catch (const std::exception&) {
+    throw std::runtime_error(param + " must specify an integer");
+  }
+  if (v < lo) throw std::runtime_error(fmt("%s must specify an integer >= %zu", param.c_str(), lo));
+  if (v > hi) throw std::runtime_error(fmt("%s must specify an integer <= %zu", param.c_str(), hi));
+  return v;
+}
+float validate_float_param(const std::string& param, const std::string& value, float lo, float hi) {
+  float v;
+  try {
+    v = std::stof(value);
+  } catch (const std::exception&) {
+    throw std::runtime_error(param + " must specify a floating point number");
+  }
+  if (v < lo) throw std::runtime_error(fmt("%s must specify a floating point number >= %f", param.c_str(), lo));
+  if (v > hi) throw std::runtime_error(fmt("%s must specify a floating point number <= %f", param.c_str(), hi));
+  return v;
+}
+
+bool ends_with(const std::string& s, const std::string& e) { return s.size() >= e.size() && s.compare(s.size() - e.size(), e.size(), e) == 0; }
+
+void usage() {
+  std::cerr << "bgx-create version " << kVersion << " (" << bgx_version() << ")\n\n"
+            << "Usage: bgx-create [OPTIONS] --reads <file> --ref <refdir> --out <biograph> [--pair <fastq pairs>] [...]\n\n"
+            << "Convert reads to BioGraph format.\n\n"
+               "  --out arg                       Output BioGraph name (.bg)\n"
+               "  --ref arg                       Reference directory (or FASTA; only its size is used here)\n"
+               "  --reads, --in arg               Input file to process (fastq, fastq.gz; - for STDIN)\n"
+               "  --format arg (=auto)            Input file format when using STDIN\n"
+               "  --interleaved                   Input reads are interleaved (fastq only)\n"
+               "  --pair arg                      Second input file containing read pairs (fastq only)\n"
+               "  --id arg                        Optional accession ID for this sample\n"
+               "  -f, --force                     Overwrite existing BioGraph\n"
+               "  --min-kmer-count arg (=5)       Minimum kmer count (min 1)\n"
+               "  --kmer-size arg (=30)           The size of kmers to use for kmer generation\n"
+               "  --trim-after-portion arg (=0.7) Trim the end of reads until they pass read correction\n"
+               "  --max-corrections arg (=8)      Correct up to the specified number of bases\n"
+               "  --min-good-run arg (=2)         Minimum number of good bases between corrections\n"
+               "  --min-reads arg (=0.4)          Minimum fraction of reads that must survive read correction\n"
+               "  --warn-reads arg (=0.7)         Warn when this fraction of reads does not survive read correction\n"
+               "  --device arg (=0)               CUDA device ordinal\n"
+               "  (accepted for compatibility, no effect here: --tmp, --keep-tmp, --threads, --max-mem, --tmp-encoding,\n"
+               "   --cache, --stats)\n";
+}
+
+Args parse(int argc, char** argv) {
+  Args a;
+  std::vector<std::string> positional;
+  auto need = [&](int& i) -> std::string {
+    if (i + 1 >= argc) die(std::string("the required argument for option '") + argv[i] + "' is missing");
+    return argv[++i];
+  };
+  for (int i = 1; i < argc; ++i) {
+    std::string o = argv[i], v;
+    const size_t eq = o.find('=');
+    bool has_v = false;
+    if (o.rfind("--", 0) == 0 && eq != std::string::npos) { v = o.substr(eq + 1); o = o.substr(0, eq); has_v = true; }
+    auto val = [&]() { return has_v ? v : need(i); };
+    if (o == "--out") a.out = val();
+    else if (o == "--ref") a.ref = val();
+    else if (o == "--reads" || o == "--in") a.reads.push_back(val());
+    else if (o == "--pair") a.pairs.push_back(val());
+    else if (o == "--format") a.format = val();
+    else if (o == "--interleaved") a.interleaved = true;
+    else if (o == "--id") a.id = val();
+    else if (o == "--force" || o == "-f") a.force = true;
+    else if (o == "--min-kmer-count") a.min_kmer_count = val();
+    else if (o == "--kmer-size") a.kmer_size = val();
+    else if (o == "--trim-after-portion") a.trim_after_portion = val();
+    else if (o == "--max-corrections") a.max_corrections = val();
+    else if (o == "--min-good-run") a.min_good_run = val();
+    else if (o == "--min-reads") a.min_reads = val();
+    else if (o == "--warn-reads") a.warn_reads = val();
+    else if (o == "--allow-long-reads") a.allow_long_reads = true;
+    else if (o == "--tmp-encoding") a.tmp_encoding = val();
+    else if (o == "--overrep-threshold") a.overrep = val();
+    else if (o == "--sample-reads") a.sample_reads = val();
+    else if (o == "--cut-reads") a.cut_reads = val();
+    else if (o == "--stats") a.stats_file = val();
+    else if (o == "--tmp") a.tmp = val();
+    else if (o == "--keep-tmp") a.keep_tmp = true;
+    else if (o == "--threads" || o == "--max-mem" || o == "--cache" || o == "--debug" || o == "--sys-err-thresh" || o == "--rnd-err-thresh" ||
+             o == "--dump-kmers") { if (o != "--cache" && o != "--debug") (void)val(); }
+    else if (o == "--device") a.device = atoi(val().c_str());
+    else if (o == "--help" || o == "-h") { usage(); exit(0); }
+    else if (o.rfind("-", 0) == 0 && o != "-") die("unrecognised option '" + o + "'");
+    else positional.push_back(o);
+  }
+  // positional: in, ref, out (biograph_create.cpp:330-332)
+  size_t pi = 0;
+  if (a.reads.empty() && pi < positional.size()) a.reads.push_back(positional[pi++]);
+  if (a.ref.empty() && pi < positional.size()) a.ref = positional[pi++];
+  if (a.out.empty() && pi < positional.size()) a.out = positional[pi++];
+  if (a.out.empty()) die("the option '--out' is required but missing");
+  if (a.reads.empty()) die("the option '--reads' is required but missing");
+  return a;
+}
+
+// ---- FASTQ input (modules/bio_format/fastq.cpp:40-126 semantics live in bgx_add_reads_fastq) ---------------
+struct LineReader {   // plain or gzip, through zlib
+  gzFile f = nullptr;
+  std::string name;
+  explicit LineReader(const std::string& path) : name(path) {
+    f = path == "/dev/stdin" ? gzdopen(0, "rb") : gzopen(path.c_str(), "rb");
+    if (!f) throw std::runtime_error("Could not open " + path + " for reading");
+    gzbuffer(f, 1 << 20);
+  }
+  ~LineReader() { if (f) gzclose(f); }
+  // appends up to max_bytes of whole lines to out; false at end of file
+  bool read_chunk(std::string& out, size_t max_bytes) {
+    const size_t start = out.size();
+    out.resize(start + max_bytes);
+    const int n = gzread(f, &out[start], (unsigned)max_bytes);
+    if (n < 0) throw std::runtime_error("read error in " + name);
+    out.resize(start + (size_t)n);
+    return n > 0;
+  }
+};
+
+// hands whole FASTQ records (4 lines) to the GPU parser; the tail of a chunk that is not a whole
+// record stays in `carry`
+uint64_t feed_fastq_text(bgx_bs::session& s, std::string& carry, bool last) {
+  size_t lines = 0, cut = 0;
+  for (size_t i = 0; i < carry.size(); ++i)
+    if (carry[i] == '\n' && (++lines % 4) == 0) cut = i + 1;
+  if (last && cut < carry.size()) {  // no newline at the end of the file
+    if (carry.back() != '\n') carry.push_back('\n');
+    lines = 0; cut = 0;
+    for (size_t i = 0; i < carry.size(); ++i)
+      if (carry[i] == '\n' && (++lines % 4) == 0) cut = i + 1;
+    if (cut < carry.size()) throw std::runtime_error("Unexpected end of fastq file: incomplete record");
+  }
+  uint64_t n = 0;
+  if (cut) {
+    std::lock_guard<std::mutex> l(s.add_mutex());
+    bgx_bs::detail::ck(bgx_add_reads_fastq(s.ctx(), carry.data(), cut, &n));
+    carry.erase(0, cut);
+  }
+  return n;
+}
+
+// two files read in step, records interleaved (mates become reads 2i, 2i + 1)
+bool next_record(LineReader& r, std::string& buf, size_t& pos, std::string rec[4]) {
+  for (int l = 0; l < 4; ++l) {
+    for (;;) {
+      const size_t nl = buf.find('\n', pos);
+      if (nl != std::string::npos) { rec[l].assign(buf, pos, nl - pos); pos = nl + 1; break; }
+      buf.erase(0, pos);
+      pos = 0;
+      if (!r.read_chunk(buf, 8 << 20)) {
+        if (l == 0 && buf.empty()) return false;
+        if (l == 3 && !buf.empty()) { rec[l] = buf; buf.clear(); break; }
+        throw std::runtime_error("Unexpected end of fastq file: incomplete record in " + r.name);
+      }
+    }
+    if (!rec[l].empty() && rec[l].back() == '\r') rec[l].pop_back();
+  }
+  return true;
+}
+
+// ---- small utilities ---------------------------------------------------------------------------------------
+std::string sha1_file(const std::string& path) {
+  uint32_t h[5] = {0x67452301u, 0xEFCDAB89u, 0x98BADCFEu, 0x10325476u, 0xC3D2E1F0u};
+  auto block = [&](const uint8_t* p) {
+    uint32_t w[80];
+    for (int i = 0; i < 16; ++i) w[i] = (uint32_t)p[4 * i] << 24 | (uint32_t)p[4 * i + 1] << 16 | (uint32_t)p[4 * i + 2] << 8 | p[4 * i + 3];
+    for (int i = 16; i < 80; ++i) { uint32_t t = w[i - 3] ^ w[i - 8] ^ w[i - 14] ^ w[i - 16]; w[i] = t << 1 | t >> 31; }
+    uint32_t a = h[0], b = h[1], c = h[2], d = h[3], e = h[4];
+    for (int i = 0; i < 80; ++i) {
+      uint32_t f, k;
+      if (i < 20) { f = (b & c) | (~b & d); k = 0x5A827999u; }
+      else if (i < 40) { f = b ^ c ^ d; k = 0x6ED9EBA1u; }
+      else if (i < 60) { f = (b & c) | (b & d) | (c & d); k = 0x8F1BBCDCu; }
+      else { f = b ^ c ^ d; k = 0xCA62C1D6u; }
+      uint32_t t = (a << 5 | a >> 27) + f + e + k + w[i];
+      e = d; d = c; c = b << 30 | b >> 2; b = a; a = t;
+    }
+    h[0] += a; h[1] += b; h[2] += c; h[3] += d; h[4] += e;
+  };
+  std::ifstream in(path, std::ios::binary);
+  if (!in) throw std::runtime_error("cannot read " + path);
+  std::vector<uint8_t> buf(1 << 20);
+  uint8_t tail[128];
+  uint64_t total = 0;
+  size_t have = 0;
+  for (;;) {
+    in.read(reinterpret_cast<char*>(buf.data()), buf.size());
+    const size_t n = (size_t)in.gcount();
+    if (!n) break;
+    total += n;
+    size_t i = 0;
+    for (; i + 64 <= n; i += 64) block(buf.data() + i);
+    have = n - i;
+    memcpy(tail, buf.data() + i, have);
+    if (n < buf.size()) break;   // the buffer is a multiple of 64, so only the last chunk leaves a partial block
+  }
+  tail[have++] = 0x80;
+  while (have % 64 != 56) tail[have++] = 0;
+  const uint64_t bits = total * 8;
+  for (int i = 7; i >= 0; --i) tail[have++] = (uint8_t)(bits >> (8 * i));
+  for (size_t i = 0; i < have; i += 64) block(tail + i);
+  char out[41];
+  snprintf(out, sizeof(out), "%08x%08x%08x%08x%08x", h[0], h[1], h[2], h[3], h[4]);
+  return out;
+}
+
+std::string make_uuid() {
+  std::random_device rd;
+  std::mt19937_64 g(((uint64_t)rd() << 32) ^ rd() ^ (uint64_t)std::chrono::steady_clock::now().time_since_epoch().count());
+  uint64_t a = g(), b = g();
+  a = (a & ~0xF000ull) | 0x4000ull;                 // version 4
+  b = (b & ~(3ull << 62)) | (2ull << 62);           // variant 1
+  return fmt("%08x-%04x-%04x-%04x-%012llx", (unsigned)(a >> 32), (unsigned)((a >> 16) & 0xffff), (unsigned)(a & 0xffff),
+             (unsigned)(b >> 48), (unsigned long long)(b & 0xffffffffffffull));
+}
+
+std::string json_str(const std::string& s) {
+  std::string o = "\"";
+  for (char c : s) {
+    if (c == '"' || c == '\\') { o += '\\'; o += c; }
+    else if (c == '\n') o += "\\n";
+    else o += c;
+  }
+  return o + "\"";
+}
+
+uint64_t reference_bases(const std::string& ref) {
+  // the reference directory holds the FASTA as source.fasta (biograph reference); a FASTA path works too
+  std::vector<std::string> cand = {ref, ref + "/source.fasta", ref + "/reference.fasta"};
+  for (const std::string& p : cand) {
+    struct stat st;
+    if (stat(p.c_str(), &st) != 0 || !S_ISREG(st.st_mode)) continue;
+    std::ifstream in(p);
+    std::string line;
+    uint64_t n = 0;
+    while (std::getline(in, line))
+      if (!line.empty() && line[0] != '>') n += line.size() - (line.back() == '\r');
+    return n;
+  }
+  return 0;
+}
+
+struct Stages {  // m_stats.start_stage / end_stage: seconds per stage, in order
+  std::vector<std::pair<std::string, double>> t;
+  std::chrono::steady_clock::time_point t0;
+  void start() { t0 = std::chrono::steady_clock::now(); }
+  void end(const std::string& name) { t.emplace_back(name, std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count()); }
+};
+
+}  // namespace
+
+int main(int argc, char** argv) {
+  try {
+    Args a = parse(argc, argv);
+    // biograph_create.cpp:483-498
+    const size_t kmer_size = validate_param("--kmer-size", a.kmer_size, 16, 32);
+    const size_t min_kmer_count = validate_param("--min-kmer-count", a.min_kmer_count, 1, 10000000);
+    const float min_corrected_reads = validate_float_param("min-reads", a.min_reads, 0.0f, 1.0f);
+    const float warn_corrected_reads = validate_float_param("warn-reads", a.warn_reads, 0.0f, 1.0f);
+    const float trim_after_portion = validate_float_param("trim-after-portion", a.trim_after_portion, 0.0f, 1.0f);
+    const unsigned max_corrections = (unsigned)validate_param("max-corrections", a.max_corrections, 0, 32);
+    const unsigned min_good_run = (unsigned)validate_param("min-good-run", a.min_good_run, 0, 64);
+    if (validate_param("overrep-threshold", a.overrep, 0, 10000000) != 0) die("--overrep-threshold other than 0 is not supported by bgx-create");
+    if (validate_float_param("sample-reads", a.sample_reads, 0.0f, 1.0f) != 0.0f) die("--sample-reads is not supported by bgx-create");
+    if (!a.cut_reads.empty()) die("--cut-reads is not supported by bgx-create");
+    if (a.allow_long_reads) die("--allow-long-reads is not supported by bgx-create (reads are at most 255 bases)");
+    static const std::set<std::string> formats = {"bam", "cram", "fastq", "auto"};
+    if (!formats.count(a.format)) die("Invalid input format '" + a.format + "'");
+    if (!a.pairs.empty() && a.pairs.size() != a.reads.size())
+      die("If pair files are present, there must be the same number of them as read files.");
+    struct stat st;
+    if (!a.force && stat(a.out.c_str(), &st) == 0) die("Refusing to overwrite '" + a.out + "'. Use --force to override.");
+
+    // biograph_dir(m_out, CREATE_BGDIR) (biograph_dir.cpp:25-37)
+    mkdir(a.out.c_str(), 0777);
+    for (const char* d : {"metadata", "coverage", "qc", "analysis"}) mkdir((a.out + "/" + d).c_str(), 0777);
+    if (stat((a.out + "/qc").c_str(), &st) != 0)
+      throw std::runtime_error("Attempted to create " + a.out + " but the resulting biograph was not valid. Cannot continue.");
+    if (a.id.empty()) {  // fs::canonical(m_out).stem()
+      std::string base = a.out;
+      while (base.size() > 1 && base.back() == '/') base.pop_back();
+      const size_t sl = base.find_last_of('/');
+      if (sl != std::string::npos) base = base.substr(sl + 1);
+      const size_t dot = base.find_last_of('.');
+      a.id = dot == std::string::npos || dot == 0 ? base : base.substr(0, dot);
+    }
+    if (a.stats_file.empty()) a.stats_file = a.out + "/qc/create_stats.json";
+    std::ofstream log(a.out + "/qc/create_log.txt");
+    auto splog = [&](const std::string& m) {
+      const time_t now = time(nullptr);
+      char ts[32];
+      strftime(ts, sizeof(ts), "%Y-%m-%d %H:%M:%S", localtime(&now));
+      log << ts << " " << m << "\n";
+      log.flush();
+    };
+    {
+      std::string cmd;
+      for (int i = 0; i < argc; ++i) cmd += std::string(i ? " " : "") + argv[i];
+      splog("bgx-create " + std::string(kVersion) + " (" + bgx_version() + "): " + cmd);
+    }
+
+    bgx_bs::count_kmer_options ko;
+    ko.kmer_size = (unsigned)kmer_size;
+    ko.min_count = (unsigned)min_kmer_count;
+    ko.device = a.device;
+    bgx_bs::read_correction_params rcp;
+    rcp.trim_after_portion = trim_after_portion;
+    rcp.frc_max_corrections = max_corrections;
+    rcp.frc_min_good_run = min_good_run;
+    bgx_bs::session sess(ko, rcp);
+    Stages stages;
+    const auto t_total = std::chrono::steady_clock::now();
+
+    // ---- import (:540-663) ----------------------------------------------------------------------------------
+    stages.start();
+    std::cerr << "Importing reads\n";
+    bgx_bs::kmer_counter counter(sess);
+    counter.start_prob_pass();
+    uint64_t read_count = 0;
+    bool got_paired = false;
+    for (size_t i = 0; i < a.reads.size(); ++i) {
+      std::string in_reads = a.reads[i] == "-" ? "/dev/stdin" : a.reads[i];
+      const std::string in_pairs = a.pairs.empty() ? "" : a.pairs[i];
+      std::string in_format = a.format;
+      if (in_format == "auto") {  // :583-606
+        if (a.interleaved) { std::cerr << "--interleaved specified. Assuming fastq format.\n"; in_format = "fastq"; }
+        else if (!in_pairs.empty()) { std::cerr << "--pair specified. Assuming fastq format.\n"; in_format = "fastq"; }
+        else if (ends_with(in_reads, ".bam")) in_format = "bam";
+        else if (ends_with(in_reads, ".cram")) in_format = "cram";
+        else if (ends_with(in_reads, ".fq") || ends_with(in_reads, ".fq.gz") || ends_with(in_reads, ".fastq") || ends_with(in_reads, ".fastq.gz")) in_format = "fastq";
+        else if (in_reads == "/dev/stdin") in_format = "bam";
+        else {
+          std::cerr << "Cannot determine the input file type of " << in_reads << ".\n"
+                    << "Input file does not end in .bam .cram .fq .fastq .fq.gz or .fastq.gz.\nPlease specify --format.\n";
+          return 1;
+        }
+      }
+      if (in_format != "fastq") die("bgx-create reads FASTQ (plain or gzip); " + in_format + " input needs the reference's htslib importer");
+      if (in_pairs.empty()) {
+        // whole-file chunks go to the GPU parser (split, validate, 2-bit pack on the device)
+        LineReader r(in_reads);
+        std::string carry;
+        uint64_t n_file = 0;
+        while (r.read_chunk(carry, 64 << 20)) n_file += feed_fastq_text(sess, carry, false);
+        n_file += feed_fastq_text(sess, carry, true);
+        if (a.interleaved) {
+          if (n_file % 2) throw std::runtime_error("Interleaved fastq " + in_reads + " holds an odd number of reads");
+          got_paired = got_paired || n_file > 0;
+        }
+        read_count += n_file;
+      } else {
+        // two files in step: mates are appended back to back
+        LineReader r1(in_reads), r2(in_pairs);
+        std::string b1, b2, rec1[4], rec2[4];
+        size_t p1 = 0, p2 = 0;
+        bgx_bs::kmer_counter::prob_pass_processor proc(counter);
+        for (;;) {
+          const bool h1 = next_record(r1, b1, p1, rec1), h2 = next_record(r2, b2, p2, rec2);
+          if (h1 != h2) throw std::runtime_error("Pair files " + in_reads + " and " + in_pairs + " hold different numbers of reads");
+          if (!h1) break;
+          proc.add(rec1[1]);
+          proc.add(rec2[1]);
+          read_count += 2;
+          got_paired = true;
+        }
+        proc.flush_all();
+      }
+    }
+    if (!a.pairs.empty() && !got_paired) throw std::runtime_error("Pair files specified but no pairs were successfully imported");
+    if (read_count == 0) throw std::runtime_error("\nNo reads were imported, exiting.");
+    counter.close_prob_pass();
+    std::cerr << "\nTotal reads imported: " << read_count << std::endl;
+    splog(fmt("%lu reads imported", (unsigned long)read_count));
+    stages.end("import");
+
+    // ---- kmerization (:665-700) ---------------------------------------------------------------------------------
+    stages.start();
+    std::cerr << "\nGenerating kmers\n";
+    bgx_bs::kmerize_bf_params kp;
+    kp.kmer_size = kmer_size;
+    kp.min_count = min_kmer_count;
+    auto kres = bgx_bs::run_kmerize_subtask(kp, bgx_bs::manifest(), &counter);
+    std::unique_ptr<bgx_bs::kmer_set> ks = std::move(kres.first);
+    splog(fmt("%lu kmers passed the minimum count of %lu", (unsigned long)ks->size(), (unsigned long)min_kmer_count));
+    {
+      std::ofstream html(a.out + "/qc/kmer_quality_report.html");
+      html << "<html><head><title>k-mer count histogram</title></head><body><h1>k-mer count histogram</h1>\n"
+           << "<p>" << ks->size() << " " << kmer_size << "-mers with count &gt;= " << min_kmer_count << "</p>\n<table><tr><th>count</th><th>k-mers</th></tr>\n";
+      for (const auto& rec : kres.second[1].records) html << "<tr><td>" << rec.first << "</td><td>" << rec.second << "</td></tr>\n";
+      html << "</table></body></html>\n";
+    }
+    stages.end("kmerization");
+
+    // ---- read correction (:727-778) -----------------------------------------------------------------------------
+    stages.start();
+    std::cerr << "\nCorrecting reads\n";
+    bgx_bs::correct_reads cr(sess, *ks, rcp);
+    cr.add_initial_repo();
+    cr.correct_all();
+    uint64_t num_corrected_reads = 0, num_corrected_bases = 0;
+    unsigned max_read_len = 0;
+    for (size_t i = 0; i < cr.size(); ++i) {
+      const unsigned len = cr.corrected_length(i);
+      if (len) { ++num_corrected_reads; num_corrected_bases += len; max_read_len = std::max(max_read_len, len); }
+    }
+    const uint64_t ref_size = reference_bases(a.ref);
+    const float cov_estimate = ref_size ? num_corrected_bases * 1. / ref_size : 0.f;
+    splog(fmt("%0.2fx estimated corrected coverage", cov_estimate));
+    const float corrected_pct = num_corrected_reads * 1. / read_count;
+    if (corrected_pct < min_corrected_reads) {
+      const std::string msg = fmt("Fewer than %2.0f%% of reads (set by --min-reads) were kept after correction (%lu / %lu remain). Cannot continue.",
+                                  min_corrected_reads * 100.0, (unsigned long)num_corrected_reads, (unsigned long)read_count);
+      splog(msg);
+      throw std::runtime_error(msg);
+    }
+    if (corrected_pct < warn_corrected_reads) {
+      const std::string msg = fmt("Warning: Fewer than %2.0f%% of reads (set by --warn-reads) survived correction (%lu / %lu remain)",
+                                  warn_corrected_reads * 100.0, (unsigned long)num_corrected_reads, (unsigned long)read_count);
+      splog(msg);
+      std::cerr << msg << "\n";
+    } else {
+      splog(fmt("%lu / %lu reads survived read correction.", (unsigned long)num_corrected_reads, (unsigned long)read_count));
+    }
+    stages.end("read_correction");
+
+    // ---- make_seqset (:914-950) -------------------------------------------------------------------------------------
+    stages.start();
+    std::cerr << "\nGenerating BioGraph\n";
+    bgx_bs::expander expand(sess, a.keep_tmp);
+    const size_t n1 = expand.sort_and_dedup("", "initial", "init_sorted", "init_expanded", 7, 255);
+    splog(fmt("Initial sort and dedup: %lu entries", (unsigned long)n1));
+    const size_t n_final = expand.sort_and_dedup("pass2_sorted", "pass2_expanded", "complete", "", 0, 0);
+    splog(fmt("Final sort and dedup: %lu entries", (unsigned long)n_final));
+    bgx_bs::builder b(sess);
+    b.build_chunks("complete", a.keep_tmp);
+    const std::string uuid = make_uuid();
+    bgx_bs::seqset_tables tables = b.make_seqset(a.out + "/seqset", bgx_bs::null_progress_handler, uuid);
+    stages.end("make_seqset");
+
+    // ---- make_readmap (:818-831) ----------------------------------------------------------------------------------------
+    stages.start();
+    std::cerr << "\nCalculating coverage...\n";
+    const std::string tmp_readmap = a.out + "/coverage/tmp.readmap";
+    bgx_bs::make_readmap::do_make(tmp_readmap, sess, uuid, got_paired, max_read_len);
+    const std::string readmap_sha = sha1_file(tmp_readmap);
+    if (rename(tmp_readmap.c_str(), (a.out + "/coverage/" + readmap_sha + ".readmap").c_str()) != 0)
+      throw std::runtime_error("cannot rename the readmap");
+    stages.end("make_readmap");
+
+    // ---- metadata (:785-811) ------------------------------------------------------------------------------------------------
+    stages.start();
+    {
+      std::ofstream os(a.out + "/metadata/bg_info.json");
+      os << "{\"accession_id\":" << json_str(a.id) << ",\"biograph_id\":" << json_str(uuid) << ",\"command_history\":[],\"samples\":{"
+         << json_str(a.id) << ":" << json_str(readmap_sha) << "},\"version\":" << json_str(kVersion) << "}";
+      if (!os.good()) throw std::runtime_error("Could not write to " + a.out + "/metadata/bg_info.json");
+    }
+    stages.end("metadata");
+    {
+      std::ofstream os(a.stats_file);
+      os.precision(17);
+      os << "{\"command\":\"create\",\"version\":" << json_str(kVersion) << ",\"accession_id\":" << json_str(a.id) << ",\"reference\":"
+         << json_str(a.ref) << ",\"imported_reads\":" << read_count << ",\"coverage\":" << cov_estimate << ",\"corrected_reads\":"
+         << num_corrected_reads << ",\"corrected_bases\":" << num_corrected_bases << ",\"avg_bases_per_read\":"
+         << (num_corrected_reads ? num_corrected_bases * 1. / num_corrected_reads : 0.0) << ",\"corrected_pct\":" << corrected_pct
+         << ",\"uuid\":" << json_str(uuid) << ",\"entries\":" << tables.num_entries << ",\"timings\":[";
+      for (const auto& s : stages.t) os << "{" << json_str(s.first) << ":" << (long)s.second << "},";
+      os << "{\"total\":" << (long)std::chrono::duration<double>(std::chrono::steady_clock::now() - t_total).count() << "}]}";
+    }
+    splog(fmt("%lu entries in the seqset", (unsigned long)tables.num_entries));
+    std::cerr << "\n" << a.out << " created.\n";
+    return 0;
+  } catch (const std::exception& e) {
+    std::cerr << e.what() << "\n";
+    return 1;
+  }
+}

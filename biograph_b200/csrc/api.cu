@@ -39,6 +39,21 @@ __global__ void corrected_ascii_kernel(const uint64_t* __restrict__ store, const
   for (int j = lane_id(); j < L; j += 32) o[j] = "ACGT"[(w[j >> 5] >> (62 - 2 * (j & 31))) & 3];
 }
 
+__global__ void reads_ascii_kernel(const uint64_t* __restrict__ words, const uint32_t* __restrict__ nmask,
+                                   const uint32_t* __restrict__ word_off, const uint16_t* __restrict__ lens,
+                                   const uint64_t* __restrict__ out_off, uint64_t n_reads, char* __restrict__ out) {
+  uint64_t r = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  if (r >= n_reads) return;
+  int L = lens[r];
+  const uint64_t* w = words + word_off[r];
+  const uint32_t* m = nmask ? nmask + word_off[r] : nullptr;
+  char* o = out + out_off[r];
+  for (int j = lane_id(); j < L; j += 32) {
+    const bool is_n = m && ((m[j >> 5] >> (31 - (j & 31))) & 1u);
+    o[j] = is_n ? 'N' : "ACGT"[(w[j >> 5] >> (62 - 2 * (j & 31))) & 3];
+  }
+}
+
 template <typename T>
 T* to_host(const T* d, size_t n, cudaStream_t s) {
   T* h = (T*)host_alloc(std::max<size_t>(n, 1) * sizeof(T));
@@ -85,7 +100,7 @@ int bgx_create(const bgx_options* opts, bgx_ctx** out) {
     // bs/kmer_counter.cpp:52-54: k in [16,31] (k-mer + 2 flag bits must fit 64 bits)
     BGX_CHECK(o.kmer_size >= 16 && o.kmer_size <= 31, "kmer_size must be in [16,31]");
     BGX_CHECK(o.min_kmer_count >= 1, "min_kmer_count must be >= 1");
-    BGX_CHECK(o.max_corrections >= 0 && o.max_corrections <= 16, "max_corrections must be in [0,16]");
+    BGX_CHECK(o.max_corrections >= 0 && o.max_corrections <= 32, "max_corrections must be in [0,32]");  // biograph_create.cpp:486
     BGX_CHECK(o.min_good_run >= 0, "min_good_run must be >= 0");
     BGX_CHECK(o.trim_after_portion >= 0.f && o.trim_after_portion <= 1.f, "trim_after_portion must be in [0,1]");
     BGX_CHECK(o.sort_key_bits == 0 || (o.sort_key_bits >= 16 && o.sort_key_bits <= 64 && o.sort_key_bits % 8 == 0),
@@ -208,6 +223,34 @@ int bgx_export_corrected(bgx_ctx* x, uint64_t* n_reads, uint16_t** lens, char** 
       BGX_CUDA(cudaMemcpyAsync(d_off.p, off.data(), (n + 1) * 8, cudaMemcpyHostToDevice, s));
       if (n) KLAUNCH(corrected_ascii_kernel)<<<(unsigned)((n * 32 + 255) / 256), 256, 0, s>>>(c->store.p, c->word_off.p, c->clen.p,
                                                                                   d_off.p, n, d_out.p);
+      BGX_CUDA(cudaGetLastError());
+      BGX_CUDA(cudaMemcpyAsync(out, d_out.p, off[n], cudaMemcpyDeviceToHost, s));
+      BGX_CUDA(cudaStreamSynchronize(s));
+      *bases = out;
+    }
+    if (lens) *lens = h_len; else host_free(h_len);
+  })
+}
+
+int bgx_export_reads(bgx_ctx* x, uint64_t* n_reads, uint16_t** lens, char** bases, uint64_t* n_bases) {
+  CTX_GUARD({
+    reads_ready(c);
+    cudaStream_t s = c->stream;
+    const uint64_t n = c->n_reads;
+    if (n_reads) *n_reads = n;
+    uint16_t* h_len = to_host(c->lens.p, n, s);
+    BGX_CUDA(cudaStreamSynchronize(s));
+    std::vector<uint64_t> off(n + 1);
+    off[0] = 0;
+    for (uint64_t r = 0; r < n; ++r) off[r + 1] = off[r] + h_len[r];
+    if (n_bases) *n_bases = off[n];
+    if (bases) {
+      char* out = (char*)host_alloc(std::max<uint64_t>(off[n], 1));
+      DevBuf<uint64_t> d_off(n + 1, s);
+      DevBuf<char> d_out(std::max<uint64_t>(off[n], 1), s);
+      BGX_CUDA(cudaMemcpyAsync(d_off.p, off.data(), (n + 1) * 8, cudaMemcpyHostToDevice, s));
+      if (n) KLAUNCH(reads_ascii_kernel)<<<(unsigned)((n * 32 + 255) / 256), 256, 0, s>>>(
+          c->words.p, c->has_n ? c->nmask.p : nullptr, c->word_off.p, c->lens.p, d_off.p, n, d_out.p);
       BGX_CUDA(cudaGetLastError());
       BGX_CUDA(cudaMemcpyAsync(out, d_out.p, off[n], cudaMemcpyDeviceToHost, s));
       BGX_CUDA(cudaStreamSynchronize(s));

@@ -28,17 +28,21 @@
 namespace bgx {
 namespace {
 
-constexpr int kMaxCorr = 16;
+// --max-corrections goes up to 32 on the reference's command line (biograph_create.cpp:486); the frame
+// stack of the DFS is sized by it, so the kernel exists for 16 (the default of 8 fits) and for 32
+constexpr int kMaxCorrLimit = 32;
 constexpr int kMaxWords = 9;  // 255 bases -> 8 words + 1 pad
 
-struct Res {
+template <int MAXC>
+struct ResT {
   int len;
   int ncorr;
-  uint8_t pos[kMaxCorr];  // logical positions of substitutions
-  uint8_t base[kMaxCorr];
+  uint8_t pos[MAXC];  // logical positions of substitutions
+  uint8_t base[MAXC];
 };
 
-struct Frame {
+template <int MAXC>
+struct FrameT {
   uint64_t kmer;   // k-mer before `start` on ENTER; k-mer at the error point afterwards
   int start;       // logical start of this frame's input
   int run;         // bases extended without correction
@@ -47,7 +51,7 @@ struct Frame {
   int budget;
   int best_size;
   int best_b;
-  Res best;
+  ResT<MAXC> best;
 };
 
 struct Params {
@@ -151,8 +155,11 @@ __device__ __forceinline__ uint64_t shift_in(uint64_t kmer, int b, uint64_t mask
 // A window is "fresh" when no substitution of the current DFS path lies inside it: its membership
 // is the probe kernel's mask bit.  The substitutions of the path are the frames' e (ascending),
 // so only the innermost one can be within k of the running position.
+template <int MAXC>
 __device__ void correct_internal(const Params& P, const Input& in, const SolidMask& sm, uint64_t kmer0, int min_run0,
-                                 int budget0, bool require_run_at_end, Frame* st, Res* out) {
+                                 int budget0, bool require_run_at_end, FrameT<MAXC>* st, ResT<MAXC>* out) {
+  using Frame = FrameT<MAXC>;
+  using Res = ResT<MAXC>;
   const uint64_t kmask = kmer_low_mask(P.k);
   int depth = 0;
   st[0].start = 0;
@@ -458,6 +465,7 @@ __global__ void __launch_bounds__(kProbeThreads, (MAXIT <= 4 ? 3 : 1)) probe_ker
 }
 
 // Pass 2: one thread per read on the slow list.
+template <int MAXC>
 __global__ void __launch_bounds__(128) correct_kernel(const uint64_t* __restrict__ words,
                                                       const uint32_t* __restrict__ nmask,
                                                       const uint32_t* __restrict__ word_off,
@@ -476,7 +484,9 @@ __global__ void __launch_bounds__(128) correct_kernel(const uint64_t* __restrict
   uint64_t w[kMaxWords];
   uint32_t m[kMaxWords];
   uint32_t smw[kMaxWords - 1];
-  Frame st[kMaxCorr + 1];
+  using Frame = FrameT<MAXC>;
+  using Res = ResT<MAXC>;
+  Frame st[MAXC + 1];
   int out_len = 0, corrections = 0, nf = 0, nr = 0;
   const int k = P.k;
   int L = 0, nw = 0;
@@ -677,7 +687,7 @@ void stage_seed_uncorrected(Context* c) {
 void stage_correct(Context* c) {
   reads_ready(c);
   BGX_CHECK(c->counted, "bgx_correct: call bgx_count_kmers first");
-  BGX_CHECK(c->opt.max_corrections <= kMaxCorr, "max_corrections > 16 is not supported");
+  BGX_CHECK(c->opt.max_corrections <= kMaxCorrLimit, "max_corrections > 32 is not supported");
   cudaStream_t s = c->stream;
   ScopedStage st_all(c, "correct_total");
   const uint64_t n = c->n_reads;
@@ -731,11 +741,15 @@ void stage_correct(Context* c) {
     // sized for the worst case (every read slow); threads past the device-side count leave at once
     BGX_CUDA(cudaMemcpyAsync(&h_slow, n_slow.p, sizeof(h_slow), cudaMemcpyDeviceToHost, s));
     BGX_CUDA(cudaStreamSynchronize(s));
-    if (h_slow)
-      KLAUNCH(correct_kernel)<<<(h_slow + 127) / 128, 128, 0, s>>>(c->words.p, c->has_n ? c->nmask.p : nullptr, c->word_off.p,
-                                                                   c->lens.p, P, slow_list.p, slow_mask.p, mask_words, n_slow.p,
-                                                                   c->store.p, c->n_words, c->clen.p, c->ncorr.p,
-                                                                   c->next_fwd.p, c->next_rev.p, totals.p);
+#define BGX_CORRECT(MAXC)                                                                                                   \
+  note_launch();                                                                                                            \
+  correct_kernel<MAXC><<<(h_slow + 127) / 128, 128, 0, s>>>(c->words.p, c->has_n ? c->nmask.p : nullptr, c->word_off.p, \
+                                                                      c->lens.p, P, slow_list.p, slow_mask.p, mask_words, n_slow.p, \
+                                                                      c->store.p, c->n_words, c->clen.p, c->ncorr.p,               \
+                                                                      c->next_fwd.p, c->next_rev.p, totals.p)
+    if (h_slow && P.max_corr <= 16) { BGX_CORRECT(16); }
+    else if (h_slow) { BGX_CORRECT(32); }
+#undef BGX_CORRECT
     BGX_CUDA(cudaGetLastError());
     st.stop();
   }

@@ -4,8 +4,10 @@
 #include <dlfcn.h>
 #include <nccl.h>
 
+#include <cstdlib>
 #include <cstring>
 #include <mutex>
+#include <string>
 
 #include "ctx.h"
 
@@ -87,31 +89,51 @@ void dist_init(Context* c, int nranks, int rank, const uint8_t id[128]) {
   c->dist.comm = comm;
 }
 
-void dist_map_peers(Context* c, void* local, void** peer) {
+void dist_map_peers_n(Context* c, void* const* local, int k, void** peer) {
   const int N = c->dist.nranks, R = c->dist.rank;
-  peer[R] = local;
+  for (int j = 0; j < k; ++j) peer[(size_t)j * N + R] = local[j];
   if (N == 1) return;
   static_assert(sizeof(cudaIpcMemHandle_t) == 64, "cudaIpcMemHandle_t is 64 bytes");
-  cudaIpcMemHandle_t h;
-  BGX_CUDA(cudaIpcGetMemHandle(&h, local));
-  uint64_t mine[8];
-  memcpy(mine, &h, 64);
-  std::vector<uint64_t> all((size_t)N * 8);
-  dist_allgather_host_u64(c, mine, 8, all.data());
+  std::vector<uint64_t> mine((size_t)k * 8), all((size_t)N * k * 8);
+  for (int j = 0; j < k; ++j) {
+    cudaIpcMemHandle_t h;
+    BGX_CUDA(cudaIpcGetMemHandle(&h, local[j]));
+    memcpy(&mine[(size_t)j * 8], &h, 64);
+  }
+  dist_allgather_host_u64(c, mine.data(), (size_t)k * 8, all.data());
   for (int r = 0; r < N; ++r) {
     if (r == R) continue;
-    std::string key(reinterpret_cast<const char*>(&all[(size_t)r * 8]), 64);
-    key.push_back((char)r);
-    auto it = c->dist.ipc_cache.find(key);
-    if (it == c->dist.ipc_cache.end()) {
-      cudaIpcMemHandle_t hr;
-      memcpy(&hr, &all[(size_t)r * 8], 64);
-      void* p = nullptr;
-      BGX_CUDA(cudaIpcOpenMemHandle(&p, hr, cudaIpcMemLazyEnablePeerAccess));
-      it = c->dist.ipc_cache.emplace(key, p).first;
+    for (int j = 0; j < k; ++j) {
+      const uint64_t* hp = &all[((size_t)r * k + j) * 8];
+      std::string key(reinterpret_cast<const char*>(hp), 64);
+      key.push_back((char)r);
+      auto it = c->dist.ipc_cache.find(key);
+      if (it == c->dist.ipc_cache.end()) {
+        cudaIpcMemHandle_t hr;
+        memcpy(&hr, hp, 64);
+        void* p = nullptr;
+        BGX_CUDA(cudaIpcOpenMemHandle(&p, hr, cudaIpcMemLazyEnablePeerAccess));
+        it = c->dist.ipc_cache.emplace(key, p).first;
+      }
+      peer[(size_t)j * N + r] = it->second;
     }
-    peer[r] = it->second;
   }
+}
+
+void dist_map_peers(Context* c, void* local, void** peer) { dist_map_peers_n(c, &local, 1, peer); }
+
+void dist_barrier(Context* c) {
+  if (c->dist.nranks == 1) return;
+  uint64_t one = 1;
+  dist_allreduce_sum_host_u64(c, &one, 1);
+}
+
+bool dist_direct_exchange() {
+  static const bool direct = [] {
+    const char* e = getenv("BGX_EXCHANGE");
+    return !(e && std::string(e) == "nccl");
+  }();
+  return direct;
 }
 
 void dist_destroy(Context* c) {

@@ -57,6 +57,12 @@ void dist_p2p_batch(Context* c, const std::vector<P2P>& sends, const std::vector
 // Mappings are cached per handle (the arena hands out the same blocks run after run).  Doubles as a
 // barrier: when it returns, every rank has passed the point of the call on its stream.
 void dist_map_peers(Context* c, void* local, void** peer);
+// the same for k blocks with one exchange: peer[j * nranks + r] = block j of rank r
+void dist_map_peers_n(Context* c, void* const* local, int k, void** peer);
+// every rank has passed this point on its stream (and the host has waited for it)
+void dist_barrier(Context* c);
+// false: BGX_EXCHANGE=nccl (exchanges as NCCL send/recv batches instead of stores into peer memory)
+bool dist_direct_exchange();
 
 // ---- small host-side metadata (counts, boundaries): staged through the device, synchronous -------------
 // out[r * n .. (r+1) * n) = rank r's in[0..n)

@@ -1138,7 +1138,7 @@ void stage_count_kmers(Context* c) {
     for (uint64_t v : ks) K_max = std::max(K_max, v);
   }
   // BGX_EXCHANGE=nccl: partition locally, then one NCCL send/recv per peer (the round-1 form; A/B hook)
-  static const bool direct_exchange = [] { const char* e = getenv("BGX_EXCHANGE"); return !(e && std::string(e) == "nccl"); }();
+  const bool direct_exchange = dist_direct_exchange();
   const int maxit = (int)((std::max<int64_t>((int64_t)c->max_len - k + 1, 1) + 31) / 32);
   BGX_CHECK(maxit <= 8, "read longer than 255 bases");
   const uint64_t batches = choose_batches(c, K, K_share);

@@ -108,13 +108,38 @@ struct BucketIndex {
   int shift;  // 64 - bits
 };
 
+// Thread i closes the buckets between the one of record i-1 and the one of record i.  A long run of
+// empty buckets -- everything below / above the key range a rank of a sharded build owns is one --
+// is left to gap_fill_kernel, which fills it with a whole grid instead of one thread.
+constexpr int kGapInline = 64, kGapList = 1024;
+struct Gap {
+  unsigned long long b0, b1;  // buckets [b0, b1] get the value v
+  uint32_t v;
+};
 __global__ void bucket_index_kernel(const uint64_t* __restrict__ keys, uint32_t n, int shift, uint32_t n_buckets,
-                                    uint32_t* __restrict__ start) {
+                                    uint32_t* __restrict__ start, Gap* __restrict__ gaps, unsigned int* __restrict__ n_gaps) {
   uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i > n) return;  // thread n closes the table
   const int64_t b_prev = i == 0 ? -1 : (int64_t)(keys[i - 1] >> shift);
   const int64_t b_cur = i == n ? (int64_t)n_buckets : (int64_t)(keys[i] >> shift);
+  if (b_cur - b_prev > kGapInline) {
+    const unsigned g = atomicAdd(n_gaps, 1u);
+    if (g < kGapList) {
+      gaps[g] = Gap{(unsigned long long)(b_prev + 1), (unsigned long long)b_cur, i};
+      return;
+    }
+  }
   for (int64_t b = b_prev + 1; b <= b_cur; ++b) start[b] = i;
+}
+
+__global__ void gap_fill_kernel(const Gap* __restrict__ gaps, const unsigned int* __restrict__ n_gaps, uint32_t* __restrict__ start) {
+  const unsigned ng = min(*n_gaps, (unsigned)kGapList);
+  for (unsigned g = 0; g < ng; ++g) {
+    const Gap gp = gaps[g];
+    for (unsigned long long b = gp.b0 + (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; b <= gp.b1;
+         b += (unsigned long long)gridDim.x * blockDim.x)
+      start[b] = gp.v;
+  }
 }
 
 __device__ __forceinline__ uint32_t lower_bound_idx(const uint64_t* __restrict__ store,
@@ -754,11 +779,17 @@ __global__ void __launch_bounds__(256) route_count_kernel(const uint64_t* __rest
   if (threadIdx.x <= (unsigned)sp.n && sc[threadIdx.x]) atomicAdd(&counts[threadIdx.x], (unsigned long long)sc[threadIdx.x]);
 }
 
+// per-destination output arrays: the local staging buffer at the destination's offset, or -- the
+// default -- the destination rank's receive buffer itself (peer mapping), at this rank's offset in it
+struct RouteOut {
+  uint64_t* keys[kMaxRanks];
+  uint64_t* locs[kMaxRanks];
+};
 __global__ void __launch_bounds__(256) route_scatter_kernel(const uint64_t* __restrict__ keys,
                                                             const uint64_t* __restrict__ locs,
                                                             const uint8_t* __restrict__ dest, uint32_t n, int nranks,
-                                                            unsigned long long* __restrict__ cursors /*start offsets*/,
-                                                            uint64_t* __restrict__ okeys, uint64_t* __restrict__ olocs) {
+                                                            unsigned long long* __restrict__ cursors /*zero*/,
+                                                            RouteOut out) {
   __shared__ unsigned int sc[kMaxRanks];
   __shared__ unsigned long long sbase[kMaxRanks];
   if (threadIdx.x < kMaxRanks) sc[threadIdx.x] = 0;
@@ -776,8 +807,8 @@ __global__ void __launch_bounds__(256) route_scatter_kernel(const uint64_t* __re
   __syncthreads();
   if (i < n) {
     unsigned long long o = sbase[d] + r;
-    okeys[o] = keys[i];
-    olocs[o] = locs[i];
+    out.keys[d][o] = keys[i];
+    out.locs[d][o] = locs[i];
   }
 }
 
@@ -982,7 +1013,11 @@ BucketIndex build_bucket_index(Context* c, const uint64_t* keys, uint32_t n, Dev
   if (const char* e = getenv("BGX_INDEX_BITS")) bits = std::max(1, std::min(28, atoi(e)));  // experiment hook
   const uint32_t nb = 1u << bits;
   buf.alloc((size_t)nb + 1, s);
-  KLAUNCH(bucket_index_kernel)<<<grid_for((uint64_t)n + 1, 256), 256, 0, s>>>(keys, n, 64 - bits, nb, buf.p);
+  DevBuf<Gap> gaps(kGapList, s);
+  DevBuf<unsigned int> n_gaps(1, s);
+  BGX_CUDA(cudaMemsetAsync(n_gaps.p, 0, sizeof(unsigned int), s));
+  KLAUNCH(bucket_index_kernel)<<<grid_for((uint64_t)n + 1, 256), 256, 0, s>>>(keys, n, 64 - bits, nb, buf.p, gaps.p, n_gaps.p);
+  KLAUNCH(gap_fill_kernel)<<<kNumSMs * 4, 256, 0, s>>>(gaps.p, n_gaps.p, buf.p);
   BGX_CUDA(cudaGetLastError());
   return BucketIndex{buf.p, 64 - bits};
 }
@@ -1306,13 +1341,6 @@ Routed route_records(Context* c, const uint64_t* keys, const uint64_t* locs, uin
     uint64_t o = 0;
     for (int r = 0; r < N; ++r) { send_cnt[r] = h[r]; send_off[r] = o; o += h[r]; }
   }
-  DevBuf<uint64_t> skeys(std::max<uint32_t>(n, 1), s), slocs(std::max<uint32_t>(n, 1), s);
-  {
-    std::vector<unsigned long long> cur(send_off.begin(), send_off.end());
-    BGX_CUDA(cudaMemcpyAsync(counts.p, cur.data(), N * 8, cudaMemcpyHostToDevice, s));
-    if (n) KLAUNCH(route_scatter_kernel)<<<grid_for(n, 256), 256, 0, s>>>(keys, locs, dest.p, n, N, counts.p, skeys.p, slocs.p);
-    BGX_CUDA(cudaGetLastError());
-  }
   st_k.stop();
   ScopedStage st_x(c, "route_exchange");
   dist_allgather_host_u64(c, send_cnt.data(), N, all.data());
@@ -1323,9 +1351,32 @@ Routed route_records(Context* c, const uint64_t* keys, const uint64_t* locs, uin
   out.n = (uint32_t)m;
   out.keys.alloc(m + 1024, s);  // slack: the sort / dedup ping-pong buffers are sized alike
   out.locs.alloc(m + 1024, s);
-  dist_alltoallv(c, skeys.p, send_off.data(), send_cnt.data(), out.keys.p, recv_off.data(), recv_cnt.data(), 8);
-  dist_alltoallv(c, slocs.p, send_off.data(), send_cnt.data(), out.locs.p, recv_off.data(), recv_cnt.data(), 8);
-  BGX_CUDA(cudaStreamSynchronize(s));  // the send buffers die with this scope
+  BGX_CUDA(cudaMemsetAsync(counts.p, 0, kMaxRanks * 8, s));   // the scatter's cursors
+  RouteOut ro;
+  if (dist_direct_exchange()) {
+    // the scatter stores every record straight into its owner's receive buffer over NVLink: this rank's
+    // records start where the ranks before it end (the count matrix is known to everyone)
+    void* local[2] = {out.keys.p, out.locs.p};
+    void* peer[2 * kMaxRanks];
+    dist_map_peers_n(c, local, 2, peer);   // also: every owner's buffers are allocated
+    for (int d = 0; d < N; ++d) {
+      uint64_t off = 0;
+      for (int src = 0; src < R; ++src) off += all[(size_t)src * N + d];
+      ro.keys[d] = static_cast<uint64_t*>(peer[d]) + off;
+      ro.locs[d] = static_cast<uint64_t*>(peer[N + d]) + off;
+    }
+    if (n) KLAUNCH(route_scatter_kernel)<<<grid_for(n, 256), 256, 0, s>>>(keys, locs, dest.p, n, N, counts.p, ro);
+    BGX_CUDA(cudaGetLastError());
+    dist_barrier(c);   // every rank's stores have landed
+  } else {
+    DevBuf<uint64_t> skeys(std::max<uint32_t>(n, 1), s), slocs(std::max<uint32_t>(n, 1), s);
+    for (int d = 0; d < N; ++d) { ro.keys[d] = skeys.p + send_off[d]; ro.locs[d] = slocs.p + send_off[d]; }
+    if (n) KLAUNCH(route_scatter_kernel)<<<grid_for(n, 256), 256, 0, s>>>(keys, locs, dest.p, n, N, counts.p, ro);
+    BGX_CUDA(cudaGetLastError());
+    dist_alltoallv(c, skeys.p, send_off.data(), send_cnt.data(), out.keys.p, recv_off.data(), recv_cnt.data(), 8);
+    dist_alltoallv(c, slocs.p, send_off.data(), send_cnt.data(), out.locs.p, recv_off.data(), recv_cnt.data(), 8);
+    BGX_CUDA(cudaStreamSynchronize(s));  // the send buffers die with this scope
+  }
   st_x.stop();
   c->add_stat("route_records_out", (double)n - (double)send_cnt[R]);
   c->add_stat("route_bytes_out", 16.0 * ((double)n - (double)send_cnt[R]));

@@ -105,6 +105,11 @@ int bgx_count_kmers(bgx_ctx* ctx);
 int bgx_export_kmers(bgx_ctx* ctx, uint32_t min_count, uint64_t* n, uint64_t** kmers,
                      uint32_t** fwd_counts, uint32_t** rev_counts, uint8_t** flags);
 
+/* The resident reads back as ASCII ('N' where the mask says so), in append order, concatenated;
+ * lens[r] = length of read r.  Serves the facade's correct(const unaligned_read&, corrected_read&)
+ * (bs/correct_reads.h:14-22), which answers per read by sequence.  Arrays are bgx_free()'d by the caller. */
+int bgx_export_reads(bgx_ctx* ctx, uint64_t* n_reads, uint16_t** lens, char** bases, uint64_t* n_bases);
+
 /* replaces: correct_reads::correct over all reads (bs/correct_reads.cpp:154-231) including
  * fast_read_correct (modules/bio_base/fast_read_correct.cpp) and the seed counts. */
 int bgx_correct(bgx_ctx* ctx);

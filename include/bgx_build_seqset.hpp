@@ -37,6 +37,7 @@
 #include <mutex>
 #include <stdexcept>
 #include <string>
+#include <unordered_map>
 #include <utility>
 #include <vector>
 
@@ -148,7 +149,11 @@ class kmer_counter {
     explicit prob_pass_processor(kmer_counter& k, size_t batch_bases = size_t(64) << 20) : m_k(k), m_batch(batch_bases) {
       m_offs.push_back(0);
     }
-    ~prob_pass_processor() { flush_all(); }
+    // a destructor must not throw (an append error here would be std::terminate): callers that care
+    // flush explicitly first, as seqset_for_reads and bgx-create do (bs/kmer_counter.cpp:214-223)
+    ~prob_pass_processor() {
+      try { flush_all(); } catch (...) {}
+    }
     void add(const char* seq, size_t len) {  // the reference takes a string_view
       m_bases.append(seq, len);
       m_offs.push_back(m_bases.size());
@@ -240,10 +245,66 @@ inline std::unique_ptr<kmer_set> run_kmerize_subtask(kmer_counter* counter, prog
   return ks;
 }
 
+// The reference's own signature (modules/bio_mapred/kmerize_bf.h:81-84):
+//   pair<unique_ptr<kmer_set>, vector<manifest>> run_kmerize_subtask(kmerize_bf_params, manifest reads,
+//                                                                    kmer_counter*, progress)
+// The reads are already resident (they arrived through prob_pass_processor::add), so the reads manifest
+// is only carried along; the three result manifests -- k-mer counts, count histogram, overrepresented
+// k-mers (kmerize_bf.cpp:444-473) -- come back as in-memory tables.
+struct kmerize_bf_params {             // modules/bio_mapred/kmerize_bf.h:8-48 (fields that reach this path)
+  size_t kmer_size = 0;
+  size_t min_count = 4;
+  size_t ref_size = 0, memory_bound = 0, num_threads = 0;
+  float skew_cutoff = 0.0f;            // 0.0: the skew filter is off (kmerize_bf.h:38)
+  size_t overrep = 0;                  // 0: overrepresentation filtering is off
+};
+struct manifest {                      // modules/io/manifest.h, reduced to what the stage hands on
+  std::string tag;
+  size_t num_records = 0;
+  std::vector<std::pair<uint64_t, uint64_t>> records;   // histogram: (count, number of k-mers)
+};
+inline std::pair<std::unique_ptr<kmer_set>, std::vector<manifest>> run_kmerize_subtask(
+    const kmerize_bf_params& params, const manifest& /*reads*/, kmer_counter* counter,
+    progress_handler_t progress = null_progress_handler) {
+  if (params.kmer_size && params.kmer_size != counter->sess().kmer_options().kmer_size)
+    throw io_exception("run_kmerize_subtask: kmer_size differs from the counter's");
+  if (params.min_count != counter->sess().kmer_options().min_count)
+    throw io_exception("run_kmerize_subtask: min_count differs from the counter's");
+  std::unique_ptr<kmer_set> ks = run_kmerize_subtask(counter, progress);
+  manifest counts, hist, overrep;
+  counts.tag = "kmers";
+  counts.num_records = ks->size();
+  hist.tag = "kmer_histogram";
+  overrep.tag = "overrep";
+  // the histogram of fwd + rev over the k-mers that passed (kmer_quality_report.html's input)
+  std::vector<uint64_t> h;
+  counter->extract_exact_counts(
+      [&](const kmer_counter::element* b, const kmer_counter::element* e) {
+        for (; b != e; ++b) {
+          const uint64_t t = (uint64_t)b->fwd_count + b->rev_count;
+          if (t >= h.size()) h.resize(std::min<uint64_t>(t, 1u << 20) + 1);
+          ++h[std::min<uint64_t>(t, h.size() - 1)];
+        }
+      },
+      (uint32_t)params.min_count);
+  for (uint64_t c = 0; c < h.size(); ++c)
+    if (h[c]) hist.records.emplace_back(c, h[c]);
+  hist.num_records = hist.records.size();
+  std::vector<manifest> out;
+  out.push_back(std::move(counts));
+  out.push_back(std::move(hist));
+  out.push_back(std::move(overrep));
+  return std::make_pair(std::move(ks), std::move(out));
+}
+
 // ---- read correction ------------------------------------------------------------------------------------
 struct corrected_read {  // modules/bio_base/corrected_read.h (fields this path fills)
   std::string corrected;   // empty = read dropped
   unsigned corrections = 0;
+};
+struct unaligned_read {  // modules/bio_base/unaligned_read.h:26-49 (the field correction reads)
+  int pair_number = 0;
+  std::string sequence;
 };
 
 class correct_reads {
@@ -267,19 +328,50 @@ class correct_reads {
     bgx_free(lens); bgx_free(bases); bgx_free(corr);
   }
   size_t size() const { return m_lens.size(); }
-  // bool correct(const unaligned_read&, corrected_read&) by read index: false = dropped
+  unsigned corrected_length(size_t read_index) const { return m_lens[read_index]; }   // 0 = dropped
+  // the result of resident read number read_index (append order): false = dropped
   bool correct(size_t read_index, corrected_read& cr) const {
     cr.corrected.assign(m_bases.data() + m_offs[read_index], m_lens[read_index]);
     cr.corrections = m_corr[read_index];
     return m_lens[read_index] != 0;
   }
+  // The reference's own signature (bs/correct_reads.h:14-22): thread-safe, called from a parallel_for
+  // over the read files (biograph_create.cpp:858-903).  Correction is a pure function of the read's
+  // bases (given the k-mer set and the parameters), so the answer for `r` is the answer of the resident
+  // read with the same sequence: the first call runs correct_all() if nobody has, and indexes the
+  // resident reads by sequence.  A read that was never added throws.
+  bool correct(const unaligned_read& r, corrected_read& cr) {
+    {
+      std::lock_guard<std::mutex> l(m_mu);
+      if (m_lens.empty()) correct_all();
+      if (m_by_seq.empty() && !m_lens.empty()) index_inputs();
+    }
+    auto it = m_by_seq.find(r.sequence);
+    if (it == m_by_seq.end()) throw io_exception("correct_reads::correct: read was not added to the k-mer counter");
+    return correct(it->second, cr);
+  }
 
  private:
+  void index_inputs() {
+    uint64_t n = 0, nb = 0;
+    uint16_t* lens = nullptr;
+    char* bases = nullptr;
+    detail::ck(bgx_export_reads(m_s.ctx(), &n, &lens, &bases, &nb));
+    uint64_t off = 0;
+    for (uint64_t i = 0; i < n; ++i) {
+      m_by_seq.emplace(std::string(bases + off, lens[i]), (size_t)i);
+      off += lens[i];
+    }
+    bgx_free(lens);
+    bgx_free(bases);
+  }
   session& m_s;
+  std::mutex m_mu;
   std::vector<uint16_t> m_lens;
   std::vector<uint8_t> m_corr;
   std::vector<uint64_t> m_offs;
   std::string m_bases;
+  std::unordered_map<std::string, size_t> m_by_seq;
 };
 
 // ---- expand / sort / dedup ---------------------------------------------------------------------------------
@@ -482,8 +574,9 @@ class builder {
     detail::ck(bgx_export_varbit(m_s.ctx(), 1, &t.shared_elements.p, &t.shared_elements.n, &t.shared_bits, &t.shared_max));
     return t;
   }
-  // writes the seqset spiral file; returns the tables it wrote
-  seqset_tables make_seqset(const std::string& path, progress_handler_t progress = null_progress_handler) {
+  // writes the seqset spiral file (uuid: file_info.json's, the BioGraph id); returns the tables it wrote
+  seqset_tables make_seqset(const std::string& path, progress_handler_t progress = null_progress_handler,
+                            const std::string& uuid = "") {
     seqset_tables t = tables();
     seqset_file_writer w(path);
     char ts[64];
@@ -492,7 +585,7 @@ class builder {
     w.add("file_info.json", std::string("{\"build_host\":\"bgx\",\"build_is_clean\":true,\"build_revision\":\"") + bgx_version() +
                                 "\",\"build_timestamp\":0,\"build_timestamp_text\":\"\",\"build_user\":\"\",\"command_line\":[],"
                                 "\"create_timestamp\":" + std::to_string((long long)now) + ",\"create_timestamp_text\":\"" + ts +
-                                "\",\"uuid\":\"\"}");
+                                "\",\"uuid\":\"" + uuid + "\"}");
     w.add("part_info.json", part_info("seqset", 1, 1, 0));  // seqset::seqset_version 1.1.0 (seqset.cpp:12)
     w.add("seqset.json", "{\"num_entries\":" + std::to_string(t.num_entries) + "}");
     w.add("fixed", t.fixed, sizeof(t.fixed));

@@ -156,7 +156,7 @@ def test_synthetic_full_path(B, glen, n, L, err, nrate, seed):
 
 
 @pytest.mark.parametrize("k,min_count,maxc,run,trim", [(16, 2, 2, 2, 0.5), (21, 3, 4, 1, 0.7), (31, 5, 8, 3, 0.9),
-                                                        (30, 5, 0, 2, 1.0), (25, 4, 16, 2, 0.0)])
+                                                        (30, 5, 0, 2, 1.0), (25, 4, 16, 2, 0.0), (30, 3, 32, 1, 0.0)])
 def test_parameter_sweep(B, k, min_count, maxc, run, trim):
     full_compare(B, _sim(8000, 4000, 120, 0.01, 40 + k, n_rate=0.001), k=k, min_count=min_count, max_corrections=maxc,
                  min_good_run=run, trim=trim)
