@@ -335,6 +335,7 @@ int bgx_stats_json(bgx_ctx* x, char* buf, size_t cap) {
     os.precision(17);
     os << "{\"n_reads\":" << c->n_reads << ",\"n_bases\":" << c->n_bases << ",\"has_n\":" << (c->has_n ? "true" : "false");
     for (const auto& k : c->stat_order) os << ",\"" << k << "\":" << c->stats[k];
+    os << ",\"peak_device_bytes\":" << dev_peak_bytes(false) << ",\"live_device_bytes\":" << dev_live_bytes();
     os << "}";
     std::string sjson = os.str();
     BGX_CHECK(sjson.size() + 1 <= cap, "bgx_stats_json: buffer too small");

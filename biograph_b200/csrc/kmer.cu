@@ -510,7 +510,7 @@ __global__ void __launch_bounds__(THREADS) kmer_count_bins_kernel(const unsigned
     const unsigned long long b = blk_solid ? atomicAdd(&counters[1], (unsigned long long)blk_solid) : 0ULL;
     base_all = a;
     base_solid = b;
-    if (a + blk_used > cap_all || (blk_solid && b + blk_solid > cap_solid)) *overflow = 2;
+    if ((cap_all && a + blk_used > cap_all) || (blk_solid && b + blk_solid > cap_solid)) *overflow = 2;
   }
   __syncthreads();
   const unsigned long long ba = base_all, bs = base_solid;
@@ -1099,6 +1099,9 @@ uint64_t choose_batches(Context* c, uint64_t K_local, uint64_t K_share) {
     const double need = 9.0 * (double)K_local + (N > 1 ? 9.0 : 0.0) * (double)K_share + 8.0 * (double)K_share;
     batches = std::max<uint64_t>(1, (uint64_t)std::ceil(need / budget));
   }
+  // ... and so that one rank counts at most ~1.2 G instances per batch: with the usual ~1/5 of them
+  // distinct that is what 2^17 sub-bins of 2 k distinct k-mers hold (128 partitions x 1024 sub-bins)
+  if (!batch_reads) batches = std::max<uint64_t>(batches, (K_share + (1200ull << 20) - 1) / (1200ull << 20));
   if (N > 1) {
     std::vector<uint64_t> all(N);
     dist_allgather_host_u64(c, &batches, 1, all.data());
@@ -1156,6 +1159,9 @@ void stage_count_kmers(Context* c) {
   int c_log2 = 12;  // 4096 slots = 64 KB of shared memory per block, three blocks per SM
   if (const char* e = getenv("BGX_BIN_SLOTS_LOG2")) c_log2 = std::max(9, std::min(13, atoi(e)));  // experiment hook
 
+  // The per-k-mer counts of ALL distinct k-mers (bgx_export_kmers below min_count) are kept when the
+  // counting is one batch, or small; a big batched count only keeps the solid k-mers.
+  const bool keep_all = batches == 1 || 16.0 * (double)K_share < 0.05 * (double)c->total_mem;
   DevBuf<int> overflow(1, s);
   std::vector<BatchOut> outs(batches);
   uint64_t n_inst = 0, total_all = 0, total_solid = 0;
@@ -1235,9 +1241,10 @@ void stage_count_kmers(Context* c) {
       c->set_stat("count_largest_bin", (double)h_scal[1]);
 
       ScopedStage st(c, "count_kernel");
-      const uint64_t cap_all = est_distinct + est_distinct / 8 + 65536;
-      const uint64_t cap_solid = std::min<uint64_t>(cap_all, own.n_inst / (uint64_t)c->opt.min_kmer_count + 1);
-      bo.all.alloc(cap_all, s);
+      const uint64_t cap_est = est_distinct + est_distinct / 8 + 65536;
+      const uint64_t cap_all = keep_all ? cap_est : 0;   // 0: the distinct list is not written
+      const uint64_t cap_solid = std::min<uint64_t>(cap_est, own.n_inst / (uint64_t)c->opt.min_kmer_count + 1);
+      bo.all.alloc(std::max<uint64_t>(cap_all, 1), s);
       bo.solid.alloc(cap_solid, s);
       DevBuf<unsigned long long> counters(2, s);
       BGX_CUDA(cudaMemsetAsync(counters.p, 0, 16, s));
@@ -1292,8 +1299,6 @@ void stage_count_kmers(Context* c) {
       c->table = std::move(outs[0].all);
       solid_list = std::move(outs[0].solid);
     } else {
-      // huge inputs do not keep the per-k-mer counts (bgx_export_kmers then refuses)
-      const bool keep_all = (double)total_all * 16.0 < 0.2 * (double)c->total_mem;
       if (keep_all) c->table.alloc(std::max<uint64_t>(total_all, 1), s);
       solid_list.alloc(std::max<uint64_t>(total_solid, 1), s);
       uint64_t oa = 0, os = 0;

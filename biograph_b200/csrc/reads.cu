@@ -333,7 +333,7 @@ void reads_append_packed(Context* c, const uint8_t* packed, const uint32_t* n_ma
   // lengths go straight to the device; word offsets, totals and the length check are computed there
   grow(c->word_off, c->n_reads + (c->n_reads ? 1 : 0), c->n_reads + n + 1, s);
   grow(c->lens, c->n_reads, c->n_reads + n, s);
-  BGX_CUDA(cudaMemcpyAsync(c->lens.p + c->n_reads, lens_in, n * sizeof(uint16_t), cudaMemcpyHostToDevice, s));
+  BGX_CUDA(cudaMemcpyAsync(c->lens.p + c->n_reads, lens_in, n * sizeof(uint16_t), cudaMemcpyDefault, s));
   DevBuf<uint32_t> nwords(n + 1, s);
   DevBuf<unsigned long long> tot(5, s);
   BGX_CUDA(cudaMemsetAsync(tot.p, 0, 5 * 8, s));
@@ -373,7 +373,7 @@ void reads_append_packed(Context* c, const uint8_t* packed, const uint32_t* n_ma
       const uint64_t w0 = h_bound[j], w1 = h_bound[j + 1];
       if (w1 > w0) {
         BGX_CUDA(cudaMemcpyAsync(c->words.p + words_before + w0, packed + 8 * (src_word0 + w0), (w1 - w0) * 8,
-                                 cudaMemcpyHostToDevice, cs));
+                                 cudaMemcpyDefault, cs));
         KLAUNCH(bswap_words_kernel)<<<(unsigned)((w1 - w0 + 255) / 256), 256, 0, cs>>>(c->words.p + words_before + w0, w1 - w0);
       }
       if (j == kChunks - 1) BGX_CUDA(cudaMemsetAsync(c->words.p + words_before + new_words, 0, sizeof(uint64_t), cs));
@@ -386,10 +386,10 @@ void reads_append_packed(Context* c, const uint8_t* packed, const uint32_t* n_ma
     }
     BGX_CUDA(cudaGetLastError());
   } else {
-  BGX_CUDA(cudaMemcpyAsync(c->words.p + words_before, packed + 8 * src_word0, new_words * 8, cudaMemcpyHostToDevice, s));
+  BGX_CUDA(cudaMemcpyAsync(c->words.p + words_before, packed + 8 * src_word0, new_words * 8, cudaMemcpyDefault, s));
   if (new_words) KLAUNCH(bswap_words_kernel)<<<(unsigned)((new_words + 255) / 256), 256, 0, s>>>(c->words.p + words_before, new_words);
   if (n_mask) {
-    BGX_CUDA(cudaMemcpyAsync(c->nmask.p + words_before, n_mask + src_word0, new_words * 4, cudaMemcpyHostToDevice, s));
+    BGX_CUDA(cudaMemcpyAsync(c->nmask.p + words_before, n_mask + src_word0, new_words * 4, cudaMemcpyDefault, s));
     if (new_words) KLAUNCH(any_nonzero_kernel)<<<(unsigned)((new_words + 255) / 256), 256, 0, s>>>(c->nmask.p + words_before, new_words, d_flag.p);
   } else {
     BGX_CUDA(cudaMemsetAsync(c->nmask.p + words_before, 0, new_words * 4, s));

@@ -370,11 +370,13 @@ __global__ void dedup_flag_kernel(const uint64_t* __restrict__ store, const uint
 // is as slow as its slowest probe chain and holds up the look-back of the tiles behind it.
 __global__ void compact_pairs_kernel(const uint64_t* __restrict__ keys, const uint64_t* __restrict__ locs,
                                      const uint32_t* __restrict__ keep, const uint32_t* __restrict__ pos, uint32_t n,
-                                     uint64_t* __restrict__ okeys, uint64_t* __restrict__ olocs) {
+                                     uint64_t* __restrict__ okeys, uint64_t* __restrict__ olocs,
+                                     const uint32_t* __restrict__ org_in, uint32_t* __restrict__ org_out) {
   uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n || !keep[i]) return;
   okeys[pos[i]] = keys[i];
   olocs[pos[i]] = locs[i];
+  if (org_out != nullptr) org_out[pos[i]] = org_in != nullptr ? org_in[i] : i;
 }
 
 // ---- closure walk ------------------------------------------------------------------------------------
@@ -392,16 +394,22 @@ __device__ __forceinline__ bool covered(const uint64_t* __restrict__ store, cons
 }
 
 // phase 1: one thread per entry; entries whose pop_front is not covered start a chain
+// where1[i] = the first entry that has pop_front(entry i) as a prefix (kNoWhere when none does): the
+// tables step re-bases it through the merge and dedup maps instead of searching again.
+constexpr uint32_t kNoWhere = 0xffffffffu;
 __global__ void __launch_bounds__(128) walk_phase1_kernel(const uint64_t* __restrict__ store,
                                                           const uint64_t* __restrict__ keys,
                                                           const uint64_t* __restrict__ locs, uint32_t n,
                                                           BucketIndex bi, uint32_t* __restrict__ chains,
-                                                          unsigned long long* __restrict__ n_chains) {
+                                                          unsigned long long* __restrict__ n_chains,
+                                                          uint32_t* __restrict__ where1) {
   uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
   bool start = false;
   if (i < n) {
     uint64_t l = locs[i];
-    start = !covered(store, keys, locs, n, bi, loc_addr(l) + 1, (int)loc_len(l) - 1, nullptr);
+    uint32_t where;
+    start = !covered(store, keys, locs, n, bi, loc_addr(l) + 1, (int)loc_len(l) - 1, &where);
+    where1[i] = start ? kNoWhere : where;
   }
   unsigned mask = __ballot_sync(0xffffffffu, start);
   if (!mask) return;
@@ -632,29 +640,51 @@ __global__ void merge_rank_kernel(const uint64_t* __restrict__ store, const uint
 // old record i moves behind the new records ranked <= i: shift = exclusive_scan(marks)[i + 1]
 __global__ void merge_scatter_old_kernel(const uint64_t* __restrict__ okeys, const uint64_t* __restrict__ olocs,
                                          uint32_t n_old, const uint32_t* __restrict__ marks_excl,
-                                         uint64_t* __restrict__ out_keys, uint64_t* __restrict__ out_locs) {
+                                         uint64_t* __restrict__ out_keys, uint64_t* __restrict__ out_locs,
+                                         uint32_t* __restrict__ org /*optional: merged position -> old index*/) {
   uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n_old) return;
   uint32_t d = i + marks_excl[i + 1];
   out_keys[d] = okeys[i];
   out_locs[d] = olocs[i];
+  if (org != nullptr) org[d] = i;
 }
 
 __global__ void merge_scatter_new_kernel(const uint64_t* __restrict__ nkeys, const uint64_t* __restrict__ nlocs,
                                          uint32_t n_new, const uint32_t* __restrict__ rank,
-                                         uint64_t* __restrict__ out_keys, uint64_t* __restrict__ out_locs) {
+                                         uint64_t* __restrict__ out_keys, uint64_t* __restrict__ out_locs,
+                                         uint32_t* __restrict__ org /*optional: kNoWhere marks a new record*/) {
   uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
   if (j >= n_new) return;
   uint32_t d = rank[j] + j;
   out_keys[d] = nkeys[j];
   out_locs[d] = nlocs[j];
+  if (org != nullptr) org[d] = kNoWhere;
 }
 
 // ---- tables ---------------------------------------------------------------------------------------------
+// The prev-bit target of entry i is the first entry that has pop_front(entry i) as a prefix.  The
+// closure walk already found it for every round-1 entry (where1, an index into the round-1 array);
+// `Reuse` carries that answer into the final array instead of searching again:
+//   round-1 index w -> merged index w + (new records merged in before old w); the new records that
+//   sort between the popped sequence x and old w were merged in right in front of old w and all have
+//   x as a prefix too (anything between x and a sequence starting with x starts with x), so among them
+//   the target is the first one not less than x; dropped records (dedup) are prefixes of their
+//   successors, so the target moves on to the next kept one: pos[.].
+// Entries that came out of the walk itself, and round-1 entries whose pop_front had no cover then,
+// are searched as before.  With no reuse data (org == nullptr) every entry is searched.
+struct Reuse {
+  const uint32_t* org;         // final index -> round-1 index, kNoWhere for a walk record
+  const uint32_t* where1;      // round-1 index -> round-1 index of the cover, kNoWhere if none
+  const uint32_t* marks_excl;  // [r + 1] = new records merged in before old r (inclusive of those right in front); nullptr: no merge
+  const uint32_t* pos;         // merged index -> final index of the first kept record at or after it; nullptr: no dedup
+  const uint64_t* mkeys;       // the merged (pre-dedup) records
+  const uint64_t* mlocs;
+};
 __global__ void __launch_bounds__(128) tables_kernel(const uint64_t* __restrict__ store,
                                                      const uint64_t* __restrict__ keys,
                                                      const uint64_t* __restrict__ locs, uint32_t n, BucketIndex bi,
-                                                     uint16_t* __restrict__ sizes, uint16_t* __restrict__ shared,
+                                                     Reuse ru, uint16_t* __restrict__ sizes, uint16_t* __restrict__ shared,
                                                      unsigned long long* __restrict__ prev_bits, uint64_t prev_words,
                                                      unsigned int* __restrict__ max_len, int* __restrict__ missing) {
   uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -675,8 +705,27 @@ __global__ void __launch_bounds__(128) tables_kernel(const uint64_t* __restrict_
     }
     shared[i] = (uint16_t)lcp;
     // prev bit: first entry having pop_front(e) as a prefix (bs/builder.cpp:85-107)
-    uint32_t where;
-    bool cov = covered(store, keys, locs, n, bi, loc_addr(l) + 1, (int)len - 1, &where);
+    uint32_t where = kNoWhere;
+    if (ru.org != nullptr && len > 1) {
+      const uint32_t o = ru.org[i];
+      const uint32_t w = o == kNoWhere ? kNoWhere : ru.where1[o];
+      if (w != kNoWhere) {
+        uint32_t wm = w;
+        if (ru.marks_excl != nullptr) {
+          const uint32_t before = ru.marks_excl[w + 1], run = before - ru.marks_excl[w];
+          wm = w + before;
+          if (run) {
+            // new records right in front of the old cover: the first one not less than x wins
+            const uint64_t xa = loc_addr(l) + 1;
+            const uint64_t xk = suffix_key(store, xa, (int)len - 1), xl = make_loc(xa, len - 1);
+            wm = lower_bound_rec(store, ru.mkeys, ru.mlocs, wm - run, wm, xk, xl);
+          }
+        }
+        where = ru.pos != nullptr ? ru.pos[wm] : wm;
+      }
+    }
+    bool cov = where != kNoWhere;
+    if (!cov) cov = covered(store, keys, locs, n, bi, loc_addr(l) + 1, (int)len - 1, &where);
     if (!cov) {
       *missing = 1;  // LOG(FATAL) << "Missing expansion?" (bs/builder.cpp:96)
     } else {
@@ -989,6 +1038,11 @@ __global__ void varbit_pack_kernel(const uint16_t* __restrict__ vals, uint64_t n
   out[w] = acc;
 }
 
+__global__ void iota_u32_kernel(uint32_t* __restrict__ out, uint32_t n) {
+  uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) out[i] = i;
+}
+
 inline unsigned grid_for(uint64_t n, unsigned block) { return (unsigned)std::max<uint64_t>(1, (n + block - 1) / block); }
 
 uint32_t read_u32(const uint32_t* d, cudaStream_t s) {
@@ -1121,18 +1175,24 @@ void sort_records(Context* c, DevBuf<uint64_t>& keys, DevBuf<uint64_t>& locs, De
 // drop every record that is a prefix of / equal to its successor; returns the survivor count and
 // leaves them in (keys, locs) (buffers are swapped with the alt ones).
 uint32_t dedup_records(Context* c, DevBuf<uint64_t>& keys, DevBuf<uint64_t>& locs, DevBuf<uint64_t>& keys_alt,
-                       DevBuf<uint64_t>& locs_alt, uint32_t n, NextRec next = NextRec{0, 0, 0}) {
+                       DevBuf<uint64_t>& locs_alt, uint32_t n, NextRec next = NextRec{0, 0, 0},
+                       DevBuf<uint32_t>* org = nullptr /*in/out: origin of every record*/,
+                       DevBuf<uint32_t>* pos_out = nullptr /*out: record -> index of the first survivor at or after it*/) {
   cudaStream_t s = c->stream;
   if (n == 0) return 0;
   ScopedStage st(c, "dedup");
-  DevBuf<uint32_t> keep(n, s), pos(n, s), tot(1, s);
+  DevBuf<uint32_t> keep(n, s), pos(n, s), tot(1, s), org2;
+  if (org != nullptr) org2.alloc(n, s);
   KLAUNCH(dedup_flag_kernel)<<<grid_for(n, 256), 256, 0, s>>>(c->seq_store(), keys.p, locs.p, n, next, keep.p);
   exclusive_scan_u32(keep.p, pos.p, n, tot.p, s);
-  KLAUNCH(compact_pairs_kernel)<<<grid_for(n, 256), 256, 0, s>>>(keys.p, locs.p, keep.p, pos.p, n, keys_alt.p, locs_alt.p);
+  KLAUNCH(compact_pairs_kernel)<<<grid_for(n, 256), 256, 0, s>>>(keys.p, locs.p, keep.p, pos.p, n, keys_alt.p, locs_alt.p,
+                                                         org != nullptr ? org->p : nullptr, org != nullptr ? org2.p : nullptr);
   BGX_CUDA(cudaGetLastError());
   uint32_t m = read_u32(tot.p, s);
   std::swap(keys, keys_alt);
   std::swap(locs, locs_alt);
+  if (org != nullptr) *org = std::move(org2);
+  if (pos_out != nullptr) *pos_out = std::move(pos);
   c->add_stat("alg_bytes_dedup", 16.0 * n + 16.0 * m);
   st.stop();
   return m;
@@ -1142,7 +1202,8 @@ uint32_t dedup_records(Context* c, DevBuf<uint64_t>& keys, DevBuf<uint64_t>& loc
 // (n1 + n_new records) ends in (keys, locs); the alt buffers are grown to hold as many.
 void merge_new_records(Context* c, DevBuf<uint64_t>& keys, DevBuf<uint64_t>& locs, DevBuf<uint64_t>& keys_alt,
                        DevBuf<uint64_t>& locs_alt, uint32_t n1, const BucketIndex& bi, const DevBuf<uint64_t>& nkeys,
-                       const DevBuf<uint64_t>& nlocs, uint32_t n_new) {
+                       const DevBuf<uint64_t>& nlocs, uint32_t n_new, DevBuf<uint32_t>* marks_out = nullptr,
+                       DevBuf<uint32_t>* org_out = nullptr) {
   cudaStream_t s = c->stream;
   const uint32_t nm = n1 + n_new;
   ScopedStage st(c, "merge");
@@ -1155,9 +1216,12 @@ void merge_new_records(Context* c, DevBuf<uint64_t>& keys, DevBuf<uint64_t>& loc
   KLAUNCH(merge_rank_kernel)<<<grid_for(n_new, 128), 128, 0, s>>>(c->seq_store(), keys.p, locs.p, n1, bi, nkeys.p, nlocs.p, n_new,
                                                          rank.p, marks.p);
   exclusive_scan_u32(marks.p, marks.p, (size_t)n1 + 2, nullptr, s);
-  if (n1) KLAUNCH(merge_scatter_old_kernel)<<<grid_for(n1, 256), 256, 0, s>>>(keys.p, locs.p, n1, marks.p, keys_alt.p, locs_alt.p);
-  KLAUNCH(merge_scatter_new_kernel)<<<grid_for(n_new, 256), 256, 0, s>>>(nkeys.p, nlocs.p, n_new, rank.p, keys_alt.p, locs_alt.p);
+  if (org_out != nullptr) org_out->alloc(nm, s);
+  uint32_t* org = org_out != nullptr ? org_out->p : nullptr;
+  if (n1) KLAUNCH(merge_scatter_old_kernel)<<<grid_for(n1, 256), 256, 0, s>>>(keys.p, locs.p, n1, marks.p, keys_alt.p, locs_alt.p, org);
+  KLAUNCH(merge_scatter_new_kernel)<<<grid_for(n_new, 256), 256, 0, s>>>(nkeys.p, nlocs.p, n_new, rank.p, keys_alt.p, locs_alt.p, org);
   BGX_CUDA(cudaGetLastError());
+  if (marks_out != nullptr) *marks_out = std::move(marks);
   std::swap(keys, keys_alt);
   std::swap(locs, locs_alt);
   if ((size_t)nm > keys_alt.n) {  // dedup writes into the alt buffers
@@ -1213,6 +1277,7 @@ void stage_build_seqset(Context* c) {
   uint32_t n_new = 0;
   DevBuf<uint64_t> nkeys, nlocs;
   DevBuf<uint32_t> index_buf;
+  DevBuf<uint32_t> where1, marks_excl, org, pos2;   // the walk's answers and the maps that re-base them (tables_kernel)
   BucketIndex bi1;
   {
     ScopedStage st(c, "walk");
@@ -1220,7 +1285,9 @@ void stage_build_seqset(Context* c) {
     DevBuf<uint32_t> chains(std::max<uint32_t>(n1, 1), s);
     DevBuf<unsigned long long> n_chains_d(1, s);
     BGX_CUDA(cudaMemsetAsync(n_chains_d.p, 0, 8, s));
-    KLAUNCH(walk_phase1_kernel)<<<grid_for(n1, 128), 128, 0, s>>>(c->store.p, keys.p, locs.p, n1, bi1, chains.p, n_chains_d.p);
+    where1.alloc(std::max<uint32_t>(n1, 1), s);
+    KLAUNCH(walk_phase1_kernel)<<<grid_for(n1, 128), 128, 0, s>>>(c->store.p, keys.p, locs.p, n1, bi1, chains.p, n_chains_d.p,
+                                                          where1.p);
     BGX_CUDA(cudaGetLastError());
     uint32_t n_chains = (uint32_t)read_u64(n_chains_d.p, s);
     c->set_stat("walk_chains", n_chains);
@@ -1250,8 +1317,8 @@ void stage_build_seqset(Context* c) {
       sort_records(c, nkeys, nlocs, nkeys_alt, nlocs_alt, n_new, "r2");
     }
     const uint32_t nm = n1 + n_new;
-    merge_new_records(c, keys, locs, keys_alt, locs_alt, n1, bi1, nkeys, nlocs, n_new);
-    n2 = dedup_records(c, keys, locs, keys_alt, locs_alt, nm);
+    merge_new_records(c, keys, locs, keys_alt, locs_alt, n1, bi1, nkeys, nlocs, n_new, &marks_excl, &org);
+    n2 = dedup_records(c, keys, locs, keys_alt, locs_alt, nm, NextRec{0, 0, 0}, &org, &pos2);
   }
   c->n_entries = n2;
   c->n_entries_global = n2;
@@ -1278,7 +1345,18 @@ void stage_build_seqset(Context* c) {
     BGX_CUDA(cudaMemsetAsync(missing.p, 0, 4, s));
     if (nb) {
       const BucketIndex bi2 = n2 == n1 && n_new == 0 ? bi1 : build_bucket_index(c, keys.p, n2, index_buf);
-      KLAUNCH(tables_kernel)<<<grid_for(nb, 128), 128, 0, s>>>(c->store.p, keys.p, locs.p, n2, bi2, c->sizes.p, c->shared.p,
+      Reuse ru{nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+      static const bool reuse = [] { const char* e = getenv("BGX_TABLES_REUSE"); return e ? atoi(e) != 0 : true; }();  // A/B hook
+      if (reuse && n_new == 0) {
+        // nothing was merged or dropped after the walk: final index == round-1 index
+        DevBuf<uint32_t>& ident = org;
+        ident.alloc(n2, s);
+        KLAUNCH(iota_u32_kernel)<<<grid_for(n2, 256), 256, 0, s>>>(ident.p, n2);
+        ru = Reuse{ident.p, where1.p, nullptr, nullptr, nullptr, nullptr};
+      } else if (reuse) {
+        ru = Reuse{org.p, where1.p, marks_excl.p, pos2.p, keys_alt.p, locs_alt.p};   // the alt buffers still hold the merged records
+      }
+      KLAUNCH(tables_kernel)<<<grid_for(nb, 128), 128, 0, s>>>(c->store.p, keys.p, locs.p, n2, bi2, ru, c->sizes.p, c->shared.p,
                                                       reinterpret_cast<unsigned long long*>(c->prev_bits.p),
                                                       c->prev_words, max_len.p, missing.p);
       DevBuf<uint32_t> gpop(c->sub_words, s), gex(c->sub_words, s), tot(1, s);

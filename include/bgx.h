@@ -82,7 +82,10 @@ int bgx_add_reads_fastq(bgx_ctx* ctx, const char* text, uint64_t size, uint64_t*
  *              word 0" (reads are always dense, so the offsets follow from lens; only the first
  *              and last entry are looked at).
  * Word offsets, base / k-mer totals and the length check are computed on the device: no host
- * loop over the reads.  Pinned host memory makes the copies asynchronous; pageable works too. */
+ * loop over the reads.  Pinned host memory makes the copies asynchronous; pageable works too.
+ * packed / n_mask / lens may also be DEVICE pointers (reads produced on the GPU, e.g. by a
+ * generator or an upstream decoder): the copies are cudaMemcpyDefault; word_offs is read on the
+ * host and must then be NULL. */
 int bgx_add_reads_packed(bgx_ctx* ctx, const uint8_t* packed, const uint32_t* n_mask,
                          const uint64_t* word_offs, const uint16_t* lens, uint64_t n_reads);
 
