@@ -3,6 +3,7 @@
 
 #include <dlfcn.h>
 #include <nccl.h>
+#include <unistd.h>
 
 #include <cstdlib>
 #include <cstring>
@@ -94,17 +95,35 @@ void dist_map_peers_n(Context* c, void* const* local, int k, void** peer) {
   for (int j = 0; j < k; ++j) peer[(size_t)j * N + R] = local[j];
   if (N == 1) return;
   static_assert(sizeof(cudaIpcMemHandle_t) == 64, "cudaIpcMemHandle_t is 64 bytes");
-  std::vector<uint64_t> mine((size_t)k * 8), all((size_t)N * k * 8);
+  // per block: IPC handle (8 words), exporting process, raw pointer, device ordinal.  Ranks that live
+  // in THIS process (bgx_bs::multi_session: one host thread per GPU) cannot open their own handles;
+  // their memory is addressed directly once peer access is enabled.
+  constexpr int W = 11;
+  const uint64_t my_pid = (uint64_t)getpid();
+  std::vector<uint64_t> mine((size_t)k * W), all((size_t)N * k * W);
   for (int j = 0; j < k; ++j) {
     cudaIpcMemHandle_t h;
     BGX_CUDA(cudaIpcGetMemHandle(&h, local[j]));
-    memcpy(&mine[(size_t)j * 8], &h, 64);
+    memcpy(&mine[(size_t)j * W], &h, 64);
+    mine[(size_t)j * W + 8] = my_pid;
+    mine[(size_t)j * W + 9] = (uint64_t)(uintptr_t)local[j];
+    mine[(size_t)j * W + 10] = (uint64_t)c->device;
   }
-  dist_allgather_host_u64(c, mine.data(), (size_t)k * 8, all.data());
+  dist_allgather_host_u64(c, mine.data(), (size_t)k * W, all.data());
   for (int r = 0; r < N; ++r) {
     if (r == R) continue;
     for (int j = 0; j < k; ++j) {
-      const uint64_t* hp = &all[((size_t)r * k + j) * 8];
+      const uint64_t* hp = &all[((size_t)r * k + j) * W];
+      if (hp[8] == my_pid) {
+        const int dev = (int)hp[10];
+        if (dev != c->device) {
+          cudaError_t e = cudaDeviceEnablePeerAccess(dev, 0);
+          if (e == cudaErrorPeerAccessAlreadyEnabled) cudaGetLastError();
+          else BGX_CUDA(e);
+        }
+        peer[(size_t)j * N + r] = reinterpret_cast<void*>((uintptr_t)hp[9]);
+        continue;
+      }
       std::string key(reinterpret_cast<const char*>(hp), 64);
       key.push_back((char)r);
       auto it = c->dist.ipc_cache.find(key);
@@ -128,15 +147,52 @@ void dist_barrier(Context* c) {
   dist_allreduce_sum_host_u64(c, &one, 1);
 }
 
-bool dist_direct_exchange() {
-  static const bool direct = [] {
+Exchange dist_exchange_mode() {
+  static const Exchange mode = [] {
     const char* e = getenv("BGX_EXCHANGE");
-    return !(e && std::string(e) == "nccl");
+    if (e && std::string(e) == "nccl") return Exchange::NCCL;
+    if (e && std::string(e) == "store") return Exchange::STORE;
+    return Exchange::COPY;
   }();
-  return direct;
+  return mode;
+}
+
+void dist_peer_copies(Context* c, const std::vector<PeerCopy>& copies) {
+  const int N = c->dist.nranks;
+  Dist& d = c->dist;
+  if (d.copy_streams.empty()) {
+    d.copy_streams.resize(N);
+    d.copy_done.resize(N);
+    for (int r = 0; r < N; ++r) {
+      BGX_CUDA(cudaStreamCreateWithFlags(&d.copy_streams[r], cudaStreamNonBlocking));
+      BGX_CUDA(cudaEventCreateWithFlags(&d.copy_done[r], cudaEventDisableTiming));
+    }
+    BGX_CUDA(cudaEventCreateWithFlags(&d.copy_go, cudaEventDisableTiming));
+  }
+  BGX_CUDA(cudaEventRecord(d.copy_go, c->stream));
+  std::vector<char> used(N, 0);
+  for (const PeerCopy& pc : copies) {
+    if (!pc.bytes) continue;
+    if (!used[pc.peer]) {
+      BGX_CUDA(cudaStreamWaitEvent(d.copy_streams[pc.peer], d.copy_go, 0));
+      used[pc.peer] = 1;
+    }
+    BGX_CUDA(cudaMemcpyAsync(pc.dst, pc.src, pc.bytes, cudaMemcpyDefault, d.copy_streams[pc.peer]));
+  }
+  for (int r = 0; r < N; ++r) {
+    if (!used[r]) continue;
+    BGX_CUDA(cudaEventRecord(d.copy_done[r], d.copy_streams[r]));
+    BGX_CUDA(cudaStreamWaitEvent(c->stream, d.copy_done[r], 0));
+  }
 }
 
 void dist_destroy(Context* c) {
+  for (cudaStream_t st : c->dist.copy_streams) { cudaStreamSynchronize(st); cudaStreamDestroy(st); }
+  for (cudaEvent_t ev : c->dist.copy_done) cudaEventDestroy(ev);
+  if (c->dist.copy_go) cudaEventDestroy(c->dist.copy_go);
+  c->dist.copy_streams.clear();
+  c->dist.copy_done.clear();
+  c->dist.copy_go = nullptr;
   for (auto& kv : c->dist.ipc_cache) cudaIpcCloseMemHandle(kv.second);
   c->dist.ipc_cache.clear();
   if (c->dist.comm) {

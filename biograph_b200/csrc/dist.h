@@ -25,6 +25,10 @@ struct Dist {
   void* comm = nullptr;  // ncclComm_t
   // peers' device blocks mapped into this process (cudaIpcOpenMemHandle), keyed by the 64-byte handle
   std::map<std::string, void*> ipc_cache;
+  // one copy stream per peer for the copy-engine exchanges
+  std::vector<cudaStream_t> copy_streams;
+  std::vector<cudaEvent_t> copy_done;
+  cudaEvent_t copy_go = nullptr;
 };
 
 // rank 0: a fresh NCCL unique id (128 bytes) to hand to every rank out of band
@@ -61,8 +65,25 @@ void dist_map_peers(Context* c, void* local, void** peer);
 void dist_map_peers_n(Context* c, void* const* local, int k, void** peer);
 // every rank has passed this point on its stream (and the host has waited for it)
 void dist_barrier(Context* c);
-// false: BGX_EXCHANGE=nccl (exchanges as NCCL send/recv batches instead of stores into peer memory)
-bool dist_direct_exchange();
+// How the two bulk exchanges of the path (k-mer words to their owners, records to theirs) move:
+//   COPY  (default) the producer writes its own memory; the blocks then go to the owners' memory with
+//         one copy-engine transfer per peer (cudaMemcpyAsync into the peer mapping), all peers at once
+//   STORE the producing kernel stores straight into the owners' memory (fused compute + exchange).
+//         Measured on B200 / NVSwitch: SM-issued 8-byte remote stores reach ~190-260 GB/s per GPU, a
+//         quarter of what the copy engines move, so this form loses (profiles/r2g_*); kept for A/B.
+//   NCCL  grouped ncclSend/ncclRecv (the round-1 form); kept for A/B.
+enum class Exchange { COPY, STORE, NCCL };
+Exchange dist_exchange_mode();   // BGX_EXCHANGE=copy|store|nccl
+struct PeerCopy {
+  void* dst = nullptr;      // in the peer's memory (a dist_map_peers pointer) or local
+  const void* src = nullptr;
+  size_t bytes = 0;
+  int peer = 0;
+};
+// all copies at once, one stream per peer, ordered after everything queued on the context's stream;
+// the context's stream continues when they are done (the data has then LEFT; dist_barrier tells when
+// everybody's has arrived)
+void dist_peer_copies(Context* c, const std::vector<PeerCopy>& copies);
 
 // ---- small host-side metadata (counts, boundaries): staged through the device, synchronous -------------
 // out[r * n .. (r+1) * n) = rank r's in[0..n)

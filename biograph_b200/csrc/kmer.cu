@@ -662,6 +662,7 @@ __global__ void solid_insert_kernel(const unsigned long long* __restrict__ keys,
   uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   unsigned long long kf = keys[i];
+  if (kf == kEmptyKey) return;   // padding of a gathered list
   uint64_t b = khash(kf & kKmerMask, k) >> bucket_shift;
   for (;;) {
 #pragma unroll
@@ -975,21 +976,24 @@ void exchange_partitions(Context* c, const Partitioned& pt, int P, Owned* own) {
 // on the sender.  The owner's buffer has one region of `cap` words per (source rank, local partition);
 // K_max = the most instances any rank brings to this batch (the same value on every rank).  If a
 // region overflows anywhere (a heavy hitter), every rank re-runs the sweep against exact offsets.
-void partition_direct(Context* c, uint64_t K_max, const PartGeom& G, int maxit, Owned* own) {
+void partition_direct(Context* c, uint64_t K_max, const PartGeom& G, int maxit, Owned* own, Partitioned* pt) {
   cudaStream_t s = c->stream;
   const int N = c->dist.nranks, R = c->dist.rank;
   const int P = 1 << G.part_bits, Pl = P / N;
   unsigned long long cap = K_max / P + K_max / (8ull * P) + 4096;
   void* peer[64];
   std::vector<unsigned long long> addr(P), counts;
+  const bool staged = dist_exchange_mode() == Exchange::COPY;   // pass 1 writes local memory, copy engines move the blocks
   {
     ScopedStage st(c, "count_exchange");
     own->rbuf.alloc((size_t)N * Pl * cap, s);
+    if (staged) pt->pk.alloc((size_t)P * cap, s);
     dist_map_peers(c, own->rbuf.p, peer);   // also: every owner's buffer is ready to be written
     st.stop();
   }
   for (int p = 0; p < P; ++p)
-    addr[p] = (unsigned long long)(uintptr_t)(static_cast<unsigned long long*>(peer[p / Pl]) + ((size_t)R * Pl + p % Pl) * cap);
+    addr[p] = staged ? (unsigned long long)(uintptr_t)(pt->pk.p + (size_t)p * cap)
+                     : (unsigned long long)(uintptr_t)(static_cast<unsigned long long*>(peer[p / Pl]) + ((size_t)R * Pl + p % Pl) * cap);
   int h_over = sweep_partition(c, G, maxit, nullptr, addr, cap, &counts);
   ScopedStage st(c, "count_exchange");
   std::vector<uint64_t> mine(P + 1), all((size_t)N * (P + 1));
@@ -1000,9 +1004,26 @@ void partition_direct(Context* c, uint64_t K_max, const PartGeom& G, int maxit, 
   bool any_over = false;
   for (int r = 0; r < N; ++r) any_over = any_over || all[(size_t)r * (P + 1) + P] != 0;
   std::vector<uint64_t> off((size_t)N * Pl, 0);   // [src][pl] -> first word in this owner's buffer
+  bool own_in_pk = false;                          // this rank's own block stays where pass 1 wrote it
   if (!any_over) {
     for (int src = 0; src < N; ++src)
       for (int pl = 0; pl < Pl; ++pl) off[(size_t)src * Pl + pl] = ((size_t)src * Pl + pl) * cap;
+    if (staged) {
+      // the block of partitions a peer owns is contiguous here and lands contiguously there: ONE copy per peer
+      std::vector<PeerCopy> copies;
+      for (int d = 0; d < N; ++d) {
+        if (d == R) continue;
+        PeerCopy pc;
+        pc.dst = static_cast<unsigned long long*>(peer[d]) + (size_t)R * Pl * cap;
+        pc.src = pt->pk.p + (size_t)d * Pl * cap;
+        pc.bytes = (size_t)Pl * cap * 8;
+        pc.peer = d;
+        copies.push_back(pc);
+      }
+      dist_peer_copies(c, copies);
+      dist_barrier(c);   // every rank's blocks have arrived
+      own_in_pk = true;
+    }
   } else {
     // exact layout, identical arithmetic on every rank: owner d lays its regions out partition-major
     auto layout = [&](int d, std::vector<uint64_t>* o) {
@@ -1042,7 +1063,9 @@ void partition_direct(Context* c, uint64_t K_max, const PartGeom& G, int maxit, 
   uint64_t out_words = 0;
   for (int pl = 0; pl < Pl; ++pl)
     for (int src = 0; src < N; ++src) {
-      own->ptr.push_back((unsigned long long)(uintptr_t)(own->rbuf.p + off[(size_t)src * Pl + pl]));
+      const unsigned long long* ptr = own_in_pk && src == R ? pt->pk.p + ((size_t)R * Pl + pl) * cap
+                                                            : own->rbuf.p + off[(size_t)src * Pl + pl];
+      own->ptr.push_back((unsigned long long)(uintptr_t)ptr);
       own->cnt.push_back(cnt_of(src, R * Pl + pl));
       own->pl.push_back((uint32_t)pl);
     }
@@ -1141,7 +1164,7 @@ void stage_count_kmers(Context* c) {
     for (uint64_t v : ks) K_max = std::max(K_max, v);
   }
   // BGX_EXCHANGE=nccl: partition locally, then one NCCL send/recv per peer (the round-1 form; A/B hook)
-  const bool direct_exchange = dist_direct_exchange();
+  const bool direct_exchange = dist_exchange_mode() != Exchange::NCCL;
   const int maxit = (int)((std::max<int64_t>((int64_t)c->max_len - k + 1, 1) + 31) / 32);
   BGX_CHECK(maxit <= 8, "read longer than 255 bases");
   const uint64_t batches = choose_batches(c, K, K_share);
@@ -1179,7 +1202,7 @@ void stage_count_kmers(Context* c) {
     Partitioned pt;
     Owned own;
     if (N > 1 && direct_exchange) {
-      partition_direct(c, K_max / batches + K_max / (16 * batches) + 1024, G, maxit, &own);
+      partition_direct(c, K_max / batches + K_max / (16 * batches) + 1024, G, maxit, &own, &pt);
     } else {
       partition_reads(c, Kb, G, maxit, N == 1 ? &est : nullptr, &pt);
       exchange_partitions(c, pt, P, &own);
@@ -1320,14 +1343,21 @@ void stage_count_kmers(Context* c) {
     const unsigned long long* all_keys = solid_list.p;
     DevBuf<unsigned long long> gathered;
     c->n_solid = n_solid_local;
+    uint64_t n_insert = n_solid_local;   // list entries handed to the insert kernel (padding included)
     if (N > 1) {
-      std::vector<uint64_t> cnts(N), offs(N), zero(N, 0), mine_cnt(N, n_solid_local);
+      // equal-sized slices (the largest owner's count, padded with empty keys): ONE in-place ncclAllGather
+      std::vector<uint64_t> cnts(N);
       dist_allgather_host_u64(c, &n_solid_local, 1, cnts.data());
-      uint64_t tot = 0;
-      for (int r = 0; r < N; ++r) { offs[r] = tot; tot += cnts[r]; }
-      gathered.alloc(std::max<uint64_t>(tot, 1), s);
-      dist_alltoallv(c, solid_list.p, zero.data(), mine_cnt.data(), gathered.p, offs.data(), cnts.data(), 8);
+      uint64_t tot = 0, slice = 1;
+      for (int r = 0; r < N; ++r) { tot += cnts[r]; slice = std::max(slice, cnts[r]); }
+      gathered.alloc(slice * N, s);
+      unsigned long long* mine = gathered.p + (uint64_t)R * slice;
+      if (n_solid_local) BGX_CUDA(cudaMemcpyAsync(mine, solid_list.p, n_solid_local * 8, cudaMemcpyDeviceToDevice, s));
+      if (slice > n_solid_local)
+        KLAUNCH(fill_u64_kernel)<<<(unsigned)((slice - n_solid_local + 255) / 256), 256, 0, s>>>(mine + n_solid_local, slice - n_solid_local, kEmptyKey);
+      dist_allgather_bytes(c, mine, gathered.p, slice * 8);
       all_keys = gathered.p;
+      n_insert = slice * N;
       c->n_solid = tot;
       c->set_stat("kmer_solid_owned", (double)n_solid_local);
     }
@@ -1340,8 +1370,8 @@ void stage_count_kmers(Context* c) {
     c->solid_slots = pow2_ceil(std::max<uint64_t>(1024, (uint64_t)((double)c->n_solid * solid_factor)));
     c->solid.alloc(c->solid_slots, s);
     KLAUNCH(fill_u64_kernel)<<<(unsigned)((c->solid_slots + 255) / 256), 256, 0, s>>>(c->solid.p, c->solid_slots, kEmptyKey);
-    if (c->n_solid)
-      KLAUNCH(solid_insert_kernel)<<<(unsigned)((c->n_solid + 255) / 256), 256, 0, s>>>(all_keys, c->n_solid, k, c->solid.p,
+    if (n_insert)
+      KLAUNCH(solid_insert_kernel)<<<(unsigned)((n_insert + 255) / 256), 256, 0, s>>>(all_keys, n_insert, k, c->solid.p,
                                                                              c->solid_slots / 4 - 1,
                                                                              2 * k - log2_exact(c->solid_slots / 4));
     BGX_CUDA(cudaGetLastError());

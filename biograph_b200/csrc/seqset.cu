@@ -1431,7 +1431,8 @@ Routed route_records(Context* c, const uint64_t* keys, const uint64_t* locs, uin
   out.locs.alloc(m + 1024, s);
   BGX_CUDA(cudaMemsetAsync(counts.p, 0, kMaxRanks * 8, s));   // the scatter's cursors
   RouteOut ro;
-  if (dist_direct_exchange()) {
+  const Exchange mode = dist_exchange_mode();
+  if (mode == Exchange::STORE) {
     // the scatter stores every record straight into its owner's receive buffer over NVLink: this rank's
     // records start where the ranks before it end (the count matrix is known to everyone)
     void* local[2] = {out.keys.p, out.locs.p};
@@ -1447,13 +1448,36 @@ Routed route_records(Context* c, const uint64_t* keys, const uint64_t* locs, uin
     BGX_CUDA(cudaGetLastError());
     dist_barrier(c);   // every rank's stores have landed
   } else {
+    // scatter into local send arrays grouped by destination, then move the groups
     DevBuf<uint64_t> skeys(std::max<uint32_t>(n, 1), s), slocs(std::max<uint32_t>(n, 1), s);
     for (int d = 0; d < N; ++d) { ro.keys[d] = skeys.p + send_off[d]; ro.locs[d] = slocs.p + send_off[d]; }
     if (n) KLAUNCH(route_scatter_kernel)<<<grid_for(n, 256), 256, 0, s>>>(keys, locs, dest.p, n, N, counts.p, ro);
     BGX_CUDA(cudaGetLastError());
-    dist_alltoallv(c, skeys.p, send_off.data(), send_cnt.data(), out.keys.p, recv_off.data(), recv_cnt.data(), 8);
-    dist_alltoallv(c, slocs.p, send_off.data(), send_cnt.data(), out.locs.p, recv_off.data(), recv_cnt.data(), 8);
-    BGX_CUDA(cudaStreamSynchronize(s));  // the send buffers die with this scope
+    if (mode == Exchange::COPY) {
+      // one copy-engine transfer per peer and array, into the owner's receive arrays where the ranks
+      // before this one end
+      void* local[2] = {out.keys.p, out.locs.p};
+      void* peer[2 * kMaxRanks];
+      dist_map_peers_n(c, local, 2, peer);   // also: every owner's buffers are allocated
+      std::vector<PeerCopy> copies;
+      for (int d = 0; d < N; ++d) {
+        uint64_t off = 0;
+        for (int src = 0; src < R; ++src) off += all[(size_t)src * N + d];
+        PeerCopy a, b;
+        a.dst = static_cast<uint64_t*>(peer[d]) + off;      a.src = skeys.p + send_off[d];
+        b.dst = static_cast<uint64_t*>(peer[N + d]) + off;  b.src = slocs.p + send_off[d];
+        a.bytes = b.bytes = send_cnt[d] * 8;
+        a.peer = b.peer = d;
+        copies.push_back(a);
+        copies.push_back(b);
+      }
+      dist_peer_copies(c, copies);
+      dist_barrier(c);   // every rank's records have arrived (and the send arrays may go)
+    } else {
+      dist_alltoallv(c, skeys.p, send_off.data(), send_cnt.data(), out.keys.p, recv_off.data(), recv_cnt.data(), 8);
+      dist_alltoallv(c, slocs.p, send_off.data(), send_cnt.data(), out.locs.p, recv_off.data(), recv_cnt.data(), 8);
+      BGX_CUDA(cudaStreamSynchronize(s));  // the send buffers die with this scope
+    }
   }
   st_x.stop();
   c->add_stat("route_records_out", (double)n - (double)send_cnt[R]);

@@ -37,6 +37,7 @@
 #include <mutex>
 #include <stdexcept>
 #include <string>
+#include <thread>
 #include <unordered_map>
 #include <utility>
 #include <vector>
@@ -129,6 +130,46 @@ class session {
   bgx_ctx* m_ctx = nullptr;
   count_kmer_options m_ko;
   std::mutex m_add_mu;
+};
+
+// One build over several GPUs of ONE process -- what a single-process caller like SEQSETMain needs
+// (modules/main/main.cpp:255-261 forks nothing but a logger): one session per device, each driven by its
+// own host thread, joined into one sharded build (NCCL communicator + peer mappings inside the library).
+//   multi_session ms(4, ko, rp);
+//   ms.parallel([&](int rank, session& s) { /* add this rank's share of the reads, run the stages */ });
+// Every stage call is collective: all ranks must make the same calls in the same order.
+class multi_session {
+ public:
+  multi_session(int n_gpus, const count_kmer_options& ko = count_kmer_options(),
+                const read_correction_params& rp = read_correction_params(), const std::vector<int>& devices = {}) {
+    if (n_gpus < 1 || (n_gpus & (n_gpus - 1))) throw io_exception("multi_session: the GPU count must be a power of two");
+    for (int r = 0; r < n_gpus; ++r) {
+      count_kmer_options k = ko;
+      k.device = devices.empty() ? r : devices[(size_t)r];
+      m_s.emplace_back(new session(k, rp));
+    }
+    if (n_gpus > 1) {
+      const std::vector<uint8_t> id = session::unique_id();
+      parallel([&](int rank, session& s) { s.dist_init(n_gpus, rank, id); });   // ncclCommInitRank: all ranks at once
+    }
+  }
+  int size() const { return (int)m_s.size(); }
+  session& rank(int r) { return *m_s[(size_t)r]; }
+  // f(rank, session) on every rank, each from its own host thread; the first exception is rethrown
+  void parallel(const std::function<void(int, session&)>& f) {
+    std::vector<std::thread> th;
+    std::vector<std::string> err(m_s.size());
+    for (int r = 0; r < size(); ++r)
+      th.emplace_back([&, r] {
+        try { f(r, *m_s[(size_t)r]); } catch (const std::exception& e) { err[(size_t)r] = e.what()[0] ? e.what() : "error"; }
+      });
+    for (auto& t : th) t.join();
+    for (const std::string& e : err)
+      if (!e.empty()) throw io_exception(e);
+  }
+
+ private:
+  std::vector<std::unique_ptr<session>> m_s;
 };
 
 // ---- k-mer counting ---------------------------------------------------------------------------------

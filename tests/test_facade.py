@@ -105,3 +105,32 @@ def test_facade_create_flow_on_golden(tmp_path, golden, golden_reads):
     want_ptr = gz["mate_loop_ptr|packed_data"].view("<u4")
     el, bits = O.varbit_pack(want_ptr.astype(np.uint16), 16888)
     assert bits == 15 and zr.read("mate_loop_ptr/elements") == el.astype("<u8").tobytes()
+
+
+def build_multi_session_test(tmp_dir):
+    exe = os.path.join(str(tmp_dir), "multi_session_test")
+    subprocess.check_call(["g++", "-std=c++17", "-O2", "-Wall", "-pthread", "-I" + os.path.join(ROOT, "include"),
+                           os.path.join(ROOT, "tests", "cpp", "multi_session_test.cpp"), "-o", exe,
+                           "-L" + os.path.join(ROOT, "biograph_b200"), "-lbgx", "-Wl,-rpath," + os.path.join(ROOT, "biograph_b200")])
+    return exe
+
+
+def test_multi_session_compiles_and_links(tmp_path):
+    assert os.path.exists(build_multi_session_test(tmp_path))
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("gpus", [2, 4])
+def test_multi_session_single_process(tmp_path, golden_reads, gpus):
+    """bgx_bs::multi_session: ONE process, one host thread per GPU (the shape SEQSETMain needs), the sharded
+    build over NCCL + peer access inside the process; tables equal to the single-GPU build"""
+    import biograph_b200 as B
+    if B.load_library().bgx_device_count() < gpus:
+        pytest.skip(f"needs >= {gpus} GPUs (run under gpurun --gpus {gpus})")
+    exe = build_multi_session_test(tmp_path)
+    reads_txt = tmp_path / "reads.txt"
+    reads_txt.write_text("\n".join(golden_reads) + "\n")
+    out = subprocess.run([exe, str(reads_txt), str(gpus)], capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0, out.stdout + out.stderr
+    res = json.loads([l for l in out.stdout.splitlines() if l.startswith("{")][-1])
+    assert res["ok"] and res["entries"] == res["expected"] == 19935
