@@ -412,6 +412,80 @@ def _fastq(reads, blank_tail=0):
     return ("".join(out) + "\n" * blank_tail).encode()
 
 
+def test_readmap_read_props_of_the_reference_test(B):
+    """modules/bio_base/readmap_test.cpp:53-168 (TEST(readmap, read_props_tests)) against the GPU readmap:
+    the reference's own pairs, and for every read and its reverse complement the properties the test
+    asserts -- unique entry, entry <-> read index, length, is_forward, get_rev_comp, and mates that point
+    at each other (get_mate / has_mate as readmap.cpp:207-268 derive them from the mate loop)."""
+    import bisect
+    T = O.tseq
+    pairs = [(T("READ1"), T("ANOTHER1")), (T("NEWB"), T("BROTHER")), (T("SOLO"), ""), (T("PREFIXread"), T("PREFIXmate")),
+             (T("readSUFFIX"), T("mateSUFFIX")), (T("PREFIXreadSUFFIX"), T("PREFIXmateSUFFIX")), (T("read"), T("mate")),
+             (T("XreadS"), T("XmateS"))]
+    reads = [r for p in pairs for r in p]
+    g = B.Bgx()
+    g.add_reads(reads)
+    g.seed_uncorrected()
+    g.build_seqset()
+    ents = g.export_entries()
+    rm = g.build_readmap(paired=True)
+    n_rows = rm["n_rows"]
+    bit = lambda words, i: (int(words[i >> 6]) >> (i & 63)) & 1
+    src = [i for i in range(len(ents)) if bit(rm["source_to_mid"]["bits"], i)]          # entries that hold reads
+    opens = [i for i in range(n_rows) if bit(rm["dest_to_mid"]["bits"], i)] + [n_rows]  # first row of each of them
+    assert len(src) == len(opens) - 1
+    loop = rm["mate_loop_ptr"]
+    fwd_of = lambda i: bool(bit(rm["is_forward"], i))
+
+    def entry_to_index(e):
+        k = bisect.bisect_left(src, e)
+        assert k < len(src) and src[k] == e          # get_bit(entry)
+        return opens[k], opens[k + 1]
+
+    def index_to_entry(i):
+        return src[bisect.bisect_right(opens, i) - 1]
+
+    def find_unique(seq):
+        lo = bisect.bisect_left(ents, seq)
+        hits = [e for e in range(lo, min(lo + 3, len(ents))) if ents[e].startswith(seq)]
+        assert len(hits) == 1                        # entry_read.end() - entry_read.begin() == 1
+        return hits[0]
+
+    def row_of(seq):
+        e = find_unique(seq)
+        a, b = entry_to_index(e)
+        rows = [i for i in range(a, b) if rm["read_lengths"][i] == len(seq)]
+        assert rows
+        return e, rows[-1] if b - a != 1 else a       # the test keeps the last row of that length
+
+    def rev_comp(i):                                  # readmap::get_rev_comp
+        for _ in range(1 if fwd_of(i) else 3):
+            i = int(loop[i])
+        return i
+
+    def props(read, mate, fwd):
+        e, i = row_of(read)
+        assert fwd_of(i) == fwd and rm["read_lengths"][i] == len(read)
+        assert index_to_entry(i) == e and ents[e][:len(read)] == read
+        rc = rev_comp(i)
+        assert ents[index_to_entry(rc)][:rm["read_lengths"][rc]] == O.revcomp(read)
+        if mate:
+            me, mi = row_of(mate)
+            assert fwd_of(mi) == fwd and rm["read_lengths"][mi] == len(mate)
+            has_mate = lambda x: int(loop[int(loop[x])]) != x
+            assert has_mate(i) and has_mate(mi)
+            assert int(loop[int(loop[i])]) == mi and int(loop[int(loop[mi])]) == i   # get_mate both ways
+            assert index_to_entry(mi) == me and ents[me][:len(mate)] == mate
+        else:
+            assert int(loop[int(loop[i])]) == i       # no mate: the loop is read <-> reverse complement
+
+    for read, mate in pairs:
+        props(read, mate, True)
+        props(O.revcomp(read), O.revcomp(mate) if mate else "", False)
+    g.close()
+
+
+
 def test_fastq_import_equals_ascii_import(B, golden_reads):
     """bgx_add_reads_fastq (fastq_reader::read semantics, modules/bio_format/fastq.cpp:40-126): same reads,
     same result as bgx_add_reads_ascii; ragged lengths, N calls, several appends, trailing blank lines."""
