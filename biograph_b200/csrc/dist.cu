@@ -157,7 +157,74 @@ Exchange dist_exchange_mode() {
   return mode;
 }
 
+namespace {
+// All copies of a batch in ONE launch: block b works on copy b % n_copies, the blocks of a copy stride
+// over it with 128-bit loads and stores (the stores go to the peer's memory over NVLink).  What NCCL's
+// own kernels do for a send, without the handshake: the destination is mapped and known to be free.
+struct CopyDesc {
+  void* dst;
+  const void* src;
+  unsigned long long n;   // units: 16 bytes if wide, else 8
+  int wide;
+};
+constexpr int kMaxCopies = 2 * 64;
+struct CopyBatch {
+  CopyDesc d[kMaxCopies];
+  int n;
+};
+template <typename T>
+__device__ __forceinline__ void copy_strided(T* __restrict__ dst, const T* __restrict__ src, unsigned long long n,
+                                             unsigned long long first, unsigned long long stride) {
+  unsigned long long i = first;
+  // four independent transfers in flight per thread
+  for (; i + 3 * stride < n; i += 4 * stride) {
+    const T a = src[i], b = src[i + stride], c = src[i + 2 * stride], d = src[i + 3 * stride];
+    dst[i] = a; dst[i + stride] = b; dst[i + 2 * stride] = c; dst[i + 3 * stride] = d;
+  }
+  for (; i < n; i += stride) dst[i] = src[i];
+}
+__global__ void __launch_bounds__(512) peer_copy_kernel(const CopyBatch* __restrict__ batch) {
+  const int n = batch->n;
+  const int which = blockIdx.x % n;
+  const CopyDesc cd = batch->d[which];
+  const unsigned blocks = (gridDim.x - which + n - 1) / n;   // blocks working on this copy
+  const unsigned long long stride = (unsigned long long)blocks * blockDim.x;
+  const unsigned long long first = (unsigned long long)(blockIdx.x / n) * blockDim.x + threadIdx.x;
+  if (cd.wide) copy_strided(static_cast<uint4*>(cd.dst), static_cast<const uint4*>(cd.src), cd.n, first, stride);
+  else copy_strided(static_cast<unsigned long long*>(cd.dst), static_cast<const unsigned long long*>(cd.src), cd.n, first, stride);
+}
+}  // namespace
+
 void dist_peer_copies(Context* c, const std::vector<PeerCopy>& copies) {
+  static const bool use_ce = [] { const char* e = getenv("BGX_PEER_COPY"); return e && std::string(e) == "ce"; }();  // A/B hook
+  if (!use_ce) {
+    // SM copy kernel (default): measured against the copy engines, which move ~110 GB/s per engine and
+    // stream here (3 peers: 325 GB/s) -- see profiles/r2h_*
+    cudaStream_t s = c->stream;
+    CopyBatch h;
+    h.n = 0;
+    std::vector<PeerCopy> odd;   // not even 8-byte shaped: plain async copies
+    for (const PeerCopy& pc : copies) {
+      if (!pc.bytes) continue;
+      const uintptr_t shape = (uintptr_t)pc.dst | (uintptr_t)pc.src | pc.bytes;
+      if ((shape & 7) || h.n == kMaxCopies) { odd.push_back(pc); continue; }
+      h.d[h.n].dst = pc.dst;
+      h.d[h.n].src = pc.src;
+      h.d[h.n].wide = (shape & 15) == 0;
+      h.d[h.n].n = pc.bytes / (h.d[h.n].wide ? 16 : 8);
+      ++h.n;
+    }
+    if (h.n) {
+      DevBuf<CopyBatch> d(1, s);
+      BGX_CUDA(cudaMemcpyAsync(d.p, &h, sizeof(CopyBatch), cudaMemcpyHostToDevice, s));
+      BGX_CUDA(cudaStreamSynchronize(s));   // h lives on this stack frame
+      const unsigned grid = (unsigned)(kNumSMs * 4 / h.n * h.n + (kNumSMs * 4 % h.n ? h.n : 0));
+      KLAUNCH(peer_copy_kernel)<<<std::max<unsigned>(grid, (unsigned)h.n), 512, 0, s>>>(d.p);
+      BGX_CUDA(cudaGetLastError());
+    }
+    for (const PeerCopy& pc : odd) BGX_CUDA(cudaMemcpyAsync(pc.dst, pc.src, pc.bytes, cudaMemcpyDefault, s));
+    return;
+  }
   const int N = c->dist.nranks;
   Dist& d = c->dist;
   if (d.copy_streams.empty()) {

@@ -49,7 +49,7 @@ namespace {
 constexpr uint64_t kWFwd = 1, kWRev = 2, kWFlip = 4;
 constexpr int kMinPartBits = 7;
 constexpr int kMaxPartBits = 10;            // <= 1024 hash partitions per batch
-constexpr int kMaxSubBits = 10;             // <= 1024 sub-bins per partition
+constexpr int kMaxSubBits = 11;             // <= 2048 sub-bins per partition
 constexpr int kPartThreads = 256;
 constexpr int kPartWarps = kPartThreads / 32;
 
@@ -241,7 +241,7 @@ __global__ void __launch_bounds__(kSplitThreads) kmer_subhist_kernel(const unsig
                                                                      const uint32_t* __restrict__ vpl,
                                                                      uint32_t blocks_per_part, int sub_shift, int sub_bits,
                                                                      unsigned long long* __restrict__ hist) {
-  __shared__ uint32_t h[1 << kMaxSubBits];
+  __shared__ uint32_t h[1 << kMaxSubBits];   // 8 KB
   const uint32_t v = blockIdx.x / blocks_per_part, t = blockIdx.x % blocks_per_part;
   const unsigned long long cnt = vcnt[v];
   const unsigned long long first = (unsigned long long)t * (kSplitTile * kHistTiles);
@@ -321,9 +321,8 @@ __global__ void __launch_bounds__(kSplitThreads, 2) kmer_split_kernel(const unsi
                                                                       unsigned long long* __restrict__ out) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   unsigned long long* stage = reinterpret_cast<unsigned long long*>(smem_raw);     // kSplitTile
-  uint16_t* stage_bin = reinterpret_cast<uint16_t*>(stage + kSplitTile);           // kSplitTile
   const int S = 1 << sub_bits;
-  unsigned long long* gdst = reinterpret_cast<unsigned long long*>(stage_bin + kSplitTile);  // S
+  unsigned long long* gdst = reinterpret_cast<unsigned long long*>(stage + kSplitTile);      // S
   uint32_t* hist = reinterpret_cast<uint32_t*>(gdst + S);                          // S
   uint32_t* bin_start = hist + S;                                                  // S
   __shared__ uint32_t n_tile_s;
@@ -354,11 +353,11 @@ __global__ void __launch_bounds__(kSplitThreads, 2) kmer_split_kernel(const unsi
   }
   __syncthreads();
   {
-    const int per = (S + kSplitThreads - 1) / kSplitThreads;  // 1..2
-    uint32_t loc[2];
+    const int per = (S + kSplitThreads - 1) / kSplitThreads;  // 1..4
+    uint32_t loc[4];
     uint32_t sum = 0;
 #pragma unroll
-    for (int j = 0; j < 2; ++j) {
+    for (int j = 0; j < 4; ++j) {
       const int d = (int)tid * per + j;
       loc[j] = (j < per && d < S) ? hist[d] : 0u;
       sum += loc[j];
@@ -367,7 +366,7 @@ __global__ void __launch_bounds__(kSplitThreads, 2) kmer_split_kernel(const unsi
     uint32_t ex = block_excl_scan_u32(sum, &tot);
     const size_t gb = (size_t)vpl[v] * S;
 #pragma unroll
-    for (int j = 0; j < 2; ++j) {
+    for (int j = 0; j < 4; ++j) {
       const int d = (int)tid * per + j;
       if (j < per && d < S) {
         bin_start[d] = ex;
@@ -388,13 +387,14 @@ __global__ void __launch_bounds__(kSplitThreads, 2) kmer_split_kernel(const unsi
       const uint32_t bin = (uint32_t)(w[i] >> (3 + sub_shift)) & smask;
       const uint32_t pos = bin_start[bin] + ((rk[i >> 1] >> (16 * (i & 1))) & 0xffffu);
       stage[pos] = w[i];
-      stage_bin[pos] = (uint16_t)bin;
     }
   }
   __syncthreads();
   const uint32_t n_staged = n_tile_s;
-  for (uint32_t j = tid; j < n_staged; j += kSplitThreads)
-    *reinterpret_cast<unsigned long long*>(gdst[stage_bin[j]] + 8ull * j) = stage[j];
+  for (uint32_t j = tid; j < n_staged; j += kSplitThreads) {
+    const unsigned long long wj = stage[j];   // the word names its own sub-bin
+    *reinterpret_cast<unsigned long long*>(gdst[(uint32_t)(wj >> (3 + sub_shift)) & smask] + 8ull * j) = wj;
+  }
 }
 
 // ---- pass 3: count one sub-bin per block in a shared-memory hash table ----------------------------------
@@ -1124,7 +1124,7 @@ uint64_t choose_batches(Context* c, uint64_t K_local, uint64_t K_share) {
   }
   // ... and so that one rank counts at most ~1.2 G instances per batch: with the usual ~1/5 of them
   // distinct that is what 2^17 sub-bins of 2 k distinct k-mers hold (128 partitions x 1024 sub-bins)
-  if (!batch_reads) batches = std::max<uint64_t>(batches, (K_share + (1200ull << 20) - 1) / (1200ull << 20));
+  if (!batch_reads) batches = std::max<uint64_t>(batches, (K_share + (1100ull << 20) - 1) / (1100ull << 20));
   if (N > 1) {
     std::vector<uint64_t> all(N);
     dist_allgather_host_u64(c, &batches, 1, all.data());
@@ -1174,10 +1174,14 @@ void stage_count_kmers(Context* c) {
   // Partitions per batch: pass 1 writes longer coalesced runs with fewer partitions (128 measured
   // best on B200), but every rank needs at least one, and a partition should stay well below 2^31
   // words.  Rank r owns the contiguous block [r*P/N, (r+1)*P/N) (same P on every rank).
+  // One GPU: 128 partitions, 256 once a partition would pass 8 M words.  Several GPUs: 64 partitions per
+  // rank (pass 1's runs shrink with the TOTAL count: 1024 partitions cost it 85 % more time on B200),
+  // pass 2 then splits finer (up to 2048 sub-bins per partition).
   int part_bits = kMinPartBits;
-  while (part_bits < kMaxPartBits && ((K_all / batches) >> part_bits) > (8ull << 20)) ++part_bits;
-  if (const char* e = getenv("BGX_PART_BITS")) part_bits = std::max(1, std::min(kMaxPartBits, atoi(e)));
-  part_bits = std::max(part_bits, rank_bits);
+  while (part_bits < 8 && ((K_share / batches) >> part_bits) > (8ull << 20)) ++part_bits;
+  part_bits = std::max(part_bits, rank_bits + 6);
+  if (const char* e = getenv("BGX_PART_BITS")) part_bits = std::max(1, atoi(e));
+  part_bits = std::max(std::min(part_bits, kMaxPartBits), rank_bits);
   BGX_CHECK(2 * k - batch_bits - part_bits >= 16, "k-mer too short for this many batches / partitions");
   int c_log2 = 12;  // 4096 slots = 64 KB of shared memory per block, three blocks per SM
   if (const char* e = getenv("BGX_BIN_SLOTS_LOG2")) c_log2 = std::max(9, std::min(13, atoi(e)));  // experiment hook
@@ -1248,7 +1252,7 @@ void stage_count_kmers(Context* c) {
         }
         KLAUNCH(scan_u64_kernel)<<<1, 1024, 0, s>>>(hist.p, n_bins, bin_off.p, scal.p, scal.p + 1);
         if (own.n_inst) {
-          const size_t smem = (size_t)kSplitTile * 10 + (size_t)S * 16;
+          const size_t smem = (size_t)kSplitTile * 8 + (size_t)S * 16;
           BGX_CUDA(cudaFuncSetAttribute(kmer_split_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
           const uint32_t tb = od.blocks(kSplitTile);
           KLAUNCH(kmer_split_kernel)<<<tb * od.V, kSplitThreads, smem, s>>>(od.part_ptr(), od.cnt.p, od.pl.p, tb, sub_shift, sub_bits,
