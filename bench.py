@@ -442,18 +442,21 @@ def main():
     e2e_val = total_bases / (e2e_ms_step / 1e3)
 
     # ---- roofline of the dominant kernel (live CUDA-event time inside the timed steps) -------------------------
+    # Every stage below is ONE kernel (or one kernel per radix pass) timed by CUDA events on the library's
+    # stream; algorithmic bytes as DESIGN.md section 3 defines them (reported by the library per run).
     peak, peak_src = measured_peak_gbs()
     kern_ms = {k_[3:]: v for k_, v in st_mean.items() if k_.startswith("ms_")}
-    kernel_of = {"count_partition": "kmer_partition_kernel", "count_kernel": "kmer_upsert_kernel",
-                 "correct": "probe_kernel + correct_kernel (reads with errors)",
-                 "sort_radix": "radix_hist_kernel + onesweep_kernel x passes", "dedup": "dedup_flag_kernel + scan + compact_pairs_kernel (2 rounds)"}
-    # correction = the warp-parallel probe pass over every read + the DFS pass over the reads it could not finish
-    kern_ms["correct"] = kern_ms.get("correct_probe", 0.0) + kern_ms.get("correct_kernel", 0.0)
-    # algorithmic bytes per launch, as defined in DESIGN.md section 3 (reported by the library per run)
+    kernel_of = {"count_partition": "kmer_partition_kernel", "count_split": "kmer_subhist_kernel + kmer_split_kernel",
+                 "count_kernel": "kmer_count_bins_kernel", "correct_probe": "probe_kernel",
+                 "sort_radix": "radix_hist_kernel + onesweep_kernel x passes",
+                 "dedup": "dedup_flag_kernel + scan + compact_pairs_kernel (2 rounds)"}
+    K_inst = st_mean.get("kmer_instances", 0.0) if world == 1 else bases * (read_len - 29) / read_len
     alg = {
         "count_partition": st_mean.get("alg_bytes_count_partition", 0.0),
+        "count_split": st_mean.get("alg_bytes_count_split", 0.0),
         "count_kernel": st_mean.get("alg_bytes_count_kernel", 0.0),
-        "correct": st_mean.get("alg_bytes_correct", 0.0),
+        # probe pass: the packed reads once + one 32-byte sector of the solid set per k-mer (SURVEY 8d "correct")
+        "correct_probe": bases / 4.0 + 32.0 * K_inst,
         "sort_radix": st_mean.get("alg_bytes_sort_radix", 0.0),
         "dedup": st_mean.get("alg_bytes_dedup", 0.0),
     }
@@ -462,14 +465,23 @@ def main():
         ms = kern_ms.get(name, 0.0)
         if ms > 0:
             stages[name] = {"ms": ms, "alg_bytes": b_, "achieved_gbs": b_ / ms / 1e6, "frac": b_ / ms / 1e6 / peak}
+    # the sort/dedup stage as SURVEY 8d evaluates it: radix passes + tie groups + dedup, and the one-touch floor
+    sd_ms = sum(kern_ms.get(k_, 0.0) for k_ in ("sort_radix", "sort_ties", "dedup"))
+    if sd_ms > 0:
+        sd_bytes = alg["sort_radix"] + alg["dedup"]
+        stages["sort_dedup_stage"] = {"ms": sd_ms, "alg_bytes": sd_bytes, "achieved_gbs": sd_bytes / sd_ms / 1e6,
+                                      "frac": sd_bytes / sd_ms / 1e6 / peak,
+                                      "one_touch_floor_frac": st_mean.get("useful_bytes_sort", 0.0) / sd_ms / 1e6 / peak}
     dom = max(alg, key=lambda n_: kern_ms.get(n_, 0.0))
     roof = {"bound": "hbm", "kernel": kernel_of[dom], "stage": dom, "achieved": stages.get(dom, {}).get("achieved_gbs"), "peak": peak,
             "unit": "GB/s", "frac": stages.get(dom, {}).get("frac"), "traffic": None, "peak_source": peak_src,
             "stages": stages, "share_of_step": kern_ms.get(dom, 0.0) / (dev_ms / args.steps)}
     tr = os.path.join(ROOT, "profiles", "traffic.json")
-    if os.path.exists(tr) and args.workload == "ecoli100x" and world == 1:  # the capture is of that workload on one GPU
+    if os.path.exists(tr) and world == 1:  # ncu DRAM bytes per launch, captured per workload on one GPU
         try:
-            roof["traffic"] = json.load(open(tr)).get(dom)
+            t_ = json.load(open(tr)).get(args.workload, {})
+            roof["traffic"] = t_.get(dom)
+            roof["traffic_over_alg"] = {k_: t_[k_] / stages[k_]["alg_bytes"] for k_ in t_ if k_ in stages and stages[k_]["alg_bytes"]}
         except Exception:
             pass
 

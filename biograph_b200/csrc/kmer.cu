@@ -1122,9 +1122,14 @@ uint64_t choose_batches(Context* c, uint64_t K_local, uint64_t K_share) {
     const double need = 9.0 * (double)K_local + (N > 1 ? 9.0 : 0.0) * (double)K_share + 8.0 * (double)K_share;
     batches = std::max<uint64_t>(1, (uint64_t)std::ceil(need / budget));
   }
-  // ... and so that one rank counts at most ~1.2 G instances per batch: with the usual ~1/5 of them
-  // distinct that is what 2^17 sub-bins of 2 k distinct k-mers hold (128 partitions x 1024 sub-bins)
-  if (!batch_reads) batches = std::max<uint64_t>(batches, (K_share + (1100ull << 20) - 1) / (1100ull << 20));
+  // ... and so that the distinct k-mers one rank counts per batch fit its sub-bins at a load factor of
+  // ~0.65: (128 partitions on one GPU, 64 per rank on several) x 2048 sub-bins x 4096 slots.  The distinct
+  // count is not known yet: a fifth of the instances is typical (E. coli 100x 0.15, chr20 30x 0.18 at
+  // 0.5 % errors); a worse input overflows a bin and re-runs with larger tables.
+  if (!batch_reads) {
+    const double cap_distinct = (N == 1 ? 128.0 : 64.0) * 2048.0 * 4096.0 * 0.65;
+    batches = std::max<uint64_t>(batches, (uint64_t)std::ceil((double)K_share / 5.0 / cap_distinct));
+  }
   if (N > 1) {
     std::vector<uint64_t> all(N);
     dist_allgather_host_u64(c, &batches, 1, all.data());
