@@ -1640,8 +1640,10 @@ void stage_build_seqset_dist(Context* c) {
     DevBuf<uint64_t> qk(std::max<uint32_t>(n1, 1), s), ql(std::max<uint32_t>(n1, 1), s);
     DevBuf<unsigned long long> nq_d(1, s);
     BGX_CUDA(cudaMemsetAsync(nq_d.p, 0, 8, s));
+    ScopedStage st_q(c, "walk_queries");
     if (n1) KLAUNCH(pop_queries_kernel)<<<grid_for(n1, 256), 256, 0, s>>>(store, keys.p, locs.p, n1, 0, qk.p, ql.p, nq_d.p);
     uint32_t nq = (uint32_t)read_u64(nq_d.p, s);
+    st_q.stop();
     Routed q = route_records(c, qk.p, ql.p, nq, sp);
     qk.release();
     ql.release();
@@ -1658,6 +1660,7 @@ void stage_build_seqset_dist(Context* c) {
     st_u.stop();
     c->set_stat("walk_chains", n_list);
     c->set_stat("walk_candidates", n_cand);
+    ScopedStage st_c(c, "walk_candidates");
     DevBuf<uint64_t> ck(std::max<uint32_t>(n_cand, 1), s), cl(std::max<uint32_t>(n_cand, 1), s);
     if (n_list) KLAUNCH(emit_uncovered_kernel)<<<grid_for((uint64_t)n_list * 32, 128), 128, 0, s>>>(store, q.keys.p, q.locs.p, cnt.p,
                                                                                          off.p, list.p, n_list, ck.p, cl.p);
@@ -1675,6 +1678,7 @@ void stage_build_seqset_dist(Context* c) {
     if (n_new) KLAUNCH(emit_uncovered_kernel)<<<grid_for((uint64_t)n_new * 32, 128), 128, 0, s>>>(store, cd.keys.p, cd.locs.p, cnt2.p,
                                                                                         off2.p, list2.p, n_new, nkeys.p, nlocs.p);
     BGX_CUDA(cudaGetLastError());
+    st_c.stop();
     st.stop();
   }
   c->set_stat("walk_new_records", n_new);
@@ -1765,19 +1769,25 @@ void stage_build_seqset_dist(Context* c) {
     DevBuf<int> flags(9, s);  // [0..3] carry to the next rank's entry 0, [4..7] single-base entries, [8] missing
     BGX_CUDA(cudaMemsetAsync(max_len.p, 0, 4, s));
     BGX_CUDA(cudaMemsetAsync(flags.p, 0, 9 * 4, s));
-    if (nb) KLAUNCH(tables_local_kernel)<<<grid_for(nb, 128), 128, 0, s>>>(store, keys.p, locs.p, n2, prev, c->sizes.p, c->shared.p,
-                                                                   max_len.p);
+    {
+      ScopedStage st_l(c, "tables_local");
+      if (nb) KLAUNCH(tables_local_kernel)<<<grid_for(nb, 128), 128, 0, s>>>(store, keys.p, locs.p, n2, prev, c->sizes.p, c->shared.p,
+                                                                     max_len.p);
+      st_l.stop();
+    }
     // prev bits: pop_front(e) tagged with e's first base, routed to the rank whose range holds
     // the first entry it is a prefix of (bs/builder.cpp:85-107)
     {
       DevBuf<uint64_t> qk(std::max<uint32_t>(n2, 1), s), ql(std::max<uint32_t>(n2, 1), s);
       DevBuf<unsigned long long> nq_d(1, s);
       BGX_CUDA(cudaMemsetAsync(nq_d.p, 0, 8, s));
+      ScopedStage st_q(c, "tables_queries");
       if (n2) {
         KLAUNCH(pop_queries_kernel)<<<grid_for(n2, 256), 256, 0, s>>>(store, keys.p, locs.p, n2, 1, qk.p, ql.p, nq_d.p);
         KLAUNCH(single_base_kernel)<<<grid_for(n2, 256), 256, 0, s>>>(keys.p, locs.p, n2, flags.p + 4);
       }
       uint32_t nq = (uint32_t)read_u64(nq_d.p, s);
+      st_q.stop();
       Routed q = route_records(c, qk.p, ql.p, nq, sp2);
       ScopedStage st_p(c, "tables_prev_apply");
       const BucketIndex bi2 = build_bucket_index(c, keys.p, n2, index_buf);
