@@ -1307,6 +1307,19 @@ void stage_count_kmers(Context* c) {
         bo.n_all = h_cnt[0];
         bo.n_solid = h_cnt[1];
         sub_bits_used = std::max(sub_bits_used, sub_bits);
+        if (batches > 1) {
+          // the lists were sized by an upper bound: keep exact-sized copies while the other batches run
+          DevBuf<unsigned long long> exact(std::max<uint64_t>(bo.n_solid, 1), s);
+          if (bo.n_solid) BGX_CUDA(cudaMemcpyAsync(exact.p, bo.solid.p, bo.n_solid * 8, cudaMemcpyDeviceToDevice, s));
+          bo.solid = std::move(exact);
+          if (keep_all) {
+            DevBuf<CountEntry> exact_all(std::max<uint64_t>(bo.n_all, 1), s);
+            if (bo.n_all) BGX_CUDA(cudaMemcpyAsync(exact_all.p, bo.all.p, bo.n_all * sizeof(CountEntry), cudaMemcpyDeviceToDevice, s));
+            bo.all = std::move(exact_all);
+          } else {
+            bo.all.release();
+          }
+        }
         break;
       }
       // a sub-bin had more distinct k-mers than table slots, or the estimate was low: finer bins,

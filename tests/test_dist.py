@@ -94,7 +94,7 @@ def test_assemble_over_gloo(world):
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("world", [2, 4])
+@pytest.mark.parametrize("world", [2, 4, 8])
 @pytest.mark.parametrize("case", ["small", "tiny", "n_and_ragged"])
 def test_multi_gpu_build_matches_oracle(case, world):
     import torch
