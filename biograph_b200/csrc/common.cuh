@@ -45,11 +45,18 @@ constexpr uint64_t kKmerMask = (1ULL << 62) - 1;      // kmer_count_table::k_kme
 constexpr uint64_t kFwdFlag = 1ULL << 63;             // k_fwd_flag  (fwd_starts_read)
 constexpr uint64_t kRevFlag = 1ULL << 62;             // k_rev_flag  (rev_starts_read)
 
-// suffix locator: base address in the corrected-base store << 16 | length
+// suffix locator: base address in the corrected-base store << 16 | tag bits | length
+//   bits 0..12   length (reads are at most 255 bases)
+//   bit  13      kLocPopSeed: the suffix one base shorter was emitted as a seed too, so its pop_front is
+//                covered by construction (it survives the dedup or is a prefix of what does) -- the
+//                sharded closure walk does not have to ask its owner
+//   bits 14..15  first base of the popped entry, on routed prev-bit queries only
 constexpr int kLocLenBits = 16;
+constexpr uint64_t kLocLenMask = (1u << 13) - 1;
+constexpr uint64_t kLocPopSeed = 1u << 13;
 __host__ __device__ __forceinline__ uint64_t make_loc(uint64_t addr, uint32_t len) { return (addr << kLocLenBits) | len; }
 __host__ __device__ __forceinline__ uint64_t loc_addr(uint64_t loc) { return loc >> kLocLenBits; }
-__host__ __device__ __forceinline__ uint32_t loc_len(uint64_t loc) { return (uint32_t)(loc & ((1u << kLocLenBits) - 1)); }
+__host__ __device__ __forceinline__ uint32_t loc_len(uint64_t loc) { return (uint32_t)(loc & kLocLenMask); }
 
 // mask keeping the top nb bases of a word (nb in [0,32])
 __host__ __device__ __forceinline__ uint64_t top_bases_mask(int nb) {

@@ -169,13 +169,14 @@ __global__ void seed_emit_kernel(const uint64_t* __restrict__ store, uint64_t fw
   uint32_t o = seed_off[r];
   uint64_t fa = (fwd_word_base + word_off[r]) * 32, ra = (rc_word_base + word_off[r]) * 32;
   int f = nf[r], v = nr[r];
+  // every seed but the last of its strand pops to the next seed (kLocPopSeed)
   for (int i = 0; i < f; ++i, ++o) {
     keys[o] = suffix_key(store, fa + i, L - i);
-    locs[o] = make_loc(fa + i, L - i);
+    locs[o] = make_loc(fa + i, L - i) | (i + 1 < f ? kLocPopSeed : 0ULL);
   }
   for (int i = 0; i < v; ++i, ++o) {
     keys[o] = suffix_key(store, ra + i, L - i);
-    locs[o] = make_loc(ra + i, L - i);
+    locs[o] = make_loc(ra + i, L - i) | (i + 1 < v ? kLocPopSeed : 0ULL);
   }
 }
 
@@ -389,7 +390,7 @@ __device__ __forceinline__ bool covered(const uint64_t* __restrict__ store, cons
   if (where) *where = lb;
   if (lb >= n) return false;
   const uint64_t el = locs[lb];
-  if (el == xl) return true;  // the very same suffix of the same read (the common case): nothing to compare
+  if ((el & ~kLocPopSeed) == xl) return true;  // the very same suffix of the same read (the common case): nothing to compare
   return prefix_or_equal(store, xk, xl, keys[lb], el);
 }
 
@@ -869,7 +870,7 @@ __device__ __forceinline__ bool covered_next(const uint64_t* __restrict__ store,
   *where = lb;
   if (lb < n) {
     const uint64_t el = locs[lb];
-    return el == xl || prefix_or_equal(store, xk, xl, keys[lb], el);
+    return (el & ~kLocPopSeed) == xl || prefix_or_equal(store, xk, xl, keys[lb], el);
   }
   return next.has && prefix_or_equal(store, xk, xl, next.key, next.loc);
 }
@@ -886,7 +887,8 @@ __global__ void pop_queries_kernel(const uint64_t* __restrict__ store, const uin
   if (i < n) {
     uint64_t l = locs[i];
     int len = (int)loc_len(l);
-    if (len > 1) {
+    // closure walk (no tag): an entry whose pop_front was a seed itself needs no answer
+    if (len > 1 && (tag_base || !(l & kLocPopSeed))) {
       has = true;
       qk = suffix_key(store, loc_addr(l) + 1, len - 1);
       ql = make_loc(loc_addr(l) + 1, len - 1);
