@@ -21,7 +21,7 @@ def units(v, u):
 
 
 out = {}
-p = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "profiles", "traffic.json")
+p = os.environ.get("TRAFFIC_JSON") or os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "profiles", "traffic.json")
 if os.path.exists(p):
     out = {k: v for k, v in json.load(open(p)).items() if isinstance(v, dict)}
 for arg in sys.argv[1:]:
