@@ -329,18 +329,23 @@ class Bgx:
         self._ck(self.L.bgx_seqset_layout(self.h, lay))
         return dict(zip(("n", "n_global", "first", "prev_words", "sub_words", "acc_words"), (int(v) for v in lay)))
 
-    def export_seqset(self):
+    def export_seqset(self, per_entry=True):
+        """per_entry=False: without the uint16 sizes / shared arrays (a file writer takes them as
+        packed_varbit_vector elements from export_varbit instead)"""
         n, ml = C.c_uint64(), C.c_uint32()
         ps, psh = C.c_void_p(), C.c_void_p()
         pb, psub, pacc = (C.c_void_p * 4)(), (C.c_void_p * 4)(), (C.c_void_p * 4)()
         fixed = (C.c_uint64 * 5)()
-        self._ck(self.L.bgx_export_seqset(self.h, C.byref(n), C.byref(ml), C.byref(ps), C.byref(psh), pb, psub, pacc,
-                                          fixed))
+        self._ck(self.L.bgx_export_seqset(self.h, C.byref(n), C.byref(ml), C.byref(ps) if per_entry else None,
+                                          C.byref(psh) if per_entry else None, pb, psub, pacc, fixed))
         N = n.value
         lay = self.seqset_layout()
         words, subw, accw = lay["prev_words"], lay["sub_words"], lay["acc_words"]
-        out = {"n": N, "n_global": lay["n_global"], "first": lay["first"], "max_entry_len": ml.value, "sizes": self._take(ps, N, np.uint16),
-               "shared": self._take(psh, N, np.uint16), "fixed": np.array(list(fixed), dtype=np.uint64)}
+        out = {"n": N, "n_global": lay["n_global"], "first": lay["first"], "max_entry_len": ml.value,
+               "fixed": np.array(list(fixed), dtype=np.uint64)}
+        if per_entry:
+            out["sizes"] = self._take(ps, N, np.uint16)
+            out["shared"] = self._take(psh, N, np.uint16)
         out["prev"] = np.stack([self._take(C.c_void_p(pb[b]), words, np.uint64) for b in range(4)]) if True else None
         out["subaccum"] = [self._take(C.c_void_p(psub[b]), subw, np.uint64) for b in range(4)]
         out["accum"] = [self._take(C.c_void_p(pacc[b]), accw, np.uint64) for b in range(4)]

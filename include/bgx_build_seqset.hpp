@@ -599,11 +599,9 @@ class builder {
   // builder::make_seqset (bs/builder.cpp:207-263) + seqset::finalize: the tables in host memory
   seqset_tables tables() {
     seqset_tables t;
-    uint16_t *sizes = nullptr, *shared = nullptr;
     uint64_t *pb[4], *ps[4], *pa[4];
-    detail::ck(bgx_export_seqset(m_s.ctx(), &t.num_entries, &t.max_entry_len, &sizes, &shared, pb, ps, pa, t.fixed));
-    bgx_free(sizes);
-    bgx_free(shared);
+    // sizes / shared travel as packed_varbit_vector elements (bgx_export_varbit below), not as uint16 arrays
+    detail::ck(bgx_export_seqset(m_s.ctx(), &t.num_entries, &t.max_entry_len, nullptr, nullptr, pb, ps, pa, t.fixed));
     uint64_t lay[6];
     detail::ck(bgx_seqset_layout(m_s.ctx(), lay));
     for (int b = 0; b < 4; ++b) {
