@@ -1237,6 +1237,9 @@ void stage_count_kmers(Context* c) {
     const uint64_t per_bin = (1ull << c_log2) / 2;
     int sub_bits = 0;
     while (sub_bits < kMaxSubBits && ((uint64_t)Pl << sub_bits) * per_bin < est_distinct) ++sub_bits;
+    // the 2048-way split writes 4-word runs (chr20 on 2 GPUs: 15.4 ms against 11.0 at 1024): stay at 1024 while
+    // the tables fill to less than two thirds (the count kernel pays ~10 % for the longer probe chains)
+    if (sub_bits == kMaxSubBits && ((uint64_t)Pl << (kMaxSubBits - 1)) * (per_bin + per_bin / 3) >= est_distinct) --sub_bits;
     if (const char* e = getenv("BGX_SUB_BITS")) sub_bits = std::max(0, std::min(kMaxSubBits, atoi(e)));  // test hook
     BatchOut& bo = outs[b];
     for (int tries = 0;; ++tries) {
