@@ -266,7 +266,10 @@ def verify_against_single_gpu(g, B, dist, rank, world, local, pinned, pinned_mas
     mine = {"first": int(part["first"]), "n": int(part["n"]), "lay": lay,
             "sha": {name: sha(a) for name, a in seqset_members(part)}}
     del part
-    g.clear_reads(); g.reset_results()
+    # the sharded context goes away on EVERY rank before rank 0 starts its own build: closing it unmaps the
+    # peers' exchange buffers and returns this rank's device memory (a block must not be freed while a peer
+    # still has it mapped)
+    g.close()
     torch.cuda.empty_cache()
     parts = [None] * world
     dist.all_gather_object(parts, mine)

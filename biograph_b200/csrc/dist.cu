@@ -254,6 +254,14 @@ void dist_peer_copies(Context* c, const std::vector<PeerCopy>& copies) {
 }
 
 void dist_destroy(Context* c) {
+  // Destroying a sharded context is collective: every rank first unmaps the peers' buffers, then all
+  // ranks meet, and only then is device memory given back (a block must not be freed while a peer still
+  // has it mapped).
+  for (auto& kv : c->dist.ipc_cache) cudaIpcCloseMemHandle(kv.second);
+  c->dist.ipc_cache.clear();
+  if (c->dist.comm && c->dist.nranks > 1) {
+    try { dist_barrier(c); } catch (...) {}
+  }
   for (cudaStream_t st : c->dist.copy_streams) { cudaStreamSynchronize(st); cudaStreamDestroy(st); }
   for (cudaEvent_t ev : c->dist.copy_done) cudaEventDestroy(ev);
   if (c->dist.copy_go) cudaEventDestroy(c->dist.copy_go);

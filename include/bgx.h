@@ -184,12 +184,14 @@ int bgx_export_entries_ascii(bgx_ctx* ctx, uint64_t first, uint64_t count, char*
                              uint64_t** offs);
 
 /* ---- multi-GPU (no reference analogue: the reference is one process) -------------------
- * One context per GPU, one process per GPU.  Rank 0 obtains an id with bgx_dist_unique_id and hands
+ * One context per GPU, driven by one process per GPU or by one host thread per GPU of a single
+ * process (bgx_bs::multi_session).  Rank 0 obtains an id with bgx_dist_unique_id and hands
  * it to every rank out of band (torch.distributed broadcast, MPI, a file); every rank then calls
  * bgx_dist_init before adding its share of the reads.  From then on bgx_count_kmers, bgx_correct,
- * bgx_build_seqset and bgx_run are COLLECTIVE: every rank must call them.  K-mer instances travel
- * to the owner of their hash partition, suffix records to the owner of their prefix range (NCCL
- * all-to-all over NVLink); each rank ends up with a contiguous range of the final seqset whose
+ * bgx_build_seqset, bgx_run and bgx_destroy are COLLECTIVE: every rank must call them.  K-mer
+ * instances travel to the owner of their hash partition, suffix records to the owner of their prefix
+ * range, through peer-mapped device memory (CUDA IPC / peer access over NVLink, an SM copy kernel;
+ * NCCL for the all-gathers and small collectives); each rank ends up with a contiguous range of the final seqset whose
  * length is a multiple of 512 entries (except the last), so the per-rank tables returned by
  * bgx_export_seqset concatenate in rank order into exactly the single-GPU tables.
  * bgx_export_kmers returns the k-mers this rank owns; bgx_export_corrected its own reads. */
