@@ -153,6 +153,12 @@ class multi_session {
       parallel([&](int rank, session& s) { s.dist_init(n_gpus, rank, id); });   // ncclCommInitRank: all ranks at once
     }
   }
+  // destroying a sharded context is collective (bgx.h): every rank goes away on its own thread
+  ~multi_session() {
+    std::vector<std::thread> th;
+    for (auto& s : m_s) th.emplace_back([&s] { s.reset(); });
+    for (auto& t : th) t.join();
+  }
   int size() const { return (int)m_s.size(); }
   session& rank(int r) { return *m_s[(size_t)r]; }
   // f(rank, session) on every rank, each from its own host thread; the first exception is rethrown
