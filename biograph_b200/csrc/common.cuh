@@ -172,17 +172,26 @@ __device__ __forceinline__ uint4 ld_stream_u4(const uint4* p) {
 // One bucket = one DRAM sector = one 256-bit load.  A key lives in the first bucket, walking
 // linearly from its home bucket, that had a free slot when it was inserted; buckets fill in slot
 // order and nothing is ever deleted, so a lookup stops at the first bucket with an empty slot.
-template <bool L1_ALLOCATE = false>
+// pf: L2 prefetch-size hint of the load (PTX .L2::64B / ::128B / ::256B; 0 = none given).  A probe wants
+// ONE 32-byte sector; what the memory system fetches per miss is measured per setting (profiles/r2m_*).
 __device__ __forceinline__ void ld_bucket4(const unsigned long long* __restrict__ set, uint64_t bucket,
-                                           unsigned long long (&k)[4]) {
-  if (L1_ALLOCATE)
-    asm volatile("ld.global.nc.v4.u64 {%0,%1,%2,%3}, [%4];"
-                 : "=l"(k[0]), "=l"(k[1]), "=l"(k[2]), "=l"(k[3])
-                 : "l"(set + 4 * bucket));
+                                           unsigned long long (&k)[4], int pf = 0) {
+  const unsigned long long* p = set + 4 * bucket;
+  if (pf == 64)
+    asm volatile("ld.global.nc.L1::no_allocate.L2::64B.v4.u64 {%0,%1,%2,%3}, [%4];"
+                 : "=l"(k[0]), "=l"(k[1]), "=l"(k[2]), "=l"(k[3]) : "l"(p));
+  else if (pf == 128)
+    asm volatile("ld.global.nc.L1::no_allocate.L2::128B.v4.u64 {%0,%1,%2,%3}, [%4];"
+                 : "=l"(k[0]), "=l"(k[1]), "=l"(k[2]), "=l"(k[3]) : "l"(p));
+  else if (pf == 256)
+    asm volatile("ld.global.nc.L1::no_allocate.L2::256B.v4.u64 {%0,%1,%2,%3}, [%4];"
+                 : "=l"(k[0]), "=l"(k[1]), "=l"(k[2]), "=l"(k[3]) : "l"(p));
+  else if (pf == 1)   // plain coherent load (no .nc)
+    asm volatile("ld.global.L1::no_allocate.v4.u64 {%0,%1,%2,%3}, [%4];"
+                 : "=l"(k[0]), "=l"(k[1]), "=l"(k[2]), "=l"(k[3]) : "l"(p));
   else
     asm volatile("ld.global.nc.L1::no_allocate.v4.u64 {%0,%1,%2,%3}, [%4];"
-                 : "=l"(k[0]), "=l"(k[1]), "=l"(k[2]), "=l"(k[3])
-                 : "l"(set + 4 * bucket));
+                 : "=l"(k[0]), "=l"(k[1]), "=l"(k[2]), "=l"(k[3]) : "l"(p));
 }
 // the stored word of `canon` if the bucket holds it, else kEmptyKey; *more = the bucket is full
 // and does not hold it (the key may sit in the next bucket)

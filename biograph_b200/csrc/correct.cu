@@ -62,6 +62,7 @@ struct Params {
   const unsigned long long* set;
   uint64_t set_mask;   // buckets - 1 (a bucket = 4 slots = one 32-byte sector)
   int set_shift;       // 2k - log2(buckets): the home bucket is the TOP bits of the (2k-bit) hash
+  int pf;              // L2 prefetch-size hint of the bucket loads (ld_bucket4)
 };
 
 // solid mask of one read: bit (p & 31) of word (p >> 5) = the k-mer starting at read position p is
@@ -134,7 +135,7 @@ __device__ __forceinline__ unsigned long long solid_find(const Params& P, uint64
   uint64_t b = khash(canon, P.k) >> P.set_shift;
   for (;;) {
     unsigned long long kk[4];
-    ld_bucket4(P.set, b, kk);
+    ld_bucket4(P.set, b, kk, P.pf);
     bool more;
     const unsigned long long e = bucket4_match(kk, canon, &more);
     if (!more) return e;
@@ -355,7 +356,7 @@ __global__ void __launch_bounds__(kProbeThreads, (MAXIT <= 4 ? 3 : 1)) probe_ker
       canon[it] = canonicalize(win >> (64 - 2 * k), k, fl);
       flip[it] = fl;
       slot[it] = khash(canon[it], k) >> P.set_shift;
-      if (live[it]) ld_bucket4(P.set, slot[it], cur[it]);
+      if (live[it]) ld_bucket4(P.set, slot[it], cur[it], P.pf);
       else cur[it][0] = cur[it][1] = cur[it][2] = cur[it][3] = kEmptyKey;
     }
     uint32_t my_mask = 0;       // lane it keeps the solid mask word of step it
@@ -370,7 +371,7 @@ __global__ void __launch_bounds__(kProbeThreads, (MAXIT <= 4 ? 3 : 1)) probe_ker
       // in rounds over all steps at once was measured slower: 5.5 against 4.4 ms on E. coli 100x.)
       while (live[it] && more) {
         slot[it] = (slot[it] + 1) & P.set_mask;
-        ld_bucket4(P.set, slot[it], cur[it]);
+        ld_bucket4(P.set, slot[it], cur[it], P.pf);
         e = bucket4_match(cur[it], canon[it], &more);
       }
       const bool found = live[it] && e != kEmptyKey;
@@ -707,6 +708,8 @@ void stage_correct(Context* c) {
   P.set = c->solid.p;
   P.set_mask = c->solid_slots / 4 - 1;
   P.set_shift = 2 * P.k;
+  P.pf = 0;
+  if (const char* e = getenv("BGX_PROBE_PF")) P.pf = atoi(e);  // experiment hook
   for (uint64_t b = c->solid_slots / 4; b > 1; b >>= 1) --P.set_shift;
   const int max_kmers = std::max<int>((int)c->max_len - P.k + 1, 1);
   const int mask_words = max_kmers <= 128 ? 4 : 8;
