@@ -42,7 +42,7 @@ EXPORTS = ["bgx_default_options", "bgx_last_error", "bgx_version", "bgx_device_c
            "bgx_free", "bgx_add_reads_ascii", "bgx_add_reads_fastq", "bgx_add_reads_packed", "bgx_add_reads_packed_async", "bgx_count_kmers", "bgx_export_kmers",
            "bgx_correct", "bgx_export_corrected", "bgx_export_reads", "bgx_build_seqset", "bgx_export_seqset",
            "bgx_export_entries_ascii", "bgx_lookup_reads", "bgx_build_readmap", "bgx_run", "bgx_reset_results", "bgx_clear_reads", "bgx_stats_json", "bgx_timer_start", "bgx_timer_stop",
-           "bgx_launch_count", "bgx_debug_sort_pairs", "bgx_dist_unique_id", "bgx_dist_init", "bgx_seqset_layout", "bgx_seed_uncorrected", "bgx_export_varbit"]
+           "bgx_launch_count", "bgx_debug_khash", "bgx_debug_count_plan", "bgx_debug_sort_pairs", "bgx_dist_unique_id", "bgx_dist_init", "bgx_seqset_layout", "bgx_seed_uncorrected", "bgx_export_varbit"]
 
 
 def load_library():
@@ -86,6 +86,11 @@ def load_library():
     L.bgx_timer_stop.argtypes = [vp, C.POINTER(C.c_double)]
     L.bgx_launch_count.restype = C.c_uint64
     L.bgx_debug_sort_pairs.argtypes = [vp, vp, vp, C.c_uint64, C.c_int, C.c_int]
+    L.bgx_debug_khash.restype = C.c_uint64
+    L.bgx_debug_khash.argtypes = [C.c_uint64, C.c_int32, C.c_int32]
+    L.bgx_debug_count_plan.restype = None
+    L.bgx_debug_count_plan.argtypes = [C.c_uint64, C.c_uint64, C.c_int32, C.c_uint64, C.c_uint64, C.c_uint64, u64p,
+                                       C.POINTER(C.c_int32)]
     L.bgx_dist_unique_id.argtypes = [vp]
     L.bgx_dist_init.argtypes = [vp, C.c_int32, C.c_int32, vp]
     L.bgx_seqset_layout.argtypes = [vp, C.c_uint64 * 6]

@@ -394,6 +394,16 @@ int bgx_debug_sort_pairs(bgx_ctx* x, uint64_t* keys, uint64_t* vals, uint64_t n,
   })
 }
 
+// host-only hooks for the CPU tests: the k-mer hash and its inverse, and the counting plan
+uint64_t bgx_debug_khash(uint64_t x, int32_t k, int32_t inverse) { return inverse ? khash_inv(x, k) : khash(x, k); }
+void bgx_debug_count_plan(uint64_t k_local, uint64_t k_share, int32_t n_ranks, uint64_t total_mem, uint64_t batch_reads,
+                          uint64_t n_reads, uint64_t* batches, int32_t* part_bits) {
+  int rank_bits = 0;
+  while ((1 << rank_bits) < n_ranks) ++rank_bits;
+  *batches = plan_count_batches(k_local, k_share, n_ranks, total_mem, batch_reads, n_reads);
+  *part_bits = plan_part_bits(k_share, *batches, rank_bits);
+}
+
 uint64_t bgx_launch_count(void) { return __atomic_load_n(&bgx::g_launches, __ATOMIC_RELAXED); }
 
 }  // extern "C"

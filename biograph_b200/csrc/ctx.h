@@ -132,6 +132,10 @@ void reads_append_fastq(Context* c, const char* text, uint64_t size, uint64_t* n
 // orders every pending upload chunk before whatever the main stream does next (and forgets them)
 void reads_ready(Context* c);
 void stage_count_kmers(Context* c);
+// planning of the counting (pure host arithmetic, kmer.cu)
+uint64_t plan_count_batches(uint64_t K_local, uint64_t K_share, int N, uint64_t total_mem, uint64_t batch_reads,
+                            uint64_t n_reads);
+int plan_part_bits(uint64_t K_share, uint64_t batches, int rank_bits);
 void export_kmers(Context* c, uint32_t min_count, uint64_t* n, uint64_t** kmers, uint32_t** fwd, uint32_t** rev,
                   uint8_t** flags);
 void stage_correct(Context* c);

@@ -36,6 +36,49 @@
 #include "ctx.h"
 
 namespace bgx {
+
+// ---- planning (pure host arithmetic; bgx_debug_count_plan exposes it to the CPU tests) ---------------------
+static uint64_t pow2_ceil_u64(uint64_t x) {
+  uint64_t p = 1;
+  while (p < x) p <<= 1;
+  return p;
+}
+
+// Hash-range batches of the counting (a power of two).  One batch keeps all K instance words twice
+// (pass-1 output and the split copy; multi-GPU also what the peers send) in HBM; more batches bound
+// those buffers to ~45 % of the device so that inputs like GRCh38 30x on 8 GPUs still fit.
+// batch_reads (option count_batch_reads / BGX_COUNT_BATCH_READS) asks for at least ceil(reads / that).
+uint64_t plan_count_batches(uint64_t K_local, uint64_t K_share, int N, uint64_t total_mem, uint64_t batch_reads,
+                            uint64_t n_reads) {
+  uint64_t batches = 1;
+  if (batch_reads) {
+    batches = std::max<uint64_t>(1, (n_reads + batch_reads - 1) / batch_reads);
+  } else {
+    const double budget = 0.45 * (double)total_mem;
+    // 8 B per word + 1/8 slack out of pass 1, what arrives from the peers, the split copy
+    const double need = 9.0 * (double)K_local + (N > 1 ? 9.0 : 0.0) * (double)K_share + 8.0 * (double)K_share;
+    batches = std::max<uint64_t>(1, (uint64_t)std::ceil(need / budget));
+    // ... and so that the distinct k-mers one rank counts per batch fit its sub-bins at a load factor of
+    // ~0.65: (128 partitions on one GPU, 64 per rank on several) x 2048 sub-bins x 4096 slots.  The distinct
+    // count is not known yet: a fifth of the instances is typical (E. coli 100x 0.15, chr20 30x 0.18 at
+    // 0.5 % errors); a worse input overflows a bin and re-runs with larger tables.
+    const double cap_distinct = (N == 1 ? 128.0 : 64.0) * 2048.0 * 4096.0 * 0.65;
+    batches = std::max<uint64_t>(batches, (uint64_t)std::ceil((double)K_share / 5.0 / cap_distinct));
+  }
+  return pow2_ceil_u64(batches);
+}
+
+// Hash partitions per batch (log2).  One GPU: 128, 256 once a partition would pass 8 M words.  Several
+// GPUs: 64 per rank -- pass 1's runs shrink with the TOTAL count (1024 partitions cost it 85 % more time on
+// B200) and pass 2 splits finer instead (up to 2048 sub-bins per partition).  Rank r owns the contiguous
+// block [r*P/N, (r+1)*P/N).
+int plan_part_bits(uint64_t K_share, uint64_t batches, int rank_bits) {
+  int part_bits = 7;
+  while (part_bits < 8 && ((K_share / batches) >> part_bits) > (8ull << 20)) ++part_bits;
+  part_bits = std::max(part_bits, rank_bits + 6);
+  return std::max(std::min(part_bits, 10), rank_bits);
+}
+
 namespace {
 
 // ---- instance words ---------------------------------------------------------------------------
@@ -47,7 +90,6 @@ namespace {
 //             flipped (bs/kmer_counter.h:318-321, bs/kmer_count_table.h:82-86)
 // 2k - drop + 3 <= 62 - 7 + 3 bits, so k = 31 fits too.
 constexpr uint64_t kWFwd = 1, kWRev = 2, kWFlip = 4;
-constexpr int kMinPartBits = 7;
 constexpr int kMaxPartBits = 10;            // <= 1024 hash partitions per batch
 constexpr int kMaxSubBits = 11;             // <= 2048 sub-bins per partition
 constexpr int kPartThreads = 256;
@@ -1111,31 +1153,14 @@ void upload_owned(Context* c, const Owned& own, OwnedDev* d) {
 // ceil(reads / that) batches.
 uint64_t choose_batches(Context* c, uint64_t K_local, uint64_t K_share) {
   const int N = c->dist.nranks;
-  uint64_t batches = 1;
   uint64_t batch_reads = c->opt.count_batch_reads > 0 ? (uint64_t)c->opt.count_batch_reads : 0;
   if (const char* e = getenv("BGX_COUNT_BATCH_READS")) batch_reads = strtoull(e, nullptr, 10);  // test hook
-  if (batch_reads) {
-    batches = std::max<uint64_t>(1, (c->n_reads + batch_reads - 1) / batch_reads);
-  } else {
-    const double budget = 0.45 * (double)c->total_mem;
-    // 8 B per word + 1/8 slack out of pass 1, what arrives from the peers, the split copy
-    const double need = 9.0 * (double)K_local + (N > 1 ? 9.0 : 0.0) * (double)K_share + 8.0 * (double)K_share;
-    batches = std::max<uint64_t>(1, (uint64_t)std::ceil(need / budget));
-  }
-  // ... and so that the distinct k-mers one rank counts per batch fit its sub-bins at a load factor of
-  // ~0.65: (128 partitions on one GPU, 64 per rank on several) x 2048 sub-bins x 4096 slots.  The distinct
-  // count is not known yet: a fifth of the instances is typical (E. coli 100x 0.15, chr20 30x 0.18 at
-  // 0.5 % errors); a worse input overflows a bin and re-runs with larger tables.
-  if (!batch_reads) {
-    const double cap_distinct = (N == 1 ? 128.0 : 64.0) * 2048.0 * 4096.0 * 0.65;
-    batches = std::max<uint64_t>(batches, (uint64_t)std::ceil((double)K_share / 5.0 / cap_distinct));
-  }
+  uint64_t batches = plan_count_batches(K_local, K_share, N, c->total_mem, batch_reads, c->n_reads);
   if (N > 1) {
     std::vector<uint64_t> all(N);
     dist_allgather_host_u64(c, &batches, 1, all.data());
     for (uint64_t v : all) batches = std::max(batches, v);
   }
-  batches = pow2_ceil(batches);
   BGX_CHECK(batches <= 4096, "k-mer counting would need more than 4096 batches");
   return batches;
 }
@@ -1176,17 +1201,8 @@ void stage_count_kmers(Context* c) {
   const int batch_bits = log2_exact(batches);
   c->set_stat("count_batches", (double)batches);
 
-  // Partitions per batch: pass 1 writes longer coalesced runs with fewer partitions (128 measured
-  // best on B200), but every rank needs at least one, and a partition should stay well below 2^31
-  // words.  Rank r owns the contiguous block [r*P/N, (r+1)*P/N) (same P on every rank).
-  // One GPU: 128 partitions, 256 once a partition would pass 8 M words.  Several GPUs: 64 partitions per
-  // rank (pass 1's runs shrink with the TOTAL count: 1024 partitions cost it 85 % more time on B200),
-  // pass 2 then splits finer (up to 2048 sub-bins per partition).
-  int part_bits = kMinPartBits;
-  while (part_bits < 8 && ((K_share / batches) >> part_bits) > (8ull << 20)) ++part_bits;
-  part_bits = std::max(part_bits, rank_bits + 6);
-  if (const char* e = getenv("BGX_PART_BITS")) part_bits = std::max(1, atoi(e));
-  part_bits = std::max(std::min(part_bits, kMaxPartBits), rank_bits);
+  int part_bits = plan_part_bits(K_share, batches, rank_bits);
+  if (const char* e = getenv("BGX_PART_BITS")) part_bits = std::max(rank_bits, std::min(kMaxPartBits, atoi(e)));  // experiment hook
   BGX_CHECK(2 * k - batch_bits - part_bits >= 16, "k-mer too short for this many batches / partitions");
   int c_log2 = 12;  // 4096 slots = 64 KB of shared memory per block, three blocks per SM
   if (const char* e = getenv("BGX_BIN_SLOTS_LOG2")) c_log2 = std::max(9, std::min(13, atoi(e)));  // experiment hook

@@ -224,6 +224,13 @@ int bgx_timer_start(bgx_ctx* ctx);
 int bgx_timer_stop(bgx_ctx* ctx, double* elapsed_ms);
 uint64_t bgx_launch_count(void);
 
+/* Host-only test hooks (no GPU needed): the bijective k-mer hash of the counting passes and its
+ * inverse, and the plan of a count (hash-range batches, log2 of the hash partitions per batch) for
+ * k_local instances on this rank, k_share owned per rank, n_ranks GPUs of total_mem bytes each. */
+uint64_t bgx_debug_khash(uint64_t x, int32_t k, int32_t inverse);
+void bgx_debug_count_plan(uint64_t k_local, uint64_t k_share, int32_t n_ranks, uint64_t total_mem,
+                          uint64_t batch_reads, uint64_t n_reads, uint64_t* batches, int32_t* part_bits);
+
 /* Test hook for the device-wide primitives (no reference analogue): stable LSD radix sort of
  * n (key, value) pairs held in HOST arrays on key bits [begin_bit, end_bit), in place, run by the
  * same kernels the seqset stage uses. */

@@ -79,3 +79,43 @@ def test_synth_reads_are_deterministic(B):
     for r in err[:50]:
         s = r.tobytes().decode()
         assert s in gs or O.revcomp(s) in gs
+
+
+def test_khash_is_a_bijection_with_its_inverse(B):
+    """the counting passes partition by the top bits of khash and drop them from the instance words; the
+    k-mer comes back through khash_inv (host copies of the device functions, common.cuh)"""
+    import random
+    L = B.load_library()
+    rng = random.Random(5)
+    for k in (16, 21, 30, 31):
+        seen = set()
+        for _ in range(20000):
+            x = rng.getrandbits(2 * k)
+            h = L.bgx_debug_khash(x, k, 0)
+            assert h < (1 << (2 * k)) and L.bgx_debug_khash(h, k, 1) == x
+            seen.add(h >> (2 * k - 10))
+        assert len(seen) == 1024          # every top-10-bit partition is hit
+    # consecutive k-mers (a shift by one base) land in unrelated partitions
+    parts = [L.bgx_debug_khash(i << 2, 30, 0) >> 52 for i in range(1, 4097)]
+    assert len(set(parts)) > 200
+
+
+@pytest.mark.parametrize("name,k_local,n,mem_gb,want_batches,want_part_bits", [
+    ("E. coli 100x, 1 GPU", 398_406_294, 1, 183, 1, 7),
+    ("chr20 30x, 1 GPU", 1_559_548_914, 1, 183, 1, 8),
+    ("chr20 30x per rank, 2 GPUs", 1_559_548_914, 2, 183, 1, 8),
+    ("chr20 30x per rank, 4 GPUs", 1_559_548_914, 4, 183, 1, 8),
+    ("chr20 30x per rank, 8 GPUs", 1_559_548_914, 8, 183, 1, 9),
+    ("GRCh38 30x over 8 GPUs", 9_377_500_000, 8, 183, 8, 9),
+    ("8 x chr20 on one GPU (the N=8 parity build)", 12_476_391_312, 1, 183, 4, 8),
+])
+def test_count_plan(B, name, k_local, n, mem_gb, want_batches, want_part_bits):
+    """hash-range batches and partitions per batch for the inputs of BASELINE.json's configs"""
+    import ctypes as C
+    L = B.load_library()
+    batches, pb = C.c_uint64(), C.c_int32()
+    L.bgx_debug_count_plan(k_local, k_local, n, mem_gb << 30, 0, 1, C.byref(batches), C.byref(pb))
+    assert (batches.value, pb.value) == (want_batches, want_part_bits), name
+    # count_batch_reads asks for at least reads / that many batches, rounded up to a power of two
+    L.bgx_debug_count_plan(k_local, k_local, n, mem_gb << 30, 1000, 5000, C.byref(batches), C.byref(pb))
+    assert batches.value == 8
