@@ -69,8 +69,11 @@ void* dev_alloc(size_t bytes, cudaStream_t s) {
     }
     if (e != cudaSuccess) {
       cudaGetLastError();
+      size_t free_b = 0, total_b = 0;
+      cudaMemGetInfo(&free_b, &total_b);
       throw Error("out of device memory allocating " + std::to_string(bytes) + " bytes (" +
-                  std::to_string(a.live_bytes) + " live)");
+                  std::to_string(a.live_bytes) + " live in this library, " + std::to_string(free_b) + " of " +
+                  std::to_string(total_b) + " free on the device)");
     }
   }
   a.live[p] = {sz, s};

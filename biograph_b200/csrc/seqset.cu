@@ -1723,6 +1723,12 @@ void stage_build_seqset_dist(Context* c) {
       recv_off[src] = m;
       m += recv_cnt[src];
     }
+    // the ping-pong partners and the walk's records are not needed any more: give them back first
+    // (GRCh38 30x on 8 GPUs: 12 GB per rank, the difference between fitting and not)
+    keys_alt.release();
+    locs_alt.release();
+    nkeys.release();
+    nlocs.release();
     DevBuf<uint64_t> k2(std::max<uint64_t>(m, 1), s), l2(std::max<uint64_t>(m, 1), s);
     dist_alltoallv(c, keys.p, send_off.data(), send_cnt.data(), k2.p, recv_off.data(), recv_cnt.data(), 8);
     dist_alltoallv(c, locs.p, send_off.data(), send_cnt.data(), l2.p, recv_off.data(), recv_cnt.data(), 8);

@@ -73,7 +73,7 @@ def gen_reads_packed(genome, n_reads, seed, device, chunk=1 << 20, error=0.005):
     return out
 
 
-def build(world, rank, local, packed, runs):
+def build(world, rank, local, packed, runs, free_input=None):
     n = packed.shape[0]
     lens = torch.full((n,), READ_LEN, dtype=torch.int16, device=packed.device)
     g = B.Bgx(device=local)
@@ -83,6 +83,10 @@ def build(world, rank, local, packed, runs):
         g.dist_init(world, rank, ids[0])
     torch.cuda.synchronize()
     g.add_reads_packed_ptr(packed.data_ptr(), None, None, lens.data_ptr(), n)
+    torch.cuda.synchronize()
+    del lens, packed
+    if free_input is not None:   # the library holds its own copy now
+        free_input()
     best, stats, all_ms = None, None, []
     for i in range(runs):
         g.reset_results()
@@ -126,7 +130,14 @@ def main():
         torch.cuda.empty_cache()
         torch.cuda.synchronize()
         t_gen = time.time() - t0
-        g, ms, st = build(world, rank, local, packed, args.runs)
+        host_copy = packed.cpu().reshape(-1) if verify else None
+        holder = [packed]
+        del packed
+
+        def free_input():
+            holder.clear()
+            torch.cuda.empty_cache()
+        g, ms, st = build(world, rank, local, holder[0], args.runs, free_input)
         peak = torch.tensor([float(st.get("peak_device_bytes", 0))], dtype=torch.float64, device="cuda")
         ent = torch.tensor([float(st.get("entries", 0))], dtype=torch.float64, device="cuda")
         if world > 1:
@@ -134,7 +145,7 @@ def main():
             dist.all_reduce(ent, op=dist.ReduceOp.SUM)
         parity = None
         if verify:
-            pinned = packed.cpu().reshape(-1)
+            pinned = host_copy
             lens = torch.full((per,), READ_LEN, dtype=torch.int16).view(torch.uint8)
             if world > 1:
                 parity = bench.verify_against_single_gpu(g, B, dist, rank, world, local, pinned, None, lens, per)
@@ -154,7 +165,6 @@ def main():
             line["sort_dedup"] = {"ms": round(sd_ms, 2), "alg_bytes": sd_bytes, "achieved_gbs": sd_bytes / sd_ms / 1e6,
                                   "frac_of_measured_hbm_peak": sd_bytes / sd_ms / 1e6 / peak_hbm}
         g.close()
-        del packed
         torch.cuda.empty_cache()
         if rank == 0:
             print(json.dumps(line), flush=True)
