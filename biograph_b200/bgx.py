@@ -42,7 +42,13 @@ EXPORTS = ["bgx_default_options", "bgx_last_error", "bgx_version", "bgx_device_c
            "bgx_free", "bgx_add_reads_ascii", "bgx_add_reads_fastq", "bgx_add_reads_packed", "bgx_add_reads_packed_async", "bgx_count_kmers", "bgx_export_kmers",
            "bgx_correct", "bgx_export_corrected", "bgx_export_reads", "bgx_build_seqset", "bgx_export_seqset",
            "bgx_export_entries_ascii", "bgx_lookup_reads", "bgx_build_readmap", "bgx_run", "bgx_reset_results", "bgx_clear_reads", "bgx_stats_json", "bgx_timer_start", "bgx_timer_stop",
-           "bgx_launch_count", "bgx_debug_khash", "bgx_debug_count_plan", "bgx_debug_sort_pairs", "bgx_dist_unique_id", "bgx_dist_init", "bgx_seqset_layout", "bgx_seed_uncorrected", "bgx_export_varbit"]
+           "bgx_launch_count", "bgx_debug_khash", "bgx_debug_count_plan", "bgx_debug_sort_pairs", "bgx_dist_unique_id", "bgx_dist_init", "bgx_seqset_layout", "bgx_seed_uncorrected", "bgx_export_varbit",
+           "bgx_merge_seqsets", "bgx_export_mergemap", "bgx_migrate_bits", "bgx_export_flat_ascii"]
+
+
+class SeqsetPart(C.Structure):
+    """bgx_seqset_part (include/bgx.h): one input of a merge"""
+    _fields_ = [("n_entries", C.c_uint64), ("sizes", C.c_void_p), ("prev_bits", C.c_void_p * 4)]
 
 
 def load_library():
@@ -96,6 +102,10 @@ def load_library():
     L.bgx_seqset_layout.argtypes = [vp, C.c_uint64 * 6]
     L.bgx_seed_uncorrected.argtypes = [vp]
     L.bgx_export_varbit.argtypes = [vp, C.c_int32, C.POINTER(vp), u64p, C.POINTER(C.c_uint32), u64p]
+    L.bgx_merge_seqsets.argtypes = [vp, C.POINTER(SeqsetPart), C.c_uint32, C.c_uint64]
+    L.bgx_export_mergemap.argtypes = [vp, C.c_uint32, C.POINTER(vp * 3), u64p, u64p]
+    L.bgx_migrate_bits.argtypes = [vp, C.c_uint32, vp, C.c_uint64, C.POINTER(vp * 3), u64p]
+    L.bgx_export_flat_ascii.argtypes = [vp, C.c_uint32, C.c_uint64, C.c_uint64, C.POINTER(vp), C.POINTER(vp)]
     _LIB = L
     return L
 
@@ -390,6 +400,59 @@ class Bgx:
         return {"n_rows": rows, "read_lengths": self._take(pl, rows, np.uint16), "mate_loop_ptr": self._take(pp, rows, np.uint64),
                 "is_forward": self._take(pf, (rows + 63) // 64, np.uint64), "source_to_mid": bc(src, n_ent),
                 "dest_to_mid": bc(dst, rows)}
+
+    # -- biograph merge (seqset_flat_builder + make_mergemap + seqset_merger) -----------------------
+    def merge_seqsets(self, parts, parallel_splits=0):
+        """parts: list of dicts {"sizes": uint16[n], "prev": uint64[4, ceil(n/64)]} (the members of a seqset
+        file).  Afterwards export_seqset / export_varbit / export_entries return the merged seqset."""
+        keep, arr = [], (SeqsetPart * len(parts))()
+        for i, p in enumerate(parts):
+            sizes = np.ascontiguousarray(p["sizes"], dtype=np.uint16)
+            n = len(sizes)
+            prev = [np.ascontiguousarray(p["prev"][b], dtype=np.uint64) for b in range(4)]
+            for w in prev:
+                if len(w) != (n + 63) // 64:
+                    raise BgxError("merge_seqsets: prev bit vectors must hold ceil(n / 64) words")
+            keep += [sizes] + prev
+            arr[i].n_entries = n
+            arr[i].sizes = sizes.ctypes.data
+            for b in range(4):
+                arr[i].prev_bits[b] = prev[b].ctypes.data
+        self._ck(self.L.bgx_merge_seqsets(self.h, arr, len(parts), int(parallel_splits)))
+        del keep
+
+    def _bitcount3(self, arr, nbits):
+        return {"bits": self._take(C.c_void_p(arr[0]), (nbits + 63) // 64, np.uint64),
+                "subaccum": self._take(C.c_void_p(arr[1]), (nbits + 511) // 512, np.uint64),
+                "accum": self._take(C.c_void_p(arr[2]), (nbits + 1 + 511) // 512, np.uint64), "nbits": nbits}
+
+    def export_mergemap(self, part):
+        """the `merged_entries` bitcount of input `part` (seqset_mergemap): bits / subaccum / accum, n_set"""
+        out = (C.c_void_p * 3)()
+        nb, ns = C.c_uint64(), C.c_uint64()
+        self._ck(self.L.bgx_export_mergemap(self.h, part, C.byref(out), C.byref(nb), C.byref(ns)))
+        r = self._bitcount3(out, int(nb.value))
+        r["n_set"] = int(ns.value)
+        return r
+
+    def migrate_bits(self, part, bits, n_old):
+        """make_readmap::fast_migrate for a bit vector over the entries of input `part` (read_ids/source_to_mid)"""
+        bits = np.ascontiguousarray(bits, dtype=np.uint64)
+        if len(bits) != (int(n_old) + 63) // 64:
+            raise BgxError("migrate_bits: the bit vector must hold ceil(n_old / 64) words")
+        out = (C.c_void_p * 3)()
+        nb = C.c_uint64()
+        self._ck(self.L.bgx_migrate_bits(self.h, part, bits.ctypes.data, int(n_old), C.byref(out), C.byref(nb)))
+        return self._bitcount3(out, int(nb.value))
+
+    def export_flat(self, part, first=0, count=None):
+        """seqset_flat::get(i) of input `part` for i in [first, first + count): list of str"""
+        pb, po = C.c_void_p(), C.c_void_p()
+        count = int(count)
+        self._ck(self.L.bgx_export_flat_ascii(self.h, part, first, count, C.byref(pb), C.byref(po)))
+        offs = self._take(po, count + 1, np.uint64)
+        seq = self._take(pb, int(offs[-1]) if count else 0, np.uint8).tobytes().decode()
+        return [seq[int(offs[i]):int(offs[i + 1])] for i in range(count)]
 
     def reset_results(self):
         self._ck(self.L.bgx_reset_results(self.h))

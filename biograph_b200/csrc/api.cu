@@ -148,6 +148,7 @@ void bgx_destroy(bgx_ctx* x) {
     c.table.release(); c.solid.release(); c.store.release(); c.gstore.release(); c.clen.release(); c.ncorr.release();
     c.next_fwd.release(); c.next_rev.release(); c.ent_key.release(); c.ent_loc.release();
     c.sizes.release(); c.shared.release(); c.prev_bits.release(); c.prev_sub.release(); c.prev_acc.release();
+    merge_release(&c);
   }
   dist_destroy(&x->c);
   dev_trim(s);
@@ -296,6 +297,23 @@ int bgx_export_entries_ascii(bgx_ctx* x, uint64_t first, uint64_t count, char** 
   CTX_GUARD({ export_entries_ascii(c, first, count, bases, offs); })
 }
 
+int bgx_merge_seqsets(bgx_ctx* x, const bgx_seqset_part* parts, uint32_t n_parts, uint64_t parallel_splits) {
+  CTX_GUARD({ stage_merge_seqsets(c, parts, n_parts, parallel_splits); })
+}
+
+int bgx_export_mergemap(bgx_ctx* x, uint32_t part, uint64_t* merged_entries[3], uint64_t* n_bits, uint64_t* n_set) {
+  CTX_GUARD({ export_mergemap(c, part, merged_entries, n_bits, n_set); })
+}
+
+int bgx_migrate_bits(bgx_ctx* x, uint32_t part, const uint64_t* old_bits, uint64_t n_old, uint64_t* migrated[3],
+                     uint64_t* n_bits) {
+  CTX_GUARD({ migrate_bits(c, part, old_bits, n_old, migrated, n_bits); })
+}
+
+int bgx_export_flat_ascii(bgx_ctx* x, uint32_t part, uint64_t first, uint64_t count, char** bases, uint64_t** offs) {
+  CTX_GUARD({ export_flat_ascii(c, part, first, count, bases, offs); })
+}
+
 int bgx_run(bgx_ctx* x) {
   CTX_GUARD({
     stage_count_kmers(c);
@@ -309,6 +327,7 @@ int bgx_reset_results(bgx_ctx* x) {
     c->table.release(); c->solid.release(); c->store.release(); c->gstore.release(); c->clen.release(); c->ncorr.release();
     c->next_fwd.release(); c->next_rev.release(); c->ent_key.release(); c->ent_loc.release();
     c->sizes.release(); c->shared.release(); c->prev_bits.release(); c->prev_sub.release(); c->prev_acc.release();
+    merge_release(c);
     c->counted = c->corrected = c->built = false;
     c->stats.clear();
     c->stat_order.clear();

@@ -2,6 +2,7 @@
 #pragma once
 
 #include <chrono>
+#include <functional>
 #include <map>
 #include <string>
 #include <vector>
@@ -82,6 +83,17 @@ struct Context {
   uint64_t n_entries_global = 0;       // multi-GPU: entries over all ranks; this rank holds
   uint64_t first_entry_global = 0;     //   [first_entry_global, first_entry_global + n_entries)
 
+  // ---- seqset merge (bgx_merge_seqsets; `biograph merge`) -----------------------------
+  // after a merge: store = the flattened entries of every input (seqset_flat), ent_* / tables = the merged
+  // seqset, and per input its flat locators (entry i -> store address, length) and its mergemap
+  struct MergePart {
+    uint64_t n = 0;            // entries of the input
+    DevBuf<uint64_t> flat_loc; // n locators into `store`: seqset_flat::get(i)
+  };
+  std::vector<MergePart> merge_parts;
+  DevBuf<unsigned long long> mergemap;   // merge_parts.size() bit vectors of n_entries bits, mergemap_words apart
+  uint64_t mergemap_words = 0;
+
   // ---- stats ---------------------------------------------------------------------------------
   std::map<std::string, double> stats;       // numeric stats (ms, counts, bytes)
   std::vector<std::string> stat_order;
@@ -142,6 +154,23 @@ void stage_correct(Context* c);
 void stage_seed_uncorrected(Context* c);
 void export_varbit(Context* c, int which, uint64_t** words, uint64_t* n_words, uint32_t* bits, uint64_t* max_value);
 void stage_build_seqset(Context* c);
+// sort -> dedup -> closure -> tables on n (key, loc) records over c->store (seqset.cu).  A merge passes
+// hooks: after_dedup sees the sorted records before the first dedup and where each one went (the
+// mergemap), parallel_splits selects seqset_merger's placement of the prev bits (1 = the builder's).
+struct MergeHooks {
+  uint64_t parallel_splits = 100000;   // g_parallel_splits, modules/io/parallel.cpp:13
+  std::function<void(const uint64_t* sorted_locs, uint32_t n, const uint32_t* pos, uint32_t n_kept)> after_dedup;
+};
+void build_seqset_from_records(Context* c, DevBuf<uint64_t>& keys, DevBuf<uint64_t>& locs, DevBuf<uint64_t>& keys_alt,
+                               DevBuf<uint64_t>& locs_alt, uint32_t n, const MergeHooks* mh);
+// bitcount::finalize of a device bit vector into host arrays {bits, subaccum, accum}; *total = set bits
+void bitcount_to_host(Context* c, const unsigned long long* bits, uint64_t nbits, uint64_t* out[3], uint64_t* total = nullptr);
+// merge.cu
+void stage_merge_seqsets(Context* c, const bgx_seqset_part* parts, uint32_t n_parts, uint64_t parallel_splits);
+void export_mergemap(Context* c, uint32_t part, uint64_t* out[3], uint64_t* n_bits, uint64_t* n_set);
+void migrate_bits(Context* c, uint32_t part, const uint64_t* old_bits, uint64_t n_old, uint64_t* out[3], uint64_t* n_bits);
+void export_flat_ascii(Context* c, uint32_t part, uint64_t first, uint64_t count, char** bases, uint64_t** offs);
+void merge_release(Context* c);
 void lookup_reads(Context* c, uint64_t* n_reads, uint64_t** fwd_entry, uint64_t** rc_entry);
 void build_readmap(Context* c, int paired, uint64_t* n_rows, uint16_t** read_lengths, uint64_t** mate_loop_ptr,
                    uint64_t** is_forward, uint64_t* read_ids_source[3], uint64_t* read_ids_dest[3]);

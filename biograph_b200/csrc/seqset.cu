@@ -24,6 +24,7 @@
 #include <vector>
 
 #include "ctx.h"
+#include "merge_core.cuh"
 
 namespace bgx {
 namespace {
@@ -738,6 +739,28 @@ __global__ void __launch_bounds__(128) tables_kernel(const uint64_t* __restrict_
   if (lane_id() == 0 && mx) atomicMax(max_len, mx);
 }
 
+// merge mode: the prev bit of entry i where seqset_merger::merge_range puts it (merge_core.cuh,
+// modules/bio_base/seqset_merger.cpp:109-197 over generate_chunks(0, n, nsplits)); thread per entry
+__global__ void __launch_bounds__(128) merge_prev_kernel(const uint64_t* __restrict__ store,
+                                                         const uint64_t* __restrict__ keys,
+                                                         const uint64_t* __restrict__ locs, uint32_t n, BucketIndex bi,
+                                                         uint64_t nsplits, unsigned long long* __restrict__ prev_bits,
+                                                         uint64_t prev_words, int* __restrict__ missing) {
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const uint64_t l = locs[i];
+  const int xn = (int)loc_len(l) - 1;
+  uint32_t lo0 = 0, hi0 = n;
+  if (xn > 0) {  // narrow the search to the bucket of x's leading bases
+    const uint64_t b = suffix_key(store, loc_addr(l) + 1, xn) >> bi.shift;
+    lo0 = bi.start[b];
+    hi0 = bi.start[b + 1];
+  }
+  const uint32_t t = mergecore::merge_prev_target(store, locs, n, i, lo0, hi0, nsplits);
+  if (t == mergecore::kNone) { *missing = 1; return; }
+  mergecore::or_bit(prev_bits + (uint64_t)(keys[i] >> 62) * prev_words, t);
+}
+
 // bitcount::finalize (modules/io/bitcount.cpp:84-123): per 512-bit group popcounts
 __global__ void bitcount_groups_kernel(const unsigned long long* __restrict__ bits, uint64_t words, uint64_t groups,
                                        uint32_t* __restrict__ group_pop, unsigned long long* __restrict__ subaccum) {
@@ -1270,10 +1293,23 @@ void stage_build_seqset(Context* c) {
     st.stop();
   }
 
+  build_seqset_from_records(c, keys, locs, keys_alt, locs_alt, n, nullptr);
+  st_all.stop();
+}
+
+// Steps 2-5 on n (key, loc) records over c->store: what `biograph create` runs after seeding, and what a
+// seqset merge runs on one record per input entry (merge.cu; `mh` non-null).
+void build_seqset_from_records(Context* c, DevBuf<uint64_t>& keys, DevBuf<uint64_t>& locs, DevBuf<uint64_t>& keys_alt,
+                               DevBuf<uint64_t>& locs_alt, uint32_t n, const MergeHooks* mh) {
+  cudaStream_t s = c->stream;
   // 2. sort + dedup
   sort_records(c, keys, locs, keys_alt, locs_alt, n, "r1");
-  uint32_t n1 = dedup_records(c, keys, locs, keys_alt, locs_alt, n);
+  DevBuf<uint32_t> pos1;
+  uint32_t n1 = dedup_records(c, keys, locs, keys_alt, locs_alt, n, NextRec{0, 0, 0}, nullptr, mh != nullptr ? &pos1 : nullptr);
   c->set_stat("entries_round1", n1);
+  // merge: the alt buffers still hold the sorted records before the dedup, pos1 where each one went
+  if (mh != nullptr && n) mh->after_dedup(locs_alt.p, n, pos1.p, n1);
+  pos1.release();
 
   // 3. closure walk: the new records are emitted into their own buffers
   uint32_t n_new = 0;
@@ -1310,6 +1346,9 @@ void stage_build_seqset(Context* c) {
     st.stop();
   }
   c->set_stat("walk_new_records", n_new);
+  // the union of seqsets is closed under pop_front (the cover of a popped entry inside its own part is a
+  // prefix of / equal to an entry of the union), so a merge has nothing to add
+  BGX_CHECK(mh == nullptr || n_new == 0, "bgx_merge_seqsets: an input is not closed under pop_front (not a seqset)");
 
   // 4. sort the new records alone, merge them into the sorted survivors by rank, dedup
   uint32_t n2 = n1;
@@ -1361,6 +1400,13 @@ void stage_build_seqset(Context* c) {
       KLAUNCH(tables_kernel)<<<grid_for(nb, 128), 128, 0, s>>>(c->store.p, keys.p, locs.p, n2, bi2, ru, c->sizes.p, c->shared.p,
                                                       reinterpret_cast<unsigned long long*>(c->prev_bits.p),
                                                       c->prev_words, max_len.p, missing.p);
+      if (mh != nullptr && mh->parallel_splits != 1) {
+        // seqset_merger's placement of the prev bits (chunk rule, merge_core.cuh) instead of the builder's
+        BGX_CUDA(cudaMemsetAsync(c->prev_bits.p, 0, std::max<uint64_t>(4 * c->prev_words, 1) * 8, s));
+        KLAUNCH(merge_prev_kernel)<<<grid_for(nb, 128), 128, 0, s>>>(c->store.p, keys.p, locs.p, n2, bi2, mh->parallel_splits,
+                                                            reinterpret_cast<unsigned long long*>(c->prev_bits.p),
+                                                            c->prev_words, missing.p);
+      }
       DevBuf<uint32_t> gpop(c->sub_words, s), gex(c->sub_words, s), tot(1, s);
       uint64_t off = 0;
       for (int b = 0; b < 4; ++b) {
@@ -1392,7 +1438,6 @@ void stage_build_seqset(Context* c) {
   c->ent_key = std::move(keys);
   c->ent_loc = std::move(locs);
   c->built = true;
-  st_all.stop();
 }
 
 // ==== multi-GPU seqset build =============================================================================
@@ -1908,6 +1953,7 @@ void export_varbit(Context* c, int which, uint64_t** words, uint64_t* n_words, u
 
 void lookup_reads(Context* c, uint64_t* n_reads, uint64_t** fwd_entry, uint64_t** rc_entry) {
   BGX_CHECK(c->built, "bgx_lookup_reads: call bgx_build_seqset first");
+  BGX_CHECK(c->corrected, "bgx_lookup_reads: the context holds a merged seqset, not a build from reads");
   BGX_CHECK(c->dist.nranks == 1, "bgx_lookup_reads: single-GPU builds only (a sharded build would route the reads like the "
                                  "pop_front queries; not built yet)");
   cudaStream_t s = c->stream;
@@ -1943,7 +1989,7 @@ static int read_flag_i(const int* d, cudaStream_t s) {
 }
 
 // bitcount::finalize of one bit vector of nbits bits (modules/io/bitcount.cpp:84-123) into host arrays
-static void bitcount_to_host(Context* c, const unsigned long long* bits, uint64_t nbits, uint64_t* out[3]) {
+void bitcount_to_host(Context* c, const unsigned long long* bits, uint64_t nbits, uint64_t* out[3], uint64_t* total) {
   cudaStream_t s = c->stream;
   const uint64_t words = (nbits + 63) / 64, sub_words = (nbits + 511) / 512, acc_words = (nbits + 1 + 511) / 512;
   DevBuf<uint32_t> gpop(std::max<uint64_t>(sub_words, 1), s), gex(std::max<uint64_t>(sub_words, 1), s), tot(1, s);
@@ -1962,12 +2008,16 @@ static void bitcount_to_host(Context* c, const unsigned long long* bits, uint64_
   if (words) BGX_CUDA(cudaMemcpyAsync(out[0], bits, words * 8, cudaMemcpyDeviceToHost, s));
   if (sub_words) BGX_CUDA(cudaMemcpyAsync(out[1], sub.p, sub_words * 8, cudaMemcpyDeviceToHost, s));
   if (acc_words) BGX_CUDA(cudaMemcpyAsync(out[2], acc.p, acc_words * 8, cudaMemcpyDeviceToHost, s));
+  uint32_t h_tot = 0;
+  BGX_CUDA(cudaMemcpyAsync(&h_tot, tot.p, 4, cudaMemcpyDeviceToHost, s));
   BGX_CUDA(cudaStreamSynchronize(s));
+  if (total != nullptr) *total = h_tot;
 }
 
 void build_readmap(Context* c, int paired, uint64_t* n_rows, uint16_t** read_lengths, uint64_t** mate_loop_ptr,
                    uint64_t** is_forward, uint64_t* read_ids_source[3], uint64_t* read_ids_dest[3]) {
   BGX_CHECK(c->built, "bgx_build_readmap: call bgx_build_seqset first");
+  BGX_CHECK(c->corrected, "bgx_build_readmap: the context holds a merged seqset, not a build from reads");
   BGX_CHECK(c->dist.nranks == 1, "bgx_build_readmap: single-GPU builds only");
   BGX_CHECK(c->n_entries < kNoLoopEntry, "Entry id too long to fit in mate loop table entry");  // make_readmap.h:77
   BGX_CHECK(!paired || c->n_reads % 2 == 0, "bgx_build_readmap: paired input needs an even number of reads (mates are reads 2i, 2i+1)");

@@ -183,6 +183,50 @@ int bgx_build_readmap(bgx_ctx* ctx, int32_t paired, uint64_t* n_rows, uint16_t**
 int bgx_export_entries_ascii(bgx_ctx* ctx, uint64_t first, uint64_t count, char** bases,
                              uint64_t** offs);
 
+/* ---- seqset merge (`biograph merge`, modules/biograph/biograph_merge.cpp:199-290) ------
+ * One input seqset as its file members hold it: entry sizes and the four prev bit vectors (bitcount
+ * `bits` layout, ceil(n_entries/64) words each; `fixed` follows from their popcounts as in
+ * seqset::finalize, modules/bio_base/seqset.cpp:113-129, and is re-derived here). */
+typedef struct bgx_seqset_part {
+  uint64_t n_entries;
+  const uint16_t* sizes;        /* n_entries */
+  const uint64_t* prev_bits[4]; /* prev_A .. prev_T */
+} bgx_seqset_part;
+
+/* replaces, in one call: seqset_flat_builder::build for every input (modules/bio_base/
+ * seqset_flat.cpp:232-290), make_mergemap::build + fill_mergemap (make_mergemap.cpp:22-44,188-259) and
+ * seqset_merger::build (seqset_merger.cpp:53-78,109-197).  Every input is flattened on the GPU (entry
+ * sequences rebuilt from the prev bits by pointer doubling), the union of all entries is sorted and
+ * prefix-deduplicated by the kernels bgx_build_seqset uses, and the tables of the merged seqset are
+ * computed; the context is then in the "built" state: bgx_export_seqset / bgx_export_varbit /
+ * bgx_export_entries_ascii return the merged seqset.
+ * parallel_splits: seqset_merger runs merge_range over generate_chunks(0, n, g_parallel_splits)
+ *   (modules/io/parallel.cpp:13,60-83) and the chunking decides on which entry of a run of entries with
+ *   a common prefix a prev bit lands; 0 = the reference's 100000 (byte-identical prev members to
+ *   `biograph merge`), 1 = builder::build_chunks' placement (what `biograph create` would write for the
+ *   union of the reads).  Entry set, sizes, shared and fixed do not depend on it.
+ * Single GPU; at most 64 inputs; fewer than 2^31 entries in total.  An input that is not a seqset
+ * (prev bit totals != entries, a size of 0, not closed under pop_front) is an error. */
+int bgx_merge_seqsets(bgx_ctx* ctx, const bgx_seqset_part* parts, uint32_t n_parts, uint64_t parallel_splits);
+
+/* replaces: seqset_mergemap_builder / make_mergemap::fill_mergemap for input `part`: the `merged_entries`
+ * bitcount (n_bits = merged entries; bit x set iff merged entry x, or a prefix of it, is an entry of the
+ * input; input entry i is merged entry find_count(i)), as {bits, subaccum, accum}.  *n_set = set bits =
+ * entries of the input (seqset_merger.cpp:33).  Arrays are bgx_free()'d by the caller. */
+int bgx_export_mergemap(bgx_ctx* ctx, uint32_t part, uint64_t* merged_entries[3], uint64_t* n_bits, uint64_t* n_set);
+
+/* replaces: the read_ids part of make_readmap::fast_migrate (modules/bio_mapred/make_readmap.cpp:459-486):
+ * a bit vector indexed by the entries of input `part` (a readmap's read_ids/source_to_mid `bits`, n_old
+ * = entries of the input) re-targeted to merged entry ids, as {bits, subaccum, accum} of n_bits = merged
+ * entries.  Every other readmap member is copied unchanged by fast_migrate (:487-520). */
+int bgx_migrate_bits(bgx_ctx* ctx, uint32_t part, const uint64_t* old_bits, uint64_t n_old, uint64_t* migrated[3],
+                     uint64_t* n_bits);
+
+/* replaces: seqset_flat::get(i) (modules/bio_base/seqset_flat.h:117-140) for entries [first, first+count)
+ * of input `part` after bgx_merge_seqsets (a merge of ONE input is a plain flatten): ASCII, concatenated,
+ * entry first+i = bases[offs[i] .. offs[i+1]). */
+int bgx_export_flat_ascii(bgx_ctx* ctx, uint32_t part, uint64_t first, uint64_t count, char** bases, uint64_t** offs);
+
 /* ---- multi-GPU (no reference analogue: the reference is one process) -------------------
  * One context per GPU, driven by one process per GPU or by one host thread per GPU of a single
  * process (bgx_bs::multi_session).  Rank 0 obtains an id with bgx_dist_unique_id and hands
