@@ -681,6 +681,284 @@ inline seqset_tables seqset_for_reads(const std::vector<std::string>& reads, con
   return path.empty() ? b.tables() : b.make_seqset(path);
 }
 
+// ---- input: reading spiral files back ----------------------------------------------------------------------
+// spiral_file_open_mmap (modules/io/spiral_file_mmap.cpp:82-160): members are stored (method 0) and read
+// by offset; the CRC fields of array members are not valid (:421-423), so nothing is verified.  Handles
+// the classic and the ZIP64 end records and the 0x0001 extra fields the reference's minizip writes.
+class spiral_file_reader {
+ public:
+  struct member { std::string name; uint64_t offset /* of the data */, size; };
+  explicit spiral_file_reader(const std::string& path) : m_path(path), m_fd(::open(path.c_str(), O_RDONLY)) {
+    if (m_fd < 0) throw io_exception("Could not open spiral file " + path + ": " + strerror(errno));
+    const off_t end = ::lseek(m_fd, 0, SEEK_END);
+    if (end < 22) throw io_exception(path + " is not a spiral file (too short)");
+    const uint64_t fsz = (uint64_t)end, tail_n = std::min<uint64_t>(fsz, 65536 + 22 + 20);
+    std::string tail = pread_str(fsz - tail_n, tail_n);
+    size_t e = std::string::npos;
+    for (size_t i = tail.size() - 22 + 1; i-- > 0;)
+      if (get32(tail, i) == 0x06054b50u) { e = i; break; }
+    if (e == std::string::npos) throw io_exception(path + " is not a spiral file (no end of central directory)");
+    uint64_t n = get16(tail, e + 10), cd_size = get32(tail, e + 12), cd_off = get32(tail, e + 16);
+    if (e >= 20 && get32(tail, e - 20) == 0x07064b50u) {  // ZIP64 locator -> ZIP64 end record
+      const uint64_t z = get64(tail, e - 20 + 8);
+      const std::string r = pread_str(z, 56);
+      if (get32(r, 0) != 0x06064b50u) throw io_exception(path + ": bad ZIP64 end of central directory");
+      n = get64(r, 32); cd_size = get64(r, 40); cd_off = get64(r, 48);
+    }
+    const std::string cd = pread_str(cd_off, cd_size);
+    size_t p = 0;
+    for (uint64_t i = 0; i < n; ++i) {
+      if (p + 46 > cd.size() || get32(cd, p) != 0x02014b50u) throw io_exception(path + ": bad central directory");
+      if (get16(cd, p + 10) != 0) throw io_exception(path + ": compressed member (a spiral file stores its members)");
+      uint64_t usize = get32(cd, p + 24), lho = get32(cd, p + 42);
+      const uint16_t nl = get16(cd, p + 28), xl = get16(cd, p + 30), cl = get16(cd, p + 32);
+      const std::string name = cd.substr(p + 46, nl);
+      size_t x = p + 46 + nl;
+      const size_t xe = x + xl;
+      while (x + 4 <= xe) {  // 0x0001: only the values that overflowed, in this order
+        const uint16_t id = get16(cd, x), len = get16(cd, x + 2);
+        if (id == 1) {
+          size_t q = x + 4;
+          if (usize == 0xffffffffull) { usize = get64(cd, q); q += 8; }
+          if (get32(cd, p + 20) == 0xffffffffu) q += 8;
+          if (lho == 0xffffffffull) lho = get64(cd, q);
+        }
+        x += 4 + (size_t)len;
+      }
+      const std::string lh = pread_str(lho, 30);
+      if (get32(lh, 0) != 0x04034b50u) throw io_exception(path + ": bad local header of " + name);
+      m_members.push_back(member{name, lho + 30 + get16(lh, 26) + get16(lh, 28), usize});
+      m_index[name] = m_members.size() - 1;
+      p = xe + cl;
+    }
+  }
+  ~spiral_file_reader() { if (m_fd >= 0) ::close(m_fd); }
+  spiral_file_reader(const spiral_file_reader&) = delete;
+  spiral_file_reader& operator=(const spiral_file_reader&) = delete;
+  const std::vector<member>& members() const { return m_members; }   // creation order
+  bool has(const std::string& name) const { return m_index.count(name) != 0; }
+  const member& find(const std::string& name) const {
+    auto it = m_index.find(name);
+    if (it == m_index.end()) throw io_exception("Path not found in spiral file " + m_path + ": " + name);
+    return m_members[it->second];
+  }
+  std::string read(const std::string& name) const { const member& m = find(name); return pread_str(m.offset, m.size); }
+  template <typename T>
+  std::vector<T> read_array(const std::string& name) const {
+    const member& m = find(name);
+    std::vector<T> v(m.size / sizeof(T));
+    pread_into(m.offset, v.data(), v.size() * sizeof(T));
+    return v;
+  }
+  // the value of a top-level string / integer field of a (compact) JSON member
+  static std::string json_string_field(const std::string& json, const std::string& key) {
+    const size_t k = json.find("\"" + key + "\":\"");
+    if (k == std::string::npos) return "";
+    const size_t b = k + key.size() + 4, e = json.find('"', b);
+    return json.substr(b, e - b);
+  }
+  static uint64_t json_uint_field(const std::string& json, const std::string& key) {
+    const size_t k = json.find("\"" + key + "\":");
+    if (k == std::string::npos) throw io_exception("field " + key + " missing in " + json);
+    return strtoull(json.c_str() + k + key.size() + 3, nullptr, 10);
+  }
+
+ private:
+  static uint16_t get16(const std::string& s, size_t i) { uint16_t v; memcpy(&v, s.data() + i, 2); return v; }
+  static uint32_t get32(const std::string& s, size_t i) { uint32_t v; memcpy(&v, s.data() + i, 4); return v; }
+  static uint64_t get64(const std::string& s, size_t i) { uint64_t v; memcpy(&v, s.data() + i, 8); return v; }
+  void pread_into(uint64_t off, void* dst, uint64_t n) const {
+    char* p = static_cast<char*>(dst);
+    while (n) {
+      const ssize_t r = ::pread(m_fd, p, (size_t)std::min<uint64_t>(n, 1ull << 30), (off_t)off);
+      if (r <= 0) throw io_exception("short read from spiral file " + m_path);
+      p += r; off += (uint64_t)r; n -= (uint64_t)r;
+    }
+  }
+  std::string pread_str(uint64_t off, uint64_t n) const {
+    std::string s(n, '\0');
+    pread_into(off, &s[0], n);
+    return s;
+  }
+  std::string m_path;
+  int m_fd;
+  std::vector<member> m_members;
+  std::unordered_map<std::string, size_t> m_index;
+};
+
+// seqset_file / seqset (modules/bio_base/seqset.cpp:46-111): the members a merge reads.  entry_sizes is a
+// packed_varbit_vector from seqset version 1.1.0 on and a raw uint8 array before (:58-62).
+class seqset_file {
+ public:
+  explicit seqset_file(const std::string& path) : m_path(path) {
+    spiral_file_reader r(path);
+    m_uuid = spiral_file_reader::json_string_field(r.read("file_info.json"), "uuid");
+    m_command_line = r.read("file_info.json");
+    m_entries = spiral_file_reader::json_uint_field(r.read("seqset.json"), "num_entries");
+    m_sizes.resize(m_entries);
+    if (r.has("entry_sizes/elements")) {
+      const std::string meta = r.read("entry_sizes/packed_varbit_vector.json");
+      const unsigned bits = (unsigned)spiral_file_reader::json_uint_field(meta, "bits_per_value");
+      if (spiral_file_reader::json_uint_field(meta, "element_count") != m_entries) throw io_exception(path + ": entry_sizes has the wrong element count");
+      const std::vector<uint64_t> el = r.read_array<uint64_t>("entry_sizes/elements");
+      const uint64_t mask = bits >= 64 ? ~0ull : ((1ull << bits) - 1);
+      for (uint64_t i = 0; i < m_entries; ++i) {  // packed_varbit_vector::get (packed_varbit_vector.cpp:80-139)
+        const uint64_t pos = i * bits, q = pos >> 6, sh = pos & 63;
+        uint64_t v = el[q] >> sh;
+        if (sh + bits > 64) v |= el[q + 1] << (64 - sh);
+        m_sizes[i] = (uint16_t)(v & mask);
+      }
+    } else {
+      const std::vector<uint8_t> raw = r.read_array<uint8_t>("entry_sizes");
+      if (raw.size() < m_entries) throw io_exception(path + ": entry_sizes is too short");
+      for (uint64_t i = 0; i < m_entries; ++i) m_sizes[i] = raw[i];
+    }
+    for (int b = 0; b < 4; ++b) {
+      m_prev[b] = r.read_array<uint64_t>(std::string("prev_") + "ACGT"[b] + "/bits");
+      if (m_prev[b].size() < (m_entries + 63) / 64) throw io_exception(path + ": prev bits are too short");
+    }
+    for (uint16_t v : m_sizes) m_max_read_len = std::max<unsigned>(m_max_read_len, v);
+  }
+  const std::string& path() const { return m_path; }
+  const std::string& uuid() const { return m_uuid; }
+  const std::string& file_info() const { return m_command_line; }
+  uint64_t size() const { return m_entries; }
+  unsigned max_read_len() const { return m_max_read_len; }
+  bgx_seqset_part part() const {
+    bgx_seqset_part p;
+    p.n_entries = m_entries;
+    p.sizes = m_sizes.data();
+    for (int b = 0; b < 4; ++b) p.prev_bits[b] = m_prev[b].data();
+    return p;
+  }
+
+ private:
+  std::string m_path, m_uuid, m_command_line;
+  uint64_t m_entries = 0;
+  unsigned m_max_read_len = 0;
+  std::vector<uint16_t> m_sizes;
+  std::vector<uint64_t> m_prev[4];
+};
+
+// seqset_flat_builder + make_mergemap + seqset_merger (modules/bio_base/seqset_flat.h, make_mergemap.h,
+// seqset_merger.h; driven by MergeSEQSETMain::do_merge, modules/biograph/biograph_merge.cpp:199-290) in ONE
+// GPU call: the reference writes a .flat and a .mergemap temp file per input and then merges; here the
+// flattened entries and the mergemaps stay on the device.
+class seqset_merger {
+ public:
+  struct mergemap_tables {  // the `merged_entries` bitcount of seqset_mergemap (seqset_mergemap.cpp:5-20)
+    uint64_t n_bits = 0, n_set = 0;
+    detail::host_array<uint64_t> bits, subaccum, accum;
+  };
+  // parallel_splits: see bgx_merge_seqsets (0 = g_parallel_splits of the reference binary)
+  seqset_merger(session& s, const std::vector<const seqset_file*>& inputs, uint64_t parallel_splits = 0)
+      : m_s(s), m_inputs(inputs), m_splits(parallel_splits) {
+    if (inputs.empty()) throw io_exception("seqset_merger: no inputs");
+  }
+  // make_mergemap::build + seqset_merger::build
+  void build(progress_handler_t progress = null_progress_handler) {
+    std::vector<bgx_seqset_part> parts;
+    for (const seqset_file* f : m_inputs) parts.push_back(f->part());
+    detail::ck(bgx_merge_seqsets(m_s.ctx(), parts.data(), (uint32_t)parts.size(), m_splits));
+    m_done = true;
+    progress(1.0);
+  }
+  // make_mergemap::total_merged_entries
+  size_t total_merged_entries() {
+    need();
+    uint64_t lay[6];
+    detail::ck(bgx_seqset_layout(m_s.ctx(), lay));
+    return (size_t)lay[1];
+  }
+  // make_mergemap::fill_mergemap(input_id, builder)
+  mergemap_tables fill_mergemap(unsigned input_id) {
+    need();
+    mergemap_tables t;
+    uint64_t* out[3];
+    detail::ck(bgx_export_mergemap(m_s.ctx(), input_id, out, &t.n_bits, &t.n_set));
+    t.bits.p = out[0]; t.bits.n = (t.n_bits + 63) / 64;
+    t.subaccum.p = out[1]; t.subaccum.n = (t.n_bits + 511) / 512;
+    t.accum.p = out[2]; t.accum.n = (t.n_bits + 1 + 511) / 512;
+    return t;
+  }
+  // ... written as the reference's .mergemap spiral file (seqset_mergemap_builder, seqset_mergemap.cpp:5-20)
+  void write_mergemap(unsigned input_id, const std::string& path, const std::string& merged_seqset_uuid) {
+    mergemap_tables t = fill_mergemap(input_id);
+    seqset_file_writer w(path);
+    w.add("file_info.json", file_info_json(""));
+    w.add("part_info.json", part_info_json("mergemap", 1, 0, 0));
+    w.add("mergemap.json", "{\"merged_seqset_uuid\":\"" + merged_seqset_uuid + "\",\"orig_seqset_uuid\":\"" + m_inputs[input_id]->uuid() + "\"}");
+    w.add("merged_entries/part_info.json", part_info_json("bitcount", 1, 0, 0));
+    w.add("merged_entries/bitcount.json", "{\"nbits\":" + std::to_string(t.n_bits) + "}");
+    w.add("merged_entries/bits", t.bits.p, t.bits.n * 8);
+    w.add("merged_entries/subaccum", t.subaccum.p, t.subaccum.n * 8);
+    w.add("merged_entries/accum", t.accum.p, t.accum.n * 8);
+    w.finish();
+  }
+  // seqset_flat::get(i) of input `input_id`, entries [first, first + count)
+  std::vector<std::string> flat_entries(unsigned input_id, uint64_t first, uint64_t count) {
+    need();
+    detail::host_array<char> bases;
+    detail::host_array<uint64_t> offs;
+    detail::ck(bgx_export_flat_ascii(m_s.ctx(), input_id, first, count, &bases.p, &offs.p));
+    std::vector<std::string> out;
+    for (uint64_t i = 0; i < count; ++i) out.emplace_back(bases.p + offs.p[i], bases.p + offs.p[i + 1]);
+    return out;
+  }
+  // the merged seqset spiral file (seqset_merger::build writes it through its create state)
+  seqset_tables write_seqset(const std::string& path, const std::string& uuid, progress_handler_t progress = null_progress_handler) {
+    need();
+    return builder(m_s).make_seqset(path, progress, uuid);
+  }
+  // make_readmap::fast_migrate (modules/bio_mapred/make_readmap.cpp:46-52,459-520): every member of the old
+  // readmap copied in order, read_ids/source_to_mid re-targeted through the input's mergemap, readmap.json
+  // pointed at the merged seqset
+  void fast_migrate(unsigned input_id, const std::string& old_readmap_path, const std::string& new_readmap_path,
+                    const std::string& merged_seqset_uuid) {
+    need();
+    spiral_file_reader r(old_readmap_path);
+    const uint64_t n_old = spiral_file_reader::json_uint_field(r.read("read_ids/source_to_mid/bitcount.json"), "nbits");
+    if (n_old != m_inputs[input_id]->size()) throw io_exception(old_readmap_path + " does not belong to " + m_inputs[input_id]->path());
+    std::vector<uint64_t> old_bits = r.read_array<uint64_t>("read_ids/source_to_mid/bits");
+    old_bits.resize((n_old + 63) / 64);
+    uint64_t* out[3];
+    uint64_t n_bits = 0;
+    detail::ck(bgx_migrate_bits(m_s.ctx(), input_id, old_bits.data(), n_old, out, &n_bits));
+    detail::host_array<uint64_t> bits, sub, acc;
+    bits.p = out[0]; bits.n = (n_bits + 63) / 64;
+    sub.p = out[1]; sub.n = (n_bits + 511) / 512;
+    acc.p = out[2]; acc.n = (n_bits + 1 + 511) / 512;
+    seqset_file_writer w(new_readmap_path);
+    for (const spiral_file_reader::member& m : r.members()) {
+      if (m.name == "file_info.json") w.add(m.name, file_info_json(""));
+      else if (m.name == "readmap.json") w.add(m.name, "{\"seqset_uuid\":\"" + merged_seqset_uuid + "\"}");
+      else if (m.name == "read_ids/source_to_mid/bitcount.json") w.add(m.name, "{\"nbits\":" + std::to_string(n_bits) + "}");
+      else if (m.name == "read_ids/source_to_mid/bits") w.add(m.name, bits.p, bits.n * 8);
+      else if (m.name == "read_ids/source_to_mid/subaccum") w.add(m.name, sub.p, sub.n * 8);
+      else if (m.name == "read_ids/source_to_mid/accum") w.add(m.name, acc.p, acc.n * 8);
+      else if (m.name.size() > 5 && m.name.compare(m.name.size() - 5, 5, ".json") == 0) w.add(m.name, r.read(m.name));
+      else { const std::string d = r.read(m.name); w.add(m.name, d.data(), d.size()); }
+    }
+    w.finish();
+  }
+  static std::string part_info_json(const char* type, int major, int minor, int patch) {
+    return std::string("{\"part_type\":\"") + type + "\",\"version\":{\"build\":\"\",\"major\":" + std::to_string(major) +
+           ",\"minor\":" + std::to_string(minor) + ",\"patch\":" + std::to_string(patch) + ",\"pre\":\"\"}}";
+  }
+  static std::string file_info_json(const std::string& uuid) {
+    return std::string("{\"build_host\":\"bgx\",\"build_is_clean\":true,\"build_revision\":\"") + bgx_version() +
+           "\",\"build_timestamp\":0,\"build_timestamp_text\":\"\",\"build_user\":\"\",\"command_line\":[],\"create_timestamp\":" +
+           std::to_string((long long)time(nullptr)) + ",\"create_timestamp_text\":\"\",\"uuid\":\"" + uuid + "\"}";
+  }
+
+ private:
+  void need() const { if (!m_done) throw io_exception("seqset_merger: call build() first"); }
+  session& m_s;
+  std::vector<const seqset_file*> m_inputs;
+  uint64_t m_splits;
+  bool m_done = false;
+};
+
 // make_readmap::do_make (modules/bio_mapred/make_readmap.{h,cpp}; called at biograph_create.cpp:818-831):
 // the tables come from bgx_build_readmap, the spiral file is written here in the reference's member
 // order (readmap 1.2.0: readmap.cpp:13; sparse_multi 1.0.0; packed_varbit_vector 1.0.0; packed_vector
