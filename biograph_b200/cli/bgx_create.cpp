@@ -11,9 +11,11 @@
 //   <out>/metadata/bg_info.json          biograph_metadata: version, biograph_id, accession_id, samples
 //   <out>/qc/create_stats.json           the counters of :796-808 + stage timings
 //   <out>/qc/create_log.txt, <out>/qc/kmer_quality_report.html, <out>/analysis/
-// Inputs: FASTQ, plain or gzip (zlib), single, --pair <second file> or --interleaved.  BAM/CRAM
-// (htslib in the reference) are rejected with a message.  There is no CPU fallback: the stages need
-// a CUDA device.
+// Inputs: FASTQ, plain or gzip (zlib), single, --pair <second file> or --interleaved; BAM (BGZF through
+// zlib, records decoded here the way read_importer does through htslib: secondary / supplementary
+// records skipped, reverse-strand records reverse-complemented, mates joined by read name).  CRAM
+// (htslib's codecs + the reference FASTA) is rejected with a message.  There is no CPU fallback: the
+// stages need a CUDA device.
 #include <sys/stat.h>
 #include <zlib.h>
 
@@ -25,6 +27,7 @@
 #include <random>
 #include <set>
 #include <sstream>
+#include <unordered_map>
 
 #include "bgx_build_seqset.hpp"
 #include "cli_util.hpp"
@@ -42,6 +45,7 @@ struct Args {
   std::string min_kmer_count = "5", kmer_size = "30", trim_after_portion = "0.7", max_corrections = "8", min_good_run = "2",
               min_reads = "0.4", warn_reads = "0.7", tmp_encoding = "gzip1", sample_reads = "0", cut_reads, overrep = "0";
   int device = 0;
+  bool dump_reads = false;   // test hook: import only, print the reads (no GPU needed for BAM input)
 };
 
 // validate_param / validate_float_param (biograph_create.cpp:337-375): same messages
@@ -75,7 +79,7 @@ void usage() {
             << "Convert reads to BioGraph format.\n\n"
                "  --out arg                       Output BioGraph name (.bg)\n"
                "  --ref arg                       Reference directory (or FASTA; only its size is used here)\n"
-               "  --reads, --in arg               Input file to process (fastq, fastq.gz; - for STDIN)\n"
+               "  --reads, --in arg               Input file to process (fastq, fastq.gz, bam; - for STDIN)\n"
                "  --format arg (=auto)            Input file format when using STDIN\n"
                "  --interleaved                   Input reads are interleaved (fastq only)\n"
                "  --pair arg                      Second input file containing read pairs (fastq only)\n"
@@ -132,6 +136,7 @@ Args parse(int argc, char** argv) {
     else if (o == "--threads" || o == "--max-mem" || o == "--cache" || o == "--debug" || o == "--sys-err-thresh" || o == "--rnd-err-thresh" ||
              o == "--dump-kmers") { if (o != "--cache" && o != "--debug") (void)val(); }
     else if (o == "--device") a.device = atoi(val().c_str());
+    else if (o == "--dump-reads") a.dump_reads = true;
     else if (o == "--help" || o == "-h") { usage(); exit(0); }
     else if (o.rfind("-", 0) == 0 && o != "-") die("unrecognised option '" + o + "'");
     else positional.push_back(o);
@@ -209,6 +214,129 @@ bool next_record(LineReader& r, std::string& buf, size_t& pos, std::string rec[4
 }
 
 // ---- small utilities ---------------------------------------------------------------------------------------
+// ---- BAM input (modules/build_seqset/read_importer.cpp:182-266,483-575; htslib there, zlib here) --------------
+// A BAM file is a series of BGZF blocks = gzip members, which zlib's gzread inflates back to back:
+//   "BAM\1", l_text, text, n_ref, { l_name, name, l_ref } x n_ref, then records
+//   block_size | refID pos l_read_name mapq bin n_cigar_op flag l_seq next_refID next_pos tlen |
+//   read_name (NUL terminated) | cigar (4 x n_cigar_op) | seq (4-bit codes, (l_seq + 1) / 2 bytes) | qual | tags
+struct BamRecord {
+  std::string qname, seq;
+  uint16_t flag = 0;
+};
+
+struct BamReader {
+  gzFile f = nullptr;
+  std::string name;
+  std::vector<uint8_t> buf;
+  uint64_t records = 0;
+  explicit BamReader(const std::string& path) : name(path) {
+    f = path == "/dev/stdin" ? gzdopen(0, "rb") : gzopen(path.c_str(), "rb");
+    if (!f) throw std::runtime_error("Unable to open file " + path);            // read_importer.cpp:490-492
+    gzbuffer(f, 1 << 20);
+    char magic[4];
+    if (!fill(magic, 4) || memcmp(magic, "BAM\1", 4) != 0) throw std::runtime_error(path + " is not a valid BAM file.");   // :513-515
+    const int32_t l_text = i32();
+    skip((uint32_t)l_text);
+    const int32_t n_ref = i32();
+    for (int32_t i = 0; i < n_ref; ++i) {
+      const int32_t l_name = i32();
+      skip((uint32_t)l_name + 4);
+    }
+  }
+  ~BamReader() { if (f) gzclose(f); }
+  bool next(BamRecord& r) {
+    int32_t block_size;
+    const int got = gzread(f, &block_size, 4);
+    if (got == 0) return false;                                                    // sam_read1 == -1: EOF
+    if (got != 4 || block_size < 32) throw std::runtime_error("sam_read1 returned -2 when reading " + name);   // :545-548
+    buf.resize((size_t)block_size);
+    if (!fill(buf.data(), (size_t)block_size)) throw std::runtime_error("sam_read1 returned -2 when reading " + name);
+    const uint8_t* b = buf.data();
+    const uint32_t l_read_name = b[8], n_cigar = rd16(b + 12), l_seq = rd32(b + 16);
+    r.flag = rd16(b + 14);
+    const size_t seq_off = 32 + (size_t)l_read_name + 4 * (size_t)n_cigar;
+    if (l_read_name == 0 || seq_off + (l_seq + 1) / 2 + l_seq > (size_t)block_size)
+      throw std::runtime_error("sam_read1 returned -4 when reading " + name);
+    r.qname.assign(reinterpret_cast<const char*>(b + 32), l_read_name - 1);
+    r.seq.resize(l_seq);
+    static const char nt16[] = "=ACMGRSVTWYHKDBN";                                 // htslib seq_nt16_str
+    for (uint32_t i = 0; i < l_seq; ++i) r.seq[i] = nt16[(b[seq_off + (i >> 1)] >> ((~i & 1) << 2)) & 0xf];   // bam_seqi
+    if (r.flag & 0x10) {                                                           // BAM_FREVERSE: reverse_complement_iupac_string
+      static const char comp[] = "TVGH..CD..M.KN...YSA.BW.R.";                     // modules/bio_base/dna_base_set.cpp:78-79
+      std::reverse(r.seq.begin(), r.seq.end());
+      for (char& c : r.seq) {
+        const int idx = c - 'A';
+        if (idx >= 0 && idx < 26) c = comp[idx];
+      }
+    }
+    ++records;
+    return true;
+  }
+
+ private:
+  static uint16_t rd16(const uint8_t* p) { uint16_t v; memcpy(&v, p, 2); return v; }
+  static uint32_t rd32(const uint8_t* p) { uint32_t v; memcpy(&v, p, 4); return v; }
+  bool fill(void* dst, size_t n) {
+    char* p = static_cast<char*>(dst);
+    while (n) {
+      const int r = gzread(f, p, (unsigned)std::min<size_t>(n, 1u << 30));
+      if (r <= 0) return false;
+      p += r; n -= (size_t)r;
+    }
+    return true;
+  }
+  int32_t i32() {
+    int32_t v;
+    if (!fill(&v, 4)) throw std::runtime_error(name + " is not a valid BAM file.");
+    return v;
+  }
+  void skip(uint32_t n) {
+    buf.resize(n);
+    if (n && !fill(buf.data(), n)) throw std::runtime_error(name + " is not a valid BAM file.");
+  }
+};
+
+// read_importer_base::bam_process_line + bam_output_unpaired (read_importer.cpp:182-203,388-470): secondary and
+// supplementary records are skipped; a record flagged as paired waits for its mate by read name, mates leave
+// together; whatever never met a mate is a single read at the end.  pair(a, b) / single(a) receive the reads;
+// returns the number of reads imported.  The k-mer counter only knows ACGT and N (dna_base(char) throws on
+// anything else, modules/bio_base/dna_base.h:38-56), so other IUPAC codes are refused with its message.
+template <typename PairFn, typename SingleFn>
+uint64_t import_bam(const std::string& path, bool* got_paired, PairFn pair, SingleFn single) {
+  BamReader in(path);
+  BamRecord rec;
+  std::unordered_map<std::string, std::string> pair_cache;   // qname -> the mate seen first
+  uint64_t n = 0;
+  auto check = [](const std::string& seq) {
+    for (char c : seq)
+      if (c != 'A' && c != 'C' && c != 'G' && c != 'T' && c != 'N') throw std::runtime_error(fmt("Failed conversion of dna_base, c = '%c'", c));
+  };
+  while (in.next(rec)) {
+    if (rec.flag & (0x100 | 0x800)) continue;                // BAM_FSECONDARY, BAM_FSUPPLEMENTARY
+    check(rec.seq);
+    ++n;
+    if (rec.flag & 0x1) {                                    // BAM_FPAIRED
+      *got_paired = true;
+      auto it = pair_cache.find(rec.qname);
+      if (it != pair_cache.end()) {
+        pair(rec.seq, it->second);                           // add_paired_read(qname, this record, the cached mate)
+        pair_cache.erase(it);
+      } else {
+        pair_cache.emplace(rec.qname, rec.seq);
+      }
+    } else {
+      single(rec.seq);
+    }
+  }
+  if (in.records == 0) std::cerr << "WARNING: " << path << ": no records present\n";
+  // deterministic order for the leftovers (the reference walks a hash map)
+  std::vector<std::string> names;
+  for (const auto& kv : pair_cache) names.push_back(kv.first);
+  std::sort(names.begin(), names.end());
+  for (const std::string& q : names) single(pair_cache[q]);
+  return n;
+}
+
 uint64_t reference_bases(const std::string& ref) {
   // the reference directory holds the FASTA as source.fasta (biograph reference); a FASTA path works too
   std::vector<std::string> cand = {ref, ref + "/source.fasta", ref + "/reference.fasta"};
@@ -246,6 +374,16 @@ int main(int argc, char** argv) {
     if (!formats.count(a.format)) die("Invalid input format '" + a.format + "'");
     if (!a.pairs.empty() && a.pairs.size() != a.reads.size())
       die("If pair files are present, there must be the same number of them as read files.");
+    if (a.dump_reads) {
+      // test hook: the BAM importer alone -- one line per imported read or pair ("a\tb"), then the count
+      bool paired = false;
+      uint64_t n = 0;
+      for (const std::string& f : a.reads)
+        n += import_bam(f, &paired, [](const std::string& x, const std::string& y) { std::cout << x << "\t" << y << "\n"; },
+                        [](const std::string& x) { std::cout << x << "\n"; });
+      std::cout << "# reads " << n << " paired " << (paired ? 1 : 0) << "\n";
+      return 0;
+    }
     struct stat st;
     if (!a.force && stat(a.out.c_str(), &st) == 0) die("Refusing to overwrite '" + a.out + "'. Use --force to override.");
 
@@ -313,7 +451,26 @@ int main(int argc, char** argv) {
           return 1;
         }
       }
-      if (in_format != "fastq") die("bgx-create reads FASTQ (plain or gzip); " + in_format + " input needs the reference's htslib importer");
+      if (in_format == "cram") die("bgx-create reads FASTQ (plain or gzip) and BAM; cram input needs the reference's htslib importer");
+      if (in_format == "bam") {
+        // mates go in back to back (reads 2i, 2i + 1 of the session are mates once anything is paired); a single
+        // read of a paired file gets a one-base partner, which correction drops (shorter than a k-mer), leaving
+        // the read a single one for make_readmap (bgx.h: "a pair with one read dropped is a single read")
+        bgx_bs::kmer_counter::prob_pass_processor proc(counter);
+        uint64_t plain_singles = 0;
+        auto add_pair = [&](const std::string& x, const std::string& y) {
+          if (plain_singles) throw std::runtime_error(in_reads + ": paired records after unpaired ones are not supported by bgx-create");
+          proc.add(x);
+          proc.add(y);
+        };
+        auto add_single = [&](const std::string& x) {
+          if (got_paired) { proc.add(x); proc.add(std::string("A")); }
+          else { proc.add(x); ++plain_singles; }
+        };
+        read_count += import_bam(in_reads, &got_paired, add_pair, add_single);
+        proc.flush_all();
+        continue;
+      }
       if (in_pairs.empty()) {
         // whole-file chunks go to the GPU parser (split, validate, 2-bit pack on the device)
         LineReader r(in_reads);
