@@ -150,6 +150,14 @@ def check_merge(part_reads, nsplits):
     assert M.flat_sequences(tb["fixed"], tb["prev"], tb["sizes"]) == merged
 
 
+def test_seqset_flat_test():  # seqset_flat_test.cpp:14-46: the flat sequences are the seqset's entry sequences
+    reads = [O.tseq(x) for x in ("abc", "bcd", "cde", "cdf", "dfg")]
+    ss = O.seqset_closed_form(reads)
+    prev01 = [unpack(ss["prev"][b], ss["n"]) for b in range(4)]
+    assert M.flat_sequences(ss["fixed"], prev01, ss["sizes"]) == seqset_entries(reads)
+    check_merge([reads], 100000)
+
+
 def test_single_simple():  # seqset_merger_test.cpp:124-127
     check_merge([[O.tseq("abc"), O.tseq("de")]], 100000)
 
