@@ -147,3 +147,28 @@ def test_golden_family_lambda(tmp_path):
     # flat entries of an input are its sorted entry sequences
     f = out["flat"][1]
     assert len(f) == parts[1]["n"] and all(a < b for a, b in zip(f, f[1:]))
+
+
+@pytest.mark.parametrize("mode", ["short", "word", "long", "max", "dup", "many"])
+def test_entry_shapes(tmp_path, mode):
+    """entries of 1-12 bases, at the 32-base word boundaries, of the maximum length, identical inputs, and up
+    to 64 inputs (the limit of one merge)"""
+    for seed in range(6):
+        rng = random.Random(sum(map(ord, mode)) * 100 + seed)
+        nparts = rng.randint(20, 64) if mode == "many" else rng.randint(1, 6)
+        base = "".join(rng.choice("ACGT") for _ in range(400))
+        reads = []
+        for _ in range(nparts):
+            rs = []
+            for _ in range(rng.randint(1, 12) if mode == "many" else rng.randint(3, 25)):
+                L = {"short": rng.randint(1, 12), "word": rng.choice([31, 32, 33, 63, 64, 65, 95, 96, 97]),
+                     "long": rng.randint(100, 200), "max": rng.choice([254, 255, 128, 129])}.get(mode, rng.randint(5, 80))
+                if rng.random() < 0.6:
+                    s = rng.randint(0, len(base) - L)
+                    rs.append(base[s:s + L])
+                else:
+                    rs.append("".join(rng.choice("ACGT" if rng.random() < 0.8 else "AC") for _ in range(L)))
+            reads.append(rs)
+        if mode == "dup" and nparts > 1:
+            reads[1] = list(reads[0])
+        check_against_oracle(tmp_path, [seqset_entries(r) for r in reads], rng.choice([1, 2, 3, 7, 64, 100000]), rng)
