@@ -2,6 +2,8 @@
 committed GPU-arm line under profiles/ (written by `python bench.py` on a B200)."""
 import json
 import os
+
+import pytest
 import subprocess
 import sys
 
@@ -38,19 +40,28 @@ def test_reference_arm_ignores_omp_num_threads():
     assert line["config"]["workload"] == "small"
 
 
-def test_committed_gpu_line_has_every_contract_key():
-    path = os.path.join(ROOT, "profiles", "r1g_bench_ecoli100x.json")
+@pytest.mark.parametrize("name,workload,n_gpus", [("r1g_bench_ecoli100x.json", "ecoli100x", 1), ("r2l_bench_chr20.json", "chr20_30x", 1),
+                                                  ("r2n_bench_chr20_8gpu.json", "chr20_30x", 8)])
+def test_committed_gpu_line_has_every_contract_key(name, workload, n_gpus):
+    path = os.path.join(ROOT, "profiles", name)
     line = json.loads([l for l in open(path).read().splitlines() if l.startswith("{")][-1])
     for k in BASE + ["gpu_launches", "roofline", "clocks"]:
         assert k in line, k
-    assert line["n_gpus"] == 1 and line["warmup"] >= 3 and line["gpu_launches"] > 0 and line["dtype"] == "u64"
-    assert line["config"]["workload"] == "ecoli100x" and "l2" in line["config"]
+    assert line["n_gpus"] == n_gpus and line["warmup"] >= 3 and line["gpu_launches"] > 0 and line["dtype"] == "u64"
+    assert line["config"]["workload"] == workload and "l2" in line["config"]
     e = line["e2e"]
     assert e["h2d_bytes_per_step"] > 0 and e["d2h_bytes_per_step"] > 0 and 0 < e["value"] < line["value"]
     r = line["roofline"]
     assert r["bound"] == "hbm" and r["unit"] == "GB/s" and abs(r["frac"] - r["achieved"] / r["peak"]) < 1e-9
     assert r["traffic"] is None or r["traffic"] > 0
-    cb = line["cpu_baseline"]
-    assert cb["kind"] == "port" and cb["cores"] >= 1 and cb["value"] > 0
+    if n_gpus == 1:   # the CPU arm runs on rank 0 at N=1 only
+        cb = line["cpu_baseline"]
+        assert cb["kind"] == "port" and cb["cores"] >= 1 and cb["value"] > 0
     c = line["clocks"]
     assert not set(c["reasons"]) & {"hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown"}
+    if name.startswith("r2"):   # round 2: the whole workload is checked inside the bench run
+        p = line["parity"]
+        assert p["checked"] and p["members_equal"] and p["mismatches"] == [] and p["entries"] > 100_000_000
+        assert ("oracle" in p["against"]) == (n_gpus == 1)
+        if n_gpus == 1:
+            assert line["cpu_baseline"]["same_config"] is True
