@@ -2,10 +2,10 @@
 committed GPU-arm line under profiles/ (written by `python bench.py` on a B200)."""
 import json
 import os
-
-import pytest
 import subprocess
 import sys
+
+import pytest
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 BASE = ["metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling", "vs_baseline",
