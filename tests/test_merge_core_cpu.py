@@ -102,7 +102,7 @@ def test_harness_builds():
 def test_reference_merge_cases(tmp_path, nsplits):
     rng = random.Random(nsplits)
     # seqset_merger_test.cpp:124-133, make_mergemap_test.cpp:123-137
-    for case in ([[O.tseq(x) for x in ("abc", "bcd", "cde", "cdf", "dfg")]],                       # seqset_flat_test.cpp:14-46
+    for case in ([[O.tseq(x) for x in ("abc", "bcd", "cde", "cdf", "dfg")]],                       # seqset_flat_test.cpp:14-45
                  [[O.tseq("abc"), O.tseq("de")]],
                  [[O.tseq("abc"), O.tseq("cde")], [O.tseq("abc"), O.tseq("efg")]],
                  [[O.tseq("ab"), O.tseq("bc"), O.tseq("cd"), O.tseq("be")], [O.tseq("AB"), O.tseq("BC"), O.tseq("CD"), O.tseq("BE")]]):

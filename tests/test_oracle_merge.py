@@ -150,7 +150,7 @@ def check_merge(part_reads, nsplits):
     assert M.flat_sequences(tb["fixed"], tb["prev"], tb["sizes"]) == merged
 
 
-def test_seqset_flat_test():  # seqset_flat_test.cpp:14-46: the flat sequences are the seqset's entry sequences
+def test_seqset_flat_test():  # seqset_flat_test.cpp:14-45: the flat sequences are the seqset's entry sequences
     reads = [O.tseq(x) for x in ("abc", "bcd", "cde", "cdf", "dfg")]
     ss = O.seqset_closed_form(reads)
     prev01 = [unpack(ss["prev"][b], ss["n"]) for b in range(4)]

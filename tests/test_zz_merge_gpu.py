@@ -109,7 +109,7 @@ def test_golden_family_lambda_every_member(B):
 @pytest.mark.parametrize("nsplits", [1, 7, 100000])
 def test_reference_merge_cases(B, nsplits):
     rng = random.Random(nsplits)
-    for case in ([[O.tseq(x) for x in ("abc", "bcd", "cde", "cdf", "dfg")]],                       # seqset_flat_test.cpp:14-46
+    for case in ([[O.tseq(x) for x in ("abc", "bcd", "cde", "cdf", "dfg")]],                       # seqset_flat_test.cpp:14-45
                  [[O.tseq("abc"), O.tseq("de")]],                                       # seqset_merger_test.cpp:124-127
                  [[O.tseq("abc"), O.tseq("cde")], [O.tseq("abc"), O.tseq("efg")]],      # :129-133
                  [[O.tseq("ab"), O.tseq("bc"), O.tseq("cd"), O.tseq("be")],             # make_mergemap_test.cpp:130-137
