@@ -92,6 +92,8 @@ void usage() {
                "  --min-good-run arg (=2)         Minimum number of good bases between corrections\n"
                "  --min-reads arg (=0.4)          Minimum fraction of reads that must survive read correction\n"
                "  --warn-reads arg (=0.7)         Warn when this fraction of reads does not survive read correction\n"
+               "  --sample-reads arg (=0)         If non-zero, sample this portion of the input reads\n"
+               "  --cut-reads arg                 e.g. 10-100: only use the 10th through the 100th base of each read\n"
                "  --device arg (=0)               CUDA device ordinal\n"
                "  (accepted for compatibility, no effect here: --tmp, --keep-tmp, --threads, --max-mem, --tmp-encoding,\n"
                "   --cache, --stats)\n";
@@ -337,6 +339,125 @@ uint64_t import_bam(const std::string& path, bool* got_paired, PairFn pair, Sing
   return n;
 }
 
+// --sample-reads and --cut-reads, per record (a single read or a pair of mates)
+struct RecordFilter {
+  double sample = 0, accum = 0.5;        // read_importer_state::process, biograph_create.cpp:125-132 (m_sample_accum = 0.5, :191)
+  unsigned cut_start = 0, cut_end = 0;   // read_batch::cut_reads, bs/read_importer.cpp:157-169; 0-0 = off
+  bool active() const { return sample != 0 || cut_end != 0; }
+  bool keep() {
+    if (sample == 0) return true;
+    accum += sample;
+    if (accum > 1) { accum -= 1; return true; }
+    return false;
+  }
+  std::string cut(const std::string& seq) const {
+    if (!cut_end) return seq;
+    const size_t this_end = std::min<size_t>(cut_end, seq.size());
+    if (this_end <= cut_start)   // CHECK_GT(this_end, start) aborts the reference here
+      throw std::runtime_error(fmt("Check failed: this_end > start (%zu vs. %u): a read is too short for --cut-reads", this_end, cut_start));
+    return seq.substr(cut_start, this_end - cut_start);
+  }
+};
+
+// validate_cut_param (biograph_create.cpp:376-412)
+std::pair<unsigned, unsigned> validate_cut_param(const std::string& param, const std::string& value) {
+  if (value.empty()) return {0, 0};
+  const size_t it = value.find('-');
+  if (it == std::string::npos) throw std::runtime_error(param + " must specify a range separated by a dash");
+  unsigned v[2];
+  const std::string part[2] = {value.substr(0, it), value.substr(it + 1)};
+  for (int i = 0; i < 2; ++i) {
+    try {
+      v[i] = (unsigned)std::stoul(part[i]);
+    } catch (const std::exception&) {
+      throw std::runtime_error(param + " must specify a numerical range; couldn't parse " + part[i] + " as a number");
+    }
+  }
+  if (v[1] <= v[0]) throw std::runtime_error(fmt("%s must specify a nonzero range; %u must be less than %u", param.c_str(), v[0], v[1]));
+  return {v[0], v[1]};
+}
+
+// Where imported records go (read_importer_base::read_batch::add_paired_read / add_unpaired_read).  `text`, when
+// set, takes whole-record FASTQ text instead (the GPU parser): used for plain single-file input without filters.
+struct ReadSink {
+  std::function<void(const std::string&, const std::string&)> pair;
+  std::function<void(const std::string&)> single;
+  std::function<uint64_t(std::string& carry, bool last)> text;
+};
+
+// the import stage over every --reads / --pair argument (SEQSETMain::run, biograph_create.cpp:575-627); returns
+// the number of reads read (before sampling, as m_read_count); *exit_code != 0: a refusal was printed
+uint64_t import_inputs(const Args& a, RecordFilter& filt, bool* got_paired, ReadSink& sink, int* exit_code) {
+  uint64_t read_count = 0;
+  auto put_pair = [&](const std::string& x, const std::string& y) { if (filt.keep()) sink.pair(filt.cut(x), filt.cut(y)); };
+  auto put_single = [&](const std::string& x) { if (filt.keep()) sink.single(filt.cut(x)); };
+  for (size_t i = 0; i < a.reads.size(); ++i) {
+    std::string in_reads = a.reads[i] == "-" ? "/dev/stdin" : a.reads[i];
+    const std::string in_pairs = a.pairs.empty() ? "" : a.pairs[i];
+    std::string in_format = a.format;
+    if (in_format == "auto") {  // :583-606
+      if (a.interleaved) { std::cerr << "--interleaved specified. Assuming fastq format.\n"; in_format = "fastq"; }
+      else if (!in_pairs.empty()) { std::cerr << "--pair specified. Assuming fastq format.\n"; in_format = "fastq"; }
+      else if (ends_with(in_reads, ".bam")) in_format = "bam";
+      else if (ends_with(in_reads, ".cram")) in_format = "cram";
+      else if (ends_with(in_reads, ".fq") || ends_with(in_reads, ".fq.gz") || ends_with(in_reads, ".fastq") || ends_with(in_reads, ".fastq.gz")) in_format = "fastq";
+      else if (in_reads == "/dev/stdin") in_format = "bam";
+      else {
+        std::cerr << "Cannot determine the input file type of " << in_reads << ".\n"
+                  << "Input file does not end in .bam .cram .fq .fastq .fq.gz or .fastq.gz.\nPlease specify --format.\n";
+        *exit_code = 1;
+        return read_count;
+      }
+    }
+    if (in_format == "cram") die("bgx-create reads FASTQ (plain or gzip) and BAM; cram input needs the reference's htslib importer");
+    if (in_format == "bam") {
+      read_count += import_bam(in_reads, got_paired, put_pair, put_single);
+    } else if (!in_pairs.empty()) {
+      // two files in step: mates leave together
+      LineReader r1(in_reads), r2(in_pairs);
+      std::string b1, b2, rec1[4], rec2[4];
+      size_t p1 = 0, p2 = 0;
+      for (;;) {
+        const bool h1 = next_record(r1, b1, p1, rec1), h2 = next_record(r2, b2, p2, rec2);
+        if (h1 != h2) throw std::runtime_error("Pair files " + in_reads + " and " + in_pairs + " hold different numbers of reads");
+        if (!h1) break;
+        *got_paired = true;
+        put_pair(rec1[1], rec2[1]);
+        read_count += 2;
+      }
+    } else if (sink.text && !filt.active() && (a.interleaved || !*got_paired)) {
+      // whole-file chunks go to the GPU parser (split, validate, 2-bit pack on the device)
+      LineReader r(in_reads);
+      std::string carry;
+      uint64_t n_file = 0;
+      while (r.read_chunk(carry, 64 << 20)) n_file += sink.text(carry, false);
+      n_file += sink.text(carry, true);
+      if (a.interleaved) {
+        if (n_file % 2) throw std::runtime_error("Interleaved fastq " + in_reads + " holds an odd number of reads");
+        *got_paired = *got_paired || n_file > 0;
+      }
+      read_count += n_file;
+    } else {
+      // one file, record by record on the host (filters, the read dump, or single reads after paired input)
+      LineReader r(in_reads);
+      std::string b, rec[4], rec2[4];
+      size_t p = 0;
+      while (next_record(r, b, p, rec)) {
+        if (a.interleaved) {
+          if (!next_record(r, b, p, rec2)) throw std::runtime_error("Interleaved fastq " + in_reads + " holds an odd number of reads");
+          *got_paired = true;
+          put_pair(rec[1], rec2[1]);
+          read_count += 2;
+        } else {
+          put_single(rec[1]);
+          ++read_count;
+        }
+      }
+    }
+  }
+  return read_count;
+}
+
 uint64_t reference_bases(const std::string& ref) {
   // the reference directory holds the FASTA as source.fasta (biograph reference); a FASTA path works too
   std::vector<std::string> cand = {ref, ref + "/source.fasta", ref + "/reference.fasta"};
@@ -367,20 +488,27 @@ int main(int argc, char** argv) {
     const unsigned max_corrections = (unsigned)validate_param("max-corrections", a.max_corrections, 0, 32);
     const unsigned min_good_run = (unsigned)validate_param("min-good-run", a.min_good_run, 0, 64);
     if (validate_param("overrep-threshold", a.overrep, 0, 10000000) != 0) die("--overrep-threshold other than 0 is not supported by bgx-create");
-    if (validate_float_param("sample-reads", a.sample_reads, 0.0f, 1.0f) != 0.0f) die("--sample-reads is not supported by bgx-create");
-    if (!a.cut_reads.empty()) die("--cut-reads is not supported by bgx-create");
+    RecordFilter filt;
+    filt.sample = validate_float_param("sample-reads", a.sample_reads, 0.0f, 1.0f);
+    {
+      const std::pair<unsigned, unsigned> cut = validate_cut_param("cut-reads", a.cut_reads);
+      filt.cut_start = cut.first;
+      filt.cut_end = cut.second;
+    }
     if (a.allow_long_reads) die("--allow-long-reads is not supported by bgx-create (reads are at most 255 bases)");
     static const std::set<std::string> formats = {"bam", "cram", "fastq", "auto"};
     if (!formats.count(a.format)) die("Invalid input format '" + a.format + "'");
     if (!a.pairs.empty() && a.pairs.size() != a.reads.size())
       die("If pair files are present, there must be the same number of them as read files.");
     if (a.dump_reads) {
-      // test hook: the BAM importer alone -- one line per imported read or pair ("a\tb"), then the count
+      // test hook: the import stage alone, no GPU -- one line per imported read or pair ("a\tb"), then the count
       bool paired = false;
-      uint64_t n = 0;
-      for (const std::string& f : a.reads)
-        n += import_bam(f, &paired, [](const std::string& x, const std::string& y) { std::cout << x << "\t" << y << "\n"; },
-                        [](const std::string& x) { std::cout << x << "\n"; });
+      int rc = 0;
+      ReadSink sink;
+      sink.pair = [](const std::string& x, const std::string& y) { std::cout << x << "\t" << y << "\n"; };
+      sink.single = [](const std::string& x) { std::cout << x << "\n"; };
+      const uint64_t n = import_inputs(a, filt, &paired, sink, &rc);
+      if (rc) return rc;
       std::cout << "# reads " << n << " paired " << (paired ? 1 : 0) << "\n";
       return 0;
     }
@@ -432,74 +560,36 @@ int main(int argc, char** argv) {
     std::cerr << "Importing reads\n";
     bgx_bs::kmer_counter counter(sess);
     counter.start_prob_pass();
-    uint64_t read_count = 0;
     bool got_paired = false;
-    for (size_t i = 0; i < a.reads.size(); ++i) {
-      std::string in_reads = a.reads[i] == "-" ? "/dev/stdin" : a.reads[i];
-      const std::string in_pairs = a.pairs.empty() ? "" : a.pairs[i];
-      std::string in_format = a.format;
-      if (in_format == "auto") {  // :583-606
-        if (a.interleaved) { std::cerr << "--interleaved specified. Assuming fastq format.\n"; in_format = "fastq"; }
-        else if (!in_pairs.empty()) { std::cerr << "--pair specified. Assuming fastq format.\n"; in_format = "fastq"; }
-        else if (ends_with(in_reads, ".bam")) in_format = "bam";
-        else if (ends_with(in_reads, ".cram")) in_format = "cram";
-        else if (ends_with(in_reads, ".fq") || ends_with(in_reads, ".fq.gz") || ends_with(in_reads, ".fastq") || ends_with(in_reads, ".fastq.gz")) in_format = "fastq";
-        else if (in_reads == "/dev/stdin") in_format = "bam";
-        else {
-          std::cerr << "Cannot determine the input file type of " << in_reads << ".\n"
-                    << "Input file does not end in .bam .cram .fq .fastq .fq.gz or .fastq.gz.\nPlease specify --format.\n";
-          return 1;
-        }
-      }
-      if (in_format == "cram") die("bgx-create reads FASTQ (plain or gzip) and BAM; cram input needs the reference's htslib importer");
-      if (in_format == "bam") {
-        // mates go in back to back (reads 2i, 2i + 1 of the session are mates once anything is paired); a single
-        // read of a paired file gets a one-base partner, which correction drops (shorter than a k-mer), leaving
-        // the read a single one for make_readmap (bgx.h: "a pair with one read dropped is a single read")
-        bgx_bs::kmer_counter::prob_pass_processor proc(counter);
-        uint64_t plain_singles = 0;
-        auto add_pair = [&](const std::string& x, const std::string& y) {
-          if (plain_singles) throw std::runtime_error(in_reads + ": paired records after unpaired ones are not supported by bgx-create");
-          proc.add(x);
-          proc.add(y);
-        };
-        auto add_single = [&](const std::string& x) {
-          if (got_paired) { proc.add(x); proc.add(std::string("A")); }
-          else { proc.add(x); ++plain_singles; }
-        };
-        read_count += import_bam(in_reads, &got_paired, add_pair, add_single);
-        proc.flush_all();
-        continue;
-      }
-      if (in_pairs.empty()) {
-        // whole-file chunks go to the GPU parser (split, validate, 2-bit pack on the device)
-        LineReader r(in_reads);
-        std::string carry;
-        uint64_t n_file = 0;
-        while (r.read_chunk(carry, 64 << 20)) n_file += feed_fastq_text(sess, carry, false);
-        n_file += feed_fastq_text(sess, carry, true);
-        if (a.interleaved) {
-          if (n_file % 2) throw std::runtime_error("Interleaved fastq " + in_reads + " holds an odd number of reads");
-          got_paired = got_paired || n_file > 0;
-        }
-        read_count += n_file;
-      } else {
-        // two files in step: mates are appended back to back
-        LineReader r1(in_reads), r2(in_pairs);
-        std::string b1, b2, rec1[4], rec2[4];
-        size_t p1 = 0, p2 = 0;
-        bgx_bs::kmer_counter::prob_pass_processor proc(counter);
-        for (;;) {
-          const bool h1 = next_record(r1, b1, p1, rec1), h2 = next_record(r2, b2, p2, rec2);
-          if (h1 != h2) throw std::runtime_error("Pair files " + in_reads + " and " + in_pairs + " hold different numbers of reads");
-          if (!h1) break;
-          proc.add(rec1[1]);
-          proc.add(rec2[1]);
-          read_count += 2;
-          got_paired = true;
-        }
-        proc.flush_all();
-      }
+    uint64_t read_count = 0;
+    {
+      // Mates go in back to back: reads 2i, 2i + 1 of the session are mates once anything is paired.  A single
+      // read among pairs (a BAM orphan, an unpaired file after a paired one) gets a one-base partner, which
+      // correction drops (shorter than a k-mer), leaving the read a single one for make_readmap (bgx.h: "a pair
+      // with one read dropped is a single read").  Pairs after plain single reads would shift that layout.
+      bgx_bs::kmer_counter::prob_pass_processor proc(counter);
+      uint64_t plain_singles = 0;
+      ReadSink sink;
+      sink.pair = [&](const std::string& x, const std::string& y) {
+        if (plain_singles) throw std::runtime_error("paired reads after unpaired ones are not supported by bgx-create: put the paired input first");
+        proc.add(x);
+        proc.add(y);
+      };
+      sink.single = [&](const std::string& x) {
+        proc.add(x);
+        if (got_paired) proc.add(std::string("A")); else ++plain_singles;
+      };
+      sink.text = [&](std::string& carry, bool last) {
+        proc.flush_all();   // keep the order of the reads across inputs
+        if (a.interleaved && plain_singles) throw std::runtime_error("paired reads after unpaired ones are not supported by bgx-create: put the paired input first");
+        const uint64_t n = feed_fastq_text(sess, carry, last);
+        if (!a.interleaved) plain_singles += n;
+        return n;
+      };
+      int rc = 0;
+      read_count = import_inputs(a, filt, &got_paired, sink, &rc);
+      if (rc) return rc;
+      proc.flush_all();
     }
     if (!a.pairs.empty() && !got_paired) throw std::runtime_error("Pair files specified but no pairs were successfully imported");
     if (read_count == 0) throw std::runtime_error("\nNo reads were imported, exiting.");
