@@ -612,7 +612,10 @@ int main(int argc, char** argv) {
       html << "<html><head><title>k-mer count histogram</title></head><body><h1>k-mer count histogram</h1>\n"
            << "<p>" << ks->size() << " " << kmer_size << "-mers with count &gt;= " << min_kmer_count << "</p>\n<table><tr><th>count</th><th>k-mers</th></tr>\n";
       for (const auto& rec : kres.second[1].records) html << "<tr><td>" << rec.first << "</td><td>" << rec.second << "</td></tr>\n";
-      html << "</table></body></html>\n";
+      // the points in the form the reference's report carries them (kmerize_bf.cpp:451-454), for tools that scrape it
+      html << "</table>\n<script>var kmer_histogram = [";
+      for (const auto& rec : kres.second[1].records) html << "{'x':" << rec.first << ",'y':" << rec.second << "},";
+      html << "];</script></body></html>\n";
     }
     stages.end("kmerization");
 
