@@ -34,7 +34,7 @@ typedef struct bgx_ctx bgx_ctx;
 typedef struct bgx_options {
   int32_t kmer_size;          /* --kmer-size, default 30; 16..31 (bs/kmer_counter.cpp:52-54) */
   int32_t min_kmer_count;     /* --min-kmer-count, default 5 */
-  int32_t max_corrections;    /* --max-corrections, default 8 (<= 16 here) */
+  int32_t max_corrections;    /* --max-corrections, default 8; 0..32 as the CLI allows (biograph_create.cpp:486) */
   int32_t min_good_run;       /* --min-good-run, default 2 */
   float trim_after_portion;   /* --trim-after-portion, default 0.7f (parsed as float: :489-490) */
   int32_t device;             /* CUDA device ordinal */
