@@ -13,9 +13,9 @@
 //   <out>/qc/create_log.txt, <out>/qc/kmer_quality_report.html, <out>/analysis/
 // Inputs: FASTQ, plain or gzip (zlib), single, --pair <second file> or --interleaved; BAM (BGZF through
 // zlib, records decoded here the way read_importer does through htslib: secondary / supplementary
-// records skipped, reverse-strand records reverse-complemented, mates joined by read name).  CRAM
-// (htslib's codecs + the reference FASTA) is rejected with a message.  There is no CPU fallback: the
-// stages need a CUDA device.
+// records skipped, reverse-strand records reverse-complemented, mates joined by read name) and CRAM 3.0
+// (cram_reader.hpp; bases rebuilt from <ref>/source.fasta).  There is no CPU fallback: the stages need
+// a CUDA device.
 #include <sys/stat.h>
 #include <zlib.h>
 
@@ -31,6 +31,7 @@
 
 #include "bgx_build_seqset.hpp"
 #include "cli_util.hpp"
+#include "cram_reader.hpp"
 
 using namespace bgx_cli;
 
@@ -79,7 +80,7 @@ void usage() {
             << "Convert reads to BioGraph format.\n\n"
                "  --out arg                       Output BioGraph name (.bg)\n"
                "  --ref arg                       Reference directory (or FASTA; only its size is used here)\n"
-               "  --reads, --in arg               Input file to process (fastq, fastq.gz, bam; - for STDIN)\n"
+               "  --reads, --in arg               Input file to process (fastq, fastq.gz, bam, cram; - for STDIN)\n"
                "  --format arg (=auto)            Input file format when using STDIN\n"
                "  --interleaved                   Input reads are interleaved (fastq only)\n"
                "  --pair arg                      Second input file containing read pairs (fastq only)\n"
@@ -221,16 +222,14 @@ bool next_record(LineReader& r, std::string& buf, size_t& pos, std::string rec[4
 //   "BAM\1", l_text, text, n_ref, { l_name, name, l_ref } x n_ref, then records
 //   block_size | refID pos l_read_name mapq bin n_cigar_op flag l_seq next_refID next_pos tlen |
 //   read_name (NUL terminated) | cigar (4 x n_cigar_op) | seq (4-bit codes, (l_seq + 1) / 2 bytes) | qual | tags
-struct BamRecord {
-  std::string qname, seq;
-  uint16_t flag = 0;
-};
+using BamRecord = bgx_cli::CramRecord;   // read name, bases as sequenced, BAM flags
 
 struct BamReader {
   gzFile f = nullptr;
   std::string name;
   std::vector<uint8_t> buf;
-  uint64_t records = 0;
+  uint64_t n_records = 0;
+  uint64_t records() const { return n_records; }
   explicit BamReader(const std::string& path) : name(path) {
     f = path == "/dev/stdin" ? gzdopen(0, "rb") : gzopen(path.c_str(), "rb");
     if (!f) throw std::runtime_error("Unable to open file " + path);            // read_importer.cpp:490-492
@@ -271,7 +270,7 @@ struct BamReader {
         if (idx >= 0 && idx < 26) c = comp[idx];
       }
     }
-    ++records;
+    ++n_records;
     return true;
   }
 
@@ -303,9 +302,8 @@ struct BamReader {
 // together; whatever never met a mate is a single read at the end.  pair(a, b) / single(a) receive the reads;
 // returns the number of reads imported.  The k-mer counter only knows ACGT and N (dna_base(char) throws on
 // anything else, modules/bio_base/dna_base.h:38-56), so other IUPAC codes are refused with its message.
-template <typename PairFn, typename SingleFn>
-uint64_t import_bam(const std::string& path, bool* got_paired, PairFn pair, SingleFn single) {
-  BamReader in(path);
+template <typename Reader, typename PairFn, typename SingleFn>
+uint64_t import_alignments(Reader& in, const std::string& path, bool* got_paired, PairFn pair, SingleFn single) {
   BamRecord rec;
   std::unordered_map<std::string, std::string> pair_cache;   // qname -> the mate seen first
   uint64_t n = 0;
@@ -330,7 +328,7 @@ uint64_t import_bam(const std::string& path, bool* got_paired, PairFn pair, Sing
       single(rec.seq);
     }
   }
-  if (in.records == 0) std::cerr << "WARNING: " << path << ": no records present\n";
+  if (in.records() == 0) std::cerr << "WARNING: " << path << ": no records present\n";
   // deterministic order for the leftovers (the reference walks a hash map)
   std::vector<std::string> names;
   for (const auto& kv : pair_cache) names.push_back(kv.first);
@@ -409,9 +407,15 @@ uint64_t import_inputs(const Args& a, RecordFilter& filt, bool* got_paired, Read
         return read_count;
       }
     }
-    if (in_format == "cram") die("bgx-create reads FASTQ (plain or gzip) and BAM; cram input needs the reference's htslib importer");
     if (in_format == "bam") {
-      read_count += import_bam(in_reads, got_paired, put_pair, put_single);
+      BamReader in(in_reads);
+      read_count += import_alignments(in, in_reads, got_paired, put_pair, put_single);
+    } else if (in_format == "cram") {
+      // CRAM_OPT_REFERENCE = <ref dir>/source.fasta (read_importer.cpp:498-509)
+      CramReader in(in_reads, a.ref);
+      read_count += import_alignments(in, in_reads, got_paired, put_pair, put_single);
+      if (getenv("BGX_CRAM_STATS"))
+        for (const auto& kv : in.stats()) std::cerr << "cram: " << kv.first << ": " << kv.second << "\n";
     } else if (!in_pairs.empty()) {
       // two files in step: mates leave together
       LineReader r1(in_reads), r2(in_pairs);
