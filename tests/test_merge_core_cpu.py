@@ -172,3 +172,35 @@ def test_entry_shapes(tmp_path, mode):
         if mode == "dup" and nparts > 1:
             reads[1] = list(reads[0])
         check_against_oracle(tmp_path, [seqset_entries(r) for r in reads], rng.choice([1, 2, 3, 7, 64, 100000]), rng)
+
+
+def test_five_hiv_seqsets(tmp_path):
+    """the five reference-built HIV seqsets (datasets/hiv/biograph/*.bg: 78 k - 559 k entries of up to 250 bases, the
+    inputs of the reference's legacy merge test, modules/biograph/biograph_merge_test.cpp:170-190) merged in one go:
+    1.02 M input entries, heavy duplication between the samples"""
+    import bisect
+    names = ["ERR381524", "ERR732129", "ERR732130", "ERR732131", "ERR732132"]
+    parts = [RS.tables(nm) for nm in names]
+    old = [pack_bits(np.arange(p["n"]) % 3 == 0) for p in parts]
+    out = run_harness(tmp_path, parts, old, 100000)
+    assert out["missing"] == 0
+    flats = []
+    for p in parts:
+        prev01 = [np.unpackbits(p["prev"][b].view(np.uint8), bitorder="little")[:p["n"]] for b in range(4)]
+        flats.append(M.flat_sequences(p["fixed"], prev01, p["sizes"]))
+    for got, want in zip(out["flat"], flats):
+        assert got == want
+    merged, bits = M.make_mergemap_sorted(flats)
+    n = len(merged)
+    assert out["n"] == n and 558849 < n < sum(p["n"] for p in parts)
+    assert np.array_equal(out["sizes"], np.array([len(e) for e in merged], dtype=np.uint16))
+    lcp = lambda a, b: next((i for i, (x, y) in enumerate(zip(a, b)) if x != y), min(len(a), len(b)))
+    step = 97
+    assert [int(out["shared"][i]) for i in range(1, n, step)] == [lcp(merged[i - 1], merged[i]) for i in range(1, n, step)]
+    prev = M.merge_prev_closed_form(merged)
+    for b in range(4):
+        assert np.array_equal(out["prev"][b], pack_bits(prev[b])), b
+    for p in range(len(parts)):
+        assert np.array_equal(out["mergemap"][p], pack_bits(bits[p]))
+        old01 = (np.arange(parts[p]["n"]) % 3 == 0).astype(np.uint8)
+        assert np.array_equal(out["migrated"][p], pack_bits(M.migrate_source_bits(old01, bits[p])))
