@@ -408,7 +408,7 @@ class CramReader {
   // ref: a reference directory holding source.fasta (what `biograph create --ref` takes), or a FASTA file; may be
   // empty when every slice embeds its reference or stores its bases verbatim
   CramReader(const std::string& path, const std::string& ref) : m_name(path), m_ref_path(ref) {
-    m_f = fopen(path.c_str(), "rb");
+    m_f = path == "/dev/stdin" ? stdin : fopen(path.c_str(), "rb");
     if (!m_f) throw std::runtime_error("Unable to open file " + path);
     uint8_t def[26];
     if (fread(def, 1, 26, m_f) != 26 || memcmp(def, "CRAM", 4) != 0) throw std::runtime_error(path + " is not a valid CRAM file.");
@@ -437,7 +437,7 @@ class CramReader {
       m_ref_names.push_back(line.substr(sn + 4, e == std::string::npos ? std::string::npos : e - sn - 4));
     }
   }
-  ~CramReader() { if (m_f) fclose(m_f); }
+  ~CramReader() { if (m_f && m_f != stdin) fclose(m_f); }
   CramReader(const CramReader&) = delete;
   CramReader& operator=(const CramReader&) = delete;
 
@@ -483,17 +483,35 @@ class CramReader {
     if (got == 0) return false;
     if (got != 4) throw cram::err("truncated container header in " + m_name);
     memcpy(&c.length, hdr, 4);
-    // the rest of the header is variable-length: read generously, then seek back
-    uint8_t buf[1024];
-    const long at = ftell(m_f);
-    const size_t n = fread(buf, 1, sizeof buf, m_f);
-    cram::Cursor cur(buf, n);
-    c.ref_id = cur.itf8(); c.start = cur.itf8(); c.span = cur.itf8(); c.n_records = cur.itf8();
-    c.record_counter = cur.ltf8(); c.bases = cur.ltf8(); c.n_blocks = cur.itf8();
-    c.landmarks = cur.itf8_array();
-    cur.u32();   // CRC32 of the header
+    // the rest of the header is variable-length integers: taken byte by byte, so a pipe works as well as a file
+    auto byte = [&]() -> uint8_t {
+      const int ch = fgetc(m_f);
+      if (ch == EOF) throw cram::err("truncated container header in " + m_name);
+      return (uint8_t)ch;
+    };
+    auto itf8 = [&]() -> int32_t {
+      uint8_t b[5];
+      b[0] = byte();
+      const int extra = b[0] < 0x80 ? 0 : b[0] < 0xc0 ? 1 : b[0] < 0xe0 ? 2 : b[0] < 0xf0 ? 3 : 4;
+      for (int i = 1; i <= extra; ++i) b[i] = byte();
+      return cram::Cursor(b, (size_t)extra + 1).itf8();
+    };
+    auto ltf8 = [&]() -> int64_t {
+      uint8_t b[9];
+      b[0] = byte();
+      int extra = 0;
+      while (extra < 8 && (b[0] & (0x80 >> extra))) ++extra;
+      for (int i = 1; i <= extra; ++i) b[i] = byte();
+      return cram::Cursor(b, (size_t)extra + 1).ltf8();
+    };
+    c.ref_id = itf8(); c.start = itf8(); c.span = itf8(); c.n_records = itf8();
+    c.record_counter = ltf8(); c.bases = ltf8(); c.n_blocks = itf8();
+    const int32_t n_landmarks = itf8();
+    if (n_landmarks < 0) throw cram::err("negative landmark count");
+    c.landmarks.resize((size_t)n_landmarks);
+    for (int32_t& l : c.landmarks) l = itf8();
+    for (int i = 0; i < 4; ++i) byte();   // CRC32 of the header
     if (c.length < 0) throw cram::err("negative container length");
-    fseek(m_f, at + (long)(cur.p - buf), SEEK_SET);
     body.resize((size_t)c.length);
     if (c.length && fread(body.data(), 1, body.size(), m_f) != body.size()) throw cram::err("truncated container in " + m_name);
     return true;

@@ -306,3 +306,15 @@ def test_features_flags_and_layouts_from_a_written_cram(tmp_path):
             ref1[4:16], rc(m2) + "\t" + m1, emb[10:30], ref2[149:157]]
     assert (n, paired) == (14, 1)   # 13 lines: one of them is a pair
     assert lines == want
+
+
+def test_stdin(fx):
+    """`--reads -` (SEQSETMain reads BAM from STDIN by default, CRAM with --format cram, biograph_create.cpp:583-606)"""
+    d, z = fx
+    want = dump(["--reads", d / "t.cram", "--ref", d / "ref"])[0]
+    for fmt, path in (("cram", d / "t.cram"),):
+        with open(path, "rb") as f:
+            r = subprocess.run([EXE, "--dump-reads", "--out", "/nonexistent/x.bg", "--reads", "-", "--format", fmt, "--ref", str(d / "ref")],
+                               stdin=f, capture_output=True, text=True, timeout=120)
+        assert r.returncode == 0, r.stderr
+        assert r.stdout.splitlines()[:-1] == want
