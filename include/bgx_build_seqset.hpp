@@ -692,6 +692,7 @@ class spiral_file_reader {
     if (m_fd < 0) throw io_exception("Could not open spiral file " + path + ": " + strerror(errno));
     const off_t end = ::lseek(m_fd, 0, SEEK_END);
     if (end < 22) throw io_exception(path + " is not a spiral file (too short)");
+    m_size = (uint64_t)end;
     const uint64_t fsz = (uint64_t)end, tail_n = std::min<uint64_t>(fsz, 65536 + 22 + 20);
     std::string tail = pread_str(fsz - tail_n, tail_n);
     size_t e = std::string::npos;
@@ -712,6 +713,7 @@ class spiral_file_reader {
       if (get16(cd, p + 10) != 0) throw io_exception(path + ": compressed member (a spiral file stores its members)");
       uint64_t usize = get32(cd, p + 24), lho = get32(cd, p + 42);
       const uint16_t nl = get16(cd, p + 28), xl = get16(cd, p + 30), cl = get16(cd, p + 32);
+      if (p + 46 + (size_t)nl + xl > cd.size()) throw io_exception(path + ": bad central directory");
       const std::string name = cd.substr(p + 46, nl);
       size_t x = p + 46 + nl;
       const size_t xe = x + xl;
@@ -746,6 +748,7 @@ class spiral_file_reader {
   template <typename T>
   std::vector<T> read_array(const std::string& name) const {
     const member& m = find(name);
+    if (m.offset > m_size || m.size > m_size - m.offset) throw io_exception("corrupt spiral file " + m_path + ": member " + name + " lies beyond the end of the file");
     std::vector<T> v(m.size / sizeof(T));
     pread_into(m.offset, v.data(), v.size() * sizeof(T));
     return v;
@@ -764,9 +767,16 @@ class spiral_file_reader {
   }
 
  private:
-  static uint16_t get16(const std::string& s, size_t i) { uint16_t v; memcpy(&v, s.data() + i, 2); return v; }
-  static uint32_t get32(const std::string& s, size_t i) { uint32_t v; memcpy(&v, s.data() + i, 4); return v; }
-  static uint64_t get64(const std::string& s, size_t i) { uint64_t v; memcpy(&v, s.data() + i, 8); return v; }
+  template <typename T>
+  static T get(const std::string& s, size_t i) {
+    if (i + sizeof(T) > s.size()) throw io_exception("corrupt spiral file: a header field lies beyond its record");
+    T v;
+    memcpy(&v, s.data() + i, sizeof(T));
+    return v;
+  }
+  static uint16_t get16(const std::string& s, size_t i) { return get<uint16_t>(s, i); }
+  static uint32_t get32(const std::string& s, size_t i) { return get<uint32_t>(s, i); }
+  static uint64_t get64(const std::string& s, size_t i) { return get<uint64_t>(s, i); }
   void pread_into(uint64_t off, void* dst, uint64_t n) const {
     char* p = static_cast<char*>(dst);
     while (n) {
@@ -776,12 +786,14 @@ class spiral_file_reader {
     }
   }
   std::string pread_str(uint64_t off, uint64_t n) const {
+    if (off > m_size || n > m_size - off) throw io_exception("corrupt spiral file " + m_path + ": a record lies beyond the end of the file");
     std::string s(n, '\0');
     pread_into(off, &s[0], n);
     return s;
   }
   std::string m_path;
   int m_fd;
+  uint64_t m_size = 0;
   std::vector<member> m_members;
   std::unordered_map<std::string, size_t> m_index;
 };
