@@ -173,6 +173,7 @@ struct Args {
   bool force = false;
   int device = 0;
   uint64_t parallel_splits = 0;
+  bool list_inputs = false;   // test hook: pre-flight + input reading only, no GPU
 };
 
 void usage() {
@@ -215,6 +216,7 @@ Args parse(int argc, char** argv) {
     else if (o == "--force" || o == "-f") a.force = true;
     else if (o == "--device") a.device = atoi(val().c_str());
     else if (o == "--parallel-splits") a.parallel_splits = strtoull(val().c_str(), nullptr, 10);
+    else if (o == "--list-inputs") a.list_inputs = true;
     else if (o == "--stats") a.stats_file = val();
     else if (o == "--tmp" || o == "--threads" || o == "--max-mem") (void)val();
     else if (o == "--keep-tmp" || o == "--cache" || o == "--debug") {}
@@ -258,6 +260,23 @@ int main(int argc, char** argv) {
       in_dirs.push_back(*bg);
     }
     if (in_dirs.size() < 2) throw std::runtime_error("Merge requires two or more unique BioGraphs.");
+    if (a.list_inputs) {
+      // test hook: what the merge would read, one JSON line per input (no GPU, nothing written)
+      for (const BgDir& d : in_dirs) {
+        std::cout << "{\"path\":" << json_str(d.path) << ",\"biograph_id\":" << json_str(d.biograph_id) << ",\"accession_id\":" << json_str(d.accession_id)
+                  << ",\"samples\":{";
+        for (size_t i = 0; i < d.samples.size(); ++i)
+          std::cout << (i ? "," : "") << json_str(d.samples[i].first) << ":" << json_str(d.samples[i].second);
+        std::cout << "},\"command_history\":" << d.command_history.size();
+        struct stat st;
+        if (stat(d.seqset().c_str(), &st) == 0) {
+          bgx_bs::seqset_file f(d.seqset());
+          std::cout << ",\"entries\":" << f.size() << ",\"max_read_len\":" << f.max_read_len() << ",\"uuid\":" << json_str(f.uuid());
+        }
+        std::cout << ",\"use_full_ids\":" << (use_full_ids ? "true" : "false") << "}\n";
+      }
+      return 0;
+    }
     if (!a.force && exists(a.out)) {
       std::cerr << "Refusing to overwrite '" + a.out + "'. Use --force to override.\n";
       return 1;

@@ -65,6 +65,36 @@ def test_preflight_messages(tmp_path):
     assert r.returncode == 1 and "unrecognised option '--bogus'" in r.stderr
 
 
+def test_list_inputs_reads_metadata_and_seqsets(tmp_path):
+    """--list-inputs: the pre-flight and the input reading of a merge without the GPU part: metadata with several
+    samples, a command history and escaped characters; seqset members re-zipped from the reference-built fixtures"""
+    import zipfile
+    members = ["seqset.json", "part_info.json", "fixed", "entry_sizes/packed_varbit_vector.json", "entry_sizes/elements",
+               "shared/packed_varbit_vector.json", "shared/elements"] + [f"prev_{b}/{m}" for b in "ACGT" for m in ("bitcount.json", "bits", "subaccum", "accum")]
+    dirs = []
+    for acc, name, samples, hist in (("fam one", "father_lambda", {"father": "aa", "mother": "bb"}, ['biograph create --in "x y.fq" --out a.bg', "second"]),
+                                     ("solo", "ERR732130", {"father": "cc"}, [])):
+        d = tmp_path / f"{name}.bg"
+        for sub in ("metadata", "coverage", "qc"):
+            os.makedirs(d / sub)
+        (d / "metadata" / "bg_info.json").write_text(json.dumps({"accession_id": acc, "biograph_id": "id-" + name, "command_history": hist,
+                                                                 "samples": samples, "version": "7.1.2-dev"}, indent=2))
+        with zipfile.ZipFile(d / "seqset", "w", zipfile.ZIP_STORED) as z:
+            z.writestr("file_info.json", json.dumps({"uuid": "uuid-" + name, "command_line": ["biograph", "create"]}, separators=(",", ":")))
+            for fn in members:
+                z.writestr(fn, RS.member(name, fn))
+        dirs.append(str(d))
+    r = run(MERGE, ["--list-inputs", "--out", str(tmp_path / "m.bg"), "--in"] + dirs)
+    assert r.returncode == 0, r.stderr
+    got = [json.loads(l) for l in r.stdout.splitlines()]
+    assert [g["accession_id"] for g in got] == ["fam one", "solo"]
+    assert got[0]["samples"] == {"father": "aa", "mother": "bb"} and got[0]["command_history"] == 2
+    assert (got[0]["entries"], got[0]["max_read_len"], got[0]["uuid"]) == (98006, 150, "uuid-father_lambda")
+    assert (got[1]["entries"], got[1]["max_read_len"]) == (78093, 250)
+    assert got[0]["use_full_ids"] is True      # "father" is a sample of both inputs (biograph_merge.cpp:137-146)
+    assert not (tmp_path / "m.bg").exists()
+
+
 def file_tables(path):
     """tables of a seqset spiral file written in the current layout"""
     z = RS.SpiralZip(path)
