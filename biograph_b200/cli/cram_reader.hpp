@@ -114,6 +114,14 @@ struct Cursor {
     return v;
   }
   bool done() const { return p >= end; }
+  // the next n bytes as a cursor of their own
+  Cursor sub(int32_t n) {
+    if (n < 0) throw err("negative length");
+    need((size_t)n);
+    Cursor s(p, (size_t)n);
+    p += n;
+    return s;
+  }
 };
 
 // ---- rANS 4x8 (order 0 and 1), the entropy coder of CRAM 3.0 blocks with method 4 ---------------------------------
@@ -259,13 +267,14 @@ struct BitReader {   // the core block, most significant bit first
   const uint8_t* p = nullptr;
   size_t n = 0, bit = 0;
   int get(int nbits) {
-    int v = 0;
+    if (nbits < 0 || nbits > 31) throw err("bit field wider than 31 bits");
+    uint32_t v = 0;
     for (int i = 0; i < nbits; ++i) {
       if ((bit >> 3) >= n) throw err("core block exhausted");
-      v = (v << 1) | ((p[bit >> 3] >> (7 - (bit & 7))) & 1);
+      v = (v << 1) | ((p[bit >> 3] >> (7 - (bit & 7))) & 1u);
       ++bit;
     }
-    return v;
+    return (int)v;
   }
 };
 
@@ -305,13 +314,15 @@ struct Encoding {
         e.alphabet = p.itf8_array();
         e.lens = p.itf8_array();
         if (e.alphabet.size() != e.lens.size() || e.alphabet.empty()) throw err("bad HUFFMAN encoding");
+        for (int32_t l : e.lens)
+          if (l < 0 || l > 31) throw err("bad HUFFMAN code length");
         // canonical codes: sort by (length, value), consecutive codes, shifted when the length grows
         for (size_t i = 0; i < e.alphabet.size(); ++i) e.codes.emplace_back(e.lens[i], e.alphabet[i]);
         std::sort(e.codes.begin(), e.codes.end());
         uint32_t code = 0;
         int prev_len = e.codes[0].first;
         for (size_t i = 0; i < e.codes.size(); ++i) {
-          if (i) { ++code; code <<= (e.codes[i].first - prev_len); prev_len = e.codes[i].first; }
+          if (i) { ++code; code = (uint32_t)((uint64_t)code << (e.codes[i].first - prev_len)); prev_len = e.codes[i].first; }
           e.code_vals.push_back(code);
         }
         break;
@@ -321,8 +332,14 @@ struct Encoding {
         e.val_enc = std::make_shared<Encoding>(parse(p));
         break;
       case BYTE_ARRAY_STOP: e.stop = p.u8(); e.ext_id = p.itf8(); break;
-      case BETA: e.offset = p.itf8(); e.nbits = p.itf8(); break;
-      case SUBEXP: e.offset = p.itf8(); e.k = p.itf8(); break;
+      case BETA:
+        e.offset = p.itf8(); e.nbits = p.itf8();
+        if (e.nbits < 0 || e.nbits > 31) throw err("bad BETA encoding");
+        break;
+      case SUBEXP:
+        e.offset = p.itf8(); e.k = p.itf8();
+        if (e.k < 0 || e.k > 30) throw err("bad SUBEXP encoding");
+        break;
       case GAMMA: e.offset = p.itf8(); break;
       default: throw err("encoding " + std::to_string(e.kind) + " is not supported by bgx-create");
     }
@@ -339,26 +356,28 @@ struct Encoding {
         size_t i = 0;
         while (i < codes.size()) {
           const int want = codes[i].first;
-          code = (code << (want - len)) | (uint32_t)s.core.get(want - len);
+          code = (uint32_t)((uint64_t)code << (want - len)) | (uint32_t)s.core.get(want - len);
           len = want;
           for (; i < codes.size() && codes[i].first == len; ++i)
             if (code_vals[i] == code) return codes[i].second;
         }
         throw err("bad HUFFMAN code in the core block");
       }
-      case BETA: return s.core.get(nbits) - offset;
+      case BETA: return (int32_t)((uint32_t)s.core.get(nbits) - (uint32_t)offset);
       case GAMMA: {
         int z = 0;
-        while (s.core.get(1) == 0) ++z;
+        while (s.core.get(1) == 0)
+          if (++z > 30) throw err("bad GAMMA code in the core block");
         return (int32_t)(((1u << z) | (uint32_t)s.core.get(z)) - (uint32_t)offset);
       }
       case SUBEXP: {
         int i = 0;
-        while (s.core.get(1) == 1) ++i;
-        int32_t v;
-        if (i == 0) v = s.core.get(k);
-        else { const int b = i + k - 1; v = (1 << b) | s.core.get(b); }
-        return v - offset;
+        while (s.core.get(1) == 1)
+          if (++i + k > 31) throw err("bad SUBEXP code in the core block");
+        uint32_t v;
+        if (i == 0) v = (uint32_t)s.core.get(k);
+        else { const int b = i + k - 1; v = (1u << b) | (uint32_t)s.core.get(b); }
+        return (int32_t)(v - (uint32_t)offset);
       }
       default: throw err("data series without a usable integer encoding");
     }
@@ -523,9 +542,7 @@ class CramReader {
     memcpy(h.sub, kDefaultSub, sizeof h.sub);
     cram::Cursor c(b.data.data(), b.data.size());
     {  // preservation map
-      const int32_t size = c.itf8();
-      cram::Cursor p(c.p, (size_t)size);
-      c.p += size;
+      cram::Cursor p = c.sub(c.itf8());
       const int32_t n = p.itf8();
       for (int32_t i = 0; i < n; ++i) {
         const char k0 = (char)p.u8(), k1 = (char)p.u8();
@@ -563,9 +580,7 @@ class CramReader {
       }
     }
     {  // data series encodings
-      const int32_t size = c.itf8();
-      cram::Cursor p(c.p, (size_t)size);
-      c.p += size;
+      cram::Cursor p = c.sub(c.itf8());
       const int32_t n = p.itf8();
       for (int32_t i = 0; i < n; ++i) {
         const int key = (p.u8() << 8);
@@ -574,9 +589,7 @@ class CramReader {
       }
     }
     {  // tag encodings
-      const int32_t size = c.itf8();
-      cram::Cursor p(c.p, (size_t)size);
-      c.p += size;
+      cram::Cursor p = c.sub(c.itf8());
       const int32_t n = p.itf8();
       for (int32_t i = 0; i < n; ++i) {
         const int32_t key = p.itf8();
@@ -691,7 +704,7 @@ class CramReader {
     m_out.resize(first + (size_t)n_records);
     std::vector<int32_t> next_frag((size_t)n_records, -1);
     std::vector<uint8_t> detached((size_t)n_records, 0);
-    int32_t last_ap = start;
+    int64_t last_ap = start;   // 64-bit: corrupt deltas must not overflow
     std::string scratch;
     for (int32_t i = 0; i < n_records; ++i) {
       CramRecord& r = m_out[first + (size_t)i];
@@ -700,7 +713,7 @@ class CramReader {
       int32_t ri = ref_id;
       if (ref_id == -2) ri = h.get("RI").get_int(sd);
       const int32_t rl = h.get("RL").get_int(sd);
-      int32_t ap = h.get("AP").get_int(sd);
+      int64_t ap = h.get("AP").get_int(sd);
       if (h.ap_delta) { ap += last_ap; last_ap = ap; }
       h.get("RG").get_int(sd);
       if (h.read_names) h.get("RN").get_bytes(sd, r.qname);
@@ -741,11 +754,11 @@ class CramReader {
         auto copy_ref_until = [&](int32_t upto) {  // read positions [rpos, upto) match the reference
           for (; rpos < upto && rpos < rl; ++rpos, ++gpos) r.seq[(size_t)rpos] = ref_base_at(gpos);
         };
-        int32_t fpos = 0;
+        int64_t fpos = 0;
         for (int32_t f = 0; f < fn; ++f) {
           const uint8_t code = h.get("FC").get_byte(sd);
           fpos += h.get("FP").get_int(sd);         // 1-based position in the read, delta coded
-          copy_ref_until(fpos - 1);
+          copy_ref_until((int32_t)std::min<int64_t>(std::max<int64_t>(fpos - 1, 0), rl));
           ++m_stats[std::string("feature ") + (char)code];
           switch (code) {
             case 'B': {                            // a base and its quality
