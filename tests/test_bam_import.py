@@ -1,4 +1,4 @@
-"""bgx-create's BAM importer (biograph_b200/cli/bgx_create.cpp: BamReader / import_bam), the reference's
+"""bgx-create's BAM importer (biograph_b200/cli/bgx_create.cpp: BamReader / import_alignments), the reference's
 read_importer_base::queue_bam + bam_process_line + bam1_to_unaligned_read
 (modules/build_seqset/read_importer.cpp:182-266,483-575; htslib there, BGZF through zlib here).  Runs through
 the --dump-reads test hook, which needs no GPU.
