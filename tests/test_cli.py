@@ -131,3 +131,16 @@ def test_create_paired_inputs(tmp_path, golden_reads):
     assert json.loads(zs[0][0].read("seqset.json")) == {"num_entries": 19935}
     rows = json.loads(zs[0][1].read("mate_loop_ptr/packed_varbit_vector.json"))["element_count"]
     assert rows == 16888
+
+
+def test_biograph_dispatcher(tmp_path):
+    """`biograph create ...` / `biograph merge ...` (modules/biograph/main.cpp) reach the two executables"""
+    exe = os.path.join(ROOT, "biograph_b200", "biograph")
+    r = subprocess.run([exe, "create", "--kmer-size", "99", "--reads", "x.fq", "--out", str(tmp_path / "o.bg")], capture_output=True, text=True)
+    assert r.returncode == 1 and "--kmer-size must specify an integer <= 32" in r.stderr
+    r = subprocess.run([exe, "merge", "--out", str(tmp_path / "m.bg")], capture_output=True, text=True)
+    assert r.returncode == 1 and "the option '--in' is required but missing" in r.stderr
+    r = subprocess.run([exe, "variants"], capture_output=True, text=True)
+    assert r.returncode == 1 and "not part of the B200 seqset path" in r.stderr
+    assert subprocess.run([exe, "help"], capture_output=True, text=True).returncode == 0
+
