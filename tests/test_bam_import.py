@@ -139,3 +139,37 @@ def test_refusals(tmp_path):
     p.write_bytes(raw[:len(raw) // 2])                            # truncated in the middle of a block
     with pytest.raises(RuntimeError, match="sam_read1 returned|not a valid BAM"):
         dump(p)
+
+
+def test_bam_input_reaches_the_gpu_stages_like_fastq_input(tmp_path):
+    """What goes to the device for a BAM is read for read, in order, what goes there for the same reads as FASTQ
+    (single file, and --pair): so the BioGraph bgx-create builds from a BAM is the one it builds from the FASTQ forms,
+    which tests/test_cli.py checks on the B200 against the reference's golden .bg (this check needs no GPU)."""
+    z = np.load(os.path.join(ROOT, "tests", "golden", "e_coli_10000snp.npz"))
+    reads = [bytes(r).decode() for r in z["reads"]]
+
+    def dump_any(args):
+        r = subprocess.run([EXE, "--dump-reads", "--out", "/nonexistent/x.bg"] + [str(a) for a in args], capture_output=True, text=True, timeout=120)
+        assert r.returncode == 0, r.stderr
+        return r.stdout.splitlines()
+    fq = lambda rs, tag: "".join(f"@{tag}{i}\n{r}\n+\n{'I' * len(r)}\n" for i, r in enumerate(rs))
+    # unpaired: every third record on the reverse strand (stored reverse-complemented), secondary alignments in between
+    recs = []
+    for i, r in enumerate(reads):
+        recs.append(bam_record(f"r{i}", rc(r), 0x10) if i % 3 == 0 else bam_record(f"r{i}", r, 0))
+        if i % 50 == 0:
+            recs.append(bam_record(f"r{i}", r[:20], 0x100))
+    write_bam(tmp_path / "g.bam", recs, block=60000)
+    (tmp_path / "g.fq").write_text(fq(reads, "r"))
+    assert dump_any(["--reads", tmp_path / "g.bam"]) == dump_any(["--reads", tmp_path / "g.fq"])
+    # paired: second mate first and on the reverse strand, supplementary pieces in between
+    a, b = reads[0::2], reads[1::2]
+    recs = []
+    for i, (x, y) in enumerate(zip(a, b)):
+        recs += [bam_record(f"q{i}", rc(y), 0x1 | 0x10 | 0x80), bam_record(f"q{i}", x, 0x1 | 0x40)]
+        if i % 97 == 0:
+            recs.append(bam_record(f"q{i}", x[:25], 0x1 | 0x800))
+    write_bam(tmp_path / "p.bam", recs, block=60000)
+    (tmp_path / "a.fq").write_text(fq(a, "p"))
+    (tmp_path / "b.fq").write_text(fq(b, "p"))
+    assert dump_any(["--reads", tmp_path / "p.bam"]) == dump_any(["--reads", tmp_path / "a.fq", "--pair", tmp_path / "b.fq"])
