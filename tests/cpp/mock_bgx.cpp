@@ -6,6 +6,7 @@
 //
 // Canned merge: N = 1000 merged entries; input p has a mergemap bit at x iff x % (p + 2) == 0; migrate_bits
 // returns bit x = old bit (x / 2) for even x; flat entries of input p are "ACGT" repeated (i % 5 + 1) times.
+#include <cstdio>
 #include <cstdlib>
 #include <cstring>
 #include <string>
@@ -77,9 +78,34 @@ int bgx_export_flat_ascii(bgx_ctx*, uint32_t, uint64_t first, uint64_t count, ch
   *offs = o;
   return 0;
 }
-// referenced by other facade classes that this test never reaches
-int bgx_add_reads_ascii(bgx_ctx*, const char*, const uint64_t*, uint64_t) { return 1; }
-int bgx_count_kmers(bgx_ctx*) { return 1; }
+// The import stage of bgx-create: every read handed to the device is appended to the file named by BGX_MOCK_LOG
+// ("A <bases>" through bgx_add_reads_ascii, "F <bases>" through the FASTQ text entry point), and the k-mer stage
+// stops the run ("mock: the import stage ended").
+static void log_read(char kind, const char* p, size_t n) {
+  const char* path = getenv("BGX_MOCK_LOG");
+  if (!path) return;
+  FILE* f = fopen(path, "a");
+  if (!f) return;
+  fprintf(f, "%c %.*s\n", kind, (int)n, p);
+  fclose(f);
+}
+int bgx_add_reads_ascii(bgx_ctx*, const char* bases, const uint64_t* offs, uint64_t n) {
+  for (uint64_t r = 0; r < n; ++r) log_read('A', bases + offs[r], (size_t)(offs[r + 1] - offs[r]));
+  return 0;
+}
+int bgx_add_reads_fastq(bgx_ctx*, const char* text, uint64_t size, uint64_t* n_reads) {
+  uint64_t line = 0, start = 0, n = 0;
+  for (uint64_t i = 0; i < size; ++i)
+    if (text[i] == '\n') {
+      if (line % 4 == 1) { log_read('F', text + start, (size_t)(i - start)); ++n; }
+      ++line;
+      start = i + 1;
+    }
+  *n_reads = n;
+  return 0;
+}
+int bgx_count_kmers(bgx_ctx*) { g_err = "mock: the import stage ended"; return 1; }
+int bgx_stats_json(bgx_ctx*, char* buf, size_t cap) { if (cap) buf[0] = 0; return 1; }
 int bgx_export_kmers(bgx_ctx*, uint32_t, uint64_t*, uint64_t**, uint32_t**, uint32_t**, uint8_t**) { return 1; }
 int bgx_export_reads(bgx_ctx*, uint64_t*, uint16_t**, char**, uint64_t*) { return 1; }
 int bgx_correct(bgx_ctx*) { return 1; }
