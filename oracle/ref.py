@@ -1,0 +1,195 @@
+"""ctypes binding of oracle/_ref/libref.so: the REFERENCE'S OWN classes for the hot path (kmer_counter, kmer_set,
+fast_read_correct, build_seqset::correct_reads, part_repo, expander, builder, seqset), compiled from the sources where
+they lie under /root/reference by `make -C oracle _ref` (see oracle/ref_shim.cpp for what is and is not the
+reference's).
+
+TEST INFRASTRUCTURE: only tests/, __graft_entry__.smoke() and bench.py's CPU arms may import this; the product
+(biograph_b200/, include/) never does.  The library is built in the development container (where /root/reference
+exists) and travels to the GPU box as a built file; `available()` says whether it is there.
+"""
+import ctypes as C
+import os
+import shutil
+import tempfile
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB = os.path.join(HERE, "_ref", "libref.so")
+_lib = None
+
+
+def available():
+    return os.path.exists(LIB)
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        L = C.CDLL(LIB)
+        L.ref_last_error.restype = C.c_char_p
+        L.ref_open.restype = C.c_void_p
+        L.ref_open.argtypes = [C.c_char_p, C.c_int, C.c_uint64]
+        L.ref_close.argtypes = [C.c_void_p]
+        L.ref_fast_read_correct.argtypes = [C.c_char_p, C.c_int, C.c_void_p, C.c_int64, C.c_int, C.c_int, C.c_int,
+                                            C.c_char_p, C.POINTER(C.c_int)]
+        L.ref_count_kmers.argtypes = [C.c_void_p, C.c_char_p, C.c_void_p, C.c_int64, C.c_int, C.c_int, C.c_uint64,
+                                      C.c_int]
+        L.ref_counts.restype = C.c_int64
+        L.ref_counts.argtypes = [C.c_void_p] + [C.POINTER(C.c_void_p)] * 4
+        L.ref_solid_size.restype = C.c_int64
+        L.ref_solid_size.argtypes = [C.c_void_p]
+        L.ref_solid.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
+        L.ref_correct.argtypes = [C.c_void_p, C.c_char_p, C.c_void_p, C.c_int64, C.c_int, C.c_int, C.c_double, C.c_int]
+        L.ref_corrected.restype = C.c_int64
+        L.ref_corrected.argtypes = [C.c_void_p] + [C.POINTER(C.c_void_p)] * 3
+        L.ref_seed.argtypes = [C.c_void_p, C.c_char_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_int]
+        L.ref_make_seqset.argtypes = [C.c_void_p]
+        L.ref_seqset_size.restype = C.c_int64
+        L.ref_seqset_size.argtypes = [C.c_void_p]
+        L.ref_seqset_tables.argtypes = [C.c_void_p] + [C.c_void_p] * 5
+        L.ref_members.restype = C.c_int64
+        L.ref_members.argtypes = [C.c_void_p]
+        L.ref_member_name.restype = C.c_char_p
+        L.ref_member_name.argtypes = [C.c_void_p, C.c_int64]
+        L.ref_member_data.restype = C.c_int64
+        L.ref_member_data.argtypes = [C.c_void_p, C.c_int64, C.POINTER(C.c_void_p)]
+        _lib = L
+    return _lib
+
+
+def _view(ptr, n, dtype):
+    n = int(n)
+    if n == 0:
+        return np.zeros(0, dtype=dtype)
+    return np.frombuffer((C.c_char * (n * np.dtype(dtype).itemsize)).from_address(ptr.value), dtype=dtype).copy()
+
+
+def _pack(reads):
+    if isinstance(reads, tuple):
+        buf, offs = reads
+        return (buf if isinstance(buf, bytes) else bytes(buf)), np.ascontiguousarray(offs, dtype=np.int64)
+    bs = [r.encode() if isinstance(r, str) else bytes(r) for r in reads]
+    offs = np.zeros(len(bs) + 1, dtype=np.int64)
+    if bs:
+        np.cumsum([len(b) for b in bs], out=offs[1:])
+    return b"".join(bs), offs
+
+
+def fast_read_correct(read, solid_kmers, k, max_corrections=2, min_good_run=2):
+    """modules/bio_base/fast_read_correct.cpp:94-182 itself; same signature as oracle.fast_read_correct."""
+    solid = np.ascontiguousarray(np.sort(np.asarray(solid_kmers, dtype=np.uint64)))
+    rb = read.encode() if isinstance(read, str) else read
+    out = C.create_string_buffer(max(1, len(rb)))
+    corr = C.c_int(0)
+    n = lib().ref_fast_read_correct(rb, len(rb), solid.ctypes.data, len(solid), k, max_corrections, min_good_run, out,
+                                    C.byref(corr))
+    if n < 0:
+        raise RuntimeError(lib().ref_last_error().decode())
+    return out.raw[:n].decode(), corr.value
+
+
+class Run:
+    """One pass of the reference's create flow; the stages can be called one by one."""
+
+    def __init__(self, threads=0, max_mem_bytes=0, tmp_dir=None):
+        self.tmp = tempfile.mkdtemp(prefix="bgx_ref_", dir=tmp_dir)
+        self.h = lib().ref_open(self.tmp.encode(), threads or (os.cpu_count() or 1), max_mem_bytes)
+
+    def close(self):
+        if self.h:
+            lib().ref_close(self.h)
+            self.h = None
+        shutil.rmtree(self.tmp, ignore_errors=True)
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+    def _ck(self, rc):
+        if rc:
+            raise RuntimeError("reference: " + lib().ref_last_error().decode())
+
+    def count_kmers(self, reads, k=30, min_count=5, counter_max_memory_bytes=0, force_exact_passes=0):
+        """kmer_counter's two-stage count, then the solid kmer_set.  Returns (counts, solid): counts = every element
+        extract_exact_counts yields, sorted by k-mer (k-mers the probabilistic pass filtered may be absent); solid =
+        the kmer_set (ascending) with flag bits (bit0 fwd_starts_read, bit1 rev_starts_read)."""
+        buf, offs = _pack(reads)
+        self._ck(lib().ref_count_kmers(self.h, buf, offs.ctypes.data, len(offs) - 1, k, min_count,
+                                       counter_max_memory_bytes, force_exact_passes))
+        p = [C.c_void_p() for _ in range(4)]
+        n = lib().ref_counts(self.h, *[C.byref(x) for x in p])
+        kmers, fwd, rev, flags = (_view(p[0], n, np.uint64), _view(p[1], n, np.uint32), _view(p[2], n, np.uint32),
+                                  _view(p[3], n, np.uint8))
+        o = np.argsort(kmers, kind="stable")
+        counts = {"kmers": kmers[o], "fwd": fwd[o], "rev": rev[o], "flags": flags[o]}
+        ns = lib().ref_solid_size(self.h)
+        sk = np.zeros(ns, dtype=np.uint64)
+        sf = np.zeros(ns, dtype=np.uint8)
+        self._ck(lib().ref_solid(self.h, sk.ctypes.data, sf.ctypes.data))
+        return counts, {"kmers": sk, "flags": sf}
+
+    def correct(self, reads, max_corrections=8, min_good_run=2, trim_after_portion=0.7, partition_depth=0):
+        """build_seqset::correct_reads::correct over every read (seeds go to the part_repo).  Returns
+        dict(seq, offs, kept) like oracle.correct_reads."""
+        buf, offs = _pack(reads)
+        self._ck(lib().ref_correct(self.h, buf, offs.ctypes.data, len(offs) - 1, max_corrections, min_good_run,
+                                   trim_after_portion, partition_depth))
+        p = [C.c_void_p() for _ in range(3)]
+        n = lib().ref_corrected(self.h, *[C.byref(x) for x in p])
+        o = _view(p[1], n + 1, np.int64)
+        return {"seq": _view(p[0], o[n], np.uint8).tobytes(), "offs": o, "kept": _view(p[2], n, np.uint8)}
+
+    def seed(self, reads, next_fwd=None, next_rev=None, partition_depth=2):
+        buf, offs = _pack(reads)
+        nf = None if next_fwd is None else np.ascontiguousarray(next_fwd, dtype=np.int32)
+        nr = None if next_rev is None else np.ascontiguousarray(next_rev, dtype=np.int32)
+        self._ck(lib().ref_seed(self.h, buf, offs.ctypes.data, len(offs) - 1, None if nf is None else nf.ctypes.data,
+                                None if nr is None else nr.ctypes.data, partition_depth))
+
+    def make_seqset(self):
+        """expander x 4 + builder (SEQSETMain::make_seqset).  Same dict as oracle.seqset_staged."""
+        self._ck(lib().ref_make_seqset(self.h))
+        n = lib().ref_seqset_size(self.h)
+        words = (n + 63) // 64
+        sizes = np.zeros(n, dtype=np.uint16)
+        shared = np.zeros(n, dtype=np.uint16)
+        prev = np.zeros((4, words), dtype=np.uint64)
+        fixed = np.zeros(5, dtype=np.uint64)
+        stats = np.zeros(6, dtype=np.int64)
+        self._ck(lib().ref_seqset_tables(self.h, sizes.ctypes.data, shared.ctypes.data, prev.ctypes.data,
+                                         fixed.ctypes.data, stats.ctypes.data))
+        return {"n": int(n), "sizes": sizes, "shared": shared, "prev": prev, "fixed": fixed, "stats": stats}
+
+    def members(self):
+        """{member path: bytes} of the in-memory seqset spiral file, as the reference's encoders wrote them."""
+        n = lib().ref_members(self.h)
+        if n < 0:
+            raise RuntimeError("reference: " + lib().ref_last_error().decode())
+        out = {}
+        for i in range(n):
+            p = C.c_void_p()
+            sz = lib().ref_member_data(self.h, i, C.byref(p))
+            out[lib().ref_member_name(self.h, i).decode()] = _view(p, sz, np.uint8).tobytes()
+        return out
+
+
+def seqset_for_reads(reads, next_fwd=None, next_rev=None, threads=0, partition_depth=2):
+    with Run(threads) as r:
+        r.seed(reads, next_fwd, next_rev, partition_depth)
+        return r.make_seqset()
+
+
+def create(reads, k=30, min_count=5, max_corrections=8, min_good_run=2, trim_after_portion=0.7, threads=0,
+           with_members=False):
+    """The whole path on the reference's classes: reads -> (counts, solid, corrected, seqset[, members])."""
+    with Run(threads) as r:
+        counts, solid = r.count_kmers(reads, k, min_count)
+        cr = r.correct(reads, max_corrections, min_good_run, trim_after_portion)
+        ss = r.make_seqset()
+        out = {"counts": counts, "solid": solid, "corrected": cr, "seqset": ss}
+        if with_members:
+            out["members"] = r.members()
+        return out

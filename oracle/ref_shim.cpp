@@ -1,0 +1,401 @@
+// ref_shim.cpp -- C entry points over the REFERENCE'S OWN classes for the hot path, compiled from the sources where
+// they lie under /root/reference (oracle/Makefile, target `_ref`; outputs only under oracle/_ref/).
+//
+// TEST INFRASTRUCTURE.  Nothing under biograph_b200/ or include/ may load this.  It exists to check the CPU
+// restatement (oracle/oracle.cpp) and the CUDA path against what the reference itself computes, and as the
+// `cpu_baseline.kind = "reference"` arm of bench.py.
+//
+// What is the reference's and what is not: every class used below (kmer_counter, kmer_set, correct_reads,
+// fast_read_correct, part_repo, expander, builder, seqset, bitcount, packed_varbit_vector, spiral_file_create_mem)
+// is compiled unmodified from /root/reference/modules/**.  The reference's Bazel build and its third-party
+// libraries (Boost, glog, json_spirit, msgpack, htslib) are absent from this image; oracle/ref_stubs/ holds minimal
+// stand-ins for the few headers of those that the leaf sources include.  The code in THIS file only restates the
+// driver sequence of SEQSETMain::run (modules/biograph/biograph_create.cpp:665-779, 835-950) and of kmerizer::run
+// (modules/bio_mapred/kmerize_bf.cpp:267-430) -- the parts of them that call the classes above -- because those two
+// functions themselves read the map-reduce temp files (manifests, msgpack kv streams) that are out of scope.
+//   * import: every read is handed to prob_pass_processor::add as read_importer_state::process does
+//     (modules/biograph/biograph_create.cpp:119-151); reads are kept in memory instead of the msgpack temp files.
+//   * k-mer filter: tot_count >= min_count and the strand-skew cut of kmer_passes with the defaults of
+//     kmerize_bf_params (modules/bio_mapred/kmerize_bf.cpp:290-318); the overrepresentation filter is off
+//     (overrep threshold 0 disables it there too).
+//   * the reference genome as a compression dictionary (add_initial_repo) is not used: result-invisible.
+#include <atomic>
+#include <cstdint>
+#include <cstring>
+#include <map>
+#include <memory>
+#include <mutex>
+#include <string>
+#include <thread>
+#include <vector>
+
+#include "modules/bio_base/fast_read_correct.h"
+#include "modules/bio_base/seqset.h"
+#include "modules/bio_mapred/kmer_set.h"
+#include "modules/build_seqset/builder.h"
+#include "modules/build_seqset/correct_reads.h"
+#include "modules/build_seqset/expand.h"
+#include "modules/build_seqset/kmer_counter.h"
+#include "modules/build_seqset/part_repo.h"
+#include "modules/io/config.h"
+#include "modules/io/parallel.h"
+#include "modules/io/spiral_file_mem.h"
+#include "modules/io/track_mem.h"
+
+namespace {
+
+thread_local std::string g_err;
+
+struct reads_view {
+  const char* bases;
+  const int64_t* offs;
+  int64_t n;
+  string_view operator[](int64_t i) const { return string_view(bases + offs[i], size_t(offs[i + 1] - offs[i])); }
+};
+
+// run f(first, last) over chunks of [0, n) on the reference's own thread pool (modules/io/parallel.h): part_repo's
+// writers and the k-mer pass processors rely on its per-thread state.
+template <class F>
+void blocks(int64_t n, int /*threads*/, const F& f) {
+  if (n <= 0) return;
+  parallel_for(0, size_t(n), [&](size_t a, size_t b) { f(int64_t(a), int64_t(b)); });
+}
+
+struct ref_run {
+  std::string tmp;
+  int threads = 1;
+  unsigned k = 30;
+  // count stage
+  std::vector<uint64_t> c_kmer;
+  std::vector<uint32_t> c_fwd, c_rev;
+  std::vector<uint8_t> c_flags;
+  std::unique_ptr<kmer_set> ks;
+  // correct stage
+  std::unique_ptr<build_seqset::part_repo> entries;
+  std::unique_ptr<build_seqset::part_counts> part_counts;
+  std::string cr_seq;
+  std::vector<int64_t> cr_offs;
+  std::vector<uint8_t> cr_kept;
+  // seqset stage
+  std::unique_ptr<spiral_file_create_mem> create;
+  std::unique_ptr<seqset> ss;
+  int64_t stats[6] = {0, 0, 0, 0, 0, 0};
+  spiral_file_mem_storage storage;
+  std::vector<std::string> member_names;
+};
+
+template <class F>
+int guarded(const F& f) {
+  try {
+    f();
+    return 0;
+  } catch (const std::exception& e) {
+    g_err = e.what();
+  } catch (...) {
+    g_err = "unknown exception";
+  }
+  return 1;
+}
+
+}  // namespace
+
+extern "C" {
+
+const char* ref_last_error() { return g_err.c_str(); }
+
+// tmp_dir must exist; the reference keeps its partition / repository files there.
+void* ref_open(const char* tmp_dir, int threads, uint64_t max_mem_bytes) {
+  auto* r = new ref_run;
+  r->tmp = tmp_dir;
+  r->threads = threads < 1 ? 1 : threads;
+  Config::set("temp_root", r->tmp);
+  Config::set("resources_root", r->tmp);
+  Config::set("path_bulkdata", r->tmp);
+  set_thread_count(std::to_string(r->threads));
+  if (max_mem_bytes) set_maximum_mem_bytes(max_mem_bytes);
+  return r;
+}
+
+void ref_close(void* h) { delete static_cast<ref_run*>(h); }
+
+// fast_read_correct on one read against an explicit list of canonical solid k-mers (ascending).
+// out must hold len bytes; returns the corrected length, *corrections = substitutions made.
+int ref_fast_read_correct(const char* read, int len, const uint64_t* solid, int64_t n_solid, int k,
+                          int max_corrections, int min_good_run, char* out, int* corrections) {
+  int n_out = -1;
+  guarded([&] {
+    frc_params params;
+    params.max_corrections = max_corrections;
+    params.min_good_run = min_good_run;
+    params.kmer_size = k;
+    params.kmer_lookup_f = [&](kmer_t kmer, frc_kmer* ki) -> bool {
+      kmer_t canon = canonicalize(kmer, k, ki->flipped);
+      const uint64_t* e = solid + n_solid;
+      const uint64_t* it = std::lower_bound(solid, e, uint64_t(canon));
+      if (it == e || *it != canon) return false;
+      ki->index = it - solid;
+      return true;
+    };
+    frc_output res = fast_read_correct(string_view(read, size_t(len)), params);
+    std::string s = res.corrected.as_string();
+    memcpy(out, s.data(), s.size());
+    if (corrections) *corrections = int(res.corrections);
+    n_out = int(s.size());
+  });
+  return n_out;
+}
+
+// Stage 1: kmer_counter (probabilistic pass, exact passes), then the solid kmer_set.
+// max_memory_bytes / partitions = 0: count_kmer_options defaults.  Returns 0 on success.
+int ref_count_kmers(void* h, const char* bases, const int64_t* offs, int64_t n, int k, int min_count,
+                    uint64_t counter_max_memory_bytes, int force_exact_passes) {
+  auto* r = static_cast<ref_run*>(h);
+  return guarded([&] {
+    reads_view rv{bases, offs, n};
+    r->k = k;
+    build_seqset::count_kmer_options opts;
+    opts.kmer_size = k;
+    opts.min_count = min_count;
+    if (counter_max_memory_bytes) opts.max_memory_bytes = counter_max_memory_bytes;
+    opts.force_exact_passes = force_exact_passes;
+    // biograph_create.cpp:549-551 bounds the probabilistic table by 100 x the reference genome's size; without a
+    // genome here the bound is 100 x the bases read, which only ever makes the table larger (fewer false positives
+    // of a filter whose false positives never reach the result).
+    opts.max_prob_table_entries = std::max<size_t>(size_t(offs[n]) * 100, 1024 * 1024);
+    build_seqset::kmer_counter counter(opts);
+    counter.start_prob_pass();
+    blocks(n, r->threads, [&](int64_t a, int64_t b) {
+      build_seqset::kmer_counter::prob_pass_processor p(counter);
+      for (int64_t i = a; i < b; ++i) p.add(rv[i]);
+    });
+    counter.close_prob_pass();
+    for (unsigned pass = 0; pass < counter.exact_passes(); ++pass) {
+      counter.start_exact_pass(pass);
+      blocks(n, r->threads, [&](int64_t a, int64_t b) {
+        build_seqset::kmer_counter::exact_pass_processor p(counter);
+        for (int64_t i = a; i < b; ++i) p.add(rv[i]);
+      });
+    }
+    counter.close_exact_passes();
+
+    // defaults of kmerize_bf_params (modules/bio_mapred/kmerize_bf.h:37-38); the create flow never changes them
+    struct { size_t prior_count = 5; float skew_cutoff = 0.0f; } kbf;
+    auto passes = [&](const build_seqset::kmer_counter::element& e) {
+      size_t tot = size_t(e.fwd_count) + e.rev_count;
+      if (tot < size_t(min_count)) return false;
+      int32_t mn = std::min(e.fwd_count, e.rev_count);
+      float low = float(mn + kbf.prior_count) / float(tot + 2 * kbf.prior_count);
+      return !(low < kbf.skew_cutoff);
+    };
+
+    std::mutex mu;
+    size_t approx = 0;
+    r->c_kmer.clear(); r->c_fwd.clear(); r->c_rev.clear(); r->c_flags.clear();
+    counter.extract_exact_counts([&](build_seqset::kmer_counter::extract_iterator s,
+                                     build_seqset::kmer_counter::extract_iterator e) {
+      std::vector<build_seqset::kmer_counter::element> local;
+      for (auto it = s; it != e; ++it) local.push_back(*it);
+      std::lock_guard<std::mutex> l(mu);
+      approx += local.size();
+      for (const auto& el : local) {
+        r->c_kmer.push_back(el.kmer);
+        r->c_fwd.push_back(el.fwd_count);
+        r->c_rev.push_back(el.rev_count);
+        r->c_flags.push_back(uint8_t((el.fwd_starts_read ? 1 : 0) | (el.rev_starts_read ? 2 : 0)));
+      }
+    });
+    size_t mem_gb = std::max<size_t>(1, get_maximum_mem_bytes() / 1024 / 1024 / 1024);
+    r->ks = make_unique<kmer_set>(
+        approx, k, mem_gb,
+        [&](const kmer_set::kmer_output_f& output_f, progress_handler_t) {
+          counter.extract_exact_counts([&](build_seqset::kmer_counter::extract_iterator s,
+                                           build_seqset::kmer_counter::extract_iterator e) {
+            for (auto it = s; it != e; ++it) {
+              auto el = *it;
+              if (!passes(el)) continue;
+              unsigned flags = 0;
+              if (el.fwd_starts_read) flags |= kmer_set::k_fwd_starts_read;
+              if (el.rev_starts_read) flags |= kmer_set::k_rev_starts_read;
+              output_f(el.kmer, flags);
+            }
+          });
+        },
+        null_progress_handler);
+    counter.close();
+  });
+}
+
+// every element extract_exact_counts yielded (unordered; k-mers below the probabilistic threshold may be absent)
+int64_t ref_counts(void* h, const uint64_t** kmers, const uint32_t** fwd, const uint32_t** rev, const uint8_t** flags) {
+  auto* r = static_cast<ref_run*>(h);
+  *kmers = r->c_kmer.data(); *fwd = r->c_fwd.data(); *rev = r->c_rev.data(); *flags = r->c_flags.data();
+  return int64_t(r->c_kmer.size());
+}
+
+// the solid set in kmer_set order (ascending), flags bit0 = fwd_starts_read, bit1 = rev_starts_read
+int64_t ref_solid_size(void* h) {
+  auto* r = static_cast<ref_run*>(h);
+  return r->ks ? int64_t(r->ks->size()) : -1;
+}
+int ref_solid(void* h, uint64_t* kmers, uint8_t* flags) {
+  auto* r = static_cast<ref_run*>(h);
+  return guarded([&] {
+    size_t i = 0;
+    for (auto it = r->ks->begin(); it != r->ks->end(); ++it, ++i) {
+      kmers[i] = *it;
+      unsigned f = r->ks->get_flags(i);
+      flags[i] = uint8_t(((f & kmer_set::k_fwd_starts_read) ? 1 : 0) | ((f & kmer_set::k_rev_starts_read) ? 2 : 0));
+    }
+  });
+}
+
+// Stage 2: build_seqset::correct_reads over every read; seeds go into the part_repo's "initial" pass.
+int ref_correct(void* h, const char* bases, const int64_t* offs, int64_t n, int max_corrections, int min_good_run,
+                double trim_after_portion, int partition_depth) {
+  auto* r = static_cast<ref_run*>(h);
+  return guarded([&] {
+    if (!r->ks) throw io_exception("ref_correct: no kmer_set (run ref_count_kmers first)");
+    reads_view rv{bases, offs, n};
+    if (partition_depth <= 0) {  // biograph_create.cpp:716-722
+      partition_depth = n < 10 * 1000 * 1000 ? 2 : n < 100 * 1000 * 1000 ? 3 : 4;
+    }
+    r->entries = make_unique<build_seqset::part_repo>(partition_depth, r->tmp + "/seq_ref-", r->tmp + "/seq_repo");
+    read_correction_params rcp;  // biograph_create.cpp:727-733
+    rcp.min_kmer_score = 0;
+    rcp.skip_snps = false;
+    rcp.exact = (max_corrections == 0);
+    // the CLI value is a float (biograph_create.cpp:489-490) widened into the params' double: 0.7f * 150 = 104.99..,
+    // where 0.7 * 150 would be 105
+    rcp.trim_after_portion = float(trim_after_portion);
+    rcp.frc_max_corrections = max_corrections;
+    rcp.frc_min_good_run = min_good_run;
+    build_seqset::correct_reads cr(*r->entries, *r->ks, rcp);
+    r->entries->open_write_pass("initial");
+    std::vector<std::string> out{size_t(n), std::string()};
+    r->cr_kept.assign(size_t(n), 0);
+    blocks(n, r->threads, [&](int64_t a, int64_t b) {
+      for (int64_t i = a; i < b; ++i) {
+        unaligned_read ur;
+        ur.sequence = std::string(rv[i]);
+        corrected_read c;
+        if (cr.correct(ur, c)) {
+          out[size_t(i)] = c.corrected.as_string();
+          r->cr_kept[size_t(i)] = 1;
+        }
+      }
+    });
+    r->entries->flush();
+    r->part_counts = r->entries->release_part_counts("initial");
+    r->cr_offs.assign(size_t(n) + 1, 0);
+    r->cr_seq.clear();
+    for (int64_t i = 0; i < n; ++i) {
+      r->cr_seq += out[size_t(i)];
+      r->cr_offs[size_t(i) + 1] = int64_t(r->cr_seq.size());
+    }
+  });
+}
+
+int64_t ref_corrected(void* h, const char** seq, const int64_t** offs, const uint8_t** kept) {
+  auto* r = static_cast<ref_run*>(h);
+  *seq = r->cr_seq.data(); *offs = r->cr_offs.data(); *kept = r->cr_kept.data();
+  return int64_t(r->cr_kept.size());
+}
+
+// Instead of stage 2: seed the part_repo from given sequences with explicit seed counts, as the reference's own
+// seqset_for_reads test helper does (modules/bio_base/seqset_testutil.cpp:24-32) -- nf / nr null: 1 and 1.
+int ref_seed(void* h, const char* bases, const int64_t* offs, int64_t n, const int32_t* nf, const int32_t* nr,
+             int partition_depth) {
+  auto* r = static_cast<ref_run*>(h);
+  return guarded([&] {
+    reads_view rv{bases, offs, n};
+    r->entries = make_unique<build_seqset::part_repo>(partition_depth > 0 ? partition_depth : 2, r->tmp + "/seq_ref-",
+                                                      r->tmp + "/seq_repo");
+    r->entries->open_write_pass("initial");
+    blocks(n, r->threads, [&](int64_t a, int64_t b) {
+      for (int64_t i = a; i < b; ++i) {
+        dna_sequence s{std::string(rv[i])};
+        r->entries->write(s, nf ? unsigned(nf[i]) : 1, nr ? unsigned(nr[i]) : 1);
+      }
+    });
+    r->entries->flush();
+    r->part_counts = r->entries->release_part_counts("initial");
+  });
+}
+
+// Stage 3: SEQSETMain::make_seqset (biograph_create.cpp:914-950): the four expander calls with the production
+// strides, build_chunks, make_seqset into an in-memory spiral file.
+int ref_make_seqset(void* h) {
+  auto* r = static_cast<ref_run*>(h);
+  return guarded([&] {
+    if (!r->entries) throw io_exception("ref_make_seqset: no entries (run ref_correct or ref_seed first)");
+    auto& entries = *r->entries;
+    entries.flush();
+    if (r->part_counts) entries.reset_part_counts("initial", std::move(r->part_counts));
+    {
+      build_seqset::expander expand(entries, false);
+      r->stats[0] = 0;
+      r->stats[1] = int64_t(expand.sort_and_dedup("", "initial", "init_sorted", "", 0, 0));
+      r->stats[2] = int64_t(expand.expand("init_sorted", "init_expanded", 7, 255));
+      r->stats[3] = int64_t(expand.sort_and_dedup("init_sorted", "init_expanded", "pass2_sorted", "pass2_expanded", 1, 6));
+      r->stats[4] = 0;
+      r->stats[5] = int64_t(expand.sort_and_dedup("pass2_sorted", "pass2_expanded", "complete", "", 0, 0));
+    }
+    build_seqset::builder b;
+    b.build_chunks(entries, "complete", false);
+    entries.partitions("complete", false, true);
+    r->entries.reset();
+    r->create = make_unique<spiral_file_create_mem>();
+    r->ss = b.make_seqset(r->create->create());
+  });
+}
+
+int64_t ref_seqset_size(void* h) {
+  auto* r = static_cast<ref_run*>(h);
+  return r->ss ? int64_t(r->ss->size()) : -1;
+}
+
+// sizes / shared: uint16[n]; prev: 4 x ceil(n/64) uint64 words (bit i of row b = entry i has base b in front);
+// fixed: uint64[5]; stats: int64[6] (what the expander calls returned, see ref_make_seqset)
+int ref_seqset_tables(void* h, uint16_t* sizes, uint16_t* shared, uint64_t* prev, uint64_t* fixed, int64_t* stats) {
+  auto* r = static_cast<ref_run*>(h);
+  return guarded([&] {
+    const seqset& ss = *r->ss;
+    size_t n = ss.size(), words = (n + 63) / 64;
+    memset(prev, 0, 4 * words * sizeof(uint64_t));
+    for (size_t i = 0; i < n; ++i) {
+      sizes[i] = uint16_t(ss.entry_size(i));
+      shared[i] = uint16_t(ss.entry_shared(i));
+      for (dna_base b : dna_bases())
+        if (ss.entry_has_front(i, b)) prev[size_t(int(b)) * words + i / 64] |= 1ULL << (i % 64);
+    }
+    for (int b = 0; b < 4; ++b) fixed[b] = ss.entry_push_front(0, dna_base(b));  // get_fixed(b) + count(0) = fixed[b]
+    fixed[4] = n;
+    if (stats) memcpy(stats, r->stats, sizeof(r->stats));
+  });
+}
+
+// the members of the in-memory spiral file exactly as the reference's encoders wrote them (closes the file)
+int64_t ref_members(void* h) {
+  auto* r = static_cast<ref_run*>(h);
+  int64_t n = -1;
+  guarded([&] {
+    if (r->create) {
+      r->ss.reset();
+      r->storage = r->create->close();
+      r->create.reset();
+      r->member_names.clear();
+      for (auto& kv : r->storage.paths) r->member_names.push_back(kv.first);
+    }
+    n = int64_t(r->member_names.size());
+  });
+  return n;
+}
+const char* ref_member_name(void* h, int64_t i) { return static_cast<ref_run*>(h)->member_names[size_t(i)].c_str(); }
+int64_t ref_member_data(void* h, int64_t i, const char** data) {
+  auto* r = static_cast<ref_run*>(h);
+  auto& mb = r->storage.paths[r->member_names[size_t(i)]];
+  *data = mb.data();
+  return int64_t(mb.size());
+}
+
+}  // extern "C"
