@@ -158,6 +158,76 @@ def cpu_port_run(reads2d, threads, k=30, keep=False):
     return dt, ss["n"]
 
 
+def cpu_ref_run(reads2d, threads, coverage, k=30, keep=False):
+    """The REFERENCE'S OWN classes (oracle/_ref/libref.so, compiled from /root/reference: kmer_counter -> kmer_set ->
+    build_seqset::correct_reads -> expander x 4 -> builder -> seqset; oracle/ref_shim.cpp) on a read set, with the
+    create flow's defaults (k 30, min count 5, 8 corrections, good run 2, trim 0.7).  Returns (seconds, entries,
+    stage seconds[, results])."""
+    from oracle import ref as R
+    from biograph_b200 import synth
+    buf, offs = synth.as_buffer(reads2d)
+    rb = (buf.tobytes(), offs)
+    del buf
+    t0 = time.perf_counter()
+    with R.Run(threads) as r:
+        counts, solid = r.count_kmers(rb, k, 5, genome_bases=max(1, int(reads2d.size // max(1, coverage))))
+        t1 = time.perf_counter()
+        cr = r.correct(rb, 8, 2, 0.7)
+        t2 = time.perf_counter()
+        ss = r.make_seqset()
+        t3 = time.perf_counter()
+    st = {"count_s": round(t1 - t0, 2), "correct_s": round(t2 - t1, 2), "seqset_s": round(t3 - t2, 2)}
+    if keep:
+        return t3 - t0, ss["n"], st, {"counts": counts, "solid": solid, "corrected": cr, "seqset": ss}
+    return t3 - t0, ss["n"], st
+
+
+def reference_available():
+    try:
+        from oracle import ref as R
+        return R.available()
+    except Exception:
+        return False
+
+
+def verify_sample_against_reference(B, device, sub, ref):
+    """A GPU build of the CPU sample against what the reference's own code computed for it: solid k-mers with their
+    counts, surviving corrected reads, every seqset table.  Never raises: a failure is reported in the line."""
+    try:
+        from biograph_b200 import synth
+        buf, offs = synth.as_buffer(sub)
+        mism = []
+        with B.Bgx(device=device) as g2:
+            g2.add_reads((buf, offs))
+            g2.run()
+            gs = g2.export_kmers(5)
+            cr = g2.export_corrected()
+            ss = g2.export_seqset()
+        c = ref["counts"]
+        m = (c["fwd"].astype(np.int64) + c["rev"]) >= 5
+        if not np.array_equal(ref["solid"]["kmers"], gs["kmers"]):
+            mism.append("solid_kmers/kmers")
+        for f in ("kmers", "fwd", "rev", "flags"):
+            if not np.array_equal(c[f][m], gs[f]):
+                mism.append("counts/" + f)
+        rcr = ref["corrected"]
+        if rcr["seq"] != cr["seq"]:
+            mism.append("corrected/bases")
+        for f in ("offs", "kept"):
+            if not np.array_equal(rcr[f], cr[f]):
+                mism.append("corrected/" + f)
+        rss = ref["seqset"]
+        if rss["n"] != ss["n"]:
+            mism.append("seqset/num_entries")
+        for t in ("sizes", "shared", "prev", "fixed"):
+            if not np.array_equal(rss[t], ss[t]):
+                mism.append("seqset/" + t)
+        return {"checked": True, "against": "oracle/_ref (the reference's own classes), the cpu_baseline sample",
+                "reads": int(sub.shape[0]), "entries": int(ss["n"]), "members_equal": not mism, "mismatches": mism}
+    except Exception as e:  # noqa: BLE001
+        return {"checked": False, "error": f"{type(e).__name__}: {e}"[:300]}
+
+
 def sha(a):
     import hashlib
     a = np.ascontiguousarray(a)
@@ -220,8 +290,11 @@ def verify_against_oracle(g, reads, threads):
 
 
 def run_reference(args):
-    """--impl reference: the reference's CPU path cannot be built offline (Bazel + Boost),
-    so this arm times the oracle port -- the restated CPU path -- with all host threads."""
+    """--impl reference: the reference's own CPU implementation of the path on the host cores.  Where
+    oracle/_ref/libref.so exists (the reference's classes compiled from its sources, oracle/Makefile) that is what
+    runs ("kind": "reference"); the reference's Bazel build as a whole is not possible offline, so
+    without the library the restated port runs instead ("kind": "port").  All host threads; each step a bounded
+    sample of the workload sized so that the whole --steps/--warmup run ends within a few minutes."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
@@ -230,28 +303,39 @@ def run_reference(args):
     threads = host_threads()
     w = WORKLOADS[args.workload]
     total = args.reads or -(-w["coverage"] * (4938920 if w["genome"] == "ecoli" else w["genome"][1]) // w["read_len"])
+    use_ref = reference_available()
+    sample_reads = args.cpu_sample_reads
+    if use_ref:  # ~3 Mbases/s on 16 threads: keep (warmup + steps) x sample near four minutes
+        sample_reads = min(sample_reads, max(50000, int(args.cpu_sample_reads * 8 / max(1, args.warmup + args.steps))))
     # bounded sample: the workload's read model at the workload's coverage over a genome prefix
-    sub = make_workload(args.workload, 0, None, genome_prefix_reads=min(total, args.cpu_sample_reads))
+    sub = make_workload(args.workload, 0, None, genome_prefix_reads=min(total, sample_reads))
     sample = sub.shape[0]
     reads = sub
     times = []
+    stage = None
     for i in range(args.warmup + args.steps):
-        dt, n_ent = cpu_port_run(sub, threads)
+        if use_ref:
+            dt, n_ent, stage = cpu_ref_run(sub, threads, w["coverage"])
+        else:
+            dt, n_ent = cpu_port_run(sub, threads)
         if i >= args.warmup:
             times.append(dt)
     bases = sub.size
     ms = 1e3 * float(np.mean(times))
     val = bases / (ms / 1e3)
+    what = ("oracle/_ref: the reference's own classes compiled from its sources (kmer_counter, kmer_set, correct_reads, "
+            "expander, builder, seqset; driver sequence restated in oracle/ref_shim.cpp)" if use_ref else
+            "oracle port (oracle/_ref not built)")
     line = {"impl": "reference", "metric": "input bases/sec to finished seqset", "value": val, "unit": "bases/s",
             "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u64", "data": "synthetic",
             "config": {"workload": args.workload, "reads_per_gpu": int(total), "read_len": int(reads.shape[1]),
                        "bases_per_gpu": int(total) * int(reads.shape[1]), "kmer_size": 30,
                        "parallelism": f"{threads} host threads (CPU path; no GPU)"},
-            "cpu_baseline": {"value": val, "unit": "bases/s", "cores": threads, "kind": "port",
+            "cpu_baseline": {"value": val, "unit": "bases/s", "cores": threads, "kind": "reference" if use_ref else "port",
                              "sample": f"{sample} reads at the workload's coverage over a genome prefix "
-                                       f"(workload has {total}), whole path (2-stage count+correct+staged seqset), "
-                                       "oracle port (reference binary not buildable offline)"},
+                                       f"(workload has {total}), whole path (2-stage count + correct + expand/sort/dedup "
+                                       f"+ build), {what}", "entries": int(n_ent), "stage_s": stage},
             "e2e": {"value": val, "unit": "bases/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line))
 
@@ -506,6 +590,23 @@ def main():
                "sample": f"the whole workload ({n_reads} reads) once, whole path (2-stage count + correct + staged "
                          f"seqset), {dt:.1f} s; oracle port (reference binary not buildable offline); this run is "
                          "also the parity check"}
+        if reference_available() and not args.no_cpu_baseline:
+            # the reference's own code on a bounded sample: the CPU baseline proper, and a second parity anchor
+            try:
+                cov = WORKLOADS[args.workload]["coverage"]
+                sub = make_workload(args.workload, 0, None, genome_prefix_reads=min(n_reads, args.cpu_sample_reads))
+                rdt, r_ent, rstage, rres = cpu_ref_run(sub, threads, cov, keep=True)
+                cpu = {"value": sub.size / rdt, "unit": "bases/s", "cores": threads, "kind": "reference",
+                       "same_config": False, "entries": int(r_ent), "stage_s": rstage,
+                       "sample": f"{sub.shape[0]} reads at the workload's coverage over a genome prefix (workload has "
+                                 f"{n_reads}), whole path once, {rdt:.1f} s; oracle/_ref = the reference's own classes "
+                                 "compiled from its sources (oracle/ref_shim.cpp says what is and is not the reference's)",
+                       "oracle_port_whole_workload": {"value": n_reads * read_len / dt, "unit": "bases/s",
+                                                      "seconds": round(dt, 1)}}
+                parity["reference_sample"] = verify_sample_against_reference(B, local, sub, rres)
+                del rres
+            except Exception as e:  # noqa: BLE001
+                parity["reference_sample"] = {"checked": False, "error": f"{type(e).__name__}: {e}"[:300]}
     elif world == 1 and not args.no_cpu_baseline:
         threads = host_threads()
         sub = make_workload(args.workload, 0, None, genome_prefix_reads=min(n_reads, args.cpu_sample_reads))

@@ -34,7 +34,7 @@ def lib():
         L.ref_fast_read_correct.argtypes = [C.c_char_p, C.c_int, C.c_void_p, C.c_int64, C.c_int, C.c_int, C.c_int,
                                             C.c_char_p, C.POINTER(C.c_int)]
         L.ref_count_kmers.argtypes = [C.c_void_p, C.c_char_p, C.c_void_p, C.c_int64, C.c_int, C.c_int, C.c_uint64,
-                                      C.c_int]
+                                      C.c_int, C.c_uint64]
         L.ref_counts.restype = C.c_int64
         L.ref_counts.argtypes = [C.c_void_p] + [C.POINTER(C.c_void_p)] * 4
         L.ref_solid_size.restype = C.c_int64
@@ -112,13 +112,14 @@ class Run:
         if rc:
             raise RuntimeError("reference: " + lib().ref_last_error().decode())
 
-    def count_kmers(self, reads, k=30, min_count=5, counter_max_memory_bytes=0, force_exact_passes=0):
+    def count_kmers(self, reads, k=30, min_count=5, counter_max_memory_bytes=0, force_exact_passes=0, genome_bases=0):
         """kmer_counter's two-stage count, then the solid kmer_set.  Returns (counts, solid): counts = every element
         extract_exact_counts yields, sorted by k-mer (k-mers the probabilistic pass filtered may be absent); solid =
-        the kmer_set (ascending) with flag bits (bit0 fwd_starts_read, bit1 rev_starts_read)."""
+        the kmer_set (ascending) with flag bits (bit0 fwd_starts_read, bit1 rev_starts_read).  genome_bases: the size
+        of the --ref genome, which bounds the probabilistic table (0: the bases read)."""
         buf, offs = _pack(reads)
         self._ck(lib().ref_count_kmers(self.h, buf, offs.ctypes.data, len(offs) - 1, k, min_count,
-                                       counter_max_memory_bytes, force_exact_passes))
+                                       counter_max_memory_bytes, force_exact_passes, genome_bases))
         p = [C.c_void_p() for _ in range(4)]
         n = lib().ref_counts(self.h, *[C.byref(x) for x in p])
         kmers, fwd, rev, flags = (_view(p[0], n, np.uint64), _view(p[1], n, np.uint32), _view(p[2], n, np.uint32),

@@ -20,6 +20,9 @@
 //     (overrep threshold 0 disables it there too).
 //   * the reference genome as a compression dictionary (add_initial_repo) is not used: result-invisible.
 #include <atomic>
+#include <chrono>
+#include <cstdio>
+#include <cstdlib>
 #include <cstdint>
 #include <cstring>
 #include <map>
@@ -148,7 +151,7 @@ int ref_fast_read_correct(const char* read, int len, const uint64_t* solid, int6
 // Stage 1: kmer_counter (probabilistic pass, exact passes), then the solid kmer_set.
 // max_memory_bytes / partitions = 0: count_kmer_options defaults.  Returns 0 on success.
 int ref_count_kmers(void* h, const char* bases, const int64_t* offs, int64_t n, int k, int min_count,
-                    uint64_t counter_max_memory_bytes, int force_exact_passes) {
+                    uint64_t counter_max_memory_bytes, int force_exact_passes, uint64_t genome_bases) {
   auto* r = static_cast<ref_run*>(h);
   return guarded([&] {
     reads_view rv{bases, offs, n};
@@ -158,17 +161,27 @@ int ref_count_kmers(void* h, const char* bases, const int64_t* offs, int64_t n, 
     opts.min_count = min_count;
     if (counter_max_memory_bytes) opts.max_memory_bytes = counter_max_memory_bytes;
     opts.force_exact_passes = force_exact_passes;
-    // biograph_create.cpp:549-551 bounds the probabilistic table by 100 x the reference genome's size; without a
-    // genome here the bound is 100 x the bases read, which only ever makes the table larger (fewer false positives
-    // of a filter whose false positives never reach the result).
-    opts.max_prob_table_entries = std::max<size_t>(size_t(offs[n]) * 100, 1024 * 1024);
+    // biograph_create.cpp:549-551 bounds the probabilistic table by 100 x the reference genome's size (--ref);
+    // genome_bases = 0: 100 x the bases read, which only makes the table larger (fewer false positives of a filter
+    // whose false positives never reach the result).
+    opts.max_prob_table_entries = std::max<size_t>(size_t(genome_bases ? genome_bases : offs[n]) * 100, 1024 * 1024);
+    const bool timing = getenv("REF_SHIM_TIMING") != nullptr;
+    auto t_last = std::chrono::steady_clock::now();
+    auto lap = [&](const char* what) {
+      auto now = std::chrono::steady_clock::now();
+      if (timing) fprintf(stderr, "ref_count_kmers: %-18s %.2f s\n", what, std::chrono::duration<double>(now - t_last).count());
+      t_last = now;
+    };
     build_seqset::kmer_counter counter(opts);
     counter.start_prob_pass();
+    lap("start_prob_pass");
     blocks(n, r->threads, [&](int64_t a, int64_t b) {
       build_seqset::kmer_counter::prob_pass_processor p(counter);
       for (int64_t i = a; i < b; ++i) p.add(rv[i]);
     });
+    lap("prob pass");
     counter.close_prob_pass();
+    lap("close_prob_pass");
     for (unsigned pass = 0; pass < counter.exact_passes(); ++pass) {
       counter.start_exact_pass(pass);
       blocks(n, r->threads, [&](int64_t a, int64_t b) {
@@ -176,7 +189,9 @@ int ref_count_kmers(void* h, const char* bases, const int64_t* offs, int64_t n, 
         for (int64_t i = a; i < b; ++i) p.add(rv[i]);
       });
     }
+    lap("exact passes");
     counter.close_exact_passes();
+    lap("close_exact_passes");
 
     // defaults of kmerize_bf_params (modules/bio_mapred/kmerize_bf.h:37-38); the create flow never changes them
     struct { size_t prior_count = 5; float skew_cutoff = 0.0f; } kbf;
@@ -204,6 +219,7 @@ int ref_count_kmers(void* h, const char* bases, const int64_t* offs, int64_t n, 
         r->c_flags.push_back(uint8_t((el.fwd_starts_read ? 1 : 0) | (el.rev_starts_read ? 2 : 0)));
       }
     });
+    lap("extract counts");
     size_t mem_gb = std::max<size_t>(1, get_maximum_mem_bytes() / 1024 / 1024 / 1024);
     r->ks = make_unique<kmer_set>(
         approx, k, mem_gb,
@@ -221,7 +237,9 @@ int ref_count_kmers(void* h, const char* bases, const int64_t* offs, int64_t n, 
           });
         },
         null_progress_handler);
+    lap("kmer_set");
     counter.close();
+    lap("close");
   });
 }
 

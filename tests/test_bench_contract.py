@@ -24,7 +24,9 @@ def test_reference_arm_line():
     assert line["config"]["workload"] == "ecoli100x"
     assert line["e2e"] == {"value": line["value"], "unit": "bases/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
     cb = line["cpu_baseline"]
-    assert cb["kind"] == "port" and cb["value"] == line["value"] and "sample" in cb
+    # the reference's own classes where oracle/_ref was built (development container; travels to the GPU box), else the port
+    from oracle import ref as R
+    assert cb["kind"] == ("reference" if R.available() else "port") and cb["value"] == line["value"] and "sample" in cb
     # all the host cores, whatever OMP_NUM_THREADS says (torchrun exports OMP_NUM_THREADS=1)
     assert cb["cores"] == len(os.sched_getaffinity(0))
 
@@ -65,3 +67,56 @@ def test_committed_gpu_line_has_every_contract_key(name, workload, n_gpus):
         assert ("oracle" in p["against"]) == (n_gpus == 1)
         if n_gpus == 1:
             assert line["cpu_baseline"]["same_config"] is True
+
+
+def test_sample_check_against_the_reference_with_a_stand_in_device():
+    """bench.py's second parity anchor (a GPU build of the cpu_baseline sample against oracle/_ref) -- its comparison
+    logic, run here with the oracle standing in for the device (the real thing needs a B200)."""
+    import numpy as np
+    sys.path.insert(0, ROOT)
+    import bench
+    from oracle import oracle as O
+    from oracle import ref as R
+    if not R.available():
+        pytest.skip("oracle/_ref not built")
+
+    class FakeBgx:
+        def __init__(self, device=0):
+            pass
+
+        def __enter__(self):
+            return self
+
+        def __exit__(self, *a):
+            pass
+
+        def add_reads(self, reads):
+            buf, offs = reads
+            self.rb = (buf.tobytes(), offs)
+
+        def run(self):
+            self.solid = O.solid_set(O.count_kmers(self.rb, 30), 5)
+            self.cr = O.correct_reads(self.rb, self.solid, 30)
+            self.ss = O.seqset_staged((self.cr["seq"], self.cr["offs"]), self.cr["next_fwd"], self.cr["next_rev"])
+
+        def export_kmers(self, min_count):
+            return self.solid
+
+        def export_corrected(self):
+            return self.cr
+
+        def export_seqset(self):
+            return self.ss
+
+    class FakeB:
+        Bgx = FakeBgx
+
+    sub = bench.make_workload("small", 0, None, genome_prefix_reads=4000)
+    dt, n_ent, stage, res = bench.cpu_ref_run(sub, 2, bench.WORKLOADS["small"]["coverage"], keep=True)
+    par = bench.verify_sample_against_reference(FakeB, 0, sub, res)
+    assert par["checked"] and par["members_equal"] and par["mismatches"] == [] and par["entries"] == n_ent > 0
+    # a wrong table is reported, not raised
+    res["seqset"]["shared"] = res["seqset"]["shared"].copy()
+    res["seqset"]["shared"][5] += 1
+    par = bench.verify_sample_against_reference(FakeB, 0, sub, res)
+    assert par["checked"] and not par["members_equal"] and par["mismatches"] == ["seqset/shared"]

@@ -1,0 +1,79 @@
+"""The CUDA path (through the C ABI) against the REFERENCE'S OWN code on the same inputs: oracle/_ref/libref.so is
+the reference's kmer_counter / kmer_set / correct_reads / expander / builder / seqset compiled from its sources
+(oracle/ref_shim.cpp).  Bit-exact: solid k-mers with their counts and flags, the surviving corrected reads, every
+seqset table and the encoded payload members.  Sorts last (the library is a built artefact that travels to the GPU
+box; where it is absent these tests skip and the oracle comparisons of test_gpu_parity.py stand alone)."""
+import numpy as np
+import pytest
+
+from oracle import ref as R
+from tests.test_ref_vs_oracle import reads_of
+
+pytestmark = [pytest.mark.gpu, pytest.mark.skipif(not R.available(), reason="oracle/_ref/libref.so not built")]
+
+
+@pytest.fixture(scope="module")
+def B():
+    import biograph_b200 as B
+    if B.load_library().bgx_device_count() == 0:
+        pytest.fail("no CUDA device visible: the gpu tests need a B200 (there is no CPU fallback)")
+    return B
+
+
+def compare(B, reads, k=30, min_count=5, max_corrections=8, min_good_run=2, trim=0.7):
+    ref = R.create(reads, k, min_count, max_corrections, min_good_run, trim, threads=8, with_members=True)
+    g = B.Bgx(kmer_size=k, min_kmer_count=min_count, max_corrections=max_corrections, min_good_run=min_good_run,
+              trim_after_portion=trim)
+    try:
+        g.add_reads(reads)
+        g.run()
+        gs = g.export_kmers(min_count)
+        cr = g.export_corrected()
+        ss = g.export_seqset()
+        vb = [g.export_varbit(0), g.export_varbit(1)]
+    finally:
+        g.close()
+    c = ref["counts"]
+    m = (c["fwd"].astype(np.int64) + c["rev"]) >= min_count
+    assert np.array_equal(ref["solid"]["kmers"], gs["kmers"])
+    for f in ("kmers", "fwd", "rev", "flags"):
+        assert np.array_equal(c[f][m], gs[f]), f
+    rcr = ref["corrected"]
+    assert np.array_equal(rcr["kept"], cr["kept"]) and np.array_equal(rcr["offs"], cr["offs"]) and rcr["seq"] == cr["seq"]
+    rss = ref["seqset"]
+    assert rss["n"] == ss["n"]
+    for t in ("sizes", "shared", "prev", "fixed"):
+        assert np.array_equal(rss[t], ss[t]), t
+    # the payload members as the reference's encoders wrote them
+    mem = ref["members"]
+    if ss["n"]:
+        assert np.array_equal(np.frombuffer(mem["entry_sizes/elements"], dtype=np.uint64), vb[0]["elements"])
+        assert np.array_equal(np.frombuffer(mem["shared/elements"], dtype=np.uint64), vb[1]["elements"])
+        for b, ch in enumerate("ACGT"):
+            assert mem[f"prev_{ch}/subaccum"] == np.ascontiguousarray(ss["subaccum"][b]).tobytes()
+            assert mem[f"prev_{ch}/accum"] == np.ascontiguousarray(ss["accum"][b]).tobytes()
+    return ss
+
+
+def test_golden_reads_gpu_vs_reference(B, golden_reads):
+    assert compare(B, golden_reads)["n"] == 19935
+
+
+@pytest.mark.parametrize("cfg", [
+    dict(genome_len=20000, n_reads=8000, read_len=100, err=0.01, seed=31),
+    dict(genome_len=8000, n_reads=5000, read_len=150, err=0.02, seed=32, n_rate=0.002),
+    dict(genome_len=6000, n_reads=5000, read_len=80, err=0.01, seed=33, ragged=True),
+    dict(genome_len=10000, n_reads=6000, read_len=120, err=0.005, seed=34, repeat_frac=0.3),
+])
+def test_random_reads_gpu_vs_reference(B, cfg):
+    compare(B, reads_of(**cfg))
+
+
+@pytest.mark.parametrize("k,min_count,maxc,run,trim", [(16, 3, 2, 2, 0.7), (24, 5, 0, 2, 0.7), (31, 2, 8, 3, 0.5)])
+def test_parameters_gpu_vs_reference(B, k, min_count, maxc, run, trim):
+    compare(B, reads_of(5000, 4000, 100, 0.015, seed=200 + k, n_rate=0.001), k, min_count, maxc, run, trim)
+
+
+def test_larger_sample_gpu_vs_reference(B):
+    # 120 k reads of a 600 kb genome at 30x: 1.2 M entries
+    compare(B, reads_of(600000, 120000, 150, 0.005, seed=41))
