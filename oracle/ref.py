@@ -48,6 +48,7 @@ def lib():
         L.ref_seqset_size.restype = C.c_int64
         L.ref_seqset_size.argtypes = [C.c_void_p]
         L.ref_seqset_tables.argtypes = [C.c_void_p] + [C.c_void_p] * 5
+        L.ref_make_readmap.argtypes = [C.c_void_p, C.c_char_p, C.c_char_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int]
         L.ref_members.restype = C.c_int64
         L.ref_members.argtypes = [C.c_void_p]
         L.ref_member_name.restype = C.c_char_p
@@ -163,6 +164,29 @@ class Run:
         self._ck(lib().ref_seqset_tables(self.h, sizes.ctypes.data, shared.ctypes.data, prev.ctypes.data,
                                          fixed.ctypes.data, stats.ctypes.data))
         return {"n": int(n), "sizes": sizes, "shared": shared, "prev": prev, "fixed": fixed, "stats": stats}
+
+    def make_readmap(self, reads, rec_offs, is_paired):
+        """make_readmap::do_make over the seqset just built (call before members()).  reads: the corrected reads;
+        rec_offs[n_rec + 1]: record r holds reads [rec_offs[r], rec_offs[r + 1]) -- one read or two mates, as the
+        corrected_reads stream holds them.  Returns {member path: bytes} of the readmap spiral file the reference
+        wrote (stored zip members, read by offset: the reference leaves the CRC fields unset)."""
+        import struct
+        import zipfile
+        buf, offs = _pack(reads)
+        ro = np.ascontiguousarray(rec_offs, dtype=np.int64)
+        path = os.path.join(self.tmp, "ref.readmap")
+        if os.path.exists(path):
+            os.unlink(path)
+        self._ck(lib().ref_make_readmap(self.h, path.encode(), buf, offs.ctypes.data, ro.ctypes.data, len(ro) - 1,
+                                        1 if is_paired else 0))
+        raw = open(path, "rb").read()
+        out = {}
+        for info in zipfile.ZipFile(path).infolist():
+            o = info.header_offset
+            sig, _, _, comp, _, _, _, _, _, nl, el = struct.unpack("<IHHHHHIIIHH", raw[o:o + 30])
+            assert sig == 0x04034B50 and comp == 0
+            out[info.filename] = raw[o + 30 + nl + el:o + 30 + nl + el + info.file_size]
+        return out
 
     def members(self):
         """{member path: bytes} of the in-memory seqset spiral file, as the reference's encoders wrote them."""

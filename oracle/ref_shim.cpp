@@ -34,7 +34,9 @@
 
 #include "modules/bio_base/fast_read_correct.h"
 #include "modules/bio_base/seqset.h"
+#include "modules/bio_base/corrected_read.h"
 #include "modules/bio_mapred/kmer_set.h"
+#include "modules/bio_mapred/make_readmap.h"
 #include "modules/build_seqset/builder.h"
 #include "modules/build_seqset/correct_reads.h"
 #include "modules/build_seqset/expand.h"
@@ -389,6 +391,32 @@ int ref_seqset_tables(void* h, uint16_t* sizes, uint16_t* shared, uint64_t* prev
     for (int b = 0; b < 4; ++b) fixed[b] = ss.entry_push_front(0, dna_base(b));  // get_fixed(b) + count(0) = fixed[b]
     fixed[4] = n;
     if (stats) memcpy(stats, r->stats, sizeof(r->stats));
+  });
+}
+
+// make_readmap::do_make (modules/bio_mapred/make_readmap.cpp:15-22, as SEQSETMain::do_readmap calls it,
+// biograph_create.cpp:818-826) over the seqset of ref_make_seqset: the readmap spiral file is written to `path`.
+// Corrected reads are given record by record as the corrected_reads kv stream holds them: record r holds reads
+// [rec_offs[r], rec_offs[r+1]) -- one read, or two mates.  The records reach make_readmap through the in-memory
+// manifest stand-in (ref_stubs/modules/mapred/manifest_parallel.h).
+int ref_make_readmap(void* h, const char* path, const char* bases, const int64_t* offs, const int64_t* rec_offs,
+                     int64_t n_rec, int is_paired) {
+  auto* r = static_cast<ref_run*>(h);
+  return guarded([&] {
+    if (!r->ss) throw io_exception("ref_make_readmap: no seqset (run ref_make_seqset first, before ref_members)");
+    auto records = std::make_shared<std::vector<std::pair<std::string, corrected_reads>>>();
+    records->reserve(size_t(n_rec));
+    for (int64_t rec = 0; rec < n_rec; ++rec) {
+      corrected_reads cr;
+      for (int64_t i = rec_offs[rec]; i < rec_offs[rec + 1]; ++i) {
+        cr.emplace_back();
+        cr.back().corrected = dna_sequence(std::string(bases + offs[i], size_t(offs[i + 1] - offs[i])));
+      }
+      records->emplace_back("r" + std::to_string(rec), std::move(cr));
+    }
+    manifest m;
+    m.ref_stub_set_records(records);
+    make_readmap::do_make(path, *r->ss, m, is_paired != 0, r->ss->max_read_len());
   });
 }
 
