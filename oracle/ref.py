@@ -49,6 +49,11 @@ def lib():
         L.ref_seqset_size.argtypes = [C.c_void_p]
         L.ref_seqset_tables.argtypes = [C.c_void_p] + [C.c_void_p] * 5
         L.ref_make_readmap.argtypes = [C.c_void_p, C.c_char_p, C.c_char_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int]
+        L.ref_merge.argtypes = [C.c_void_p, C.c_int, C.c_void_p]
+        L.ref_mergemap.restype = C.c_int64
+        L.ref_mergemap.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_void_p)]
+        L.ref_flat.argtypes = [C.c_void_p, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), C.POINTER(C.c_int64)]
+        L.ref_free.argtypes = [C.c_void_p]
         L.ref_members.restype = C.c_int64
         L.ref_members.argtypes = [C.c_void_p]
         L.ref_member_name.restype = C.c_char_p
@@ -154,6 +159,32 @@ class Run:
     def make_seqset(self):
         """expander x 4 + builder (SEQSETMain::make_seqset).  Same dict as oracle.seqset_staged."""
         self._ck(lib().ref_make_seqset(self.h))
+        return self.seqset_tables()
+
+    def merge_from(self, runs):
+        """`biograph merge`'s seqset path over the seqsets of `runs` (each has done make_seqset) into this run:
+        seqset_flat_builder, make_mergemap, seqset_mergemap, seqset_merger.  Returns (merged tables, [mergemap bit
+        words per input])."""
+        arr = (C.c_void_p * len(runs))(*[r.h for r in runs])
+        self._ck(lib().ref_merge(arr, len(runs), self.h))
+        maps = []
+        for i in range(len(runs)):
+            p = C.c_void_p()
+            nw = lib().ref_mergemap(self.h, i, C.byref(p))
+            maps.append(_view(p, nw, np.uint64))
+        return self.seqset_tables(), maps
+
+    def flat(self):
+        """seqset_flat over this run's seqset: the sequence of every entry (list of bytes)"""
+        ps, po, n = C.c_void_p(), C.c_void_p(), C.c_int64()
+        self._ck(lib().ref_flat(self.h, C.byref(ps), C.byref(po), C.byref(n)))
+        offs = _view(po, n.value + 1, np.int64)
+        seq = _view(ps, offs[-1], np.uint8).tobytes()
+        lib().ref_free(ps)
+        lib().ref_free(po)
+        return [seq[offs[i]:offs[i + 1]] for i in range(n.value)]
+
+    def seqset_tables(self):
         n = lib().ref_seqset_size(self.h)
         words = (n + 63) // 64
         sizes = np.zeros(n, dtype=np.uint16)

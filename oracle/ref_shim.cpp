@@ -35,6 +35,9 @@
 #include "modules/bio_base/fast_read_correct.h"
 #include "modules/bio_base/seqset.h"
 #include "modules/bio_base/corrected_read.h"
+#include "modules/bio_base/make_mergemap.h"
+#include "modules/bio_base/seqset_flat.h"
+#include "modules/bio_base/seqset_merger.h"
 #include "modules/bio_mapred/kmer_set.h"
 #include "modules/bio_mapred/make_readmap.h"
 #include "modules/build_seqset/builder.h"
@@ -87,6 +90,8 @@ struct ref_run {
   int64_t stats[6] = {0, 0, 0, 0, 0, 0};
   spiral_file_mem_storage storage;
   std::vector<std::string> member_names;
+  // merge: one bit vector over the merged entries per input (bit x: merged entry x comes from this input)
+  std::vector<std::vector<uint64_t>> mergemaps;
 };
 
 template <class F>
@@ -419,6 +424,91 @@ int ref_make_readmap(void* h, const char* path, const char* bases, const int64_t
     make_readmap::do_make(path, *r->ss, m, is_paired != 0, r->ss->max_read_len());
   });
 }
+
+// `biograph merge`'s seqset path (modules/biograph/biograph_merge.cpp:196-285) over the seqsets of n_in runs that
+// have done ref_make_seqset: seqset_flat_builder per input, make_mergemap over the flats, one seqset_mergemap per
+// input, seqset_merger::build.  Everything goes through in-memory spiral files instead of the temp files.  The merged
+// seqset lands in `out` (ref_seqset_tables / ref_members work on it), the mergemap bits in ref_mergemap.
+int ref_merge(void** ins, int n_in, void* out) {
+  auto* o = static_cast<ref_run*>(out);
+  return guarded([&] {
+    std::vector<const seqset*> sets;
+    for (int i = 0; i < n_in; ++i) {
+      auto* r = static_cast<ref_run*>(ins[i]);
+      if (!r->ss) throw io_exception("ref_merge: an input has no seqset");
+      sets.push_back(r->ss.get());
+    }
+    std::vector<std::unique_ptr<seqset_flat>> flats;
+    std::vector<const seqset_flat*> flat_ptrs;
+    for (const seqset* s : sets) {
+      spiral_file_create_mem c;
+      seqset_flat_builder b(s);
+      b.build(c.create());
+      spiral_file_open_mem op(c.close());
+      flats.emplace_back(new seqset_flat(op.open(), s));
+      flat_ptrs.push_back(flats.back().get());
+    }
+    o->create = make_unique<spiral_file_create_mem>();
+    make_mergemap mm(flat_ptrs);
+    mm.build();
+    size_t total = mm.total_merged_entries();
+    std::vector<std::unique_ptr<seqset_mergemap>> maps;
+    std::vector<const seqset_mergemap*> map_ptrs;
+    o->mergemaps.clear();
+    for (int i = 0; i < n_in; ++i) {
+      spiral_file_create_mem c;
+      seqset_mergemap_builder b(c.create(), sets[size_t(i)]->uuid(), o->create->uuid(), total);
+      mm.fill_mergemap(unsigned(i), &b);
+      spiral_file_open_mem op(c.close());
+      maps.emplace_back(new seqset_mergemap(op.open()));
+      map_ptrs.push_back(maps.back().get());
+      std::vector<uint64_t> bits((total + 63) / 64, 0);
+      const bitcount& bc = maps.back()->get_bitcount();
+      for (size_t x = 0; x < total; ++x)
+        if (bc.get(x)) bits[x / 64] |= 1ULL << (x % 64);
+      o->mergemaps.push_back(std::move(bits));
+    }
+    seqset_merger merger(flat_ptrs, map_ptrs);
+    // seqset_merger keeps the merged seqset to itself; reopen what it wrote
+    merger.build(o->create->create());
+    o->storage = o->create->close();
+    o->create.reset();
+    o->member_names.clear();
+    for (auto& kv : o->storage.paths) o->member_names.push_back(kv.first);
+    spiral_file_open_mem op(o->storage);
+    o->ss = make_unique<seqset>(op.open());
+  });
+}
+int64_t ref_mergemap(void* h, int input, const uint64_t** bits) {
+  auto* r = static_cast<ref_run*>(h);
+  if (input < 0 || size_t(input) >= r->mergemaps.size()) return -1;
+  *bits = r->mergemaps[size_t(input)].data();
+  return int64_t(r->mergemaps[size_t(input)].size());
+}
+// the flat sequence of every entry of the run's seqset, through the reference's seqset_flat (ASCII, offs[n + 1])
+int ref_flat(void* h, char** seq, int64_t** offs, int64_t* n_out) {
+  auto* r = static_cast<ref_run*>(h);
+  return guarded([&] {
+    if (!r->ss) throw io_exception("ref_flat: no seqset");
+    spiral_file_create_mem c;
+    seqset_flat_builder b(r->ss.get());
+    b.build(c.create());
+    spiral_file_open_mem op(c.close());
+    seqset_flat flat(op.open(), r->ss.get());
+    std::string all;
+    std::vector<int64_t> o{0};
+    for (auto it = flat.begin(); it != flat.end(); ++it) {
+      all += (*it).as_string();
+      o.push_back(int64_t(all.size()));
+    }
+    *seq = static_cast<char*>(malloc(all.size() + 1));
+    memcpy(*seq, all.data(), all.size());
+    *offs = static_cast<int64_t*>(malloc(o.size() * sizeof(int64_t)));
+    memcpy(*offs, o.data(), o.size() * sizeof(int64_t));
+    *n_out = int64_t(o.size()) - 1;
+  });
+}
+void ref_free(void* p) { free(p); }
 
 // the members of the in-memory spiral file exactly as the reference's encoders wrote them (closes the file)
 int64_t ref_members(void* h) {
