@@ -588,7 +588,7 @@ def main():
         parity, dt = verify_against_oracle(g, reads, threads)
         cpu = {"value": n_reads * read_len / dt, "unit": "bases/s", "cores": threads, "kind": "port", "same_config": True,
                "sample": f"the whole workload ({n_reads} reads) once, whole path (2-stage count + correct + staged "
-                         f"seqset), {dt:.1f} s; oracle port (reference binary not buildable offline); this run is "
+                         f"seqset), {dt:.1f} s; oracle port (the restated CPU path); this run is "
                          "also the parity check"}
         if reference_available() and not args.no_cpu_baseline:
             # the reference's own code on a bounded sample: the CPU baseline proper, and a second parity anchor
@@ -615,7 +615,7 @@ def main():
         cpu = {"value": sample * read_len / dt, "unit": "bases/s", "cores": threads, "kind": "port", "same_config": False,
                "sample": f"{sample} reads at the workload's coverage over a genome prefix (workload has {n_reads}), "
                          f"whole path (2-stage count + correct + staged seqset) once, {dt:.1f} s; oracle port "
-                         "(reference binary not buildable offline)"}
+                         "(oracle/_ref not built)"}
     elif world > 1 and not args.no_verify:
         parity = verify_against_single_gpu(g, B, dist, rank, world, local, pinned, pinned_mask, pinned_lens, n_reads)
 

@@ -7,7 +7,10 @@
 // Parity status: PINNED.  tests/test_oracle_golden.py checks this file against the
 // reference's own golden fixture (golden/e_coli_10000snp.fq -> golden/e_coli_10000snp.bg/seqset,
 // every payload member byte-for-byte), the builder_test / expand_test known answers and the
-// fast_read_correct_test analytic cases (fixtures committed under tests/golden/).
+// fast_read_correct_test analytic cases (fixtures committed under tests/golden/); and
+// tests/test_ref_vs_oracle.py checks it against the reference's OWN classes (oracle/_ref/libref.so,
+// compiled from the sources under /root/reference, see ref_shim.cpp) on the same inputs: counts,
+// flags, solid set, corrected reads, every seqset table and encoded member.
 //
 // Each function cites the reference file:line (relative to the reference checkout) it follows.
 // "bs/" abbreviates modules/build_seqset/.

@@ -19,10 +19,11 @@ tests/golden/make_golden_readmap.py): every payload member reproduced.
 Paired reads: readmap_tables_paired is the parallel form (what the GPU computes), and
 readmap_tables_paired_literal transcribes the reference's two passes statement by statement
 (:168-188 rows, :262-300 first pass, :302-360 the sequential claim pass with its `claimed` bit
-vector); tests check the two against each other.  PARITY OF THE PAIRED FORM IS UNPINNED: the only
-readmap in the reference tree that follows the current row order is the unpaired golden (the paired
-readmaps under datasets/ were written by an older build), so the paired form rests on
-the transcription and on the properties the reference's readmap_test.cpp:53-168 checks."""
+vector); tests check the two against each other.  The paired form is pinned against the reference's
+OWN make_readmap, compiled from its sources into oracle/_ref and run on the same records
+(tests/test_ref_readmap.py: every payload member byte for byte); the only readmap in the reference
+tree that follows the current row order is the unpaired golden (the paired readmaps under datasets/
+were written by an older build), so no fixture could."""
 import numpy as np
 
 K_NO_LOOP_ENTRY = (1 << 37) - 1
