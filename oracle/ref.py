@@ -49,6 +49,12 @@ def lib():
         L.ref_seqset_size.argtypes = [C.c_void_p]
         L.ref_seqset_tables.argtypes = [C.c_void_p] + [C.c_void_p] * 5
         L.ref_make_readmap.argtypes = [C.c_void_p, C.c_char_p, C.c_char_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int]
+        L.ref_open_seqset_file.argtypes = [C.c_void_p, C.c_char_p]
+        L.ref_seqset_uuid.restype = C.c_char_p
+        L.ref_seqset_uuid.argtypes = [C.c_void_p]
+        L.ref_readmap_rows.restype = C.c_int64
+        L.ref_readmap_rows.argtypes = [C.c_char_p]
+        L.ref_read_readmap_file.argtypes = [C.c_char_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_char_p]
         L.ref_merge.argtypes = [C.c_void_p, C.c_int, C.c_void_p]
         L.ref_mergemap.restype = C.c_int64
         L.ref_mergemap.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_void_p)]
@@ -161,6 +167,15 @@ class Run:
         self._ck(lib().ref_make_seqset(self.h))
         return self.seqset_tables()
 
+    def open_seqset_file(self, path):
+        """a seqset spiral file through the reference's own reader (spiral_file_open_mmap + seqset); returns its
+        tables.  flat() then walks every entry's sequence through the reference's seqset_flat."""
+        self._ck(lib().ref_open_seqset_file(self.h, os.fsencode(path)))
+        return self.seqset_tables()
+
+    def seqset_uuid(self):
+        return lib().ref_seqset_uuid(self.h).decode()
+
     def merge_from(self, runs):
         """`biograph merge`'s seqset path over the seqsets of `runs` (each has done make_seqset) into this run:
         seqset_flat_builder, make_mergemap, seqset_mergemap, seqset_merger.  Returns (merged tables, [mergemap bit
@@ -230,6 +245,23 @@ class Run:
             sz = lib().ref_member_data(self.h, i, C.byref(p))
             out[lib().ref_member_name(self.h, i).decode()] = _view(p, sz, np.uint8).tobytes()
         return out
+
+
+def read_readmap_file(path):
+    """a readmap spiral file through the reference's own reader (readmap::open_anonymous_readmap) and accessors:
+    dict(entry_id, read_lengths, is_forward, mate_loop_ptr, seqset_uuid), one element per row"""
+    p = os.fsencode(path)
+    n = lib().ref_readmap_rows(p)
+    if n < 0:
+        raise RuntimeError("reference: " + lib().ref_last_error().decode())
+    entry = np.zeros(n, dtype=np.uint64)
+    ln = np.zeros(n, dtype=np.int32)
+    fwd = np.zeros(n, dtype=np.uint8)
+    ptr = np.zeros(n, dtype=np.uint64)
+    uuid = C.create_string_buffer(64)
+    if lib().ref_read_readmap_file(p, entry.ctypes.data, ln.ctypes.data, fwd.ctypes.data, ptr.ctypes.data, uuid):
+        raise RuntimeError("reference: " + lib().ref_last_error().decode())
+    return {"entry_id": entry, "read_lengths": ln, "is_forward": fwd, "mate_loop_ptr": ptr, "seqset_uuid": uuid.value.decode()}
 
 
 def seqset_for_reads(reads, next_fwd=None, next_rev=None, threads=0, partition_depth=2):

@@ -36,6 +36,7 @@
 #include "modules/bio_base/seqset.h"
 #include "modules/bio_base/corrected_read.h"
 #include "modules/bio_base/make_mergemap.h"
+#include "modules/bio_base/readmap.h"
 #include "modules/bio_base/seqset_flat.h"
 #include "modules/bio_base/seqset_merger.h"
 #include "modules/bio_mapred/kmer_set.h"
@@ -48,6 +49,7 @@
 #include "modules/io/config.h"
 #include "modules/io/parallel.h"
 #include "modules/io/spiral_file_mem.h"
+#include "modules/io/spiral_file_mmap.h"
 #include "modules/io/track_mem.h"
 
 namespace {
@@ -86,6 +88,7 @@ struct ref_run {
   std::vector<uint8_t> cr_kept;
   // seqset stage
   std::unique_ptr<spiral_file_create_mem> create;
+  std::unique_ptr<spiral_file_open_mmap> open_mmap;  // ref_open_seqset_file (declared before ss: outlives it)
   std::unique_ptr<seqset> ss;
   int64_t stats[6] = {0, 0, 0, 0, 0, 0};
   spiral_file_mem_storage storage;
@@ -371,6 +374,52 @@ int ref_make_seqset(void* h) {
     r->entries.reset();
     r->create = make_unique<spiral_file_create_mem>();
     r->ss = b.make_seqset(r->create->create());
+  });
+}
+
+// Opens a seqset spiral FILE with the reference's own reader (spiral_file_open_mmap + seqset::seqset(open state):
+// zip directory through the vendored minizip, part types and versions, bitcount / packed_varbit_vector members) --
+// for files the facade's writer or bgx-create wrote.  ref_seqset_tables / ref_flat then work on it.
+int ref_open_seqset_file(void* h, const char* path) {
+  auto* r = static_cast<ref_run*>(h);
+  return guarded([&] {
+    r->ss.reset();
+    r->open_mmap = make_unique<spiral_file_open_mmap>(path);
+    r->ss = make_unique<seqset>(r->open_mmap->open());
+  });
+}
+const char* ref_seqset_uuid(void* h) {
+  auto* r = static_cast<ref_run*>(h);
+  static thread_local std::string u;
+  u = r->ss ? r->ss->uuid() : "";
+  return u.c_str();
+}
+
+// Opens a readmap spiral FILE with the reference's own reader (readmap::open_anonymous_readmap: sparse_multi,
+// packed_varbit_vector, packed_vector members) and reads every row back through its public accessors:
+// entry = index_to_entry, len = get_readlength, fwd = get_is_forward, ptr = the row's mate-loop pointer
+// (get_rev_comp for a forward row, get_mate_rc for a reverse one: one step along the loop, readmap.cpp:248-290).
+// Arrays must hold ref_readmap_rows(path) elements.
+int64_t ref_readmap_rows(const char* path) {
+  int64_t n = -1;
+  guarded([&] { n = int64_t(readmap::open_anonymous_readmap(path)->size()); });
+  return n;
+}
+int ref_read_readmap_file(const char* path, uint64_t* entry, int32_t* len, uint8_t* fwd, uint64_t* ptr,
+                          char* seqset_uuid_out /* 64 bytes */) {
+  return guarded([&] {
+    std::unique_ptr<readmap> rm = readmap::open_anonymous_readmap(path);
+    if (!rm->has_pairing_data() || !rm->has_mate_loop()) throw io_exception("readmap without a mate loop table");
+    size_t n = rm->size();
+    for (size_t i = 0; i < n; ++i) {
+      entry[i] = rm->index_to_entry(i);
+      len[i] = rm->get_readlength(uint32_t(i));
+      fwd[i] = rm->get_is_forward(uint32_t(i)) ? 1 : 0;
+      ptr[i] = fwd[i] ? rm->get_rev_comp(uint32_t(i)) : rm->get_mate_rc(uint32_t(i));
+    }
+    std::string u = rm->metadata().seqset_uuid;
+    strncpy(seqset_uuid_out, u.c_str(), 63);
+    seqset_uuid_out[63] = 0;
   });
 }
 

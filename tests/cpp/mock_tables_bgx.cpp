@@ -1,0 +1,131 @@
+// mock_tables_bgx.cpp -- a stand-in for the C ABI that serves FINISHED seqset tables from raw files (written by the
+// test from the CPU oracle's result), so that bgx_bs::builder::make_seqset -- the facade's seqset spiral-file writer --
+// runs without a GPU.  The file it writes is then opened by the reference's OWN reader (oracle/_ref:
+// spiral_file_open_mmap + seqset), tests/test_ref_reads_facade_files.py.  Test infrastructure.
+//
+// $BGX_MOCK_TABLES/: meta.txt = "num_entries max_entry_len prev_words sub_words acc_words sizes_bits sizes_max
+// shared_bits shared_max"; fixed.bin; prev_bits_<b>.bin, prev_sub_<b>.bin, prev_acc_<b>.bin (b = 0..3);
+// sizes_elements.bin, shared_elements.bin (uint64 words).
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "bgx.h"
+
+struct bgx_ctx {};
+static std::string g_err;
+
+static std::string dir() {
+  const char* d = getenv("BGX_MOCK_TABLES");
+  return d ? d : ".";
+}
+static bool slurp(const std::string& name, std::vector<char>* out) {
+  FILE* f = fopen((dir() + "/" + name).c_str(), "rb");
+  if (!f) { g_err = "mock: cannot open " + name; return false; }
+  fseek(f, 0, SEEK_END);
+  long n = ftell(f);
+  fseek(f, 0, SEEK_SET);
+  out->resize((size_t)n);
+  size_t got = n ? fread(out->data(), 1, (size_t)n, f) : 0;
+  fclose(f);
+  return got == (size_t)n;
+}
+static uint64_t* words_of(const std::string& name, uint64_t* n_words) {
+  std::vector<char> b;
+  if (!slurp(name, &b)) return nullptr;
+  uint64_t* p = (uint64_t*)malloc(b.size() ? b.size() : 8);
+  memcpy(p, b.data(), b.size());
+  if (n_words) *n_words = b.size() / 8;
+  return p;
+}
+struct meta_t { unsigned long long n, maxlen, pw, sw, aw, sbits, smax, hbits, hmax; };
+static bool meta(meta_t* m) {
+  std::vector<char> b;
+  if (!slurp("meta.txt", &b)) return false;
+  b.push_back(0);
+  return sscanf(b.data(), "%llu %llu %llu %llu %llu %llu %llu %llu %llu", &m->n, &m->maxlen, &m->pw, &m->sw, &m->aw, &m->sbits,
+                &m->smax, &m->hbits, &m->hmax) == 9;
+}
+
+extern "C" {
+void bgx_default_options(bgx_options* o) { memset(o, 0, sizeof *o); }
+const char* bgx_last_error(void) { return g_err.c_str(); }
+const char* bgx_version(void) { return "mock-tables"; }
+int bgx_create(const bgx_options*, bgx_ctx** out) { *out = new bgx_ctx(); return 0; }
+void bgx_destroy(bgx_ctx* c) { delete c; }
+void bgx_free(void* p) { free(p); }
+int bgx_build_seqset(bgx_ctx*) { return 0; }
+int bgx_seqset_layout(bgx_ctx*, uint64_t lay[6]) {
+  meta_t m;
+  if (!meta(&m)) return 1;
+  lay[0] = lay[1] = m.n; lay[2] = 0; lay[3] = m.pw; lay[4] = m.sw; lay[5] = m.aw;
+  return 0;
+}
+int bgx_export_seqset(bgx_ctx*, uint64_t* n_entries, uint32_t* max_entry_len, uint16_t** sizes, uint16_t** shared,
+                      uint64_t* prev_bits[4], uint64_t* prev_subaccum[4], uint64_t* prev_accum[4], uint64_t fixed[5]) {
+  meta_t m;
+  if (!meta(&m)) return 1;
+  if (sizes || shared) { g_err = "mock: per-entry arrays are not served"; return 1; }
+  if (n_entries) *n_entries = m.n;
+  if (max_entry_len) *max_entry_len = (uint32_t)m.maxlen;
+  for (int b = 0; b < 4; ++b) {
+    const std::string s = std::to_string(b);
+    if (prev_bits && !(prev_bits[b] = words_of("prev_bits_" + s + ".bin", nullptr))) return 1;
+    if (prev_subaccum && !(prev_subaccum[b] = words_of("prev_sub_" + s + ".bin", nullptr))) return 1;
+    if (prev_accum && !(prev_accum[b] = words_of("prev_acc_" + s + ".bin", nullptr))) return 1;
+  }
+  if (fixed) {
+    uint64_t* f = words_of("fixed.bin", nullptr);
+    if (!f) return 1;
+    memcpy(fixed, f, 40);
+    free(f);
+  }
+  return 0;
+}
+int bgx_export_varbit(bgx_ctx*, int32_t which, uint64_t** words, uint64_t* n_words, uint32_t* bits_per_value, uint64_t* max_value) {
+  meta_t m;
+  if (!meta(&m)) return 1;
+  *words = words_of(which == 0 ? "sizes_elements.bin" : "shared_elements.bin", n_words);
+  if (!*words) return 1;
+  *bits_per_value = (uint32_t)(which == 0 ? m.sbits : m.hbits);
+  *max_value = which == 0 ? m.smax : m.hmax;
+  return 0;
+}
+// readmap tables: rm_meta.txt = "n_rows"; rm_lens.bin (uint16), rm_ptr.bin, rm_fwd.bin (uint64 words),
+// rm_src_<i>.bin / rm_dst_<i>.bin (i = 0 bits, 1 subaccum, 2 accum)
+int bgx_build_readmap(bgx_ctx*, int32_t, uint64_t* n_rows, uint16_t** read_lengths, uint64_t** mate_loop_ptr, uint64_t** is_forward,
+                      uint64_t* source[3], uint64_t* dest[3]) {
+  std::vector<char> b;
+  if (!slurp("rm_meta.txt", &b)) return 1;
+  b.push_back(0);
+  *n_rows = strtoull(b.data(), nullptr, 10);
+  *read_lengths = (uint16_t*)words_of("rm_lens.bin", nullptr);
+  *mate_loop_ptr = words_of("rm_ptr.bin", nullptr);
+  *is_forward = words_of("rm_fwd.bin", nullptr);
+  if (!*read_lengths || !*mate_loop_ptr || !*is_forward) return 1;
+  for (int i = 0; i < 3; ++i) {
+    source[i] = words_of("rm_src_" + std::to_string(i) + ".bin", nullptr);
+    dest[i] = words_of("rm_dst_" + std::to_string(i) + ".bin", nullptr);
+    if (!source[i] || !dest[i]) return 1;
+  }
+  return 0;
+}
+// entry points the facade header references elsewhere; none is reached by the writer test
+int bgx_merge_seqsets(bgx_ctx*, const bgx_seqset_part*, uint32_t, uint64_t) { return 1; }
+int bgx_export_mergemap(bgx_ctx*, uint32_t, uint64_t*[3], uint64_t*, uint64_t*) { return 1; }
+int bgx_migrate_bits(bgx_ctx*, uint32_t, const uint64_t*, uint64_t, uint64_t*[3], uint64_t*) { return 1; }
+int bgx_export_flat_ascii(bgx_ctx*, uint32_t, uint64_t, uint64_t, char**, uint64_t**) { return 1; }
+int bgx_add_reads_ascii(bgx_ctx*, const char*, const uint64_t*, uint64_t) { return 1; }
+int bgx_add_reads_fastq(bgx_ctx*, const char*, uint64_t, uint64_t*) { return 1; }
+int bgx_count_kmers(bgx_ctx*) { return 1; }
+int bgx_stats_json(bgx_ctx*, char* buf, size_t cap) { if (cap) buf[0] = 0; return 1; }
+int bgx_export_kmers(bgx_ctx*, uint32_t, uint64_t*, uint64_t**, uint32_t**, uint32_t**, uint8_t**) { return 1; }
+int bgx_export_reads(bgx_ctx*, uint64_t*, uint16_t**, char**, uint64_t*) { return 1; }
+int bgx_correct(bgx_ctx*) { return 1; }
+int bgx_seed_uncorrected(bgx_ctx*) { return 1; }
+int bgx_export_corrected(bgx_ctx*, uint64_t*, uint16_t**, char**, uint64_t*, uint8_t**, uint16_t**, uint16_t**) { return 1; }
+int bgx_dist_unique_id(uint8_t*) { return 1; }
+int bgx_dist_init(bgx_ctx*, int32_t, int32_t, const uint8_t*) { return 1; }
+}

@@ -1,0 +1,150 @@
+"""Drop-in check of the `.bg` seqset output: the facade's spiral-file writer (bgx_bs::builder::make_seqset, the code
+bgx-create uses) writes a seqset file, and the REFERENCE'S OWN reader opens it (oracle/_ref: spiral_file_open_mmap
+over the vendored minizip, part types / versions, seqset::seqset(open state), bitcount, packed_varbit_vector) and
+returns the same tables; seqset_flat then walks every entry's sequence through the reference's pop_front logic.
+The tables come from the CPU oracle through a mock of the C ABI (tests/cpp/mock_tables_bgx.cpp), so no GPU is needed:
+what is under test is the file, not the tables.  CPU only."""
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+from oracle import oracle as O
+from oracle import ref as R
+from tests.test_ref_vs_oracle import reads_of
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+pytestmark = pytest.mark.skipif(not R.available(), reason="oracle/_ref/libref.so not built (no reference checkout)")
+
+
+@pytest.fixture(scope="module")
+def writer(tmp_path_factory):
+    d = str(tmp_path_factory.mktemp("facade_writer"))
+    inc = os.path.join(ROOT, "include")
+    subprocess.check_call(["g++", "-std=c++17", "-O1", "-Wall", "-I", inc, "-shared", "-fPIC",
+                           os.path.join(ROOT, "tests", "cpp", "mock_tables_bgx.cpp"), "-o", os.path.join(d, "libbgx.so")])
+    subprocess.check_call(["g++", "-std=c++17", "-O1", "-Wall", "-I", inc, os.path.join(ROOT, "tests", "cpp", "facade_write_test.cpp"),
+                           "-L", d, "-lbgx", "-Wl,-rpath," + d, "-lpthread", "-o", os.path.join(d, "facade_write_test")])
+    return d
+
+
+def write_tables(d, ss):
+    n = ss["n"]
+    mx = int(ss["sizes"].max())
+    se, sb = O.varbit_pack(ss["sizes"], mx)
+    he, hb = O.varbit_pack(ss["shared"], mx - 1)
+    acc_words = None
+    for b in range(4):
+        sub, acc, _ = O.bitcount_finalize(ss["prev"][b], n)
+        ss["prev"][b].tofile(os.path.join(d, f"prev_bits_{b}.bin"))
+        sub.tofile(os.path.join(d, f"prev_sub_{b}.bin"))
+        acc.tofile(os.path.join(d, f"prev_acc_{b}.bin"))
+        acc_words = len(acc)
+    ss["fixed"].astype(np.uint64).tofile(os.path.join(d, "fixed.bin"))
+    se.tofile(os.path.join(d, "sizes_elements.bin"))
+    he.tofile(os.path.join(d, "shared_elements.bin"))
+    bits = lambda v: max(1, int(v).bit_length())  # noqa: E731
+    with open(os.path.join(d, "meta.txt"), "w") as f:
+        f.write(f"{n} {mx} {ss['prev'].shape[1]} {(n + 511) // 512} {acc_words} {bits(mx)} {mx} {bits(mx - 1)} {mx - 1}\n")
+
+
+@pytest.mark.parametrize("case", ["golden", "random", "long_reads"])
+def test_reference_reader_opens_the_facade_written_seqset(writer, tmp_path, golden_reads, case):
+    reads = {"golden": lambda: golden_reads, "random": lambda: reads_of(8000, 5000, 100, 0.01, seed=51),
+             "long_reads": lambda: reads_of(3000, 1500, 250, 0.005, seed=52)}[case]()
+    solid = O.solid_set(O.count_kmers(reads, 30), 5)
+    cr = O.correct_reads(reads, solid, 30)
+    ss = O.seqset_closed_form((cr["seq"], cr["offs"]))
+    tables = str(tmp_path / "tables")
+    os.mkdir(tables)
+    write_tables(tables, ss)
+    path = str(tmp_path / "seqset")
+    uuid = "0f0e0d0c-1111-2222-3333-444455556666"
+    env = dict(os.environ, BGX_MOCK_TABLES=tables)
+    out = subprocess.run([os.path.join(writer, "facade_write_test"), path, uuid], env=env, capture_output=True, text=True)
+    assert out.returncode == 0, out.stderr
+    with R.Run(2) as r:
+        got = r.open_seqset_file(path)           # the reference's reader accepts the file ...
+        assert r.seqset_uuid() == uuid
+        assert got["n"] == ss["n"]
+        for t in ("sizes", "shared", "prev", "fixed"):   # ... and sees the tables that went in
+            assert np.array_equal(got[t], ss[t]), t
+        flat = r.flat()                           # every entry's sequence through the reference's own traversal
+    ents = sorted(set(O.entries_closed_form_py(O.corrected_list(cr)))) if case != "golden" else None
+    assert flat == sorted(flat) and len(flat) == ss["n"]
+    assert [len(e) for e in flat] == ss["sizes"].tolist()
+    if ents is not None:
+        assert [e.decode() for e in flat] == ents
+
+
+def test_reference_reader_refuses_a_damaged_file(writer, tmp_path, golden_reads):
+    # the same reader is not lenient: a truncated file is an error, not garbage tables
+    solid = O.solid_set(O.count_kmers(golden_reads, 30), 5)
+    cr = O.correct_reads(golden_reads, solid, 30)
+    ss = O.seqset_closed_form((cr["seq"], cr["offs"]))
+    tables = str(tmp_path / "tables")
+    os.mkdir(tables)
+    write_tables(tables, ss)
+    path = str(tmp_path / "seqset")
+    subprocess.check_call([os.path.join(writer, "facade_write_test"), path, "u"], env=dict(os.environ, BGX_MOCK_TABLES=tables),
+                          stdout=subprocess.DEVNULL)
+    raw = open(path, "rb").read()
+    open(path, "wb").write(raw[:len(raw) // 2])
+    with R.Run(1) as r:
+        with pytest.raises(RuntimeError):
+            r.open_seqset_file(path)
+
+
+# ---- readmap files -----------------------------------------------------------------------------------------------
+def _readmap_case(seed, is_paired):
+    import bisect
+
+    from oracle import readmap as RM
+    from tests.test_oracle_readmap import _random_paired_case
+    reads, kept, ents = _random_paired_case(seed, 400, 500, 45, 0.3, 0.1)
+
+    def lookup(s):
+        i = bisect.bisect_left(ents, s)
+        assert ents[i].startswith(s)
+        return i
+
+    fwd = [lookup(r) if k else 0 for r, k in zip(reads, kept)]
+    rc = [lookup(O.revcomp(r)) if k else 0 for r, k in zip(reads, kept)]
+    lens = [len(r) for r in reads]
+    if is_paired:
+        t = RM.readmap_tables_paired(*RM.pair_records(fwd, rc, lens, kept), len(ents))
+    else:
+        k = np.asarray(kept, dtype=bool)
+        t = RM.readmap_tables(np.asarray(fwd)[k], np.asarray(rc)[k], np.asarray(lens)[k], len(ents))
+    return t, len(ents), max(len(e) for e in ents)
+
+
+@pytest.mark.parametrize("is_paired", [False, True])
+def test_reference_reader_opens_the_facade_written_readmap(writer, tmp_path, is_paired):
+    from oracle import readmap as RM
+    t, n_entries, max_len = _readmap_case(61 + is_paired, is_paired)
+    d = str(tmp_path / "tables")
+    os.mkdir(d)
+    n = t["n_rows"]
+    open(os.path.join(d, "meta.txt"), "w").write(f"{n_entries} {max_len} 0 0 0 1 1 1 1\n")  # bgx_seqset_layout: entry count
+    open(os.path.join(d, "rm_meta.txt"), "w").write(f"{n}\n")
+    t["read_lengths"].astype(np.uint16).tofile(os.path.join(d, "rm_lens.bin"))
+    t["mate_loop_ptr"].astype(np.uint64).tofile(os.path.join(d, "rm_ptr.bin"))
+    RM.pack_bits(t["is_forward"]).tofile(os.path.join(d, "rm_fwd.bin"))
+    for name, bits in (("src", t["source_to_mid"]), ("dst", t["dest_to_mid"])):
+        words = RM.pack_bits(bits)
+        sub, acc, _ = O.bitcount_finalize(words, len(bits))
+        for i, a in enumerate((words, sub, acc)):
+            a.tofile(os.path.join(d, f"rm_{name}_{i}.bin"))
+    path = str(tmp_path / "x.readmap")
+    uuid = "aaaaaaaa-bbbb-cccc-dddd-eeeeeeeeeeee"
+    out = subprocess.run([os.path.join(writer, "facade_write_test"), "readmap", path, uuid, "1" if is_paired else "0", str(max_len)],
+                         env=dict(os.environ, BGX_MOCK_TABLES=d), capture_output=True, text=True)
+    assert out.returncode == 0, out.stderr
+    got = R.read_readmap_file(path)   # readmap::open_anonymous_readmap + its accessors, row by row
+    assert got["seqset_uuid"] == uuid
+    assert np.array_equal(got["entry_id"], t["entry_id"])
+    assert np.array_equal(got["read_lengths"], t["read_lengths"].astype(np.int32))
+    assert np.array_equal(got["is_forward"], t["is_forward"])
+    assert np.array_equal(got["mate_loop_ptr"], t["mate_loop_ptr"])
