@@ -45,6 +45,7 @@ def lib():
         L.ref_corrected.argtypes = [C.c_void_p] + [C.POINTER(C.c_void_p)] * 3
         L.ref_seed.argtypes = [C.c_void_p, C.c_char_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_int]
         L.ref_make_seqset.argtypes = [C.c_void_p]
+        L.ref_make_seqset_file.argtypes = [C.c_void_p, C.c_char_p]
         L.ref_seqset_size.restype = C.c_int64
         L.ref_seqset_size.argtypes = [C.c_void_p]
         L.ref_seqset_tables.argtypes = [C.c_void_p] + [C.c_void_p] * 5
@@ -162,9 +163,13 @@ class Run:
         self._ck(lib().ref_seed(self.h, buf, offs.ctypes.data, len(offs) - 1, None if nf is None else nf.ctypes.data,
                                 None if nr is None else nr.ctypes.data, partition_depth))
 
-    def make_seqset(self):
-        """expander x 4 + builder (SEQSETMain::make_seqset).  Same dict as oracle.seqset_staged."""
-        self._ck(lib().ref_make_seqset(self.h))
+    def make_seqset(self, path=None):
+        """expander x 4 + builder (SEQSETMain::make_seqset).  Same dict as oracle.seqset_staged.  path: the seqset
+        is written there by the reference's own spiral_file_create_mmap (as <out>.bg/seqset) and reopened."""
+        if path is None:
+            self._ck(lib().ref_make_seqset(self.h))
+        else:
+            self._ck(lib().ref_make_seqset_file(self.h, os.fsencode(path)))
         return self.seqset_tables()
 
     def open_seqset_file(self, path):

@@ -352,7 +352,7 @@ int ref_seed(void* h, const char* bases, const int64_t* offs, int64_t n, const i
 
 // Stage 3: SEQSETMain::make_seqset (biograph_create.cpp:914-950): the four expander calls with the production
 // strides, build_chunks, make_seqset into an in-memory spiral file.
-int ref_make_seqset(void* h) {
+static int make_seqset_impl(void* h, const char* path) {
   auto* r = static_cast<ref_run*>(h);
   return guarded([&] {
     if (!r->entries) throw io_exception("ref_make_seqset: no entries (run ref_correct or ref_seed first)");
@@ -372,10 +372,25 @@ int ref_make_seqset(void* h) {
     b.build_chunks(entries, "complete", false);
     entries.partitions("complete", false, true);
     r->entries.reset();
-    r->create = make_unique<spiral_file_create_mem>();
-    r->ss = b.make_seqset(r->create->create());
+    if (path) {
+      // as SEQSETMain::make_seqset does: into a spiral FILE (biograph_create.cpp:943-946), then reopened
+      {
+        spiral_file_create_mmap c(path);
+        b.make_seqset(c.create());
+      }
+      r->open_mmap = make_unique<spiral_file_open_mmap>(path);
+      r->ss = make_unique<seqset>(r->open_mmap->open());
+    } else {
+      r->create = make_unique<spiral_file_create_mem>();
+      r->ss = b.make_seqset(r->create->create());
+    }
   });
 }
+
+int ref_make_seqset(void* h) { return make_seqset_impl(h, nullptr); }
+// the same, written by the reference's own spiral_file_create_mmap to `path` (a seqset file as `biograph create`
+// leaves it in <out>.bg/seqset), then reopened from there
+int ref_make_seqset_file(void* h, const char* path) { return make_seqset_impl(h, path); }
 
 // Opens a seqset spiral FILE with the reference's own reader (spiral_file_open_mmap + seqset::seqset(open state):
 // zip directory through the vendored minizip, part types and versions, bitcount / packed_varbit_vector members) --

@@ -148,3 +148,60 @@ def test_reference_reader_opens_the_facade_written_readmap(writer, tmp_path, is_
     assert np.array_equal(got["read_lengths"], t["read_lengths"].astype(np.int32))
     assert np.array_equal(got["is_forward"], t["is_forward"])
     assert np.array_equal(got["mate_loop_ptr"], t["mate_loop_ptr"])
+
+
+# ---- the other direction: files the REFERENCE wrote, read by the facade -------------------------------------------
+def _fnv(b):
+    h = 1469598103934665603
+    for x in bytes(b):
+        h = ((h ^ x) * 1099511628211) & 0xFFFFFFFFFFFFFFFF
+    return "%016x" % h
+
+
+@pytest.fixture(scope="module")
+def reader_exe(tmp_path_factory):
+    lib = os.path.join(ROOT, "biograph_b200")
+    if not os.path.exists(os.path.join(lib, "libbgx.so")):
+        pytest.fail("libbgx.so is missing: run __graft_entry__.build()")
+    exe = str(tmp_path_factory.mktemp("rd") / "spiral_reader_test")
+    subprocess.check_call(["g++", "-std=c++17", "-O1", "-I", os.path.join(ROOT, "include"),
+                           os.path.join(ROOT, "tests", "cpp", "spiral_reader_test.cpp"), "-o", exe, "-L", lib, "-lbgx", f"-Wl,-rpath,{lib}"])
+    return exe
+
+
+def test_facade_reader_opens_a_reference_written_seqset(reader_exe, writer, tmp_path):
+    """spiral_file_create_mmap (minizip, zip64 = 1, CRC fields unset) wrote it; spiral_file_reader / seqset_file -- what
+    bgx-merge opens its inputs with -- read it; and the facade's own writer frames the same members the same way"""
+    import json
+    reads = reads_of(6000, 4000, 100, 0.01, seed=71)
+    path = str(tmp_path / "ref_seqset")
+    with R.Run(2) as r:
+        solid = O.solid_set(O.count_kmers(reads, 30), 5)
+        cr = O.correct_reads(reads, solid, 30)
+        r.seed(O.corrected_list(cr))
+        t = r.make_seqset(path)          # written by the reference, reopened by the reference
+        uuid = r.seqset_uuid()
+    got = json.loads(subprocess.check_output([reader_exe, "seqset", path]))
+    words = (t["n"] + 63) // 64
+    assert got["n"] == t["n"] and got["uuid"] == uuid and got["max_read_len"] == int(t["sizes"].max())
+    assert got["sizes"] == _fnv(t["sizes"].astype("<u2").tobytes())
+    for b in range(4):
+        assert got[f"prev{b}"] == _fnv(t["prev"][b][:words].astype("<u8").tobytes())
+    # member for member: names in the reference's order, payload sizes, and the local-header framing of the
+    # facade's writer over the same tables (JSON texts differ in key order / build stamp, so compare payload members)
+    ref_members = json.loads(subprocess.check_output([reader_exe, "members", path]))
+    tables = str(tmp_path / "tables")
+    os.mkdir(tables)
+    ss = dict(t)
+    write_tables(tables, ss)
+    mine = str(tmp_path / "my_seqset")
+    subprocess.check_call([os.path.join(writer, "facade_write_test"), mine, uuid], env=dict(os.environ, BGX_MOCK_TABLES=tables),
+                          stdout=subprocess.DEVNULL)
+    my_members = json.loads(subprocess.check_output([reader_exe, "members", mine]))
+    assert [m["name"] for m in my_members] == [m["name"] for m in ref_members]
+    for a, b_ in zip(my_members, ref_members):
+        if not a["name"].endswith(".json"):
+            assert (a["size"], a["fnv"]) == (b_["size"], b_["fnv"]), a["name"]
+        # same distance from a member's local header to its data: same header layout incl. the ZIP64 extra field
+    gaps = lambda ms, raw: [m["offset"] - raw.rfind(b"PK\x03\x04", 0, m["offset"]) - len(m["name"]) for m in ms]  # noqa: E731
+    assert gaps(my_members, open(mine, "rb").read()) == gaps(ref_members, open(path, "rb").read())
