@@ -56,6 +56,7 @@ def lib():
         L.ref_readmap_rows.restype = C.c_int64
         L.ref_readmap_rows.argtypes = [C.c_char_p]
         L.ref_read_readmap_file.argtypes = [C.c_char_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_char_p]
+        L.ref_open_biograph.argtypes = [C.c_char_p, C.c_char_p, C.c_size_t]
         L.ref_merge.argtypes = [C.c_void_p, C.c_int, C.c_void_p]
         L.ref_mergemap.restype = C.c_int64
         L.ref_mergemap.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_void_p)]
@@ -250,6 +251,19 @@ class Run:
             sz = lib().ref_member_data(self.h, i, C.byref(p))
             out[lib().ref_member_name(self.h, i).decode()] = _view(p, sz, np.uint8).tobytes()
         return out
+
+
+def open_biograph(path):
+    """a whole .bg directory through the reference's own biograph_dir / seqset / readmap (as its consumers open one):
+    dict of what it sees (ids, entry and row counts, pair statistics)"""
+    buf = C.create_string_buffer(1 << 14)
+    if lib().ref_open_biograph(os.fsencode(path), buf, len(buf)):
+        raise RuntimeError("reference: " + lib().ref_last_error().decode())
+    out = {}
+    for line in buf.value.decode().splitlines():
+        k, _, v = line.partition("=")
+        out[k] = int(v) if v.isdigit() else v
+    return out
 
 
 def read_readmap_file(path):

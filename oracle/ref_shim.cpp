@@ -27,6 +27,7 @@
 #include <cstring>
 #include <map>
 #include <memory>
+#include <sstream>
 #include <mutex>
 #include <string>
 #include <thread>
@@ -34,6 +35,7 @@
 
 #include "modules/bio_base/fast_read_correct.h"
 #include "modules/bio_base/seqset.h"
+#include "modules/bio_base/biograph_dir.h"
 #include "modules/bio_base/corrected_read.h"
 #include "modules/bio_base/make_mergemap.h"
 #include "modules/bio_base/readmap.h"
@@ -435,6 +437,30 @@ int ref_read_readmap_file(const char* path, uint64_t* entry, int32_t* len, uint8
     std::string u = rm->metadata().seqset_uuid;
     strncpy(seqset_uuid_out, u.c_str(), 63);
     seqset_uuid_out[63] = 0;
+  });
+}
+
+// Opens a whole BioGraph directory the way the reference's consumers do (biograph_dir(path, READ_BGDIR): directory
+// layout + metadata/bg_info.json; seqset_file(bgdir.seqset()); readmap(seqset, bgdir.find_readmap(""))) -- the readmap
+// constructor CHECKs that readmap.json's seqset_uuid is the seqset's -- and reports what it sees as "key=value" lines.
+int ref_open_biograph(const char* path, char* out, size_t cap) {
+  return guarded([&] {
+    biograph_dir bg(path, READ_BGDIR);
+    auto ss = std::make_shared<seqset>(bg.seqset());
+    std::string rm_path = bg.find_readmap("");
+    readmap rm(ss, rm_path);
+    readmap::pair_stats ps = rm.get_pair_stats();
+    std::ostringstream os;
+    os << "biograph_id=" << bg.biograph_id() << "\naccession_id=" << bg.accession_id() << "\nversion=" << bg.get_metadata().version
+       << "\nsamples=" << bg.samples().size() << "\nsample_accession=" << bg.find_readmap_accession("")
+       << "\nreadmap_path=" << rm_path << "\nseqset_uuid=" << ss->uuid() << "\nseqset_entries=" << ss->size()
+       << "\nmax_read_len=" << ss->max_read_len() << "\nreadmap_rows=" << rm.size() << "\nreadmap_seqset_uuid="
+       << rm.metadata().seqset_uuid << "\nnum_bases=" << rm.get_num_bases() << "\npaired_reads=" << ps.paired_reads
+       << "\nunpaired_reads=" << ps.unpaired_reads << "\npaired_bases=" << ps.paired_bases << "\nunpaired_bases="
+       << ps.unpaired_bases << "\nmin_read_len=" << rm.min_read_len() << "\nreadmap_max_read_len=" << rm.max_read_len() << "\n";
+    std::string s = os.str();
+    if (s.size() + 1 > cap) throw io_exception("ref_open_biograph: buffer too small");
+    memcpy(out, s.c_str(), s.size() + 1);
   });
 }
 

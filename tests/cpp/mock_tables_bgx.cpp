@@ -1,8 +1,13 @@
-// mock_tables_bgx.cpp -- a stand-in for the C ABI that serves FINISHED seqset tables from raw files (written by the
-// test from the CPU oracle's result), so that bgx_bs::builder::make_seqset -- the facade's seqset spiral-file writer --
-// runs without a GPU.  The file it writes is then opened by the reference's OWN reader (oracle/_ref:
-// spiral_file_open_mmap + seqset), tests/test_ref_reads_facade_files.py.  Test infrastructure.
+// mock_tables_bgx.cpp -- a stand-in for the C ABI that serves FINISHED results from raw files (written by the test
+// from the CPU oracle's result), so that the HOST side of the drop-in -- the facade's spiral-file writers, and the whole
+// bgx-create executable with its .bg directory, metadata and stats -- runs without a GPU.  What it writes is then
+// opened by the reference's OWN readers (oracle/_ref: biograph_dir, spiral_file_open_mmap + seqset, readmap),
+// tests/test_ref_reads_facade_files.py.  Test infrastructure; installed as "libbgx.so" in a scratch directory and
+// put in front of the real one with LD_LIBRARY_PATH.
 //
+// The compute entry points (add reads, count, correct, build) succeed without doing anything; the exports serve:
+// km_kmers.bin / km_fwd.bin / km_rev.bin / km_flags.bin (every counted k-mer, ascending; filtered by min_count here),
+// cr_lens.bin (uint16 per read, 0 = dropped) / cr_bases.bin / cr_corr.bin (uint8 per read), stats.json (optional).
 // $BGX_MOCK_TABLES/: meta.txt = "num_entries max_entry_len prev_words sub_words acc_words sizes_bits sizes_max
 // shared_bits shared_max"; fixed.bin; prev_bits_<b>.bin, prev_sub_<b>.bin, prev_acc_<b>.bin (b = 0..3);
 // sizes_elements.bin, shared_elements.bin (uint64 words).
@@ -117,15 +122,57 @@ int bgx_merge_seqsets(bgx_ctx*, const bgx_seqset_part*, uint32_t, uint64_t) { re
 int bgx_export_mergemap(bgx_ctx*, uint32_t, uint64_t*[3], uint64_t*, uint64_t*) { return 1; }
 int bgx_migrate_bits(bgx_ctx*, uint32_t, const uint64_t*, uint64_t, uint64_t*[3], uint64_t*) { return 1; }
 int bgx_export_flat_ascii(bgx_ctx*, uint32_t, uint64_t, uint64_t, char**, uint64_t**) { return 1; }
-int bgx_add_reads_ascii(bgx_ctx*, const char*, const uint64_t*, uint64_t) { return 1; }
-int bgx_add_reads_fastq(bgx_ctx*, const char*, uint64_t, uint64_t*) { return 1; }
-int bgx_count_kmers(bgx_ctx*) { return 1; }
-int bgx_stats_json(bgx_ctx*, char* buf, size_t cap) { if (cap) buf[0] = 0; return 1; }
-int bgx_export_kmers(bgx_ctx*, uint32_t, uint64_t*, uint64_t**, uint32_t**, uint32_t**, uint8_t**) { return 1; }
+int bgx_add_reads_ascii(bgx_ctx*, const char*, const uint64_t*, uint64_t) { return 0; }
+int bgx_add_reads_fastq(bgx_ctx*, const char* text, uint64_t size, uint64_t* n_reads) {
+  uint64_t lines = 0;
+  for (uint64_t i = 0; i < size; ++i) lines += text[i] == '\n';
+  if (n_reads) *n_reads = lines / 4;
+  return 0;
+}
+int bgx_count_kmers(bgx_ctx*) { return 0; }
+int bgx_stats_json(bgx_ctx*, char* buf, size_t cap) {
+  std::vector<char> b;
+  if (!slurp("stats.json", &b)) b.assign({'{', '}'});
+  if (b.size() + 1 > cap) return 1;
+  memcpy(buf, b.data(), b.size());
+  buf[b.size()] = 0;
+  return 0;
+}
+int bgx_export_kmers(bgx_ctx*, uint32_t min_count, uint64_t* n, uint64_t** kmers, uint32_t** fwd, uint32_t** rev, uint8_t** flags) {
+  std::vector<char> k, f, r, fl;
+  if (!slurp("km_kmers.bin", &k) || !slurp("km_fwd.bin", &f) || !slurp("km_rev.bin", &r) || !slurp("km_flags.bin", &fl)) return 1;
+  const uint64_t total = k.size() / 8;
+  const uint64_t* K = (const uint64_t*)k.data();
+  const uint32_t *F = (const uint32_t*)f.data(), *R = (const uint32_t*)r.data();
+  uint64_t* ok = (uint64_t*)malloc(total * 8 + 8);
+  uint32_t *of = (uint32_t*)malloc(total * 4 + 4), *orv = (uint32_t*)malloc(total * 4 + 4);
+  uint8_t* ofl = (uint8_t*)malloc(total + 1);
+  uint64_t m = 0;
+  for (uint64_t i = 0; i < total; ++i)
+    if ((uint64_t)F[i] + R[i] >= min_count) { ok[m] = K[i]; of[m] = F[i]; orv[m] = R[i]; ofl[m] = (uint8_t)fl[i]; ++m; }
+  *n = m;
+  if (kmers) *kmers = ok; else free(ok);
+  if (fwd) *fwd = of; else free(of);
+  if (rev) *rev = orv; else free(orv);
+  if (flags) *flags = ofl; else free(ofl);
+  return 0;
+}
 int bgx_export_reads(bgx_ctx*, uint64_t*, uint16_t**, char**, uint64_t*) { return 1; }
-int bgx_correct(bgx_ctx*) { return 1; }
+int bgx_correct(bgx_ctx*) { return 0; }
 int bgx_seed_uncorrected(bgx_ctx*) { return 1; }
-int bgx_export_corrected(bgx_ctx*, uint64_t*, uint16_t**, char**, uint64_t*, uint8_t**, uint16_t**, uint16_t**) { return 1; }
+int bgx_export_corrected(bgx_ctx*, uint64_t* n_reads, uint16_t** lens, char** bases, uint64_t* n_bases, uint8_t** corrections,
+                         uint16_t** next_fwd, uint16_t** next_rev) {
+  std::vector<char> l, b, c;
+  if (!slurp("cr_lens.bin", &l) || !slurp("cr_bases.bin", &b) || !slurp("cr_corr.bin", &c)) return 1;
+  if (next_fwd || next_rev) { g_err = "mock: seed counts are not served"; return 1; }
+  auto dup = [](const std::vector<char>& v) { void* p = malloc(v.size() + 1); memcpy(p, v.data(), v.size()); return p; };
+  if (n_reads) *n_reads = l.size() / 2;
+  if (n_bases) *n_bases = b.size();
+  if (lens) *lens = (uint16_t*)dup(l);
+  if (bases) *bases = (char*)dup(b);
+  if (corrections) *corrections = (uint8_t*)dup(c);
+  return 0;
+}
 int bgx_dist_unique_id(uint8_t*) { return 1; }
 int bgx_dist_init(bgx_ctx*, int32_t, int32_t, const uint8_t*) { return 1; }
 }

@@ -205,3 +205,95 @@ def test_facade_reader_opens_a_reference_written_seqset(reader_exe, writer, tmp_
         # same distance from a member's local header to its data: same header layout incl. the ZIP64 extra field
     gaps = lambda ms, raw: [m["offset"] - raw.rfind(b"PK\x03\x04", 0, m["offset"]) - len(m["name"]) for m in ms]  # noqa: E731
     assert gaps(my_members, open(mine, "rb").read()) == gaps(ref_members, open(path, "rb").read())
+
+
+# ---- a whole .bg directory written by bgx-create, opened by the reference ------------------------------------------
+def _serve_create_results(d, reads, paired):
+    """everything bgx-create asks the device for, computed by the oracle and written where the mock C ABI reads it"""
+    import bisect
+
+    from oracle import readmap as RM
+    oc = O.count_kmers(reads, 30)
+    solid = O.solid_set(oc, 5)
+    cr = O.correct_reads(reads, solid, 30)
+    ss = O.seqset_closed_form((cr["seq"], cr["offs"]))
+    write_tables(d, ss)
+    oc["kmers"].astype(np.uint64).tofile(os.path.join(d, "km_kmers.bin"))
+    oc["fwd"].astype(np.uint32).tofile(os.path.join(d, "km_fwd.bin"))
+    oc["rev"].astype(np.uint32).tofile(os.path.join(d, "km_rev.bin"))
+    oc["flags"].astype(np.uint8).tofile(os.path.join(d, "km_flags.bin"))
+    lens = np.diff(cr["offs"]).astype(np.uint16)
+    lens.tofile(os.path.join(d, "cr_lens.bin"))
+    open(os.path.join(d, "cr_bases.bin"), "wb").write(cr["seq"])
+    cr["corrections"].astype(np.uint8).tofile(os.path.join(d, "cr_corr.bin"))
+    open(os.path.join(d, "stats.json"), "w").write('{"entries":%d,"entries_round1":%d,"walk_new_records":0}' % (ss["n"], ss["n"]))
+    # the readmap the device would build: entry of every kept read and of its reverse complement
+    seqs = [cr["seq"][cr["offs"][i]:cr["offs"][i + 1]].decode() for i in range(len(lens))]
+    ents = sorted(O.entries_closed_form_py([s for s in seqs if s]))
+    assert len(ents) == ss["n"]
+
+    def lookup(s):
+        i = bisect.bisect_left(ents, s)
+        assert ents[i].startswith(s)
+        return i
+
+    kept = lens > 0
+    fwd = [lookup(s) if k else 0 for s, k in zip(seqs, kept)]
+    rc = [lookup(O.revcomp(s)) if k else 0 for s, k in zip(seqs, kept)]
+    if paired:
+        t = RM.readmap_tables_paired(*RM.pair_records(fwd, rc, lens.astype(np.int64), kept), len(ents))
+    else:
+        t = RM.readmap_tables(np.asarray(fwd)[kept], np.asarray(rc)[kept], lens[kept].astype(np.int64), len(ents))
+    open(os.path.join(d, "rm_meta.txt"), "w").write(f"{t['n_rows']}\n")
+    t["read_lengths"].astype(np.uint16).tofile(os.path.join(d, "rm_lens.bin"))
+    t["mate_loop_ptr"].astype(np.uint64).tofile(os.path.join(d, "rm_ptr.bin"))
+    RM.pack_bits(t["is_forward"]).tofile(os.path.join(d, "rm_fwd.bin"))
+    for name, bits in (("src", t["source_to_mid"]), ("dst", t["dest_to_mid"])):
+        words = RM.pack_bits(bits)
+        sub, acc, _ = O.bitcount_finalize(words, len(bits))
+        for i, a in enumerate((words, sub, acc)):
+            a.tofile(os.path.join(d, f"rm_{name}_{i}.bin"))
+    return ss, cr, t, lens
+
+
+@pytest.mark.parametrize("paired", [False, True])
+def test_reference_opens_the_bg_directory_bgx_create_writes(writer, tmp_path, paired):
+    """bgx-create end to end on the host (flags, import, stages, seqset + readmap files, sha1-named readmap,
+    metadata/bg_info.json, qc/create_stats.json) with the device results served by the mock; then the reference's
+    biograph_dir + seqset + readmap open the directory as any of its tools would"""
+    import json
+    exe = os.path.join(ROOT, "biograph_b200", "bgx-create")
+    if not os.path.exists(exe):
+        pytest.fail("bgx-create is missing: run __graft_entry__.build()")
+    reads = reads_of(7000, 4000, 100, 0.01, seed=81)
+    d = str(tmp_path / "served")
+    os.mkdir(d)
+    ss, cr, t, lens = _serve_create_results(d, reads, paired)
+    fq = tmp_path / "reads.fastq"
+    fq.write_text("".join(f"@r{i}/{1 + i % 2}\n{r}\n+\n{'I' * len(r)}\n" for i, r in enumerate(reads)))
+    out = str(tmp_path / "sample1.bg")
+    env = dict(os.environ, BGX_MOCK_TABLES=d, LD_LIBRARY_PATH=writer + os.pathsep + os.environ.get("LD_LIBRARY_PATH", ""))
+    cmd = [exe, "--reads", str(fq), "--out", out, "--id", "NA0001"] + (["--interleaved"] if paired else [])
+    run = subprocess.run(cmd, env=env, capture_output=True, text=True)
+    assert run.returncode == 0, run.stderr[-2000:]
+    assert "mock-tables" in open(os.path.join(out, "qc", "create_log.txt")).read()   # the mock was the library in use
+    bg = R.open_biograph(out)
+    n_kept = int((lens > 0).sum())
+    assert bg["accession_id"] == "NA0001" and bg["sample_accession"] == "NA0001" and bg["samples"] == 1
+    assert bg["biograph_id"] == bg["seqset_uuid"] == bg["readmap_seqset_uuid"] and len(bg["biograph_id"]) == 36
+    assert bg["seqset_entries"] == ss["n"] and bg["max_read_len"] == int(ss["sizes"].max())
+    assert bg["readmap_rows"] == t["n_rows"] == 2 * n_kept
+    assert bg["num_bases"] == int(lens.sum())
+    if paired:
+        both = int(np.sum((lens[0::2] > 0) & (lens[1::2] > 0)))
+        assert bg["paired_reads"] == 2 * both and bg["unpaired_reads"] == n_kept - 2 * both
+    else:
+        assert bg["paired_reads"] == 0 and bg["unpaired_reads"] == n_kept
+    assert bg["readmap_max_read_len"] == int(lens.max()) and bg["min_read_len"] == int(lens[lens > 0].min())
+    # the readmap is named by its sha1 and listed under the accession id (biograph_create.cpp:827-828,798)
+    import hashlib
+    sha = os.path.basename(bg["readmap_path"])[:-len(".readmap")]
+    assert hashlib.sha1(open(bg["readmap_path"], "rb").read()).hexdigest() == sha
+    st = json.load(open(os.path.join(out, "qc", "create_stats.json")))
+    assert st["imported_reads"] == len(reads) and st["corrected_reads"] == n_kept and st["corrected_bases"] == int(lens.sum())
+    assert st["entries"] == ss["n"] and st["uuid"] == bg["biograph_id"]

@@ -1,0 +1,82 @@
+"""One-off (CPU only, minutes): the restated oracle against oracle/_ref -- the reference's OWN classes compiled from
+its sources -- over a WHOLE bench workload, every stage output.  bench.py checks the CUDA path against the oracle
+over the whole workload on the GPU box; this closes the chain at the same size: CUDA path == oracle == reference.
+
+  python tools/ref_full_workload.py ecoli100x > profiles/r2u_oracle_vs_reference_ecoli100x.json
+"""
+import hashlib
+import json
+import os
+import sys
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import bench  # noqa: E402
+from biograph_b200 import synth  # noqa: E402
+from oracle import oracle as O  # noqa: E402
+from oracle import ref as R  # noqa: E402
+
+
+def sha(a):
+    a = np.ascontiguousarray(a)
+    return hashlib.sha256(a.view(np.uint8).reshape(-1).data if a.size else b"").hexdigest()[:16]
+
+
+def main():
+    name = sys.argv[1] if len(sys.argv) > 1 else "ecoli100x"
+    reads_override = int(sys.argv[2]) if len(sys.argv) > 2 else None
+    threads = bench.host_threads()
+    reads = bench.make_workload(name, 0, reads_override)
+    cov = bench.WORKLOADS[name]["coverage"]
+    buf, offs = synth.as_buffer(reads)
+    rb = (buf.tobytes(), offs)
+    del buf
+    t0 = time.perf_counter()
+    with R.Run(threads) as r:
+        counts, solid = r.count_kmers(rb, 30, 5, genome_bases=max(1, reads.size // cov))
+        t1 = time.perf_counter()
+        rcr = r.correct(rb, 8, 2, 0.7)
+        t2 = time.perf_counter()
+        rss = r.make_seqset()
+        t3 = time.perf_counter()
+    oc = O.count_kmers(rb, 30, threads=threads, prefilter_min=5)
+    osol = O.solid_set(oc, 5)
+    del oc
+    ocr = O.correct_reads(rb, osol, 30, 8, 2, 0.7, threads=threads)
+    oss = O.seqset_staged((ocr["seq"], ocr["offs"]), ocr["next_fwd"], ocr["next_rev"], threads=threads)
+    t4 = time.perf_counter()
+    mism = []
+    m = (counts["fwd"].astype(np.int64) + counts["rev"]) >= 5
+    if not np.array_equal(solid["kmers"], osol["kmers"]):
+        mism.append("solid/kmers")
+    for f in ("kmers", "fwd", "rev", "flags"):
+        if not np.array_equal(counts[f][m], osol[f]):
+            mism.append("counts/" + f)
+    if rcr["seq"] != ocr["seq"]:
+        mism.append("corrected/bases")
+    for f in ("offs", "kept"):
+        if not np.array_equal(rcr[f], ocr[f]):
+            mism.append("corrected/" + f)
+    if rss["n"] != oss["n"]:
+        mism.append("seqset/num_entries")
+    digests = {"solid_kmers": sha(osol["kmers"]), "solid_counts": sha(np.stack([osol["fwd"], osol["rev"]])),
+               "corrected_bases": sha(np.frombuffer(ocr["seq"], dtype=np.uint8))}
+    for t in ("sizes", "shared", "prev", "fixed"):
+        digests["seqset/" + t] = sha(oss[t])
+        if not np.array_equal(rss[t], oss[t]):
+            mism.append("seqset/" + t)
+    print(json.dumps({
+        "what": "oracle port vs oracle/_ref (the reference's own classes) over a whole bench workload, CPU only",
+        "workload": name, "reads": int(reads.shape[0]), "read_len": int(reads.shape[1]), "bases": int(reads.size),
+        "host_threads": threads, "solid_kmers": int(len(osol["kmers"])), "corrected_reads": int(ocr["kept"].sum()),
+        "entries": int(oss["n"]), "equal": not mism, "mismatches": mism, "sha256_16_oracle": digests,
+        "reference_seconds": {"count": round(t1 - t0, 1), "correct": round(t2 - t1, 1), "seqset": round(t3 - t2, 1),
+                              "total": round(t3 - t0, 1), "bases_per_s": reads.size / (t3 - t0)},
+        "oracle_port_seconds": round(t4 - t3, 1)}))
+
+
+if __name__ == "__main__":
+    main()
