@@ -228,6 +228,25 @@ def verify_sample_against_reference(B, device, sub, ref):
         return {"checked": False, "error": f"{type(e).__name__}: {e}"[:300]}
 
 
+def reference_full_workload_digests(workload, parity):
+    """The reference's own code over the WHOLE workload takes minutes on a CPU, so it was run once in the development
+    container (tools/ref_full_workload.py) and its per-member digests committed under profiles/: equal digests = equal
+    bytes.  Returns the comparison for the bench line (None: no committed digests for this workload)."""
+    try:
+        rf = os.path.join(ROOT, "profiles", f"r2u_oracle_vs_reference_{workload}.json")
+        if not os.path.exists(rf):
+            return None
+        rj = json.load(open(rf))
+        want = rj["sha256_16_reference"]
+        diff = sorted(k_ for k_ in want if parity["sha256_16"].get(k_) != want[k_])
+        return {"against": "oracle/_ref (the reference's own classes) over the whole workload; digests committed in "
+                           + os.path.relpath(rf, ROOT), "reads": rj["reads"], "entries": rj["entries"],
+                "digests_compared": len(want), "digests_equal": not diff and rj["entries"] == parity["entries"],
+                "differing": diff}
+    except Exception as e:  # noqa: BLE001
+        return {"digests_equal": None, "error": f"{type(e).__name__}: {e}"[:300]}
+
+
 def sha(a):
     import hashlib
     a = np.ascontiguousarray(a)
@@ -590,6 +609,10 @@ def main():
                "sample": f"the whole workload ({n_reads} reads) once, whole path (2-stage count + correct + staged "
                          f"seqset), {dt:.1f} s; oracle port (the restated CPU path); this run is "
                          "also the parity check"}
+        if args.reads is None:
+            rfw = reference_full_workload_digests(args.workload, parity)
+            if rfw is not None:
+                parity["reference_full_workload"] = rfw
         if reference_available() and not args.no_cpu_baseline:
             # the reference's own code on a bounded sample: the CPU baseline proper, and a second parity anchor
             try:

@@ -62,17 +62,25 @@ def main():
             mism.append("corrected/" + f)
     if rss["n"] != oss["n"]:
         mism.append("seqset/num_entries")
-    digests = {"solid_kmers": sha(osol["kmers"]), "solid_counts": sha(np.stack([osol["fwd"], osol["rev"]])),
-               "corrected_bases": sha(np.frombuffer(ocr["seq"], dtype=np.uint8))}
     for t in ("sizes", "shared", "prev", "fixed"):
-        digests["seqset/" + t] = sha(oss[t])
         if not np.array_equal(rss[t], oss[t]):
             mism.append("seqset/" + t)
+    # digests of the REFERENCE's output, under the names and in the forms bench.py's `parity.sha256_16` uses for the
+    # CUDA path's output on the GPU box: equal digests = equal bytes, without the two ever meeting on one machine
+    digests = {"solid_kmers": sha(counts["kmers"][m]), "solid_counts": sha(np.stack([counts["fwd"][m], counts["rev"][m]])),
+               "corrected_bases": sha(np.frombuffer(rcr["seq"], dtype=np.uint8))}
+    rss["subaccum"], rss["accum"] = [], []
+    for b in range(4):
+        sub, acc, _ = O.bitcount_finalize(rss["prev"][b], rss["n"])
+        rss["subaccum"].append(sub)
+        rss["accum"].append(acc)
+    for name, a in bench.seqset_members(rss):
+        digests["seqset/" + name] = sha(a)
     print(json.dumps({
         "what": "oracle port vs oracle/_ref (the reference's own classes) over a whole bench workload, CPU only",
         "workload": name, "reads": int(reads.shape[0]), "read_len": int(reads.shape[1]), "bases": int(reads.size),
         "host_threads": threads, "solid_kmers": int(len(osol["kmers"])), "corrected_reads": int(ocr["kept"].sum()),
-        "entries": int(oss["n"]), "equal": not mism, "mismatches": mism, "sha256_16_oracle": digests,
+        "entries": int(oss["n"]), "equal": not mism, "mismatches": mism, "sha256_16_reference": digests,
         "reference_seconds": {"count": round(t1 - t0, 1), "correct": round(t2 - t1, 1), "seqset": round(t3 - t2, 1),
                               "total": round(t3 - t0, 1), "bases_per_s": reads.size / (t3 - t0)},
         "oracle_port_seconds": round(t4 - t3, 1)}))
