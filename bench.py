@@ -234,7 +234,7 @@ def reference_full_workload_digests(workload, parity):
     bytes.  Returns the comparison for the bench line (None: no committed digests for this workload)."""
     try:
         rf = os.path.join(ROOT, "profiles", f"r2u_oracle_vs_reference_{workload}.json")
-        if not os.path.exists(rf):
+        if not os.path.exists(rf) or os.path.getsize(rf) == 0:
             return None
         rj = json.load(open(rf))
         want = rj["sha256_16_reference"]
