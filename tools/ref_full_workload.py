@@ -74,8 +74,8 @@ def main():
         sub, acc, _ = O.bitcount_finalize(rss["prev"][b], rss["n"])
         rss["subaccum"].append(sub)
         rss["accum"].append(acc)
-    for name, a in bench.seqset_members(rss):
-        digests["seqset/" + name] = sha(a)
+    for member, a in bench.seqset_members(rss):
+        digests["seqset/" + member] = sha(a)
     print(json.dumps({
         "what": "oracle port vs oracle/_ref (the reference's own classes) over a whole bench workload, CPU only",
         "workload": name, "reads": int(reads.shape[0]), "read_len": int(reads.shape[1]), "bases": int(reads.size),
