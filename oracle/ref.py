@@ -58,6 +58,7 @@ def lib():
         L.ref_read_readmap_file.argtypes = [C.c_char_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_char_p]
         L.ref_open_biograph.argtypes = [C.c_char_p, C.c_char_p, C.c_size_t]
         L.ref_merge.argtypes = [C.c_void_p, C.c_int, C.c_void_p]
+        L.ref_fast_migrate.argtypes = [C.c_void_p, C.c_int, C.c_char_p, C.c_char_p]
         L.ref_mergemap.restype = C.c_int64
         L.ref_mergemap.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_void_p)]
         L.ref_flat.argtypes = [C.c_void_p, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), C.POINTER(C.c_int64)]
@@ -88,6 +89,20 @@ def _pack(reads):
     if bs:
         np.cumsum([len(b) for b in bs], out=offs[1:])
     return b"".join(bs), offs
+
+
+def _zip_members(path):
+    """{member path: bytes} of a spiral file (stored zip members, read by offset: the reference leaves the CRC fields unset)"""
+    import struct
+    import zipfile
+    raw = open(path, "rb").read()
+    out = {}
+    for info in zipfile.ZipFile(path).infolist():
+        o = info.header_offset
+        sig, _, _, comp, _, _, _, _, _, nl, el = struct.unpack("<IHHHHHIIIHH", raw[o:o + 30])
+        assert sig == 0x04034B50 and comp == 0
+        out[info.filename] = raw[o + 30 + nl + el:o + 30 + nl + el + info.file_size]
+    return out
 
 
 def fast_read_correct(read, solid_kmers, k, max_corrections=2, min_good_run=2):
@@ -217,28 +232,25 @@ class Run:
                                          fixed.ctypes.data, stats.ctypes.data))
         return {"n": int(n), "sizes": sizes, "shared": shared, "prev": prev, "fixed": fixed, "stats": stats}
 
-    def make_readmap(self, reads, rec_offs, is_paired):
+    def fast_migrate(self, input_index, old_readmap_path, new_readmap_path):
+        """make_readmap::fast_migrate: the readmap file of merge input `input_index` onto this (merged) run's seqset;
+        returns {member path: bytes} of the new file"""
+        self._ck(lib().ref_fast_migrate(self.h, input_index, os.fsencode(old_readmap_path), os.fsencode(new_readmap_path)))
+        return _zip_members(new_readmap_path)
+
+    def make_readmap(self, reads, rec_offs, is_paired, keep_path=None):
         """make_readmap::do_make over the seqset just built (call before members()).  reads: the corrected reads;
         rec_offs[n_rec + 1]: record r holds reads [rec_offs[r], rec_offs[r + 1]) -- one read or two mates, as the
         corrected_reads stream holds them.  Returns {member path: bytes} of the readmap spiral file the reference
         wrote (stored zip members, read by offset: the reference leaves the CRC fields unset)."""
-        import struct
-        import zipfile
         buf, offs = _pack(reads)
         ro = np.ascontiguousarray(rec_offs, dtype=np.int64)
-        path = os.path.join(self.tmp, "ref.readmap")
+        path = keep_path or os.path.join(self.tmp, "ref.readmap")
         if os.path.exists(path):
             os.unlink(path)
-        self._ck(lib().ref_make_readmap(self.h, path.encode(), buf, offs.ctypes.data, ro.ctypes.data, len(ro) - 1,
+        self._ck(lib().ref_make_readmap(self.h, os.fsencode(path), buf, offs.ctypes.data, ro.ctypes.data, len(ro) - 1,
                                         1 if is_paired else 0))
-        raw = open(path, "rb").read()
-        out = {}
-        for info in zipfile.ZipFile(path).infolist():
-            o = info.header_offset
-            sig, _, _, comp, _, _, _, _, _, nl, el = struct.unpack("<IHHHHHIIIHH", raw[o:o + 30])
-            assert sig == 0x04034B50 and comp == 0
-            out[info.filename] = raw[o + 30 + nl + el:o + 30 + nl + el + info.file_size]
-        return out
+        return _zip_members(path)
 
     def members(self):
         """{member path: bytes} of the in-memory seqset spiral file, as the reference's encoders wrote them."""

@@ -97,6 +97,7 @@ struct ref_run {
   std::vector<std::string> member_names;
   // merge: one bit vector over the merged entries per input (bit x: merged entry x comes from this input)
   std::vector<std::vector<uint64_t>> mergemaps;
+  std::vector<std::unique_ptr<seqset_mergemap>> mergemap_objs;  // kept for ref_fast_migrate
 };
 
 template <class F>
@@ -542,7 +543,8 @@ int ref_merge(void** ins, int n_in, void* out) {
     make_mergemap mm(flat_ptrs);
     mm.build();
     size_t total = mm.total_merged_entries();
-    std::vector<std::unique_ptr<seqset_mergemap>> maps;
+    std::vector<std::unique_ptr<seqset_mergemap>>& maps = o->mergemap_objs;
+    maps.clear();
     std::vector<const seqset_mergemap*> map_ptrs;
     o->mergemaps.clear();
     for (int i = 0; i < n_in; ++i) {
@@ -567,6 +569,17 @@ int ref_merge(void** ins, int n_in, void* out) {
     for (auto& kv : o->storage.paths) o->member_names.push_back(kv.first);
     spiral_file_open_mem op(o->storage);
     o->ss = make_unique<seqset>(op.open());
+  });
+}
+// make_readmap::fast_migrate (modules/bio_mapred/make_readmap.cpp:459-520, as MergeSEQSETMain runs it per sample,
+// biograph_merge.cpp:291-312): the readmap FILE of input `input` moves to the merged seqset of `h` (after ref_merge).
+int ref_fast_migrate(void* h, int input, const char* old_readmap_path, const char* new_readmap_path) {
+  auto* r = static_cast<ref_run*>(h);
+  return guarded([&] {
+    if (input < 0 || size_t(input) >= r->mergemap_objs.size()) throw io_exception("ref_fast_migrate: no such input");
+    std::unique_ptr<readmap> old_rm = readmap::open_anonymous_readmap(old_readmap_path);
+    spiral_file_create_mmap c(new_readmap_path);
+    make_readmap::fast_migrate(*old_rm, *r->mergemap_objs[size_t(input)], c.create());
   });
 }
 int64_t ref_mergemap(void* h, int input, const uint64_t** bits) {

@@ -101,3 +101,45 @@ def test_merge_beyond_parallel_splits():
     # and the prev bit of a candidate lands on the first entry OF THE CHUNK that holds the last entry it prefixes
     tab = merge_case(read_sets(21, 2, 16000, 130000, 60, err=0.05), literal=False)
     assert tab["n"] > 2 * M.K_PARALLEL_SPLITS
+
+
+def test_fast_migrate_on_the_reference(tmp_path):
+    """make_readmap::fast_migrate through the reference's own code: each input's readmap (written by the reference's
+    make_readmap) moved onto the merged seqset; the oracle's migrate_source_bits gives the new source bits, every
+    other payload member is carried over unchanged, and the migrated file opens against the merged seqset"""
+    sets = read_sets(31, 2, 250, 2000, 45)
+    runs = [R.Run(2) for _ in sets]
+    out = R.Run(2)
+    try:
+        old_members, ents = [], []
+        for p, (r, rd) in enumerate(zip(runs, sets)):
+            r.seed(rd)
+            r.make_seqset()
+            ents.append(r.flat())
+            old_members.append(r.make_readmap(rd, list(range(len(rd) + 1)), False, keep_path=str(tmp_path / f"in{p}.readmap")))
+        tab, maps = out.merge_from(runs)
+        merged, bits = M.make_mergemap(ents)
+        for p in range(len(sets)):
+            new = out.fast_migrate(p, str(tmp_path / f"in{p}.readmap"), str(tmp_path / f"out{p}.readmap"))
+            old = old_members[p]
+            old_src = np.unpackbits(np.frombuffer(old["read_ids/source_to_mid/bits"], dtype=np.uint8), bitorder="little")[:len(ents[p])]
+            want = words(M.migrate_source_bits(old_src, bits[p]))
+            got = np.frombuffer(new["read_ids/source_to_mid/bits"], dtype=np.uint64)
+            n = min(len(got), len(want))
+            assert np.array_equal(got[:n], want[:n]) and not got[n:].any() and not want[n:].any()
+            sub, acc, _ = O.bitcount_finalize(want, len(merged))
+            assert np.array_equal(np.frombuffer(new["read_ids/source_to_mid/subaccum"], dtype=np.uint64), sub)
+            assert np.array_equal(np.frombuffer(new["read_ids/source_to_mid/accum"], dtype=np.uint64), acc)
+            for name in ("read_ids/dest_to_mid/bits", "read_ids/dest_to_mid/subaccum", "read_ids/dest_to_mid/accum",
+                         "read_lengths/elements", "mate_loop_ptr/elements", "is_forward/packed_data"):
+                assert new[name] == old[name], name
+            # every read still points at its own sequence: row i's entry in the merged seqset starts with the read
+            rows = R.read_readmap_file(str(tmp_path / f"out{p}.readmap"))
+            old_rows = R.read_readmap_file(str(tmp_path / f"in{p}.readmap"))
+            for i in range(0, len(rows["entry_id"]), 7):
+                a = merged[int(rows["entry_id"][i])][:int(rows["read_lengths"][i])]
+                b = ents[p][int(old_rows["entry_id"][i])][:int(old_rows["read_lengths"][i])]
+                assert a == b
+    finally:
+        for r in runs + [out]:
+            r.close()
