@@ -182,6 +182,17 @@ def cpu_ref_run(reads2d, threads, coverage, k=30, keep=False):
     return t3 - t0, ss["n"], st
 
 
+def arm_config(workload, n_reads, read_len, world):
+    """`config` of the JSON line: the job both arms are measured on (the reference arm prints the same dict, as the
+    contract asks: "on your arm's config"; how ITS run was parallelised is in `host_parallelism`)"""
+    return {"workload": workload, "reads_per_gpu": int(n_reads), "read_len": int(read_len),
+            "bases_per_gpu": int(n_reads) * int(read_len), "kmer_size": 30,
+            "parallelism": (f"one sharded build over {world} GPUs: reads split by rank ({world} genomes of this size), k-mers "
+                            "routed by hash partition, suffix records by prefix range (NCCL all-to-all)")
+            if world > 1 else "1 gpu",
+            "l2": "flushed between steps (256 MiB memset); working set >> L2"}
+
+
 def reference_available():
     try:
         from oracle import ref as R
@@ -348,9 +359,8 @@ def run_reference(args):
     line = {"impl": "reference", "metric": "input bases/sec to finished seqset", "value": val, "unit": "bases/s",
             "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u64", "data": "synthetic",
-            "config": {"workload": args.workload, "reads_per_gpu": int(total), "read_len": int(reads.shape[1]),
-                       "bases_per_gpu": int(total) * int(reads.shape[1]), "kmer_size": 30,
-                       "parallelism": f"{threads} host threads (CPU path; no GPU)"},
+            "config": arm_config(args.workload, total, reads.shape[1], args.gpus),
+            "host_parallelism": f"{threads} host threads (CPU path; no GPU)",
             "cpu_baseline": {"value": val, "unit": "bases/s", "cores": threads, "kind": "reference" if use_ref else "port",
                              "sample": f"{sample} reads at the workload's coverage over a genome prefix "
                                        f"(workload has {total}), whole path (2-stage count + correct + expand/sort/dedup "
@@ -647,12 +657,8 @@ def main():
             "metric": "input bases/sec to finished seqset", "value": value, "unit": "bases/s", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "u64", "data": "synthetic",
-            "config": {"workload": args.workload, "reads_per_gpu": int(n_reads), "read_len": int(read_len),
-                       "bases_per_gpu": bases, "kmer_size": 30, "entries": ss_n,
-                       "parallelism": (f"one sharded build over {world} GPUs: reads split by rank ({world} genomes of this size), k-mers "
-                                       "routed by hash partition, suffix records by prefix range (NCCL all-to-all)")
-                       if world > 1 else "1 gpu",
-                       "l2": "flushed between steps (256 MiB memset); working set >> L2"},
+            "config": arm_config(args.workload, n_reads, read_len, world),
+            "entries": ss_n,
             "e2e": {"value": e2e_val, "unit": "bases/s", "ms_per_step": e2e_ms_step, "h2d_bytes_per_step": int(h2d),
                     "d2h_bytes_per_step": int(d2h)},
             "gpu_launches": int(launches),

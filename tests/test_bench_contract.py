@@ -22,6 +22,10 @@ def test_reference_arm_line():
     assert line["impl"] == "reference" and line["metric"] == "input bases/sec to finished seqset" and line["unit"] == "bases/s"
     assert line["higher_is_better"] is True and line["vs_baseline"] is None and line["value"] > 0
     assert line["config"]["workload"] == "ecoli100x"
+    # the same `config` dict as the GPU arm prints for this job (r2l_bench_ecoli100x.json: 3 292 614 reads of 150 bases)
+    sys.path.insert(0, ROOT)
+    import bench
+    assert line["config"] == bench.arm_config("ecoli100x", 3292614, 150, 1) and "host threads" in line["host_parallelism"]
     assert line["e2e"] == {"value": line["value"], "unit": "bases/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
     cb = line["cpu_baseline"]
     # the reference's own classes where oracle/_ref was built (development container; travels to the GPU box), else the port
