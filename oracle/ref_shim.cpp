@@ -6,19 +6,27 @@
 // `cpu_baseline.kind = "reference"` arm of bench.py.
 //
 // What is the reference's and what is not: every class used below (kmer_counter, kmer_set, correct_reads,
-// fast_read_correct, part_repo, expander, builder, seqset, bitcount, packed_varbit_vector, spiral_file_create_mem)
-// is compiled unmodified from /root/reference/modules/**.  The reference's Bazel build and its third-party
-// libraries (Boost, glog, json_spirit, msgpack, htslib) are absent from this image; oracle/ref_stubs/ holds minimal
-// stand-ins for the few headers of those that the leaf sources include.  The code in THIS file only restates the
-// driver sequence of SEQSETMain::run (modules/biograph/biograph_create.cpp:665-779, 835-950) and of kmerizer::run
-// (modules/bio_mapred/kmerize_bf.cpp:267-430) -- the parts of them that call the classes above -- because those two
-// functions themselves read the map-reduce temp files (manifests, msgpack kv streams) that are out of scope.
-//   * import: every read is handed to prob_pass_processor::add as read_importer_state::process does
-//     (modules/biograph/biograph_create.cpp:119-151); reads are kept in memory instead of the msgpack temp files.
-//   * k-mer filter: tot_count >= min_count and the strand-skew cut of kmer_passes with the defaults of
-//     kmerize_bf_params (modules/bio_mapred/kmerize_bf.cpp:290-318); the overrepresentation filter is off
-//     (overrep threshold 0 disables it there too).
-//   * the reference genome as a compression dictionary (add_initial_repo) is not used: result-invisible.
+// fast_read_correct, part_repo, expander, builder, seqset, bitcount, packed_varbit_vector, sparse_multi, make_readmap,
+// readmap, seqset_flat, make_mergemap, seqset_mergemap, seqset_merger, biograph_dir, spiral_file_create_mem / _mmap,
+// spiral_file_open_mem / _mmap) is compiled unmodified from /root/reference/modules/**.  The reference's Bazel build
+// and its third-party libraries (Boost, glog, json_spirit, msgpack, htslib) are absent from this image;
+// oracle/ref_stubs/ holds minimal stand-ins for the few headers of those that the leaf sources include.  The code in
+// THIS file only restates DRIVER sequences -- which class is called when, with the CLI's defaults -- because the
+// functions that hold them in the reference read the map-reduce temp files (manifests, msgpack kv streams) that are
+// out of scope:
+//   * ref_count_kmers / ref_correct / ref_make_seqset: SEQSETMain::run (modules/biograph/biograph_create.cpp:665-779,
+//     835-950) and kmerizer::run (modules/bio_mapred/kmerize_bf.cpp:267-430).
+//       - import: every read is handed to prob_pass_processor::add as read_importer_state::process does
+//         (biograph_create.cpp:119-151); reads are kept in memory instead of the msgpack temp files.
+//       - k-mer filter: tot_count >= min_count and the strand-skew cut of kmer_passes with the defaults of
+//         kmerize_bf_params (kmerize_bf.cpp:290-318); the overrepresentation filter is off (threshold 0 disables it
+//         there too).
+//       - the reference genome as a compression dictionary (add_initial_repo) is not used: result-invisible.
+//   * ref_make_readmap: make_readmap::do_make as SEQSETMain::do_readmap calls it (biograph_create.cpp:818-826); the
+//     corrected-read records reach it through the in-memory manifest stand-in.
+//   * ref_merge / ref_fast_migrate: MergeSEQSETMain (modules/biograph/biograph_merge.cpp:196-312) through in-memory
+//     spiral files.
+//   * ref_open_seqset_file / ref_read_readmap_file / ref_open_biograph: the reference's readers on files that bgx wrote.
 #include <atomic>
 #include <chrono>
 #include <cstdio>
