@@ -193,6 +193,45 @@ def arm_config(workload, n_reads, read_len, world):
             "l2": "flushed between steps (256 MiB memset); working set >> L2"}
 
 
+def cpu_ref_run_isolated(workload, sample_reads, threads, coverage):
+    """cpu_ref_run(keep=True) in a child process (`bench.py --_ref-sample`): the reference's code CHECK-fails by
+    design where it finds something it does not expect, and that must not take the bench line with it.  The child
+    regenerates the (deterministic) sample, runs the reference's classes and leaves what the parity check needs in an
+    .npz.  Returns (seconds, entries, stage seconds, results) like cpu_ref_run."""
+    import subprocess
+    import tempfile
+    with tempfile.TemporaryDirectory(prefix="bgx_bench_ref_") as d:
+        out = os.path.join(d, "ref.npz")
+        cmd = [sys.executable, os.path.abspath(__file__), "--_ref-sample", out, "--workload", workload,
+               "--cpu-sample-reads", str(sample_reads), "--_threads", str(threads)]
+        r = subprocess.run(cmd, capture_output=True, text=True, timeout=1800)
+        if r.returncode != 0 or not os.path.exists(out):
+            raise RuntimeError(f"reference sample run failed (rc {r.returncode}): {r.stderr[-300:]}")
+        z = np.load(out)
+        meta = json.loads(str(z["meta"]))
+        res = {"counts": {f: z["c_" + f] for f in ("kmers", "fwd", "rev", "flags")},
+               "solid": {"kmers": z["s_kmers"], "flags": z["s_flags"]},
+               "corrected": {"seq": z["cr_seq"].tobytes(), "offs": z["cr_offs"], "kept": z["cr_kept"]},
+               "seqset": {"n": int(meta["entries"]), "sizes": z["ss_sizes"], "shared": z["ss_shared"], "prev": z["ss_prev"],
+                          "fixed": z["ss_fixed"]}}
+        return meta["seconds"], int(meta["entries"]), meta["stage_s"], res
+
+
+def ref_sample_child(args):
+    """the child of cpu_ref_run_isolated"""
+    w = WORKLOADS[args.workload]
+    sub = make_workload(args.workload, 0, None, genome_prefix_reads=args.cpu_sample_reads)
+    dt, n_ent, stage, res = cpu_ref_run(sub, args._threads or host_threads(), w["coverage"], keep=True)
+    c = res["counts"]
+    m = (c["fwd"].astype(np.int64) + c["rev"]) >= 5   # the parity check reads the solid part only
+    np.savez(args._ref_sample, meta=json.dumps({"seconds": dt, "entries": int(n_ent), "stage_s": stage}),
+             c_kmers=c["kmers"][m], c_fwd=c["fwd"][m], c_rev=c["rev"][m], c_flags=c["flags"][m],
+             s_kmers=res["solid"]["kmers"], s_flags=res["solid"]["flags"],
+             cr_seq=np.frombuffer(res["corrected"]["seq"], dtype=np.uint8), cr_offs=res["corrected"]["offs"],
+             cr_kept=res["corrected"]["kept"], ss_sizes=res["seqset"]["sizes"], ss_shared=res["seqset"]["shared"],
+             ss_prev=res["seqset"]["prev"], ss_fixed=res["seqset"]["fixed"])
+
+
 def reference_available():
     try:
         from oracle import ref as R
@@ -439,7 +478,11 @@ def main():
     ap.add_argument("--reads", type=int, default=None, help="override the read count (debug)")
     ap.add_argument("--cpu-sample-reads", type=int, default=600000)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--_ref-sample", dest="_ref_sample", default=None, help=argparse.SUPPRESS)
+    ap.add_argument("--_threads", dest="_threads", type=int, default=0, help=argparse.SUPPRESS)
     args = ap.parse_args()
+    if args._ref_sample:
+        return ref_sample_child(args)
     if args.impl == "reference":
         return run_reference(args)
 
@@ -628,7 +671,7 @@ def main():
             try:
                 cov = WORKLOADS[args.workload]["coverage"]
                 sub = make_workload(args.workload, 0, None, genome_prefix_reads=min(n_reads, args.cpu_sample_reads))
-                rdt, r_ent, rstage, rres = cpu_ref_run(sub, threads, cov, keep=True)
+                rdt, r_ent, rstage, rres = cpu_ref_run_isolated(args.workload, sub.shape[0], threads, cov)
                 cpu = {"value": sub.size / rdt, "unit": "bases/s", "cores": threads, "kind": "reference",
                        "same_config": False, "entries": int(r_ent), "stage_s": rstage,
                        "sample": f"{sub.shape[0]} reads at the workload's coverage over a genome prefix (workload has "

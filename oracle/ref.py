@@ -20,7 +20,14 @@ _lib = None
 
 
 def available():
-    return os.path.exists(LIB)
+    """the library was built (development container) and loads here"""
+    if not os.path.exists(LIB):
+        return False
+    try:
+        lib()
+        return True
+    except OSError:
+        return False
 
 
 def lib():

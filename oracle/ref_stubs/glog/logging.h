@@ -1,16 +1,21 @@
 // Stand-in for glog's CHECK family (test infrastructure, see ../README.md): a failed check prints the streamed
-// message and aborts; DCHECKs are compiled in.
+// message and throws std::runtime_error, so that a host process embedding oracle/_ref (pytest, bench.py) reports it
+// instead of dying -- unless another exception is already in flight, where it aborts as glog does.  DCHECKs are
+// compiled in.
 #pragma once
 #include <cstdlib>
+#include <exception>
+#include <stdexcept>
 #include <iostream>
 #include <sstream>
 namespace ref_stub {
 struct check_fail {
   std::ostringstream os;
   check_fail(const char* file, int line, const char* what) { os << file << ":" << line << " check failed: " << what << " "; }
-  [[noreturn]] ~check_fail() {
+  ~check_fail() noexcept(false) {
     std::cerr << os.str() << std::endl;
-    std::abort();
+    if (std::uncaught_exceptions() > 0) std::abort();
+    throw std::runtime_error(os.str());
   }
   template <class T>
   check_fail& operator<<(const T& v) {

@@ -116,7 +116,10 @@ def test_sample_check_against_the_reference_with_a_stand_in_device():
         Bgx = FakeBgx
 
     sub = bench.make_workload("small", 0, None, genome_prefix_reads=4000)
-    dt, n_ent, stage, res = bench.cpu_ref_run(sub, 2, bench.WORKLOADS["small"]["coverage"], keep=True)
+    # as the bench does it: the reference runs in a child process that regenerates the same sample
+    dt, n_ent, stage, res = bench.cpu_ref_run_isolated("small", sub.shape[0], 2, bench.WORKLOADS["small"]["coverage"])
+    same = bench.cpu_ref_run(sub, 2, bench.WORKLOADS["small"]["coverage"], keep=True)[3]
+    assert same["corrected"]["seq"] == res["corrected"]["seq"] and np.array_equal(same["seqset"]["prev"], res["seqset"]["prev"])
     par = bench.verify_sample_against_reference(FakeB, 0, sub, res)
     assert par["checked"] and par["members_equal"] and par["mismatches"] == [] and par["entries"] == n_ent > 0
     # a wrong table is reported, not raised

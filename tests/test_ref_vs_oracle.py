@@ -135,6 +135,15 @@ def test_parameter_space(k, min_count, maxc, run, trim):
     compare_pipeline(reads, k, min_count, maxc, run, trim)
 
 
+def test_trim_portion_zero_check_fails_in_the_reference():
+    # --trim-after-portion 0 passes the CLI's range check, but a read without any solid k-mer then reaches
+    # CHECK_GT(next_fwd_read, 0) (correct_reads.cpp:212): the reference dies there (here: the stand-in CHECK throws).
+    # The CUDA path drops such a read, like every read whose corrected length is below the needed one.
+    reads = reads_of(3000, 2000, 100, 0.015, seed=162, n_rate=0.001)
+    with pytest.raises(RuntimeError, match="correct_reads.cpp:212"):
+        R.create(reads, 30, 1, 32, 0, 0.0)
+
+
 def test_reference_refuses_k32_in_correction():
     # the CLI accepts --kmer-size 16..32 (biograph_create.cpp:483) but the kmer_set refuses 32: the product's
     # bgx_create limit of 31 is the reference's effective limit
