@@ -170,7 +170,7 @@ int ref_fast_read_correct(const char* read, int len, const uint64_t* solid, int6
 }
 
 // Stage 1: kmer_counter (probabilistic pass, exact passes), then the solid kmer_set.
-// max_memory_bytes / partitions = 0: count_kmer_options defaults.  Returns 0 on success.
+// counter_max_memory_bytes = 0: the create flow's budget (get_maximum_mem_bytes()).  Returns 0 on success.
 int ref_count_kmers(void* h, const char* bases, const int64_t* offs, int64_t n, int k, int min_count,
                     uint64_t counter_max_memory_bytes, int force_exact_passes, uint64_t genome_bases) {
   auto* r = static_cast<ref_run*>(h);
@@ -180,7 +180,9 @@ int ref_count_kmers(void* h, const char* bases, const int64_t* offs, int64_t n, 
     build_seqset::count_kmer_options opts;
     opts.kmer_size = k;
     opts.min_count = min_count;
-    if (counter_max_memory_bytes) opts.max_memory_bytes = counter_max_memory_bytes;
+    // biograph_create.cpp:546: the counter may use the process's whole memory budget (--max-mem, default 48 GiB or
+    // the machine's RAM); count_kmer_options' own default of 20 MB is for unit tests and means dozens of exact passes
+    opts.max_memory_bytes = counter_max_memory_bytes ? counter_max_memory_bytes : get_maximum_mem_bytes();
     opts.force_exact_passes = force_exact_passes;
     // biograph_create.cpp:549-551 bounds the probabilistic table by 100 x the reference genome's size (--ref);
     // genome_bases = 0: 100 x the bases read, which only makes the table larger (fewer false positives of a filter
@@ -203,6 +205,7 @@ int ref_count_kmers(void* h, const char* bases, const int64_t* offs, int64_t n, 
     lap("prob pass");
     counter.close_prob_pass();
     lap("close_prob_pass");
+    if (timing) fprintf(stderr, "ref_count_kmers: %u exact passes, counter budget %.1f GB\n", counter.exact_passes(), opts.max_memory_bytes / 1e9);
     for (unsigned pass = 0; pass < counter.exact_passes(); ++pass) {
       counter.start_exact_pass(pass);
       blocks(n, r->threads, [&](int64_t a, int64_t b) {
