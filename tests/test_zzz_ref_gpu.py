@@ -77,3 +77,62 @@ def test_parameters_gpu_vs_reference(B, k, min_count, maxc, run, trim):
 def test_larger_sample_gpu_vs_reference(B):
     # 120 k reads of a 600 kb genome at 30x: 1.2 M entries
     compare(B, reads_of(600000, 120000, 150, 0.005, seed=41))
+
+
+def readmap_vs_reference(B, reads, paired):
+    """bgx_build_readmap against the reference's own make_readmap (modules/bio_mapred/make_readmap.cpp compiled into
+    oracle/_ref) over the reference's own seqset of the same reads: every payload member of the readmap file"""
+    from tests.test_ref_readmap import check, varbit_pack64
+    from oracle import oracle as O
+    g = B.Bgx()
+    try:
+        g.add_reads(reads)
+        g.run()
+        cr = g.export_corrected()
+        ss = g.export_seqset()
+        got = g.build_readmap(paired=paired)
+    finally:
+        g.close()
+    kept = cr["kept"].astype(bool)
+    seqs = [cr["seq"][cr["offs"][i]:cr["offs"][i + 1]].decode() for i in range(len(kept))]
+    rec, ro = [], [0]
+    step = 2 if paired else 1
+    for i in range(0, len(seqs), step):   # one record per pair (or read); a dropped mate leaves a one-read record
+        c = [seqs[j] for j in range(i, min(i + step, len(seqs))) if kept[j]]
+        if c:
+            rec += c
+            ro.append(len(rec))
+    with R.Run(8) as r:
+        r.count_kmers(reads, 30, 5)
+        rcr = r.correct(reads)
+        assert rcr["seq"] == cr["seq"] and np.array_equal(rcr["kept"], cr["kept"])
+        rss = r.make_seqset()
+        assert rss["n"] == ss["n"]
+        mem = r.make_readmap(rec, ro, paired)
+    exp = {"read_lengths/elements": O.varbit_pack(got["read_lengths"], int(ss["sizes"].max()))[0],
+           "mate_loop_ptr/elements": varbit_pack64(got["mate_loop_ptr"], got["n_rows"]),
+           "is_forward/packed_data": got["is_forward"]}
+    for name in ("source_to_mid", "dest_to_mid"):
+        for part in ("bits", "subaccum", "accum"):
+            exp[f"read_ids/{name}/{part}"] = got[name][part]
+    check(mem, exp)
+    return got["n_rows"]
+
+
+def _paired_reads(seed):
+    from biograph_b200 import synth
+    genome = synth.random_genome(5000, seed=seed)
+    r2 = synth.simulate_reads(genome, 4000, read_len=100, error_rate=0.004, seed=seed + 1, paired=True, frag_mean=250, frag_sd=20)
+    sim = [bytes(row).decode() for row in r2]
+    rng = np.random.default_rng(seed + 2)
+    reads = list(sim)
+    for _ in range(300):   # same first read with another pair's mate; exact duplicate pairs
+        i, j = int(rng.integers(0, len(sim) // 2)), int(rng.integers(0, len(sim) // 2))
+        reads += [sim[2 * i], sim[2 * j + 1], sim[2 * i], sim[2 * i + 1]]
+    reads += ["ACGT" * 5, sim[0], sim[1], "T" * 35]   # pairs with a read the corrector drops
+    return reads
+
+
+@pytest.mark.parametrize("paired", [False, True])
+def test_readmap_gpu_vs_reference(B, paired):
+    assert readmap_vs_reference(B, _paired_reads(91), paired) > 5000
