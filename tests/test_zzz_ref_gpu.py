@@ -136,3 +136,34 @@ def _paired_reads(seed):
 @pytest.mark.parametrize("paired", [False, True])
 def test_readmap_gpu_vs_reference(B, paired):
     assert readmap_vs_reference(B, _paired_reads(91), paired) > 5000
+
+
+def test_merge_gpu_vs_reference(B):
+    """bgx_merge_seqsets against the reference's own merge classes (seqset_flat, make_mergemap, seqset_mergemap,
+    seqset_merger of oracle/_ref): three seqsets the reference's builder made, merged by both -- every table of the
+    merged seqset (prev bits under the reference's chunk rule, > 100 000 merged entries) and the mergemap bits"""
+    from tests.test_ref_merge import read_sets
+    sets = read_sets(41, 3, 12000, 90000, 60, err=0.05)
+    runs = [R.Run(8) for _ in sets]
+    out = R.Run(8)
+    try:
+        parts = []
+        for r, rd in zip(runs, sets):
+            r.seed(rd)
+            t = r.make_seqset()
+            parts.append({"sizes": t["sizes"], "prev": t["prev"]})
+        want, maps = out.merge_from(runs)
+        assert want["n"] > 100000
+        with B.Bgx() as g:
+            g.merge_seqsets(parts)       # parallel_splits = 0: the reference's g_parallel_splits
+            ss = g.export_seqset()
+            assert ss["n"] == want["n"]
+            for t in ("sizes", "shared", "prev", "fixed"):
+                assert np.array_equal(ss[t], want[t]), t
+            for p in range(len(sets)):
+                mm = g.export_mergemap(p)
+                assert np.array_equal(mm["bits"], maps[p]), f"mergemap {p}"
+                assert mm["n_set"] == len(parts[p]["sizes"])
+    finally:
+        for r in runs + [out]:
+            r.close()
