@@ -116,3 +116,22 @@ def test_pairs_built_unpaired_mode_is_refused():
         run.make_seqset()
         with pytest.raises(RuntimeError, match="Unexpected read pairing"):
             run.make_readmap(reads, list(range(0, len(reads) + 1, 2)), False)
+
+
+def test_paired_readmap_degenerate_pairs():
+    """pairs whose mates are identical, reverse complements of each other, prefixes of each other, given both ways
+    round, and repeated: the canonical orientation (make_readmap.cpp:170-175 compares the SEQUENCES) and the claim order
+    inside runs of identical rows"""
+    rng = np.random.default_rng(123)
+    genome = "".join("ACGT"[i] for i in rng.integers(0, 4, 300))
+    a, b, c = genome[10:50], genome[60:95], genome[100:140]
+    pal = "ACGTACGTTTAAACGTACGT"                      # its own reverse complement
+    assert O.revcomp(pal) == pal
+    pairs = [(a, a), (a, O.revcomp(a)), (O.revcomp(a), a), (a, a[:25]), (a[:25], a), (b, c), (c, b), (b, c), (pal, pal),
+             (pal, a), (a, pal), (O.revcomp(b), O.revcomp(c)), (c, c), (c, O.revcomp(c))] * 3
+    reads = [r for p in pairs for r in p]
+    kept = np.ones(len(reads), dtype=bool)
+    kept[[5, 12, 13, 40]] = False                     # a few dropped mates, one pair dropped entirely
+    ents = sorted(O.entries_closed_form_py([r for r, k in zip(reads, kept) if k]))
+    run_case(reads, kept, ents, True)
+    run_case(reads, kept, ents, False)

@@ -225,3 +225,27 @@ def test_seed_counts_do_not_change_the_seqset():
     o = O.seqset_closed_form(reads)
     for t in ("sizes", "shared", "prev", "fixed"):
         assert np.array_equal(o[t], base[t]), t
+
+
+def adversarial_reads():
+    """k-mers that are their own reverse complement, homopolymer and short-period reads, plus ordinary reads"""
+    rng = np.random.default_rng(77)
+    half = "".join("ACGT"[i] for i in rng.integers(0, 4, 15))
+    pal30 = half + O.revcomp(half)                        # a 30-base reverse-complement palindrome
+    assert O.revcomp(pal30) == pal30
+    flank = lambda n: "".join("ACGT"[i] for i in rng.integers(0, 4, n))  # noqa: E731
+    l, r_ = flank(20), flank(20)
+    reads = []
+    for i in range(12):
+        reads += [l + pal30 + r_, O.revcomp(l + pal30 + r_), pal30, l[5:] + pal30 + r_[:7]]
+    reads += ["A" * 60] * 7 + ["T" * 45] * 6 + ["AC" * 40] * 8 + ["GT" * 33] * 5 + ["ACG" * 25] * 9 + ["AAAAAAAAAC" * 6] * 6
+    return reads + reads_of(2500, 1500, 90, 0.01, seed=78)
+
+
+def test_palindromes_homopolymers_and_tandem_repeats():
+    """k-mers that are their own reverse complement (even k: neither strand is 'the' canonical one -- fwd / rev counts
+    and the flag swap of kmer_count_table.h:54-103 show it), homopolymer and short-period reads (one k-mer counted many
+    times per read, suffixes that are prefixes of each other), all of them through the whole flow"""
+    reads = adversarial_reads()
+    for k, mc in ((30, 5), (16, 4), (24, 3)):
+        compare_pipeline(reads, k, mc, 4, 2, 0.6)

@@ -74,6 +74,13 @@ def test_parameters_gpu_vs_reference(B, k, min_count, maxc, run, trim):
     compare(B, reads_of(5000, 4000, 100, 0.015, seed=200 + k, n_rate=0.001), k, min_count, maxc, run, trim)
 
 
+@pytest.mark.parametrize("k,min_count", [(30, 5), (16, 4)])
+def test_adversarial_reads_gpu_vs_reference(B, k, min_count):
+    # reverse-complement palindromes as k-mers, homopolymers, short-period repeats
+    from tests.test_ref_vs_oracle import adversarial_reads
+    compare(B, adversarial_reads(), k, min_count, 4, 2, 0.6)
+
+
 def test_larger_sample_gpu_vs_reference(B):
     # 120 k reads of a 600 kb genome at 30x: 1.2 M entries
     compare(B, reads_of(600000, 120000, 150, 0.005, seed=41))
