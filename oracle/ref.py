@@ -63,7 +63,7 @@ def lib():
         L.ref_readmap_rows.restype = C.c_int64
         L.ref_readmap_rows.argtypes = [C.c_char_p]
         L.ref_read_readmap_file.argtypes = [C.c_char_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_char_p]
-        L.ref_open_biograph.argtypes = [C.c_char_p, C.c_char_p, C.c_size_t]
+        L.ref_open_biograph.argtypes = [C.c_char_p, C.c_char_p, C.c_char_p, C.c_size_t]
         L.ref_merge.argtypes = [C.c_void_p, C.c_int, C.c_void_p]
         L.ref_fast_migrate.argtypes = [C.c_void_p, C.c_int, C.c_char_p, C.c_char_p]
         L.ref_mergemap.restype = C.c_int64
@@ -272,11 +272,12 @@ class Run:
         return out
 
 
-def open_biograph(path):
+def open_biograph(path, sample=""):
     """a whole .bg directory through the reference's own biograph_dir / seqset / readmap (as its consumers open one):
-    dict of what it sees (ids, entry and row counts, pair statistics)"""
+    dict of what it sees (ids, entry and row counts, pair statistics).  sample: accession id or readmap id when the
+    BioGraph holds more than one."""
     buf = C.create_string_buffer(1 << 14)
-    if lib().ref_open_biograph(os.fsencode(path), buf, len(buf)):
+    if lib().ref_open_biograph(os.fsencode(path), sample.encode(), buf, len(buf)):
         raise RuntimeError("reference: " + lib().ref_last_error().decode())
     out = {}
     for line in buf.value.decode().splitlines():

@@ -455,16 +455,17 @@ int ref_read_readmap_file(const char* path, uint64_t* entry, int32_t* len, uint8
 // Opens a whole BioGraph directory the way the reference's consumers do (biograph_dir(path, READ_BGDIR): directory
 // layout + metadata/bg_info.json; seqset_file(bgdir.seqset()); readmap(seqset, bgdir.find_readmap(""))) -- the readmap
 // constructor CHECKs that readmap.json's seqset_uuid is the seqset's -- and reports what it sees as "key=value" lines.
-int ref_open_biograph(const char* path, char* out, size_t cap) {
+int ref_open_biograph(const char* path, const char* sample /* accession id or readmap id; "" = the only one */, char* out,
+                      size_t cap) {
   return guarded([&] {
     biograph_dir bg(path, READ_BGDIR);
     auto ss = std::make_shared<seqset>(bg.seqset());
-    std::string rm_path = bg.find_readmap("");
+    std::string rm_path = bg.find_readmap(sample ? sample : "");
     readmap rm(ss, rm_path);
     readmap::pair_stats ps = rm.get_pair_stats();
     std::ostringstream os;
     os << "biograph_id=" << bg.biograph_id() << "\naccession_id=" << bg.accession_id() << "\nversion=" << bg.get_metadata().version
-       << "\nsamples=" << bg.samples().size() << "\nsample_accession=" << bg.find_readmap_accession("")
+       << "\nsamples=" << bg.samples().size() << "\nsample_accession=" << bg.find_readmap_accession(sample ? sample : "")
        << "\nreadmap_path=" << rm_path << "\nseqset_uuid=" << ss->uuid() << "\nseqset_entries=" << ss->size()
        << "\nmax_read_len=" << ss->max_read_len() << "\nreadmap_rows=" << rm.size() << "\nreadmap_seqset_uuid="
        << rm.metadata().seqset_uuid << "\nnum_bases=" << rm.get_num_bases() << "\npaired_reads=" << ps.paired_reads

@@ -11,6 +11,7 @@
 // $BGX_MOCK_TABLES/: meta.txt = "num_entries max_entry_len prev_words sub_words acc_words sizes_bits sizes_max
 // shared_bits shared_max"; fixed.bin; prev_bits_<b>.bin, prev_sub_<b>.bin, prev_acc_<b>.bin (b = 0..3);
 // sizes_elements.bin, shared_elements.bin (uint64 words).
+#include <algorithm>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -118,9 +119,72 @@ int bgx_build_readmap(bgx_ctx*, int32_t, uint64_t* n_rows, uint16_t** read_lengt
   return 0;
 }
 // entry points the facade header references elsewhere; none is reached by the writer test
-int bgx_merge_seqsets(bgx_ctx*, const bgx_seqset_part*, uint32_t, uint64_t) { return 1; }
-int bgx_export_mergemap(bgx_ctx*, uint32_t, uint64_t*[3], uint64_t*, uint64_t*) { return 1; }
-int bgx_migrate_bits(bgx_ctx*, uint32_t, const uint64_t*, uint64_t, uint64_t*[3], uint64_t*) { return 1; }
+// ---- bgx-merge: the merged seqset is served like a built one (meta.txt ...); mm_<p>.bin = the mergemap bit words of
+// input p over the merged entries.  The inputs bgx-merge hands over are checked against in_<p>_sizes.bin (uint16), so
+// that the facade's reading of the input .bg files is part of what is tested.  The bitcount index and the readmap
+// migration are computed here from those bits (bitcount.cpp:84-123, make_readmap.cpp:472-486).
+static void bitcount3(const std::vector<uint64_t>& bits, uint64_t nbits, uint64_t* out[3]) {
+  const uint64_t words = (nbits + 63) / 64, nsub = (nbits + 511) / 512, nacc = (nbits + 1 + 511) / 512;
+  uint64_t* b = (uint64_t*)calloc(words + 1, 8);
+  uint64_t* sub = (uint64_t*)calloc(nsub + 1, 8);
+  uint64_t* acc = (uint64_t*)calloc(nacc + 1, 8);
+  memcpy(b, bits.data(), words * 8);
+  uint64_t s = 0, total = 0;
+  for (uint64_t i = 0; i < words; ++i) {
+    if (i % 8 == 0) { acc[i / 8] = total; if (i) sub[i / 8 - 1] = s; s = 0; }
+    const uint64_t c = (uint64_t)__builtin_popcountll(bits[i]);
+    s = (s << 8) | c;
+    total += c;
+  }
+  for (uint64_t left = words % 8; left; left = (left + 1) % 8) s <<= 8;
+  if (nbits) sub[nsub - 1] = s;
+  if (nbits % 512 == 0) acc[nbits / 512] = total;
+  out[0] = b; out[1] = sub; out[2] = acc;
+}
+static bool mergemap_bits(uint32_t part, std::vector<uint64_t>* bits, uint64_t* nbits) {
+  meta_t m;
+  if (!meta(&m)) return false;
+  std::vector<char> raw;
+  if (!slurp("mm_" + std::to_string(part) + ".bin", &raw)) return false;
+  bits->assign((m.n + 63) / 64, 0);
+  memcpy(bits->data(), raw.data(), std::min(raw.size(), bits->size() * 8));
+  *nbits = m.n;
+  return true;
+}
+int bgx_merge_seqsets(bgx_ctx*, const bgx_seqset_part* parts, uint32_t n, uint64_t) {
+  for (uint32_t p = 0; p < n; ++p) {
+    std::vector<char> want;
+    if (!slurp("in_" + std::to_string(p) + "_sizes.bin", &want)) return 1;
+    if (want.size() != parts[p].n_entries * 2 || memcmp(want.data(), parts[p].sizes, want.size()) != 0) {
+      g_err = "mock: input " + std::to_string(p) + " was not read from its .bg as written";
+      return 1;
+    }
+  }
+  return 0;
+}
+int bgx_export_mergemap(bgx_ctx*, uint32_t part, uint64_t* out[3], uint64_t* n_bits, uint64_t* n_set) {
+  std::vector<uint64_t> bits;
+  if (!mergemap_bits(part, &bits, n_bits)) return 1;
+  uint64_t set = 0;
+  for (uint64_t w : bits) set += (uint64_t)__builtin_popcountll(w);
+  *n_set = set;
+  bitcount3(bits, *n_bits, out);
+  return 0;
+}
+int bgx_migrate_bits(bgx_ctx*, uint32_t part, const uint64_t* old_bits, uint64_t n_old, uint64_t* out[3], uint64_t* n_bits) {
+  std::vector<uint64_t> mm;
+  if (!mergemap_bits(part, &mm, n_bits)) return 1;
+  std::vector<uint64_t> bits(mm.size(), 0);
+  uint64_t e = 0;   // the e-th set bit of the mergemap is where old entry e went
+  for (uint64_t x = 0; x < *n_bits; ++x)
+    if ((mm[x >> 6] >> (x & 63)) & 1) {
+      if (e < n_old && ((old_bits[e >> 6] >> (e & 63)) & 1)) bits[x >> 6] |= 1ull << (x & 63);
+      ++e;
+    }
+  if (e != n_old) { g_err = "mock: the mergemap does not cover the input"; return 1; }
+  bitcount3(bits, *n_bits, out);
+  return 0;
+}
 int bgx_export_flat_ascii(bgx_ctx*, uint32_t, uint64_t, uint64_t, char**, uint64_t**) { return 1; }
 int bgx_add_reads_ascii(bgx_ctx*, const char*, const uint64_t*, uint64_t) { return 0; }
 int bgx_add_reads_fastq(bgx_ctx*, const char* text, uint64_t size, uint64_t* n_reads) {

@@ -297,3 +297,65 @@ def test_reference_opens_the_bg_directory_bgx_create_writes(writer, tmp_path, pa
     st = json.load(open(os.path.join(out, "qc", "create_stats.json")))
     assert st["imported_reads"] == len(reads) and st["corrected_reads"] == n_kept and st["corrected_bases"] == int(lens.sum())
     assert st["entries"] == ss["n"] and st["uuid"] == bg["biograph_id"]
+
+
+# ---- a merged .bg directory written by bgx-merge, opened by the reference -----------------------------------------
+def _bgx_create_under_mock(writer, tmp_path, name, reads, paired):
+    d = str(tmp_path / (name + "_served"))
+    os.mkdir(d)
+    ss, cr, t, lens = _serve_create_results(d, reads, paired)
+    fq = tmp_path / (name + ".fastq")
+    fq.write_text("".join(f"@r{i}\n{r}\n+\n{'I' * len(r)}\n" for i, r in enumerate(reads)))
+    out = str(tmp_path / (name + ".bg"))
+    env = dict(os.environ, BGX_MOCK_TABLES=d, LD_LIBRARY_PATH=writer + os.pathsep + os.environ.get("LD_LIBRARY_PATH", ""))
+    cmd = [os.path.join(ROOT, "biograph_b200", "bgx-create"), "--reads", str(fq), "--out", out, "--id", name] + (["--interleaved"] if paired else [])
+    run = subprocess.run(cmd, env=env, capture_output=True, text=True)
+    assert run.returncode == 0, run.stderr[-2000:]
+    seqs = [cr["seq"][cr["offs"][i]:cr["offs"][i + 1]] for i in range(len(lens)) if lens[i]]
+    return out, ss, sorted(e.encode() for e in O.entries_closed_form_py([s.decode() for s in seqs])), t
+
+
+def test_reference_opens_the_bg_directory_bgx_merge_writes(writer, tmp_path):
+    """two BioGraphs (one paired, one not) written by bgx-create, merged by bgx-merge -- host side end to end: the
+    facade reads the input .bg directories (the mock checks what it was handed), writes the merged seqset, migrates
+    both readmaps, writes the two-sample metadata -- with the device results served from the merge oracle; then the
+    reference's biograph_dir + seqset + readmap open the merged directory sample by sample, and every migrated row
+    still points at an entry that starts with its read"""
+    from oracle import merge as M
+    from tests.test_ref_merge import words
+    exe = os.path.join(ROOT, "biograph_b200", "bgx-merge")
+    if not os.path.exists(exe):
+        pytest.fail("bgx-merge is missing: run __graft_entry__.build()")
+    genome_reads = reads_of(6000, 5000, 100, 0.01, seed=95)
+    a_bg, a_ss, a_ents, a_rm = _bgx_create_under_mock(writer, tmp_path, "SAMPLE_A", genome_reads[:2600], True)
+    b_bg, b_ss, b_ents, b_rm = _bgx_create_under_mock(writer, tmp_path, "SAMPLE_B", genome_reads[2000:], False)
+    merged, bits = M.make_mergemap([a_ents, b_ents])
+    assert len(merged) > max(len(a_ents), len(b_ents))          # overlapping, neither contains the other
+    tb = M.merge_tables(merged)
+    d = str(tmp_path / "merge_served")
+    os.mkdir(d)
+    write_tables(d, {"n": tb["n"], "sizes": tb["sizes"], "shared": tb["shared"], "fixed": tb["fixed"],
+                     "prev": np.stack([words(tb["prev"][b]) for b in range(4)])})
+    for p, (ss, mm) in enumerate(((a_ss, bits[0]), (b_ss, bits[1]))):
+        ss["sizes"].astype(np.uint16).tofile(os.path.join(d, f"in_{p}_sizes.bin"))
+        words(mm).tofile(os.path.join(d, f"mm_{p}.bin"))
+    out = str(tmp_path / "family.bg")
+    env = dict(os.environ, BGX_MOCK_TABLES=d, LD_LIBRARY_PATH=writer + os.pathsep + os.environ.get("LD_LIBRARY_PATH", ""))
+    run = subprocess.run([exe, "--in", a_bg, "--in", b_bg, "--out", out], env=env, capture_output=True, text=True)
+    assert run.returncode == 0, run.stderr[-2000:]
+    with R.Run(2) as r:
+        got = r.open_seqset_file(os.path.join(out, "seqset"))
+        assert got["n"] == tb["n"] and np.array_equal(got["sizes"], tb["sizes"]) and np.array_equal(got["shared"], tb["shared"])
+        flat = r.flat()
+    assert flat == merged
+    for name, ents, rm in (("SAMPLE_A", a_ents, a_rm), ("SAMPLE_B", b_ents, b_rm)):
+        bg = R.open_biograph(out, name)                    # readmap(seqset, path) CHECKs the uuid link
+        assert bg["samples"] == 2 and bg["sample_accession"] == name and bg["accession_id"] == "SAMPLE_A+SAMPLE_B"
+        assert bg["biograph_id"] == bg["seqset_uuid"] == bg["readmap_seqset_uuid"]
+        assert bg["seqset_entries"] == len(merged) and bg["readmap_rows"] == rm["n_rows"]
+        rows = R.read_readmap_file(bg["readmap_path"])
+        assert np.array_equal(rows["read_lengths"], rm["read_lengths"].astype(np.int32))
+        assert np.array_equal(rows["mate_loop_ptr"], rm["mate_loop_ptr"]) and np.array_equal(rows["is_forward"], rm["is_forward"])
+        for i in range(len(rows["entry_id"])):
+            ln = int(rows["read_lengths"][i])
+            assert flat[int(rows["entry_id"][i])][:ln] == ents[int(rm["entry_id"][i])][:ln]
