@@ -158,6 +158,7 @@ Args parse(int argc, char** argv) {
 struct LineReader {   // plain or gzip, through zlib
   gzFile f = nullptr;
   std::string name;
+  uint64_t linenum = 0;   // fastq_reader::m_linenum of the record parser reading from here
   explicit LineReader(const std::string& path) : name(path) {
     f = path == "/dev/stdin" ? gzdopen(0, "rb") : gzopen(path.c_str(), "rb");
     if (!f) throw std::runtime_error("Could not open " + path + " for reading");
@@ -175,44 +176,84 @@ struct LineReader {   // plain or gzip, through zlib
   }
 };
 
+// The GPU parser takes well-formed text only: records of exactly four lines, the whole file ending in a newline.
+// Anything else -- a malformed record, blank lines between records (which the reference skips, fastq.cpp:45-58), an
+// unterminated last line -- raises this, and the caller goes on with the host record parser from the first byte that
+// was not handed over yet, which gives the reference's verdict: the same reads, or the same message with the line
+// number counted over the whole file.
+struct NeedHostParser {};
+
 // hands whole FASTQ records (4 lines) to the GPU parser; the tail of a chunk that is not a whole
-// record stays in `carry`
-uint64_t feed_fastq_text(bgx_bs::session& s, std::string& carry, bool last) {
+// record stays in `carry`.  `lines_done` counts the lines that went to the device.
+uint64_t feed_fastq_text(bgx_bs::session& s, std::string& carry, bool last, uint64_t* lines_done) {
   size_t lines = 0, cut = 0;
   for (size_t i = 0; i < carry.size(); ++i)
     if (carry[i] == '\n' && (++lines % 4) == 0) cut = i + 1;
-  if (last && cut < carry.size()) {  // no newline at the end of the file
-    if (carry.back() != '\n') carry.push_back('\n');
-    lines = 0; cut = 0;
-    for (size_t i = 0; i < carry.size(); ++i)
-      if (carry[i] == '\n' && (++lines % 4) == 0) cut = i + 1;
-    if (cut < carry.size()) throw std::runtime_error("Unexpected end of fastq file: incomplete record");
-  }
   uint64_t n = 0;
   if (cut) {
     std::lock_guard<std::mutex> l(s.add_mutex());
-    bgx_bs::detail::ck(bgx_add_reads_fastq(s.ctx(), carry.data(), cut, &n));
+    if (bgx_add_reads_fastq(s.ctx(), carry.data(), cut, &n) != 0) throw NeedHostParser();   // nothing was appended
     carry.erase(0, cut);
+    *lines_done += lines - lines % 4;
   }
+  (void)last;   // what is left at the end of the file is the caller's to hand to the host parser
   return n;
 }
 
-// two files read in step, records interleaved (mates become reads 2i, 2i + 1)
-bool next_record(LineReader& r, std::string& buf, size_t& pos, std::string rec[4]) {
-  for (int l = 0; l < 4; ++l) {
+// One FASTQ record on the host (paired files, filters, the read dump), with fastq_reader::read's rules and messages
+// (modules/bio_format/fastq.cpp:40-126; the importer reads without keeping qualities, read_importer.cpp:633-635):
+// blank lines before a record are skipped, every line is checked, and errors carry the reader's line count.
+//   rec[0] = id line, rec[1] = bases, rec[2] = '+' line, rec[3] = qualities.
+// Lines end at '\n' and lose one trailing '\r' (io.cpp:177-196).  A last line without a newline is handed out without
+// being consumed (io.cpp:215-223), so the reader sees it again as the next record's id line and fails there: the
+// reference cannot import a FASTQ whose last line is unterminated, and neither can this.
+struct FastqLines {
+  LineReader& r;
+  std::string& buf;
+  size_t& pos;
+  uint64_t& linenum;
+  // false: end of input and nothing left
+  bool readline(std::string& line) {
     for (;;) {
       const size_t nl = buf.find('\n', pos);
-      if (nl != std::string::npos) { rec[l].assign(buf, pos, nl - pos); pos = nl + 1; break; }
+      if (nl != std::string::npos) {
+        line.assign(buf, pos, nl - pos);
+        pos = nl + 1;
+        if (!line.empty() && line.back() == '\r') line.pop_back();
+        return true;
+      }
       buf.erase(0, pos);
       pos = 0;
       if (!r.read_chunk(buf, 8 << 20)) {
-        if (l == 0 && buf.empty()) return false;
-        if (l == 3 && !buf.empty()) { rec[l] = buf; buf.clear(); break; }
-        throw std::runtime_error("Unexpected end of fastq file: incomplete record in " + r.name);
+        if (buf.empty()) return false;
+        line = buf;   // unterminated last line: not consumed
+        return true;
       }
     }
-    if (!rec[l].empty() && rec[l].back() == '\r') rec[l].pop_back();
   }
+};
+
+bool next_record(LineReader& r, std::string& buf, size_t& pos, std::string rec[4]) {
+  FastqLines in{r, buf, pos, r.linenum};
+  auto fail = [&](const char* what) { throw std::runtime_error("line " + std::to_string(r.linenum) + ": " + what); };
+  for (;;) {   // until a non-blank line or the end
+    ++r.linenum;
+    if (!in.readline(rec[0])) return false;
+    if (!rec[0].empty()) break;
+  }
+  if (rec[0].size() < 2) fail("Sequence id too short");
+  if (rec[0][0] != '@') fail("Sequence id missing @");
+  if (!in.readline(rec[1])) fail("End of file while reading sequence line");
+  ++r.linenum;
+  if (rec[1].empty()) fail("Expecting sequence, found empty line");
+  if (rec[1].find_first_not_of("ACGTN") != std::string::npos) fail("Sequence contains unexpected characters");
+  if (!in.readline(rec[2])) fail("End of file while reading + line");
+  ++r.linenum;
+  if (rec[2].empty()) fail("Expecting +, found empty line");
+  if (rec[2][0] != '+') fail("Expecting + as first char of line");
+  if (!in.readline(rec[3])) fail("End of file while reading quality line");
+  ++r.linenum;
+  if (rec[3].size() != rec[1].size()) fail("Quality line not same length as sequence");
   return true;
 }
 
@@ -380,7 +421,7 @@ std::pair<unsigned, unsigned> validate_cut_param(const std::string& param, const
 struct ReadSink {
   std::function<void(const std::string&, const std::string&)> pair;
   std::function<void(const std::string&)> single;
-  std::function<uint64_t(std::string& carry, bool last)> text;
+  std::function<uint64_t(std::string& carry, bool last, uint64_t* lines_done)> text;
 };
 
 // the import stage over every --reads / --pair argument (SEQSETMain::run, biograph_create.cpp:575-627); returns
@@ -434,8 +475,26 @@ uint64_t import_inputs(const Args& a, RecordFilter& filt, bool* got_paired, Read
       LineReader r(in_reads);
       std::string carry;
       uint64_t n_file = 0;
-      while (r.read_chunk(carry, 64 << 20)) n_file += sink.text(carry, false);
-      n_file += sink.text(carry, true);
+      try {
+        while (r.read_chunk(carry, 64 << 20)) n_file += sink.text(carry, false, &r.linenum);
+        n_file += sink.text(carry, true, &r.linenum);
+        if (!carry.empty()) throw NeedHostParser();   // a cut-off record, blank lines, an unterminated last line
+      } catch (const NeedHostParser&) {
+        // from here on record by record on the host: `carry` holds everything the device has not taken
+        std::string rec[4], rec2[4];
+        size_t p = 0;
+        if (a.interleaved && n_file % 2) throw std::runtime_error("internal: the device took half a pair");
+        while (next_record(r, carry, p, rec)) {
+          if (a.interleaved) {
+            if (!next_record(r, carry, p, rec2)) throw std::runtime_error("Interleaved fastq " + in_reads + " holds an odd number of reads");
+            sink.pair(rec[1], rec2[1]);
+            n_file += 2;
+          } else {
+            sink.single(rec[1]);
+            ++n_file;
+          }
+        }
+      }
       if (a.interleaved) {
         if (n_file % 2) throw std::runtime_error("Interleaved fastq " + in_reads + " holds an odd number of reads");
         *got_paired = *got_paired || n_file > 0;
@@ -583,10 +642,10 @@ int main(int argc, char** argv) {
         proc.add(x);
         if (got_paired) proc.add(std::string("A")); else ++plain_singles;
       };
-      sink.text = [&](std::string& carry, bool last) {
+      sink.text = [&](std::string& carry, bool last, uint64_t* lines_done) {
         proc.flush_all();   // keep the order of the reads across inputs
         if (a.interleaved && plain_singles) throw std::runtime_error("paired reads after unpaired ones are not supported by bgx-create: put the paired input first");
-        const uint64_t n = feed_fastq_text(sess, carry, last);
+        const uint64_t n = feed_fastq_text(sess, carry, last, lines_done);
         if (!a.interleaved) plain_singles += n;
         return n;
       };

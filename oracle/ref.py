@@ -63,6 +63,8 @@ def lib():
         L.ref_readmap_rows.restype = C.c_int64
         L.ref_readmap_rows.argtypes = [C.c_char_p]
         L.ref_read_readmap_file.argtypes = [C.c_char_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_char_p]
+        L.ref_read_fastq.argtypes = [C.c_char_p, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), C.POINTER(C.c_int64), C.c_char_p,
+                                     C.c_size_t]
         L.ref_open_biograph.argtypes = [C.c_char_p, C.c_char_p, C.c_char_p, C.c_size_t]
         L.ref_merge.argtypes = [C.c_void_p, C.c_int, C.c_void_p]
         L.ref_fast_migrate.argtypes = [C.c_void_p, C.c_int, C.c_char_p, C.c_char_p]
@@ -270,6 +272,20 @@ class Run:
             sz = lib().ref_member_data(self.h, i, C.byref(p))
             out[lib().ref_member_name(self.h, i).decode()] = _view(p, sz, np.uint8).tobytes()
         return out
+
+
+def read_fastq(path):
+    """fastq_reader::read over a file through the reference's own file_reader: (reads accepted before the end or the
+    first error, the io_exception's text or "")"""
+    pb, po, n = C.c_void_p(), C.c_void_p(), C.c_int64()
+    err = C.create_string_buffer(512)
+    if lib().ref_read_fastq(os.fsencode(path), C.byref(pb), C.byref(po), C.byref(n), err, len(err)):
+        raise RuntimeError("reference: " + lib().ref_last_error().decode())
+    offs = _view(po, n.value + 1, np.int64)
+    seq = _view(pb, offs[-1], np.uint8).tobytes().decode()
+    lib().ref_free(pb)
+    lib().ref_free(po)
+    return [seq[offs[i]:offs[i + 1]] for i in range(n.value)], err.value.decode()
 
 
 def open_biograph(path, sample=""):

@@ -49,6 +49,8 @@
 #include "modules/bio_base/readmap.h"
 #include "modules/bio_base/seqset_flat.h"
 #include "modules/bio_base/seqset_merger.h"
+#include "modules/bio_format/fastq.h"
+#include "modules/io/file_io.h"
 #include "modules/bio_mapred/kmer_set.h"
 #include "modules/bio_mapred/make_readmap.h"
 #include "modules/build_seqset/builder.h"
@@ -449,6 +451,35 @@ int ref_read_readmap_file(const char* path, uint64_t* entry, int32_t* len, uint8
     std::string u = rm->metadata().seqset_uuid;
     strncpy(seqset_uuid_out, u.c_str(), 63);
     seqset_uuid_out[63] = 0;
+  });
+}
+
+// fastq_reader::read (modules/bio_format/fastq.cpp:40-126) over a FASTQ file through the reference's file_reader, as
+// read_importer feeds it: the bases of every record it accepts (concatenated, offs[n + 1]) and, where it throws, the
+// exception's text (an empty string = the whole file was accepted).  Buffers come from malloc: ref_free.
+int ref_read_fastq(const char* path, char** bases, int64_t** offs, int64_t* n_reads, char* error, size_t error_cap) {
+  return guarded([&] {
+    std::string all, err;
+    std::vector<int64_t> o{0};
+    try {
+      file_reader fr(path);
+      fastq_reader rd(fr, false /* as read_importer does: qualities are not kept, read_importer.cpp:633-635 */);
+      read_id id;
+      unaligned_read r;
+      while (rd.read(id, r)) {
+        all += r.sequence;
+        o.push_back(int64_t(all.size()));
+      }
+    } catch (const io_exception& e) {
+      err = e.what();
+    }
+    *bases = static_cast<char*>(malloc(all.size() + 1));
+    memcpy(*bases, all.data(), all.size());
+    *offs = static_cast<int64_t*>(malloc(o.size() * sizeof(int64_t)));
+    memcpy(*offs, o.data(), o.size() * sizeof(int64_t));
+    *n_reads = int64_t(o.size()) - 1;
+    strncpy(error, err.c_str(), error_cap - 1);
+    error[error_cap - 1] = 0;
   });
 }
 

@@ -16,6 +16,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <string>
+#include <utility>
 #include <vector>
 
 #include "bgx.h"
@@ -186,11 +187,42 @@ int bgx_migrate_bits(bgx_ctx*, uint32_t part, const uint64_t* old_bits, uint64_t
   return 0;
 }
 int bgx_export_flat_ascii(bgx_ctx*, uint32_t, uint64_t, uint64_t, char**, uint64_t**) { return 1; }
-int bgx_add_reads_ascii(bgx_ctx*, const char*, const uint64_t*, uint64_t) { return 0; }
+// Every read handed over is appended to $BGX_MOCK_LOG (if set): "A <bases>" through bgx_add_reads_ascii, "F <bases>"
+// through the FASTQ text entry point.
+static void log_read(char kind, const char* p, size_t n) {
+  const char* path = getenv("BGX_MOCK_LOG");
+  if (!path) return;
+  FILE* f = fopen(path, "a");
+  if (!f) return;
+  fprintf(f, "%c %.*s\n", kind, (int)n, p);
+  fclose(f);
+}
+int bgx_add_reads_ascii(bgx_ctx*, const char* bases, const uint64_t* offs, uint64_t n) {
+  for (uint64_t r = 0; r < n; ++r) log_read('A', bases + offs[r], (size_t)(offs[r + 1] - offs[r]));
+  return 0;
+}
+// The device parser's contract (biograph_b200/csrc/reads.cu: reads_append_fastq, fq_records_kernel): the text ends in
+// a newline; blank lines only after the last record; every record is four lines that pass fastq_reader::read's
+// checks; on any error NOTHING is appended.  No '\r' handling.
 int bgx_add_reads_fastq(bgx_ctx*, const char* text, uint64_t size, uint64_t* n_reads) {
-  uint64_t lines = 0;
-  for (uint64_t i = 0; i < size; ++i) lines += text[i] == '\n';
-  if (n_reads) *n_reads = lines / 4;
+  if (n_reads) *n_reads = 0;
+  if (size == 0) return 0;
+  if (text[size - 1] != '\n') { g_err = "Partial line in fastq file (the text must end with a newline)"; return 1; }
+  std::vector<std::pair<uint64_t, uint64_t>> lines;   // start, length
+  for (uint64_t i = 0, st = 0; i < size; ++i)
+    if (text[i] == '\n') { lines.emplace_back(st, i - st); st = i + 1; }
+  while (!lines.empty() && lines.back().second == 0) lines.pop_back();
+  const uint64_t n = lines.size() / 4;
+  for (uint64_t r = 0; r < n; ++r) {
+    const auto &id = lines[4 * r], &sq = lines[4 * r + 1], &pl = lines[4 * r + 2], &ql = lines[4 * r + 3];
+    bool ok = id.second >= 2 && text[id.first] == '@' && sq.second > 0 && sq.second <= 255 && pl.second > 0 && text[pl.first] == '+' &&
+              ql.second == sq.second;
+    for (uint64_t i = 0; ok && i < sq.second; ++i) ok = strchr("ACGTN", text[sq.first + i]) != nullptr;
+    if (!ok) { g_err = "line " + std::to_string(4 * r + 1) + ": malformed record (mock of the device parser)"; return 1; }
+  }
+  if (lines.size() % 4) { g_err = "End of file inside a record (mock of the device parser)"; return 1; }
+  for (uint64_t r = 0; r < n; ++r) log_read('F', text + lines[4 * r + 1].first, (size_t)lines[4 * r + 1].second);
+  if (n_reads) *n_reads = n;
   return 0;
 }
 int bgx_count_kmers(bgx_ctx*) { return 0; }
