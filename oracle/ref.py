@@ -65,6 +65,7 @@ def lib():
         L.ref_read_readmap_file.argtypes = [C.c_char_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_char_p]
         L.ref_read_fastq.argtypes = [C.c_char_p, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), C.POINTER(C.c_int64), C.c_char_p,
                                      C.c_size_t]
+        L.ref_biograph_dir.argtypes = [C.c_char_p, C.c_char_p, C.c_char_p]
         L.ref_open_biograph.argtypes = [C.c_char_p, C.c_char_p, C.c_char_p, C.c_size_t]
         L.ref_merge.argtypes = [C.c_void_p, C.c_int, C.c_void_p]
         L.ref_fast_migrate.argtypes = [C.c_void_p, C.c_int, C.c_char_p, C.c_char_p]
@@ -272,6 +273,25 @@ class Run:
             sz = lib().ref_member_data(self.h, i, C.byref(p))
             out[lib().ref_member_name(self.h, i).decode()] = _view(p, sz, np.uint8).tobytes()
         return out
+
+
+def write_biograph(path, accession_id, reads, rec_offs=None, is_paired=False, threads=2):
+    """A BioGraph directory as the reference writes one, from reads taken as already corrected: biograph_dir creates
+    the layout, the builder's seqset goes to <path>/seqset through spiral_file_create_mmap, make_readmap::do_make to
+    <path>/coverage/<sha1>.readmap, biograph_dir::save_metadata writes metadata/bg_info.json.  Returns the seqset tables."""
+    import hashlib
+    if lib().ref_biograph_dir(os.fsencode(path), accession_id.encode(), b""):
+        raise RuntimeError("reference: " + lib().ref_last_error().decode())
+    with Run(threads) as r:
+        r.seed(reads)
+        tables = r.make_seqset(os.path.join(path, "seqset"))
+        tmp = os.path.join(path, "coverage", "tmp.readmap")
+        r.make_readmap(reads, rec_offs if rec_offs is not None else list(range(len(reads) + 1)), is_paired, keep_path=tmp)
+    sha = hashlib.sha1(open(tmp, "rb").read()).hexdigest()
+    os.rename(tmp, os.path.join(path, "coverage", sha + ".readmap"))
+    if lib().ref_biograph_dir(os.fsencode(path), accession_id.encode(), sha.encode()):
+        raise RuntimeError("reference: " + lib().ref_last_error().decode())
+    return tables
 
 
 def read_fastq(path):

@@ -483,6 +483,23 @@ int ref_read_fastq(const char* path, char** bases, int64_t** offs, int64_t* n_re
   });
 }
 
+// The directory side of `biograph create` (biograph_create.cpp:518, 785-811) through the reference's own biograph_dir:
+// creates <dir>/{metadata,coverage,qc,analysis} (call first), or -- with sample_readmap_id set -- writes
+// metadata/bg_info.json for one sample (biograph_id is taken from <dir>/seqset by save_metadata itself).
+int ref_biograph_dir(const char* dir, const char* accession_id, const char* sample_readmap_id) {
+  return guarded([&] {
+    biograph_dir bg(dir, CREATE_BGDIR);
+    if (sample_readmap_id && *sample_readmap_id) {
+      biograph_metadata m = bg.get_metadata();
+      m.accession_id = accession_id;
+      m.samples[accession_id] = sample_readmap_id;
+      m.command_history.push_back("oracle/_ref");
+      bg.set_metadata(m);
+      bg.save_metadata();
+    }
+  });
+}
+
 // Opens a whole BioGraph directory the way the reference's consumers do (biograph_dir(path, READ_BGDIR): directory
 // layout + metadata/bg_info.json; seqset_file(bgdir.seqset()); readmap(seqset, bgdir.find_readmap(""))) -- the readmap
 // constructor CHECKs that readmap.json's seqset_uuid is the seqset's -- and reports what it sees as "key=value" lines.

@@ -315,8 +315,36 @@ def _bgx_create_under_mock(writer, tmp_path, name, reads, paired):
     return out, ss, sorted(e.encode() for e in O.entries_closed_form_py([s.decode() for s in seqs])), t
 
 
-def test_reference_opens_the_bg_directory_bgx_merge_writes(writer, tmp_path):
-    """two BioGraphs (one paired, one not) written by bgx-create, merged by bgx-merge -- host side end to end: the
+def _reference_written_bg(tmp_path, name, reads, paired):
+    """an input BioGraph as the REFERENCE writes it (biograph_dir, spiral_file_create_mmap, make_readmap, save_metadata)
+    from reads taken as corrected; returns what _bgx_create_under_mock returns"""
+    import bisect
+
+    from oracle import readmap as RM
+    out = str(tmp_path / (name + ".bg"))
+    ro = list(range(0, len(reads) + 1, 2)) if paired else None
+    ss = R.write_biograph(out, name, reads, ro, paired)
+    ents = sorted(e.encode() for e in O.entries_closed_form_py(reads))
+    assert len(ents) == ss["n"]
+    look = [e.decode() for e in ents]
+
+    def lookup(s_):
+        i = bisect.bisect_left(look, s_)
+        assert look[i].startswith(s_)
+        return i
+
+    fwd = np.array([lookup(r) for r in reads])
+    rc = np.array([lookup(O.revcomp(r)) for r in reads])
+    lens = np.array([len(r) for r in reads])
+    kept = np.ones(len(reads), dtype=bool)
+    t = RM.readmap_tables_paired(*RM.pair_records(fwd, rc, lens, kept), len(ents)) if paired else RM.readmap_tables(fwd, rc, lens, len(ents))
+    return out, ss, ents, t
+
+
+@pytest.mark.parametrize("inputs", ["bgx-create", "reference"])
+def test_reference_opens_the_bg_directory_bgx_merge_writes(writer, tmp_path, inputs):
+    """two BioGraphs (one paired, one not) written by bgx-create -- or by the REFERENCE itself: BioGraphs users already
+    have --, merged by bgx-merge -- host side end to end: the
     facade reads the input .bg directories (the mock checks what it was handed), writes the merged seqset, migrates
     both readmaps, writes the two-sample metadata -- with the device results served from the merge oracle; then the
     reference's biograph_dir + seqset + readmap open the merged directory sample by sample, and every migrated row
@@ -327,8 +355,14 @@ def test_reference_opens_the_bg_directory_bgx_merge_writes(writer, tmp_path):
     if not os.path.exists(exe):
         pytest.fail("bgx-merge is missing: run __graft_entry__.build()")
     genome_reads = reads_of(6000, 5000, 100, 0.01, seed=95)
-    a_bg, a_ss, a_ents, a_rm = _bgx_create_under_mock(writer, tmp_path, "SAMPLE_A", genome_reads[:2600], True)
-    b_bg, b_ss, b_ents, b_rm = _bgx_create_under_mock(writer, tmp_path, "SAMPLE_B", genome_reads[2000:], False)
+    if inputs == "bgx-create":
+        a_bg, a_ss, a_ents, a_rm = _bgx_create_under_mock(writer, tmp_path, "SAMPLE_A", genome_reads[:2600], True)
+        b_bg, b_ss, b_ents, b_rm = _bgx_create_under_mock(writer, tmp_path, "SAMPLE_B", genome_reads[2000:], False)
+    else:
+        clean = reads_of(6000, 3000, 100, 0.0, seed=96)
+        a_bg, a_ss, a_ents, a_rm = _reference_written_bg(tmp_path, "SAMPLE_A", clean[:1600], True)
+        other = reads_of(5000, 1500, 90, 0.0, seed=97)          # another genome, plus a share of the first one's reads
+        b_bg, b_ss, b_ents, b_rm = _reference_written_bg(tmp_path, "SAMPLE_B", other + clean[1200:1240], False)
     merged, bits = M.make_mergemap([a_ents, b_ents])
     assert len(merged) > max(len(a_ents), len(b_ents))          # overlapping, neither contains the other
     tb = M.merge_tables(merged)
