@@ -545,6 +545,8 @@ int main(int argc, char** argv) {
     // biograph_create.cpp:483-498
     const size_t kmer_size = validate_param("--kmer-size", a.kmer_size, 16, 32);
     const size_t min_kmer_count = validate_param("--min-kmer-count", a.min_kmer_count, 1, 10000000);
+    // the range check lets 32 through, the k-mer counter's constructor does not (bs/kmer_counter.cpp:52-54)
+    if (kmer_size > 31) throw std::runtime_error("A maximum kmer size of 31 is supported for read correction");
     const float min_corrected_reads = validate_float_param("min-reads", a.min_reads, 0.0f, 1.0f);
     const float warn_corrected_reads = validate_float_param("warn-reads", a.warn_reads, 0.0f, 1.0f);
     const float trim_after_portion = validate_float_param("trim-after-portion", a.trim_after_portion, 0.0f, 1.0f);

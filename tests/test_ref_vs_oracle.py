@@ -145,8 +145,8 @@ def test_trim_portion_zero_check_fails_in_the_reference():
 
 
 def test_reference_refuses_k32_in_correction():
-    # the CLI accepts --kmer-size 16..32 (biograph_create.cpp:483) but the kmer_set refuses 32: the product's
-    # bgx_create limit of 31 is the reference's effective limit
+    # the CLI accepts --kmer-size 16..32 (biograph_create.cpp:483) but kmer_counter's constructor refuses 32
+    # (bs/kmer_counter.cpp:52-54): the product's bgx_create limit of 31 is the reference's effective limit
     reads = reads_of(2000, 500, 100, 0.0, seed=3)
     with R.Run(2) as r:
         with pytest.raises(RuntimeError, match="maximum kmer size of 31"):
