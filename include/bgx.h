@@ -69,7 +69,10 @@ int bgx_add_reads_ascii(bgx_ctx* ctx, const char* bases, const uint64_t* offs, u
  * (modules/bio_format/fastq.cpp:40-126: four lines per record, '@' id line, sequence over ACGTN,
  * '+' line, quality line as long as the sequence), then packed like bgx_add_reads_ascii.  The text
  * must hold whole records and end with a newline; blank lines are accepted after the last record
- * only.  *n_reads = records added.  gzip, BAM/CRAM and read names/pairing stay with the importer. */
+ * only; CR LF line ends are not handled.  On any error nothing is appended, so a caller can hand the same
+ * bytes to a record-by-record parser instead (bgx-create does: blank lines between records, CR LF and an
+ * unterminated last line then get fastq_reader's own treatment).  *n_reads = records added.  gzip, BAM/CRAM and
+ * read names/pairing stay with the importer. */
 int bgx_add_reads_fastq(bgx_ctx* ctx, const char* text, uint64_t size, uint64_t* n_reads);
 
 /* Same, for reads already 2-bit packed (T0 of the benchmark clock).
