@@ -185,16 +185,17 @@ struct NeedHostParser {};
 
 // hands whole FASTQ records (4 lines) to the GPU parser; the tail of a chunk that is not a whole
 // record stays in `carry`.  `lines_done` counts the lines that went to the device.
-uint64_t feed_fastq_text(bgx_bs::session& s, std::string& carry, bool last, uint64_t* lines_done) {
+uint64_t feed_fastq_text(bgx_bs::session& s, std::string& carry, bool last, uint64_t* lines_done, unsigned unit_lines) {
+  // unit_lines: 4 = whole records; 8 = whole pairs of an interleaved file, so that the device never holds half a pair
   size_t lines = 0, cut = 0;
   for (size_t i = 0; i < carry.size(); ++i)
-    if (carry[i] == '\n' && (++lines % 4) == 0) cut = i + 1;
+    if (carry[i] == '\n' && (++lines % unit_lines) == 0) cut = i + 1;
   uint64_t n = 0;
   if (cut) {
     std::lock_guard<std::mutex> l(s.add_mutex());
     if (bgx_add_reads_fastq(s.ctx(), carry.data(), cut, &n) != 0) throw NeedHostParser();   // nothing was appended
     carry.erase(0, cut);
-    *lines_done += lines - lines % 4;
+    *lines_done += lines - lines % unit_lines;
   }
   (void)last;   // what is left at the end of the file is the caller's to hand to the host parser
   return n;
@@ -430,6 +431,8 @@ uint64_t import_inputs(const Args& a, RecordFilter& filt, bool* got_paired, Read
   uint64_t read_count = 0;
   auto put_pair = [&](const std::string& x, const std::string& y) { if (filt.keep()) sink.pair(filt.cut(x), filt.cut(y)); };
   auto put_single = [&](const std::string& x) { if (filt.keep()) sink.single(filt.cut(x)); };
+  // read_importer.cpp:688-693: the last read of an interleaved file with an odd number of reads is counted and dropped
+  auto odd_interleaved = [&] { std::cerr << "Warning: interleaved fastq specified, but read an odd number of reads.\n"; };
   for (size_t i = 0; i < a.reads.size(); ++i) {
     std::string in_reads = a.reads[i] == "-" ? "/dev/stdin" : a.reads[i];
     const std::string in_pairs = a.pairs.empty() ? "" : a.pairs[i];
@@ -462,13 +465,25 @@ uint64_t import_inputs(const Args& a, RecordFilter& filt, bool* got_paired, Read
       LineReader r1(in_reads), r2(in_pairs);
       std::string b1, b2, rec1[4], rec2[4];
       size_t p1 = 0, p2 = 0;
+      bool second_done = false;
       for (;;) {
-        const bool h1 = next_record(r1, b1, p1, rec1), h2 = next_record(r2, b2, p2, rec2);
-        if (h1 != h2) throw std::runtime_error("Pair files " + in_reads + " and " + in_pairs + " hold different numbers of reads");
+        // read_importer.cpp:680-725: a record of the first file takes the next record of the second as its mate while
+        // there is one; whatever either file holds beyond the other is imported as unpaired reads
+        const bool h1 = next_record(r1, b1, p1, rec1);
         if (!h1) break;
-        *got_paired = true;
-        put_pair(rec1[1], rec2[1]);
-        read_count += 2;
+        if (!second_done && next_record(r2, b2, p2, rec2)) {
+          *got_paired = true;
+          put_pair(rec1[1], rec2[1]);
+          read_count += 2;
+        } else {
+          second_done = true;
+          put_single(rec1[1]);
+          ++read_count;
+        }
+      }
+      while (!second_done && next_record(r2, b2, p2, rec2)) {   // "in_file2 may contain more unpaired reads"
+        put_single(rec2[1]);
+        ++read_count;
       }
     } else if (sink.text && !filt.active() && (a.interleaved || !*got_paired)) {
       // whole-file chunks go to the GPU parser (split, validate, 2-bit pack on the device)
@@ -483,10 +498,9 @@ uint64_t import_inputs(const Args& a, RecordFilter& filt, bool* got_paired, Read
         // from here on record by record on the host: `carry` holds everything the device has not taken
         std::string rec[4], rec2[4];
         size_t p = 0;
-        if (a.interleaved && n_file % 2) throw std::runtime_error("internal: the device took half a pair");
         while (next_record(r, carry, p, rec)) {
           if (a.interleaved) {
-            if (!next_record(r, carry, p, rec2)) throw std::runtime_error("Interleaved fastq " + in_reads + " holds an odd number of reads");
+            if (!next_record(r, carry, p, rec2)) { odd_interleaved(); ++n_file; break; }
             sink.pair(rec[1], rec2[1]);
             n_file += 2;
           } else {
@@ -495,10 +509,7 @@ uint64_t import_inputs(const Args& a, RecordFilter& filt, bool* got_paired, Read
           }
         }
       }
-      if (a.interleaved) {
-        if (n_file % 2) throw std::runtime_error("Interleaved fastq " + in_reads + " holds an odd number of reads");
-        *got_paired = *got_paired || n_file > 0;
-      }
+      if (a.interleaved) *got_paired = *got_paired || n_file >= 2;
       read_count += n_file;
     } else {
       // one file, record by record on the host (filters, the read dump, or single reads after paired input)
@@ -507,7 +518,7 @@ uint64_t import_inputs(const Args& a, RecordFilter& filt, bool* got_paired, Read
       size_t p = 0;
       while (next_record(r, b, p, rec)) {
         if (a.interleaved) {
-          if (!next_record(r, b, p, rec2)) throw std::runtime_error("Interleaved fastq " + in_reads + " holds an odd number of reads");
+          if (!next_record(r, b, p, rec2)) { odd_interleaved(); ++read_count; break; }
           *got_paired = true;
           put_pair(rec[1], rec2[1]);
           read_count += 2;
@@ -647,7 +658,7 @@ int main(int argc, char** argv) {
       sink.text = [&](std::string& carry, bool last, uint64_t* lines_done) {
         proc.flush_all();   // keep the order of the reads across inputs
         if (a.interleaved && plain_singles) throw std::runtime_error("paired reads after unpaired ones are not supported by bgx-create: put the paired input first");
-        const uint64_t n = feed_fastq_text(sess, carry, last, lines_done);
+        const uint64_t n = feed_fastq_text(sess, carry, last, lines_done, a.interleaved ? 8 : 4);
         if (!a.interleaved) plain_singles += n;
         return n;
       };

@@ -198,3 +198,16 @@ def test_fastq_text_path_interleaved(mock_dir, tmp_path):
     p.write_text(text)
     got, err, kinds = bgx_text_path(mock_dir, p, tmp_path, ["--interleaved"])
     assert err == "" and got == reads and "A" in kinds
+
+
+def test_fastq_text_path_interleaved_odd_and_even(mock_dir, tmp_path):
+    # read_importer.cpp:688-693: the odd last read of an interleaved file is counted and dropped (a warning, no error);
+    # the device takes whole pairs only, the left-over record reaches the host parser, which drops it
+    reads = ["ACGTACGTAC" * 3 + "G" * i for i in range(1, 10)]
+    fq = lambda rs: "".join(f"@p{i}\n{r}\n+\n{'I' * len(r)}\n" for i, r in enumerate(rs))  # noqa: E731
+    (tmp_path / "odd.fastq").write_text(fq(reads))
+    got, err, kinds = bgx_text_path(mock_dir, tmp_path / "odd.fastq", tmp_path, ["--interleaved"])
+    assert err == "" and got == reads[:8] and kinds == {"F"}
+    (tmp_path / "even.fastq").write_text(fq(reads[:8]))
+    got, err, kinds = bgx_text_path(mock_dir, tmp_path / "even.fastq", tmp_path, ["--interleaved"])
+    assert err == "" and got == reads[:8] and kinds == {"F"}
