@@ -646,12 +646,20 @@ int main(int argc, char** argv) {
       bgx_bs::kmer_counter::prob_pass_processor proc(counter);
       uint64_t plain_singles = 0;
       ReadSink sink;
+      // read_importer_state::process (biograph_create.cpp:133-139; --allow-long-reads is refused above)
+      auto check_len = [](const std::string& x) {
+        if (x.size() > 255)
+          throw std::runtime_error(fmt("Encountered read of length %ld, which is larger than the maximum read length %d", (long)x.size(), 255));
+      };
       sink.pair = [&](const std::string& x, const std::string& y) {
+        check_len(x);
+        check_len(y);
         if (plain_singles) throw std::runtime_error("paired reads after unpaired ones are not supported by bgx-create: put the paired input first");
         proc.add(x);
         proc.add(y);
       };
       sink.single = [&](const std::string& x) {
+        check_len(x);
         proc.add(x);
         if (got_paired) proc.add(std::string("A")); else ++plain_singles;
       };

@@ -211,3 +211,17 @@ def test_fastq_text_path_interleaved_odd_and_even(mock_dir, tmp_path):
     (tmp_path / "even.fastq").write_text(fq(reads[:8]))
     got, err, kinds = bgx_text_path(mock_dir, tmp_path / "even.fastq", tmp_path, ["--interleaved"])
     assert err == "" and got == reads[:8] and kinds == {"F"}
+
+
+def test_long_read_message(mock_dir, tmp_path):
+    # read_importer_state::process (biograph_create.cpp:133-139): a read of more than 255 bases is refused with the
+    # reference's words, on the text path (the device parser refuses the chunk, the host parser takes over) and on the
+    # paired path
+    long_read = "ACGT" * 70
+    fq = f"@ok\nACGTACGT\n+\nIIIIIIII\n@long\n{long_read}\n+\n{'I' * len(long_read)}\n"
+    (tmp_path / "l.fastq").write_text(fq)
+    msg = "Encountered read of length 280, which is larger than the maximum read length 255"
+    _, err, _ = bgx_text_path(mock_dir, tmp_path / "l.fastq", tmp_path)
+    assert err == msg
+    _, err, _ = bgx_text_path(mock_dir, tmp_path / "l.fastq", tmp_path, ["--pair", str(tmp_path / "l.fastq")])
+    assert err == msg
