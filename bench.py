@@ -278,17 +278,22 @@ def verify_sample_against_reference(B, device, sub, ref):
         return {"checked": False, "error": f"{type(e).__name__}: {e}"[:300]}
 
 
-def reference_full_workload_digests(workload, parity):
+def reference_full_workload_digests(workload, parity, ranks=1):
     """The reference's own code over the WHOLE workload takes minutes on a CPU, so it was run once in the development
     container (tools/ref_full_workload.py) and its per-member digests committed under profiles/: equal digests = equal
-    bytes.  Returns the comparison for the bench line (None: no committed digests for this workload)."""
+    bytes.  ranks > 1: the concatenated reads of a sharded run's ranks (its parity block holds the digests of the
+    assembled tables under the bare member names).  Returns the comparison for the bench line (None: no committed
+    digests for this workload)."""
     try:
-        rf = os.path.join(ROOT, "profiles", f"r2u_oracle_vs_reference_{workload}.json")
+        rf = os.path.join(ROOT, "profiles", f"r2u_oracle_vs_reference_{workload}" + (f"_x{ranks}" if ranks > 1 else "") + ".json")
         if not os.path.exists(rf) or os.path.getsize(rf) == 0:
             return None
         rj = json.load(open(rf))
         want = rj["sha256_16_reference"]
-        diff = sorted(k_ for k_ in want if parity["sha256_16"].get(k_) != want[k_])
+        have = parity["sha256_16"]
+        if ranks > 1:   # the sharded line digests the seqset members only, without the "seqset/" prefix
+            want = {k_[len("seqset/"):]: v for k_, v in want.items() if k_.startswith("seqset/")}
+        diff = sorted(k_ for k_ in want if have.get(k_) != want[k_])
         return {"against": "oracle/_ref (the reference's own classes) over the whole workload; digests committed in "
                            + os.path.relpath(rf, ROOT), "reads": rj["reads"], "entries": rj["entries"],
                 "digests_compared": len(want), "digests_equal": not diff and rj["entries"] == parity["entries"],
@@ -700,6 +705,10 @@ def main():
                          "(oracle/_ref not built)"}
     elif world > 1 and not args.no_verify:
         parity = verify_against_single_gpu(g, B, dist, rank, world, local, pinned, pinned_mask, pinned_lens, n_reads)
+        if rank == 0 and args.reads is None and isinstance(parity, dict) and "sha256_16" in parity:
+            rfw = reference_full_workload_digests(args.workload, parity, world)
+            if rfw is not None:
+                parity["reference_full_workload"] = rfw
 
     if rank == 0:
         line = {

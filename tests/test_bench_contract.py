@@ -129,24 +129,27 @@ def test_sample_check_against_the_reference_with_a_stand_in_device():
     assert par["checked"] and not par["members_equal"] and par["mismatches"] == ["seqset/shared"]
 
 
-@pytest.mark.parametrize("workload,gpu_line", [("ecoli100x", "r2l_bench_ecoli100x.json"), ("chr20_30x", "r2l_bench_chr20.json")])
-def test_gpu_line_digests_equal_the_reference_over_the_whole_workload(workload, gpu_line):
+@pytest.mark.parametrize("workload,gpu_line,ranks", [("ecoli100x", "r2l_bench_ecoli100x.json", 1), ("chr20_30x", "r2l_bench_chr20.json", 1),
+                                                     ("ecoli100x", "r2k_bench_ecoli100x_2gpu.json", 2)])
+def test_gpu_line_digests_equal_the_reference_over_the_whole_workload(workload, gpu_line, ranks):
     """Two committed records that never met on one machine: the bench line measured on a B200 (its `parity.sha256_16`
     are digests of what the CUDA path produced for the whole workload) and tools/ref_full_workload.py's digests of what
     the reference's OWN classes (oracle/_ref) produce for the same workload on a CPU.  Equal digests = equal bytes."""
     sys.path.insert(0, ROOT)
     import bench
-    ref_file = os.path.join(ROOT, "profiles", f"r2u_oracle_vs_reference_{workload}.json")
+    # ranks = 2: one sharded build on two GPUs over two genomes' reads; its line digests the assembled tables
+    ref_file = os.path.join(ROOT, "profiles", f"r2u_oracle_vs_reference_{workload}" + (f"_x{ranks}" if ranks > 1 else "") + ".json")
     if not os.path.exists(ref_file) or os.path.getsize(ref_file) == 0:
         pytest.skip("no committed reference digests for " + workload)
     rj = json.load(open(ref_file))
     assert rj["equal"] is True and rj["mismatches"] == []          # the oracle port agreed with the reference there
     line = json.loads([l for l in open(os.path.join(ROOT, "profiles", gpu_line)) if l.startswith("{")][-1])
     assert line["config"]["workload"] == workload and line["parity"]["members_equal"] is True
-    got = bench.reference_full_workload_digests(workload, line["parity"])
-    assert got["digests_equal"] is True and got["differing"] == [] and got["digests_compared"] == 18
+    got = bench.reference_full_workload_digests(workload, line["parity"], ranks)
+    assert got["digests_equal"] is True and got["differing"] == [] and got["digests_compared"] == (18 if ranks == 1 else 15)
     assert got["entries"] == line["parity"]["entries"] == rj["entries"]
     # and a changed member is noticed
     bad = json.loads(json.dumps(line["parity"]))
-    bad["sha256_16"]["seqset/prev_G/bits"] = "0" * 16
-    assert bench.reference_full_workload_digests(workload, bad)["differing"] == ["seqset/prev_G/bits"]
+    key = "seqset/prev_G/bits" if ranks == 1 else "prev_G/bits"
+    bad["sha256_16"][key] = "0" * 16
+    assert bench.reference_full_workload_digests(workload, bad, ranks)["differing"] == [key]
